@@ -1,0 +1,113 @@
+"""Deterministic parity cases shared by make_golden.py (which runs the reference on them in the
+build container) and by the tests (which run the oracle / the CUDA path on them anywhere).
+
+Inputs and weights are regenerated from seeds with the CPU torch generator, so only the
+reference's OUTPUTS need to be committed as fixtures.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List
+
+import torch
+
+
+@dataclass(frozen=True)
+class Case:
+    name: str
+    variant: str            # "amp" | "cassie" | "humanoid" | "rma"
+    obs_dim: int            # actor input dim (RMA: obs + latent, fed directly to the actor)
+    hidden: tuple
+    act_dim: int
+    batch: int
+    spike_ts: int = 5
+    pop: int = 10
+    obs_kind: str = "normal"   # "normal" | "stress"
+    seed: int = 0
+    trained: bool = False      # perturb weights away from default init (as after a few Adam steps)
+    full: bool = True          # store full traces / grads (small cases) or summaries (big cases)
+
+    @property
+    def enc_eps(self) -> float:
+        return 1e-5 if self.variant == "humanoid" else 0.0
+
+    @property
+    def dec_tanh(self) -> bool:
+        return self.variant == "cassie"
+
+
+CASES: List[Case] = [
+    Case("tiny_amp", "amp", 6, (32, 24), 3, 16, seed=1),
+    Case("tiny_cassie_tanh", "cassie", 5, (16,), 2, 12, seed=2),
+    Case("tiny_humanoid_eps", "humanoid", 7, (24, 24, 24), 4, 10, seed=3),
+    Case("tiny_rma_T8", "rma", 9, (40, 16), 3, 8, spike_ts=8, seed=4),
+    Case("tiny_stress", "amp", 6, (32, 24), 3, 64, obs_kind="stress", seed=5, trained=True),
+    Case("ragged_b1", "amp", 3, (8,), 1, 1, seed=6),
+    Case("ragged_b131", "cassie", 11, (72, 40), 5, 131, seed=7, trained=True),
+    # BASELINE.json configs[0] dims (C1), batch cut to keep the fixture small
+    Case("c1_dims", "amp", 48, (256, 256), 12, 256, seed=8, full=False),
+    Case("humanoid_dims", "humanoid", 38, (256, 256, 256), 10, 128, seed=9, full=False),
+    Case("amp_actual_dims", "amp", 42, (512, 256, 128), 12, 128, seed=10, full=False, trained=True),
+]
+
+
+def case_by_name(name: str) -> Case:
+    for c in CASES:
+        if c.name == name:
+            return c
+    raise KeyError(name)
+
+
+def _uniform(g: torch.Generator, shape, bound: float) -> torch.Tensor:
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
+
+
+def make_state_dict(c: Case) -> Dict[str, torch.Tensor]:
+    """Actor state dict with the reference's key names and nn.Linear-style
+    U(+-1/sqrt(fan_in)) init, drawn from our own generator (NOT torch's global RNG)."""
+    g = torch.Generator().manual_seed(1000 + c.seed)
+    O, P, A = c.obs_dim, c.pop, c.act_dim
+    sd: Dict[str, torch.Tensor] = {}
+    mean = torch.linspace(-5.0, 5.0, P, dtype=torch.float32).reshape(1, 1, P).repeat(1, O, 1)
+    std = torch.full((1, O, P), math.sqrt(0.15), dtype=torch.float32)
+    if c.trained:
+        mean = mean + _uniform(g, mean.shape, 0.05)
+        std = std + _uniform(g, std.shape, 0.02)
+    sd["actor.encoder.mean"] = mean
+    sd["actor.encoder.std"] = std
+    dims = [O * P] + list(c.hidden) + [A * P]
+    for i in range(len(dims) - 1):
+        k, n = dims[i], dims[i + 1]
+        bound = 1.0 / math.sqrt(k)
+        scale = 1.6 if c.trained else 1.0
+        name = f"actor.snn.hidden_layers.{i}" if i < len(c.hidden) else "actor.snn.out_pop_layer"
+        sd[name + ".weight"] = _uniform(g, (n, k), bound * scale)
+        sd[name + ".bias"] = _uniform(g, (n,), bound * scale)
+    bound = 1.0 / math.sqrt(P)
+    sd["actor.decoder.decoder.weight"] = _uniform(g, (A, 1, P), bound)
+    sd["actor.decoder.decoder.bias"] = _uniform(g, (A,), bound)
+    sd["actor.log_std"] = torch.full((A,), -0.001, dtype=torch.float32)
+    if c.trained:
+        sd["actor.log_std"] = sd["actor.log_std"] + _uniform(g, (A,), 0.1)
+    return sd
+
+
+def make_obs(c: Case) -> torch.Tensor:
+    g = torch.Generator().manual_seed(2000 + c.seed)
+    x = torch.randn(c.batch, c.obs_dim, generator=g, dtype=torch.float32)
+    if c.obs_kind == "stress":
+        # cover the encoder's +-5 receptive range, the env's +-100 clip
+        # (AMP legged_robot_config.py:166) and exact receptive-field centres
+        x = x * 3.0
+        x[0::7] = x[0::7].clamp(-5, 5).round()
+        x[1::7] = 100.0
+        x[2::7] = -100.0
+        x[3::7] = 0.0
+    return x
+
+
+def make_gmu(c: Case) -> torch.Tensor:
+    """Upstream gradient dL/dmu used for the backward fixtures."""
+    g = torch.Generator().manual_seed(3000 + c.seed)
+    return torch.randn(c.batch, c.act_dim, generator=g, dtype=torch.float32)

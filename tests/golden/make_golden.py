@@ -1,0 +1,133 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference modules from /root/reference.
+
+Runs only in the build container (the GPU box has no /root/reference); its outputs
+(tests/golden/*.npz) are committed.  Usage:  python tests/golden/make_golden.py
+
+For every case in cases.py: load the case's seeded state-dict into the reference
+PopSpikeActor of that fork, run forward on the case's observations, record the encoder spikes,
+every LIF layer's (voltage, spike) trace (by wrapping SpikeMLP.neuron_model), mu and std, then
+backpropagate sum(mu * G) and record all parameter gradients and d/d obs.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import io
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from cases import CASES, make_gmu, make_obs, make_state_dict  # noqa: E402
+
+REF = "/root/reference"
+PKG_ROOT = {
+    "amp": f"{REF}/AMP/AMP_for_hardware-main/rsl_rl",
+    "cassie": f"{REF}/CASSIE/rsl_rl-master",
+    "humanoid": f"{REF}/HUMANOID/pbrs-humanoid-dev/gpu_rl",
+    "rma": f"{REF}/RMA/quadruped-robot-master/rl-robotics/rsl_rl",
+}
+
+
+def import_ref(variant: str, sub: str = "modules.actor_critic"):
+    """Import rsl_rl.<sub> from the given fork (never rsl_rl.runners: wandb.init at import)."""
+    for k in [k for k in sys.modules if k == "rsl_rl" or k.startswith("rsl_rl.")]:
+        del sys.modules[k]
+    sys.path.insert(0, PKG_ROOT[variant])
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod = importlib.import_module("rsl_rl." + sub)
+    finally:
+        sys.path.pop(0)
+    return mod
+
+
+def pack_bits(x: torch.Tensor) -> np.ndarray:
+    return np.packbits(x.to(torch.uint8).numpy().reshape(-1))
+
+
+def run_actor_case(c):
+    ac = import_ref(c.variant)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        actor = ac.PopSpikeActor(c.obs_dim, c.act_dim, c.pop, c.pop, list(c.hidden), (-5, 5),
+                                 math.sqrt(0.15), spike_ts=c.spike_ts, device="cpu")
+    sd = {k[len("actor."):]: v for k, v in make_state_dict(c).items()}
+    actor.load_state_dict(sd)
+    L = len(c.hidden) + 1
+    rec = []
+    orig = actor.snn.neuron_model
+
+    def wrapped(syn, pre, cur, volt, spk):
+        out = orig(syn, pre, cur, volt, spk)
+        rec.append((out[1].detach().clone(), out[2].detach().clone()))
+        return out
+
+    actor.snn.neuron_model = wrapped
+    enc_out = {}
+    h = actor.encoder.register_forward_hook(lambda m, i, o: enc_out.__setitem__("s", o.detach().clone()))
+    obs = make_obs(c).requires_grad_(True)
+    G = make_gmu(c)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mu, std = actor(obs)
+    h.remove()
+    (mu * G).sum().backward()
+    T = c.spike_ts
+    volt = [torch.stack([rec[t * L + l][0] for t in range(T)]) for l in range(L)]
+    spk = [torch.stack([rec[t * L + l][1] for t in range(T)]) for l in range(L)]
+    enc = enc_out["s"].permute(2, 0, 1).contiguous()       # [B,K0,T] -> [T,B,K0]
+    out = {"mu": mu.detach().numpy(), "std": std.detach().numpy()}
+    # log_std only feeds the Normal head, so it has no gradient from mu
+    grads = {n: p.grad.detach() for n, p in actor.named_parameters() if p.grad is not None}
+    assert set(n for n, _ in actor.named_parameters()) - set(grads) == {"log_std"}
+    if c.full:
+        out["enc_spikes"] = enc.numpy().astype(np.uint8)
+        for l in range(L):
+            out[f"volt{l}"] = volt[l].numpy()
+            out[f"spk{l}"] = spk[l].numpy().astype(np.uint8)
+        for n, g in grads.items():
+            out["grad." + n] = g.numpy()
+        out["grad.obs"] = obs.grad.numpy()
+    else:
+        out["enc_spikes_bits"] = pack_bits(enc)
+        for l in range(L):
+            out[f"spk{l}_bits"] = pack_bits(spk[l])
+            out[f"volt{l}_absmax"] = np.float32(volt[l].abs().max())
+        for n, g in grads.items():
+            flat = g.reshape(-1)
+            out["gradnorm." + n] = np.float64(flat.double().norm())
+            out["gradsamp." + n] = flat[:: max(1, flat.numel() // 4096)].numpy()
+        out["grad.obs"] = obs.grad.numpy()
+    return out
+
+
+def run_gae_case():
+    """RolloutStorage.compute_returns of the reference on a seeded rollout (CASSIE copy)."""
+    st = import_ref("cassie", "storage.rollout_storage")
+    g = torch.Generator().manual_seed(77)
+    S, N = 24, 37
+    storage = st.RolloutStorage(N, S, [5], [None], [3], device="cpu")
+    storage.rewards.copy_(torch.randn(S, N, 1, generator=g))
+    storage.values.copy_(torch.randn(S, N, 1, generator=g))
+    storage.dones.copy_((torch.rand(S, N, 1, generator=g) < 0.1).to(torch.uint8))
+    last = torch.randn(N, 1, generator=g)
+    storage.compute_returns(last, 0.99, 0.95)
+    return {"returns": storage.returns.numpy(), "advantages": storage.advantages.numpy()}
+
+
+def main():
+    for c in CASES:
+        out = run_actor_case(c)
+        path = os.path.join(HERE, f"actor_{c.name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{c.name:22s} -> {os.path.getsize(path) / 1024:.1f} KiB  mu[0]={out['mu'][0][:3]}")
+    np.savez_compressed(os.path.join(HERE, "gae_cassie.npz"), **run_gae_case())
+    print("gae_cassie done")
+
+
+if __name__ == "__main__":
+    main()
