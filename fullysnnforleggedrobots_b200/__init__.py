@@ -1,0 +1,11 @@
+"""B200-native spiking actor-critic hot path.
+
+Public surface mirrors rsl_rl's for this path only:
+    ActorCritic, PopSpikeActor      modules/actor_critic.py of the four reference forks
+    PPO, RolloutStorage             algorithms/ppo.py, storage/rollout_storage.py
+"""
+from . import _lib  # noqa: F401
+from .actor import PopSpikeActor  # noqa: F401
+from .engine import SnnEngine, gae  # noqa: F401
+
+__all__ = ["PopSpikeActor", "SnnEngine", "gae"]

@@ -1,0 +1,337 @@
+// api.cu — C-ABI entry points declared in include/snn_b200.h.  Host-side launch sequencing only:
+// every buffer is caller-owned, nothing here allocates device memory or synchronises.
+#include <cstdio>
+#include <cstring>
+
+#include "dw_gemm.cuh"
+#include "plan.cuh"
+#include "scan_gemm.cuh"
+#include "simt_kernels.cuh"
+
+using namespace snn;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return fail(SNN_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__));   \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                      \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess) return fail(SNN_ECUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DeviceInfo {
+  int checked = 0;     // 0 = not yet, 1 = ok, -1 = wrong arch
+  int num_sms = 0;
+  int attrs_set = 0;
+};
+DeviceInfo g_dev[64];
+
+int device_ready(int* num_sms) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(SNN_EINVAL, "device index out of range");
+  DeviceInfo& di = g_dev[dev];
+  if (di.checked == 0) {
+    int major = 0, sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    di.num_sms = sms;
+    di.checked = (major == 10) ? 1 : -1;
+  }
+  if (di.checked < 0) return fail(SNN_EARCH, "device is not compute capability 10.x (sm_100a kernels only, no fallback)");
+  if (!di.attrs_set) {
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_FWD>(96))));
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_DX>(96))));
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_DX_ENC>(96))));
+    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kDwSmemBytes)));
+    di.attrs_set = 1;
+  }
+  *num_sms = di.num_sms;
+  return SNN_OK;
+}
+
+int plan_for(const SnnDesc* d, int64_t B, int num_sms, SnnPlan* p) {
+  if (d == nullptr) return fail(SNN_EINVAL, "null descriptor");
+  if (make_plan(*d, B, num_sms, p) != SNN_OK) return fail(SNN_EINVAL, "unsupported SnnDesc (dims, spike_ts 1..16, planes 1..3)");
+  return SNN_OK;
+}
+
+inline uint8_t* at(void* base, size_t off) { return static_cast<uint8_t*>(base) + off; }
+inline const uint8_t* at(const void* base, size_t off) { return static_cast<const uint8_t*>(base) + off; }
+
+int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
+            void* bits_base, void* volt_base /* nullable */, const SnnPlan& p, int num_sms, cudaStream_t st) {
+  if (B == 0) return SNN_OK;
+  uint32_t* enc_bits = reinterpret_cast<uint32_t*>(at(bits_base, p.tr_enc_bits));
+  {
+    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>((p.Bpad + 7) / 8));
+    encode_kernel<<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
+                                       p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+    LAUNCH_CHECK("encode_kernel");
+  }
+  const uint32_t* in_bits = enc_bits;
+  for (int l = 0; l < p.L; ++l) {
+    const LayerPlan& lp = p.layer[l];
+    ScanGemmParams q{};
+    q.a_bits = in_bits;
+    q.b_img = at(packed, lp.w_img);
+    q.b_plane = lp.w_plane;
+    q.b_planes = d->fwd_planes;
+    q.KP = lp.KP; q.NPout = lp.NP; q.NCmax = p.NCmax; q.T = p.T;
+    q.B = static_cast<int>(B); q.Bpad = static_cast<int>(p.Bpad); q.R = p.R;
+    q.nchunks = (lp.NP + p.NCmax - 1) / p.NCmax;
+    q.nitems = static_cast<int>(p.Bpad / 128) * q.nchunks;
+    q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
+    q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
+    q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
+    const int grid = q.nitems < num_sms ? q.nitems : num_sms;
+    scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(p.NCmax), st>>>(q);
+    LAUNCH_CHECK("scan_gemm_kernel<FWD>");
+    in_bits = q.out_bits;
+  }
+  {
+    const int n = static_cast<int>(B) * p.A;
+    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
+                                                   p.T, prm->dec_w, prm->dec_b, d->dec_tanh, mu);
+    LAUNCH_CHECK("decode_kernel");
+  }
+  return SNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* snn_last_error(void) { return g_err; }
+int snn_abi_version(void) { return 1; }
+
+size_t snn_packed_weights_bytes(const SnnDesc* d) {
+  SnnPlan p;
+  if (d == nullptr || make_plan(*d, 1, 148, &p) != SNN_OK) return 0;
+  return p.packed_bytes;
+}
+size_t snn_trace_bytes(const SnnDesc* d, int64_t B) {
+  SnnPlan p;
+  if (d == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return 0;
+  return p.trace_bytes;
+}
+size_t snn_workspace_bytes(const SnnDesc* d, int64_t B, int backward) {
+  SnnPlan p;
+  if (d == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return 0;
+  return backward ? p.ws_bwd_bytes : p.ws_fwd_bytes;
+}
+
+int snn_pack_weights(const SnnDesc* d, const SnnParams* prm, void* packed, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  SnnPlan p;
+  if ((rc = plan_for(d, 1, sms, &p))) return rc;
+  if (prm == nullptr || packed == nullptr) return fail(SNN_EINVAL, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int l = 0; l < p.L; ++l) {
+    const LayerPlan& lp = p.layer[l];
+    if (prm->weight[l] == nullptr || prm->bias[l] == nullptr) return fail(SNN_EINVAL, "null weight/bias pointer");
+    const int total = lp.NP * lp.KP / 8;
+    pack_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP,
+                                                       at(packed, lp.w_img), lp.w_plane, at(packed, lp.wt_img),
+                                                       lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad)));
+    LAUNCH_CHECK("pack_w_kernel");
+  }
+  return SNN_OK;
+}
+
+int snn_fwd_infer(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  SnnPlan p;
+  if ((rc = plan_for(d, B, sms, &p))) return rc;
+  if (!prm || !packed || !obs || !mu || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if (workspace_bytes < p.ws_fwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
+  return forward(d, prm, packed, obs, B, mu, workspace, nullptr, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+int snn_fwd_train(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
+                  void* trace, size_t trace_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  SnnPlan p;
+  if ((rc = plan_for(d, B, sms, &p))) return rc;
+  if (!prm || !packed || !obs || !mu || !trace) return fail(SNN_EINVAL, "null pointer");
+  if (trace_bytes < p.trace_bytes) return fail(SNN_ENOMEM, "trace buffer too small");
+  return forward(d, prm, packed, obs, B, mu, trace, trace, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, const float* mu,
+            const float* g_mu, const void* trace, const SnnGrads* g, void* workspace, size_t workspace_bytes,
+            void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  SnnPlan p;
+  if ((rc = plan_for(d, B, sms, &p))) return rc;
+  if (!prm || !packed || !obs || !mu || !g_mu || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if (workspace_bytes < p.ws_bwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
+  if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
+  float* dbpart = reinterpret_cast<float*>(at(workspace, p.ws_dbpart));
+  float* partial = reinterpret_cast<float*>(at(workspace, p.ws_partial));
+  float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
+  float* g_a = reinterpret_cast<float*>(at(workspace, p.ws_ga));
+  const uint32_t* enc_bits = reinterpret_cast<const uint32_t*>(at(trace, p.tr_enc_bits));
+
+  // ---- output population layer: scan with g_up from the decoder
+  const int top = p.L - 1;
+  {
+    const LayerPlan& lp = p.layer[top];
+    dim3 grd(lp.NP / 128, Bp / 32);
+    top_scan_kernel<<<grd, 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+                                         reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
+                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart);
+    LAUNCH_CHECK("top_scan_kernel");
+    reduce_rows_kernel<<<(lp.N + 127) / 128, 128, 0, st>>>(dbpart, Bp / 32, lp.NP, lp.N, g->bias[top]);
+    LAUNCH_CHECK("reduce_rows_kernel(db top)");
+  }
+  // ---- walk down the layers
+  for (int l = top; l >= 0; --l) {
+    const LayerPlan& lp = p.layer[l];
+    const int slot = (p.L - 1 - l) & 1;
+    const uint8_t* G = at(workspace, p.ws_g[slot]);
+    const size_t Gplane = p.ws_g_plane[slot];
+    {   // dW_l
+      DwGemmParams q{};
+      q.g_img = G; q.g_plane = Gplane;
+      q.x_bits = l == 0 ? enc_bits : reinterpret_cast<const uint32_t*>(at(trace, p.layer[l - 1].tr_bits));
+      q.NP = lp.NP; q.KP = lp.KP; q.R = p.R;
+      q.n_tiles = (lp.KP + 255) / 256;
+      q.rblocks = static_cast<int>(p.R / 64);
+      const int tiles = (lp.NP / 128) * q.n_tiles;
+      int splits = sms / tiles;
+      if (splits < 1) splits = 1;
+      if (splits > q.rblocks) splits = q.rblocks;
+      q.splits = splits;
+      q.partial = partial;
+      dw_gemm_kernel<<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
+      LAUNCH_CHECK("dw_gemm_kernel");
+      dim3 rg((lp.K + 127) / 128, lp.N);
+      reduce_partials_kernel<<<rg, 128, 0, st>>>(partial, splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
+      LAUNCH_CHECK("reduce_partials_kernel");
+    }
+    {   // dX_l + scan of the layer below (or of the encoder)
+      ScanGemmParams q{};
+      q.a_img = G; q.a_plane = Gplane;
+      q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
+      q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = p.NCmax; q.T = p.T;
+      q.B = Bi; q.Bpad = Bp; q.R = p.R;
+      q.nchunks = (lp.KP + p.NCmax - 1) / p.NCmax;
+      q.nitems = (Bp / 128) * q.nchunks;
+      const int grid = q.nitems < sms ? q.nitems : sms;
+      if (l > 0) {
+        const LayerPlan& lo = p.layer[l - 1];
+        q.v_in = reinterpret_cast<const float*>(at(trace, lo.tr_volt));
+        q.g_img = at(workspace, p.ws_g[slot ^ 1]);
+        q.g_plane = p.ws_g_plane[slot ^ 1];
+        q.db_part = dbpart;
+        scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(p.NCmax), st>>>(q);
+        LAUNCH_CHECK("scan_gemm_kernel<DX>");
+        reduce_rows_kernel<<<(lo.N + 127) / 128, 128, 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
+        LAUNCH_CHECK("reduce_rows_kernel(db)");
+      } else {
+        q.g_a = g_a;
+        scan_gemm_kernel<MODE_DX_ENC><<<grid, ScanCfg<MODE_DX_ENC>::THREADS, scan_gemm_smem_bytes<MODE_DX_ENC>(p.NCmax), st>>>(q);
+        LAUNCH_CHECK("scan_gemm_kernel<DX_ENC>");
+      }
+    }
+  }
+  // ---- decoder parameter gradients
+  {
+    const int AP = p.A * p.Pd;
+    if (AP + p.A > 1024) return fail(SNN_EINVAL, "act_dim * de_pop too large for dec_bwd_kernel");
+    const int nblk = (Bi + 127) / 128;
+    const uint32_t* top_bits = reinterpret_cast<const uint32_t*>(at(trace, p.layer[top].tr_bits));
+    dec_bwd_kernel<<<nblk, ((AP + p.A + 31) / 32) * 32, 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
+                                                               p.T, small);
+    LAUNCH_CHECK("dec_bwd_kernel");
+    reduce_rows_kernel<<<(AP + 127) / 128, 128, 0, st>>>(small, nblk, AP + p.A, AP, g->dec_w);
+    reduce_rows_kernel<<<(p.A + 127) / 128, 128, 0, st>>>(small + AP, nblk, AP + p.A, p.A, g->dec_b);
+    LAUNCH_CHECK("reduce_rows_kernel(dec)");
+  }
+  // ---- encoder parameter gradients (+ d obs)
+  {
+    const int nblk = (Bi + 63) / 64;
+    enc_bwd_kernel<<<nblk, 256, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
+    LAUNCH_CHECK("enc_bwd_kernel");
+    reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
+    reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
+    LAUNCH_CHECK("reduce_rows_kernel(enc)");
+    if (g->obs != nullptr) {
+      const int n = Bi * p.O;
+      enc_dobs_kernel<<<(n + 255) / 256, 256, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0P,
+                                                       d->enc_eps, g->obs);
+      LAUNCH_CHECK("enc_dobs_kernel");
+    }
+  }
+  return SNN_OK;
+}
+
+int snn_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, int64_t S,
+            int64_t N, float gamma, float lam, float* returns, float* advantages, int normalize, void* scratch,
+            void* stream) {
+  if (!rewards || !dones || !values || !last_values || !returns || !advantages || !scratch)
+    return fail(SNN_EINVAL, "null pointer");
+  if (S <= 0 || N <= 0) return fail(SNN_EINVAL, "empty rollout");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = static_cast<int>((N + 127) / 128);
+  if (nb > 1024) return fail(SNN_EINVAL, "more than 131072 environments per rank not supported by snn_gae");
+  double* part_sum = static_cast<double*>(scratch);        // [1024]
+  double* part_sq = part_sum + 1024;                       // [256]
+  gae_scan_kernel<<<nb, 128, 0, st>>>(rewards, dones, values, last_values, static_cast<int>(S), static_cast<int>(N), gamma,
+                                      lam, returns, advantages, part_sum);
+  LAUNCH_CHECK("gae_scan_kernel");
+  if (normalize) {
+    const int64_t count = S * N;
+    gae_var_kernel<<<256, 256, 0, st>>>(advantages, count, part_sum, nb, part_sq);
+    gae_norm_kernel<<<256, 256, 0, st>>>(advantages, count, part_sum, nb, part_sq, 256);
+    LAUNCH_CHECK("gae_norm_kernel");
+  }
+  return SNN_OK;
+}
+
+int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out) {
+  SnnPlan p;
+  if (d == nullptr || out == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return fail(SNN_EINVAL, "bad descriptor");
+  // [0]=L [1]=T [2]=Bpad [3]=R [4]=K0P [5]=enc_bits_off then per layer: NP, KP, bits_off, volt_off
+  const int need = 6 + 4 * p.L;
+  if (n_out < need) return fail(SNN_EINVAL, "output array too small");
+  out[0] = p.L; out[1] = p.T; out[2] = p.Bpad; out[3] = p.R; out[4] = p.K0P; out[5] = static_cast<int64_t>(p.tr_enc_bits);
+  for (int l = 0; l < p.L; ++l) {
+    out[6 + 4 * l] = p.layer[l].NP;
+    out[7 + 4 * l] = p.layer[l].KP;
+    out[8 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_bits);
+    out[9 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_volt);
+  }
+  return need;
+}
+
+}  // extern "C"

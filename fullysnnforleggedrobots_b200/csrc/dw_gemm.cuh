@@ -1,0 +1,195 @@
+// dw_gemm.cuh — weight-gradient GEMM  dW[n,k] = sum_r g_c[r,n] * x[r,k]   (r = (t, b) rows)
+// (the "dW += g_c^T x_t" line of SURVEY.md §8a, i.e. what autograd's mm-backward of nn.Linear does
+// for AMP/.../modules/actor_critic.py:228 summed over the T spike steps).
+//
+// The contraction runs over batch rows, so both operands are MN-major for the tensor core:
+//   A = g_c hi/lo bf16 planes, read straight from their swz64 images (rows = r = MMA-K,
+//       cols = n = MMA-M) with 1-D bulk copies,
+//   B = input spikes x (exact in bf16), expanded in shared memory from the bit-packed trace
+//       (rows = r = MMA-K, cols = k = MMA-N).
+// One CTA owns one [128 x <=256] fp32 output tile in TMEM and a contiguous slice of r (split-K over
+// the batch); partial tiles go to a workspace and are summed by reduce_partials_kernel — a fixed
+// order, so gradients are bit-reproducible run to run.
+#pragma once
+#include "plan.cuh"
+#include "umma.cuh"
+
+namespace snn {
+
+struct DwGemmParams {
+  const uint8_t* g_img;    // 2 planes, swz64 image [NP/64][R rows]
+  size_t g_plane;
+  const uint32_t* x_bits;  // [KP/32][R]
+  int NP, KP;
+  int64_t R;
+  int n_tiles;             // ceil(KP / 256)
+  int splits;              // CTAs per output tile
+  int rblocks;             // R / 64
+  float* partial;          // [gridDim.x][128][256]
+};
+
+constexpr int kDwStages = 3;
+constexpr int kDwStageBytes = 65536;   // 32 KiB A (2 planes x 2 n-chunks x 8 KiB) + 32 KiB B (4 k-chunks x 8 KiB)
+constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + 4096 + 256;
+
+__global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint4* lut = reinterpret_cast<uint4*>(ring + kDwStages * kDwStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + 4096);
+  uint64_t* empty = full + kDwStages;
+  uint64_t* acc_full = empty + kDwStages;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
+  const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+  const int kc0 = nt * 4;                                   // first 64-wide k chunk of this tile
+  const int nck = min(4, p.KP / 64 - kc0);                  // k chunks in this tile
+  const int per = (p.rblocks + p.splits - 1) / p.splits;
+  const int rb0 = split * per, rb1 = min(p.rblocks, rb0 + per);
+
+  if (tid == 0) {
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 256);
+  for (int i = tid; i < 256; i += blockDim.x) {
+    uint4 v;
+    v.x = ((i & 1) ? 0x3F80u : 0u) | ((i & 2) ? 0x3F800000u : 0u);
+    v.y = ((i & 4) ? 0x3F80u : 0u) | ((i & 8) ? 0x3F800000u : 0u);
+    v.z = ((i & 16) ? 0x3F80u : 0u) | ((i & 32) ? 0x3F800000u : 0u);
+    v.w = ((i & 64) ? 0x3F80u : 0u) | ((i & 128) ? 0x3F800000u : 0u);
+    lut[i] = v;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t i = 0;
+      for (int rb = rb0; rb < rb1; ++rb, ++i) {
+        const uint32_t s = i % kDwStages;
+        mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], 32768u);
+        uint8_t* dst = ring + s * kDwStageBytes;
+        for (int pl = 0; pl < 2; ++pl)
+          for (int nc = 0; nc < 2; ++nc)
+            bulk_g2s(dst + pl * 16384 + nc * 8192,
+                     p.g_img + pl * p.g_plane + (static_cast<size_t>(mt * 2 + nc) * p.R + static_cast<size_t>(rb) * 64) * 128,
+                     8192u, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), 1, 1);
+      uint32_t i = 0;
+      uint32_t acc = 0;
+      for (int rb = rb0; rb < rb1; ++rb, ++i) {
+        const uint32_t s = i % kDwStages;
+        mbar_wait(&full[s], (i / kDwStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_base = smem_u32(ring + s * kDwStageBytes);
+        const uint32_t b_base = a_base + 32768;
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            umma_bf16(tmem_base, make_smem_desc(a_base + pl * 16384 + k16 * 2048, 8192, 1024),
+                      make_smem_desc(b_base + k16 * 2048, 8192, 1024), idesc, acc);
+            acc = 1u;
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* out = p.partial + (static_cast<size_t>(blockIdx.x) * 128 + row) * 256;
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const bool any = rb1 > rb0;
+    for (int g = 0; g < nck * 4; ++g) {
+      uint32_t x[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 16), x);
+      tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(out + g * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = any ? make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]), __uint_as_float(x[4 * j + 2]),
+                                   __uint_as_float(x[4 * j + 3]))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (warp >= 8) {
+    const int e = tid - 256;
+    const int row = e & 63, half = e >> 6;
+    const int sw = row & 7;
+    uint32_t i = 0;
+    for (int rb = rb0; rb < rb1; ++rb, ++i) {
+      const size_t r = static_cast<size_t>(rb) * 64 + row;
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kcl = half + 2 * u;
+        if (kcl < nck) {
+          w[2 * u] = __ldg(p.x_bits + static_cast<size_t>(2 * (kc0 + kcl)) * p.R + r);
+          w[2 * u + 1] = __ldg(p.x_bits + static_cast<size_t>(2 * (kc0 + kcl) + 1) * p.R + r);
+        } else {
+          w[2 * u] = 0; w[2 * u + 1] = 0;
+        }
+      }
+      const uint32_t s = i % kDwStages;
+      mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
+      uint8_t* bst = ring + s * kDwStageBytes + 32768;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kcl = half + 2 * u;
+        if (kcl < nck) {
+          uint8_t* dst = bst + kcl * 8192 + (row >> 3) * 1024 + sw * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t byte = ((j < 4 ? w[2 * u] : w[2 * u + 1]) >> ((j & 3) * 8)) & 0xFFu;
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dW[n][k] = sum_s partial[(tile * splits + s)][n % 128][k % 256]; also reduces the per-CTA bias partials.
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int n_tiles, int N, int K,
+                                       float* __restrict__ dW) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k >= K || n >= N) return;
+  const int tile = (n >> 7) * n_tiles + (k >> 8);
+  const float* src = partial + (static_cast<size_t>(tile) * splits * 128 + (n & 127)) * 256 + (k & 255);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
+  dW[static_cast<size_t>(n) * K + k] = acc;
+}
+
+__global__ void reduce_db_kernel(const float* __restrict__ part, int nparts, int NP, int N, float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * NP + n];
+  db[n] = acc;
+}
+
+}  // namespace snn

@@ -1,0 +1,143 @@
+// plan.cuh — padded dimensions and byte offsets of every caller-owned buffer.
+//
+// Data layout in HBM:
+//   * "swz64 image" of a bf16 matrix X[R rows][C cols] (R % 8 == 0, C % 64 == 0):
+//       [C/64 column chunks][R/8 row groups][8 rows][128 bytes], the eight 16-byte pieces of a
+//       128-byte row XOR-permuted by (row % 8).  A contiguous run of rows of one column chunk is
+//       exactly a 128B-swizzled tcgen05 operand tile, so it is fetched with ONE 1-D bulk copy and
+//       can be consumed K-major (rows = M/N, cols = K) or MN-major (rows = K, cols = M/N).
+//   * spike bits: uint32 words [C/32][R]; word (c32, r) holds columns 32*c32 .. +31 of row r.
+//   * rows of time-stepped tensors: r = t * Bpad + b, Bpad = roundup(B, 128).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/snn_b200.h"
+
+namespace snn {
+
+constexpr int kTileM = 128;       // batch rows per MMA tile (UMMA_M, cta_group::1)
+constexpr int kChunkK = 64;       // bf16 elements per 128-byte swizzled row
+constexpr int kMaxT = 16;
+
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// byte offset of element (r, c) inside a swz64 image with R rows
+__host__ __device__ inline size_t swz64_offset(int64_t r, int64_t c, int64_t R) {
+  const int64_t chunk = c >> 6, cc = c & 63;
+  return static_cast<size_t>(chunk) * static_cast<size_t>(R) * 128 + static_cast<size_t>(r >> 3) * 1024 +
+         static_cast<size_t>(r & 7) * 128 + static_cast<size_t>(((cc >> 3) ^ (r & 7)) << 4) + (cc & 7) * 2;
+}
+
+struct LayerPlan {
+  int K, N;          // logical fan-in / fan-out
+  int KP, NP;        // padded: KP % 64 == 0, NP % 128 == 0
+  size_t w_img;      // packed: forward operand, 3 planes of swz64 image of W  [NP rows][KP cols]
+  size_t w_plane;    // bytes per plane of w_img
+  size_t wt_img;     // packed: backward operand, 2 planes of swz64 image of W^T [KP rows][NP cols]
+  size_t wt_plane;
+  size_t bias_pad;   // packed: fp32 bias padded to NP
+  size_t tr_bits;    // trace: output spike words [NP/32][R]
+  size_t tr_volt;    // trace: fp32 voltages [T][Bpad][NP]
+};
+
+struct SnnPlan {
+  int L;             // number of LIF layers (hidden + output population)
+  int T;
+  int O, A, Pe, Pd;
+  int K0, K0P;       // encoder neurons, padded
+  int NCmax;         // accumulator columns per timestep in the scan-GEMMs (T * NCmax <= 512)
+  int64_t B, Bpad, R;
+  LayerPlan layer[SNN_MAX_LAYERS];
+  size_t packed_bytes;
+  size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][R]
+  size_t trace_bytes;
+  // backward workspace
+  size_t ws_g[2];           // two ping-pong G image buffers (2 planes each)
+  size_t ws_g_plane[2];
+  size_t ws_ga;             // fp32 [Bpad][K0P]  d loss / d pop_act
+  size_t ws_partial;        // fp32 split-K partials of dW
+  size_t ws_dbpart;         // fp32 per-CTA partial bias grads
+  size_t ws_small;          // scratch for small reductions (decoder / encoder grads)
+  size_t ws_bwd_bytes;
+  size_t ws_fwd_bytes;      // forward-only workspace == a trace without voltages
+  int dw_max_ctas;
+};
+
+// returns 0 or SNN_EINVAL
+inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
+  SnnPlan p{};
+  if (d.obs_dim <= 0 || d.act_dim <= 0 || d.en_pop <= 0 || d.de_pop <= 0) return SNN_EINVAL;
+  if (d.num_hidden < 1 || d.num_hidden + 1 > SNN_MAX_LAYERS) return SNN_EINVAL;
+  if (d.spike_ts < 1 || d.spike_ts > kMaxT) return SNN_EINVAL;
+  if (d.fwd_planes < 1 || d.fwd_planes > 3) return SNN_EINVAL;
+  if (B < 0) return SNN_EINVAL;
+  p.L = d.num_hidden + 1;
+  p.T = d.spike_ts;
+  p.O = d.obs_dim; p.A = d.act_dim; p.Pe = d.en_pop; p.Pd = d.de_pop;
+  p.K0 = d.obs_dim * d.en_pop;
+  p.K0P = static_cast<int>(round_up(p.K0, 64));
+  p.NCmax = p.T <= 5 ? 96 : (p.T <= 8 ? 64 : 32);
+  p.B = B;
+  p.Bpad = round_up(B > 0 ? B : 1, kTileM);
+  p.R = p.Bpad * p.T;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) { size_t o = off; off += round_up(static_cast<int64_t>(bytes), 1024); return o; };
+  int k = p.K0, kp = p.K0P;
+  for (int l = 0; l < p.L; ++l) {
+    LayerPlan& lp = p.layer[l];
+    const int n = l < d.num_hidden ? d.hidden[l] : d.act_dim * d.de_pop;
+    if (n <= 0 || n > 2048) return SNN_EINVAL;
+    lp.K = k; lp.KP = kp; lp.N = n; lp.NP = static_cast<int>(round_up(n, 128));
+    lp.w_plane = static_cast<size_t>(lp.KP / 64) * lp.NP * 128;
+    lp.wt_plane = static_cast<size_t>(lp.NP / 64) * lp.KP * 128;
+    lp.w_img = take(3 * lp.w_plane);
+    lp.wt_img = take(2 * lp.wt_plane);
+    lp.bias_pad = take(static_cast<size_t>(lp.NP) * 4);
+    k = n; kp = lp.NP;
+  }
+  if (p.K0P > 8192) return SNN_EINVAL;
+  p.packed_bytes = off;
+  // trace
+  off = 0;
+  p.tr_enc_bits = take(static_cast<size_t>(p.K0P / 32) * p.R * 4);
+  for (int l = 0; l < p.L; ++l) p.layer[l].tr_bits = take(static_cast<size_t>(p.layer[l].NP / 32) * p.R * 4);
+  p.ws_fwd_bytes = off;
+  for (int l = 0; l < p.L; ++l) p.layer[l].tr_volt = take(static_cast<size_t>(p.R) * p.layer[l].NP * 4);
+  p.trace_bytes = off;
+  // backward workspace
+  off = 0;
+  size_t gmax[2] = {0, 0};
+  for (int l = 0; l < p.L; ++l) {
+    const size_t plane = static_cast<size_t>(p.layer[l].NP / 64) * p.R * 128;
+    const int slot = (p.L - 1 - l) & 1;
+    if (plane > gmax[slot]) gmax[slot] = plane;
+  }
+  for (int s = 0; s < 2; ++s) { p.ws_g_plane[s] = gmax[s]; p.ws_g[s] = take(2 * gmax[s]); }
+  p.ws_ga = take(static_cast<size_t>(p.Bpad) * p.K0P * 4);
+  p.dw_max_ctas = num_sms > 0 ? 2 * num_sms : 296;
+  size_t part = 0;
+  for (int l = 0; l < p.L; ++l) {
+    // worst case: every CTA of the dW launch writes one 128 x 256 fp32 tile
+    const size_t tiles = static_cast<size_t>(p.layer[l].NP / 128) * ((p.layer[l].KP + 255) / 256);
+    const size_t ctas = tiles > static_cast<size_t>(p.dw_max_ctas) ? tiles : static_cast<size_t>(p.dw_max_ctas);
+    const size_t b = ctas * 128 * 256 * 4;
+    if (b > part) part = b;
+  }
+  p.ws_partial = take(part);
+  int npmax = p.K0P;
+  for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
+  size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;
+  const size_t dbp_top = static_cast<size_t>(p.Bpad / 32) * p.layer[p.L - 1].NP;
+  if (dbp_top > dbp) dbp = dbp_top;
+  p.ws_dbpart = take(dbp * 4);
+  size_t small = static_cast<size_t>(p.Bpad / 64) * 2 * p.K0;
+  const size_t small_dec = static_cast<size_t>(p.Bpad / 128) * (p.A * p.Pd + p.A);
+  if (small_dec > small) small = small_dec;
+  p.ws_small = take(small * 4 + 1024);
+  p.ws_bwd_bytes = off;
+  *out = p;
+  return SNN_OK;
+}
+
+}  // namespace snn

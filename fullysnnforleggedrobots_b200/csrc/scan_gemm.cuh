@@ -1,0 +1,396 @@
+// scan_gemm.cuh — the "T-accumulator GEMM + time scan" kernel family (tcgen05 / TMEM / bulk-TMA).
+//
+// One work item = (128 batch rows) x (one chunk of <= NCmax output neurons).  For such an item the
+// kernel keeps T accumulators [128 x NC] fp32 in TMEM (T * NCmax <= 512 columns), one per spike
+// timestep, fills them with tcgen05.mma over the whole contraction dimension, and then the
+// epilogue warps run the sequential-in-time recurrence with all neuron state in registers:
+//
+//   MODE_FWD     A = spikes of the layer below (bit-packed in HBM, expanded to bf16 0/1 tiles in
+//                shared memory), B = bf16 hi/mid/lo planes of W.   Epilogue = LIF update
+//                (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b); v = .75 v (1-s) + c;
+//                s = v > .5.   Emits spike bits (+ fp32 voltage trace when training).
+//   MODE_DX      A = bf16 hi/lo planes of g_c of the layer above, B = hi/lo planes of W^T.
+//                Epilogue = BPTT recurrence of SURVEY.md §8a for the layer below (surrogate
+//                gradient of PseudoSpikeRect, actor_critic.py:154-167).  Emits g_c planes + db.
+//   MODE_DX_ENC  same GEMM into the encoder neurons; epilogue = straight-through encoder
+//                recurrence (actor_critic.py:50-59,116-119): Gamma_t = g_t + 0.001 Gamma_{t+1}.
+//                Emits g_a = sum_t Gamma_t.
+//
+// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner,
+// warps 4-7 = epilogue (TMEM lane quarter = warp % 4), warps 8-11 = spike-bit expanders (FWD only).
+#pragma once
+#include "plan.cuh"
+#include "umma.cuh"
+
+namespace snn {
+
+enum { MODE_FWD = 0, MODE_DX = 1, MODE_DX_ENC = 2 };
+
+struct ScanGemmParams {
+  // A operand
+  const uint32_t* a_bits;   // FWD: [KP/32][R]
+  const uint8_t* a_img;     // DX: 2 planes of swz64 image [KP/64][R rows]
+  size_t a_plane;           // bytes between A planes
+  // B operand: planes of swz64 image [KP/64][NPout rows]
+  const uint8_t* b_img;
+  size_t b_plane;
+  int b_planes;             // FWD: 1..3 ; DX: 2
+  int KP;                   // contraction length (padded, % 64 == 0)
+  int NPout;                // output neurons (padded, % 32 == 0)
+  int NCmax;                // chunk width, % 32 == 0, T * NCmax <= 512
+  int T;
+  int B, Bpad;
+  int64_t R;                // T * Bpad
+  int nitems, nchunks;
+  // FWD
+  const float* bias;        // [NPout]
+  uint32_t* out_bits;       // [NPout/32][R]
+  float* v_out;             // [R][NPout] or null (inference)
+  // DX
+  const float* v_in;        // [R][NPout] voltages of the layer whose gradient is produced
+  uint8_t* g_img;           // 2 planes of swz64 image [NPout/64][R rows]
+  size_t g_plane;
+  float* db_part;           // [gridDim.x][NPout]
+  // DX_ENC
+  float* g_a;               // [Bpad][NPout]
+};
+
+template <int MODE> struct ScanCfg;
+template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, THREADS = 384; };
+template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, THREADS = 256; };
+template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, THREADS = 256; };
+
+constexpr int kScanMaxNP = 8192;   // floats of per-column smem scratch (bias / db)
+
+template <int MODE>
+__host__ __device__ constexpr size_t scan_gemm_smem_bytes(int NCmax) {
+  return 1024 /*align slack*/ + static_cast<size_t>(ScanCfg<MODE>::NA) * ScanCfg<MODE>::A_STAGE +
+         static_cast<size_t>(ScanCfg<MODE>::NB) * 3 * NCmax * 128 + 4096 /*LUT*/ + kScanMaxNP * 4 + 256;
+}
+
+// sum over the 32 lanes of x[j] for every j; lane j returns column j's total
+__device__ __forceinline__ float warp_transpose_reduce32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int h = 16, n = 32; h >= 1; h >>= 1, n >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? x[i] : x[i + n / 2];
+      const float keep = up ? x[i + n / 2] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return x[0];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
+  using C = ScanCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage = 3 * p.NCmax * 128;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + C::NA * C::A_STAGE;
+  uint4* lut = reinterpret_cast<uint4*>(b_ring + C::NB * b_stage);
+  float* s_col = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(lut) + 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + kScanMaxNP);
+  uint64_t* full_a = bars;                 // [NA]
+  uint64_t* empty_a = full_a + C::NA;      // [NA]
+  uint64_t* full_b = empty_a + C::NA;      // [NB]
+  uint64_t* empty_b = full_b + C::NB;      // [NB]
+  uint64_t* acc_full = empty_b + C::NB;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KC = p.KP / 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::NA; ++s) {
+      mbar_init(&full_a[s], MODE == MODE_FWD ? 128 : 1);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  if (MODE == MODE_FWD) {
+    // LUT: byte of 8 spike bits -> eight bf16 {0, 1}
+    for (int i = tid; i < 256; i += blockDim.x) {
+      uint4 v;
+      v.x = ((i & 1) ? 0x3F80u : 0u) | ((i & 2) ? 0x3F800000u : 0u);
+      v.y = ((i & 4) ? 0x3F80u : 0u) | ((i & 8) ? 0x3F800000u : 0u);
+      v.z = ((i & 16) ? 0x3F80u : 0u) | ((i & 32) ? 0x3F800000u : 0u);
+      v.w = ((i & 64) ? 0x3F80u : 0u) | ((i & 128) ? 0x3F800000u : 0u);
+      lut[i] = v;
+    }
+    for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = p.bias[i];
+  } else {
+    for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================================================== producer (one lane)
+    if (lane == 0) {
+      uint32_t ib = 0, ia = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const int m = item / p.nchunks, c = item - m * p.nchunks;
+        const int n0 = c * p.NCmax;
+        const int ncw = min(p.NCmax, p.NPout - n0);
+        for (int kc = 0; kc < KC; ++kc) {
+          const uint32_t sb = ib % C::NB;
+          mbar_wait(&empty_b[sb], ((ib / C::NB) & 1) ^ 1);
+          mbar_expect_tx(&full_b[sb], static_cast<uint32_t>(p.b_planes * ncw * 128));
+          for (int pl = 0; pl < p.b_planes; ++pl)
+            bulk_g2s(b_ring + sb * b_stage + pl * p.NCmax * 128,
+                     p.b_img + pl * p.b_plane + (static_cast<size_t>(kc) * p.NPout + n0) * 128,
+                     static_cast<uint32_t>(ncw * 128), &full_b[sb]);
+          ++ib;
+          if (MODE != MODE_FWD) {
+            for (int t = 0; t < p.T; ++t) {
+              const uint32_t sa = ia % C::NA;
+              mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
+              mbar_expect_tx(&full_a[sa], 32768u);
+              const size_t row0 = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128;
+              for (int pl = 0; pl < 2; ++pl)
+                bulk_g2s(a_ring + sa * C::A_STAGE + pl * 16384,
+                         p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.R + row0) * 128, 16384u,
+                         &full_a[sa]);
+              ++ia;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      uint32_t ib = 0, ia = 0, it = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+        const int c = item % p.nchunks;
+        const int n0 = c * p.NCmax;
+        const int ncw = min(p.NCmax, p.NPout - n0);
+        const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncw), 0, 0);
+        mbar_wait(acc_empty, (it & 1) ^ 1);
+        tc_fence_after_sync();
+        for (int kc = 0; kc < KC; ++kc) {
+          const uint32_t sb = ib % C::NB;
+          mbar_wait(&full_b[sb], (ib / C::NB) & 1);
+          const uint32_t b_base = smem_u32(b_ring + sb * b_stage);
+          for (int t = 0; t < p.T; ++t) {
+            const uint32_t sa = ia % C::NA;
+            mbar_wait(&full_a[sa], (ia / C::NA) & 1);
+            tc_fence_after_sync();
+            const uint32_t a_base = smem_u32(a_ring + sa * C::A_STAGE);
+            const uint32_t d = tmem_base + static_cast<uint32_t>(t * p.NCmax);
+            uint32_t acc = kc > 0 ? 1u : 0u;
+            if (MODE == MODE_FWD) {
+              for (int pl = 0; pl < p.b_planes; ++pl) {
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  umma_bf16(d, make_smem_desc(a_base + k16 * 32, 16, 1024),
+                            make_smem_desc(b_base + pl * p.NCmax * 128 + k16 * 32, 16, 1024), idesc, acc);
+                  acc = 1u;
+                }
+              }
+            } else {
+              // g_c ~ (a_hi + a_lo), W^T ~ (b_hi + b_lo): hi*hi + hi*lo + lo*hi (lo*lo < 2^-16 relative)
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr) {
+                const int pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  umma_bf16(d, make_smem_desc(a_base + pa * 16384 + k16 * 32, 16, 1024),
+                            make_smem_desc(b_base + pb * p.NCmax * 128 + k16 * 32, 16, 1024), idesc, acc);
+                  acc = 1u;
+                }
+              }
+            }
+            umma_commit(&empty_a[sa]);
+            ++ia;
+          }
+          umma_commit(&empty_b[sb]);
+          ++ib;
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue: the time scan
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+      const int m = item / p.nchunks, c = item - m * p.nchunks;
+      const int n0 = c * p.NCmax;
+      const int ncw = min(p.NCmax, p.NPout - n0);
+      const int b = m * 128 + row;
+      const bool valid = b < p.B;
+      mbar_wait(acc_full, it & 1);
+      tc_fence_after_sync();
+      if (MODE == MODE_FWD) {
+        for (int g = 0; g < ncw / 32; ++g) {
+          float cur[32], vol[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
+          uint32_t sprev = 0;
+          const int col0 = n0 + g * 32;
+          for (int t = 0; t < p.T; ++t) {
+            uint32_t x0[16], x1[16];
+            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32), x0);
+            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32 + 16), x1);
+            tmem_ld_wait();
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float syn = __fadd_rn(__uint_as_float(j < 16 ? x0[j] : x1[j - 16]), s_col[col0 + j]);
+              const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
+              const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
+              cur[j] = cj;
+              vol[j] = vj;
+              word |= (vj > 0.5f ? 1u : 0u) << j;
+            }
+            const size_t r = static_cast<size_t>(t) * p.Bpad + b;
+            p.out_bits[static_cast<size_t>(col0 >> 5) * p.R + r] = valid ? word : 0u;
+            if (p.v_out != nullptr && valid) {
+              float4* dst = reinterpret_cast<float4*>(p.v_out + r * p.NPout + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
+            }
+            sprev = word;
+          }
+        }
+      } else if (MODE == MODE_DX) {
+        for (int g = 0; g < ncw / 32; ++g) {
+          float dbacc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col0 = n0 + g * 32 + h * 16;
+            float gvn[16], gcn[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
+            for (int t = p.T - 1; t >= 0; --t) {
+              uint32_t x[16];
+              tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32 + h * 16), x);
+              const size_t r = static_cast<size_t>(t) * p.Bpad + b;
+              float v[16];
+              if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(p.v_in + r * p.NPout + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 f = __ldg(src + j);
+                  v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+              }
+              tmem_ld_wait();
+              float hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float gup = valid ? __uint_as_float(x[j]) : 0.f;
+                const float vj = v[j];
+                const float gs = gup - gvn[j] * (0.75f * vj);
+                const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
+                const float keep = vj > 0.5f ? 0.f : 0.75f;
+                const float gv = gs * win + gvn[j] * keep;
+                const float gc = gv + 0.5f * gcn[j];
+                gvn[j] = gv;
+                gcn[j] = gc;
+                dbacc[h * 16 + j] += gc;
+                hi[j] = bf16_round(gc);
+                lo[j] = gc - hi[j];
+              }
+              const size_t base = static_cast<size_t>(col0 >> 6) * p.R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+              const int p0 = (col0 & 63) >> 3;
+              const int sw = static_cast<int>(r & 7);
+              uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+              uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+              uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+              uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+              *reinterpret_cast<uint4*>(p.g_img + base + ((p0 ^ sw) << 4)) = h0;
+              *reinterpret_cast<uint4*>(p.g_img + base + (((p0 + 1) ^ sw) << 4)) = h1;
+              *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + ((p0 ^ sw) << 4)) = l0;
+              *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + (((p0 + 1) ^ sw) << 4)) = l1;
+            }
+          }
+          const float tot = warp_transpose_reduce32(dbacc, lane);
+          atomicAdd(&s_col[n0 + g * 32 + lane], tot);
+        }
+      } else {   // MODE_DX_ENC
+        for (int g = 0; g < ncw / 16; ++g) {
+          const int col0 = n0 + g * 16;
+          float gam[16], ga[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { gam[j] = 0.f; ga[j] = 0.f; }
+          for (int t = p.T - 1; t >= 0; --t) {
+            uint32_t x[16];
+            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 16), x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              gam[j] = __uint_as_float(x[j]) + 0.001f * gam[j];
+              ga[j] += gam[j];
+            }
+          }
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(p.g_a + static_cast<size_t>(b) * p.NPout + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(ga[4 * j], ga[4 * j + 1], ga[4 * j + 2], ga[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(acc_empty);
+    }
+  } else if (MODE == MODE_FWD && warp >= 8) {
+    // ===================================================== spike-bit expanders
+    const int e = tid - 256;   // row inside the tile
+    uint32_t ia = 0;
+    const int sw = e & 7;
+    uint8_t* const row_base = a_ring + (e >> 3) * 1024 + sw * 128;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int m = item / p.nchunks;
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int t = 0; t < p.T; ++t) {
+          const size_t r = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128 + e;
+          const uint32_t w0 = __ldg(p.a_bits + static_cast<size_t>(2 * kc) * p.R + r);
+          const uint32_t w1 = __ldg(p.a_bits + static_cast<size_t>(2 * kc + 1) * p.R + r);
+          const uint32_t sa = ia % C::NA;
+          mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
+          uint8_t* dst = row_base + sa * C::A_STAGE;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t byte = ((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFFu;
+            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&full_a[sa]);
+          ++ia;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (MODE == MODE_DX) {
+    for (int i = tid; i < p.NPout; i += blockDim.x) p.db_part[static_cast<size_t>(blockIdx.x) * p.NPout + i] = s_col[i];
+  }
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace snn

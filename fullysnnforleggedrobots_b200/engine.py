@@ -1,0 +1,187 @@
+"""SnnEngine — owns the device buffers one PopSpikeActor needs and drives the C-ABI kernels.
+
+Buffers (all torch-allocated, caller-owned from the library's point of view):
+  packed   bf16 hi/mid/lo plane images of every layer's W and W^T (re-packed when parameters change)
+  ws_fwd   bit-packed spike trains of one inference call
+  trace    spike bits + fp32 voltage traces of one training forward (lives until its backward)
+  ws_bwd   g_c plane images, split-K partials, small reduction scratch
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_f32_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the spiking actor has no CPU fallback")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous float32")
+
+
+class SnnEngine:
+    def __init__(self, obs_dim: int, act_dim: int, en_pop: int, de_pop: int, hidden: Sequence[int],
+                 spike_ts: int = 5, dec_tanh: bool = False, enc_eps: float = 0.0, fwd_planes: int = 3):
+        if len(hidden) + 1 > _lib.SNN_MAX_LAYERS:
+            raise ValueError("too many hidden layers")
+        d = _lib.SnnDesc()
+        d.obs_dim, d.act_dim, d.en_pop, d.de_pop = obs_dim, act_dim, en_pop, de_pop
+        d.num_hidden = len(hidden)
+        for i, h in enumerate(hidden):
+            d.hidden[i] = int(h)
+        d.spike_ts = spike_ts
+        d.dec_tanh = 1 if dec_tanh else 0
+        d.enc_eps = float(enc_eps)
+        d.fwd_planes = fwd_planes
+        self.desc = d
+        self.L = len(hidden) + 1
+        self.dims = [obs_dim * en_pop] + [int(h) for h in hidden] + [act_dim * de_pop]
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._ws: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _params_struct(self, enc_mean, enc_std, weights, biases, dec_w, dec_b) -> _lib.SnnParams:
+        p = _lib.SnnParams()
+        p.enc_mean, p.enc_std = enc_mean.data_ptr(), enc_std.data_ptr()
+        for i in range(self.L):
+            p.weight[i] = weights[i].data_ptr()
+            p.bias[i] = biases[i].data_ptr()
+        p.dec_w, p.dec_b = dec_w.data_ptr(), dec_b.data_ptr()
+        return p
+
+    def _buffer(self, kind: str, nbytes: int, device) -> torch.Tensor:
+        key = (kind, str(device))
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1024), dtype=torch.uint8, device=device)
+            self._ws[key] = buf
+        return buf
+
+    def packed_weights(self, weights: List[torch.Tensor], biases: List[torch.Tensor], params_struct) -> torch.Tensor:
+        """bf16 plane images; re-packed only when a weight/bias tensor changed (version counter)."""
+        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases))
+        dev = weights[0].device
+        if self._packed is None or self._packed.device != dev:
+            n = _lib.lib().snn_packed_weights_bytes(C.byref(self.desc))
+            if n == 0:
+                raise RuntimeError("snn_packed_weights_bytes: unsupported network description")
+            self._packed = torch.empty(n, dtype=torch.uint8, device=dev)
+            self._packed_key = None
+        if key != self._packed_key:
+            _lib.check(_lib.lib().snn_pack_weights(C.byref(self.desc), C.byref(params_struct), _ptr(self._packed),
+                                                   _stream_ptr(dev)), "snn_pack_weights")
+            self._packed_key = key
+        return self._packed
+
+    def invalidate(self):
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ calls
+    def forward(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, train: bool):
+        """Returns (mu, trace or None)."""
+        _check_f32_cuda(obs, "obs")
+        for t, n in ((enc_mean, "encoder.mean"), (enc_std, "encoder.std"), (dec_w, "decoder.weight"),
+                     (dec_b, "decoder.bias"), *[(w, "weight") for w in weights], *[(b, "bias") for b in biases]):
+            _check_f32_cuda(t, n)
+        if obs.dim() != 2 or obs.shape[1] != self.desc.obs_dim:
+            raise RuntimeError(f"obs must be [B, {self.desc.obs_dim}], got {tuple(obs.shape)}")
+        dev = obs.device
+        B = obs.shape[0]
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
+            packed = self.packed_weights(weights, biases, ps)
+            mu = torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
+            if B == 0:
+                return mu, None
+            if train:
+                nbytes = L.snn_trace_bytes(C.byref(self.desc), B)
+                trace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.check(L.snn_fwd_train(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
+                                           _ptr(trace), nbytes, None, 0, _stream_ptr(dev)), "snn_fwd_train")
+                return mu, trace
+            nbytes = L.snn_workspace_bytes(C.byref(self.desc), B, 0)
+            ws = self._buffer("fwd", nbytes, dev)
+            _lib.check(L.snn_fwd_infer(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
+                                       _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_fwd_infer")
+            return mu, None
+
+    def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool):
+        dev = obs.device
+        B = obs.shape[0]
+        L = _lib.lib()
+        g_mu = g_mu.contiguous().float()
+        with torch.cuda.device(dev):
+            ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
+            packed = self.packed_weights(weights, biases, ps)
+            g = _lib.SnnGrads()
+            out = {
+                "enc_mean": torch.empty_like(enc_mean), "enc_std": torch.empty_like(enc_std),
+                "weights": [torch.empty_like(w) for w in weights], "biases": [torch.empty_like(b) for b in biases],
+                "dec_w": torch.empty_like(dec_w), "dec_b": torch.empty_like(dec_b),
+                "obs": torch.empty_like(obs) if need_dobs else None,
+            }
+            g.enc_mean, g.enc_std = out["enc_mean"].data_ptr(), out["enc_std"].data_ptr()
+            for i in range(self.L):
+                g.weight[i] = out["weights"][i].data_ptr()
+                g.bias[i] = out["biases"][i].data_ptr()
+            g.dec_w, g.dec_b = out["dec_w"].data_ptr(), out["dec_b"].data_ptr()
+            g.obs = out["obs"].data_ptr() if need_dobs else None
+            nbytes = L.snn_workspace_bytes(C.byref(self.desc), B, 1)
+            ws = self._buffer("bwd", nbytes, dev)
+            _lib.check(L.snn_bwd(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu), _ptr(g_mu),
+                                 _ptr(trace), C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_bwd")
+        return out
+
+    # ------------------------------------------------------------------ test hooks
+    def unpack_trace(self, trace: torch.Tensor, B: int):
+        """Decode a training trace into dense tensors (tests / debugging only; not on the product path)."""
+        arr = (C.c_int64 * (6 + 4 * _lib.SNN_MAX_LAYERS))()
+        n = _lib.check(_lib.lib().snn_debug_trace_layout(C.byref(self.desc), B, arr, len(arr)), "trace layout")
+        Lc, T, Bpad, R, K0P, enc_off = (int(arr[i]) for i in range(6))
+        raw = trace.cpu()
+
+        def bits(off, ncols_p, ncols):
+            words = raw[off: off + (ncols_p // 32) * R * 4].view(torch.int32).reshape(ncols_p // 32, R)
+            sh = torch.arange(32, dtype=torch.int32).reshape(1, 32, 1)
+            b = ((words.unsqueeze(1) >> sh) & 1).reshape(ncols_p, T, Bpad)      # [col, t, b]
+            return b.permute(1, 2, 0)[:, :B, :ncols].to(torch.float32).contiguous()
+
+        res = {"enc_spikes": bits(enc_off, K0P, self.dims[0]), "spikes": [], "volt": []}
+        for l in range(Lc):
+            NP, KP, boff, voff = (int(arr[6 + 4 * l + i]) for i in range(4))
+            res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
+            v = raw[voff: voff + R * NP * 4].view(torch.float32).reshape(T, Bpad, NP)
+            res["volt"].append(v[:, :B, :self.dims[l + 1]].contiguous())
+        return res
+
+
+def gae(rewards, dones, values, last_values, gamma: float, lam: float, normalize: bool = True):
+    """RolloutStorage.compute_returns on [S, N] tensors -> (returns, advantages)."""
+    for t, n in ((rewards, "rewards"), (values, "values"), (last_values, "last_values")):
+        _check_f32_cuda(t, n)
+    if dones.dtype != torch.uint8 or not dones.is_cuda or not dones.is_contiguous():
+        raise RuntimeError("dones must be a contiguous CUDA uint8 tensor")
+    S, N = rewards.shape[0], rewards.shape[1]
+    dev = rewards.device
+    returns = torch.empty_like(rewards)
+    adv = torch.empty_like(rewards)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().snn_gae(_ptr(rewards), _ptr(dones), _ptr(values), _ptr(last_values), S, N,
+                                      float(gamma), float(lam), _ptr(returns), _ptr(adv), 1 if normalize else 0,
+                                      _ptr(scratch), _stream_ptr(dev)), "snn_gae")
+    return returns, adv

@@ -1,0 +1,120 @@
+/*
+ * snn_b200.h — C ABI of the B200 (sm_100a) spiking-actor hot path.
+ *
+ * Drop-in boundary for the population-coded spiking actor of
+ * thisisnotahuman/FullySNNforLeggedRobots.  Every entry point replaces one
+ * PyTorch-level call of the reference; citations are relative to
+ *   AMP/AMP_for_hardware-main/rsl_rl/rsl_rl/modules/actor_critic.py   ("AMP:<line>")
+ *   AMP/AMP_for_hardware-main/rsl_rl/rsl_rl/storage/rollout_storage.py ("STO:<line>")
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - every buffer is allocated and owned by the caller; kernels never allocate
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success, a negative SNN_E* code otherwise; snn_last_error() gives text
+ *   - there is no CPU fallback: SNN_EARCH is returned when the device is not sm_100
+ */
+#ifndef SNN_B200_H
+#define SNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNN_MAX_LAYERS 8      /* hidden layers + output population layer */
+
+enum {
+  SNN_OK = 0,
+  SNN_EINVAL = -1,   /* bad descriptor / null pointer / unsupported size */
+  SNN_EARCH = -2,    /* device is not compute capability 10.x */
+  SNN_ECUDA = -3,    /* a CUDA runtime call or launch failed */
+  SNN_ENOMEM = -4    /* caller-provided workspace / trace too small */
+};
+
+/* Static description of one PopSpikeActor (AMP:274-298).  POD, copied by value. */
+typedef struct SnnDesc {
+  int32_t obs_dim;                 /* O: actor input width (AMP:277)                       */
+  int32_t act_dim;                 /* A: number of actions                                 */
+  int32_t en_pop;                  /* encoder population per obs dim (reference: 10)        */
+  int32_t de_pop;                  /* decoder population per action  (reference: 10)        */
+  int32_t num_hidden;              /* number of hidden LIF layers (AMP:192-214)            */
+  int32_t hidden[SNN_MAX_LAYERS];  /* hidden layer widths                                  */
+  int32_t spike_ts;                /* T: spike timesteps (reference: 5), 1..16             */
+  int32_t dec_tanh;                /* 1: tanh on decoder output (CASSIE copy :147)         */
+  float enc_eps;                   /* added to std^2 in the encoder (HUMANOID copy :107)   */
+  int32_t fwd_planes;              /* bf16 planes per fp32 weight in forward: 3 = lossless
+                                      ("fp32-parity mode"), 2 or 1 = faster, approximate   */
+} SnnDesc;
+
+/* Parameter pointers, fp32, in the reference's own layouts (state-dict tensors as they are). */
+typedef struct SnnParams {
+  const float* enc_mean;                 /* actor.encoder.mean   [1,O,P]  (AMP:85-89)       */
+  const float* enc_std;                  /* actor.encoder.std    [1,O,P]  (AMP:90-92)       */
+  const float* weight[SNN_MAX_LAYERS];   /* hidden_layers.i.weight / out_pop_layer.weight [N,K] */
+  const float* bias[SNN_MAX_LAYERS];     /* same, .bias [N]                                 */
+  const float* dec_w;                    /* actor.decoder.decoder.weight [A,1,P] (AMP:137)  */
+  const float* dec_b;                    /* actor.decoder.decoder.bias   [A]                */
+} SnnParams;
+
+/* Gradient outputs (fp32, same shapes as SnnParams).  All are OVERWRITTEN, not accumulated. */
+typedef struct SnnGrads {
+  float* enc_mean;
+  float* enc_std;
+  float* weight[SNN_MAX_LAYERS];
+  float* bias[SNN_MAX_LAYERS];
+  float* dec_w;
+  float* dec_b;
+  float* obs;                            /* d loss / d obs [B,O]; may be NULL (RMA latent path only) */
+} SnnGrads;
+
+const char* snn_last_error(void);
+int snn_abi_version(void);
+
+/* Sizes of the caller-owned buffers, in bytes.  B = batch rows of the call. */
+size_t snn_packed_weights_bytes(const SnnDesc* d);           /* bf16 plane images of all layers */
+size_t snn_trace_bytes(const SnnDesc* d, int64_t B);         /* spike bits + fp32 voltage traces */
+size_t snn_workspace_bytes(const SnnDesc* d, int64_t B, int backward);
+
+/* Split every fp32 weight matrix into bf16 hi/mid/lo planes laid out as swizzled tensor-core
+ * operand tiles (for W and W^T).  Must be re-run after every optimizer step.
+ * Replaces nothing in the reference: it is the price of feeding nn.Linear weights (AMP:208-214)
+ * to tcgen05 MMAs without losing fp32 mantissa bits. */
+int snn_pack_weights(const SnnDesc* d, const SnnParams* p, void* packed, void* stream);
+
+/* PopSpikeActor.forward under inference_mode (AMP:300-320; called from ActorCritic.act /
+ * act_inference, AMP:410-426): obs [B,O] -> mu [B,A].  No traces are kept. */
+int snn_fwd_infer(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
+                  int64_t B, float* mu, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same forward with the traces BPTT needs (what autograd would save: AMP:154-167, 216-232). */
+int snn_fwd_train(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
+                  int64_t B, float* mu, void* trace, size_t trace_bytes,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Surrogate-gradient BPTT: what loss.backward() does to the reference graph.
+ * g_mu [B,A] is d loss / d mu; mu is the forward output (needed for the tanh variant). */
+int snn_bwd(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
+            int64_t B, const float* mu, const float* g_mu, const void* trace,
+            const SnnGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* RolloutStorage.compute_returns (STO:124-138): reverse GAE scan over S steps and N envs plus
+ * the global advantage normalisation.  rewards/values/returns/advantages are [S,N] fp32,
+ * dones [S,N] uint8, last_values [N].  scratch: >= 16 KiB. */
+int snn_gae(const float* rewards, const uint8_t* dones, const float* values,
+            const float* last_values, int64_t S, int64_t N, float gamma, float lam,
+            float* returns, float* advantages, int normalize, void* scratch, void* stream);
+
+/* Debug / test hooks: unpack internal buffers into plain tensors (tests only). */
+int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out);
+
+/* Device-time of the kernels of the last fwd/bwd call is measured by the caller with CUDA
+ * events on `stream`; the library itself never synchronises. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNN_B200_H */

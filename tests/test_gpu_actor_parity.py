@@ -1,0 +1,105 @@
+"""GPU parity: the sm_100a kernels (through the C-ABI) against the CPU oracle and the committed
+reference fixtures, on the seeded cases of tests/golden/cases.py.
+
+Tolerances (BASELINE.json north_star): spike trains <= 0.1 % mismatch (threshold ties only); mu and
+gradients within 1e-4 relative (to the tensor's max-abs scale) in fp32-parity mode (3 bf16 planes).
+"""
+import math
+
+import pytest
+import torch
+
+from cases import CASES, make_gmu, make_obs, make_state_dict
+from helpers import load_golden, mismatch_rate, oracle_params, rel_err
+from oracle import snn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SPIKE_TOL = 1e-3
+REL_TOL = 1e-4
+
+
+def build_actor(c, device="cuda", **kw):
+    from fullysnnforleggedrobots_b200 import PopSpikeActor
+    actor = PopSpikeActor(c.obs_dim, c.act_dim, c.pop, c.pop, list(c.hidden), (-5, 5), math.sqrt(0.15),
+                          spike_ts=c.spike_ts, enc_eps=c.enc_eps, dec_tanh=c.dec_tanh, **kw)
+    sd = {k[len("actor."):]: v for k, v in make_state_dict(c).items()}
+    actor.load_state_dict(sd)
+    return actor.to(device)
+
+
+def run_train(actor, c):
+    obs = make_obs(c).cuda().requires_grad_(True)
+    mu, std = actor(obs)
+    return obs, mu, std
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c.name)
+def test_forward_infer_matches_oracle(c):
+    actor = build_actor(c)
+    p = oracle_params(c)
+    obs = make_obs(c)
+    mu_ref, std_ref = O.actor_forward(obs, p)
+    with torch.inference_mode():
+        mu, std = actor(obs.cuda())
+    assert mu.shape == mu_ref.shape
+    bad = ((mu.cpu() - mu_ref).abs() > REL_TOL * mu_ref.abs().max()).any(dim=1).float().mean().item()
+    assert bad <= 0.02, f"{bad:.4f} of samples differ in mu"      # a flipped tie moves that sample's mu
+    assert rel_err(std.cpu(), std_ref) < 1e-6
+    g = load_golden(c.name)
+    bad_g = ((mu.cpu() - torch.from_numpy(g["mu"])).abs() > REL_TOL * mu_ref.abs().max()).any(dim=1).float().mean().item()
+    assert bad_g <= 0.02
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c.name)
+def test_train_traces_match_oracle(c):
+    actor = build_actor(c)
+    p = oracle_params(c)
+    obs_cpu = make_obs(c)
+    mu_ref, _, tr_ref = O.actor_forward(obs_cpu, p, want_traces=True)
+    layers = actor.snn.linear_layers()
+    mu, trace = actor.engine.forward(obs_cpu.cuda(), actor.encoder.mean.data, actor.encoder.std.data,
+                                     [l.weight.data for l in layers], [l.bias.data for l in layers],
+                                     actor.decoder.decoder.weight.data, actor.decoder.decoder.bias.data, train=True)
+    tr = actor.engine.unpack_trace(trace, c.batch)
+    assert mismatch_rate(tr["enc_spikes"], tr_ref.enc_spikes) <= SPIKE_TOL
+    for l in range(len(p.weights)):
+        mm = mismatch_rate(tr["spikes"][l], tr_ref.spikes[l])
+        assert mm <= SPIKE_TOL, f"layer {l}: spike mismatch {mm}"
+        same = (tr["spikes"][l] == tr_ref.spikes[l])
+        dv = ((tr["volt"][l] - tr_ref.volt[l]).abs() * same).max().item()
+        assert dv <= 1e-4 * max(1.0, tr_ref.volt[l].abs().max().item()), f"layer {l}: voltage diff {dv}"
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c.name)
+def test_backward_matches_oracle(c):
+    actor = build_actor(c)
+    p = oracle_params(c)
+    obs_cpu = make_obs(c)
+    G = make_gmu(c)
+    mu_ref, _, tr_ref = O.actor_forward(obs_cpu, p, want_traces=True)
+    gr = O.actor_backward(obs_cpu, p, tr_ref, G, need_dobs=True)
+    obs, mu, std = run_train(actor, c)
+    (mu * G.cuda()).sum().backward()
+    L = len(p.weights)
+    layers = actor.snn.linear_layers()
+    # a tie-flipped spike changes the gradient of that sample; tolerate that through a looser bound
+    # only if the forward actually differed.
+    flipped = ((mu.detach().cpu() - mu_ref).abs() > REL_TOL * mu_ref.abs().max()).any().item()
+    tol = 5e-2 if flipped else REL_TOL
+    for l in range(L):
+        assert rel_err(layers[l].weight.grad.cpu(), gr["weights"][l]) < tol, f"dW{l}"
+        assert rel_err(layers[l].bias.grad.cpu(), gr["biases"][l]) < tol, f"db{l}"
+    assert rel_err(actor.decoder.decoder.weight.grad.cpu(), gr["dec_w"]) < tol
+    assert rel_err(actor.decoder.decoder.bias.grad.cpu(), gr["dec_b"]) < tol
+    assert rel_err(actor.encoder.mean.grad.cpu(), gr["enc_mean"]) < tol
+    assert rel_err(actor.encoder.std.grad.cpu(), gr["enc_std"]) < tol
+    assert rel_err(obs.grad.cpu(), gr["obs"]) < tol
+    assert actor.log_std.grad is None
+
+
+def test_cpu_tensor_raises():
+    c = CASES[0]
+    actor = build_actor(c)
+    with pytest.raises(RuntimeError):
+        actor(make_obs(c))     # CPU obs: no fallback
