@@ -56,16 +56,16 @@ struct ScanGemmParams {
 };
 
 template <int MODE> struct ScanCfg;
-template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, THREADS = 384; };
-template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, THREADS = 256; };
-template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, THREADS = 256; };
+template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, THREADS = 384; };
+template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, THREADS = 256; };
+template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, THREADS = 256; };
 
-constexpr int kScanMaxNP = 8192;   // floats of per-column smem scratch (bias / db)
+constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (FWD: bias, DX: db); layer widths <= 2048
 
 template <int MODE>
 __host__ __device__ constexpr size_t scan_gemm_smem_bytes(int NCmax) {
   return 1024 /*align slack*/ + static_cast<size_t>(ScanCfg<MODE>::NA) * ScanCfg<MODE>::A_STAGE +
-         static_cast<size_t>(ScanCfg<MODE>::NB) * 3 * NCmax * 128 + 4096 /*LUT*/ + kScanMaxNP * 4 + 256;
+         static_cast<size_t>(ScanCfg<MODE>::NB) * ScanCfg<MODE>::BP * NCmax * 128 + 4096 /*LUT*/ + kScanMaxNP * 4 + 256;
 }
 
 // sum over the 32 lanes of x[j] for every j; lane j returns column j's total
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   using C = ScanCfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_stage = 3 * p.NCmax * 128;
+  const int b_stage = C::BP * p.NCmax * 128;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + C::NA * C::A_STAGE;
   uint4* lut = reinterpret_cast<uint4*>(b_ring + C::NB * b_stage);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       lut[i] = v;
     }
     for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = p.bias[i];
-  } else {
+  } else if (MODE == MODE_DX) {
     for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = 0.f;
   }
   tc_fence_before_sync();
