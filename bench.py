@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the spiking actor-critic hot path (BASELINE.json configs[1]):
+
+    A1 AMP spiking actor-critic PPO update: 4096 envs x 24-step rollout, surrogate-gradient BPTT.
+
+A "step" is one full PPO `update()` over the rollout (5 epochs x 4 minibatches of 24 576 samples: actor
+forward with traces, critic, PPO losses, BPTT backward, grad-norm clip, Adam; reference
+rsl_rl/algorithms/ppo.py:120-187).  metric = PPO samples/s = envs * steps_per_env * epochs / update time,
+summed over ranks (weak scaling: every rank owns its own 4096 environments, gradients are all-reduced).
+
+  python bench.py --gpus 1 --steps 3 --warmup 3            # our arm
+  python bench.py --impl reference --steps 3 --warmup 3    # CPU arm (oracle port of the reference path)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+WORKLOAD = {
+    "name": "a1_amp_ppo_update_4096x24",
+    "num_envs": 4096, "steps_per_env": 24, "obs_dim": 48, "act_dim": 12,
+    "actor_hidden": [256, 256], "critic_hidden": [256, 256], "spike_ts": 5,
+    "epochs": 5, "mini_batches": 4,
+}
+METRIC = "ppo_samples_per_s_fwd_bptt"
+UNIT = "samples/s"
+CPU_SAMPLE_ROWS = 8192
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops_sustained": p.get("bf16_tflops_sustained", 1400.0), "bf16_tflops": p.get("bf16_tflops", 1590.0),
+                "hbm_gbs": p.get("hbm_gbs", 6650.0), "source": "MEASURED_PEAKS.json"}
+    return {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_minibatch_runner(rows: int, seed: int = 0):
+    """Oracle port of one PPO minibatch step (actor fwd with autograd graph, critic, losses, BPTT, clip, Adam)
+    of the reference on the host cores.  Returns a callable running one step on `rows` samples."""
+    from cases import Case, make_state_dict
+    from oracle import ppo_oracle as P
+    W = WORKLOAD
+    c = Case("bench", "amp", W["obs_dim"], tuple(W["actor_hidden"]), W["act_dim"], 1, spike_ts=W["spike_ts"], seed=seed)
+    sd = make_state_dict(c)
+    g = torch.Generator().manual_seed(seed)
+    dims = [W["obs_dim"]] + W["critic_hidden"] + [1]
+    for i in range(len(dims) - 1):
+        b = 1.0 / math.sqrt(dims[i])
+        sd[f"critic.{2 * i}.weight"] = (torch.rand(dims[i + 1], dims[i], generator=g) * 2 - 1) * b
+        sd[f"critic.{2 * i}.bias"] = (torch.rand(dims[i + 1], generator=g) * 2 - 1) * b
+    sd["std"] = torch.ones(W["act_dim"])
+    ac = P.OracleActorCritic(sd, spike_ts=W["spike_ts"])
+    cfg = P.PPOConfig()
+    opt = torch.optim.Adam(ac.parameters(), lr=cfg.learning_rate)
+    A = W["act_dim"]
+    obs = torch.randn(rows, W["obs_dim"], generator=g)
+    batch = (obs, obs, torch.randn(rows, A, generator=g) * 0.5, torch.randn(rows, 1, generator=g),
+             torch.randn(rows, 1, generator=g), torch.randn(rows, 1, generator=g),
+             -0.5 * A * math.log(2 * math.pi) + torch.randn(rows, 1, generator=g) * 0.1 - 2.0,
+             torch.randn(rows, A, generator=g) * 0.3, torch.ones(rows, A))
+    state = {"lr": cfg.learning_rate}
+
+    def step():
+        _, state["lr"] = P.ppo_minibatch_step(ac, opt, batch, cfg, state["lr"])
+
+    return step
+
+
+def time_cpu(rows: int, steps: int, warmup: int):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_minibatch_runner(rows)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return rows / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    value, dt = time_cpu(CPU_SAMPLE_ROWS, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    sample = (f"one PPO minibatch step (actor fwd+BPTT, critic, losses, clip, Adam) on {CPU_SAMPLE_ROWS} of the "
+              f"24576 minibatch rows per timed step; oracle port of the reference (torch CPU fp32 autograd)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], **{k: v for k, v in WORKLOAD.items() if k != "name"}},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from fullysnnforleggedrobots_b200 import PPO, ActorCritic, _lib
+    from fullysnnforleggedrobots_b200 import dist as snn_dist
+
+    W = WORKLOAD
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the spiking actor has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    reducer = snn_dist.init_from_env("nccl") if world > 1 else None
+
+    torch.manual_seed(0)
+    ac = ActorCritic(W["obs_dim"], W["obs_dim"], W["act_dim"], actor_hidden_dims=W["actor_hidden"],
+                     critic_hidden_dims=W["critic_hidden"], activation="elu", init_noise_std=1.0,
+                     spike_ts=W["spike_ts"])
+    alg = PPO(ac, num_learning_epochs=W["epochs"], num_mini_batches=W["mini_batches"], clip_param=0.2, gamma=0.99,
+              lam=0.95, value_loss_coef=1.0, entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0,
+              use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device=dev, data_parallel=reducer)
+    N, S, O, A = W["num_envs"], W["steps_per_env"], W["obs_dim"], W["act_dim"]
+    alg.init_storage(N, S, [O], [None], [A])
+
+    # ---- synthetic rollout (seeded per rank), produced on the host in pinned memory
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = {
+        "obs": torch.randn(S, N, O, generator=g).pin_memory(),
+        "rewards": torch.randn(S, N, generator=g).pin_memory(),
+        "dones": (torch.rand(S, N, generator=g) < 0.02).to(torch.uint8).pin_memory(),
+        "last_obs": torch.randn(N, O, generator=g).pin_memory(),
+    }
+    with torch.inference_mode():
+        for s in range(S):
+            obs = host["obs"][s].to(dev, non_blocking=True)
+            alg.act(obs, obs)
+            alg.process_env_step(host["rewards"][s].to(dev), host["dones"][s].to(dev), {})
+        alg.compute_returns(host["last_obs"].to(dev))
+    st = alg.storage
+    # host copies of what the rollout phase produced (for the end-to-end leg)
+    for name in ("actions", "values", "actions_log_prob", "mu", "sigma"):
+        host[name] = getattr(st, name).detach().cpu().pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    samples_per_step = N * S * W["epochs"]          # per rank
+
+    # ---- device-resident leg
+    def step_resident():
+        alg.update()
+
+    for _ in range(args.warmup):
+        step_resident()
+    L = _lib.lib()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.snn_profile_enable(1)
+    launches0 = L.snn_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = L.snn_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    import ctypes as C
+    pms, pfl, pln = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int64 * 4)()
+    L.snn_profile_read(pms, pfl, pln)
+    L.snn_profile_enable(0)
+    ms_per_step = ms_total / args.steps
+    value = world * samples_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, loss out, every step
+    h2d_fields = ["obs", "rewards", "dones", "actions", "values", "actions_log_prob", "mu", "sigma", "last_obs"]
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in h2d_fields)
+
+    def step_e2e():
+        st.observations.copy_(host["obs"], non_blocking=True)
+        st.rewards.copy_(host["rewards"].unsqueeze(-1), non_blocking=True)
+        st.dones.copy_(host["dones"].unsqueeze(-1), non_blocking=True)
+        st.actions.copy_(host["actions"], non_blocking=True)
+        st.values.copy_(host["values"], non_blocking=True)
+        st.actions_log_prob.copy_(host["actions_log_prob"], non_blocking=True)
+        st.mu.copy_(host["mu"], non_blocking=True)
+        st.sigma.copy_(host["sigma"], non_blocking=True)
+        last = host["last_obs"].to(dev, non_blocking=True)
+        with torch.inference_mode():
+            alg.compute_returns(last)
+        return alg.update()                      # returns two host floats (device -> host read of the losses)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * samples_per_step / (ms_e2e * 1e-3)
+
+    # ---- forward-only metric (rollout `act`): env-steps/s at B = num_envs
+    obs_dev = host["obs"][0].to(dev)
+
+    def step_act():
+        with torch.inference_mode():
+            ac.act_inference(obs_dev)
+
+    for _ in range(10):
+        step_act()
+    ms_act = timed(step_act, 50) / 50
+    act_value = world * N / (ms_act * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    cats = ["fwd_scan_gemm", "dx_scan_gemm", "dw_gemm", "other_simt"]
+    per_cat = {c: {"ms": pms[i], "launches": int(pln[i]), "algo_tflops": (pfl[i] / (pms[i] * 1e-3) / 1e12) if pms[i] > 0 else 0.0}
+               for i, c in enumerate(cats)}
+    dom = max(range(3), key=lambda i: pms[i])
+    achieved = per_cat[cats[dom]]["algo_tflops"]
+    tc_ms = pms[0] + pms[1] + pms[2]
+    tc_fl = pfl[0] + pfl[1] + pfl[2]
+    roofline = {
+        "bound": "tensor", "kernel": cats[dom], "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
+        "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+        "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+        "note": "achieved = ALGORITHMIC flops (2*B*K*N*T per layer GEMM, one product per MAC) / CUDA-event kernel time; "
+                "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC",
+        "all_tensor_kernels": {"ms": tc_ms, "algo_tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
+                               "share_of_step": tc_ms / ms_total},
+        "per_kernel": per_cat,
+    }
+    cpu_value, cpu_dt = time_cpu(CPU_SAMPLE_ROWS, 3, 2) if world == 1 else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 planes (fp32-parity), fp32 accumulate", "data": "synthetic",
+        "config": {"workload": W["name"], **{k: v for k, v in W.items() if k != "name"},
+                   "parallelism": f"dp{world}", "envs_per_gpu": N,
+                   "l2": "inputs larger than L2: 54 MB rollout + 0.3 GB traces per minibatch vs 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 8},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "extra": {"act_env_steps_per_s": act_value, "act_ms": ms_act, "act_batch": N},
+    }
+    if cpu_value is not None:
+        line["cpu_baseline"] = {
+            "value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one PPO minibatch step on {CPU_SAMPLE_ROWS} of 24576 rows, 2 warm-up + 3 timed, oracle port "
+                      f"(torch CPU fp32 autograd); {cpu_dt:.2f} s/step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

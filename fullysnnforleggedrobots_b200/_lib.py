@@ -88,6 +88,9 @@ _SIGS = {
                           C.c_void_p]),
     "snn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                           C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "snn_profile_enable": (C.c_int, [C.c_int]),
+    "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "snn_launch_count": (C.c_int64, []),
     "snn_debug_trace_layout": (C.c_int, [C.POINTER(SnnDesc), C.c_int64, C.POINTER(C.c_int64), C.c_int]),
 }
 

@@ -2,6 +2,7 @@
 // every buffer is caller-owned, nothing here allocates device memory or synchronises.
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "dw_gemm.cuh"
 #include "plan.cuh"
@@ -30,6 +31,37 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess) return fail(SNN_ECUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
+
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream, read back later
+enum { CAT_FWD = 0, CAT_DX = 1, CAT_DW = 2, CAT_OTHER = 3, NUM_CAT = 4 };
+struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[NUM_CAT] = {0, 0, 0, 0};
+  double flops[NUM_CAT] = {0, 0, 0, 0};
+  long long launches[NUM_CAT] = {0, 0, 0, 0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+Profiler g_prof;
+long long g_launch_count = 0;
+
+struct ProfScope {
+  cudaStream_t st; int idx = -1;
+  ProfScope(int cat, double flops, cudaStream_t s) : st(s) {
+    ++g_launch_count;
+    if (!g_prof.on) return;
+    ProfRec r{cat, g_prof.get(), g_prof.get(), flops};
+    cudaEventRecord(r.a, st);
+    g_prof.recs.push_back(r);
+    idx = static_cast<int>(g_prof.recs.size()) - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof.recs[idx].b, st); }
+};
 
 struct DeviceInfo {
   int checked = 0;     // 0 = not yet, 1 = ok, -1 = wrong arch
@@ -81,8 +113,10 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   uint32_t* enc_bits = reinterpret_cast<uint32_t*>(at(bits_base, p.tr_enc_bits));
   {
     dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>((p.Bpad + 7) / 8));
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     encode_kernel<<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
                                        p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+    }
     LAUNCH_CHECK("encode_kernel");
   }
   const uint32_t* in_bits = enc_bits;
@@ -101,14 +135,18 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = q.nitems < num_sms ? q.nitems : num_sms;
+    { ProfScope prof__(CAT_FWD, 2.0 * B * lp.K * lp.N * p.T, st);
     scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(p.NCmax), st>>>(q);
+    }
     LAUNCH_CHECK("scan_gemm_kernel<FWD>");
     in_bits = q.out_bits;
   }
   {
     const int n = static_cast<int>(B) * p.A;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
                                                    p.T, prm->dec_w, prm->dec_b, d->dec_tanh, mu);
+    }
     LAUNCH_CHECK("decode_kernel");
   }
   return SNN_OK;
@@ -149,9 +187,11 @@ int snn_pack_weights(const SnnDesc* d, const SnnParams* prm, void* packed, void*
     const LayerPlan& lp = p.layer[l];
     if (prm->weight[l] == nullptr || prm->bias[l] == nullptr) return fail(SNN_EINVAL, "null weight/bias pointer");
     const int total = lp.NP * lp.KP / 8;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     pack_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP,
                                                        at(packed, lp.w_img), lp.w_plane, at(packed, lp.wt_img),
                                                        lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad)));
+    }
     LAUNCH_CHECK("pack_w_kernel");
   }
   return SNN_OK;
@@ -206,11 +246,15 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const LayerPlan& lp = p.layer[top];
     dim3 grd(lp.NP / 128, Bp / 32);
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     top_scan_kernel<<<grd, 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
                                          p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart);
+    }
     LAUNCH_CHECK("top_scan_kernel");
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     reduce_rows_kernel<<<(lp.N + 127) / 128, 128, 0, st>>>(dbpart, Bp / 32, lp.NP, lp.N, g->bias[top]);
+    }
     LAUNCH_CHECK("reduce_rows_kernel(db top)");
   }
   // ---- walk down the layers
@@ -232,10 +276,14 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
       q.partial = partial;
+      { ProfScope prof__(CAT_DW, 2.0 * B * lp.K * lp.N * p.T, st);
       dw_gemm_kernel<<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
+      }
       LAUNCH_CHECK("dw_gemm_kernel");
       dim3 rg((lp.K + 127) / 128, lp.N);
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
       reduce_partials_kernel<<<rg, 128, 0, st>>>(partial, splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
+      }
       LAUNCH_CHECK("reduce_partials_kernel");
     }
     {   // dX_l + scan of the layer below (or of the encoder)
@@ -253,13 +301,19 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         q.g_img = at(workspace, p.ws_g[slot ^ 1]);
         q.g_plane = p.ws_g_plane[slot ^ 1];
         q.db_part = dbpart;
+        { ProfScope prof__(CAT_DX, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(p.NCmax), st>>>(q);
+        }
         LAUNCH_CHECK("scan_gemm_kernel<DX>");
+        { ProfScope prof__(CAT_OTHER, 0.0, st);
         reduce_rows_kernel<<<(lo.N + 127) / 128, 128, 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
+        }
         LAUNCH_CHECK("reduce_rows_kernel(db)");
       } else {
         q.g_a = g_a;
+        { ProfScope prof__(CAT_DX, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX_ENC><<<grid, ScanCfg<MODE_DX_ENC>::THREADS, scan_gemm_smem_bytes<MODE_DX_ENC>(p.NCmax), st>>>(q);
+        }
         LAUNCH_CHECK("scan_gemm_kernel<DX_ENC>");
       }
     }
@@ -270,25 +324,39 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     if (AP + p.A > 1024) return fail(SNN_EINVAL, "act_dim * de_pop too large for dec_bwd_kernel");
     const int nblk = (Bi + 127) / 128;
     const uint32_t* top_bits = reinterpret_cast<const uint32_t*>(at(trace, p.layer[top].tr_bits));
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     dec_bwd_kernel<<<nblk, ((AP + p.A + 31) / 32) * 32, 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
                                                                p.T, small);
+    }
     LAUNCH_CHECK("dec_bwd_kernel");
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     reduce_rows_kernel<<<(AP + 127) / 128, 128, 0, st>>>(small, nblk, AP + p.A, AP, g->dec_w);
+    }
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     reduce_rows_kernel<<<(p.A + 127) / 128, 128, 0, st>>>(small + AP, nblk, AP + p.A, p.A, g->dec_b);
+    }
     LAUNCH_CHECK("reduce_rows_kernel(dec)");
   }
   // ---- encoder parameter gradients (+ d obs)
   {
     const int nblk = (Bi + 63) / 64;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     enc_bwd_kernel<<<nblk, 256, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
+    }
     LAUNCH_CHECK("enc_bwd_kernel");
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
+    }
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
+    }
     LAUNCH_CHECK("reduce_rows_kernel(enc)");
     if (g->obs != nullptr) {
       const int n = Bi * p.O;
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
       enc_dobs_kernel<<<(n + 255) / 256, 256, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0P,
                                                        d->enc_eps, g->obs);
+      }
       LAUNCH_CHECK("enc_dobs_kernel");
     }
   }
@@ -306,17 +374,47 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values, con
   if (nb > 1024) return fail(SNN_EINVAL, "more than 131072 environments per rank not supported by snn_gae");
   double* part_sum = static_cast<double*>(scratch);        // [1024]
   double* part_sq = part_sum + 1024;                       // [256]
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
   gae_scan_kernel<<<nb, 128, 0, st>>>(rewards, dones, values, last_values, static_cast<int>(S), static_cast<int>(N), gamma,
                                       lam, returns, advantages, part_sum);
+  }
   LAUNCH_CHECK("gae_scan_kernel");
   if (normalize) {
     const int64_t count = S * N;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     gae_var_kernel<<<256, 256, 0, st>>>(advantages, count, part_sum, nb, part_sq);
+    }
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
     gae_norm_kernel<<<256, 256, 0, st>>>(advantages, count, part_sum, nb, part_sq, 256);
+    }
     LAUNCH_CHECK("gae_norm_kernel");
   }
   return SNN_OK;
 }
+
+int snn_profile_enable(int on) {
+  for (auto& r : g_prof.recs) { g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b); }
+  g_prof.recs.clear();
+  for (int c = 0; c < NUM_CAT; ++c) { g_prof.ms[c] = 0; g_prof.flops[c] = 0; g_prof.launches[c] = 0; }
+  g_prof.on = on != 0;
+  return SNN_OK;
+}
+
+int snn_profile_read(double* ms, double* flops, int64_t* launches) {
+  if (!ms || !flops || !launches) return fail(SNN_EINVAL, "null pointer");
+  for (auto& r : g_prof.recs) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    g_prof.ms[r.cat] += t; g_prof.flops[r.cat] += r.flops; g_prof.launches[r.cat] += 1;
+    g_prof.pool.push_back(r.a); g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  for (int c = 0; c < NUM_CAT; ++c) { ms[c] = g_prof.ms[c]; flops[c] = g_prof.flops[c]; launches[c] = g_prof.launches[c]; }
+  return NUM_CAT;
+}
+
+int64_t snn_launch_count(void) { return g_launch_count; }
 
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out) {
   SnnPlan p;

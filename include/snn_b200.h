@@ -108,6 +108,15 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values,
             const float* last_values, int64_t S, int64_t N, float gamma, float lam,
             float* returns, float* advantages, int normalize, void* scratch, void* stream);
 
+/* Optional per-launch device timing used by bench.py's roofline: while enabled, every kernel launch is
+ * bracketed by CUDA events on its stream.  Categories: 0 = forward scan-GEMM, 1 = backward dX scan-GEMM,
+ * 2 = dW GEMM, 3 = all other (SIMT) kernels.  snn_profile_read synchronises on the recorded events and
+ * returns accumulated milliseconds, ALGORITHMIC flops (2*B*K*N*T, unpadded, one product per MAC) and launch
+ * counts since the last snn_profile_enable.  snn_launch_count counts every kernel this library launched. */
+int snn_profile_enable(int on);
+int snn_profile_read(double* ms4, double* flops4, int64_t* launches4);
+int64_t snn_launch_count(void);
+
 /* Debug / test hooks: unpack internal buffers into plain tensors (tests only). */
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out);
 

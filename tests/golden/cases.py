@@ -111,3 +111,51 @@ def make_gmu(c: Case) -> torch.Tensor:
     """Upstream gradient dL/dmu used for the backward fixtures."""
     g = torch.Generator().manual_seed(3000 + c.seed)
     return torch.randn(c.batch, c.act_dim, generator=g, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------- PPO update case
+@dataclass(frozen=True)
+class PPOCase:
+    name: str = "ppo_cassie_tiny"
+    variant: str = "cassie"
+    obs_dim: int = 6
+    hidden: tuple = (32, 24)
+    critic_hidden: tuple = (16, 16)
+    act_dim: int = 3
+    num_envs: int = 8
+    num_steps: int = 4
+    epochs: int = 2
+    seed: int = 21
+    gamma: float = 0.99
+    lam: float = 0.95
+    lr: float = 1e-3
+    entropy_coef: float = 0.01
+
+
+PPO_CASE = PPOCase()
+
+
+def make_ppo_state_dict(pc: PPOCase) -> Dict[str, torch.Tensor]:
+    c = Case("ppo_actor", pc.variant, pc.obs_dim, pc.hidden, pc.act_dim, 1, seed=pc.seed)
+    sd = make_state_dict(c)
+    g = torch.Generator().manual_seed(4000 + pc.seed)
+    dims = [pc.obs_dim] + list(pc.critic_hidden) + [1]
+    for i in range(len(dims) - 1):
+        bound = 1.0 / math.sqrt(dims[i])
+        sd[f"critic.{2 * i}.weight"] = _uniform(g, (dims[i + 1], dims[i]), bound)
+        sd[f"critic.{2 * i}.bias"] = _uniform(g, (dims[i + 1],), bound)
+    sd["std"] = torch.ones(pc.act_dim)
+    return sd
+
+
+def make_ppo_rollout(pc: PPOCase):
+    """Seeded rollout inputs that do not depend on the policy: obs, rewards, dones, action noise, last obs."""
+    g = torch.Generator().manual_seed(5000 + pc.seed)
+    S, N = pc.num_steps, pc.num_envs
+    return {
+        "obs": torch.randn(S, N, pc.obs_dim, generator=g),
+        "rewards": torch.randn(S, N, generator=g),
+        "dones": (torch.rand(S, N, generator=g) < 0.15).to(torch.uint8),
+        "noise": torch.randn(S, N, pc.act_dim, generator=g),
+        "last_obs": torch.randn(N, pc.obs_dim, generator=g),
+    }

@@ -22,7 +22,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from cases import CASES, make_gmu, make_obs, make_state_dict  # noqa: E402
+from cases import CASES, PPO_CASE, make_gmu, make_obs, make_ppo_rollout, make_ppo_state_dict, make_state_dict  # noqa: E402
 
 REF = "/root/reference"
 PKG_ROOT = {
@@ -119,6 +119,54 @@ def run_gae_case():
     return {"returns": storage.returns.numpy(), "advantages": storage.advantages.numpy()}
 
 
+def run_ppo_case(pc):
+    """The reference PPO.update (CASSIE copy) on a seeded rollout: 1 minibatch x `epochs` Adam steps.
+    Records what the rollout phase produced (so tests can re-feed it) and the parameters after the update."""
+    import_ref(pc.variant, "modules.actor_critic")
+    mods = importlib.import_module("rsl_rl.modules")
+    algs = importlib.import_module("rsl_rl.algorithms")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ac = mods.ActorCritic(pc.obs_dim, pc.obs_dim, pc.act_dim, actor_hidden_dims=list(pc.hidden),
+                              critic_hidden_dims=list(pc.critic_hidden), activation="elu", init_noise_std=1.0)
+    ac.actor.encoder.device = ac.actor.snn.device = "cpu"
+    ac.load_state_dict(make_ppo_state_dict(pc))
+    alg = algs.PPO(ac, num_learning_epochs=pc.epochs, num_mini_batches=1, clip_param=0.2, gamma=pc.gamma,
+                   lam=pc.lam, value_loss_coef=1.0, entropy_coef=pc.entropy_coef, learning_rate=pc.lr,
+                   max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cpu")
+    alg.init_storage(pc.num_envs, pc.num_steps, [pc.obs_dim], [None], [pc.act_dim])
+    ro = make_ppo_rollout(pc)
+    st = alg.storage
+    with contextlib.redirect_stdout(io.StringIO()), torch.inference_mode():
+        for s in range(pc.num_steps):
+            mu = ac.act_inference(ro["obs"][s])
+            sigma = torch.exp(ac.actor.log_std).expand_as(mu)
+            actions = mu + sigma * ro["noise"][s]
+            ac.update_distribution(ro["obs"][s])
+            st.observations[s].copy_(ro["obs"][s])
+            st.actions[s].copy_(actions)
+            st.rewards[s].copy_(ro["rewards"][s].view(-1, 1))
+            st.dones[s].copy_(ro["dones"][s].view(-1, 1))
+            st.values[s].copy_(ac.evaluate(ro["obs"][s]))
+            st.actions_log_prob[s].copy_(ac.get_actions_log_prob(actions).view(-1, 1))
+            st.mu[s].copy_(ac.action_mean)
+            st.sigma[s].copy_(ac.action_std)
+            st.step += 1
+        alg.compute_returns(ro["last_obs"])
+    out = {"actions": st.actions.numpy().copy(), "values": st.values.numpy().copy(),
+           "actions_log_prob": st.actions_log_prob.numpy().copy(), "mu": st.mu.numpy().copy(),
+           "sigma": st.sigma.numpy().copy(), "returns": st.returns.numpy().copy(),
+           "advantages": st.advantages.numpy().copy()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        vl, sl = alg.update()
+    out["mean_value_loss"] = np.float64(vl)
+    out["mean_surrogate_loss"] = np.float64(sl)
+    out["final_lr"] = np.float64(alg.learning_rate)
+    for k, v in ac.state_dict().items():
+        out["final." + k] = v.detach().numpy().copy()
+    return out
+
+
 def main():
     for c in CASES:
         out = run_actor_case(c)
@@ -127,6 +175,8 @@ def main():
         print(f"{c.name:22s} -> {os.path.getsize(path) / 1024:.1f} KiB  mu[0]={out['mu'][0][:3]}")
     np.savez_compressed(os.path.join(HERE, "gae_cassie.npz"), **run_gae_case())
     print("gae_cassie done")
+    np.savez_compressed(os.path.join(HERE, f"{PPO_CASE.name}.npz"), **run_ppo_case(PPO_CASE))
+    print("ppo case done")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,108 @@
+"""GPU parity of the actor-critic / PPO / rollout-storage surface against the reference fixture
+(ppo_cassie_tiny.npz: the reference's own PPO.update on a seeded rollout) and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cases import PPO_CASE, make_ppo_rollout, make_ppo_state_dict
+from helpers import GOLD, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def load():
+    return dict(np.load(os.path.join(GOLD, f"{PPO_CASE.name}.npz")))
+
+
+def make_alg(pc):
+    from fullysnnforleggedrobots_b200 import PPO, ActorCriticCassie
+    ac = ActorCriticCassie(pc.obs_dim, pc.obs_dim, pc.act_dim, actor_hidden_dims=list(pc.hidden),
+                           critic_hidden_dims=list(pc.critic_hidden), activation="elu", init_noise_std=1.0)
+    ac.load_state_dict(make_ppo_state_dict(pc))
+    alg = PPO(ac, num_learning_epochs=pc.epochs, num_mini_batches=1, clip_param=0.2, gamma=pc.gamma, lam=pc.lam,
+              value_loss_coef=1.0, entropy_coef=pc.entropy_coef, learning_rate=pc.lr, max_grad_norm=1.0,
+              use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cuda")
+    alg.init_storage(pc.num_envs, pc.num_steps, [pc.obs_dim], [None], [pc.act_dim])
+    return ac, alg
+
+
+def test_state_dict_keys_match_reference():
+    pc, g = PPO_CASE, load()
+    ac, _ = make_alg(pc)
+    ref_keys = sorted(k[len("final."):] for k in g if k.startswith("final."))
+    assert sorted(ac.state_dict().keys()) == ref_keys
+
+
+def test_act_and_rollout_quantities():
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    with torch.inference_mode():
+        for s in range(pc.num_steps):
+            obs = ro["obs"][s].cuda()
+            a = alg.act(obs, obs)
+            assert a.shape == (pc.num_envs, pc.act_dim)
+            assert rel_err(ac.action_mean.cpu(), g["mu"][s]) < 1e-4
+            assert rel_err(ac.action_std.cpu(), g["sigma"][s]) < 1e-6
+            assert rel_err(alg.transition.values.cpu(), g["values"][s]) < 1e-5
+            lp = ac.get_actions_log_prob(torch.from_numpy(g["actions"][s]).cuda())
+            assert rel_err(lp.cpu(), g["actions_log_prob"][s].reshape(-1)) < 1e-4
+            alg.process_env_step(ro["rewards"][s].cuda(), ro["dones"][s].cuda(), {})
+    assert alg.storage.step == pc.num_steps
+    with pytest.raises(AssertionError):
+        alg.transition.observations = ro["obs"][0].cuda()
+        alg.transition.critic_observations = ro["obs"][0].cuda()
+        alg.storage.add_transitions(alg.transition)      # "Rollout buffer overflow"
+
+
+def fill_storage(alg, pc, g, ro):
+    st = alg.storage
+    st.observations.copy_(ro["obs"])
+    st.actions.copy_(torch.from_numpy(g["actions"]))
+    st.rewards.copy_(ro["rewards"].unsqueeze(-1))
+    st.dones.copy_(ro["dones"].unsqueeze(-1))
+    st.values.copy_(torch.from_numpy(g["values"]))
+    st.actions_log_prob.copy_(torch.from_numpy(g["actions_log_prob"]))
+    st.mu.copy_(torch.from_numpy(g["mu"]))
+    st.sigma.copy_(torch.from_numpy(g["sigma"]))
+    st.step = pc.num_steps
+
+
+def test_gae_and_update_match_reference():
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    fill_storage(alg, pc, g, ro)
+    alg.compute_returns(ro["last_obs"].cuda())
+    assert rel_err(alg.storage.returns.cpu(), g["returns"]) < 1e-5
+    assert rel_err(alg.storage.advantages.cpu(), g["advantages"]) < 1e-4
+    vl, sl = alg.update()
+    assert abs(vl / g["mean_value_loss"] - 1) < 1e-4
+    assert abs(sl - g["mean_surrogate_loss"]) < 1e-4 * max(1.0, abs(g["mean_surrogate_loss"]))
+    assert abs(alg.learning_rate / g["final_lr"] - 1) < 1e-12
+    sd0 = make_ppo_state_dict(pc)
+    for k, v in ac.state_dict().items():
+        ref = torch.from_numpy(g["final." + k])
+        if k == "std":
+            assert torch.equal(v.cpu(), ref)
+            continue
+        d_ref = ref - sd0[k]
+        d = v.cpu() - sd0[k]
+        frac_bad = ((d - d_ref).abs() > 0.02 * pc.lr).float().mean().item()
+        assert frac_bad < 0.005, (k, frac_bad)
+
+
+def test_gae_kernel_large_matches_oracle():
+    from fullysnnforleggedrobots_b200 import gae
+    from oracle import snn_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    S, N = 24, 4096
+    rewards = torch.randn(S, N, generator=gen)
+    values = torch.randn(S, N, generator=gen)
+    dones = (torch.rand(S, N, generator=gen) < 0.05).to(torch.uint8)
+    last = torch.randn(N, generator=gen)
+    ret_ref, adv_ref = O.gae_returns(rewards.unsqueeze(-1), dones.unsqueeze(-1), values.unsqueeze(-1),
+                                     last.unsqueeze(-1), 0.99, 0.95)
+    ret, adv = gae(rewards.cuda(), dones.cuda(), values.cuda(), last.cuda(), 0.99, 0.95)
+    assert rel_err(ret.cpu(), ret_ref.squeeze(-1)) < 1e-6
+    assert rel_err(adv.cpu(), adv_ref.squeeze(-1)) < 1e-5
