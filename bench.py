@@ -240,12 +240,12 @@ def run_ours(args):
     def step_resident():
         alg.update()
 
-    for _ in range(args.warmup):
-        step_resident()
     L = _lib.lib()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # started before warm-up: nvidia-smi needs ~0.5 s before its first sample
+    for _ in range(args.warmup):
+        step_resident()
     L.snn_profile_enable(1)
     launches0 = L.snn_launch_count()
     ms_total = timed(step_resident, args.steps)
@@ -276,9 +276,12 @@ def run_ours(args):
             alg.compute_returns(last)
         return alg.update()                      # returns two host floats (device -> host read of the losses)
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_value = world * samples_per_step / (ms_e2e * 1e-3)
+    if args.quick:
+        ms_e2e, e2e_value = float("nan"), float("nan")
+    else:
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps) / args.steps
+        e2e_value = world * samples_per_step / (ms_e2e * 1e-3)
 
     # ---- forward-only metric (rollout `act`): env-steps/s at B = num_envs
     obs_dev = host["obs"][0].to(dev)
@@ -287,9 +290,9 @@ def run_ours(args):
         with torch.inference_mode():
             ac.act_inference(obs_dev)
 
-    for _ in range(10):
+    for _ in range(2 if args.quick else 10):
         step_act()
-    ms_act = timed(step_act, 50) / 50
+    ms_act = timed(step_act, 2 if args.quick else 50) / (2 if args.quick else 50)
     act_value = world * N / (ms_act * 1e-3)
 
     if rank != 0:
@@ -315,7 +318,7 @@ def run_ours(args):
                                "share_of_step": tc_ms / ms_total},
         "per_kernel": per_cat,
     }
-    cpu_value, cpu_dt = time_cpu(CPU_SAMPLE_ROWS, 3, 2) if world == 1 else (None, None)
+    cpu_value, cpu_dt = time_cpu(CPU_SAMPLE_ROWS, 3, 2) if (world == 1 and not args.quick) else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -347,6 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="resident leg only (for ncu runs): no e2e / act / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
