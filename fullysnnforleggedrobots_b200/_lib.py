@@ -88,6 +88,11 @@ _SIGS = {
                           C.c_void_p]),
     "snn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                           C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "snn_ppo_head": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+                     + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
+    "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 6
+                      + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "snn_launch_count": (C.c_int64, []),

@@ -6,6 +6,7 @@
 
 #include "dw_gemm.cuh"
 #include "plan.cuh"
+#include "ppo_kernels.cuh"
 #include "scan_gemm.cuh"
 #include "simt_kernels.cuh"
 
@@ -389,6 +390,66 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values, con
     }
     LAUNCH_CHECK("gae_norm_kernel");
   }
+  return SNN_OK;
+}
+
+int snn_ppo_head(const float* mu, const float* log_std, const float* value, const float* actions,
+                 const float* old_logp, const float* adv, const float* returns, const float* target_v,
+                 const float* old_mu, const float* old_sigma, int64_t B, int A, float clip, float value_coef,
+                 float ent_coef, int clipped_value, float* g_mu, float* g_value, float* g_log_std, float* stats,
+                 void* scratch, size_t scratch_bytes, void* stream) {
+  if (!mu || !log_std || !value || !actions || !old_logp || !adv || !returns || !target_v || !old_mu || !old_sigma ||
+      !g_mu || !g_value || !g_log_std || !stats || !scratch)
+    return fail(SNN_EINVAL, "null pointer");
+  if (B <= 0 || A <= 0 || A > kHeadMaxA) return fail(SNN_EINVAL, "bad B / act_dim (act_dim <= 64)");
+  const int nblk = static_cast<int>((B + 255) / 256);
+  if (scratch_bytes < static_cast<size_t>(nblk) * (4 + A) * 4) return fail(SNN_ENOMEM, "ppo head scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PpoHeadParams q{};
+  q.mu = mu; q.log_std = log_std; q.value = value; q.actions = actions; q.old_logp = old_logp; q.adv = adv;
+  q.returns = returns; q.target_v = target_v; q.old_mu = old_mu; q.old_sigma = old_sigma;
+  q.B = static_cast<int>(B); q.A = A; q.clip = clip; q.value_coef = value_coef; q.ent_coef = ent_coef;
+  q.clipped_value = clipped_value; q.inv_count = 1.0f / static_cast<float>(B);
+  q.g_mu = g_mu; q.g_value = g_value; q.part = static_cast<float*>(scratch);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  ppo_head_kernel<<<nblk, 256, 0, st>>>(q);
+  }
+  LAUNCH_CHECK("ppo_head_kernel");
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  ppo_head_finalize_kernel<<<1, 128, 0, st>>>(q.part, nblk, A, q.B, log_std, ent_coef, 1.0f, g_log_std, stats);
+  }
+  LAUNCH_CHECK("ppo_head_finalize_kernel");
+  return SNN_OK;
+}
+
+int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, void* stream) {
+  if (!kl || !lr) return fail(SNN_EINVAL, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  lr_adapt_kernel<<<1, 32, 0, st>>>(kl, kl_scale, desired_kl, lr);
+  }
+  LAUNCH_CHECK("lr_adapt_kernel");
+  return SNN_OK;
+}
+
+int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
+                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                  float* norm_out, void* scratch, void* stream) {
+  if (!params || !grads || !m || !v || !lr || !step || !scratch) return fail(SNN_EINVAL, "null pointer");
+  if (n <= 0) return fail(SNN_EINVAL, "empty parameter buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nb = static_cast<int>((n + 256 * 8 - 1) / (256 * 8));
+  if (nb > 296) nb = 296;
+  float* partial = static_cast<float*>(scratch);     // >= 296 floats
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, grad_scale, partial, step);
+  }
+  LAUNCH_CHECK("sumsq_kernel");
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  clip_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, partial, nb, lr, step, beta1, beta2, eps, weight_decay,
+                                       max_norm, grad_scale, norm_out);
+  }
+  LAUNCH_CHECK("clip_adam_kernel");
   return SNN_OK;
 }
 

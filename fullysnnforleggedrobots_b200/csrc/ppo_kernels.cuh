@@ -1,0 +1,218 @@
+// ppo_kernels.cuh — the PPO head and the optimizer as fused kernels.
+//
+//   ppo_head_kernel / ppo_head_finalize_kernel
+//       everything between the network outputs and their gradients in PPO.update
+//       (AMP/.../algorithms/ppo.py:132-171 + modules/actor_critic.py:398-421): Normal log-prob, entropy,
+//       KL to the rollout policy, clipped surrogate, clipped value loss — forward AND the closed-form
+//       gradient w.r.t. mu, value and log_std, in one pass over the minibatch.  ~45 PyTorch kernels
+//       and their autograd nodes in the reference.
+//   lr_adapt_kernel
+//       the adaptive-KL learning-rate schedule (ppo.py:139-151) without the host round trip.
+//   sumsq_kernel / clip_adam_kernel
+//       nn.utils.clip_grad_norm_ + torch.optim.Adam.step (ppo.py:176-177) over ONE flat fp32 buffer.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace snn {
+
+struct PpoHeadParams {
+  const float* mu;          // [B,A] actor output
+  const float* log_std;     // [A]
+  const float* value;       // [B]
+  const float* actions;     // [B,A]
+  const float* old_logp;    // [B]
+  const float* adv;         // [B]
+  const float* returns;     // [B]
+  const float* target_v;    // [B] values stored in the rollout
+  const float* old_mu;      // [B,A]
+  const float* old_sigma;   // [B,A]
+  int B, A;
+  float clip, value_coef, ent_coef;
+  int clipped_value;
+  float inv_count;          // 1 / (B * world): loss means are over the GLOBAL minibatch
+  float* g_mu;              // [B,A]
+  float* g_value;           // [B]
+  float* part;              // [gridDim.x][4 + A] partial sums: surrogate, value loss, kl, (unused), g_log_std[a]
+};
+
+constexpr int kHeadMaxA = 64;
+constexpr float kHalfLog2Pi = 0.91893853320467274178f;
+
+__device__ __forceinline__ float block_sum_256(float x, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = x;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 8) t = sh[threadIdx.x];
+  if (threadIdx.x < 32) {
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) ppo_head_kernel(const PpoHeadParams p) {
+  __shared__ float sh[8];
+  __shared__ float s_sigma[kHeadMaxA], s_inv_var[kHeadMaxA], s_log_sigma[kHeadMaxA];
+  if (threadIdx.x < p.A) {
+    const float ls = p.log_std[threadIdx.x];
+    const float s = expf(ls);
+    s_sigma[threadIdx.x] = s;
+    s_inv_var[threadIdx.x] = 1.f / (s * s);
+    s_log_sigma[threadIdx.x] = logf(s);
+  }
+  __syncthreads();
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  const bool live = b < p.B;
+  float sur = 0.f, vl = 0.f, kl = 0.f, g_logp = 0.f;
+  if (live) {
+    const float* mu = p.mu + static_cast<size_t>(b) * p.A;
+    const float* act = p.actions + static_cast<size_t>(b) * p.A;
+    const float* omu = p.old_mu + static_cast<size_t>(b) * p.A;
+    const float* osg = p.old_sigma + static_cast<size_t>(b) * p.A;
+    float logp = 0.f;
+    for (int a = 0; a < p.A; ++a) {
+      const float d = act[a] - mu[a];
+      logp += -(d * d) * 0.5f * s_inv_var[a] - s_log_sigma[a] - kHalfLog2Pi;
+      const float os = osg[a], dm = omu[a] - mu[a];
+      kl += logf(s_sigma[a] / os + 1.e-5f) + (os * os + dm * dm) * 0.5f * s_inv_var[a] - 0.5f;
+    }
+    const float ad = p.adv[b];
+    const float ratio = expf(logp - p.old_logp[b]);
+    const float s1 = -ad * ratio;
+    const float s2 = -ad * fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
+    sur = fmaxf(s1, s2);
+    g_logp = (s1 >= s2 ? -ad : 0.f) * ratio * p.inv_count;     // d mean(sur) / d logp
+    // value loss
+    const float v = p.value[b], R = p.returns[b];
+    const float e1 = v - R;
+    float gv;
+    if (p.clipped_value) {
+      const float tv = p.target_v[b];
+      const float dv = v - tv;
+      const float vc = tv + fminf(fmaxf(dv, -p.clip), p.clip);
+      const float e2 = vc - R;
+      const float l1 = e1 * e1, l2 = e2 * e2;
+      vl = fmaxf(l1, l2);
+      const float inside = (dv >= -p.clip && dv <= p.clip) ? 1.f : 0.f;
+      const float g1 = 2.f * e1, g2 = 2.f * e2 * inside;
+      gv = l1 > l2 ? g1 : (l1 < l2 ? g2 : 0.5f * (g1 + g2));
+    } else {
+      vl = e1 * e1;
+      gv = 2.f * e1;
+    }
+    p.g_value[b] = gv * p.value_coef * p.inv_count;
+    float* gm = p.g_mu + static_cast<size_t>(b) * p.A;
+    for (int a = 0; a < p.A; ++a) gm[a] = g_logp * (act[a] - mu[a]) * s_inv_var[a];
+  }
+  float* out = p.part + static_cast<size_t>(blockIdx.x) * (4 + p.A);
+  float t;
+  t = block_sum_256(sur, sh); if (threadIdx.x == 0) out[0] = t;
+  t = block_sum_256(vl, sh);  if (threadIdx.x == 0) out[1] = t;
+  t = block_sum_256(kl, sh);  if (threadIdx.x == 0) out[2] = t;
+  if (threadIdx.x == 0) out[3] = 0.f;
+  for (int a = 0; a < p.A; ++a) {
+    float x = 0.f;
+    if (live) {
+      const float d = p.actions[static_cast<size_t>(b) * p.A + a] - p.mu[static_cast<size_t>(b) * p.A + a];
+      x = g_logp * (d * d * s_inv_var[a] - 1.f);      // d logp / d log_std = (a-mu)^2/sigma^2 - 1
+    }
+    t = block_sum_256(x, sh);
+    if (threadIdx.x == 0) out[4 + a] = t;
+  }
+}
+
+// stats: [0] surrogate mean (local), [1] value-loss mean (local), [2] kl mean (local), [3] entropy mean,
+//        [4] accumulated surrogate, [5] accumulated value loss, [6] number of accumulated steps
+// g_log_std[a] = sum_b(...) - ent_coef / world   (entropy bonus: d(-c * mean_b sum_a log sigma_a)/d log_std = -c)
+__global__ void ppo_head_finalize_kernel(const float* __restrict__ part, int nparts, int A, int B,
+                                         const float* __restrict__ log_std, float ent_coef, float inv_world,
+                                         float* __restrict__ g_log_std, float* __restrict__ stats) {
+  const int i = threadIdx.x;
+  if (i < 3) {
+    double acc = 0.0;
+    for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * (4 + A) + i];
+    const float mean = static_cast<float>(acc / B);
+    stats[i] = mean;
+    if (i == 0) stats[4] += mean;
+    if (i == 1) stats[5] += mean;
+    if (i == 2) stats[6] += 1.f;
+  } else if (i == 3) {
+    float e = 0.f;
+    for (int a = 0; a < A; ++a) e += 0.5f + kHalfLog2Pi + log_std[a];
+    stats[3] = e;
+  } else if (i >= 4 && i < 4 + A) {
+    double acc = 0.0;
+    for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * (4 + A) + i];
+    g_log_std[i - 4] = static_cast<float>(acc) - ent_coef * inv_world;
+  }
+}
+
+// ppo.py:145-148.  kl_mean = kl[0] * kl_scale (kl_scale = 1/world when kl[0] is a sum of rank means).
+__global__ void lr_adapt_kernel(const float* __restrict__ kl, float kl_scale, float desired_kl, float* __restrict__ lr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float k = kl[0] * kl_scale;
+    float l = lr[0];
+    if (k > desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
+    else if (k < desired_kl / 2.0f && k > 0.0f) l = fminf(1e-2f, l * 1.5f);
+    lr[0] = l;
+  }
+}
+
+// partial[blockIdx.x] = sum of g^2 over this block's grid-stride slice; block 0 also advances the step counter.
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float grad_scale,
+                                                   float* __restrict__ partial, int* __restrict__ step) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float x = g[i] * grad_scale;
+    acc += x * x;
+  }
+  const float t = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = t;
+    if (blockIdx.x == 0) step[0] += 1;
+  }
+}
+
+// clip_grad_norm_(max_norm) + Adam (torch semantics: lerp first moment, eps outside the bias-corrected sqrt).
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ partial, int nparts,
+                                                       const float* __restrict__ lr, const int* __restrict__ step,
+                                                       float beta1, float beta2, float eps, float weight_decay,
+                                                       float max_norm, float grad_scale, float* __restrict__ norm_out) {
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < nparts; ++i) tot += partial[i];
+    const float norm = static_cast<float>(sqrt(tot));
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    s_coef = coef;
+    const double t = static_cast<double>(step[0]);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    s_step_size = static_cast<float>(static_cast<double>(lr[0]) / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+    if (blockIdx.x == 0 && norm_out != nullptr) norm_out[0] = norm;
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    float gi = g[i] * grad_scale * coef;
+    const float pi = prm[i];
+    if (weight_decay != 0.f) gi = gi + weight_decay * pi;
+    float mi = m[i], vi = v[i];
+    mi = mi + (gi - mi) * (1.f - beta1);
+    vi = vi * beta2 + gi * gi * (1.f - beta2);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    prm[i] = pi - step_size * (mi / denom);
+  }
+}
+
+}  // namespace snn

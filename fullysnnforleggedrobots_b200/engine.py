@@ -89,9 +89,20 @@ class SnnEngine:
     def invalidate(self):
         self._packed_key = None
 
+    def repack(self, enc_mean, enc_std, weights, biases, dec_w, dec_b):
+        """Unconditional re-pack (the fused optimizer updates parameters behind torch's version counters)."""
+        self._packed_key = None
+        ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
+        with torch.cuda.device(weights[0].device):
+            self.packed_weights(weights, biases, ps)
+
+    def trace_bytes(self, B: int) -> int:
+        return int(_lib.lib().snn_trace_bytes(C.byref(self.desc), B))
+
     # ------------------------------------------------------------------ calls
-    def forward(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, train: bool):
-        """Returns (mu, trace or None)."""
+    def forward(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, train: bool, out_mu=None,
+                out_trace=None):
+        """Returns (mu, trace or None).  out_mu / out_trace: optional caller-owned (static) output buffers."""
         _check_f32_cuda(obs, "obs")
         for t, n in ((enc_mean, "encoder.mean"), (enc_std, "encoder.std"), (dec_w, "decoder.weight"),
                      (dec_b, "decoder.bias"), *[(w, "weight") for w in weights], *[(b, "bias") for b in biases]):
@@ -104,12 +115,14 @@ class SnnEngine:
         with torch.cuda.device(dev):
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
             packed = self.packed_weights(weights, biases, ps)
-            mu = torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
+            mu = out_mu if out_mu is not None else torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
             if B == 0:
                 return mu, None
             if train:
                 nbytes = L.snn_trace_bytes(C.byref(self.desc), B)
-                trace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                trace = out_trace if out_trace is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                if trace.numel() < nbytes:
+                    raise RuntimeError("trace buffer too small")
                 _lib.check(L.snn_fwd_train(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
                                            _ptr(trace), nbytes, None, 0, _stream_ptr(dev)), "snn_fwd_train")
                 return mu, trace
@@ -119,7 +132,9 @@ class SnnEngine:
                                        _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_fwd_infer")
             return mu, None
 
-    def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool):
+    def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool,
+                 out=None):
+        """out: optional dict of caller-owned gradient tensors (same keys as the returned dict); overwritten."""
         dev = obs.device
         B = obs.shape[0]
         L = _lib.lib()
@@ -128,12 +143,13 @@ class SnnEngine:
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
             packed = self.packed_weights(weights, biases, ps)
             g = _lib.SnnGrads()
-            out = {
-                "enc_mean": torch.empty_like(enc_mean), "enc_std": torch.empty_like(enc_std),
-                "weights": [torch.empty_like(w) for w in weights], "biases": [torch.empty_like(b) for b in biases],
-                "dec_w": torch.empty_like(dec_w), "dec_b": torch.empty_like(dec_b),
-                "obs": torch.empty_like(obs) if need_dobs else None,
-            }
+            if out is None:
+                out = {
+                    "enc_mean": torch.empty_like(enc_mean), "enc_std": torch.empty_like(enc_std),
+                    "weights": [torch.empty_like(w) for w in weights], "biases": [torch.empty_like(b) for b in biases],
+                    "dec_w": torch.empty_like(dec_w), "dec_b": torch.empty_like(dec_b),
+                    "obs": torch.empty_like(obs) if need_dobs else None,
+                }
             g.enc_mean, g.enc_std = out["enc_mean"].data_ptr(), out["enc_std"].data_ptr()
             for i in range(self.L):
                 g.weight[i] = out["weights"][i].data_ptr()

@@ -1,34 +1,58 @@
 """PPO — same surface as rsl_rl.algorithms.PPO (reference: AMP/AMP_for_hardware-main/rsl_rl/rsl_rl/algorithms/
 ppo.py:38-187; CASSIE identical but default lr, HUMANOID adds Adam weight_decay=1e-5 at :70-72).
 
-act / process_env_step / compute_returns / update keep the reference's semantics.  What changes underneath:
-the actor forward/backward are the fused sm_100a kernels, GAE is one kernel, minibatches are contiguous
-slices, the two per-minibatch `.item()` host syncs (:179-180) are deferred to one sync per update, and under
-data parallelism the gradients (plus the KL statistic that drives the adaptive learning rate) are summed with
-ONE NCCL all-reduce per minibatch step (dist.py).
+act / process_env_step / compute_returns / update keep the reference's semantics.  Underneath, `update()` runs a
+fused minibatch step with no host round trip (CUDA-graph replayed):
+
+    actor forward (sm_100a kernels, traces kept)          snn_fwd_train
+    critic forward                                        dense ELU MLP (torch / cuBLAS; not spiking)
+    PPO head: log-prob, entropy, KL, surrogate, value     snn_ppo_head    (forward + closed-form gradients)
+    loss, and d loss / d (mu, value, log_std)
+    actor BPTT backward straight into the flat bucket     snn_bwd
+    critic backward                                       torch autograd on the critic only
+    [data parallel: ONE all-reduce of the flat bucket, KL statistic riding in its tail]
+    adaptive-KL learning rate on the device               snn_lr_adapt
+    clip_grad_norm_ + Adam over the flat bucket           snn_clip_adam
+    bf16 plane re-pack of the updated weights             snn_pack_weights
+
+The generic path (`fused=False`, or a policy whose actor input needs a gradient such as the RMA latent) keeps
+the reference's op-by-op structure through torch autograd, still on the same kernels.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
-import torch.optim as optim
 
+from . import _lib
+from .optim import FlatAdam
 from .storage import RolloutStorage
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
 
 
 class PPO:
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998,
                  lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
                  use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device='cpu', weight_decay=0.0,
-                 data_parallel=None):
+                 data_parallel=None, fused=True, use_cuda_graph=True):
         self.device = device
         self.desired_kl = desired_kl
         self.schedule = schedule
-        self.learning_rate = learning_rate
+        self._lr = learning_rate
         self.actor_critic = actor_critic
         self.actor_critic.to(self.device)
         self.storage = None
-        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        self.dp = data_parallel            # dist.GradientAllReducer or None
+        if self.dp is not None:
+            self.dp.broadcast_parameters(self.actor_critic)
+        # `std` never receives a gradient in SNN mode (the actor owns log_std): torch's Adam skips it, so do we
+        dead = {id(getattr(self.actor_critic, "std", None))}
+        self._trainable = [p for p in self.actor_critic.parameters() if id(p) not in dead]
+        self.optimizer = FlatAdam(self._trainable, lr=learning_rate, weight_decay=weight_decay, tail=1)
         self.transition = RolloutStorage.Transition()
         self.clip_param = clip_param
         self.num_learning_epochs = num_learning_epochs
@@ -39,9 +63,23 @@ class PPO:
         self.lam = lam
         self.max_grad_norm = max_grad_norm
         self.use_clipped_value_loss = use_clipped_value_loss
-        self.dp = data_parallel            # dist.GradientAllReducer or None
-        if self.dp is not None:
-            self.dp.broadcast_parameters(self.actor_critic)
+        self.fused = fused
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
+        self._fast_state = None
+        dev = self.optimizer.flat_params.device
+        self._stats = torch.zeros(8, dtype=torch.float32, device=dev)
+
+    # learning_rate is a plain attribute in the reference; here the truth lives on the device during update()
+    @property
+    def learning_rate(self):
+        return self._lr
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self._lr = float(v)
+        if hasattr(self, "optimizer"):
+            self.optimizer.set_lr(self._lr)
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape,
@@ -80,17 +118,9 @@ class PPO:
         last_values = self.actor_critic.evaluate(last_critic_obs).detach()
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
-    # ------------------------------------------------------------------ update
-    def _adapt_lr(self, kl_mean: float):
-        if kl_mean > self.desired_kl * 2.0:
-            self.learning_rate = max(1e-5, self.learning_rate / 1.5)
-        elif kl_mean < self.desired_kl / 2.0 and kl_mean > 0.0:
-            self.learning_rate = min(1e-2, self.learning_rate * 1.5)
-        for param_group in self.optimizer.param_groups:
-            param_group['lr'] = self.learning_rate
-
+    # ------------------------------------------------------------------ generic (autograd) minibatch step
     def losses(self, batch):
-        """Forward of one minibatch: returns (loss, surrogate_loss, value_loss, kl_mean tensor or None)."""
+        """Forward of one minibatch through autograd: (loss, surrogate_loss, value_loss, kl_mean or None)."""
         (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch,
          old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, hid_states_batch, masks_batch) = batch
         ac = self.actor_critic
@@ -121,24 +151,159 @@ class PPO:
         loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_batch.mean()
         return loss, surrogate_loss, value_loss, kl_mean
 
+    def _adaptive(self):
+        return self.desired_kl is not None and self.schedule == 'adaptive'
+
+    def _finish_step(self):
+        """all-reduce (data parallel) -> adaptive lr -> clip + Adam -> re-pack: shared by both paths."""
+        opt = self.optimizer
+        world = 1 if self.dp is None else self.dp.world_size
+        if self.dp is not None:
+            self.dp.allreduce_sum(opt.flat_grads)          # ONE collective: gradients + KL statistic in the tail
+        dev = opt.flat_params.device
+        with torch.cuda.device(dev):
+            if self._adaptive():
+                _lib.check(_lib.lib().snn_lr_adapt(_p(opt.flat_grads[opt.n:]), 1.0 / world, float(self.desired_kl),
+                                                   _p(opt.lr_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                           "snn_lr_adapt")
+        opt.step(max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0, grad_scale=1.0 / world)
+        actor = self.actor_critic.actor
+        layers = actor.snn.linear_layers()
+        actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
+                            [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
+                            actor.decoder.decoder.bias.data)
+
+    def _step_generic(self, batch):
+        loss, surrogate_loss, value_loss, kl_mean = self.losses(batch)
+        opt = self.optimizer
+        opt.zero_grad()
+        loss.backward()
+        if kl_mean is not None:
+            opt.flat_grads[opt.n:].copy_(kl_mean.reshape(1))
+        self._finish_step()
+        self._stats[4] += surrogate_loss.detach()
+        self._stats[5] += value_loss.detach()
+
+    # ------------------------------------------------------------------ fused minibatch step
+    def _fast_supported(self):
+        ac = self.actor_critic
+        return (self.fused and type(ac).__name__ != "ActorCriticRMA" and not ac.is_recurrent
+                and self.optimizer.flat_params.is_cuda and ac.actor.act_dim <= 64)
+
+    def _fast_setup(self, mb):
+        ac = self.actor_critic
+        dev = self.optimizer.flat_params.device
+        A = ac.actor.act_dim
+        st = {
+            "mb": mb,
+            "mu": torch.empty(mb, A, dtype=torch.float32, device=dev),
+            "g_mu": torch.empty(mb, A, dtype=torch.float32, device=dev),
+            "g_value": torch.empty(mb, dtype=torch.float32, device=dev),
+            "trace": torch.empty(ac.actor.engine.trace_bytes(mb), dtype=torch.uint8, device=dev),
+            "scratch": torch.empty(((mb + 255) // 256) * (4 + A) * 4 + 1024, dtype=torch.uint8, device=dev),
+        }
+        layers = ac.actor.snn.linear_layers()
+        st["actor_tensors"] = (ac.actor.encoder.mean, ac.actor.encoder.std, [l.weight for l in layers],
+                               [l.bias for l in layers], ac.actor.decoder.decoder.weight, ac.actor.decoder.decoder.bias)
+        st["grads_out"] = {
+            "enc_mean": ac.actor.encoder.mean.grad, "enc_std": ac.actor.encoder.std.grad,
+            "weights": [l.weight.grad for l in layers], "biases": [l.bias.grad for l in layers],
+            "dec_w": ac.actor.decoder.decoder.weight.grad, "dec_b": ac.actor.decoder.decoder.bias.grad, "obs": None,
+        }
+        self._fast_state = st
+        self._graphs = {}
+
+    def _step_fast(self, f, i):
+        """One fused minibatch step on rows [i*mb, (i+1)*mb) of the permuted fields `f`.  No host sync."""
+        st = self._fast_state
+        mb = st["mb"]
+        sl = slice(i * mb, (i + 1) * mb)
+        ac, opt = self.actor_critic, self.optimizer
+        dev = opt.flat_params.device
+        em, es, ws, bs, dw, db = st["actor_tensors"]
+        opt.zero_grad()
+        eng = ac.actor.engine
+        mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
+                                db.data, train=True, out_mu=st["mu"], out_trace=st["trace"])
+        with torch.enable_grad():
+            value = ac.evaluate(f["critic_obs"][sl])
+        L = _lib.lib()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(L.snn_ppo_head(
+                _p(mu), _p(ac.actor.log_std.data), _p(value.detach()), _p(f["actions"][sl]), _p(f["logp"][sl]),
+                _p(f["adv"][sl]), _p(f["returns"][sl]), _p(f["values"][sl]), _p(f["mu"][sl]), _p(f["sigma"][sl]),
+                mb, ac.actor.act_dim, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
+                1 if self.use_clipped_value_loss else 0, _p(st["g_mu"]), _p(st["g_value"]), _p(ac.actor.log_std.grad),
+                _p(self._stats), _p(st["scratch"]), st["scratch"].numel(), stream), "snn_ppo_head")
+        # KL statistic rides in the tail of the gradient bucket (one all-reduce under data parallelism)
+        opt.flat_grads[opt.n:].copy_(self._stats[2:3])
+        eng.backward(f["obs"][sl], mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws],
+                     [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"])
+        value.backward(st["g_value"].view_as(value))
+        self._finish_step()
+
+    def _run_fast(self, f, i):
+        if not self.use_cuda_graph:
+            return self._step_fast(f, i)
+        if self.dp is not None:
+            # NCCL inside a captured graph is avoided: eager step (still no host sync)
+            return self._step_fast(f, i)
+        g = self._graphs.get(i)
+        if g is None:
+            # warm-up on a side stream (allocator + lazy init), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            snap = self._snapshot()
+            with torch.cuda.stream(s):
+                self._step_fast(f, i)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._step_fast(f, i)
+            except Exception as e:  # noqa: BLE001
+                print(f"[PPO] CUDA graph capture failed ({e}); falling back to eager fused steps")
+                self.use_cuda_graph = False
+                self._restore(snap)
+                return self._step_fast(f, i)
+            self._restore(snap)
+            self._graphs[i] = g
+        g.replay()
+
+    def _snapshot(self):
+        opt = self.optimizer
+        return (opt.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_dev.clone(),
+                opt.lr_dev.clone(), self._stats.clone())
+
+    def _restore(self, snap):
+        opt = self.optimizer
+        opt.flat_params.copy_(snap[0]); opt.exp_avg.copy_(snap[1]); opt.exp_avg_sq.copy_(snap[2])
+        opt.step_dev.copy_(snap[3]); opt.lr_dev.copy_(snap[4]); self._stats.copy_(snap[5])
+        actor = self.actor_critic.actor
+        layers = actor.snn.linear_layers()
+        actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
+                            [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
+                            actor.decoder.decoder.bias.data)
+
+    # ------------------------------------------------------------------ update
     def update(self):
-        generator = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
-        vl_sum = torch.zeros((), device=self.device)
-        sl_sum = torch.zeros((), device=self.device)
-        for batch in generator:
-            loss, surrogate_loss, value_loss, kl_mean = self.losses(batch)
-            if kl_mean is not None:
-                if self.dp is not None:
-                    kl_mean = self.dp.allreduce_sum(kl_mean.reshape(1).double())[0] / self.dp.world_size
-                self._adapt_lr(float(kl_mean))          # host sync: the reference's `if kl_mean > ...` (:145)
-            self.optimizer.zero_grad()
-            loss.backward()
-            if self.dp is not None:
-                self.dp.allreduce_gradients(self.actor_critic)
-            nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
-            self.optimizer.step()
-            vl_sum += value_loss.detach()
-            sl_sum += surrogate_loss.detach()
+        self._stats.zero_()
+        self.optimizer.set_lr(self._lr)
         num_updates = self.num_learning_epochs * self.num_mini_batches
+        if self._fast_supported():
+            f, mb = self.storage.permute_once(self.num_mini_batches)
+            if self._fast_state is None or self._fast_state["mb"] != mb:
+                self._fast_setup(mb)
+            for _ in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    self._run_fast(f, i)
+        else:
+            for batch in self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs):
+                self._step_generic(batch)
+        stats = self._stats.tolist()                       # the one host sync of the update
+        self._lr = self.optimizer.sync_lr_from_device()
         self.storage.clear()
-        return vl_sum.item() / num_updates, sl_sum.item() / num_updates
+        return stats[5] / num_updates, stats[4] / num_updates

@@ -113,6 +113,28 @@ class RolloutStorage:
         crit = self.privileged_observations.flatten(0, 1) if self.privileged_observations is not None else None
         return obs, crit
 
+    def permute_once(self, num_mini_batches):
+        """Draw the update's permutation (reference :151) and gather every field ONCE into persistent,
+        minibatch-contiguous buffers (static addresses: the fused update replays CUDA graphs over them).
+        Returns (dict of [num_mini_batches * mini_batch_size, feat] tensors, mini_batch_size)."""
+        batch_size = self.num_envs * self.num_transitions_per_env
+        mini_batch_size = batch_size // num_mini_batches
+        n = num_mini_batches * mini_batch_size
+        indices = torch.randperm(n, requires_grad=False, device=self.device)
+        src = {"obs": self.observations, "critic_obs": self.privileged_observations, "actions": self.actions,
+               "values": self.values, "returns": self.returns, "logp": self.actions_log_prob,
+               "adv": self.advantages, "mu": self.mu, "sigma": self.sigma, "hist": self.observation_histories}
+        if not hasattr(self, "_perm") or self._perm_n != n:
+            self._perm = {k: torch.empty(n, *v.shape[2:], device=self.device, dtype=v.dtype)
+                          for k, v in src.items() if v is not None}
+            self._perm_n = n
+        for k, buf in self._perm.items():
+            torch.index_select(src[k].flatten(0, 1), 0, indices, out=buf)
+        out = dict(self._perm)
+        if "critic_obs" not in out:
+            out["critic_obs"] = out["obs"]
+        return out, mini_batch_size
+
     def mini_batch_generator(self, num_mini_batches, num_epochs=8):
         """Yields the reference's 11-tuple (:183-184); rows are permuted once, minibatches are contiguous slices."""
         batch_size = self.num_envs * self.num_transitions_per_env

@@ -108,6 +108,29 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values,
             const float* last_values, int64_t S, int64_t N, float gamma, float lam,
             float* returns, float* advantages, int normalize, void* scratch, void* stream);
 
+/* Fused PPO head (AMP/.../algorithms/ppo.py:132-171 with modules/actor_critic.py:398-421): Normal log-prob,
+ * entropy, KL to the rollout policy, clipped surrogate and clipped value loss, forward AND closed-form
+ * gradients in one pass.  Inputs [B,A] / [B] fp32.  Outputs: g_mu [B,A], g_value [B], g_log_std [A] =
+ * d loss / d (mu, value, log_std) for loss = mean(surrogate) + value_coef*mean(value loss) - ent_coef*mean(entropy);
+ * stats[0..3] = surrogate mean, value-loss mean, KL mean, entropy; stats[4..6] accumulate surrogate, value loss,
+ * step count across calls (caller zeroes them).  scratch >= ceil(B/256)*(4+A)*4 bytes. */
+int snn_ppo_head(const float* mu, const float* log_std, const float* value, const float* actions,
+                 const float* old_logp, const float* adv, const float* returns, const float* target_v,
+                 const float* old_mu, const float* old_sigma, int64_t B, int A, float clip, float value_coef,
+                 float ent_coef, int clipped_value, float* g_mu, float* g_value, float* g_log_std, float* stats,
+                 void* scratch, size_t scratch_bytes, void* stream);
+
+/* Adaptive-KL learning-rate rule (ppo.py:145-148) on a DEVICE learning rate: no host round trip.
+ * kl_mean = kl[0] * kl_scale. */
+int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, void* stream);
+
+/* clip_grad_norm_(max_norm) + Adam.step (ppo.py:176-177) over one flat fp32 buffer of n parameters.
+ * grads are first multiplied by grad_scale (1/world after a SUM all-reduce).  lr and step live on the device;
+ * step is incremented by this call.  norm_out (nullable) receives the pre-clip gradient norm.  scratch >= 2 KiB. */
+int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
+                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                  float* norm_out, void* scratch, void* stream);
+
 /* Optional per-launch device timing used by bench.py's roofline: while enabled, every kernel launch is
  * bracketed by CUDA events on its stream.  Categories: 0 = forward scan-GEMM, 1 = backward dX scan-GEMM,
  * 2 = dW GEMM, 3 = all other (SIMT) kernels.  snn_profile_read synchronises on the recorded events and

@@ -16,14 +16,14 @@ def load():
     return dict(np.load(os.path.join(GOLD, f"{PPO_CASE.name}.npz")))
 
 
-def make_alg(pc):
+def make_alg(pc, **kw):
     from fullysnnforleggedrobots_b200 import PPO, ActorCriticCassie
     ac = ActorCriticCassie(pc.obs_dim, pc.obs_dim, pc.act_dim, actor_hidden_dims=list(pc.hidden),
                            critic_hidden_dims=list(pc.critic_hidden), activation="elu", init_noise_std=1.0)
     ac.load_state_dict(make_ppo_state_dict(pc))
     alg = PPO(ac, num_learning_epochs=pc.epochs, num_mini_batches=1, clip_param=0.2, gamma=pc.gamma, lam=pc.lam,
               value_loss_coef=1.0, entropy_coef=pc.entropy_coef, learning_rate=pc.lr, max_grad_norm=1.0,
-              use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cuda")
+              use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cuda", **kw)
     alg.init_storage(pc.num_envs, pc.num_steps, [pc.obs_dim], [None], [pc.act_dim])
     return ac, alg
 
@@ -69,9 +69,10 @@ def fill_storage(alg, pc, g, ro):
     st.step = pc.num_steps
 
 
-def test_gae_and_update_match_reference():
+@pytest.mark.parametrize("mode", ["fused_graph", "fused_eager", "generic"])
+def test_gae_and_update_match_reference(mode):
     pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
-    ac, alg = make_alg(pc)
+    ac, alg = make_alg(pc, fused=mode != "generic", use_cuda_graph=mode == "fused_graph")
     fill_storage(alg, pc, g, ro)
     alg.compute_returns(ro["last_obs"].cuda())
     assert rel_err(alg.storage.returns.cpu(), g["returns"]) < 1e-5
@@ -79,7 +80,9 @@ def test_gae_and_update_match_reference():
     vl, sl = alg.update()
     assert abs(vl / g["mean_value_loss"] - 1) < 1e-4
     assert abs(sl - g["mean_surrogate_loss"]) < 1e-4 * max(1.0, abs(g["mean_surrogate_loss"]))
-    assert abs(alg.learning_rate / g["final_lr"] - 1) < 1e-12
+    assert abs(alg.learning_rate / g["final_lr"] - 1) < 1e-6
+    if mode == "fused_graph":
+        assert alg.use_cuda_graph and len(alg._graphs) == 1      # the graph path really ran
     sd0 = make_ppo_state_dict(pc)
     for k, v in ac.state_dict().items():
         ref = torch.from_numpy(g["final." + k])
@@ -106,3 +109,16 @@ def test_gae_kernel_large_matches_oracle():
     ret, adv = gae(rewards.cuda(), dones.cuda(), values.cuda(), last.cuda(), 0.99, 0.95)
     assert rel_err(ret.cpu(), ret_ref.squeeze(-1)) < 1e-6
     assert rel_err(adv.cpu(), adv_ref.squeeze(-1)) < 1e-5
+
+
+def test_second_update_replays_graph_and_stays_finite():
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    for _ in range(3):
+        fill_storage(alg, pc, g, ro)
+        alg.compute_returns(ro["last_obs"].cuda())
+        vl, sl = alg.update()
+        assert vl == vl and sl == sl
+    assert all(torch.isfinite(p).all() for p in ac.parameters())
+    sd = alg.optimizer.state_dict()
+    assert len(sd["state"]) == len(alg.optimizer.params)
