@@ -246,15 +246,16 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const int top = p.L - 1;
   {
     const LayerPlan& lp = p.layer[top];
-    dim3 grd(lp.NP / 128, Bp / 32);
+    if (lp.NP > 256) return fail(SNN_EINVAL, "output population wider than 256 neurons is not supported by top_scan_kernel");
+    dim3 tblk(lp.NP / 8, 256 / (lp.NP / 8));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<grd, 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<Bp / 128, tblk, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
                                          p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart);
     }
     LAUNCH_CHECK("top_scan_kernel");
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(lp.N + 127) / 128, 128, 0, st>>>(dbpart, Bp / 32, lp.NP, lp.N, g->bias[top]);
+    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, Bp / 128, lp.NP, lp.N, g->bias[top]);
     }
     LAUNCH_CHECK("reduce_rows_kernel(db top)");
   }
@@ -307,7 +308,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         }
         LAUNCH_CHECK("scan_gemm_kernel<DX>");
         { ProfScope prof__(CAT_OTHER, 0.0, st);
-        reduce_rows_kernel<<<(lo.N + 127) / 128, 128, 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
+        reduce_rows_kernel<<<(lo.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
         }
         LAUNCH_CHECK("reduce_rows_kernel(db)");
       } else {
@@ -323,33 +324,33 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const int AP = p.A * p.Pd;
     if (AP + p.A > 1024) return fail(SNN_EINVAL, "act_dim * de_pop too large for dec_bwd_kernel");
-    const int nblk = (Bi + 127) / 128;
+    const int nblk = (Bi + 255) / 256;
     const uint32_t* top_bits = reinterpret_cast<const uint32_t*>(at(trace, p.layer[top].tr_bits));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    dec_bwd_kernel<<<nblk, ((AP + p.A + 31) / 32) * 32, 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
+    dec_bwd_kernel<<<dim3((AP + p.A + 31) / 32, nblk), dim3(32, 8), 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
                                                                p.T, small);
     }
     LAUNCH_CHECK("dec_bwd_kernel");
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(AP + 127) / 128, 128, 0, st>>>(small, nblk, AP + p.A, AP, g->dec_w);
+    reduce_rows_kernel<<<(AP + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, AP + p.A, AP, g->dec_w);
     }
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.A + 127) / 128, 128, 0, st>>>(small + AP, nblk, AP + p.A, p.A, g->dec_b);
+    reduce_rows_kernel<<<(p.A + 31) / 32, dim3(32, 8), 0, st>>>(small + AP, nblk, AP + p.A, p.A, g->dec_b);
     }
     LAUNCH_CHECK("reduce_rows_kernel(dec)");
   }
   // ---- encoder parameter gradients (+ d obs)
   {
-    const int nblk = (Bi + 63) / 64;
+    const int nblk = (Bi + 255) / 256;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    enc_bwd_kernel<<<nblk, 256, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
+    enc_bwd_kernel<<<dim3((p.K0 + 31) / 32, nblk), dim3(32, 8), 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
     }
     LAUNCH_CHECK("enc_bwd_kernel");
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
+    reduce_rows_kernel<<<(p.K0 + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
     }
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.K0 + 127) / 128, 128, 0, st>>>(small + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
+    reduce_rows_kernel<<<(p.K0 + 31) / 32, dim3(32, 8), 0, st>>>(small + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
     }
     LAUNCH_CHECK("reduce_rows_kernel(enc)");
     if (g->obs != nullptr) {

@@ -71,21 +71,44 @@ __device__ __forceinline__ float pop_activation(float x, float mean, float std, 
   return static_cast<float>(exp(static_cast<double>(q)));   // correctly rounded fp32 exp
 }
 
+// fp32 activation for gradient use (no spike decision depends on its last ulp)
+__device__ __forceinline__ float pop_activation_fast(float x, float mean, float std, float eps) {
+  const float d = x - mean;
+  return expf(-0.5f * d * d / (std * std + eps));
+}
+
+__device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin) {
+  float u = 0.f;
+  uint32_t bits = 0;
+  margin = 1.f;
+  for (int t = 0; t < T; ++t) {
+    u = __fadd_rn(u, a);
+    margin = fminf(margin, fabsf(u - 0.999f));
+    if (u > 0.999f) { bits |= 1u << t; u = __fsub_rn(u, 0.999f); }
+  }
+  return bits;
+}
+
 __global__ void encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                               const float* __restrict__ std, int B, int Bpad, int O, int P, int K0, int T,
                               float eps, int64_t R, uint32_t* __restrict__ bits) {
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int b = blockIdx.y * blockDim.y + threadIdx.y;
   if (b >= Bpad) return;
-  float a = 0.f;
-  const bool live = (b < B) && (k < K0);
-  if (live) a = pop_activation(obs[static_cast<size_t>(b) * O + k / P], mean[k], std[k], eps);
-  float u = 0.f;
+  uint32_t sp = 0;
+  if ((b < B) && (k < K0)) {
+    const float x = obs[static_cast<size_t>(b) * O + k / P], mk = mean[k], sk = std[k];
+    // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then exp
+    const float d = __fsub_rn(x, mk);
+    const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), __fadd_rn(__fmul_rn(sk, sk), eps));
+    float margin;
+    sp = regular_spikes(expf(q), T, margin);
+    // expf is good to ~2 ulp; only a membrane within ~1e-5 of the threshold could see the difference:
+    // redo those few with the correctly rounded exp
+    if (margin < 1e-5f) sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+  }
   for (int t = 0; t < T; ++t) {
-    u = __fadd_rn(u, a);
-    const bool s = live && (u > 0.999f);
-    if (s) u = __fsub_rn(u, 0.999f);
-    const uint32_t word = __ballot_sync(0xffffffffu, s);
+    const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
     if (threadIdx.x == 0) bits[static_cast<size_t>(blockIdx.x) * R + static_cast<size_t>(t) * Bpad + b] = word;
   }
 }
@@ -114,101 +137,166 @@ __global__ void decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int 
 // ------------------------------------------------------------------ BPTT of the output population layer
 // g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the
 // recurrence of SURVEY.md §8a.  Writes g_c hi/lo planes as swz64 image and per-block bias partials.
-__global__ void top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu, int dec_tanh,
-                                const float* __restrict__ dec_w, const float* __restrict__ volt, int B, int Bpad,
-                                int A, int P, int NP, int T, int64_t R, uint8_t* __restrict__ g_img, size_t g_plane,
-                                float* __restrict__ db_part) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;   // blockDim.x == 128, NP % 128 == 0
-  const int b0 = blockIdx.y * 32;
-  const bool col_live = n < A * P;
-  const int a = col_live ? n / P : 0;
-  const float w = col_live ? dec_w[n] : 0.f;
-  float dbacc = 0.f;
-  for (int bb = 0; bb < 32; ++bb) {
-    const int b = b0 + bb;
-    if (b >= Bpad) break;
-    float gup = 0.f;
-    const bool live = col_live && b < B;
-    if (live) {
-      float G = g_mu[static_cast<size_t>(b) * A + a];
-      if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
-      gup = __fdiv_rn(G * w, static_cast<float>(T));
+__global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+                                                      int dec_tanh, const float* __restrict__ dec_w,
+                                                      const float* __restrict__ volt, int B, int Bpad, int A, int P,
+                                                      int NP, int T, int64_t R, uint8_t* __restrict__ g_img,
+                                                      size_t g_plane, float* __restrict__ db_part) {
+  // blockDim = (NP/8 column groups [<= 32], 256/(NP/8) rows); block covers 128 rows; grid = (Bpad/128)
+  const int cg = threadIdx.x, ry = threadIdx.y, rows_per_it = blockDim.y;
+  const int n0 = cg * 8;
+  float w[8];
+  int aidx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + j;
+    const bool live = n < A * P;
+    w[j] = live ? dec_w[n] : 0.f;
+    aidx[j] = live ? n / P : -1;
+  }
+  float dbacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dbacc[j] = 0.f;
+  const float invT = static_cast<float>(T);
+  for (int rb = ry; rb < 128; rb += rows_per_it) {
+    const int b = blockIdx.x * 128 + rb;
+    const bool row_live = b < B;
+    float gup[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gup[j] = 0.f;
+      if (row_live && aidx[j] >= 0) {
+        float G = g_mu[static_cast<size_t>(b) * A + aidx[j]];
+        if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + aidx[j]]; G = G * (1.f - m * m); }
+        gup[j] = __fdiv_rn(G * w[j], invT);
+      }
     }
-    float gvn = 0.f, gcn = 0.f;
+    float gvn[8], gcn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
     for (int t = T - 1; t >= 0; --t) {
       const size_t r = static_cast<size_t>(t) * Bpad + b;
-      const float v = live ? volt[r * NP + n] : 0.f;
-      const float gs = gup - gvn * (0.75f * v);
-      const float win = fabsf(__fsub_rn(v, 0.5f)) < 0.5f ? 1.f : 0.f;
-      const float keep = v > 0.5f ? 0.f : 0.75f;
-      const float gv = gs * win + gvn * keep;
-      const float gc = gv + 0.5f * gcn;
-      gvn = gv; gcn = gc;
-      dbacc += gc;
-      const float hi = bf16_round(gc);
-      const float lo = gc - hi;
-      const size_t off = swz64_offset(static_cast<int64_t>(r), n, R);
-      *reinterpret_cast<uint16_t*>(g_img + off) = static_cast<uint16_t>(pack_bf16x2(hi, 0.f) & 0xFFFFu);
-      *reinterpret_cast<uint16_t*>(g_img + g_plane + off) = static_cast<uint16_t>(pack_bf16x2(lo, 0.f) & 0xFFFFu);
+      float v[8];
+      if (row_live) {
+        const float4* src = reinterpret_cast<const float4*>(volt + r * NP + n0);
+        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gs = gup[j] - gvn[j] * (0.75f * v[j]);
+        const float win = fabsf(__fsub_rn(v[j], 0.5f)) < 0.5f ? 1.f : 0.f;
+        const float keep = v[j] > 0.5f ? 0.f : 0.75f;
+        const float gv = gs * win + gvn[j] * keep;
+        const float gc = gv + 0.5f * gcn[j];
+        gvn[j] = gv; gcn[j] = gc;
+        dbacc[j] += gc;
+        hi[j] = bf16_round(gc);
+        lo[j] = gc - hi[j];
+      }
+      const size_t off = swz64_offset(static_cast<int64_t>(r), n0, R);
+      *reinterpret_cast<uint4*>(g_img + off) =
+          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+      *reinterpret_cast<uint4*>(g_img + g_plane + off) =
+          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
     }
   }
-  db_part[static_cast<size_t>(blockIdx.y) * NP + n] = dbacc;
+  // reduce the bias gradient over the block's rows
+  __shared__ float sh[256 * 8];
+  float* mine = sh + (ry * blockDim.x + cg) * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = dbacc[j];
+  __syncthreads();
+  if (ry == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f;
+      for (int y = 0; y < rows_per_it; ++y) acc += sh[(y * blockDim.x + cg) * 8 + j];
+      db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + j] = acc;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ decoder gradients
 // d w_dec[a,p] = sum_b G[b,a] rate[b, aP+p] ; d bias[a] = sum_b G[b,a].  Block = 128 rows; partials out.
-__global__ void dec_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu, int dec_tanh,
-                               const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A, int P, int T,
-                               float* __restrict__ part /* [gridDim.x][A*P + A] */) {
-  const int i = threadIdx.x;
+__global__ void __launch_bounds__(256) dec_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+                                                     int dec_tanh, const uint32_t* __restrict__ bits, int64_t R, int B,
+                                                     int Bpad, int A, int P, int T,
+                                                     float* __restrict__ part /* [gridDim.y][A*P + A] */) {
+  // block (32 columns, 8 row lanes); grid = (ceil((AP + A)/32), ceil(B/256)); each thread walks 32 rows
   const int AP = A * P;
-  if (i >= AP + A) return;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool col_live = i < AP + A;
   const bool is_w = i < AP;
-  const int a = is_w ? i / P : i - AP;
-  const int b0 = blockIdx.x * 128;
+  const int a = col_live ? (is_w ? i / P : i - AP) : 0;
   float acc = 0.f;
-  for (int bb = 0; bb < 128; ++bb) {
-    const int b = b0 + bb;
-    if (b >= B) break;
-    float G = g_mu[static_cast<size_t>(b) * A + a];
-    if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
-    if (is_w) {
-      int cnt = 0;
-      for (int t = 0; t < T; ++t)
-        cnt += (bits[static_cast<size_t>(i >> 5) * R + static_cast<size_t>(t) * Bpad + b] >> (i & 31)) & 1u;
-      acc += G * __fdiv_rn(static_cast<float>(cnt), static_cast<float>(T));
-    } else {
-      acc += G;
+  if (col_live) {
+    for (int j = 0; j < 32; ++j) {
+      const int b = blockIdx.y * 256 + j * 8 + threadIdx.y;
+      if (b >= B) break;
+      float G = g_mu[static_cast<size_t>(b) * A + a];
+      if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
+      if (is_w) {
+        int cnt = 0;
+        for (int t = 0; t < T; ++t)
+          cnt += (bits[static_cast<size_t>(i >> 5) * R + static_cast<size_t>(t) * Bpad + b] >> (i & 31)) & 1u;
+        acc += G * __fdiv_rn(static_cast<float>(cnt), static_cast<float>(T));
+      } else {
+        acc += G;
+      }
     }
   }
-  part[static_cast<size_t>(blockIdx.x) * (AP + A) + i] = acc;
+  __shared__ float sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col_live) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    part[static_cast<size_t>(blockIdx.y) * (AP + A) + i] = t;
+  }
 }
 
 // ------------------------------------------------------------------ encoder gradients
 // From g_a = d loss / d pop_act [Bpad][K0P]:
 //   d mean = sum_b g_a a (x-mean)/var ; d std = sum_b g_a a (x-mean)^2 std / var^2 ; (var = std^2 + eps)
 // Block = 64 rows, threads stride over k; partials [gridDim.x][2][K0].
-__global__ void enc_bwd_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
-                               const float* __restrict__ std, const float* __restrict__ g_a, int B, int O, int P,
-                               int K0, int K0P, float eps, float* __restrict__ part) {
-  const int b0 = blockIdx.x * 64;
-  for (int k = threadIdx.x; k < K0; k += blockDim.x) {
+__global__ void __launch_bounds__(256) enc_bwd_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
+                                                     const float* __restrict__ std, const float* __restrict__ g_a,
+                                                     int B, int O, int P, int K0, int K0P, float eps,
+                                                     float* __restrict__ part /* [gridDim.y][2][K0] */) {
+  // block (32 encoder neurons, 8 row lanes); grid = (ceil(K0/32), ceil(B/256)); each thread walks 32 rows
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const bool live = k < K0;
+  float dm = 0.f, ds = 0.f;
+  if (live) {
     const float mk = mean[k], sk = std[k];
-    const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
+    const float inv_var = 1.f / (sk * sk + eps);
     const int o = k / P;
-    float dm = 0.f, ds = 0.f;
-    for (int bb = 0; bb < 64; ++bb) {
-      const int b = b0 + bb;
-      if (b >= B) break;
-      const float x = obs[static_cast<size_t>(b) * O + o];
-      const float a = pop_activation(x, mk, sk, eps);
-      const float ga = g_a[static_cast<size_t>(b) * K0P + k] * a;
-      const float d = x - mk;
-      dm += ga * d / var;
-      ds += ga * d * d / (var * var) * sk;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int b = blockIdx.y * 256 + j * 8 + threadIdx.y;
+      if (b < B) {
+        const float x = obs[static_cast<size_t>(b) * O + o];
+        const float d = x - mk;
+        const float a = expf(-0.5f * d * d * inv_var);
+        const float ga = g_a[static_cast<size_t>(b) * K0P + k] * a;
+        dm += ga * d * inv_var;
+        ds += ga * d * d * inv_var * inv_var * sk;
+      }
     }
-    part[(static_cast<size_t>(blockIdx.x) * 2) * K0 + k] = dm;
-    part[(static_cast<size_t>(blockIdx.x) * 2 + 1) * K0 + k] = ds;
+  }
+  __shared__ float sh[2][8][33];
+  sh[0][threadIdx.y][threadIdx.x] = dm;
+  sh[1][threadIdx.y][threadIdx.x] = ds;
+  __syncthreads();
+  if (threadIdx.y < 2 && live) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[threadIdx.y][y][threadIdx.x];
+    part[(static_cast<size_t>(blockIdx.y) * 2 + threadIdx.y) * K0 + k] = t;
   }
 }
 
@@ -225,20 +313,27 @@ __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __re
     const int k = o * P + pp;
     const float mk = mean[k], sk = std[k];
     const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
-    const float a = pop_activation(x, mk, sk, eps);
+    const float a = pop_activation_fast(x, mk, sk, eps);
     acc += g_a[static_cast<size_t>(b) * K0P + k] * a * (-(x - mk)) / var;
   }
   d_obs[idx] = acc;
 }
 
-// out[i] = sum_s part[s * stride + i]
-__global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, size_t stride, int n,
-                                   float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[i] = sum_s part[s * stride + i]; block (32 columns, 8 part lanes), fixed summation order
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, int nparts, size_t stride,
+                                                         int n, float* __restrict__ out) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * stride + i];
-  out[i] = acc;
+  if (i < n)
+    for (int s = threadIdx.y; s < nparts; s += 8) acc += part[static_cast<size_t>(s) * stride + i];
+  __shared__ float sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    out[i] = t;
+  }
 }
 
 // ------------------------------------------------------------------ GAE (rollout_storage.py:124-138)

@@ -66,6 +66,8 @@ class PPO:
         self.fused = fused
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
+        self._graph_launches = {}
+        self.replayed_kernel_launches = 0      # kernels of this library launched through CUDA-graph replays
         self._fast_state = None
         dev = self.optimizer.flat_params.device
         self._stats = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -261,6 +263,7 @@ class PPO:
             torch.cuda.synchronize()
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().snn_launch_count()
             try:
                 with torch.cuda.graph(g):
                     self._step_fast(f, i)
@@ -271,7 +274,9 @@ class PPO:
                 return self._step_fast(f, i)
             self._restore(snap)
             self._graphs[i] = g
+            self._graph_launches[i] = int(_lib.lib().snn_launch_count() - n0)
         g.replay()
+        self.replayed_kernel_launches += self._graph_launches[i]
 
     def _snapshot(self):
         opt = self.optimizer
