@@ -30,17 +30,22 @@ struct DwGemmParams {
 
 constexpr int kDwStages = 3;
 constexpr int kDwStageBytes = 65536;   // 32 KiB A (2 planes x 2 n-chunks x 8 KiB) + 32 KiB B (4 k-chunks x 8 KiB)
-constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + 4096 + 256;
+constexpr int kDwBitStages = 8;        // ring of spike-word stages: 8 runs of 64 rows x 4 B
+constexpr int kDwBitStageBytes = 2048;
+constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + kDwBitStages * kDwBitStageBytes + 4096 + 512;
 
 __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint4* lut = reinterpret_cast<uint4*>(ring + kDwStages * kDwStageBytes);
+  uint8_t* bits_ring = ring + kDwStages * kDwStageBytes;
+  uint4* lut = reinterpret_cast<uint4*>(bits_ring + kDwBitStages * kDwBitStageBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + 4096);
   uint64_t* empty = full + kDwStages;
   uint64_t* acc_full = empty + kDwStages;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* full_bits = acc_full + 1;
+  uint64_t* empty_bits = full_bits + kDwBitStages;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + kDwBitStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
@@ -52,6 +57,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 128); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -73,6 +79,15 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     if (lane == 0) {
       uint32_t i = 0;
       for (int rb = rb0; rb < rb1; ++rb, ++i) {
+        {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
+          const uint32_t sbit = i % kDwBitStages;
+          mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
+          mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
+          uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
+          for (int w = 0; w < 2 * nck; ++w)
+            bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
+                     &full_bits[sbit]);
+        }
         const uint32_t s = i % kDwStages;
         mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
         mbar_expect_tx(&full[s], 32768u);
@@ -132,18 +147,21 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     const int sw = row & 7;
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
-      const size_t r = static_cast<size_t>(rb) * 64 + row;
+      const uint32_t sbit = i % kDwBitStages;
+      mbar_wait(&full_bits[sbit], (i / kDwBitStages) & 1);
+      const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + sbit * kDwBitStageBytes);
       uint32_t w[4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int kcl = half + 2 * u;
         if (kcl < nck) {
-          w[2 * u] = __ldg(p.x_bits + static_cast<size_t>(2 * (kc0 + kcl)) * p.R + r);
-          w[2 * u + 1] = __ldg(p.x_bits + static_cast<size_t>(2 * (kc0 + kcl) + 1) * p.R + r);
+          w[2 * u] = wsrc[(2 * kcl) * 64 + row];
+          w[2 * u + 1] = wsrc[(2 * kcl + 1) * 64 + row];
         } else {
           w[2 * u] = 0; w[2 * u + 1] = 0;
         }
       }
+      mbar_arrive(&empty_bits[sbit]);
       const uint32_t s = i % kDwStages;
       mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
       uint8_t* bst = ring + s * kDwStageBytes + 32768;

@@ -38,7 +38,7 @@ struct LayerPlan {
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
   size_t tr_bits;    // trace: output spike words [NP/32][R]
-  size_t tr_volt;    // trace: fp32 voltages [T][Bpad][NP]
+  size_t tr_volt;    // trace: fp32 voltages [T][NP/16][Bpad][16] (column-group-major)
 };
 
 struct SnnPlan {

@@ -5,8 +5,9 @@
 // timestep, fills them with tcgen05.mma over the whole contraction dimension, and then the
 // epilogue warps run the sequential-in-time recurrence with all neuron state in registers:
 //
-//   MODE_FWD     A = spikes of the layer below (bit-packed in HBM, expanded to bf16 0/1 tiles in
-//                shared memory), B = bf16 hi/mid/lo planes of W.   Epilogue = LIF update
+//   MODE_FWD     A = spikes of the layer below (bit-packed in HBM, staged by bulk copies into a
+//                shared-memory ring and expanded there to bf16 0/1 operand tiles), B = bf16
+//                hi/mid/lo planes of W.   Epilogue = LIF update
 //                (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b); v = .75 v (1-s) + c;
 //                s = v > .5.   Emits spike bits (+ fp32 voltage trace when training).
 //   MODE_DX      A = bf16 hi/lo planes of g_c of the layer above, B = hi/lo planes of W^T.
@@ -16,8 +17,13 @@
 //                recurrence (actor_critic.py:50-59,116-119): Gamma_t = g_t + 0.001 Gamma_{t+1}.
 //                Emits g_a = sum_t Gamma_t.
 //
-// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner,
-// warps 4-7 = epilogue (TMEM lane quarter = warp % 4), warps 8-11 = spike-bit expanders (FWD only).
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 4-7 and 8-11 =
+// two epilogue groups (TMEM lane quarter = warp % 4; the groups split the 16-column groups of a
+// chunk), warps 12-15 = spike-bit expanders (FWD only).
+//
+// Voltage traces use a column-group-major layout  v[t][n / 16][Bpad][16]  so that the 32 rows a warp
+// owns are one contiguous 2 KiB run for every 16-column group (coalesced writes here, coalesced
+// reads in the backward epilogue).
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
@@ -45,9 +51,9 @@ struct ScanGemmParams {
   // FWD
   const float* bias;        // [NPout]
   uint32_t* out_bits;       // [NPout/32][R]
-  float* v_out;             // [R][NPout] or null (inference)
+  float* v_out;             // [T][NPout/16][Bpad][16] or null (inference)
   // DX
-  const float* v_in;        // [R][NPout] voltages of the layer whose gradient is produced
+  const float* v_in;        // [T][NPout/16][Bpad][16] voltages of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of swz64 image [NPout/64][R rows]
   size_t g_plane;
   float* db_part;           // [gridDim.x][NPout]
@@ -56,22 +62,25 @@ struct ScanGemmParams {
 };
 
 template <int MODE> struct ScanCfg;
-template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, THREADS = 384; };
-template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, THREADS = 256; };
-template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, THREADS = 256; };
+template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, NBITS = 16, THREADS = 512; };
+template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
+template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
 
 constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (FWD: bias, DX: db); layer widths <= 2048
+constexpr int kBitsStage = 1024;   // one A stage worth of spike words: 2 x (128 rows x 4 B)
 
 template <int MODE>
 __host__ __device__ constexpr size_t scan_gemm_smem_bytes(int NCmax) {
   return 1024 /*align slack*/ + static_cast<size_t>(ScanCfg<MODE>::NA) * ScanCfg<MODE>::A_STAGE +
-         static_cast<size_t>(ScanCfg<MODE>::NB) * ScanCfg<MODE>::BP * NCmax * 128 + 4096 /*LUT*/ + kScanMaxNP * 4 + 256;
+         static_cast<size_t>(ScanCfg<MODE>::NB) * ScanCfg<MODE>::BP * NCmax * 128 + 4096 /*LUT*/ +
+         static_cast<size_t>(ScanCfg<MODE>::NBITS) * kBitsStage + kScanMaxNP * 4 + 512;
 }
 
-// sum over the 32 lanes of x[j] for every j; lane j returns column j's total
-__device__ __forceinline__ float warp_transpose_reduce32(float (&x)[32], int lane) {
+// x[16] per lane (16 columns of this lane's row) -> sum over the warp's 32 rows; lanes 2c and 2c+1 both
+// return column c's total
+__device__ __forceinline__ float warp_transpose_reduce16(float (&x)[16], int lane) {
 #pragma unroll
-  for (int h = 16, n = 32; h >= 1; h >>= 1, n >>= 1) {
+  for (int h = 16, n = 16; h >= 2; h >>= 1, n >>= 1) {
     const bool up = (lane & h) != 0;
 #pragma unroll
     for (int i = 0; i < n / 2; ++i) {
@@ -80,19 +89,21 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&x)[32], int lan
       x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
     }
   }
-  return x[0];
+  return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
   using C = ScanCfg<MODE>;
+  constexpr uint32_t NBM = C::NBITS > 0 ? C::NBITS : 1;   // modulus of the spike-word ring (unused in DX modes)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage = C::BP * p.NCmax * 128;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + C::NA * C::A_STAGE;
   uint4* lut = reinterpret_cast<uint4*>(b_ring + C::NB * b_stage);
-  float* s_col = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(lut) + 4096);
+  uint8_t* bits_ring = reinterpret_cast<uint8_t*>(lut) + 4096;
+  float* s_col = reinterpret_cast<float*>(bits_ring + C::NBITS * kBitsStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_col + kScanMaxNP);
   uint64_t* full_a = bars;                 // [NA]
   uint64_t* empty_a = full_a + C::NA;      // [NA]
@@ -100,7 +111,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   uint64_t* empty_b = full_b + C::NB;      // [NB]
   uint64_t* acc_full = empty_b + C::NB;
   uint64_t* acc_empty = acc_full + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* full_bits = acc_empty + 1;     // [NBITS]
+  uint64_t* empty_bits = full_bits + C::NBITS;   // [NBITS]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + C::NBITS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
@@ -111,8 +124,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       mbar_init(&empty_a[s], 1);
     }
     for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 128); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, 256);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -152,17 +166,24 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
                      p.b_img + pl * p.b_plane + (static_cast<size_t>(kc) * p.NPout + n0) * 128,
                      static_cast<uint32_t>(ncw * 128), &full_b[sb]);
           ++ib;
-          if (MODE != MODE_FWD) {
-            for (int t = 0; t < p.T; ++t) {
+          for (int t = 0; t < p.T; ++t, ++ia) {
+            const size_t row0 = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128;
+            if (MODE == MODE_FWD) {
+              // spike words of this A stage: two 512-byte runs (128 rows x one 32-column word each)
+              const uint32_t s = ia % NBM;
+              mbar_wait(&empty_bits[s], ((ia / NBM) & 1) ^ 1);
+              mbar_expect_tx(&full_bits[s], static_cast<uint32_t>(kBitsStage));
+              uint8_t* dst = bits_ring + s * kBitsStage;
+              bulk_g2s(dst, p.a_bits + static_cast<size_t>(2 * kc) * p.R + row0, 512u, &full_bits[s]);
+              bulk_g2s(dst + 512, p.a_bits + static_cast<size_t>(2 * kc + 1) * p.R + row0, 512u, &full_bits[s]);
+            } else {
               const uint32_t sa = ia % C::NA;
               mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
               mbar_expect_tx(&full_a[sa], 32768u);
-              const size_t row0 = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128;
               for (int pl = 0; pl < 2; ++pl)
                 bulk_g2s(a_ring + sa * C::A_STAGE + pl * 16384,
                          p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.R + row0) * 128, 16384u,
                          &full_a[sa]);
-              ++ia;
             }
           }
         }
@@ -221,9 +242,10 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         umma_commit(acc_full);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================================================== epilogue: the time scan
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================== epilogue: the time scan (two groups of 4 warps)
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;          // 0: even 16-column groups, 1: odd ones
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t it = 0;
@@ -235,22 +257,24 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       const bool valid = b < p.B;
       mbar_wait(acc_full, it & 1);
       tc_fence_after_sync();
-      if (MODE == MODE_FWD) {
-        for (int g = 0; g < ncw / 32; ++g) {
-          float cur[32], vol[32];
+      for (int g = half; g < ncw / 16; g += 2) {
+        const int col0 = n0 + g * 16;
+        const uint32_t t_col = t_lane + static_cast<uint32_t>(g * 16);
+        if (MODE == MODE_FWD) {
+          float cur[16], vol[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
+          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
           uint32_t sprev = 0;
-          const int col0 = n0 + g * 32;
+          uint32_t x[16], xn[16];
+          tmem_ld16(t_col, x);
+          tmem_ld_wait();
+          uint16_t* bits16 = reinterpret_cast<uint16_t*>(p.out_bits) + (static_cast<size_t>(col0 >> 5) * p.R) * 2 + ((col0 >> 4) & 1);
           for (int t = 0; t < p.T; ++t) {
-            uint32_t x0[16], x1[16];
-            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32), x0);
-            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32 + 16), x1);
-            tmem_ld_wait();
+            if (t + 1 < p.T) tmem_ld16(t_col + static_cast<uint32_t>((t + 1) * p.NCmax), xn);
             uint32_t word = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float syn = __fadd_rn(__uint_as_float(j < 16 ? x0[j] : x1[j - 16]), s_col[col0 + j]);
+            for (int j = 0; j < 16; ++j) {
+              const float syn = __fadd_rn(__uint_as_float(x[j]), s_col[col0 + j]);
               const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
               const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
               cur[j] = cj;
@@ -258,84 +282,83 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
               word |= (vj > 0.5f ? 1u : 0u) << j;
             }
             const size_t r = static_cast<size_t>(t) * p.Bpad + b;
-            p.out_bits[static_cast<size_t>(col0 >> 5) * p.R + r] = valid ? word : 0u;
+            bits16[r * 2] = static_cast<uint16_t>(valid ? word : 0u);
             if (p.v_out != nullptr && valid) {
-              float4* dst = reinterpret_cast<float4*>(p.v_out + r * p.NPout + col0);
+              float4* dst = reinterpret_cast<float4*>(
+                  p.v_out + ((static_cast<size_t>(t) * (p.NPout >> 4) + (col0 >> 4)) * p.Bpad + b) * 16);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
             }
             sprev = word;
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = xn[j];
           }
-        }
-      } else if (MODE == MODE_DX) {
-        for (int g = 0; g < ncw / 32; ++g) {
-          float dbacc[32];
+        } else if (MODE == MODE_DX) {
+          float gvn[16], gcn[16], dbacc[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dbacc[j] = 0.f;
+          for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; dbacc[j] = 0.f; }
+          const float* vbase = p.v_in + (static_cast<size_t>(col0 >> 4) * p.Bpad + b) * 16;
+          const size_t vstep = static_cast<size_t>(p.NPout >> 4) * p.Bpad * 16;     // floats between timesteps
+          float4 vn[4];
+          if (valid) {
+            const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(p.T - 1) * vstep);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col0 = n0 + g * 32 + h * 16;
-            float gvn[16], gcn[16];
+            for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
+          }
+          for (int t = p.T - 1; t >= 0; --t) {
+            uint32_t x[16];
+            tmem_ld16(t_col + static_cast<uint32_t>(t * p.NCmax), x);
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
-            for (int t = p.T - 1; t >= 0; --t) {
-              uint32_t x[16];
-              tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 32 + h * 16), x);
-              const size_t r = static_cast<size_t>(t) * p.Bpad + b;
-              float v[16];
-              if (valid) {
-                const float4* src = reinterpret_cast<const float4*>(p.v_in + r * p.NPout + col0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 f = __ldg(src + j);
-                  v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
-              }
-              tmem_ld_wait();
-              float hi[16], lo[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float gup = valid ? __uint_as_float(x[j]) : 0.f;
-                const float vj = v[j];
-                const float gs = gup - gvn[j] * (0.75f * vj);
-                const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
-                const float keep = vj > 0.5f ? 0.f : 0.75f;
-                const float gv = gs * win + gvn[j] * keep;
-                const float gc = gv + 0.5f * gcn[j];
-                gvn[j] = gv;
-                gcn[j] = gc;
-                dbacc[h * 16 + j] += gc;
-                hi[j] = bf16_round(gc);
-                lo[j] = gc - hi[j];
-              }
-              const size_t base = static_cast<size_t>(col0 >> 6) * p.R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
-              const int p0 = (col0 & 63) >> 3;
-              const int sw = static_cast<int>(r & 7);
-              uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-              uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-              uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-              uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
-              *reinterpret_cast<uint4*>(p.g_img + base + ((p0 ^ sw) << 4)) = h0;
-              *reinterpret_cast<uint4*>(p.g_img + base + (((p0 + 1) ^ sw) << 4)) = h1;
-              *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + ((p0 ^ sw) << 4)) = l0;
-              *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + (((p0 + 1) ^ sw) << 4)) = l1;
+            for (int j = 0; j < 4; ++j) {
+              v[4 * j] = valid ? vn[j].x : 0.f; v[4 * j + 1] = valid ? vn[j].y : 0.f;
+              v[4 * j + 2] = valid ? vn[j].z : 0.f; v[4 * j + 3] = valid ? vn[j].w : 0.f;
             }
+            if (valid && t > 0) {   // prefetch the next (earlier) timestep's voltages
+              const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
+            }
+            tmem_ld_wait();
+            const size_t r = static_cast<size_t>(t) * p.Bpad + b;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float gup = valid ? __uint_as_float(x[j]) : 0.f;
+              const float vj = v[j];
+              const float gs = gup - gvn[j] * (0.75f * vj);
+              const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
+              const float keep = vj > 0.5f ? 0.f : 0.75f;
+              const float gv = gs * win + gvn[j] * keep;
+              const float gc = gv + 0.5f * gcn[j];
+              gvn[j] = gv;
+              gcn[j] = gc;
+              dbacc[j] += gc;
+              hi[j] = bf16_round(gc);
+              lo[j] = gc - hi[j];
+            }
+            const size_t base = static_cast<size_t>(col0 >> 6) * p.R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+            const int p0 = (col0 & 63) >> 3;
+            const int sw = static_cast<int>(r & 7);
+            const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+            const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+            const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+            *reinterpret_cast<uint4*>(p.g_img + base + ((p0 ^ sw) << 4)) = h0;
+            *reinterpret_cast<uint4*>(p.g_img + base + (((p0 + 1) ^ sw) << 4)) = h1;
+            *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + ((p0 ^ sw) << 4)) = l0;
+            *reinterpret_cast<uint4*>(p.g_img + p.g_plane + base + (((p0 + 1) ^ sw) << 4)) = l1;
           }
-          const float tot = warp_transpose_reduce32(dbacc, lane);
-          atomicAdd(&s_col[n0 + g * 32 + lane], tot);
-        }
-      } else {   // MODE_DX_ENC
-        for (int g = 0; g < ncw / 16; ++g) {
-          const int col0 = n0 + g * 16;
+          const float tot = warp_transpose_reduce16(dbacc, lane);
+          if ((lane & 1) == 0) atomicAdd(&s_col[col0 + (lane >> 1)], tot);
+        } else {   // MODE_DX_ENC
           float gam[16], ga[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { gam[j] = 0.f; ga[j] = 0.f; }
           for (int t = p.T - 1; t >= 0; --t) {
             uint32_t x[16];
-            tmem_ld16(t_lane + static_cast<uint32_t>(t * p.NCmax + g * 16), x);
+            tmem_ld16(t_col + static_cast<uint32_t>(t * p.NCmax), x);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -353,31 +376,29 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       tc_fence_before_sync();
       mbar_arrive(acc_empty);
     }
-  } else if (MODE == MODE_FWD && warp >= 8) {
-    // ===================================================== spike-bit expanders
-    const int e = tid - 256;   // row inside the tile
+  } else if (MODE == MODE_FWD && warp >= 12) {
+    // ===================================================== spike-bit expanders (smem words -> bf16 A tile)
+    const int e = tid - 384;   // row inside the tile
     uint32_t ia = 0;
     const int sw = e & 7;
     uint8_t* const row_base = a_ring + (e >> 3) * 1024 + sw * 128;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      const int m = item / p.nchunks;
-      for (int kc = 0; kc < KC; ++kc) {
-        for (int t = 0; t < p.T; ++t) {
-          const size_t r = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128 + e;
-          const uint32_t w0 = __ldg(p.a_bits + static_cast<size_t>(2 * kc) * p.R + r);
-          const uint32_t w1 = __ldg(p.a_bits + static_cast<size_t>(2 * kc + 1) * p.R + r);
-          const uint32_t sa = ia % C::NA;
-          mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
-          uint8_t* dst = row_base + sa * C::A_STAGE;
+      for (int i = 0; i < KC * p.T; ++i, ++ia) {
+        const uint32_t s = ia % NBM;
+        mbar_wait(&full_bits[s], (ia / NBM) & 1);
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + s * kBitsStage);
+        const uint32_t w0 = wsrc[e], w1 = wsrc[128 + e];
+        mbar_arrive(&empty_bits[s]);
+        const uint32_t sa = ia % C::NA;
+        mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
+        uint8_t* dst = row_base + sa * C::A_STAGE;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t byte = ((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFFu;
-            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(&full_a[sa]);
-          ++ia;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t byte = ((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFFu;
+          *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
         }
+        fence_proxy_async_smem();
+        mbar_arrive(&full_a[sa]);
       }
     }
   }

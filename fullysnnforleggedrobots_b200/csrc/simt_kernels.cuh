@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
       const size_t r = static_cast<size_t>(t) * Bpad + b;
       float v[8];
       if (row_live) {
-        const float4* src = reinterpret_cast<const float4*>(volt + r * NP + n0);
+        const float4* src = reinterpret_cast<const float4*>(
+            volt + ((static_cast<size_t>(t) * (NP >> 4) + (n0 >> 4)) * Bpad + b) * 16 + (n0 & 15));
         const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
         v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
       } else {

@@ -180,7 +180,9 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[6 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            v = raw[voff: voff + R * NP * 4].view(torch.float32).reshape(T, Bpad, NP)
+            # voltage trace layout: [t][n / 16][Bpad][16]
+            v = raw[voff: voff + R * NP * 4].view(torch.float32).reshape(T, NP // 16, Bpad, 16)
+            v = v.permute(0, 2, 1, 3).reshape(T, Bpad, NP)
             res["volt"].append(v[:, :B, :self.dims[l + 1]].contiguous())
         return res
 
