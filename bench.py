@@ -261,8 +261,11 @@ def run_ours(args):
     step_resident()
     L.snn_profile_enable(1)
     ms_prof_total = timed(step_resident, args.steps)
-    pms, pfl, pln = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int64 * 4)()
-    L.snn_profile_read(pms, pfl, pln)
+    pms32, pfl32, pln32 = (C.c_double * 32)(), (C.c_double * 32)(), (C.c_int64 * 32)()
+    L.snn_profile_read(pms32, pfl32, pln32)
+    pms = [sum(pms32[k + 4 * l] for l in range(8)) for k in range(4)]
+    pfl = [sum(pfl32[k + 4 * l] for l in range(8)) for k in range(4)]
+    pln = [sum(pln32[k + 4 * l] for l in range(8)) for k in range(4)]
     L.snn_profile_enable(0)
     alg.use_cuda_graph = graph_flag
 

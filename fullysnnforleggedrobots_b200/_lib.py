@@ -96,6 +96,7 @@ _SIGS = {
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "snn_launch_count": (C.c_int64, []),
+    "snn_debug_set_cycle_buffer": (C.c_int, [C.c_void_p]),
     "snn_debug_trace_layout": (C.c_int, [C.POINTER(SnnDesc), C.c_int64, C.POINTER(C.c_int64), C.c_int]),
 }
 

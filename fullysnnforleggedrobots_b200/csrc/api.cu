@@ -1,6 +1,7 @@
 // api.cu — C-ABI entry points declared in include/snn_b200.h.  Host-side launch sequencing only:
 // every buffer is caller-owned, nothing here allocates device memory or synchronises.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,15 +35,15 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
   } while (0)
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream, read back later
-enum { CAT_FWD = 0, CAT_DX = 1, CAT_DW = 2, CAT_OTHER = 3, NUM_CAT = 4 };
+enum { CAT_FWD = 0, CAT_DX = 1, CAT_DW = 2, CAT_OTHER = 3, NUM_KIND = 4, NUM_CAT = 32 };   // slot = kind + 4 * layer
 struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
 struct Profiler {
   bool on = false;
   std::vector<ProfRec> recs;
   std::vector<cudaEvent_t> pool;
-  double ms[NUM_CAT] = {0, 0, 0, 0};
-  double flops[NUM_CAT] = {0, 0, 0, 0};
-  long long launches[NUM_CAT] = {0, 0, 0, 0};
+  double ms[NUM_CAT] = {};
+  double flops[NUM_CAT] = {};
+  long long launches[NUM_CAT] = {};
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -99,6 +100,14 @@ int device_ready(int* num_sms) {
   return SNN_OK;
 }
 
+unsigned long long* g_dbg_out = nullptr;   // set by snn_debug_set_cycle_buffer (tools only)
+
+int debug_mask() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("SNN_DBG"); m = e ? atoi(e) : 0; }
+  return m;
+}
+
 int plan_for(const SnnDesc* d, int64_t B, int num_sms, SnnPlan* p) {
   if (d == nullptr) return fail(SNN_EINVAL, "null descriptor");
   if (make_plan(*d, B, num_sms, p) != SNN_OK) return fail(SNN_EINVAL, "unsupported SnnDesc (dims, spike_ts 1..16, planes 1..3)");
@@ -132,11 +141,13 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.B = static_cast<int>(B); q.Bpad = static_cast<int>(p.Bpad); q.R = p.R;
     q.nchunks = (lp.NP + p.NCmax - 1) / p.NCmax;
     q.nitems = static_cast<int>(p.Bpad / 128) * q.nchunks;
+    q.dbg = debug_mask();
+    q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(l) * 148 * 16 : nullptr;
     q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
     q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = q.nitems < num_sms ? q.nitems : num_sms;
-    { ProfScope prof__(CAT_FWD, 2.0 * B * lp.K * lp.N * p.T, st);
+    { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
     scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(p.NCmax), st>>>(q);
     }
     LAUNCH_CHECK("scan_gemm_kernel<FWD>");
@@ -278,7 +289,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
       q.partial = partial;
-      { ProfScope prof__(CAT_DW, 2.0 * B * lp.K * lp.N * p.T, st);
+      { ProfScope prof__(CAT_DW + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
       dw_gemm_kernel<<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }
       LAUNCH_CHECK("dw_gemm_kernel");
@@ -291,6 +302,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     {   // dX_l + scan of the layer below (or of the encoder)
       ScanGemmParams q{};
       q.a_img = G; q.a_plane = Gplane;
+      q.dbg = debug_mask();
+      q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(8 + l) * 148 * 16 : nullptr;
       q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
       q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = p.NCmax; q.T = p.T;
       q.B = Bi; q.Bpad = Bp; q.R = p.R;
@@ -303,7 +316,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         q.g_img = at(workspace, p.ws_g[slot ^ 1]);
         q.g_plane = p.ws_g_plane[slot ^ 1];
         q.db_part = dbpart;
-        { ProfScope prof__(CAT_DX, 2.0 * B * lp.K * lp.N * p.T, st);
+        { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(p.NCmax), st>>>(q);
         }
         LAUNCH_CHECK("scan_gemm_kernel<DX>");
@@ -313,7 +326,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         LAUNCH_CHECK("reduce_rows_kernel(db)");
       } else {
         q.g_a = g_a;
-        { ProfScope prof__(CAT_DX, 2.0 * B * lp.K * lp.N * p.T, st);
+        { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX_ENC><<<grid, ScanCfg<MODE_DX_ENC>::THREADS, scan_gemm_smem_bytes<MODE_DX_ENC>(p.NCmax), st>>>(q);
         }
         LAUNCH_CHECK("scan_gemm_kernel<DX_ENC>");
@@ -477,6 +490,8 @@ int snn_profile_read(double* ms, double* flops, int64_t* launches) {
 }
 
 int64_t snn_launch_count(void) { return g_launch_count; }
+
+int snn_debug_set_cycle_buffer(void* buf) { g_dbg_out = static_cast<unsigned long long*>(buf); return SNN_OK; }
 
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out) {
   SnnPlan p;

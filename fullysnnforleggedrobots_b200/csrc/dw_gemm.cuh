@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const int rb0 = split * per, rb1 = min(p.rblocks, rb0 + per);
 
   if (tid == 0) {
-    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 129); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 128); }
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -76,20 +76,22 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t i = 0;
-      for (int rb = rb0; rb < rb1; ++rb, ++i) {
-        {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
-          const uint32_t sbit = i % kDwBitStages;
-          mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
-          mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
-          uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
-          for (int w = 0; w < 2 * nck; ++w)
-            bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
-                     &full_bits[sbit]);
-        }
-        const uint32_t s = i % kDwStages;
-        mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
+    // producer: warp-uniform loop, one elected lane issues the bulk copies
+    uint32_t i = 0;
+    for (int rb = rb0; rb < rb1; ++rb, ++i) {
+      const uint32_t sbit = i % kDwBitStages;
+      mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
+      if (elect_one()) {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
+        mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
+        uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
+        for (int w = 0; w < 2 * nck; ++w)
+          bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
+                   &full_bits[sbit]);
+      }
+      __syncwarp();
+      const uint32_t s = i % kDwStages;
+      mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], 32768u);
         uint8_t* dst = ring + s * kDwStageBytes;
         for (int pl = 0; pl < 2; ++pl)
@@ -98,87 +100,92 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
                      p.g_img + pl * p.g_plane + (static_cast<size_t>(mt * 2 + nc) * p.R + static_cast<size_t>(rb) * 64) * 128,
                      8192u, &full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), 1, 1);
-      uint32_t i = 0;
-      uint32_t acc = 0;
-      for (int rb = rb0; rb < rb1; ++rb, ++i) {
-        const uint32_t s = i % kDwStages;
-        mbar_wait(&full[s], (i / kDwStages) & 1);
-        tc_fence_after_sync();
-        const uint32_t a_base = smem_u32(ring + s * kDwStageBytes);
-        const uint32_t b_base = a_base + 32768;
+    // MMA issuer: warp-uniform loop, one elected lane issues
+    const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), 1, 1);
+    const uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t ring_lo = smem_desc_lo(smem_u32(ring), 8192);
+    uint32_t i = 0;
+    for (int rb = rb0; rb < rb1; ++rb, ++i) {
+      const uint32_t s = i % kDwStages;
+      mbar_wait(&full[s], (i / kDwStages) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_lo = ring_lo + s * (kDwStageBytes >> 4);
+        const uint32_t b_lo = a_lo + (32768 >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
-            umma_bf16(tmem_base, make_smem_desc(a_base + pl * 16384 + k16 * 2048, 8192, 1024),
-                      make_smem_desc(b_base + k16 * 2048, 8192, 1024), idesc, acc);
-            acc = 1u;
-          }
+          for (int pl = 0; pl < 2; ++pl)
+            umma_bf16_lohi(tmem_base, a_lo + pl * (16384 >> 4) + k16 * (2048 >> 4), dhi, b_lo + k16 * (2048 >> 4), dhi, idesc,
+                           (i > 0 || k16 > 0 || pl > 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);
+        if (rb == rb1 - 1) umma_commit(acc_full);
       }
-      umma_commit(acc_full);
+      __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    float* out = p.partial + (static_cast<size_t>(blockIdx.x) * 128 + row) * 256;
-    mbar_wait(acc_full, 0);
-    tc_fence_after_sync();
-    const bool any = rb1 > rb0;
-    for (int g = 0; g < nck * 4; ++g) {
-      uint32_t x[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 16), x);
-      tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(out + g * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = any ? make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]), __uint_as_float(x[4 * j + 2]),
-                                   __uint_as_float(x[4 * j + 3]))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  } else if (warp >= 8) {
-    const int e = tid - 256;
-    const int row = e & 63, half = e >> 6;
-    const int sw = row & 7;
+    if (rb1 <= rb0 && elect_one()) umma_commit(acc_full);
+  } else if (warp >= 4) {
+    // spike-bit expanders: warp ew owns every eighth stage and expands all of it (64 rows x nck k-chunks);
+    // warps 4-7 also run the epilogue once their stages are done
+    const int ew = warp - 4;
+    const int sw = lane & 7;
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
+      if (static_cast<int>(i & 7) != ew) continue;
       const uint32_t sbit = i % kDwBitStages;
       mbar_wait(&full_bits[sbit], (i / kDwBitStages) & 1);
       const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + sbit * kDwBitStageBytes);
-      uint32_t w[4];
+      uint32_t w[2][8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kcl = half + 2 * u;
-        if (kcl < nck) {
-          w[2 * u] = wsrc[(2 * kcl) * 64 + row];
-          w[2 * u + 1] = wsrc[(2 * kcl + 1) * 64 + row];
-        } else {
-          w[2 * u] = 0; w[2 * u + 1] = 0;
-        }
-      }
-      mbar_arrive(&empty_bits[sbit]);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[h][u] = (u < 2 * nck) ? wsrc[u * 64 + lane + 32 * h] : 0u;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bits[sbit]);
       const uint32_t s = i % kDwStages;
       mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
       uint8_t* bst = ring + s * kDwStageBytes + 32768;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kcl = half + 2 * u;
-        if (kcl < nck) {
-          uint8_t* dst = bst + kcl * 8192 + (row >> 3) * 1024 + sw * 128;
+      for (int h = 0; h < 2; ++h) {
+        const int row = lane + 32 * h;
+        uint8_t* rbase = bst + (row >> 3) * 1024 + sw * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t byte = ((j < 4 ? w[2 * u] : w[2 * u + 1]) >> ((j & 3) * 8)) & 0xFFu;
-            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
+        for (int kcl = 0; kcl < 4; ++kcl) {
+          if (kcl < nck) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t byte = ((j < 4 ? w[h][2 * kcl] : w[h][2 * kcl + 1]) >> ((j & 3) * 8)) & 0xFFu;
+              *reinterpret_cast<uint4*>(rbase + kcl * 8192 + ((j ^ sw) << 4)) = lut[byte];
+            }
           }
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    if (warp < 8) {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      float* out = p.partial + (static_cast<size_t>(blockIdx.x) * 128 + row) * 256;
+      mbar_wait(acc_full, 0);
+      tc_fence_after_sync();
+      const bool any = rb1 > rb0;
+      for (int g = 0; g < nck * 4; ++g) {
+        uint32_t x[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 16), x);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(out + g * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = any ? make_float4(__uint_as_float(x[4 * j]), __uint_as_float(x[4 * j + 1]), __uint_as_float(x[4 * j + 2]),
+                                     __uint_as_float(x[4 * j + 3]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   tc_fence_before_sync();

@@ -48,6 +48,8 @@ struct ScanGemmParams {
   int B, Bpad;
   int64_t R;                // T * Bpad
   int nitems, nchunks;
+  unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
+  int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand
   // FWD
   const float* bias;        // [NPout]
   uint32_t* out_bits;       // [NPout/32][R]
@@ -92,6 +94,13 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&x)[16], int lan
   return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
 }
 
+#define SNN_TWAIT(bar, par, slot)                                   \
+  do {                                                              \
+    const long long t0__ = clock64();                               \
+    mbar_wait(bar, par);                                            \
+    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
+  } while (0)
+
 template <int MODE>
 __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
   using C = ScanCfg<MODE>;
@@ -117,14 +126,16 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
+  unsigned long long wcyc[3] = {0, 0, 0};
+  const long long t_start = clock64();
 
   if (tid == 0) {
     for (int s = 0; s < C::NA; ++s) {
-      mbar_init(&full_a[s], MODE == MODE_FWD ? 128 : 1);
+      mbar_init(&full_a[s], 1);
       mbar_init(&empty_a[s], 1);
     }
     for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 128); }
+    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 256);
     fence_mbar_init();
@@ -150,8 +161,8 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===================================================== producer (one lane)
-    if (lane == 0) {
+    // ===================================================== producer (warp-uniform loop, one elected lane issues)
+    {
       uint32_t ib = 0, ia = 0;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         const int m = item / p.nchunks, c = item - m * p.nchunks;
@@ -159,87 +170,109 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         const int ncw = min(p.NCmax, p.NPout - n0);
         for (int kc = 0; kc < KC; ++kc) {
           const uint32_t sb = ib % C::NB;
-          mbar_wait(&empty_b[sb], ((ib / C::NB) & 1) ^ 1);
-          mbar_expect_tx(&full_b[sb], static_cast<uint32_t>(p.b_planes * ncw * 128));
-          for (int pl = 0; pl < p.b_planes; ++pl)
-            bulk_g2s(b_ring + sb * b_stage + pl * p.NCmax * 128,
-                     p.b_img + pl * p.b_plane + (static_cast<size_t>(kc) * p.NPout + n0) * 128,
-                     static_cast<uint32_t>(ncw * 128), &full_b[sb]);
+          SNN_TWAIT(&empty_b[sb], ((ib / C::NB) & 1) ^ 1, 0);
+          if (elect_one()) {
+            mbar_expect_tx(&full_b[sb], static_cast<uint32_t>(p.b_planes * ncw * 128));
+            for (int pl = 0; pl < p.b_planes; ++pl)
+              bulk_g2s(b_ring + sb * b_stage + pl * p.NCmax * 128,
+                       p.b_img + pl * p.b_plane + (static_cast<size_t>(kc) * p.NPout + n0) * 128,
+                       static_cast<uint32_t>(ncw * 128), &full_b[sb]);
+          }
+          __syncwarp();
           ++ib;
           for (int t = 0; t < p.T; ++t, ++ia) {
             const size_t row0 = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128;
             if (MODE == MODE_FWD) {
               // spike words of this A stage: two 512-byte runs (128 rows x one 32-column word each)
               const uint32_t s = ia % NBM;
-              mbar_wait(&empty_bits[s], ((ia / NBM) & 1) ^ 1);
-              mbar_expect_tx(&full_bits[s], static_cast<uint32_t>(kBitsStage));
-              uint8_t* dst = bits_ring + s * kBitsStage;
-              bulk_g2s(dst, p.a_bits + static_cast<size_t>(2 * kc) * p.R + row0, 512u, &full_bits[s]);
-              bulk_g2s(dst + 512, p.a_bits + static_cast<size_t>(2 * kc + 1) * p.R + row0, 512u, &full_bits[s]);
+              SNN_TWAIT(&empty_bits[s], ((ia / NBM) & 1) ^ 1, 1);
+              if (elect_one()) {
+                if (p.dbg & 8) {
+                  mbar_arrive(&full_bits[s]);
+                } else {
+                  mbar_expect_tx(&full_bits[s], static_cast<uint32_t>(kBitsStage));
+                  uint8_t* dst = bits_ring + s * kBitsStage;
+                  bulk_g2s(dst, p.a_bits + static_cast<size_t>(2 * kc) * p.R + row0, 512u, &full_bits[s]);
+                  bulk_g2s(dst + 512, p.a_bits + static_cast<size_t>(2 * kc + 1) * p.R + row0, 512u, &full_bits[s]);
+                }
+              }
+              __syncwarp();
             } else {
               const uint32_t sa = ia % C::NA;
-              mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
-              mbar_expect_tx(&full_a[sa], 32768u);
-              for (int pl = 0; pl < 2; ++pl)
-                bulk_g2s(a_ring + sa * C::A_STAGE + pl * 16384,
-                         p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.R + row0) * 128, 16384u,
-                         &full_a[sa]);
+              SNN_TWAIT(&empty_a[sa], ((ia / C::NA) & 1) ^ 1, 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_a[sa], 32768u);
+                for (int pl = 0; pl < 2; ++pl)
+                  bulk_g2s(a_ring + sa * C::A_STAGE + pl * 16384,
+                           p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.R + row0) * 128, 16384u,
+                           &full_a[sa]);
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       uint32_t ib = 0, ia = 0, it = 0;
+      const uint32_t dhi = smem_desc_hi(1024);
+      const uint32_t a_ring_lo = smem_desc_lo(smem_u32(a_ring), 16);
+      const uint32_t b_ring_lo = smem_desc_lo(smem_u32(b_ring), 16);
+      const uint32_t b_plane_lo = static_cast<uint32_t>(p.NCmax * 128) >> 4;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
         const int c = item % p.nchunks;
         const int n0 = c * p.NCmax;
         const int ncw = min(p.NCmax, p.NPout - n0);
         const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncw), 0, 0);
-        mbar_wait(acc_empty, (it & 1) ^ 1);
+        SNN_TWAIT(acc_empty, (it & 1) ^ 1, 0);
         tc_fence_after_sync();
         for (int kc = 0; kc < KC; ++kc) {
           const uint32_t sb = ib % C::NB;
-          mbar_wait(&full_b[sb], (ib / C::NB) & 1);
-          const uint32_t b_base = smem_u32(b_ring + sb * b_stage);
+          SNN_TWAIT(&full_b[sb], (ib / C::NB) & 1, 1);
+          const uint32_t b_lo = b_ring_lo + sb * (static_cast<uint32_t>(b_stage) >> 4);
           for (int t = 0; t < p.T; ++t) {
             const uint32_t sa = ia % C::NA;
-            mbar_wait(&full_a[sa], (ia / C::NA) & 1);
+            SNN_TWAIT(&full_a[sa], (ia / C::NA) & 1, 2);
             tc_fence_after_sync();
-            const uint32_t a_base = smem_u32(a_ring + sa * C::A_STAGE);
-            const uint32_t d = tmem_base + static_cast<uint32_t>(t * p.NCmax);
-            uint32_t acc = kc > 0 ? 1u : 0u;
-            if (MODE == MODE_FWD) {
-              for (int pl = 0; pl < p.b_planes; ++pl) {
+            if (elect_one()) {
+              const uint32_t a_lo = a_ring_lo + sa * (C::A_STAGE >> 4);
+              const uint32_t d = tmem_base + static_cast<uint32_t>(t * p.NCmax);
+              uint32_t acc = kc > 0 ? 1u : 0u;
+              if (p.dbg & 1) {
+              } else if (MODE == MODE_FWD) {
+                for (int pl = 0; pl < p.b_planes; ++pl) {
 #pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  umma_bf16(d, make_smem_desc(a_base + k16 * 32, 16, 1024),
-                            make_smem_desc(b_base + pl * p.NCmax * 128 + k16 * 32, 16, 1024), idesc, acc);
-                  acc = 1u;
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + pl * b_plane_lo + k16 * 2, dhi, idesc, acc);
+                    acc = 1u;
+                  }
+                }
+              } else {
+                // g_c ~ (a_hi + a_lo), W^T ~ (b_hi + b_lo): hi*hi + hi*lo + lo*hi (lo*lo < 2^-16 relative)
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                  const uint32_t pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    umma_bf16_lohi(d, a_lo + pa * (16384 >> 4) + k16 * 2, dhi, b_lo + pb * b_plane_lo + k16 * 2, dhi,
+                                   idesc, acc);
+                    acc = 1u;
+                  }
                 }
               }
-            } else {
-              // g_c ~ (a_hi + a_lo), W^T ~ (b_hi + b_lo): hi*hi + hi*lo + lo*hi (lo*lo < 2^-16 relative)
-#pragma unroll
-              for (int pr = 0; pr < 3; ++pr) {
-                const int pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  umma_bf16(d, make_smem_desc(a_base + pa * 16384 + k16 * 32, 16, 1024),
-                            make_smem_desc(b_base + pb * p.NCmax * 128 + k16 * 32, 16, 1024), idesc, acc);
-                  acc = 1u;
-                }
+              if (p.dbg & 16) mbar_arrive(&empty_a[sa]); else umma_commit(&empty_a[sa]);
+              if (t == p.T - 1) {
+                umma_commit(&empty_b[sb]);
+                if (kc == KC - 1) umma_commit(acc_full);
               }
             }
-            umma_commit(&empty_a[sa]);
+            __syncwarp();
             ++ia;
           }
-          umma_commit(&empty_b[sb]);
           ++ib;
         }
-        umma_commit(acc_full);
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -255,9 +288,19 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       const int ncw = min(p.NCmax, p.NPout - n0);
       const int b = m * 128 + row;
       const bool valid = b < p.B;
-      mbar_wait(acc_full, it & 1);
+      if (MODE == MODE_DX && valid) {
+        // the scan below reads this row's voltages [t][g] (64 B each) straight from HBM-resident traces:
+        // pull them into L2 now, while the tensor core is still busy with this item's MMAs
+        const size_t vstep = static_cast<size_t>(p.NPout >> 4) * p.Bpad * 16;
+        for (int g = half; g < ncw / 16; g += 2) {
+          const float* vb = p.v_in + (static_cast<size_t>((n0 >> 4) + g) * p.Bpad + b) * 16;
+          for (int t = 0; t < p.T; ++t)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<size_t>(t) * vstep));
+        }
+      }
+      SNN_TWAIT(acc_full, it & 1, 0);
       tc_fence_after_sync();
-      for (int g = half; g < ncw / 16; g += 2) {
+      for (int g = half; g < ((p.dbg & 2) ? 0 : ncw / 16); g += 2) {
         const int col0 = n0 + g * 16;
         const uint32_t t_col = t_lane + static_cast<uint32_t>(g * 16);
         if (MODE == MODE_FWD) {
@@ -378,31 +421,49 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
     }
   } else if (MODE == MODE_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 A tile)
-    const int e = tid - 384;   // row inside the tile
+    // Each of the four warps owns every fourth A stage and expands the whole 128-row tile of it (4 rows per
+    // lane), so four stages are in flight and the per-stage barrier / proxy-fence cost is paid once per warp.
+    const int ew = warp - 12;
     uint32_t ia = 0;
-    const int sw = e & 7;
-    uint8_t* const row_base = a_ring + (e >> 3) * 1024 + sw * 128;
+    const int sw = lane & 7;
+    uint8_t* const lane_base = a_ring + (lane >> 3) * 1024 + sw * 128;     // row = lane + 32 j -> + j * 4096
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       for (int i = 0; i < KC * p.T; ++i, ++ia) {
+        if (static_cast<int>(ia & 3) != ew) continue;
         const uint32_t s = ia % NBM;
-        mbar_wait(&full_bits[s], (ia / NBM) & 1);
+        SNN_TWAIT(&full_bits[s], (ia / NBM) & 1, 0);
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + s * kBitsStage);
-        const uint32_t w0 = wsrc[e], w1 = wsrc[128 + e];
-        mbar_arrive(&empty_bits[s]);
-        const uint32_t sa = ia % C::NA;
-        mbar_wait(&empty_a[sa], ((ia / C::NA) & 1) ^ 1);
-        uint8_t* dst = row_base + sa * C::A_STAGE;
+        uint32_t w0[4], w1[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t byte = ((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFFu;
-          *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = lut[byte];
+        for (int j = 0; j < 4; ++j) { w0[j] = wsrc[lane + 32 * j]; w1[j] = wsrc[128 + lane + 32 * j]; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bits[s]);
+        const uint32_t sa = ia % C::NA;
+        SNN_TWAIT(&empty_a[sa], ((ia / C::NA) & 1) ^ 1, 1);
+        uint8_t* dst = lane_base + sa * C::A_STAGE;
+        if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const uint32_t byte = ((c8 < 4 ? w0[j] : w1[j]) >> ((c8 & 3) * 8)) & 0xFFu;
+              *reinterpret_cast<uint4*>(dst + j * 4096 + ((c8 ^ sw) << 4)) = lut[byte];
+            }
+          }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&full_a[sa]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
       }
     }
   }
 
+  if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 12)) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 4 ? 2 : 3));
+    unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
+    o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
+    o[3] = static_cast<unsigned long long>(clock64() - t_start);
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (MODE == MODE_DX) {

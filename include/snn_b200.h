@@ -132,15 +132,18 @@ int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t
                   float* norm_out, void* scratch, void* stream);
 
 /* Optional per-launch device timing used by bench.py's roofline: while enabled, every kernel launch is
- * bracketed by CUDA events on its stream.  Categories: 0 = forward scan-GEMM, 1 = backward dX scan-GEMM,
- * 2 = dW GEMM, 3 = all other (SIMT) kernels.  snn_profile_read synchronises on the recorded events and
- * returns accumulated milliseconds, ALGORITHMIC flops (2*B*K*N*T, unpadded, one product per MAC) and launch
- * counts since the last snn_profile_enable.  snn_launch_count counts every kernel this library launched. */
+ * bracketed by CUDA events on its stream.  Slot = kind + 4 * layer, kind: 0 = forward scan-GEMM, 1 = backward
+ * dX scan-GEMM, 2 = dW GEMM, 3 = all other (SIMT) kernels (layer 0).  snn_profile_read synchronises on the
+ * recorded events and returns, per slot (32 of them), accumulated milliseconds, ALGORITHMIC flops (2*B*K*N*T,
+ * unpadded, one product per MAC) and launch counts since the last snn_profile_enable.  snn_launch_count counts
+ * every kernel this library launched. */
 int snn_profile_enable(int on);
-int snn_profile_read(double* ms4, double* flops4, int64_t* launches4);
+int snn_profile_read(double* ms32, double* flops32, int64_t* launches32);
 int64_t snn_launch_count(void);
 
 /* Debug / test hooks: unpack internal buffers into plain tensors (tests only). */
+/* tools only: device buffer of 16 * 148 * 16 uint64 receiving per-role barrier-wait cycle counts (NULL = off) */
+int snn_debug_set_cycle_buffer(void* buf);
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out);
 
 /* Device-time of the kernels of the last fwd/bwd call is measured by the caller with CUDA
