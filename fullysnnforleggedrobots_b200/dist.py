@@ -29,6 +29,26 @@ def init_from_env(backend: Optional[str] = None) -> "GradientAllReducer | None":
     return GradientAllReducer()
 
 
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block of environments owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def normalize_advantages_global(adv: torch.Tensor, allreduce_sum) -> torch.Tensor:
+    """(adv - mean) / (std + 1e-8) with mean / unbiased std over ALL ranks' samples
+    (reference rollout_storage.py:137-138 computes them over the single process's whole rollout).
+    `allreduce_sum(t)` must sum a float64 tensor over ranks in place and return it."""
+    a = adv.double()
+    stats = torch.stack([a.sum(), (a * a).sum(), torch.tensor(float(a.numel()), device=a.device, dtype=torch.float64)])
+    stats = allreduce_sum(stats)
+    n = stats[2]
+    mean = stats[0] / n
+    var = (stats[1] - n * mean * mean) / (n - 1)
+    return (adv - mean.to(adv.dtype)) / (var.clamp_min(0).sqrt().to(adv.dtype) + 1e-8)
+
+
 class GradientAllReducer:
     def __init__(self, group=None):
         self.group = group

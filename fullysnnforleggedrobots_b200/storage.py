@@ -89,14 +89,8 @@ class RolloutStorage:
         self.returns = ret.view(S, N, 1)
         if not normalize:
             # data parallel: global mean / unbiased std over all ranks' samples
-            a = adv.double()
-            stats = torch.stack([a.sum(), (a * a).sum(), torch.tensor(float(a.numel()), device=a.device,
-                                                                       dtype=torch.float64)])
-            stats = self.advantage_stats_allreduce(stats)
-            n = stats[2]
-            mean = stats[0] / n
-            var = (stats[1] - n * mean * mean) / (n - 1)
-            adv = ((adv - mean.float()) / (var.clamp_min(0).sqrt().float() + 1e-8))
+            from .dist import normalize_advantages_global
+            adv = normalize_advantages_global(adv, self.advantage_stats_allreduce)
         self.advantages = adv.view(S, N, 1)
 
     def get_statistics(self):

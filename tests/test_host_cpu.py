@@ -1,0 +1,87 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, size queries work without a GPU, the modules keep the reference's state-dict keys and
+constructor surface, and CUDA-less use fails loudly instead of falling back."""
+import ctypes as C
+import math
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "snn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(snn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fullysnnforleggedrobots_b200 import _lib
+    lib = _lib.lib()
+    declared = header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in snn_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.snn_abi_version() == 1
+
+
+def test_size_queries_without_gpu():
+    from fullysnnforleggedrobots_b200 import SnnEngine, _lib
+    eng = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=5)
+    L = _lib.lib()
+    assert L.snn_packed_weights_bytes(C.byref(eng.desc)) > 3 * 2 * (512 * 256 + 256 * 256 + 256 * 128)
+    t1, t2 = L.snn_trace_bytes(C.byref(eng.desc), 128), L.snn_trace_bytes(C.byref(eng.desc), 129)
+    assert 0 < t1 < t2 and t2 == L.snn_trace_bytes(C.byref(eng.desc), 256)      # rows pad to 128
+    assert L.snn_workspace_bytes(C.byref(eng.desc), 4096, 1) > L.snn_workspace_bytes(C.byref(eng.desc), 4096, 0)
+    bad = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=40)                      # unsupported T
+    assert L.snn_trace_bytes(C.byref(bad.desc), 128) == 0
+
+
+def test_state_dict_keys_and_init_match_reference_layout():
+    from fullysnnforleggedrobots_b200 import ActorCritic, ActorCriticRMA
+    ac = ActorCritic(48, 48, 12, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256])
+    keys = set(ac.state_dict().keys())
+    expect = {"std", "actor.log_std", "actor.encoder.mean", "actor.encoder.std", "actor.snn.hidden_layers.0.weight",
+              "actor.snn.hidden_layers.0.bias", "actor.snn.hidden_layers.1.weight", "actor.snn.hidden_layers.1.bias",
+              "actor.snn.out_pop_layer.weight", "actor.snn.out_pop_layer.bias", "actor.decoder.decoder.weight",
+              "actor.decoder.decoder.bias", "critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias",
+              "critic.4.weight", "critic.4.bias"}
+    assert keys == expect
+    sd = ac.state_dict()
+    assert sd["actor.encoder.mean"].shape == (1, 48, 10) and sd["actor.decoder.decoder.weight"].shape == (12, 1, 10)
+    assert torch.allclose(sd["actor.encoder.mean"][0, 0], torch.linspace(-5, 5, 10))
+    assert torch.allclose(sd["actor.encoder.std"], torch.full((1, 48, 10), math.sqrt(0.15)))
+    assert torch.allclose(sd["actor.log_std"], torch.full((12,), -0.001))
+    assert ac.is_recurrent is False and ac.reset() is None
+    rma = ActorCriticRMA(30, 20, 60, 12, actor_hidden_dims=[64], critic_hidden_dims=[64])
+    rk = set(rma.state_dict().keys())
+    assert {"env_factor_encoder.0.weight", "encoder.0.weight", "adaptation_module.0.weight"} <= rk
+    assert rma.actor.obs_dim == 30 + 18
+
+
+def test_unknown_kwargs_are_reported_and_ignored(capsys):
+    from fullysnnforleggedrobots_b200 import ActorCritic
+    ActorCritic(8, 8, 2, actor_hidden_dims=[16], critic_hidden_dims=[16], some_unknown_flag=3)
+    assert "unexpected arguments" in capsys.readouterr().out
+
+
+def test_no_cpu_fallback():
+    from fullysnnforleggedrobots_b200 import ActorCritic, PPO
+    ac = ActorCritic(8, 8, 2, actor_hidden_dims=[16], critic_hidden_dims=[16])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ac.act(torch.randn(4, 8))
+    with pytest.raises(RuntimeError):
+        PPO(ac, device="cpu")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fullysnnforleggedrobots_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
