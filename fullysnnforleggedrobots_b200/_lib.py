@@ -41,6 +41,18 @@ class SnnGrads(C.Structure):
                 ("dec_w", C.c_void_p), ("dec_b", C.c_void_p), ("obs", C.c_void_p)]
 
 
+class SnnMlpDesc(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("num_hidden", C.c_int32), ("hidden", C.c_int32 * SNN_MAX_LAYERS)]
+
+
+class SnnMlpParams(C.Structure):
+    _fields_ = [("weight", C.c_void_p * (SNN_MAX_LAYERS + 1)), ("bias", C.c_void_p * (SNN_MAX_LAYERS + 1))]
+
+
+class SnnMlpGrads(C.Structure):
+    _fields_ = [("weight", C.c_void_p * (SNN_MAX_LAYERS + 1)), ("bias", C.c_void_p * (SNN_MAX_LAYERS + 1))]
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + \
         [os.path.join(INCLUDE, "snn_b200.h")]
@@ -88,6 +100,14 @@ _SIGS = {
                           C.c_void_p]),
     "snn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                           C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "snn_mlp_packed_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc)]),
+    "snn_mlp_trace_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc), C.c_int64]),
+    "snn_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc), C.c_int64]),
+    "snn_mlp_pack": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_void_p]),
+    "snn_mlp_fwd": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_void_p, C.c_int64,
+                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_mlp_bwd": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_int64, C.c_void_p,
+                              C.c_void_p, C.POINTER(SnnMlpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snn_ppo_head": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
                      + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

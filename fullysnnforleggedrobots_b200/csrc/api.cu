@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "dw_gemm.cuh"
+#include "mlp_kernels.cuh"
 #include "plan.cuh"
 #include "ppo_kernels.cuh"
 #include "scan_gemm.cuh"
@@ -92,8 +93,14 @@ int device_ready(int* num_sms) {
                                   static_cast<int>(scan_gemm_smem_bytes<MODE_DX>(96))));
     CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(scan_gemm_smem_bytes<MODE_DX_ENC>(96))));
-    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
+    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kDwSmemBytes)));
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_MLP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_MLP_FWD>(128))));
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_MLP_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_MLP_DX>(128))));
     di.attrs_set = 1;
   }
   *num_sms = di.num_sms;
@@ -260,13 +267,13 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     if (lp.NP > 256) return fail(SNN_EINVAL, "output population wider than 256 neurons is not supported by top_scan_kernel");
     dim3 tblk(lp.NP / 8, 256 / (lp.NP / 8));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<Bp / 128, tblk, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<Bp / 32, tblk, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
                                          p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart);
     }
     LAUNCH_CHECK("top_scan_kernel");
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, Bp / 128, lp.NP, lp.N, g->bias[top]);
+    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, Bp / 32, lp.NP, lp.N, g->bias[top]);
     }
     LAUNCH_CHECK("reduce_rows_kernel(db top)");
   }
@@ -290,7 +297,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       q.splits = splits;
       q.partial = partial;
       { ProfScope prof__(CAT_DW + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-      dw_gemm_kernel<<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
+      dw_gemm_kernel<false><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }
       LAUNCH_CHECK("dw_gemm_kernel");
       dim3 rg((lp.K + 127) / 128, lp.N);
@@ -337,7 +344,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const int AP = p.A * p.Pd;
     if (AP + p.A > 1024) return fail(SNN_EINVAL, "act_dim * de_pop too large for dec_bwd_kernel");
-    const int nblk = (Bi + 255) / 256;
+    const int nblk = (Bi + 63) / 64;
     const uint32_t* top_bits = reinterpret_cast<const uint32_t*>(at(trace, p.layer[top].tr_bits));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     dec_bwd_kernel<<<dim3((AP + p.A + 31) / 32, nblk), dim3(32, 8), 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
@@ -354,7 +361,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   }
   // ---- encoder parameter gradients (+ d obs)
   {
-    const int nblk = (Bi + 255) / 256;
+    const int nblk = (Bi + 63) / 64;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     enc_bwd_kernel<<<dim3((p.K0 + 31) / 32, nblk), dim3(32, 8), 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
     }
@@ -403,6 +410,188 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values, con
     gae_norm_kernel<<<256, 256, 0, st>>>(advantages, count, part_sum, nb, part_sq, 256);
     }
     LAUNCH_CHECK("gae_norm_kernel");
+  }
+  return SNN_OK;
+}
+
+// ------------------------------------------------------------------ dense ELU critic on the tensor cores
+size_t snn_mlp_packed_bytes(const SnnMlpDesc* d) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, 1, &p) != SNN_OK) return 0;
+  return p.packed_bytes;
+}
+size_t snn_mlp_trace_bytes(const SnnMlpDesc* d, int64_t B) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return 0;
+  return p.trace_bytes;
+}
+size_t snn_mlp_workspace_bytes(const SnnMlpDesc* d, int64_t B) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return 0;
+  return p.ws_bytes;
+}
+
+int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* prm, void* packed, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  MlpPlan p;
+  if (!d || !prm || !packed || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, 1, &p) != SNN_OK)
+    return fail(SNN_EINVAL, "bad MLP descriptor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int l = 0; l < p.H; ++l) {
+    const MlpLayerPlan& lp = p.layer[l];
+    if (!prm->weight[l] || !prm->bias[l]) return fail(SNN_EINVAL, "null weight/bias pointer");
+    const int total = lp.NP * lp.KP / 8;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    pack_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP,
+                                                       at(packed, lp.w_img), lp.w_plane, at(packed, lp.wt_img),
+                                                       lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad)));
+    }
+    LAUNCH_CHECK("pack_w_kernel(mlp)");
+  }
+  return SNN_OK;
+}
+
+int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, const float* x, int64_t B,
+                float* value, void* trace, size_t trace_bytes, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return fail(SNN_EINVAL, "bad MLP descriptor");
+  if (!prm || !packed || !x || !value || !trace) return fail(SNN_EINVAL, "null pointer");
+  if (trace_bytes < p.trace_bytes) return fail(SNN_ENOMEM, "mlp trace too small");
+  if (p.layer[p.H - 1].NP > 256) return fail(SNN_EINVAL, "last hidden layer wider than 256 is not supported by the value head");
+  if (B == 0) return SNN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
+  {
+    const int total = Bp * p.K0P / 8;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    planes_from_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, Bi, Bp, p.in_dim, p.K0P, at(trace, p.tr_x), p.tr_x_plane);
+    }
+    LAUNCH_CHECK("planes_from_f32_kernel");
+  }
+  const uint8_t* a_img = at(trace, p.tr_x);
+  size_t a_plane = p.tr_x_plane;
+  for (int l = 0; l < p.H; ++l) {
+    const MlpLayerPlan& lp = p.layer[l];
+    ScanGemmParams q{};
+    q.a_img = a_img; q.a_plane = a_plane;
+    q.b_img = at(packed, lp.w_img); q.b_plane = lp.w_plane; q.b_planes = 2;
+    q.KP = lp.KP; q.NPout = lp.NP; q.NCmax = 128; q.T = 1;
+    q.B = Bi; q.Bpad = Bp; q.R = p.Bpad;
+    q.nchunks = lp.NP / 128;
+    q.nitems = (Bp / 128) * q.nchunks;
+    q.dbg = 0;
+    q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
+    q.g_img = at(trace, lp.tr_h); q.g_plane = lp.tr_h_plane;
+    const int grid = q.nitems < sms ? q.nitems : sms;
+    { ProfScope prof__(CAT_FWD + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+    scan_gemm_kernel<MODE_MLP_FWD><<<grid, ScanCfg<MODE_MLP_FWD>::THREADS, scan_gemm_smem_bytes<MODE_MLP_FWD>(128), st>>>(q);
+    }
+    LAUNCH_CHECK("scan_gemm_kernel<MLP_FWD>");
+    a_img = at(trace, lp.tr_h); a_plane = lp.tr_h_plane;
+  }
+  {
+    const MlpLayerPlan& lp = p.layer[p.H - 1];
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    value_head_fwd_kernel<<<(Bi + 7) / 8, 256, 0, st>>>(a_img, a_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], prm->bias[p.H], value);
+    }
+    LAUNCH_CHECK("value_head_fwd_kernel");
+  }
+  return SNN_OK;
+}
+
+int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, int64_t B, const float* g_value,
+                const void* trace, const SnnMlpGrads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return fail(SNN_EINVAL, "bad MLP descriptor");
+  if (!prm || !packed || !g_value || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if (workspace_bytes < p.ws_bytes) return fail(SNN_ENOMEM, "mlp workspace too small");
+  if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
+  float* dbpart = reinterpret_cast<float*>(at(workspace, p.ws_dbpart));
+  float* partial = reinterpret_cast<float*>(at(workspace, p.ws_partial));
+  float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
+  const int top = p.H - 1;
+  {   // output layer backward + dz of the last hidden layer
+    const MlpLayerPlan& lp = p.layer[top];
+    const int nblk = Bp / 64;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    value_head_bwd_kernel<<<nblk, 256, 0, st>>>(at(trace, lp.tr_h), lp.tr_h_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], g_value,
+                                                at(workspace, p.ws_dz[0]), p.ws_dz_plane[0], small);
+    }
+    LAUNCH_CHECK("value_head_bwd_kernel");
+    const size_t stride = 2 * static_cast<size_t>(lp.NP) + 1;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, stride, lp.N, g->weight[p.H]);
+    }
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(small + lp.NP, nblk, stride, lp.N, g->bias[top]);
+    }
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(small + 2 * lp.NP, nblk, stride, 1, g->bias[p.H]);
+    }
+    LAUNCH_CHECK("reduce_rows_kernel(value head)");
+  }
+  for (int l = top; l >= 0; --l) {
+    const MlpLayerPlan& lp = p.layer[l];
+    const int slot = (top - l) & 1;
+    const uint8_t* G = at(workspace, p.ws_dz[slot]);
+    const size_t Gplane = p.ws_dz_plane[slot];
+    {   // dW_l = dz_l^T . input_l
+      DwGemmParams q{};
+      q.g_img = G; q.g_plane = Gplane;
+      q.x_img = l == 0 ? at(trace, p.tr_x) : at(trace, p.layer[l - 1].tr_h);
+      q.x_plane = l == 0 ? p.tr_x_plane : p.layer[l - 1].tr_h_plane;
+      q.NP = lp.NP; q.KP = lp.KP; q.R = p.Bpad;
+      q.n_tiles = (lp.KP + 255) / 256;
+      q.rblocks = Bp / 64;
+      const int tiles = (lp.NP / 128) * q.n_tiles;
+      int splits = sms / tiles;
+      if (splits < 1) splits = 1;
+      if (splits > q.rblocks) splits = q.rblocks;
+      q.splits = splits;
+      q.partial = partial;
+      { ProfScope prof__(CAT_DW + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+      dw_gemm_kernel<true><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
+      }
+      LAUNCH_CHECK("dw_gemm_kernel<dense>");
+      dim3 rg((lp.K + 127) / 128, lp.N);
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
+      reduce_partials_kernel<<<rg, 128, 0, st>>>(partial, splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
+      }
+      LAUNCH_CHECK("reduce_partials_kernel(mlp)");
+    }
+    if (l > 0) {   // dz_{l-1} = (dz_l . W_l) * ELU'(z_{l-1})
+      const MlpLayerPlan& lo = p.layer[l - 1];
+      ScanGemmParams q{};
+      q.a_img = G; q.a_plane = Gplane;
+      q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
+      q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = 128; q.T = 1;
+      q.B = Bi; q.Bpad = Bp; q.R = p.Bpad;
+      q.nchunks = lp.KP / 128;
+      q.nitems = (Bp / 128) * q.nchunks;
+      q.dbg = 0;
+      q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
+      q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
+      q.db_part = dbpart;
+      const int grid = q.nitems < sms ? q.nitems : sms;
+      { ProfScope prof__(CAT_DX + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+      scan_gemm_kernel<MODE_MLP_DX><<<grid, ScanCfg<MODE_MLP_DX>::THREADS, scan_gemm_smem_bytes<MODE_MLP_DX>(128), st>>>(q);
+      }
+      LAUNCH_CHECK("scan_gemm_kernel<MLP_DX>");
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
+      reduce_rows_kernel<<<(lo.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
+      }
+      LAUNCH_CHECK("reduce_rows_kernel(mlp db)");
+    }
   }
   return SNN_OK;
 }

@@ -19,7 +19,9 @@ namespace snn {
 struct DwGemmParams {
   const uint8_t* g_img;    // 2 planes, swz64 image [NP/64][R rows]
   size_t g_plane;
-  const uint32_t* x_bits;  // [KP/32][R]
+  const uint32_t* x_bits;  // [KP/32][R]           (spiking layers: binary input, expanded in shared memory)
+  const uint8_t* x_img;    // 2 planes, swz64 image [KP/64][R rows]   (dense layers: real-valued input)
+  size_t x_plane;
   int NP, KP;
   int64_t R;
   int n_tiles;             // ceil(KP / 256)
@@ -34,15 +36,20 @@ constexpr int kDwBitStages = 8;        // ring of spike-word stages: 8 runs of 6
 constexpr int kDwBitStageBytes = 2048;
 constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + kDwBitStages * kDwBitStageBytes + 4096 + 512;
 
+// DENSE = false: B operand = spike bits expanded in smem (3 stages of 64 KiB).
+// DENSE = true : B operand = hi/lo planes bulk-copied like A (2 stages of 96 KiB), three products.
+template <bool DENSE>
 __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
+  constexpr int kStages = DENSE ? 2 : 3;
+  constexpr int kStageBytes = DENSE ? 98304 : 65536;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint8_t* bits_ring = ring + kDwStages * kDwStageBytes;
+  uint8_t* bits_ring = ring + kStages * kStageBytes;
   uint4* lut = reinterpret_cast<uint4*>(bits_ring + kDwBitStages * kDwBitStageBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + 4096);
-  uint64_t* empty = full + kDwStages;
-  uint64_t* acc_full = empty + kDwStages;
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
   uint64_t* full_bits = acc_full + 1;
   uint64_t* empty_bits = full_bits + kDwBitStages;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + kDwBitStages);
@@ -56,7 +63,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const int rb0 = split * per, rb1 = min(p.rblocks, rb0 + per);
 
   if (tid == 0) {
-    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], DENSE ? 1 : 2); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -79,21 +86,30 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     // producer: warp-uniform loop, one elected lane issues the bulk copies
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
-      const uint32_t sbit = i % kDwBitStages;
-      mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
-      if (elect_one()) {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
-        mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
-        uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
-        for (int w = 0; w < 2 * nck; ++w)
-          bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
-                   &full_bits[sbit]);
+      if (!DENSE) {
+        const uint32_t sbit = i % kDwBitStages;
+        mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
+        if (elect_one()) {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
+          mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
+          uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
+          for (int w = 0; w < 2 * nck; ++w)
+            bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
+                     &full_bits[sbit]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      const uint32_t s = i % kDwStages;
-      mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
+      const uint32_t s = i % kStages;
+      mbar_wait(&empty[s], ((i / kStages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&full[s], 32768u);
-        uint8_t* dst = ring + s * kDwStageBytes;
+        mbar_expect_tx(&full[s], DENSE ? static_cast<uint32_t>(32768 + nck * 16384) : 32768u);
+        uint8_t* dst = ring + s * kStageBytes;
+        if (DENSE) {
+          for (int pl = 0; pl < 2; ++pl)
+            for (int kcl = 0; kcl < nck; ++kcl)
+              bulk_g2s(dst + 32768 + pl * 32768 + kcl * 8192,
+                       p.x_img + pl * p.x_plane + (static_cast<size_t>(kc0 + kcl) * p.R + static_cast<size_t>(rb) * 64) * 128,
+                       8192u, &full[s]);
+        }
         for (int pl = 0; pl < 2; ++pl)
           for (int nc = 0; nc < 2; ++nc)
             bulk_g2s(dst + pl * 16384 + nc * 8192,
@@ -109,18 +125,27 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     const uint32_t ring_lo = smem_desc_lo(smem_u32(ring), 8192);
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
-      const uint32_t s = i % kDwStages;
-      mbar_wait(&full[s], (i / kDwStages) & 1);
+      const uint32_t s = i % kStages;
+      mbar_wait(&full[s], (i / kStages) & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        const uint32_t a_lo = ring_lo + s * (kDwStageBytes >> 4);
+        const uint32_t a_lo = ring_lo + s * (kStageBytes >> 4);
         const uint32_t b_lo = a_lo + (32768 >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
+          if (DENSE) {
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl)
-            umma_bf16_lohi(tmem_base, a_lo + pl * (16384 >> 4) + k16 * (2048 >> 4), dhi, b_lo + k16 * (2048 >> 4), dhi, idesc,
-                           (i > 0 || k16 > 0 || pl > 0) ? 1u : 0u);
+            for (int pr = 0; pr < 3; ++pr) {
+              const uint32_t pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
+              umma_bf16_lohi(tmem_base, a_lo + pa * (16384 >> 4) + k16 * (2048 >> 4), dhi,
+                             b_lo + pb * (32768 >> 4) + k16 * (2048 >> 4), dhi, idesc, (i > 0 || k16 > 0 || pr > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              umma_bf16_lohi(tmem_base, a_lo + pl * (16384 >> 4) + k16 * (2048 >> 4), dhi, b_lo + k16 * (2048 >> 4), dhi, idesc,
+                             (i > 0 || k16 > 0 || pl > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
         if (rb == rb1 - 1) umma_commit(acc_full);
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     const int ew = warp - 4;
     const int sw = lane & 7;
     uint32_t i = 0;
-    for (int rb = rb0; rb < rb1; ++rb, ++i) {
+    for (int rb = rb0; rb < (DENSE ? rb0 : rb1); ++rb, ++i) {
       if (static_cast<int>(i & 7) != ew) continue;
       const uint32_t sbit = i % kDwBitStages;
       mbar_wait(&full_bits[sbit], (i / kDwBitStages) & 1);
@@ -146,9 +171,9 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
         for (int u = 0; u < 8; ++u) w[h][u] = (u < 2 * nck) ? wsrc[u * 64 + lane + 32 * h] : 0u;
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bits[sbit]);
-      const uint32_t s = i % kDwStages;
-      mbar_wait(&empty[s], ((i / kDwStages) & 1) ^ 1);
-      uint8_t* bst = ring + s * kDwStageBytes + 32768;
+      const uint32_t s = i % kStages;
+      mbar_wait(&empty[s], ((i / kStages) & 1) ^ 1);
+      uint8_t* bst = ring + s * kStageBytes + 32768;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int row = lane + 32 * h;

@@ -1,0 +1,125 @@
+// mlp_kernels.cuh — SIMT ends of the dense ELU critic (AMP/.../modules/actor_critic.py:359-368, 428-430):
+// input -> operand planes, the 1-wide output layer and its backward.  The hidden layers run on the tensor
+// cores through scan_gemm_kernel<MODE_MLP_FWD / MODE_MLP_DX> and dw_gemm_kernel<true>.
+#pragma once
+#include "plan.cuh"
+#include "umma.cuh"
+
+namespace snn {
+
+// x [B][K] fp32 -> hi/lo bf16 planes as swz64 image [KP/64][Bpad rows]; padding rows / columns are zero
+__global__ void planes_from_f32_kernel(const float* __restrict__ x, int B, int Bpad, int K, int KP,
+                                       uint8_t* __restrict__ img, size_t plane) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kp8 = KP / 8;
+  if (idx >= Bpad * kp8) return;
+  const int r = idx / kp8, c0 = (idx - r * kp8) * 8;
+  float h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float v = (r < B && c < K) ? x[static_cast<size_t>(r) * K + c] : 0.f;
+    h[j] = bf16_round(v);
+    l[j] = v - h[j];
+  }
+  const size_t off = swz64_offset(r, c0, Bpad);
+  *reinterpret_cast<uint4*>(img + off) =
+      make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+  *reinterpret_cast<uint4*>(img + plane + off) =
+      make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+__device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float (&x)[8]) {
+  const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+    x[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+  }
+}
+
+// value[b] = sum_n h[b,n] w[n] + bias.  One warp per row, lane = 8-column piece (NP <= 256).
+__global__ void __launch_bounds__(256) value_head_fwd_kernel(const uint8_t* __restrict__ h_img, size_t h_plane, int Bpad,
+                                                            int B, int N, int NP, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ value) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float acc = 0.f;
+  if (lane * 8 < NP) {
+    const size_t off = swz64_offset(b, lane * 8, Bpad);
+    float h[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h_img + off)), __ldg(reinterpret_cast<const uint4*>(h_img + h_plane + off)), h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = lane * 8 + j;
+      if (n < N) acc += h[j] * w[n];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) value[b] = acc + bias[0];
+}
+
+// dz[b,n] = g_v[b] w[n] ELU'(h[b,n]) -> planes; partials per block of 64 rows:
+//   part[blk][0..NP)      = sum_b g_v[b] h[b,n]      (d w_out)
+//   part[blk][NP..2NP)    = sum_b dz[b,n]            (d bias of the last hidden layer)
+//   part[blk][2NP]        = sum_b g_v[b]             (d bias_out)
+__global__ void __launch_bounds__(256) value_head_bwd_kernel(const uint8_t* __restrict__ h_img, size_t h_plane, int Bpad,
+                                                            int B, int N, int NP, const float* __restrict__ w,
+                                                            const float* __restrict__ g_v, uint8_t* __restrict__ dz_img,
+                                                            size_t dz_plane, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool col_live = lane * 8 < NP;
+  float wl[8], dw[8], dbh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = lane * 8 + j;
+    wl[j] = (col_live && n < N) ? w[n] : 0.f;
+    dw[j] = 0.f; dbh[j] = 0.f;
+  }
+  float dbo = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const int b = blockIdx.x * 64 + i * 8 + wid;
+    if (b >= Bpad) break;
+    const float g = b < B ? g_v[b] : 0.f;
+    if (lane == 0) dbo += g;
+    if (col_live) {
+      const size_t off = swz64_offset(b, lane * 8, Bpad);
+      float h[8], dz[8], hi[8], lo[8];
+      if (b < B) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(h_img + off)), __ldg(reinterpret_cast<const uint4*>(h_img + h_plane + off)), h);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dz[j] = g * wl[j] * (h[j] > 0.f ? 1.f : h[j] + 1.f);
+        dw[j] += g * h[j];
+        dbh[j] += dz[j];
+        hi[j] = bf16_round(dz[j]);
+        lo[j] = dz[j] - hi[j];
+      }
+      *reinterpret_cast<uint4*>(dz_img + off) =
+          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+      *reinterpret_cast<uint4*>(dz_img + dz_plane + off) =
+          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+    }
+  }
+  __shared__ float sh[8][2 * 256 + 1];
+  if (col_live) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sh[wid][lane * 8 + j] = dw[j]; sh[wid][256 + lane * 8 + j] = dbh[j]; }
+  }
+  if (lane == 0) sh[wid][512] = dbo;
+  __syncthreads();
+  float* out = part + static_cast<size_t>(blockIdx.x) * (2 * NP + 1);
+  for (int i = threadIdx.x; i < 2 * NP + 1; i += 256) {
+    const int src = i < NP ? i : (i < 2 * NP ? 256 + (i - NP) : 512);
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][src];
+    out[i] = t;
+  }
+}
+
+}  // namespace snn

@@ -132,10 +132,86 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart = take(dbp * 4);
   size_t small = static_cast<size_t>(p.Bpad / 64) * 2 * p.K0;
-  const size_t small_dec = static_cast<size_t>(p.Bpad / 128) * (p.A * p.Pd + p.A);
+  const size_t small_dec = static_cast<size_t>(p.Bpad / 64) * (p.A * p.Pd + p.A);
   if (small_dec > small) small = small_dec;
   p.ws_small = take(small * 4 + 1024);
   p.ws_bwd_bytes = off;
+  *out = p;
+  return SNN_OK;
+}
+
+// ------------------------------------------------------------------ dense ELU MLP with one output (the critic)
+struct MlpLayerPlan {
+  int K, N, KP, NP;
+  size_t w_img, w_plane;     // 3 planes (hi, mid, lo) of W [NP rows][KP cols]; the MLP kernels use hi + mid
+  size_t wt_img, wt_plane;   // 2 planes of W^T [KP rows][NP cols]
+  size_t bias_pad;
+  size_t tr_h;               // trace: 2 planes of the layer's ELU output [NP/64][Bpad rows]
+  size_t tr_h_plane;
+};
+
+struct MlpPlan {
+  int H;                     // hidden (ELU) layers; the output layer [1 x hidden[H-1]] is handled by SIMT kernels
+  int in_dim, K0P;
+  int64_t B, Bpad;
+  MlpLayerPlan layer[SNN_MAX_LAYERS];
+  size_t packed_bytes;
+  size_t tr_x, tr_x_plane;   // trace: 2 planes of the input [K0P/64][Bpad rows]
+  size_t trace_bytes;
+  size_t ws_dz[2], ws_dz_plane[2];
+  size_t ws_partial, ws_dbpart, ws_small;
+  size_t ws_bytes;
+};
+
+inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int64_t B, MlpPlan* out) {
+  MlpPlan p{};
+  if (in_dim <= 0 || num_hidden < 1 || num_hidden > SNN_MAX_LAYERS || B < 0) return SNN_EINVAL;
+  p.H = num_hidden;
+  p.in_dim = in_dim;
+  p.K0P = static_cast<int>(round_up(in_dim, 64));
+  p.B = B;
+  p.Bpad = round_up(B > 0 ? B : 1, kTileM);
+  size_t off = 0;
+  auto take = [&off](size_t bytes) { size_t o = off; off += round_up(static_cast<int64_t>(bytes), 1024); return o; };
+  int k = in_dim, kp = p.K0P;
+  for (int l = 0; l < p.H; ++l) {
+    MlpLayerPlan& lp = p.layer[l];
+    if (hidden[l] <= 0 || hidden[l] > 2048) return SNN_EINVAL;
+    lp.K = k; lp.KP = kp; lp.N = hidden[l]; lp.NP = static_cast<int>(round_up(hidden[l], 128));
+    lp.w_plane = static_cast<size_t>(lp.KP / 64) * lp.NP * 128;
+    lp.wt_plane = static_cast<size_t>(lp.NP / 64) * lp.KP * 128;
+    lp.w_img = take(3 * lp.w_plane);
+    lp.wt_img = take(2 * lp.wt_plane);
+    lp.bias_pad = take(static_cast<size_t>(lp.NP) * 4);
+    k = lp.N; kp = lp.NP;
+  }
+  if (p.K0P > 2048) return SNN_EINVAL;
+  p.packed_bytes = off;
+  off = 0;
+  p.tr_x_plane = static_cast<size_t>(p.K0P / 64) * p.Bpad * 128;
+  p.tr_x = take(2 * p.tr_x_plane);
+  size_t dzmax = 0;
+  int npmax = p.K0P;
+  for (int l = 0; l < p.H; ++l) {
+    MlpLayerPlan& lp = p.layer[l];
+    lp.tr_h_plane = static_cast<size_t>(lp.NP / 64) * p.Bpad * 128;
+    lp.tr_h = take(2 * lp.tr_h_plane);
+    if (lp.tr_h_plane > dzmax) dzmax = lp.tr_h_plane;
+    if (lp.NP > npmax) npmax = lp.NP;
+  }
+  p.trace_bytes = off;
+  off = 0;
+  for (int s = 0; s < 2; ++s) { p.ws_dz_plane[s] = dzmax; p.ws_dz[s] = take(2 * dzmax); }
+  size_t part = 0;
+  for (int l = 0; l < p.H; ++l) {
+    const size_t tiles = static_cast<size_t>(p.layer[l].NP / 128) * ((p.layer[l].KP + 255) / 256);
+    const size_t ctas = tiles > 296 ? tiles : 296;
+    if (ctas * 128 * 256 * 4 > part) part = ctas * 128 * 256 * 4;
+  }
+  p.ws_partial = take(part);
+  p.ws_dbpart = take(static_cast<size_t>(296) * npmax * 4);
+  p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (2 * npmax + 8) * 4 + 1024);
+  p.ws_bytes = off;
   *out = p;
   return SNN_OK;
 }

@@ -30,7 +30,7 @@
 
 namespace snn {
 
-enum { MODE_FWD = 0, MODE_DX = 1, MODE_DX_ENC = 2 };
+enum { MODE_FWD = 0, MODE_DX = 1, MODE_DX_ENC = 2, MODE_MLP_FWD = 3, MODE_MLP_DX = 4 };
 
 struct ScanGemmParams {
   // A operand
@@ -61,15 +61,55 @@ struct ScanGemmParams {
   float* db_part;           // [gridDim.x][NPout]
   // DX_ENC
   float* g_a;               // [Bpad][NPout]
+  // MLP_FWD: writes ELU(acc + bias) as hi/lo planes into g_img.  MLP_DX: reads the layer's ELU output planes
+  const uint8_t* h_img;     // 2 planes of swz64 image [NPout/64][R rows]
+  size_t h_plane;
 };
 
 template <int MODE> struct ScanCfg;
 template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, NBITS = 16, THREADS = 512; };
 template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
 template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
+template <> struct ScanCfg<MODE_MLP_FWD> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
+template <> struct ScanCfg<MODE_MLP_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
 
 constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (FWD: bias, DX: db); layer widths <= 2048
 constexpr int kBitsStage = 1024;   // one A stage worth of spike words: 2 x (128 rows x 4 B)
+
+// 16 consecutive columns of one row -> hi/lo bf16 planes of a swz64 image (two 16-byte pieces per plane)
+__device__ __forceinline__ void store_planes16(uint8_t* img, size_t plane, int64_t R, size_t r, int col0, const float (&x)[16]) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(x[j]); lo[j] = x[j] - hi[j]; }
+  const size_t base = static_cast<size_t>(col0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+  const int p0 = (col0 & 63) >> 3;
+  const int sw = static_cast<int>(r & 7);
+  const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+  const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+  const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+  const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+  *reinterpret_cast<uint4*>(img + base + ((p0 ^ sw) << 4)) = h0;
+  *reinterpret_cast<uint4*>(img + base + (((p0 + 1) ^ sw) << 4)) = h1;
+  *reinterpret_cast<uint4*>(img + plane + base + ((p0 ^ sw) << 4)) = l0;
+  *reinterpret_cast<uint4*>(img + plane + base + (((p0 + 1) ^ sw) << 4)) = l1;
+}
+// inverse: hi + lo of 16 consecutive columns of one row
+__device__ __forceinline__ void load_planes16(const uint8_t* img, size_t plane, int64_t R, size_t r, int col0, float (&x)[16]) {
+  const size_t base = static_cast<size_t>(col0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+  const int p0 = (col0 & 63) >> 3;
+  const int sw = static_cast<int>(r & 7);
+  const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(img + base + ((p0 ^ sw) << 4)));
+  const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(img + base + (((p0 + 1) ^ sw) << 4)));
+  const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + ((p0 ^ sw) << 4)));
+  const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + (((p0 + 1) ^ sw) << 4)));
+  const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+    x[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+  }
+}
 
 template <int MODE>
 __host__ __device__ constexpr size_t scan_gemm_smem_bytes(int NCmax) {
@@ -152,7 +192,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       lut[i] = v;
     }
     for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = p.bias[i];
-  } else if (MODE == MODE_DX) {
+  } else if (MODE == MODE_MLP_FWD) {
+    for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = p.bias[i];
+  } else if (MODE == MODE_DX || MODE == MODE_MLP_DX) {
     for (int i = tid; i < p.NPout; i += blockDim.x) s_col[i] = 0.f;
   }
   tc_fence_before_sync();
@@ -395,6 +437,31 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           }
           const float tot = warp_transpose_reduce16(dbacc, lane);
           if ((lane & 1) == 0) atomicAdd(&s_col[col0 + (lane >> 1)], tot);
+        } else if (MODE == MODE_MLP_FWD) {
+          // dense layer: h = ELU(acc + bias) (torch: x > 0 ? x : exp(x) - 1), kept as hi/lo planes for the next GEMMs
+          uint32_t x[16];
+          tmem_ld16(t_col, x);
+          tmem_ld_wait();
+          float h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float z = __uint_as_float(x[j]) + s_col[col0 + j];
+            h[j] = valid ? (z > 0.f ? z : expf(z) - 1.f) : 0.f;
+          }
+          store_planes16(p.g_img, p.g_plane, p.R, static_cast<size_t>(b), col0, h);
+        } else if (MODE == MODE_MLP_DX) {
+          // dz = (dz_above . W) * ELU'(z), ELU'(z) = 1 for z > 0 else exp(z) = h + 1
+          uint32_t x[16];
+          tmem_ld16(t_col, x);
+          float h[16];
+          load_planes16(p.h_img, p.h_plane, p.R, static_cast<size_t>(b), col0, h);
+          tmem_ld_wait();
+          float dz[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dz[j] = valid ? __uint_as_float(x[j]) * (h[j] > 0.f ? 1.f : h[j] + 1.f) : 0.f;
+          store_planes16(p.g_img, p.g_plane, p.R, static_cast<size_t>(b), col0, dz);
+          const float tot = warp_transpose_reduce16(dz, lane);
+          if ((lane & 1) == 0) atomicAdd(&s_col[col0 + (lane >> 1)], tot);
         } else {   // MODE_DX_ENC
           float gam[16], ga[16];
 #pragma unroll
@@ -466,7 +533,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (MODE == MODE_DX) {
+  if (MODE == MODE_DX || MODE == MODE_MLP_DX) {
     for (int i = tid; i < p.NPout; i += blockDim.x) p.db_part[static_cast<size_t>(blockIdx.x) * p.NPout + i] = s_col[i];
   }
   if (warp == 1) {

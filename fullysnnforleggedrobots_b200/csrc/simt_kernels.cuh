@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
                                                       const float* __restrict__ volt, int B, int Bpad, int A, int P,
                                                       int NP, int T, int64_t R, uint8_t* __restrict__ g_img,
                                                       size_t g_plane, float* __restrict__ db_part) {
-  // blockDim = (NP/8 column groups [<= 32], 256/(NP/8) rows); block covers 128 rows; grid = (Bpad/128)
+  // blockDim = (NP/8 column groups [<= 32], 256/(NP/8) rows); block covers 32 rows; grid = (Bpad/32)
   const int cg = threadIdx.x, ry = threadIdx.y, rows_per_it = blockDim.y;
   const int n0 = cg * 8;
   float w[8];
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) dbacc[j] = 0.f;
   const float invT = static_cast<float>(T);
-  for (int rb = ry; rb < 128; rb += rows_per_it) {
-    const int b = blockIdx.x * 128 + rb;
+  for (int rb = ry; rb < 32; rb += rows_per_it) {
+    const int b = blockIdx.x * 32 + rb;
     const bool row_live = b < B;
     float gup[8];
 #pragma unroll
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) dec_bwd_kernel(const float* __restrict__ 
                                                      int dec_tanh, const uint32_t* __restrict__ bits, int64_t R, int B,
                                                      int Bpad, int A, int P, int T,
                                                      float* __restrict__ part /* [gridDim.y][A*P + A] */) {
-  // block (32 columns, 8 row lanes); grid = (ceil((AP + A)/32), ceil(B/256)); each thread walks 32 rows
+  // block (32 columns, 8 row lanes); grid = (ceil((AP + A)/32), ceil(B/64)); each thread walks 8 rows
   const int AP = A * P;
   const int i = blockIdx.x * 32 + threadIdx.x;
   const bool col_live = i < AP + A;
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(256) dec_bwd_kernel(const float* __restrict__ 
   const int a = col_live ? (is_w ? i / P : i - AP) : 0;
   float acc = 0.f;
   if (col_live) {
-    for (int j = 0; j < 32; ++j) {
-      const int b = blockIdx.y * 256 + j * 8 + threadIdx.y;
+    for (int j = 0; j < 8; ++j) {
+      const int b = blockIdx.y * 64 + j * 8 + threadIdx.y;
       if (b >= B) break;
       float G = g_mu[static_cast<size_t>(b) * A + a];
       if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) enc_bwd_kernel(const float* __restrict__ 
                                                      const float* __restrict__ std, const float* __restrict__ g_a,
                                                      int B, int O, int P, int K0, int K0P, float eps,
                                                      float* __restrict__ part /* [gridDim.y][2][K0] */) {
-  // block (32 encoder neurons, 8 row lanes); grid = (ceil(K0/32), ceil(B/256)); each thread walks 32 rows
+  // block (32 encoder neurons, 8 row lanes); grid = (ceil(K0/32), ceil(B/64)); each thread walks 8 rows
   const int k = blockIdx.x * 32 + threadIdx.x;
   const bool live = k < K0;
   float dm = 0.f, ds = 0.f;
@@ -277,9 +277,9 @@ __global__ void __launch_bounds__(256) enc_bwd_kernel(const float* __restrict__ 
     const float mk = mean[k], sk = std[k];
     const float inv_var = 1.f / (sk * sk + eps);
     const int o = k / P;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
-      const int b = blockIdx.y * 256 + j * 8 + threadIdx.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = blockIdx.y * 64 + j * 8 + threadIdx.y;
       if (b < B) {
         const float x = obs[static_cast<size_t>(b) * O + o];
         const float d = x - mk;

@@ -203,3 +203,99 @@ def gae(rewards, dones, values, last_values, gamma: float, lam: float, normalize
                                       float(gamma), float(lam), _ptr(returns), _ptr(adv), 1 if normalize else 0,
                                       _ptr(scratch), _stream_ptr(dev)), "snn_gae")
     return returns, adv
+
+
+class CriticEngine:
+    """Dense ELU critic (Linear -> ELU -> ... -> Linear(., 1)) on the tensor-core kernels (snn_mlp_*).
+
+    `linears` is the list of nn.Linear modules of the reference's `critic` nn.Sequential
+    (AMP/.../modules/actor_critic.py:359-368).  Used by the fused PPO update; `ActorCritic.evaluate` in the
+    rollout keeps the torch path (small batches, no gradient)."""
+
+    def __init__(self, linears):
+        if len(linears) < 2 or linears[-1].out_features != 1:
+            raise ValueError("critic must end in Linear(., 1) and have at least one hidden layer")
+        if len(linears) - 1 > _lib.SNN_MAX_LAYERS:
+            raise ValueError("too many critic layers")
+        d = _lib.SnnMlpDesc()
+        d.in_dim = linears[0].in_features
+        d.num_hidden = len(linears) - 1
+        for i, l in enumerate(linears[:-1]):
+            d.hidden[i] = l.out_features
+        if linears[-2].out_features > 256:
+            raise ValueError("last hidden layer wider than 256 is not supported by the value-head kernels")
+        self.desc = d
+        self.linears = list(linears)
+        self._packed = None
+        self._ws = None
+        if _lib.lib().snn_mlp_packed_bytes(C.byref(d)) == 0:
+            raise ValueError("unsupported critic dimensions")
+
+    @staticmethod
+    def from_sequential(seq):
+        """Return a CriticEngine if `seq` is Linear/ELU/.../Linear(., 1), else None."""
+        mods = list(seq)
+        lin = [m for m in mods if isinstance(m, torch.nn.Linear)]
+        act = [m for m in mods if not isinstance(m, torch.nn.Linear)]
+        ok = (len(mods) == 2 * len(lin) - 1 and all(isinstance(m, torch.nn.ELU) and m.alpha == 1.0 for m in act)
+              and all(isinstance(mods[2 * i], torch.nn.Linear) for i in range(len(lin))))
+        if not ok:
+            return None
+        try:
+            return CriticEngine(lin)
+        except ValueError:
+            return None
+
+    def _params(self):
+        p = _lib.SnnMlpParams()
+        for i, l in enumerate(self.linears):
+            p.weight[i] = l.weight.data_ptr()
+            p.bias[i] = l.bias.data_ptr()
+        return p
+
+    def trace_bytes(self, B):
+        return int(_lib.lib().snn_mlp_trace_bytes(C.byref(self.desc), B))
+
+    def repack(self):
+        dev = self.linears[0].weight.device
+        L = _lib.lib()
+        if self._packed is None or self._packed.device != dev:
+            self._packed = torch.empty(L.snn_mlp_packed_bytes(C.byref(self.desc)), dtype=torch.uint8, device=dev)
+        ps = self._params()
+        with torch.cuda.device(dev):
+            _lib.check(L.snn_mlp_pack(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _stream_ptr(dev)), "snn_mlp_pack")
+
+    def forward(self, x, out_value=None, out_trace=None):
+        _check_f32_cuda(x, "critic_obs")
+        dev = x.device
+        B = x.shape[0]
+        L = _lib.lib()
+        if self._packed is None:
+            self.repack()
+        nbytes = L.snn_mlp_trace_bytes(C.byref(self.desc), B)
+        trace = out_trace if out_trace is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        value = out_value if out_value is not None else torch.empty(B, dtype=torch.float32, device=dev)
+        ps = self._params()
+        with torch.cuda.device(dev):
+            _lib.check(L.snn_mlp_fwd(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _ptr(x), B, _ptr(value),
+                                     _ptr(trace), trace.numel(), _stream_ptr(dev)), "snn_mlp_fwd")
+        return value, trace
+
+    def backward(self, g_value, trace, B, out=None):
+        """Gradients of sum_b g_value[b] * value[b]; `out` = (list of weight grads, list of bias grads) to overwrite."""
+        dev = g_value.device
+        L = _lib.lib()
+        if out is None:
+            out = ([torch.empty_like(l.weight) for l in self.linears], [torch.empty_like(l.bias) for l in self.linears])
+        g = _lib.SnnMlpGrads()
+        for i in range(len(self.linears)):
+            g.weight[i] = out[0][i].data_ptr()
+            g.bias[i] = out[1][i].data_ptr()
+        nbytes = L.snn_mlp_workspace_bytes(C.byref(self.desc), B)
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ps = self._params()
+        with torch.cuda.device(dev):
+            _lib.check(L.snn_mlp_bwd(C.byref(self.desc), C.byref(ps), _ptr(self._packed), B, _ptr(g_value), _ptr(trace),
+                                     C.byref(g), _ptr(self._ws), self._ws.numel(), _stream_ptr(dev)), "snn_mlp_bwd")
+        return out

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .engine import CriticEngine
 from .optim import FlatAdam
 from .storage import RolloutStorage
 
@@ -38,7 +39,7 @@ class PPO:
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998,
                  lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
                  use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device='cpu', weight_decay=0.0,
-                 data_parallel=None, fused=True, use_cuda_graph=True):
+                 data_parallel=None, fused=True, use_cuda_graph=True, fused_critic=True):
         self.device = device
         self.desired_kl = desired_kl
         self.schedule = schedule
@@ -64,6 +65,7 @@ class PPO:
         self.max_grad_norm = max_grad_norm
         self.use_clipped_value_loss = use_clipped_value_loss
         self.fused = fused
+        self.fused_critic = fused_critic
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -174,6 +176,8 @@ class PPO:
         actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
                             [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
                             actor.decoder.decoder.bias.data)
+        if self._fast_state is not None and self._fast_state.get("critic") is not None:
+            self._fast_state["critic"].repack()
 
     def _step_generic(self, batch):
         loss, surrogate_loss, value_loss, kl_mean = self.losses(batch)
@@ -212,6 +216,15 @@ class PPO:
             "weights": [l.weight.grad for l in layers], "biases": [l.bias.grad for l in layers],
             "dec_w": ac.actor.decoder.decoder.weight.grad, "dec_b": ac.actor.decoder.decoder.bias.grad, "obs": None,
         }
+        st["critic"] = None
+        if self.fused_critic:
+            ce = CriticEngine.from_sequential(ac.critic) if isinstance(ac.critic, nn.Sequential) else None
+            if ce is not None:
+                ce.repack()
+                st["critic"] = ce
+                st["value"] = torch.empty(mb, dtype=torch.float32, device=dev)
+                st["critic_trace"] = torch.empty(ce.trace_bytes(mb), dtype=torch.uint8, device=dev)
+                st["critic_grads"] = ([l.weight.grad for l in ce.linears], [l.bias.grad for l in ce.linears])
         self._fast_state = st
         self._graphs = {}
 
@@ -227,8 +240,12 @@ class PPO:
         eng = ac.actor.engine
         mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
                                 db.data, train=True, out_mu=st["mu"], out_trace=st["trace"])
-        with torch.enable_grad():
-            value = ac.evaluate(f["critic_obs"][sl])
+        ce = st["critic"]
+        if ce is not None:
+            value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
+        else:
+            with torch.enable_grad():
+                value = ac.evaluate(f["critic_obs"][sl])
         L = _lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
@@ -242,7 +259,10 @@ class PPO:
         opt.flat_grads[opt.n:].copy_(self._stats[2:3])
         eng.backward(f["obs"][sl], mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws],
                      [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"])
-        value.backward(st["g_value"].view_as(value))
+        if ce is not None:
+            ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
+        else:
+            value.backward(st["g_value"].view_as(value))
         self._finish_step()
 
     def _run_fast(self, f, i):
@@ -292,6 +312,8 @@ class PPO:
         actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
                             [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
                             actor.decoder.decoder.bias.data)
+        if self._fast_state is not None and self._fast_state.get("critic") is not None:
+            self._fast_state["critic"].repack()
 
     # ------------------------------------------------------------------ update
     def update(self):

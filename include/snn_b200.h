@@ -108,6 +108,34 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values,
             const float* last_values, int64_t S, int64_t N, float gamma, float lam,
             float* returns, float* advantages, int normalize, void* scratch, void* stream);
 
+/* ---- dense ELU MLP with one output: the critic (AMP:359-368, evaluate :428-430) -------------------------------
+ * Linear -> ELU -> ... -> Linear(., 1).  Hidden layers run on tcgen05 with hi/lo bf16 operand planes (three
+ * products, ~2^-16 relative); the 1-wide output layer and its backward are SIMT.  weight[i] / bias[i] for
+ * i < num_hidden are the hidden layers [N,K] / [N]; index num_hidden is the output layer [1,N] / [1]. */
+typedef struct SnnMlpDesc {
+  int32_t in_dim;
+  int32_t num_hidden;
+  int32_t hidden[SNN_MAX_LAYERS];
+} SnnMlpDesc;
+typedef struct SnnMlpParams {
+  const float* weight[SNN_MAX_LAYERS + 1];
+  const float* bias[SNN_MAX_LAYERS + 1];
+} SnnMlpParams;
+typedef struct SnnMlpGrads {
+  float* weight[SNN_MAX_LAYERS + 1];
+  float* bias[SNN_MAX_LAYERS + 1];
+} SnnMlpGrads;
+size_t snn_mlp_packed_bytes(const SnnMlpDesc* d);
+size_t snn_mlp_trace_bytes(const SnnMlpDesc* d, int64_t B);
+size_t snn_mlp_workspace_bytes(const SnnMlpDesc* d, int64_t B);
+int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* p, void* packed, void* stream);
+/* value [B] = critic(x [B,in_dim]); trace keeps the operand planes of x and of every hidden activation */
+int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, const float* x, int64_t B,
+                float* value, void* trace, size_t trace_bytes, void* stream);
+/* gradients of sum_b g_value[b] * value[b] w.r.t. every weight / bias (overwritten) */
+int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, int64_t B, const float* g_value,
+                const void* trace, const SnnMlpGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused PPO head (AMP/.../algorithms/ppo.py:132-171 with modules/actor_critic.py:398-421): Normal log-prob,
  * entropy, KL to the rollout policy, clipped surrogate and clipped value loss, forward AND closed-form
  * gradients in one pass.  Inputs [B,A] / [B] fp32.  Outputs: g_mu [B,A], g_value [B], g_log_std [A] =

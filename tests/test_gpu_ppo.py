@@ -122,3 +122,28 @@ def test_second_update_replays_graph_and_stays_finite():
     assert all(torch.isfinite(p).all() for p in ac.parameters())
     sd = alg.optimizer.state_dict()
     assert len(sd["state"]) == len(alg.optimizer.params)
+
+
+@pytest.mark.parametrize("dims,B", [((48, 256, 256), 300), ((20, 512, 256, 128), 131), ((7, 24), 5)])
+def test_tensor_core_critic_matches_torch_fp32(dims, B):
+    """snn_mlp_fwd / snn_mlp_bwd vs a plain PyTorch fp32 critic (reference: nn.Sequential Linear/ELU)."""
+    from fullysnnforleggedrobots_b200 import CriticEngine
+    torch.manual_seed(3)
+    layers = []
+    for i in range(len(dims) - 1):
+        layers += [torch.nn.Linear(dims[i], dims[i + 1]), torch.nn.ELU()]
+    layers.append(torch.nn.Linear(dims[-1], 1))
+    seq = torch.nn.Sequential(*layers).cuda()
+    ce = CriticEngine.from_sequential(seq)
+    assert ce is not None
+    x = torch.randn(B, dims[0], device="cuda") * 1.5
+    gv = torch.randn(B, device="cuda")
+    value, trace = ce.forward(x)
+    ref = seq(x)
+    assert rel_err(value.cpu(), ref.detach().squeeze(-1).cpu()) < 1e-4
+    ref.backward(gv.view_as(ref))
+    gw, gb = ce.backward(gv, trace, B)
+    lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+    for i, l in enumerate(lin):
+        assert rel_err(gw[i].cpu(), l.weight.grad.cpu()) < 1e-4, f"dW{i}"
+        assert rel_err(gb[i].cpu(), l.bias.grad.cpu()) < 1e-4, f"db{i}"
