@@ -67,7 +67,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.idx), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -263,9 +263,16 @@ def run_ours(args):
     ms_prof_total = timed(step_resident, args.steps)
     pms32, pfl32, pln32 = (C.c_double * 32)(), (C.c_double * 32)(), (C.c_int64 * 32)()
     L.snn_profile_read(pms32, pfl32, pln32)
-    pms = [sum(pms32[k + 4 * l] for l in range(8)) for k in range(4)]
-    pfl = [sum(pfl32[k + 4 * l] for l in range(8)) for k in range(4)]
-    pln = [sum(pln32[k + 4 * l] for l in range(8)) for k in range(4)]
+    # layers 0..3 = the spiking actor, 4..7 = the dense critic (same kernel family, MLP epilogues)
+    pms = [sum(pms32[k + 4 * l] for l in range(4)) for k in range(4)]
+    pfl = [sum(pfl32[k + 4 * l] for l in range(4)) for k in range(4)]
+    pln = [sum(pln32[k + 4 * l] for l in range(4)) for k in range(4)]
+    cms = [sum(pms32[k + 4 * l] for l in range(4, 8)) for k in range(4)]
+    cfl = [sum(pfl32[k + 4 * l] for l in range(4, 8)) for k in range(4)]
+    cln = [sum(pln32[k + 4 * l] for l in range(4, 8)) for k in range(4)]
+    per_layer = {f"{['fwd', 'dx', 'dw'][k]}_layer{l}": {"us_per_launch": 1e3 * pms32[k + 4 * l] / pln32[k + 4 * l],
+                                                        "algo_tflops": pfl32[k + 4 * l] / (pms32[k + 4 * l] * 1e-3) / 1e12}
+                 for l in range(8) for k in range(3) if pln32[k + 4 * l] > 0}
     L.snn_profile_enable(0)
     alg.use_cuda_graph = graph_flag
 
@@ -330,6 +337,9 @@ def run_ours(args):
                                "share_of_step": tc_ms / ms_total,
                                "eager_profiled_ms_per_step": ms_prof_total / args.steps},
         "per_kernel": per_cat,
+        "per_layer": per_layer,
+        "critic_tensor_kernels": {"ms": sum(cms[:3]), "launches": int(sum(cln[:3])),
+                                  "algo_tflops": sum(cfl[:3]) / (sum(cms[:3]) * 1e-3) / 1e12 if sum(cms[:3]) > 0 else 0.0},
     }
     cpu_value, cpu_dt = time_cpu(CPU_SAMPLE_ROWS, 3, 2) if (world == 1 and not args.quick) else (None, None)
     line = {

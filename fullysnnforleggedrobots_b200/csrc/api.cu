@@ -115,6 +115,39 @@ int debug_mask() {
   return m;
 }
 
+struct Deferred {
+  RowJobs rows{};
+  PartJobs parts{};
+  int max_n = 0, max_K = 0, max_N = 0;
+  void row(const float* src, int nparts, size_t stride, int n, float* dst) {
+    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride)};
+    if (n > max_n) max_n = n;
+  }
+  void part(const float* partial, int splits, int n_tiles, int N, int K, float* dW) {
+    parts.j[parts.count++] = PartJob{partial, dW, splits, n_tiles, N, K};
+    if (K > max_K) max_K = K;
+    if (N > max_N) max_N = N;
+  }
+};
+
+int launch_deferred(const Deferred& df, cudaStream_t st) {
+  if (df.parts.count > 0) {
+    dim3 grd((df.max_K + 127) / 128, df.max_N, df.parts.count);
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    multi_reduce_partials_kernel<<<grd, 128, 0, st>>>(df.parts);
+    }
+    LAUNCH_CHECK("multi_reduce_partials_kernel");
+  }
+  if (df.rows.count > 0) {
+    dim3 grd((df.max_n + 31) / 32, df.rows.count);
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    multi_reduce_rows_kernel<<<grd, dim3(32, 8), 0, st>>>(df.rows);
+    }
+    LAUNCH_CHECK("multi_reduce_rows_kernel");
+  }
+  return SNN_OK;
+}
+
 int plan_for(const SnnDesc* d, int64_t B, int num_sms, SnnPlan* p) {
   if (d == nullptr) return fail(SNN_EINVAL, "null descriptor");
   if (make_plan(*d, B, num_sms, p) != SNN_OK) return fail(SNN_EINVAL, "unsupported SnnDesc (dims, spike_ts 1..16, planes 1..3)");
@@ -254,9 +287,11 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
-  float* dbpart = reinterpret_cast<float*>(at(workspace, p.ws_dbpart));
-  float* partial = reinterpret_cast<float*>(at(workspace, p.ws_partial));
+  auto dbpart_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_dbpart + static_cast<size_t>(l) * p.ws_dbpart_stride)); };
+  auto partial_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_partial + static_cast<size_t>(l) * p.ws_partial_stride)); };
   float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
+  float* small_enc = reinterpret_cast<float*>(at(workspace, p.ws_small_enc));
+  Deferred df;
   float* g_a = reinterpret_cast<float*>(at(workspace, p.ws_ga));
   const uint32_t* enc_bits = reinterpret_cast<const uint32_t*>(at(trace, p.tr_enc_bits));
 
@@ -269,13 +304,10 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     top_scan_kernel<<<Bp / 32, tblk, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
-                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart);
+                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top));
     }
     LAUNCH_CHECK("top_scan_kernel");
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, Bp / 32, lp.NP, lp.N, g->bias[top]);
-    }
-    LAUNCH_CHECK("reduce_rows_kernel(db top)");
+    df.row(dbpart_of(top), Bp / 32, lp.NP, lp.N, g->bias[top]);
   }
   // ---- walk down the layers
   for (int l = top; l >= 0; --l) {
@@ -295,16 +327,12 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       if (splits < 1) splits = 1;
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
-      q.partial = partial;
+      q.partial = partial_of(l);
       { ProfScope prof__(CAT_DW + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
       dw_gemm_kernel<false><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }
       LAUNCH_CHECK("dw_gemm_kernel");
-      dim3 rg((lp.K + 127) / 128, lp.N);
-      { ProfScope prof__(CAT_OTHER, 0.0, st);
-      reduce_partials_kernel<<<rg, 128, 0, st>>>(partial, splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
-      }
-      LAUNCH_CHECK("reduce_partials_kernel");
+      df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
     }
     {   // dX_l + scan of the layer below (or of the encoder)
       ScanGemmParams q{};
@@ -322,15 +350,12 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         q.v_in = reinterpret_cast<const float*>(at(trace, lo.tr_volt));
         q.g_img = at(workspace, p.ws_g[slot ^ 1]);
         q.g_plane = p.ws_g_plane[slot ^ 1];
-        q.db_part = dbpart;
+        q.db_part = dbpart_of(l - 1);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(p.NCmax), st>>>(q);
         }
         LAUNCH_CHECK("scan_gemm_kernel<DX>");
-        { ProfScope prof__(CAT_OTHER, 0.0, st);
-        reduce_rows_kernel<<<(lo.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
-        }
-        LAUNCH_CHECK("reduce_rows_kernel(db)");
+        df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
       } else {
         q.g_a = g_a;
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
@@ -351,28 +376,18 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
                                                                p.T, small);
     }
     LAUNCH_CHECK("dec_bwd_kernel");
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(AP + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, AP + p.A, AP, g->dec_w);
-    }
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.A + 31) / 32, dim3(32, 8), 0, st>>>(small + AP, nblk, AP + p.A, p.A, g->dec_b);
-    }
-    LAUNCH_CHECK("reduce_rows_kernel(dec)");
+    df.row(small, nblk, AP + p.A, AP, g->dec_w);
+    df.row(small + AP, nblk, AP + p.A, p.A, g->dec_b);
   }
   // ---- encoder parameter gradients (+ d obs)
   {
     const int nblk = (Bi + 63) / 64;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    enc_bwd_kernel<<<dim3((p.K0 + 31) / 32, nblk), dim3(32, 8), 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small);
+    enc_bwd_kernel<<<dim3((p.K0 + 31) / 32, nblk), dim3(32, 8), 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small_enc);
     }
     LAUNCH_CHECK("enc_bwd_kernel");
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.K0 + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
-    }
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(p.K0 + 31) / 32, dim3(32, 8), 0, st>>>(small + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
-    }
-    LAUNCH_CHECK("reduce_rows_kernel(enc)");
+    df.row(small_enc, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
+    df.row(small_enc + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
     if (g->obs != nullptr) {
       const int n = Bi * p.O;
       { ProfScope prof__(CAT_OTHER, 0.0, st);
@@ -382,7 +397,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       LAUNCH_CHECK("enc_dobs_kernel");
     }
   }
-  return SNN_OK;
+  return launch_deferred(df, st);
 }
 
 int snn_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, int64_t S,
@@ -516,9 +531,10 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
-  float* dbpart = reinterpret_cast<float*>(at(workspace, p.ws_dbpart));
-  float* partial = reinterpret_cast<float*>(at(workspace, p.ws_partial));
+  auto dbpart_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_dbpart + static_cast<size_t>(l) * p.ws_dbpart_stride)); };
+  auto partial_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_partial + static_cast<size_t>(l) * p.ws_partial_stride)); };
   float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
+  Deferred df;
   const int top = p.H - 1;
   {   // output layer backward + dz of the last hidden layer
     const MlpLayerPlan& lp = p.layer[top];
@@ -529,16 +545,9 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
     }
     LAUNCH_CHECK("value_head_bwd_kernel");
     const size_t stride = 2 * static_cast<size_t>(lp.NP) + 1;
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(small, nblk, stride, lp.N, g->weight[p.H]);
-    }
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<(lp.N + 31) / 32, dim3(32, 8), 0, st>>>(small + lp.NP, nblk, stride, lp.N, g->bias[top]);
-    }
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(small + 2 * lp.NP, nblk, stride, 1, g->bias[p.H]);
-    }
-    LAUNCH_CHECK("reduce_rows_kernel(value head)");
+    df.row(small, nblk, stride, lp.N, g->weight[p.H]);
+    df.row(small + lp.NP, nblk, stride, lp.N, g->bias[top]);
+    df.row(small + 2 * lp.NP, nblk, stride, 1, g->bias[p.H]);
   }
   for (int l = top; l >= 0; --l) {
     const MlpLayerPlan& lp = p.layer[l];
@@ -558,16 +567,12 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       if (splits < 1) splits = 1;
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
-      q.partial = partial;
+      q.partial = partial_of(l);
       { ProfScope prof__(CAT_DW + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
       dw_gemm_kernel<true><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }
       LAUNCH_CHECK("dw_gemm_kernel<dense>");
-      dim3 rg((lp.K + 127) / 128, lp.N);
-      { ProfScope prof__(CAT_OTHER, 0.0, st);
-      reduce_partials_kernel<<<rg, 128, 0, st>>>(partial, splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
-      }
-      LAUNCH_CHECK("reduce_partials_kernel(mlp)");
+      df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
     }
     if (l > 0) {   // dz_{l-1} = (dz_l . W_l) * ELU'(z_{l-1})
       const MlpLayerPlan& lo = p.layer[l - 1];
@@ -581,19 +586,16 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       q.dbg = 0;
       q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
       q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
-      q.db_part = dbpart;
+      q.db_part = dbpart_of(l - 1);
       const int grid = q.nitems < sms ? q.nitems : sms;
       { ProfScope prof__(CAT_DX + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
       scan_gemm_kernel<MODE_MLP_DX><<<grid, ScanCfg<MODE_MLP_DX>::THREADS, scan_gemm_smem_bytes<MODE_MLP_DX>(128), st>>>(q);
       }
       LAUNCH_CHECK("scan_gemm_kernel<MLP_DX>");
-      { ProfScope prof__(CAT_OTHER, 0.0, st);
-      reduce_rows_kernel<<<(lo.N + 31) / 32, dim3(32, 8), 0, st>>>(dbpart, grid, lo.NP, lo.N, g->bias[l - 1]);
-      }
-      LAUNCH_CHECK("reduce_rows_kernel(mlp db)");
+      df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
     }
   }
-  return SNN_OK;
+  return launch_deferred(df, st);
 }
 
 int snn_ppo_head(const float* mu, const float* log_std, const float* value, const float* actions,

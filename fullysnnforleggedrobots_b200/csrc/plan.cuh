@@ -56,9 +56,9 @@ struct SnnPlan {
   size_t ws_g[2];           // two ping-pong G image buffers (2 planes each)
   size_t ws_g_plane[2];
   size_t ws_ga;             // fp32 [Bpad][K0P]  d loss / d pop_act
-  size_t ws_partial;        // fp32 split-K partials of dW
-  size_t ws_dbpart;         // fp32 per-CTA partial bias grads
-  size_t ws_small;          // scratch for small reductions (decoder / encoder grads)
+  size_t ws_partial, ws_partial_stride;   // fp32 split-K partials of dW, one region per layer
+  size_t ws_dbpart, ws_dbpart_stride;     // fp32 partial bias grads, one region per layer
+  size_t ws_small, ws_small_enc;          // partials of the decoder (ws_small) / encoder (ws_small_enc) gradients
   size_t ws_bwd_bytes;
   size_t ws_fwd_bytes;      // forward-only workspace == a trace without voltages
   int dw_max_ctas;
@@ -124,17 +124,17 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
     const size_t b = ctas * 128 * 256 * 4;
     if (b > part) part = b;
   }
-  p.ws_partial = take(part);
+  p.ws_partial_stride = static_cast<size_t>(round_up(static_cast<int64_t>(part), 1024));
+  p.ws_partial = take(p.ws_partial_stride * p.L);
   int npmax = p.K0P;
   for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
   size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;
   const size_t dbp_top = static_cast<size_t>(p.Bpad / 32) * p.layer[p.L - 1].NP;
   if (dbp_top > dbp) dbp = dbp_top;
-  p.ws_dbpart = take(dbp * 4);
-  size_t small = static_cast<size_t>(p.Bpad / 64) * 2 * p.K0;
-  const size_t small_dec = static_cast<size_t>(p.Bpad / 64) * (p.A * p.Pd + p.A);
-  if (small_dec > small) small = small_dec;
-  p.ws_small = take(small * 4 + 1024);
+  p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
+  p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
+  p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (p.A * p.Pd + p.A) * 4 + 1024);
+  p.ws_small_enc = take(static_cast<size_t>(p.Bpad / 64) * 2 * p.K0 * 4 + 1024);
   p.ws_bwd_bytes = off;
   *out = p;
   return SNN_OK;
@@ -159,7 +159,7 @@ struct MlpPlan {
   size_t tr_x, tr_x_plane;   // trace: 2 planes of the input [K0P/64][Bpad rows]
   size_t trace_bytes;
   size_t ws_dz[2], ws_dz_plane[2];
-  size_t ws_partial, ws_dbpart, ws_small;
+  size_t ws_partial, ws_partial_stride, ws_dbpart, ws_dbpart_stride, ws_small;
   size_t ws_bytes;
 };
 
@@ -208,8 +208,10 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int6
     const size_t ctas = tiles > 296 ? tiles : 296;
     if (ctas * 128 * 256 * 4 > part) part = ctas * 128 * 256 * 4;
   }
-  p.ws_partial = take(part);
-  p.ws_dbpart = take(static_cast<size_t>(296) * npmax * 4);
+  p.ws_partial_stride = static_cast<size_t>(round_up(static_cast<int64_t>(part), 1024));
+  p.ws_partial = take(p.ws_partial_stride * p.H);
+  p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(296) * npmax * 4, 1024));
+  p.ws_dbpart = take(p.ws_dbpart_stride * p.H);
   p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (2 * npmax + 8) * 4 + 1024);
   p.ws_bytes = off;
   *out = p;

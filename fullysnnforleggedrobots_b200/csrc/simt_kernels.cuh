@@ -337,6 +337,41 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
   }
 }
 
+// Several independent row reductions / split-K reductions in ONE launch (blockIdx.y resp. .z selects the job):
+// the backward pass defers all of its small reductions to the end instead of launching ten tiny kernels.
+struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; };
+struct RowJobs { RowJob j[12]; int count; };
+__global__ void __launch_bounds__(256) multi_reduce_rows_kernel(const RowJobs jobs) {
+  const RowJob jb = jobs.j[blockIdx.y];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x * 32 >= jb.n) return;
+  float acc = 0.f;
+  if (i < jb.n)
+    for (int s = threadIdx.y; s < jb.nparts; s += 8) acc += jb.src[static_cast<size_t>(s) * jb.stride + i];
+  __shared__ float sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < jb.n) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    jb.dst[i] = t;
+  }
+}
+
+struct PartJob { const float* partial; float* dW; int splits, n_tiles, N, K; };
+struct PartJobs { PartJob j[8]; int count; };
+__global__ void multi_reduce_partials_kernel(const PartJobs jobs) {
+  const PartJob jb = jobs.j[blockIdx.z];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (k >= jb.K || n >= jb.N) return;
+  const int tile = (n >> 7) * jb.n_tiles + (k >> 8);
+  const float* src = jb.partial + (static_cast<size_t>(tile) * jb.splits * 128 + (n & 127)) * 256 + (k & 255);
+  float acc = 0.f;
+  for (int s = 0; s < jb.splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
+  jb.dW[static_cast<size_t>(n) * jb.K + k] = acc;
+}
+
 // ------------------------------------------------------------------ GAE (rollout_storage.py:124-138)
 // Thread per environment, reverse scan over S steps; [S][N] layout makes every step a coalesced row.
 __global__ void gae_scan_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,

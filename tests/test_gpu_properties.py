@@ -1,0 +1,133 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes (C1 dims: obs 48, hidden 256-256,
+12 actions, T=5; B = 4096 rollout step and B = 24576 PPO minibatch), where the CPU oracle is too slow to be the
+checker: row independence, run-to-run reproducibility, linearity of BPTT in the upstream gradient, the decoder as
+a checksum of the recorded spike trains, sub-sampled oracle parity, and the edge cases B = 0 / B = 1."""
+import math
+
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_actor(seed=0, **kw):
+    from fullysnnforleggedrobots_b200 import PopSpikeActor
+    torch.manual_seed(seed)
+    return PopSpikeActor(48, 12, 10, 10, [256, 256], (-5, 5), math.sqrt(0.15), spike_ts=5, **kw).cuda()
+
+
+def params_of(actor):
+    layers = actor.snn.linear_layers()
+    return (actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
+            [l.bias.data for l in layers], actor.decoder.decoder.weight.data, actor.decoder.decoder.bias.data)
+
+
+def grads_of(actor, obs, G):
+    for p in actor.parameters():
+        p.grad = None
+    mu, _ = actor(obs)
+    (mu * G).sum().backward()
+    return mu.detach(), {n: p.grad.detach().clone() for n, p in actor.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("B", [4096, 24576])
+def test_rows_are_independent_and_runs_reproducible(B):
+    actor = make_actor()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn(B, 48, device="cuda", generator=g)
+    with torch.inference_mode():
+        mu_full, _ = actor(obs)
+        mu_again, _ = actor(obs)
+        mu_part, _ = actor(obs[1000:1777].contiguous())         # ragged sub-batch, different tiling
+    assert torch.equal(mu_full, mu_again)
+    assert torch.equal(mu_full[1000:1777], mu_part)
+    assert torch.isfinite(mu_full).all()
+
+
+def test_training_forward_equals_inference_forward_and_trace_checksum():
+    B = 24576
+    actor = make_actor()
+    obs = torch.randn(B, 48, device="cuda")
+    with torch.inference_mode():
+        mu_inf, _ = actor(obs)
+    mu, trace = actor.engine.forward(obs, *params_of(actor), train=True)
+    assert torch.equal(mu, mu_inf)
+    tr = actor.engine.unpack_trace(trace, B)
+    # decoder recomputed on the host from the recorded output spike train == mu (checksum of the trace)
+    rate = tr["spikes"][-1].sum(0) / 5.0                                              # [B, 120]
+    w = actor.decoder.decoder.weight.data.cpu().reshape(12, 10)
+    mu_chk = (rate.reshape(B, 12, 10) * w).sum(-1) + actor.decoder.decoder.bias.data.cpu()
+    assert rel_err(mu.cpu(), mu_chk) < 1e-5
+    # spikes are exactly the thresholded voltages, layer by layer
+    for l in range(3):
+        assert torch.equal(tr["spikes"][l], (tr["volt"][l] > 0.5).float())
+    assert 0.02 < tr["enc_spikes"].mean().item() < 0.15
+
+
+def test_bptt_is_linear_in_upstream_gradient_and_reproducible():
+    B = 24576
+    actor = make_actor()
+    obs = torch.randn(B, 48, device="cuda")
+    G1 = torch.randn(B, 12, device="cuda")
+    G2 = torch.randn(B, 12, device="cuda")
+    _, g1 = grads_of(actor, obs, G1)
+    _, g2 = grads_of(actor, obs, G2)
+    _, g12 = grads_of(actor, obs, G1 + 2.0 * G2)
+    _, g1b = grads_of(actor, obs, G1)
+    for k in g1:
+        assert rel_err(g12[k], g1[k] + 2.0 * g2[k]) < 2e-4, k
+        if k.endswith("weight") or "encoder" in k:
+            assert torch.equal(g1[k], g1b[k]), f"{k} not bit-reproducible"      # fixed-order split-K reduction
+        else:
+            assert rel_err(g1[k], g1b[k]) < 1e-5, k
+
+
+def test_full_size_subsample_matches_oracle():
+    """Oracle parity on a 192-row sub-sample of a 24576-row minibatch (forward exact rows; gradients of a loss that
+    only touches those rows)."""
+    from oracle import snn_oracle as O
+    B = 24576
+    actor = make_actor()
+    obs = torch.randn(B, 48, device="cuda")
+    idx = torch.arange(5000, 5192, device="cuda")
+    G = torch.zeros(B, 12, device="cuda")
+    G[idx] = torch.randn(192, 12, device="cuda")
+    mu, grads = grads_of(actor, obs, G)
+    sd = {"actor." + k: v.detach().cpu() for k, v in actor.state_dict().items()}
+    p = O.ActorParams.from_state_dict(sd, spike_ts=5)
+    obs_s = obs[idx].cpu()
+    mu_ref, _, tr = O.actor_forward(obs_s, p, want_traces=True)
+    gr = O.actor_backward(obs_s, p, tr, G[idx].cpu(), need_dobs=False)
+    bad = ((mu[idx].cpu() - mu_ref).abs() > 1e-4 * mu_ref.abs().max()).any(dim=1).float().mean().item()
+    assert bad <= 0.01
+    if bad == 0:
+        assert rel_err(grads["snn.hidden_layers.0.weight"].cpu(), gr["weights"][0]) < 1e-4
+        assert rel_err(grads["snn.out_pop_layer.bias"].cpu(), gr["biases"][2]) < 1e-4
+        assert rel_err(grads["encoder.mean"].cpu(), gr["enc_mean"]) < 1e-4
+
+
+def test_edge_batches():
+    actor = make_actor()
+    with torch.inference_mode():
+        mu0, std = actor(torch.empty(0, 48, device="cuda"))
+        mu1, _ = actor(torch.zeros(1, 48, device="cuda"))
+    assert mu0.shape == (0, 12) and std.shape == (12,)
+    assert mu1.shape == (1, 12) and torch.isfinite(mu1).all()
+    with pytest.raises(RuntimeError):
+        actor(torch.zeros(4, 47, device="cuda"))          # wrong observation width
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_reduced_plane_modes_stay_close(planes):
+    """fwd_planes < 3 (approximate weights) is a speed option, not the parity mode: spikes may flip, but rarely."""
+    B = 4096
+    ref = make_actor(seed=5)
+    fast = make_actor(seed=5, fwd_planes=planes)
+    obs = torch.randn(B, 48, device="cuda")
+    _, t_ref = ref.engine.forward(obs, *params_of(ref), train=True)
+    _, t_fast = fast.engine.forward(obs, *params_of(fast), train=True)
+    a, b = ref.engine.unpack_trace(t_ref, B), fast.engine.unpack_trace(t_fast, B)
+    mm = max((a["spikes"][l] != b["spikes"][l]).float().mean().item() for l in range(3))
+    assert mm < (2e-2 if planes == 1 else 1e-4)
