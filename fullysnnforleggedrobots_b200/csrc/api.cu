@@ -194,9 +194,9 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     in_bits = q.out_bits;
   }
   {
-    const int n = static_cast<int>(B) * p.A;
+    const int n = static_cast<int>(B);
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
+    decode_kernel<<<(n + 127) / 128, 128, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
                                                    p.T, prm->dec_w, prm->dec_b, d->dec_tanh, mu);
     }
     LAUNCH_CHECK("decode_kernel");
@@ -299,10 +299,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const int top = p.L - 1;
   {
     const LayerPlan& lp = p.layer[top];
-    if (lp.NP > 256) return fail(SNN_EINVAL, "output population wider than 256 neurons is not supported by top_scan_kernel");
-    dim3 tblk(lp.NP / 8, 256 / (lp.NP / 8));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<Bp / 32, tblk, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<Bp / 32, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
                                          p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top));
     }
@@ -340,9 +338,10 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       q.dbg = debug_mask();
       q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(8 + l) * 148 * 16 : nullptr;
       q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
-      q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = p.NCmax; q.T = p.T;
+      const int ncx = l > 0 ? p.NCdx : p.NCmax;        // hidden layers: double-buffered accumulators, narrower chunks
+      q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = ncx; q.T = p.T;
       q.B = Bi; q.Bpad = Bp; q.R = p.R;
-      q.nchunks = (lp.KP + p.NCmax - 1) / p.NCmax;
+      q.nchunks = (lp.KP + ncx - 1) / ncx;
       q.nitems = (Bp / 128) * q.nchunks;
       const int grid = q.nitems < sms ? q.nitems : sms;
       if (l > 0) {
@@ -352,7 +351,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         q.g_plane = p.ws_g_plane[slot ^ 1];
         q.db_part = dbpart_of(l - 1);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-        scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(p.NCmax), st>>>(q);
+        scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(ncx), st>>>(q);
         }
         LAUNCH_CHECK("scan_gemm_kernel<DX>");
         df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);

@@ -47,6 +47,7 @@ struct SnnPlan {
   int O, A, Pe, Pd;
   int K0, K0P;       // encoder neurons, padded
   int NCmax;         // accumulator columns per timestep in the scan-GEMMs (T * NCmax <= 512)
+  int NCdx;          // same for the double-buffered backward scan-GEMM (T * NCdx <= 256)
   int64_t B, Bpad, R;
   LayerPlan layer[SNN_MAX_LAYERS];
   size_t packed_bytes;
@@ -78,6 +79,7 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.K0 = d.obs_dim * d.en_pop;
   p.K0P = static_cast<int>(round_up(p.K0, 64));
   p.NCmax = p.T <= 5 ? 96 : (p.T <= 8 ? 64 : 32);
+  p.NCdx = p.T <= 5 ? 48 : (p.T <= 8 ? 32 : 16);
   p.B = B;
   p.Bpad = round_up(B > 0 ? B : 1, kTileM);
   p.R = p.Bpad * p.T;

@@ -67,11 +67,11 @@ struct ScanGemmParams {
 };
 
 template <int MODE> struct ScanCfg;
-template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, NBITS = 16, THREADS = 512; };
-template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
-template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
-template <> struct ScanCfg<MODE_MLP_FWD> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
-template <> struct ScanCfg<MODE_MLP_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, THREADS = 384; };
+template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA = 6, NB = 2, BP = 3, NBITS = 16, SETS = 1, THREADS = 512; };
+template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
+template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 1, THREADS = 384; };
+template <> struct ScanCfg<MODE_MLP_FWD> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
+template <> struct ScanCfg<MODE_MLP_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
 
 constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (FWD: bias, DX: db); layer widths <= 2048
 constexpr int kBitsStage = 1024;   // one A stage worth of spike words: 2 x (128 rows x 4 B)
@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   uint64_t* empty_a = full_a + C::NA;      // [NA]
   uint64_t* full_b = empty_a + C::NA;      // [NB]
   uint64_t* empty_b = full_b + C::NB;      // [NB]
-  uint64_t* acc_full = empty_b + C::NB;
-  uint64_t* acc_empty = acc_full + 1;
-  uint64_t* full_bits = acc_empty + 1;     // [NBITS]
+  uint64_t* acc_full = empty_b + C::NB;    // [SETS]: SETS == 2 double-buffers the accumulators (T * NCmax <= 256 per set)
+  uint64_t* acc_empty = acc_full + C::SETS;  // [SETS]
+  uint64_t* full_bits = acc_empty + C::SETS;     // [NBITS]
   uint64_t* empty_bits = full_bits + C::NBITS;   // [NBITS]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + C::NBITS);
 
@@ -176,8 +176,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
     }
     for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 256);
+    for (int s = 0; s < C::SETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -268,7 +267,8 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         const int n0 = c * p.NCmax;
         const int ncw = min(p.NCmax, p.NPout - n0);
         const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncw), 0, 0);
-        SNN_TWAIT(acc_empty, (it & 1) ^ 1, 0);
+        const uint32_t aset = it % C::SETS;
+        SNN_TWAIT(&acc_empty[aset], ((it / C::SETS) & 1) ^ 1, 0);
         tc_fence_after_sync();
         for (int kc = 0; kc < KC; ++kc) {
           const uint32_t sb = ib % C::NB;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
             tc_fence_after_sync();
             if (elect_one()) {
               const uint32_t a_lo = a_ring_lo + sa * (C::A_STAGE >> 4);
-              const uint32_t d = tmem_base + static_cast<uint32_t>(t * p.NCmax);
+              const uint32_t d = tmem_base + aset * (512 / C::SETS) + static_cast<uint32_t>(t * p.NCmax);
               uint32_t acc = kc > 0 ? 1u : 0u;
               if (p.dbg & 1) {
               } else if (MODE == MODE_FWD) {
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
               if (p.dbg & 16) mbar_arrive(&empty_a[sa]); else umma_commit(&empty_a[sa]);
               if (t == p.T - 1) {
                 umma_commit(&empty_b[sb]);
-                if (kc == KC - 1) umma_commit(acc_full);
+                if (kc == KC - 1) umma_commit(&acc_full[aset]);
               }
             }
             __syncwarp();
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
     const int half = (warp - 4) >> 2;          // 0: even 16-column groups, 1: odd ones
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t it = 0;
+    uint32_t it = 0, gctr = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
       const int m = item / p.nchunks, c = item - m * p.nchunks;
       const int n0 = c * p.NCmax;
@@ -334,17 +334,19 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         // the scan below reads this row's voltages [t][g] (64 B each) straight from HBM-resident traces:
         // pull them into L2 now, while the tensor core is still busy with this item's MMAs
         const size_t vstep = static_cast<size_t>(p.NPout >> 4) * p.Bpad * 16;
-        for (int g = half; g < ncw / 16; g += 2) {
+        for (int g = static_cast<int>((half + gctr) & 1u); g < ncw / 16; g += 2) {
           const float* vb = p.v_in + (static_cast<size_t>((n0 >> 4) + g) * p.Bpad + b) * 16;
           for (int t = 0; t < p.T; ++t)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<size_t>(t) * vstep));
         }
       }
-      SNN_TWAIT(acc_full, it & 1, 0);
+      const uint32_t aset = it % C::SETS;
+      SNN_TWAIT(&acc_full[aset], (it / C::SETS) & 1, 0);
       tc_fence_after_sync();
-      for (int g = half; g < ((p.dbg & 2) ? 0 : ncw / 16); g += 2) {
+      const int ng = (p.dbg & 2) ? 0 : ncw / 16;
+      for (int g = static_cast<int>((half + gctr) & 1u); g < ng; g += 2) {
         const int col0 = n0 + g * 16;
-        const uint32_t t_col = t_lane + static_cast<uint32_t>(g * 16);
+        const uint32_t t_col = t_lane + aset * (512 / C::SETS) + static_cast<uint32_t>(g * 16);
         if (MODE == MODE_FWD) {
           float cur[16], vol[16];
 #pragma unroll
@@ -483,8 +485,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           }
         }
       }
+      gctr += static_cast<uint32_t>(ncw / 16);
       tc_fence_before_sync();
-      mbar_arrive(acc_empty);
+      mbar_arrive(&acc_empty[aset]);
     }
   } else if (MODE == MODE_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 A tile)

@@ -89,23 +89,27 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
   return bits;
 }
 
-__global__ void encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
-                              const float* __restrict__ std, int B, int Bpad, int O, int P, int K0, int T,
-                              float eps, int64_t R, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
+                                                    const float* __restrict__ std, int B, int Bpad, int O, int P,
+                                                    int K0, int T, float eps, int64_t R, uint32_t* __restrict__ bits) {
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int b = blockIdx.y * blockDim.y + threadIdx.y;
   if (b >= Bpad) return;
   uint32_t sp = 0;
   if ((b < B) && (k < K0)) {
-    const float x = obs[static_cast<size_t>(b) * O + k / P], mk = mean[k], sk = std[k];
-    // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then exp
+    const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
+    const float x = obs[static_cast<size_t>(b) * O + o], mk = mean[k], sk = std[k];
+    const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
     const float d = __fsub_rn(x, mk);
-    const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), __fadd_rn(__fmul_rn(sk, sk), eps));
+    // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
+    // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
     float margin;
-    sp = regular_spikes(expf(q), T, margin);
-    // expf is good to ~2 ulp; only a membrane within ~1e-5 of the threshold could see the difference:
-    // redo those few with the correctly rounded exp
-    if (margin < 1e-5f) sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+    sp = regular_spikes(__expf(-0.5f * d * d * __frcp_rn(var)), T, margin);
+    if (margin < 4e-5f) {
+      // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then a correctly rounded exp
+      const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), var);
+      sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+    }
   }
   for (int t = 0; t < T; ++t) {
     const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
@@ -115,110 +119,136 @@ __global__ void encode_kernel(const float* __restrict__ obs, const float* __rest
 
 // ------------------------------------------------------------------ decoder
 // actor_critic.py:140-150: rate = spike count / T ; mu[b,a] = sum_p w[a,p] rate[b, a P + p] + bias[a] (; tanh)
-__global__ void decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A, int P, int T,
-                              const float* __restrict__ dec_w, const float* __restrict__ dec_b, int dec_tanh,
-                              float* __restrict__ mu) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * A) return;
-  const int b = idx / A, a = idx - b * A;
-  float acc = 0.f;
-  for (int pp = 0; pp < P; ++pp) {
-    const int n = a * P + pp;
-    int cnt = 0;
-    for (int t = 0; t < T; ++t)
-      cnt += (bits[static_cast<size_t>(n >> 5) * R + static_cast<size_t>(t) * Bpad + b] >> (n & 31)) & 1u;
-    const float rate = __fdiv_rn(static_cast<float>(cnt), static_cast<float>(T));
-    acc = __fmaf_rn(dec_w[n], rate, acc);
+__global__ void __launch_bounds__(128) decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A,
+                                                    int P, int T, const float* __restrict__ dec_w,
+                                                    const float* __restrict__ dec_b, int dec_tanh, float* __restrict__ mu) {
+  // one thread per sample: loads its T x (A*P/32) spike words (coalesced across samples), then walks the actions
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float invT = static_cast<float>(T);
+  for (int a = 0; a < A; ++a) {
+    const int n0 = a * P;
+    const int w0 = n0 >> 5, w1 = (n0 + P - 1) >> 5, sh = n0 & 31;
+    float acc = 0.f;
+    if (P <= 16) {
+      int cnt[16];
+#pragma unroll
+      for (int pp = 0; pp < 16; ++pp) cnt[pp] = 0;
+      for (int t = 0; t < T; ++t) {
+        const size_t r = static_cast<size_t>(t) * Bpad + b;
+        const uint32_t lo = __ldg(bits + static_cast<size_t>(w0) * R + r);
+        const uint32_t hi = w1 != w0 ? __ldg(bits + static_cast<size_t>(w1) * R + r) : 0u;
+        const uint32_t x = __funnelshift_r(lo, hi, sh);      // bits n0 .. n0+31 of this sample at step t
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) cnt[pp] += (x >> pp) & 1u;
+      }
+#pragma unroll
+      for (int pp = 0; pp < 16; ++pp)
+        if (pp < P) acc = __fmaf_rn(dec_w[n0 + pp], __fdiv_rn(static_cast<float>(cnt[pp]), invT), acc);
+    } else {
+      for (int pp = 0; pp < P; ++pp) {
+        const int n = n0 + pp;
+        int cnt = 0;
+        for (int t = 0; t < T; ++t)
+          cnt += (__ldg(bits + static_cast<size_t>(n >> 5) * R + static_cast<size_t>(t) * Bpad + b) >> (n & 31)) & 1u;
+        acc = __fmaf_rn(dec_w[n], __fdiv_rn(static_cast<float>(cnt), invT), acc);
+      }
+    }
+    acc = __fadd_rn(acc, dec_b[a]);
+    mu[static_cast<size_t>(b) * A + a] = dec_tanh ? tanhf(acc) : acc;
   }
-  acc = __fadd_rn(acc, dec_b[a]);
-  mu[idx] = dec_tanh ? tanhf(acc) : acc;
 }
 
 // ------------------------------------------------------------------ BPTT of the output population layer
 // g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the
 // recurrence of SURVEY.md §8a.  Writes g_c hi/lo planes as swz64 image and per-block bias partials.
+__device__ __forceinline__ float warp_col_sums16(float (&x)[16], int lane) {   // see scan_gemm.cuh
+#pragma unroll
+  for (int h = 16, n = 16; h >= 2; h >>= 1, n >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? x[i] : x[i + n / 2];
+      const float keep = up ? x[i + n / 2] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
+}
+
 __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                       int dec_tanh, const float* __restrict__ dec_w,
                                                       const float* __restrict__ volt, int B, int Bpad, int A, int P,
                                                       int NP, int T, int64_t R, uint8_t* __restrict__ g_img,
                                                       size_t g_plane, float* __restrict__ db_part) {
-  // blockDim = (NP/8 column groups [<= 32], 256/(NP/8) rows); block covers 32 rows; grid = (Bpad/32)
-  const int cg = threadIdx.x, ry = threadIdx.y, rows_per_it = blockDim.y;
-  const int n0 = cg * 8;
-  float w[8];
-  int aidx[8];
+  // block = 8 warps x 32 rows; lane = row, warp w walks the 16-column groups w, w+8, ...  grid = Bpad / 32.
+  // A warp reads 32 rows x 64 B = one contiguous 2 KiB run of the voltage trace per (t, group).
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const bool row_live = b < B;
+  const float Tf = static_cast<float>(T);
+  for (int g16 = wid; g16 < NP / 16; g16 += 8) {
+    const int n0 = g16 * 16;
+    float gup[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int n = n0 + j;
-    const bool live = n < A * P;
-    w[j] = live ? dec_w[n] : 0.f;
-    aidx[j] = live ? n / P : -1;
-  }
-  float dbacc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dbacc[j] = 0.f;
-  const float invT = static_cast<float>(T);
-  for (int rb = ry; rb < 32; rb += rows_per_it) {
-    const int b = blockIdx.x * 32 + rb;
-    const bool row_live = b < B;
-    float gup[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + j;
       gup[j] = 0.f;
-      if (row_live && aidx[j] >= 0) {
-        float G = g_mu[static_cast<size_t>(b) * A + aidx[j]];
-        if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + aidx[j]]; G = G * (1.f - m * m); }
-        gup[j] = __fdiv_rn(G * w[j], invT);
+      if (row_live && n < A * P) {
+        const int a = n / P;
+        float G = g_mu[static_cast<size_t>(b) * A + a];
+        if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
+        gup[j] = __fdiv_rn(G * dec_w[n], Tf);
       }
     }
-    float gvn[8], gcn[8];
+    float gvn[16], gcn[16], dbacc[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
+    for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; dbacc[j] = 0.f; }
+    const float* vbase = volt + (static_cast<size_t>(g16) * Bpad + b) * 16;
+    const size_t vstep = static_cast<size_t>(NP >> 4) * Bpad * 16;
     for (int t = T - 1; t >= 0; --t) {
-      const size_t r = static_cast<size_t>(t) * Bpad + b;
-      float v[8];
+      float v[16];
       if (row_live) {
-        const float4* src = reinterpret_cast<const float4*>(
-            volt + ((static_cast<size_t>(t) * (NP >> 4) + (n0 >> 4)) * Bpad + b) * 16 + (n0 & 15));
-        const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+        const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldg(src + j);
+          v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
-      float hi[8], lo[8];
+      float gc[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const float gs = gup[j] - gvn[j] * (0.75f * v[j]);
         const float win = fabsf(__fsub_rn(v[j], 0.5f)) < 0.5f ? 1.f : 0.f;
         const float keep = v[j] > 0.5f ? 0.f : 0.75f;
         const float gv = gs * win + gvn[j] * keep;
-        const float gc = gv + 0.5f * gcn[j];
-        gvn[j] = gv; gcn[j] = gc;
-        dbacc[j] += gc;
-        hi[j] = bf16_round(gc);
-        lo[j] = gc - hi[j];
+        gc[j] = gv + 0.5f * gcn[j];
+        gvn[j] = gv; gcn[j] = gc[j];
+        dbacc[j] += gc[j];
       }
-      const size_t off = swz64_offset(static_cast<int64_t>(r), n0, R);
-      *reinterpret_cast<uint4*>(g_img + off) =
+      // hi/lo planes, two 16-byte pieces per plane
+      const size_t r = static_cast<size_t>(t) * Bpad + b;
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(gc[j]); lo[j] = gc[j] - hi[j]; }
+      const size_t base = static_cast<size_t>(n0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+      const int p0 = (n0 & 63) >> 3;
+      const int sw = static_cast<int>(r & 7);
+      *reinterpret_cast<uint4*>(g_img + base + ((p0 ^ sw) << 4)) =
           make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(g_img + g_plane + off) =
+      *reinterpret_cast<uint4*>(g_img + base + (((p0 + 1) ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+      *reinterpret_cast<uint4*>(g_img + g_plane + base + ((p0 ^ sw) << 4)) =
           make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+      *reinterpret_cast<uint4*>(g_img + g_plane + base + (((p0 + 1) ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
     }
-  }
-  // reduce the bias gradient over the block's rows
-  __shared__ float sh[256 * 8];
-  float* mine = sh + (ry * blockDim.x + cg) * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) mine[j] = dbacc[j];
-  __syncthreads();
-  if (ry == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float acc = 0.f;
-      for (int y = 0; y < rows_per_it; ++y) acc += sh[(y * blockDim.x + cg) * 8 + j];
-      db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + j] = acc;
-    }
+    const float tot = warp_col_sums16(dbacc, lane);
+    if ((lane & 1) == 0) db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + (lane >> 1)] = tot;
   }
 }
 
