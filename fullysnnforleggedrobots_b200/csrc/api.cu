@@ -141,7 +141,7 @@ int launch_deferred(const Deferred& df, cudaStream_t st) {
   if (df.rows.count > 0) {
     dim3 grd((df.max_n + 31) / 32, df.rows.count);
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    multi_reduce_rows_kernel<<<grd, dim3(32, 8), 0, st>>>(df.rows);
+    multi_reduce_rows_kernel<<<grd, dim3(32, 32), 0, st>>>(df.rows);
     }
     LAUNCH_CHECK("multi_reduce_rows_kernel");
   }
@@ -162,7 +162,7 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   if (B == 0) return SNN_OK;
   uint32_t* enc_bits = reinterpret_cast<uint32_t*>(at(bits_base, p.tr_enc_bits));
   {
-    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>((p.Bpad + 7) / 8));
+    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>(p.Bpad / 128));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     encode_kernel<<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
                                        p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
@@ -194,9 +194,9 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     in_bits = q.out_bits;
   }
   {
-    const int n = static_cast<int>(B);
+    const int n = static_cast<int>(B) * p.A;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    decode_kernel<<<(n + 127) / 128, 128, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
+    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
                                                    p.T, prm->dec_w, prm->dec_b, d->dec_tanh, mu);
     }
     LAUNCH_CHECK("decode_kernel");

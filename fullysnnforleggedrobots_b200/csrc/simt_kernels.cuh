@@ -92,41 +92,49 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                                     const float* __restrict__ std, int B, int Bpad, int O, int P,
                                                     int K0, int T, float eps, int64_t R, uint32_t* __restrict__ bits) {
+  // block (32 neurons, 8 warps) covers 128 rows: each warp walks 16 rows (few, fat blocks: the per-row work is tiny)
   const int k = blockIdx.x * 32 + threadIdx.x;
-  const int b = blockIdx.y * blockDim.y + threadIdx.y;
-  if (b >= Bpad) return;
-  uint32_t sp = 0;
-  if ((b < B) && (k < K0)) {
-    const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
-    const float x = obs[static_cast<size_t>(b) * O + o], mk = mean[k], sk = std[k];
-    const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
-    const float d = __fsub_rn(x, mk);
-    // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
-    // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
-    float margin;
-    sp = regular_spikes(__expf(-0.5f * d * d * __frcp_rn(var)), T, margin);
-    if (margin < 4e-5f) {
-      // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then a correctly rounded exp
-      const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), var);
-      sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+  const bool k_live = k < K0;
+  const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
+  const float mk = k_live ? mean[k] : 0.f, sk = k_live ? std[k] : 1.f;
+  const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
+  const float inv_var = __frcp_rn(var);
+  for (int i = 0; i < 16; ++i) {
+    const int b = blockIdx.y * 128 + i * 8 + threadIdx.y;
+    if (b >= Bpad) break;
+    uint32_t sp = 0;
+    if ((b < B) && k_live) {
+      const float x = obs[static_cast<size_t>(b) * O + o];
+      const float d = __fsub_rn(x, mk);
+      // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
+      // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
+      float margin;
+      sp = regular_spikes(__expf(-0.5f * d * d * inv_var), T, margin);
+      if (margin < 4e-5f) {
+        // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then a correctly rounded exp
+        const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), var);
+        sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+      }
     }
-  }
-  for (int t = 0; t < T; ++t) {
-    const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
-    if (threadIdx.x == 0) bits[static_cast<size_t>(blockIdx.x) * R + static_cast<size_t>(t) * Bpad + b] = word;
+    for (int t = 0; t < T; ++t) {
+      const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
+      if (threadIdx.x == 0) bits[static_cast<size_t>(blockIdx.x) * R + static_cast<size_t>(t) * Bpad + b] = word;
+    }
   }
 }
 
 // ------------------------------------------------------------------ decoder
 // actor_critic.py:140-150: rate = spike count / T ; mu[b,a] = sum_p w[a,p] rate[b, a P + p] + bias[a] (; tanh)
-__global__ void __launch_bounds__(128) decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A,
+__global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A,
                                                     int P, int T, const float* __restrict__ dec_w,
                                                     const float* __restrict__ dec_b, int dec_tanh, float* __restrict__ mu) {
-  // one thread per sample: loads its T x (A*P/32) spike words (coalesced across samples), then walks the actions
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  // one thread per (action, sample), samples fastest: the <= 2 spike words an action's population spans are
+  // loaded coalesced across samples
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * A) return;
+  const int a0 = idx / B, b = idx - a0 * B;
   const float invT = static_cast<float>(T);
-  for (int a = 0; a < A; ++a) {
+  for (int a = a0; a == a0; ++a) {
     const int n0 = a * P;
     const int w0 = n0 >> 5, w1 = (n0 + P - 1) >> 5, sh = n0 & 31;
     float acc = 0.f;
@@ -176,6 +184,36 @@ __device__ __forceinline__ float warp_col_sums16(float (&x)[16], int lane) {   /
   return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
 }
 
+// one BPTT step of 16 neurons of one row: updates the recurrence state and writes the hi/lo planes of g_c
+__device__ __forceinline__ void top_scan_step(const float (&gup)[16], const float (&v)[16], float (&gvn)[16], float (&gcn)[16],
+                                              float (&dbacc)[16], uint8_t* g_img, size_t g_plane, int64_t R, size_t r, int n0) {
+  float gc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float gs = gup[j] - gvn[j] * (0.75f * v[j]);
+    const float win = fabsf(__fsub_rn(v[j], 0.5f)) < 0.5f ? 1.f : 0.f;
+    const float keep = v[j] > 0.5f ? 0.f : 0.75f;
+    const float gv = gs * win + gvn[j] * keep;
+    gc[j] = gv + 0.5f * gcn[j];
+    gvn[j] = gv; gcn[j] = gc[j];
+    dbacc[j] += gc[j];
+  }
+  float hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(gc[j]); lo[j] = gc[j] - hi[j]; }
+  const size_t base = static_cast<size_t>(n0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+  const int p0 = (n0 & 63) >> 3;
+  const int sw = static_cast<int>(r & 7);
+  *reinterpret_cast<uint4*>(g_img + base + ((p0 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+  *reinterpret_cast<uint4*>(g_img + base + (((p0 + 1) ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+  *reinterpret_cast<uint4*>(g_img + g_plane + base + ((p0 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+  *reinterpret_cast<uint4*>(g_img + g_plane + base + (((p0 + 1) ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+}
+
 __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                       int dec_tanh, const float* __restrict__ dec_w,
                                                       const float* __restrict__ volt, int B, int Bpad, int A, int P,
@@ -206,46 +244,38 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
     for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; dbacc[j] = 0.f; }
     const float* vbase = volt + (static_cast<size_t>(g16) * Bpad + b) * 16;
     const size_t vstep = static_cast<size_t>(NP >> 4) * Bpad * 16;
-    for (int t = T - 1; t >= 0; --t) {
-      float v[16];
-      if (row_live) {
-        const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep);
+    if (T <= 8) {
+      // the voltage loads do not depend on the recurrence: issue all of them first
+      float4 vall[8][4];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          vall[t][j] = (t < T && row_live) ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep) + j)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int t = 7; t >= 0; --t) {
+        if (t < T) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[4 * j] = vall[t][j].x; v[4 * j + 1] = vall[t][j].y; v[4 * j + 2] = vall[t][j].z; v[4 * j + 3] = vall[t][j].w;
+          }
+          top_scan_step(gup, v, gvn, gcn, dbacc, g_img, g_plane, R, static_cast<size_t>(t) * Bpad + b, n0);
+        }
+      }
+    } else {
+      for (int t = T - 1; t >= 0; --t) {
+        float v[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldg(src + j);
+          const float4 f = row_live ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep) + j)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        top_scan_step(gup, v, gvn, gcn, dbacc, g_img, g_plane, R, static_cast<size_t>(t) * Bpad + b, n0);
       }
-      float gc[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float gs = gup[j] - gvn[j] * (0.75f * v[j]);
-        const float win = fabsf(__fsub_rn(v[j], 0.5f)) < 0.5f ? 1.f : 0.f;
-        const float keep = v[j] > 0.5f ? 0.f : 0.75f;
-        const float gv = gs * win + gvn[j] * keep;
-        gc[j] = gv + 0.5f * gcn[j];
-        gvn[j] = gv; gcn[j] = gc[j];
-        dbacc[j] += gc[j];
-      }
-      // hi/lo planes, two 16-byte pieces per plane
-      const size_t r = static_cast<size_t>(t) * Bpad + b;
-      float hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(gc[j]); lo[j] = gc[j] - hi[j]; }
-      const size_t base = static_cast<size_t>(n0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
-      const int p0 = (n0 & 63) >> 3;
-      const int sw = static_cast<int>(r & 7);
-      *reinterpret_cast<uint4*>(g_img + base + ((p0 ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(g_img + base + (((p0 + 1) ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-      *reinterpret_cast<uint4*>(g_img + g_plane + base + ((p0 ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-      *reinterpret_cast<uint4*>(g_img + g_plane + base + (((p0 + 1) ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
     }
     const float tot = warp_col_sums16(dbacc, lane);
     if ((lane & 1) == 0) db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + (lane >> 1)] = tot;
@@ -371,19 +401,19 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
 // the backward pass defers all of its small reductions to the end instead of launching ten tiny kernels.
 struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; };
 struct RowJobs { RowJob j[12]; int count; };
-__global__ void __launch_bounds__(256) multi_reduce_rows_kernel(const RowJobs jobs) {
+__global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs jobs) {   // block (32, 32)
   const RowJob jb = jobs.j[blockIdx.y];
   const int i = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x * 32 >= jb.n) return;
   float acc = 0.f;
   if (i < jb.n)
-    for (int s = threadIdx.y; s < jb.nparts; s += 8) acc += jb.src[static_cast<size_t>(s) * jb.stride + i];
-  __shared__ float sh[8][33];
+    for (int s = threadIdx.y; s < jb.nparts; s += 32) acc += jb.src[static_cast<size_t>(s) * jb.stride + i];
+  __shared__ float sh[32][33];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && i < jb.n) {
     float t = 0.f;
-    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    for (int y = 0; y < 32; ++y) t += sh[y][threadIdx.x];
     jb.dst[i] = t;
   }
 }
