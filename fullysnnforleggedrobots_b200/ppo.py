@@ -66,6 +66,7 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         self.fused = fused
         self.fused_critic = fused_critic
+        self.overlap_critic = True          # critic kernels on a second stream (parallel CUDA-graph branch)
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -225,6 +226,7 @@ class PPO:
                 st["value"] = torch.empty(mb, dtype=torch.float32, device=dev)
                 st["critic_trace"] = torch.empty(ce.trace_bytes(mb), dtype=torch.uint8, device=dev)
                 st["critic_grads"] = ([l.weight.grad for l in ce.linears], [l.bias.grad for l in ce.linears])
+                st["side_stream"] = torch.cuda.Stream(device=dev) if self.overlap_critic else None
         self._fast_state = st
         self._graphs = {}
 
@@ -238,14 +240,26 @@ class PPO:
         em, es, ws, bs, dw, db = st["actor_tensors"]
         opt.zero_grad()
         eng = ac.actor.engine
+        ce = st["critic"]
+        side = st.get("side_stream") if ce is not None else None
+        main = torch.cuda.current_stream(dev)
+        if ce is not None:
+            # the critic chain is independent of the actor chain until the PPO head: run it on a second stream so
+            # that its kernels fill the launch / drain gaps of the actor's persistent kernels (fork/join is captured
+            # into the CUDA graph as parallel branches)
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
+            else:
+                value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
         mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
                                 db.data, train=True, out_mu=st["mu"], out_trace=st["trace"])
-        ce = st["critic"]
-        if ce is not None:
-            value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
-        else:
+        if ce is None:
             with torch.enable_grad():
                 value = ac.evaluate(f["critic_obs"][sl])
+        elif side is not None:
+            main.wait_stream(side)
         L = _lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
@@ -257,10 +271,17 @@ class PPO:
                 _p(self._stats), _p(st["scratch"]), st["scratch"].numel(), stream), "snn_ppo_head")
         # KL statistic rides in the tail of the gradient bucket (one all-reduce under data parallelism)
         opt.flat_grads[opt.n:].copy_(self._stats[2:3])
+        if ce is not None and side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
         eng.backward(f["obs"][sl], mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws],
                      [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"])
         if ce is not None:
-            ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
+            if side is not None:
+                main.wait_stream(side)
+            else:
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
         else:
             value.backward(st["g_value"].view_as(value))
         self._finish_step()
