@@ -95,6 +95,8 @@ int device_ready(int* num_sms) {
                                   static_cast<int>(scan_gemm_smem_bytes<MODE_DX_ENC>(96))));
     CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
+    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_FWD_TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(scan_gemm_smem_bytes<MODE_FWD_TA>(64))));
     CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
     CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_MLP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -177,9 +179,17 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.b_img = at(packed, lp.w_img);
     q.b_plane = lp.w_plane;
     q.b_planes = d->fwd_planes;
-    q.KP = lp.KP; q.NPout = lp.NP; q.NCmax = p.NCmax; q.T = p.T;
+    // T <= 5: spike operand staged in tensor memory (no shared-memory A reads), 64-column chunks
+    // chunk width: balanced split of the layer (e.g. 128 -> 64 + 64, not 96 + 32)
+    const int nch0 = (lp.NP + p.NCmax - 1) / p.NCmax;
+    const int ncb = static_cast<int>(round_up((lp.NP + nch0 - 1) / nch0, 32));
+    // narrow layers (<= 128 neurons): spike operand staged in TENSOR memory (tcgen05.st + TS-mode MMAs, two issuer
+    // warps) measured faster than the shared-memory operand path; wide layers: the opposite (SNN_DBG=32 forces TA)
+    const bool ta = p.T * 64 <= kTaAccCols && (lp.NP <= 128 || (debug_mask() & 32));
+    const int ncf = ta ? 64 : (ncb < p.NCmax ? ncb : p.NCmax);
+    q.KP = lp.KP; q.NPout = lp.NP; q.NCmax = ncf; q.T = p.T;
     q.B = static_cast<int>(B); q.Bpad = static_cast<int>(p.Bpad); q.R = p.R;
-    q.nchunks = (lp.NP + p.NCmax - 1) / p.NCmax;
+    q.nchunks = (lp.NP + ncf - 1) / ncf;
     q.nitems = static_cast<int>(p.Bpad / 128) * q.nchunks;
     q.dbg = debug_mask();
     q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(l) * 148 * 16 : nullptr;
@@ -188,7 +198,10 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = q.nitems < num_sms ? q.nitems : num_sms;
     { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-    scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(p.NCmax), st>>>(q);
+    if (ta)
+      scan_gemm_kernel<MODE_FWD_TA><<<grid, ScanCfg<MODE_FWD_TA>::THREADS, scan_gemm_smem_bytes<MODE_FWD_TA>(64), st>>>(q);
+    else
+      scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(ncf), st>>>(q);
     }
     LAUNCH_CHECK("scan_gemm_kernel<FWD>");
     in_bits = q.out_bits;

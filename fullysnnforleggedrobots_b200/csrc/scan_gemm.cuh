@@ -30,7 +30,7 @@
 
 namespace snn {
 
-enum { MODE_FWD = 0, MODE_DX = 1, MODE_DX_ENC = 2, MODE_MLP_FWD = 3, MODE_MLP_DX = 4 };
+enum { MODE_FWD = 0, MODE_DX = 1, MODE_DX_ENC = 2, MODE_MLP_FWD = 3, MODE_MLP_DX = 4, MODE_FWD_TA = 5 };
 
 struct ScanGemmParams {
   // A operand
@@ -71,9 +71,12 @@ template <> struct ScanCfg<MODE_FWD> { static constexpr int A_STAGE = 16384, NA 
 template <> struct ScanCfg<MODE_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
 template <> struct ScanCfg<MODE_DX_ENC> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 1, THREADS = 384; };
 template <> struct ScanCfg<MODE_MLP_FWD> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
+// forward with the spike operand in TENSOR memory (T * NCmax <= 320 accumulator columns + 6 A stages of 32 columns)
+template <> struct ScanCfg<MODE_FWD_TA> { static constexpr int A_STAGE = 0, NA = 6, NB = 4, BP = 3, NBITS = 16, SETS = 1, THREADS = 512; };
 template <> struct ScanCfg<MODE_MLP_DX> { static constexpr int A_STAGE = 32768, NA = 4, NB = 2, BP = 2, NBITS = 0, SETS = 2, THREADS = 384; };
 
 constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (FWD: bias, DX: db); layer widths <= 2048
+constexpr int kTaAccCols = 320;    // MODE_FWD_TA: TMEM columns [0, 320) = accumulators, [320, 512) = 6 A stages
 constexpr int kBitsStage = 1024;   // one A stage worth of spike words: 2 x (128 rows x 4 B)
 
 // 16 consecutive columns of one row -> hi/lo bf16 planes of a swz64 image (two 16-byte pieces per plane)
@@ -144,6 +147,8 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&x)[16], int lan
 template <int MODE>
 __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
   using C = ScanCfg<MODE>;
+  constexpr bool IS_FWD = MODE == MODE_FWD || MODE == MODE_FWD_TA;
+  constexpr bool TA = MODE == MODE_FWD_TA;
   constexpr uint32_t NBM = C::NBITS > 0 ? C::NBITS : 1;   // modulus of the spike-word ring (unused in DX modes)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -171,16 +176,16 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 
   if (tid == 0) {
     for (int s = 0; s < C::NA; ++s) {
-      mbar_init(&full_a[s], 1);
+      mbar_init(&full_a[s], TA ? 4 : 1);
       mbar_init(&empty_a[s], 1);
     }
-    for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
-    for (int s = 0; s < C::SETS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < C::NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], TA ? 2 : 1); }
+    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], TA ? 4 : 1); }
+    for (int s = 0; s < C::SETS; ++s) { mbar_init(&acc_full[s], TA ? 2 : 1); mbar_init(&acc_empty[s], 256); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
-  if (MODE == MODE_FWD) {
+  if (IS_FWD) {
     // LUT: byte of 8 spike bits -> eight bf16 {0, 1}
     for (int i = tid; i < 256; i += blockDim.x) {
       uint4 v;
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           ++ib;
           for (int t = 0; t < p.T; ++t, ++ia) {
             const size_t row0 = static_cast<size_t>(t) * p.Bpad + static_cast<size_t>(m) * 128;
-            if (MODE == MODE_FWD) {
+            if (IS_FWD) {
               // spike words of this A stage: two 512-byte runs (128 rows x one 32-column word each)
               const uint32_t s = ia % NBM;
               SNN_TWAIT(&empty_bits[s], ((ia / NBM) & 1) ^ 1, 1);
@@ -254,9 +259,11 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (TA && warp == 2)) {
     // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    // MODE_FWD_TA runs TWO issuer warps (even / odd timesteps: independent accumulators)
     {
+      const int issuer = warp - 1;
       uint32_t ib = 0, ia = 0, it = 0;
       const uint32_t dhi = smem_desc_hi(1024);
       const uint32_t a_ring_lo = smem_desc_lo(smem_u32(a_ring), 16);
@@ -274,7 +281,8 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           const uint32_t sb = ib % C::NB;
           SNN_TWAIT(&full_b[sb], (ib / C::NB) & 1, 1);
           const uint32_t b_lo = b_ring_lo + sb * (static_cast<uint32_t>(b_stage) >> 4);
-          for (int t = 0; t < p.T; ++t) {
+          for (int t = 0; t < p.T; ++t, ++ia) {
+            if (TA && (t & 1) != issuer) continue;         // TA: two issuer warps split the timesteps
             const uint32_t sa = ia % C::NA;
             SNN_TWAIT(&full_a[sa], (ia / C::NA) & 1, 2);
             tc_fence_after_sync();
@@ -283,6 +291,15 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
               const uint32_t d = tmem_base + aset * (512 / C::SETS) + static_cast<uint32_t>(t * p.NCmax);
               uint32_t acc = kc > 0 ? 1u : 0u;
               if (p.dbg & 1) {
+              } else if (TA) {
+                const uint32_t a_t = tmem_base + kTaAccCols + sa * 32;
+                for (int pl = 0; pl < p.b_planes; ++pl) {
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    umma_bf16_ts(d, a_t + k16 * 8, b_lo + pl * b_plane_lo + k16 * 2, dhi, idesc, acc);
+                    acc = 1u;
+                  }
+                }
               } else if (MODE == MODE_FWD) {
                 for (int pl = 0; pl < p.b_planes; ++pl) {
 #pragma unroll
@@ -305,14 +322,15 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
                 }
               }
               if (p.dbg & 16) mbar_arrive(&empty_a[sa]); else umma_commit(&empty_a[sa]);
-              if (t == p.T - 1) {
-                umma_commit(&empty_b[sb]);
-                if (kc == KC - 1) umma_commit(&acc_full[aset]);
-              }
             }
             __syncwarp();
-            ++ia;
           }
+          // this issuer's MMAs of the k-chunk are all issued: release the B stage / publish the accumulators
+          if (elect_one()) {
+            umma_commit(&empty_b[sb]);
+            if (kc == KC - 1) umma_commit(&acc_full[aset]);
+          }
+          __syncwarp();
           ++ib;
         }
       }
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       for (int g = static_cast<int>((half + gctr) & 1u); g < ng; g += 2) {
         const int col0 = n0 + g * 16;
         const uint32_t t_col = t_lane + aset * (512 / C::SETS) + static_cast<uint32_t>(g * 16);
-        if (MODE == MODE_FWD) {
+        if (IS_FWD) {
           float cur[16], vol[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
@@ -488,6 +506,39 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       gctr += static_cast<uint32_t>(ncw / 16);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[aset]);
+    }
+  } else if (TA && warp >= 12) {
+    // ===================================================== spike-bit expanders, tensor-memory variant
+    // thread = batch row (TMEM lane); per A stage: 64 spike bits -> 32 packed bf16x2 words -> tcgen05.st
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kTaAccCols;
+    uint32_t ia = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      for (int i = 0; i < KC * p.T; ++i, ++ia) {
+        const uint32_t s = ia % NBM;
+        SNN_TWAIT(&full_bits[s], (ia / NBM) & 1, 0);
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + s * kBitsStage);
+        const uint32_t w0 = wsrc[row], w1 = wsrc[128 + row];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bits[s]);
+        uint32_t r[32];
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 v = lut[((c8 < 4 ? w0 : w1) >> ((c8 & 3) * 8)) & 0xFFu];
+          r[4 * c8] = v.x; r[4 * c8 + 1] = v.y; r[4 * c8 + 2] = v.z; r[4 * c8 + 3] = v.w;
+        }
+        const uint32_t sa = ia % C::NA;
+        SNN_TWAIT(&empty_a[sa], ((ia / C::NA) & 1) ^ 1, 1);
+        tc_fence_after_sync();
+        if (!(p.dbg & 4)) {
+          tmem_st32(t_row + sa * 32, r);
+          tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+      }
     }
   } else if (MODE == MODE_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 A tile)
