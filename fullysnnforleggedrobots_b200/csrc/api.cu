@@ -339,6 +339,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
       q.partial = partial_of(l);
+      q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(4 + l) * 148 * 16 : nullptr;
       { ProfScope prof__(CAT_DW + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
       dw_gemm_kernel<false><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }

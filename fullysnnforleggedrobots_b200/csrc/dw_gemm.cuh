@@ -14,6 +14,15 @@
 #include "plan.cuh"
 #include "umma.cuh"
 
+#ifndef SNN_TWAIT
+#define SNN_TWAIT(bar, par, slot)                                   \
+  do {                                                              \
+    const long long t0__ = clock64();                               \
+    mbar_wait(bar, par);                                            \
+    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
+  } while (0)
+#endif
+
 namespace snn {
 
 struct DwGemmParams {
@@ -28,6 +37,7 @@ struct DwGemmParams {
   int splits;              // CTAs per output tile
   int rblocks;             // R / 64
   float* partial;          // [gridDim.x][128][256]
+  unsigned long long* dbg_out;   // optional [gridDim.x][16] wait-cycle counters (tools/role_cycles.py)
 };
 
 constexpr int kDwStages = 3;
@@ -55,6 +65,8 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + kDwBitStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long wcyc[3] = {0, 0, 0};
+  const long long t_start = clock64();
   const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
   const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
   const int kc0 = nt * 4;                                   // first 64-wide k chunk of this tile
@@ -83,23 +95,11 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // producer: warp-uniform loop, one elected lane issues the bulk copies
+    // operand producer: warp-uniform loop, one elected lane issues the bulk copies of the g_c (and dense x) tiles
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
-      if (!DENSE) {
-        const uint32_t sbit = i % kDwBitStages;
-        mbar_wait(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1);
-        if (elect_one()) {   // spike words of this stage: for every k-chunk two runs of 64 rows x 4 B
-          mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
-          uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
-          for (int w = 0; w < 2 * nck; ++w)
-            bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
-                     &full_bits[sbit]);
-        }
-        __syncwarp();
-      }
       const uint32_t s = i % kStages;
-      mbar_wait(&empty[s], ((i / kStages) & 1) ^ 1);
+      SNN_TWAIT(&empty[s], ((i / kStages) & 1) ^ 1, 1);
       if (elect_one()) {
         mbar_expect_tx(&full[s], DENSE ? static_cast<uint32_t>(32768 + nck * 16384) : 32768u);
         uint8_t* dst = ring + s * kStageBytes;
@@ -118,6 +118,21 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
       }
       __syncwarp();
     }
+  } else if (warp == 2 && !DENSE) {
+    // spike-word producer, decoupled from the operand producer so that it runs the full depth of its ring ahead
+    uint32_t i = 0;
+    for (int rb = rb0; rb < rb1; ++rb, ++i) {
+      const uint32_t sbit = i % kDwBitStages;
+      SNN_TWAIT(&empty_bits[sbit], ((i / kDwBitStages) & 1) ^ 1, 0);
+      if (elect_one()) {   // for every k-chunk two runs of 64 rows x 4 B
+        mbar_expect_tx(&full_bits[sbit], static_cast<uint32_t>(nck * 512));
+        uint8_t* bd = bits_ring + sbit * kDwBitStageBytes;
+        for (int w = 0; w < 2 * nck; ++w)
+          bulk_g2s(bd + w * 256, p.x_bits + static_cast<size_t>(2 * kc0 + w) * p.R + static_cast<size_t>(rb) * 64, 256u,
+                   &full_bits[sbit]);
+      }
+      __syncwarp();
+    }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform loop, one elected lane issues
     const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), 1, 1);
@@ -126,7 +141,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
       const uint32_t s = i % kStages;
-      mbar_wait(&full[s], (i / kStages) & 1);
+      SNN_TWAIT(&full[s], (i / kStages) & 1, 0);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint32_t a_lo = ring_lo + s * (kStageBytes >> 4);
@@ -154,15 +169,16 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     }
     if (rb1 <= rb0 && elect_one()) umma_commit(acc_full);
   } else if (warp >= 4) {
-    // spike-bit expanders: warp ew owns every eighth stage and expands all of it (64 rows x nck k-chunks);
-    // warps 4-7 also run the epilogue once their stages are done
+    // spike-bit expanders: warp ew (< kStages) owns ring slot ew, i.e. every kStages-th stage, and expands all of
+    // it (64 rows x nck k-chunks).  One warp per slot keeps each slot's uses in order: a warp can never wait on an
+    // mbarrier phase that is two phases ahead (parity aliasing).  Warps 4-7 run the epilogue afterwards.
     const int ew = warp - 4;
     const int sw = lane & 7;
     uint32_t i = 0;
     for (int rb = rb0; rb < (DENSE ? rb0 : rb1); ++rb, ++i) {
-      if (static_cast<int>(i & 7) != ew) continue;
+      if (static_cast<int>(i % kStages) != ew) continue;
       const uint32_t sbit = i % kDwBitStages;
-      mbar_wait(&full_bits[sbit], (i / kDwBitStages) & 1);
+      SNN_TWAIT(&full_bits[sbit], (i / kDwBitStages) & 1, 0);
       const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + sbit * kDwBitStageBytes);
       uint32_t w[2][8];
 #pragma unroll
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bits[sbit]);
       const uint32_t s = i % kStages;
-      mbar_wait(&empty[s], ((i / kStages) & 1) ^ 1);
+      SNN_TWAIT(&empty[s], ((i / kStages) & 1) ^ 1, 1);
       uint8_t* bst = ring + s * kStageBytes + 32768;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -212,6 +228,12 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  }
+  if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 3);
+    unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
+    o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
+    o[3] = static_cast<unsigned long long>(clock64() - t_start);
   }
   tc_fence_before_sync();
   __syncthreads();

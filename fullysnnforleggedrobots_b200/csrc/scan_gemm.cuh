@@ -137,12 +137,14 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&x)[16], int lan
   return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
 }
 
+#ifndef SNN_TWAIT
 #define SNN_TWAIT(bar, par, slot)                                   \
   do {                                                              \
     const long long t0__ = clock64();                               \
     mbar_wait(bar, par);                                            \
     wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
   } while (0)
+#endif
 
 template <int MODE>
 __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
@@ -366,9 +368,9 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         const int col0 = n0 + g * 16;
         const uint32_t t_col = t_lane + aset * (512 / C::SETS) + static_cast<uint32_t>(g * 16);
         if (IS_FWD) {
-          float cur[16], vol[16];
+          float cur[16], vol[16], bia[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
+          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; bia[j] = s_col[col0 + j]; }
           uint32_t sprev = 0;
           uint32_t x[16], xn[16];
           tmem_ld16(t_col, x);
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
             uint32_t word = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float syn = __fadd_rn(__uint_as_float(x[j]), s_col[col0 + j]);
+              const float syn = __fadd_rn(__uint_as_float(x[j]), bia[j]);
               const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
               const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
               cur[j] = cj;

@@ -42,8 +42,8 @@ for slot in range(16):
     x = d[slot]
     if x.sum() == 0:
         continue
-    kind = "fwd" if slot < 8 else "dx"
-    print(f" {kind} layer {slot % 8}:")
+    kind = "fwd" if slot < 4 else ("dw" if slot < 8 else "dx")
+    print(f" {kind} layer {slot % 4 if slot < 8 else slot % 8}:")
     for r in range(4):
         tot = x[:, r, 3].mean().item() / 1e3
         if tot == 0:
