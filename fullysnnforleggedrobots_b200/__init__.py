@@ -9,8 +9,8 @@ from .actor import PopSpikeActor  # noqa: F401
 from .actor_critic import (ActorCritic, ActorCriticAMP, ActorCriticCassie, ActorCriticHumanoid,  # noqa: F401
                            ActorCriticRMA, VARIANTS)
 from .engine import CriticEngine, SnnEngine, gae  # noqa: F401
-from .ppo import PPO  # noqa: F401
-from .storage import RolloutStorage  # noqa: F401
+from .ppo import PPO, PPORMA  # noqa: F401
+from .storage import RolloutStorage, RolloutStorageRMA  # noqa: F401
 
 __all__ = ["PopSpikeActor", "SnnEngine", "CriticEngine", "gae", "ActorCritic", "ActorCriticAMP", "ActorCriticCassie",
-           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "RolloutStorage"]
+           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "RolloutStorage", "RolloutStorageRMA"]

@@ -28,7 +28,7 @@ import torch.nn as nn
 from . import _lib
 from .engine import CriticEngine
 from .optim import FlatAdam
-from .storage import RolloutStorage
+from .storage import RolloutStorage, RolloutStorageRMA
 
 
 def _p(t):
@@ -355,3 +355,97 @@ class PPO:
         self._lr = self.optimizer.sync_lr_from_device()
         self.storage.clear()
         return stats[5] / num_updates, stats[4] / num_updates
+
+
+class PPORMA(PPO):
+    """RMA fork's PPO (RMA/quadruped-robot-master/rl-robotics/rsl_rl/rsl_rl/algorithms/ppo.py:41-221): the policy acts
+    on (obs, privileged_obs), and every minibatch step is followed by `num_adaptation_module_substeps` regression
+    steps of the adaptation module onto the (detached) privileged-encoder latent with a second Adam (:200-213).
+    The actor's input needs a gradient (it contains the latent), so this class uses the autograd path: the spiking
+    actor still runs on the sm_100a kernels, snn_bwd additionally returns d loss / d actor-input."""
+
+    def __init__(self, actor_critic, num_adaptation_module_substeps=1, **kwargs):
+        kwargs["fused"] = False
+        super().__init__(actor_critic, **kwargs)
+        self.num_adaptation_module_substeps = num_adaptation_module_substeps
+        self.adaptation_optimizer = torch.optim.Adam(self.actor_critic.adaptation_module.parameters(),
+                                                     lr=kwargs.get("learning_rate", 1e-3))
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
+                     action_shape):
+        self.storage = RolloutStorageRMA(num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape,
+                                         obs_history_shape, action_shape, self.device)
+        if self.dp is not None:
+            self.storage.advantage_stats_allreduce = self.dp.allreduce_sum
+
+    def act(self, obs, privileged_obs, obs_history):
+        ac = self.actor_critic
+        self.transition.actions = ac.act(obs, privileged_obs).detach()
+        self.transition.values = ac.evaluate(obs, privileged_obs).detach()
+        self.transition.actions_log_prob = ac.get_actions_log_prob(self.transition.actions).detach()
+        self.transition.action_mean = ac.action_mean.detach()
+        self.transition.action_sigma = ac.action_std.detach()
+        self.transition.observations = obs
+        self.transition.critic_observations = obs
+        self.transition.privileged_observations = privileged_obs
+        self.transition.observation_histories = obs_history
+        return self.transition.actions
+
+    def compute_returns(self, last_critic_obs, last_critic_privileged_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs, last_critic_privileged_obs).detach()
+        self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    def losses(self, batch):
+        (obs_batch, critic_obs_batch, privileged_obs_batch, obs_history_batch, actions_batch, target_values_batch,
+         advantages_batch, returns_batch, old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, hid_states_batch,
+         masks_batch) = batch
+        ac = self.actor_critic
+        ac.act(obs_batch, privileged_obs_batch, masks=masks_batch, hidden_states=hid_states_batch[0])
+        actions_log_prob_batch = ac.get_actions_log_prob(actions_batch)
+        value_batch = ac.evaluate(critic_obs_batch, privileged_obs_batch, masks=masks_batch,
+                                  hidden_states=hid_states_batch[1])
+        mu_batch, sigma_batch, entropy_batch = ac.action_mean, ac.action_std, ac.entropy
+        kl_mean = None
+        if self.desired_kl is not None and self.schedule == 'adaptive':
+            with torch.no_grad():
+                kl = torch.sum(torch.log(sigma_batch / old_sigma_batch + 1.e-5)
+                               + (torch.square(old_sigma_batch) + torch.square(old_mu_batch - mu_batch))
+                               / (2.0 * torch.square(sigma_batch)) - 0.5, axis=-1)
+                kl_mean = torch.mean(kl)
+        ratio = torch.exp(actions_log_prob_batch - torch.squeeze(old_actions_log_prob_batch))
+        surrogate = -torch.squeeze(advantages_batch) * ratio
+        surrogate_clipped = -torch.squeeze(advantages_batch) * torch.clamp(ratio, 1.0 - self.clip_param,
+                                                                           1.0 + self.clip_param)
+        surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
+        if self.use_clipped_value_loss:
+            value_clipped = target_values_batch + (value_batch - target_values_batch).clamp(-self.clip_param,
+                                                                                            self.clip_param)
+            value_loss = torch.max((value_batch - returns_batch).pow(2), (value_clipped - returns_batch).pow(2)).mean()
+        else:
+            value_loss = (returns_batch - value_batch).pow(2).mean()
+        loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_batch.mean()
+        return loss, surrogate_loss, value_loss, kl_mean
+
+    def update(self):
+        self._stats.zero_()
+        self.optimizer.set_lr(self._lr)
+        ac = self.actor_critic
+        adapt_sum = torch.zeros((), device=self.optimizer.flat_params.device)
+        for batch in self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs):
+            self._step_generic(batch)
+            privileged_obs_batch, obs_history_batch = batch[2], batch[3]
+            for _ in range(self.num_adaptation_module_substeps):
+                adaptation_pred = ac.adaptation_module(obs_history_batch)
+                with torch.no_grad():
+                    adaptation_target = ac.env_factor_encoder(privileged_obs_batch)
+                adaptation_loss = torch.nn.functional.mse_loss(adaptation_pred, adaptation_target)
+                self.optimizer.zero_grad()             # gradients are views of the flat bucket: zero, never None
+                adaptation_loss.backward()
+                self.adaptation_optimizer.step()
+                adapt_sum += adaptation_loss.detach()
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        stats = self._stats.tolist()
+        self._lr = self.optimizer.sync_lr_from_device()
+        self.storage.clear()
+        return (stats[5] / num_updates, stats[4] / num_updates,
+                float(adapt_sum) / (num_updates * self.num_adaptation_module_substeps))

@@ -29,6 +29,7 @@ class RolloutStorage:
             self.action_sigma = None
             self.hidden_states = None
             self.observation_histories = None      # RMA only
+            self.privileged_observations = None    # RMA only
 
         def clear(self):
             self.__init__()
@@ -137,15 +138,47 @@ class RolloutStorage:
         take = lambda t: t.flatten(0, 1).index_select(0, indices)
         obs = take(self.observations)
         crit = take(self.privileged_observations) if self.privileged_observations is not None else obs
-        hist = take(self.observation_histories) if self.observation_histories is not None else None
         actions, values, returns = take(self.actions), take(self.values), take(self.returns)
         logp, adv, mu, sigma = take(self.actions_log_prob), take(self.advantages), take(self.mu), take(self.sigma)
         for _ in range(num_epochs):
             for i in range(num_mini_batches):
                 sl = slice(i * mini_batch_size, (i + 1) * mini_batch_size)
-                if hist is None:
-                    yield (obs[sl], crit[sl], actions[sl], values[sl], adv[sl], returns[sl], logp[sl], mu[sl],
-                           sigma[sl], (None, None), None)
-                else:   # RMA 13-tuple (RMA storage/rollout_storage.py:210-211)
-                    yield (obs[sl], crit[sl], hist[sl], actions[sl], values[sl], adv[sl], returns[sl], logp[sl],
-                           mu[sl], sigma[sl], (None, None), None, None)
+                yield (obs[sl], crit[sl], actions[sl], values[sl], adv[sl], returns[sl], logp[sl], mu[sl],
+                       sigma[sl], (None, None), None)
+
+
+class RolloutStorageRMA(RolloutStorage):
+    """RMA fork's storage (RMA/quadruped-robot-master/rl-robotics/rsl_rl/rsl_rl/storage/rollout_storage.py:38-269):
+    privileged observations and observation histories are always stored, the critic sees the plain observations,
+    and the generator yields the 13-tuple of :210-211."""
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, obs_history_shape,
+                 actions_shape, device='cpu'):
+        super().__init__(num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape, device,
+                         obs_history_shape=obs_history_shape)
+
+    def add_transitions(self, transition):
+        # RMA keeps the privileged observations in their own field (reference :113-115)
+        t = transition
+        crit = t.critic_observations
+        t.critic_observations = getattr(t, "privileged_observations", None)
+        try:
+            super().add_transitions(t)
+        finally:
+            t.critic_observations = crit
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8):
+        batch_size = self.num_envs * self.num_transitions_per_env
+        mini_batch_size = batch_size // num_mini_batches
+        indices = torch.randperm(num_mini_batches * mini_batch_size, requires_grad=False, device=self.device)
+        take = lambda t: t.flatten(0, 1).index_select(0, indices)
+        obs = take(self.observations)
+        priv = take(self.privileged_observations)
+        hist = take(self.observation_histories)
+        actions, values, returns = take(self.actions), take(self.values), take(self.returns)
+        logp, adv, mu, sigma = take(self.actions_log_prob), take(self.advantages), take(self.mu), take(self.sigma)
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                sl = slice(i * mini_batch_size, (i + 1) * mini_batch_size)
+                yield (obs[sl], obs[sl], priv[sl], hist[sl], actions[sl], values[sl], adv[sl], returns[sl], logp[sl],
+                       mu[sl], sigma[sl], (None, None), None)

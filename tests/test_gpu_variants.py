@@ -1,0 +1,114 @@
+"""The four fork variants of ActorCritic / PPO on the GPU: RMA's privileged-latent path (d loss / d actor-input flows
+into env_factor_encoder), HUMANOID's encoder epsilon, CASSIE's tanh, AMP's fixed_std — gradients checked against a
+CPU composite of plain PyTorch MLPs and the spiking-actor oracle on the same weights."""
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import snn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu_twin_grads(ac, actor_in_fn, critic_in_fn, G, H, enc_eps=0.0, dec_tanh=False):
+    """loss = sum(mu * G) + sum(value * H) on CPU with identical weights; returns {param name: grad}."""
+    sd = {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}
+    leaves = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+
+    def mlp(prefix, x):
+        i = 0
+        while f"{prefix}.{i}.weight" in leaves:
+            x = torch.addmm(leaves[f"{prefix}.{i}.bias"], x, leaves[f"{prefix}.{i}.weight"].t())
+            if f"{prefix}.{i + 2}.weight" in leaves:
+                x = torch.nn.functional.elu(x)
+            i += 2
+        return x
+
+    p = O.ActorParams.from_state_dict(leaves, spike_ts=5, enc_eps=enc_eps, dec_tanh=dec_tanh)
+    # from_state_dict detaches: rebuild with the leaves themselves
+    ws, bs, i = [], [], 0
+    while f"actor.snn.hidden_layers.{i}.weight" in leaves:
+        ws.append(leaves[f"actor.snn.hidden_layers.{i}.weight"]); bs.append(leaves[f"actor.snn.hidden_layers.{i}.bias"]); i += 1
+    ws.append(leaves["actor.snn.out_pop_layer.weight"]); bs.append(leaves["actor.snn.out_pop_layer.bias"])
+    p = O.ActorParams(leaves["actor.encoder.mean"], leaves["actor.encoder.std"], ws, bs,
+                      leaves["actor.decoder.decoder.weight"], leaves["actor.decoder.decoder.bias"], leaves["actor.log_std"],
+                      spike_ts=5, enc_eps=enc_eps, dec_tanh=dec_tanh)
+    mu, _ = O.actor_forward_autograd(actor_in_fn(mlp), p)
+    value = mlp("critic", critic_in_fn(mlp))
+    ((mu * G).sum() + (value * H).sum()).backward()
+    return mu.detach(), value.detach(), {k: v.grad for k, v in leaves.items() if v.grad is not None}
+
+
+def test_rma_latent_gradient_path():
+    from fullysnnforleggedrobots_b200 import ActorCriticRMA
+    torch.manual_seed(11)
+    B, no, npriv, nh, na = 96, 20, 9, 30, 4
+    ac = ActorCriticRMA(no, npriv, nh, na, actor_hidden_dims=[64, 32], critic_hidden_dims=[32, 16],
+                        encoder_hidden_dims=[24, 12], adaptation_hidden_dims=[24, 12], encoder_latent_dims=6).cuda()
+    obs, priv = torch.randn(B, no), torch.randn(B, npriv)
+    G, H = torch.randn(B, na), torch.randn(B, 1)
+    ac.update_distribution(obs.cuda(), priv.cuda())
+    mu = ac.action_mean
+    value = ac.evaluate(obs.cuda(), priv.cuda())
+    ((mu * G.cuda()).sum() + (value * H.cuda()).sum()).backward()
+    lat = lambda mlp: mlp("env_factor_encoder", priv)
+    mu_ref, v_ref, gr = cpu_twin_grads(ac, lambda mlp: torch.cat((obs, lat(mlp)), -1),
+                                       lambda mlp: torch.cat((obs, lat(mlp)), -1), G, H)
+    assert rel_err(mu.detach().cpu(), mu_ref) < 1e-4
+    assert rel_err(value.detach().cpu(), v_ref) < 1e-4
+    for name, prm in ac.named_parameters():
+        if name.startswith("encoder."):        # alias of env_factor_encoder (registered twice, like the reference)
+            continue
+        if name in gr:
+            assert rel_err(prm.grad.cpu(), gr[name]) < 2e-4, name
+    assert ac.env_factor_encoder[0].weight.grad.abs().max() > 0        # the latent path carries gradient
+    assert ac.adaptation_module[0].weight.grad is None
+    pol = {}
+    a = ac.act_inference(obs.cuda(), torch.randn(B, nh).cuda(), policy_info=pol)
+    assert a.shape == (B, na) and "latents" in pol
+
+
+def test_rma_ppo_update_runs_and_trains_adaptation_module():
+    from fullysnnforleggedrobots_b200 import PPORMA, ActorCriticRMA
+    torch.manual_seed(12)
+    N, S, no, npriv, nh, na = 64, 6, 20, 9, 30, 4
+    ac = ActorCriticRMA(no, npriv, nh, na, actor_hidden_dims=[64, 32], critic_hidden_dims=[32, 16],
+                        encoder_hidden_dims=[24, 12], adaptation_hidden_dims=[24, 12], encoder_latent_dims=6)
+    alg = PPORMA(ac, num_learning_epochs=2, num_mini_batches=2, entropy_coef=0.01, schedule="adaptive", device="cuda",
+                 num_adaptation_module_substeps=2)
+    alg.init_storage(N, S, [no], [npriv], [nh], [na])
+    w0 = ac.adaptation_module[0].weight.detach().clone()
+    e0 = ac.env_factor_encoder[0].weight.detach().clone()
+    with torch.inference_mode():
+        for _ in range(S):
+            obs, priv, hist = torch.randn(N, no).cuda(), torch.randn(N, npriv).cuda(), torch.randn(N, nh).cuda()
+            alg.act(obs, priv, hist)
+            alg.process_env_step(torch.randn(N).cuda(), (torch.rand(N) < 0.1).cuda(), {})
+        alg.compute_returns(obs, priv)
+    vl, sl, al = alg.update()
+    assert all(x == x for x in (vl, sl, al)) and al > 0
+    assert not torch.equal(ac.adaptation_module[0].weight, w0)
+    assert not torch.equal(ac.env_factor_encoder[0].weight, e0)
+    assert all(torch.isfinite(p).all() for p in ac.parameters())
+
+
+@pytest.mark.parametrize("variant,enc_eps,dec_tanh", [("amp", 0.0, False), ("humanoid", 1e-5, False), ("cassie", 0.0, True)])
+def test_fork_variants_match_cpu_twin(variant, enc_eps, dec_tanh):
+    from fullysnnforleggedrobots_b200 import VARIANTS
+    torch.manual_seed(13)
+    B, no, na = 80, 14, 3
+    ac = VARIANTS[variant](no, no, na, actor_hidden_dims=[48, 24], critic_hidden_dims=[32, 16]).cuda()
+    obs = torch.randn(B, no)
+    G, H = torch.randn(B, na), torch.randn(B, 1)
+    ac.update_distribution(obs.cuda())
+    mu, value = ac.action_mean, ac.evaluate(obs.cuda())
+    ((mu * G.cuda()).sum() + (value * H.cuda()).sum()).backward()
+    mu_ref, v_ref, gr = cpu_twin_grads(ac, lambda mlp: obs, lambda mlp: obs, G, H, enc_eps=enc_eps, dec_tanh=dec_tanh)
+    assert rel_err(mu.detach().cpu(), mu_ref) < 1e-4
+    for name, prm in ac.named_parameters():
+        if name in gr:
+            assert rel_err(prm.grad.cpu(), gr[name]) < 2e-4, name
+    assert ac.std.grad is None                       # dead parameter in SNN mode, as in the reference
+    if variant == "amp":
+        fixed = VARIANTS[variant](no, no, na, actor_hidden_dims=[16], critic_hidden_dims=[16], fixed_std=True)
+        assert not isinstance(fixed.std, torch.nn.Parameter) and fixed.fixed_std
