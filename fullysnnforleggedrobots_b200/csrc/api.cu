@@ -152,7 +152,7 @@ int launch_deferred(const Deferred& df, cudaStream_t st) {
 
 int plan_for(const SnnDesc* d, int64_t B, int num_sms, SnnPlan* p) {
   if (d == nullptr) return fail(SNN_EINVAL, "null descriptor");
-  if (make_plan(*d, B, num_sms, p) != SNN_OK) return fail(SNN_EINVAL, "unsupported SnnDesc (dims, spike_ts 1..16, planes 1..3)");
+  if (make_plan(*d, B, num_sms, p) != SNN_OK) return fail(SNN_EINVAL, "unsupported SnnDesc (dims, spike_ts 1..32, planes 1..3)");
   return SNN_OK;
 }
 
@@ -364,6 +364,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         q.g_img = at(workspace, p.ws_g[slot ^ 1]);
         q.g_plane = p.ws_g_plane[slot ^ 1];
         q.db_part = dbpart_of(l - 1);
+        q.sets = p.T * ncx <= 256 ? 2 : 1;
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(ncx), st>>>(q);
         }

@@ -18,7 +18,7 @@ namespace snn {
 
 constexpr int kTileM = 128;       // batch rows per MMA tile (UMMA_M, cta_group::1)
 constexpr int kChunkK = 64;       // bf16 elements per 128-byte swizzled row
-constexpr int kMaxT = 16;
+constexpr int kMaxT = 32;
 
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -78,8 +78,8 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.O = d.obs_dim; p.A = d.act_dim; p.Pe = d.en_pop; p.Pd = d.de_pop;
   p.K0 = d.obs_dim * d.en_pop;
   p.K0P = static_cast<int>(round_up(p.K0, 64));
-  p.NCmax = p.T <= 5 ? 96 : (p.T <= 8 ? 64 : 32);
-  p.NCdx = p.T <= 5 ? 48 : (p.T <= 8 ? 32 : 16);
+  p.NCmax = p.T <= 5 ? 96 : (p.T <= 8 ? 64 : (p.T <= 16 ? 32 : 16));
+  p.NCdx = p.T <= 5 ? 48 : (p.T <= 8 ? 32 : 16);      // T > 16: single accumulator set (T * 16 > 256)
   p.B = B;
   p.Bpad = round_up(B > 0 ? B : 1, kTileM);
   p.R = p.Bpad * p.T;

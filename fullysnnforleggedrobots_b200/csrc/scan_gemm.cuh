@@ -49,6 +49,7 @@ struct ScanGemmParams {
   int64_t R;                // T * Bpad
   int nitems, nchunks;
   unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
+  int sets;                 // accumulator sets actually used (<= ScanCfg::SETS); 0 = ScanCfg::SETS
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand
   // FWD
   const float* bias;        // [NPout]
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
+  const uint32_t nsets = (C::SETS == 2 && p.sets != 1) ? 2u : 1u;
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
 
@@ -276,8 +278,8 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
         const int n0 = c * p.NCmax;
         const int ncw = min(p.NCmax, p.NPout - n0);
         const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncw), 0, 0);
-        const uint32_t aset = it % C::SETS;
-        SNN_TWAIT(&acc_empty[aset], ((it / C::SETS) & 1) ^ 1, 0);
+        const uint32_t aset = it % nsets;
+        SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
         tc_fence_after_sync();
         for (int kc = 0; kc < KC; ++kc) {
           const uint32_t sb = ib % C::NB;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
             tc_fence_after_sync();
             if (elect_one()) {
               const uint32_t a_lo = a_ring_lo + sa * (C::A_STAGE >> 4);
-              const uint32_t d = tmem_base + aset * (512 / C::SETS) + static_cast<uint32_t>(t * p.NCmax);
+              const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(t * p.NCmax);
               uint32_t acc = kc > 0 ? 1u : 0u;
               if (p.dbg & 1) {
               } else if (TA) {
@@ -360,13 +362,13 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
             asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + static_cast<size_t>(t) * vstep));
         }
       }
-      const uint32_t aset = it % C::SETS;
-      SNN_TWAIT(&acc_full[aset], (it / C::SETS) & 1, 0);
+      const uint32_t aset = it % nsets;
+      SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
       const int ng = (p.dbg & 2) ? 0 : ncw / 16;
       for (int g = static_cast<int>((half + gctr) & 1u); g < ng; g += 2) {
         const int col0 = n0 + g * 16;
-        const uint32_t t_col = t_lane + aset * (512 / C::SETS) + static_cast<uint32_t>(g * 16);
+        const uint32_t t_col = t_lane + aset * 256 + static_cast<uint32_t>(g * 16);
         if (IS_FWD) {
           float cur[16], vol[16], bia[16];
 #pragma unroll

@@ -43,7 +43,7 @@ typedef struct SnnDesc {
   int32_t de_pop;                  /* decoder population per action  (reference: 10)        */
   int32_t num_hidden;              /* number of hidden LIF layers (AMP:192-214)            */
   int32_t hidden[SNN_MAX_LAYERS];  /* hidden layer widths                                  */
-  int32_t spike_ts;                /* T: spike timesteps (reference: 5), 1..16             */
+  int32_t spike_ts;                /* T: spike timesteps (reference: 5), 1..32             */
   int32_t dec_tanh;                /* 1: tanh on decoder output (CASSIE copy :147)         */
   float enc_eps;                   /* added to std^2 in the encoder (HUMANOID copy :107)   */
   int32_t fwd_planes;              /* bf16 planes per fp32 weight in forward: 3 = lossless

@@ -131,3 +131,30 @@ def test_reduced_plane_modes_stay_close(planes):
     a, b = ref.engine.unpack_trace(t_ref, B), fast.engine.unpack_trace(t_fast, B)
     mm = max((a["spikes"][l] != b["spikes"][l]).float().mean().item() for l in range(3))
     assert mm < (2e-2 if planes == 1 else 1e-4)
+
+
+@pytest.mark.parametrize("T,B", [(10, 300), (20, 257), (32, 64), (1, 40)])
+def test_other_spike_timestep_counts_match_oracle(T, B):
+    """BASELINE.json configs[4] sweeps T = 5 / 10 / 20; the kernels support 1..32 (narrower accumulator chunks)."""
+    from fullysnnforleggedrobots_b200 import PopSpikeActor
+    from oracle import snn_oracle as O
+    torch.manual_seed(T)
+    actor = PopSpikeActor(12, 3, 10, 10, [64, 48], (-5, 5), math.sqrt(0.15), spike_ts=T).cuda()
+    obs = torch.randn(B, 12)
+    G = torch.randn(B, 3)
+    x = obs.cuda().requires_grad_(True)
+    mu, _ = actor(x)
+    (mu * G.cuda()).sum().backward()
+    sd = {"actor." + k: v.detach().cpu() for k, v in actor.state_dict().items()}
+    p = O.ActorParams.from_state_dict(sd, spike_ts=T)
+    mu_ref, _, tr = O.actor_forward(obs, p, want_traces=True)
+    gr = O.actor_backward(obs, p, tr, G, need_dobs=True)
+    flipped = ((mu.detach().cpu() - mu_ref).abs() > 1e-4 * mu_ref.abs().max()).any(dim=1).float().mean().item()
+    assert flipped <= 0.01
+    if flipped == 0:
+        layers = actor.snn.linear_layers()
+        for l in range(3):
+            assert rel_err(layers[l].weight.grad.cpu(), gr["weights"][l]) < 1e-4, f"dW{l}"
+            assert rel_err(layers[l].bias.grad.cpu(), gr["biases"][l]) < 1e-4, f"db{l}"
+        assert rel_err(actor.encoder.mean.grad.cpu(), gr["enc_mean"]) < 1e-4
+        assert rel_err(x.grad.cpu(), gr["obs"]) < 1e-4

@@ -37,7 +37,7 @@ def test_size_queries_without_gpu():
     t1, t2 = L.snn_trace_bytes(C.byref(eng.desc), 128), L.snn_trace_bytes(C.byref(eng.desc), 129)
     assert 0 < t1 < t2 and t2 == L.snn_trace_bytes(C.byref(eng.desc), 256)      # rows pad to 128
     assert L.snn_workspace_bytes(C.byref(eng.desc), 4096, 1) > L.snn_workspace_bytes(C.byref(eng.desc), 4096, 0)
-    bad = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=40)                      # unsupported T
+    bad = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=40)                      # unsupported T (> 32)
     assert L.snn_trace_bytes(C.byref(bad.desc), 128) == 0
 
 
