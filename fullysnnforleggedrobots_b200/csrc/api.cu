@@ -166,11 +166,16 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>(p.Bpad / 128));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    encode_kernel<<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
-                                       p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+    if (p.T == 5)
+      encode_kernel<5><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
+                                            p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+    else
+      encode_kernel<0><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
+                                            p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
     }
     LAUNCH_CHECK("encode_kernel");
   }
+  if (debug_mask() & 64) return SNN_OK;      // timing experiments: encoder only
   const uint32_t* in_bits = enc_bits;
   for (int l = 0; l < p.L; ++l) {
     const LayerPlan& lp = p.layer[l];

@@ -77,18 +77,32 @@ __device__ __forceinline__ float pop_activation_fast(float x, float mean, float 
   return expf(-0.5f * d * d / (std * std + eps));
 }
 
+template <int TT>
 __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin) {
   float u = 0.f;
   uint32_t bits = 0;
   margin = 1.f;
-  for (int t = 0; t < T; ++t) {
-    u = __fadd_rn(u, a);
-    margin = fminf(margin, fabsf(u - 0.999f));
-    if (u > 0.999f) { bits |= 1u << t; u = __fsub_rn(u, 0.999f); }
+  if (TT > 0) {
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      u = __fadd_rn(u, a);
+      margin = fminf(margin, fabsf(u - 0.999f));
+      const bool s = u > 0.999f;
+      bits |= s ? (1u << t) : 0u;
+      u = s ? __fsub_rn(u, 0.999f) : u;
+    }
+  } else {
+    for (int t = 0; t < T; ++t) {
+      u = __fadd_rn(u, a);
+      margin = fminf(margin, fabsf(u - 0.999f));
+      if (u > 0.999f) { bits |= 1u << t; u = __fsub_rn(u, 0.999f); }
+    }
   }
   return bits;
 }
 
+// TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T
+template <int TT>
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                                     const float* __restrict__ std, int B, int Bpad, int O, int P,
                                                     int K0, int T, float eps, int64_t R, uint32_t* __restrict__ bits) {
@@ -98,27 +112,32 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ o
   const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
   const float mk = k_live ? mean[k] : 0.f, sk = k_live ? std[k] : 1.f;
   const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
-  const float inv_var = __frcp_rn(var);
+  const float nh_inv_var = -0.5f * __frcp_rn(var);
+  const int b0 = blockIdx.y * 128 + threadIdx.y;
+  const float* xp = obs + static_cast<size_t>(b0) * O + o;
+  uint32_t* wp = bits + static_cast<size_t>(blockIdx.x) * R + b0;
+  const int nt = TT > 0 ? TT : T;
+#pragma unroll 4
   for (int i = 0; i < 16; ++i) {
-    const int b = blockIdx.y * 128 + i * 8 + threadIdx.y;
+    const int b = b0 + i * 8;
     if (b >= Bpad) break;
     uint32_t sp = 0;
     if ((b < B) && k_live) {
-      const float x = obs[static_cast<size_t>(b) * O + o];
-      const float d = __fsub_rn(x, mk);
+      const float d = __fsub_rn(xp[static_cast<size_t>(i) * 8 * O], mk);
       // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
       // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
       float margin;
-      sp = regular_spikes(__expf(-0.5f * d * d * inv_var), T, margin);
+      sp = regular_spikes<TT>(__expf(d * d * nh_inv_var), T, margin);
       if (margin < 4e-5f) {
         // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then a correctly rounded exp
         const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), var);
-        sp = regular_spikes(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+        sp = regular_spikes<0>(static_cast<float>(exp(static_cast<double>(q))), T, margin);
       }
     }
-    for (int t = 0; t < T; ++t) {
+    uint32_t* w = wp + i * 8;
+    for (int t = 0; t < nt; ++t) {
       const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
-      if (threadIdx.x == 0) bits[static_cast<size_t>(blockIdx.x) * R + static_cast<size_t>(t) * Bpad + b] = word;
+      if (threadIdx.x == 0) w[static_cast<size_t>(t) * Bpad] = word;
     }
   }
 }
@@ -244,35 +263,20 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
     for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; dbacc[j] = 0.f; }
     const float* vbase = volt + (static_cast<size_t>(g16) * Bpad + b) * 16;
     const size_t vstep = static_cast<size_t>(NP >> 4) * Bpad * 16;
-    if (T <= 8) {
-      // the voltage loads do not depend on the recurrence: issue all of them first
-      float4 vall[8][4];
+    {
+      // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's load in flight
+      float4 vn[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          vall[t][j] = (t < T && row_live) ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep) + j)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int t = 7; t >= 0; --t) {
-        if (t < T) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[4 * j] = vall[t][j].x; v[4 * j + 1] = vall[t][j].y; v[4 * j + 2] = vall[t][j].z; v[4 * j + 3] = vall[t][j].w;
-          }
-          top_scan_step(gup, v, gvn, gcn, dbacc, g_img, g_plane, R, static_cast<size_t>(t) * Bpad + b, n0);
-        }
-      }
-    } else {
+      for (int j = 0; j < 4; ++j)
+        vn[j] = row_live ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(T - 1) * vstep) + j)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int t = T - 1; t >= 0; --t) {
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 f = row_live ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t) * vstep) + j)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+        for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
+        if (t > 0 && row_live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep) + j);
         }
         top_scan_step(gup, v, gvn, gcn, dbacc, g_img, g_plane, R, static_cast<size_t>(t) * Bpad + b, n0);
       }

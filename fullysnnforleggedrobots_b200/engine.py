@@ -101,8 +101,9 @@ class SnnEngine:
 
     # ------------------------------------------------------------------ calls
     def forward(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, train: bool, out_mu=None,
-                out_trace=None):
-        """Returns (mu, trace or None).  out_mu / out_trace: optional caller-owned (static) output buffers."""
+                out_trace=None, assume_packed: bool = False):
+        """Returns (mu, trace or None).  out_mu / out_trace: optional caller-owned (static) output buffers.
+        assume_packed: the caller re-packs explicitly after every optimizer step (fused PPO path)."""
         _check_f32_cuda(obs, "obs")
         for t, n in ((enc_mean, "encoder.mean"), (enc_std, "encoder.std"), (dec_w, "decoder.weight"),
                      (dec_b, "decoder.bias"), *[(w, "weight") for w in weights], *[(b, "bias") for b in biases]):
@@ -114,7 +115,7 @@ class SnnEngine:
         L = _lib.lib()
         with torch.cuda.device(dev):
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
-            packed = self.packed_weights(weights, biases, ps)
+            packed = self._packed if (assume_packed and self._packed is not None) else self.packed_weights(weights, biases, ps)
             mu = out_mu if out_mu is not None else torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
             if B == 0:
                 return mu, None
@@ -133,7 +134,7 @@ class SnnEngine:
             return mu, None
 
     def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool,
-                 out=None):
+                 out=None, assume_packed: bool = False):
         """out: optional dict of caller-owned gradient tensors (same keys as the returned dict); overwritten."""
         dev = obs.device
         B = obs.shape[0]
@@ -141,7 +142,7 @@ class SnnEngine:
         g_mu = g_mu.contiguous().float()
         with torch.cuda.device(dev):
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
-            packed = self.packed_weights(weights, biases, ps)
+            packed = self._packed if (assume_packed and self._packed is not None) else self.packed_weights(weights, biases, ps)
             g = _lib.SnnGrads()
             if out is None:
                 out = {

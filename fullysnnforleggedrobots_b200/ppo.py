@@ -254,7 +254,7 @@ class PPO:
             else:
                 value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
         mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
-                                db.data, train=True, out_mu=st["mu"], out_trace=st["trace"])
+                                db.data, train=True, out_mu=st["mu"], out_trace=st["trace"], assume_packed=True)
         if ce is None:
             with torch.enable_grad():
                 value = ac.evaluate(f["critic_obs"][sl])
@@ -276,7 +276,7 @@ class PPO:
             with torch.cuda.stream(side):
                 ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
         eng.backward(f["obs"][sl], mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws],
-                     [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"])
+                     [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"], assume_packed=True)
         if ce is not None:
             if side is not None:
                 main.wait_stream(side)
