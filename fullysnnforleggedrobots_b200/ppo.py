@@ -161,10 +161,13 @@ class PPO:
 
     def _finish_step(self):
         """all-reduce (data parallel) -> adaptive lr -> clip + Adam -> re-pack: shared by both paths."""
+        if self.dp is not None:
+            self.dp.allreduce_sum(self.optimizer.flat_grads)   # ONE collective: gradients + KL statistic in the tail
+        self._post_allreduce()
+
+    def _post_allreduce(self):
         opt = self.optimizer
         world = 1 if self.dp is None else self.dp.world_size
-        if self.dp is not None:
-            self.dp.allreduce_sum(opt.flat_grads)          # ONE collective: gradients + KL statistic in the tail
         dev = opt.flat_params.device
         with torch.cuda.device(dev):
             if self._adaptive():
@@ -230,8 +233,9 @@ class PPO:
         self._fast_state = st
         self._graphs = {}
 
-    def _step_fast(self, f, i):
-        """One fused minibatch step on rows [i*mb, (i+1)*mb) of the permuted fields `f`.  No host sync."""
+    def _step_fast(self, f, i, finish=True):
+        """One fused minibatch step on rows [i*mb, (i+1)*mb) of the permuted fields `f`.  No host sync.
+        finish=False stops before the all-reduce / optimizer (data-parallel CUDA-graph segments)."""
         st = self._fast_state
         mb = st["mb"]
         sl = slice(i * mb, (i + 1) * mb)
@@ -284,14 +288,52 @@ class PPO:
                 ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
         else:
             value.backward(st["g_value"].view_as(value))
-        self._finish_step()
+        if finish:
+            self._finish_step()
+
+    def _capture(self, fn, snap):
+        """Warm `fn` up on a side stream, restore the training state, capture it into a CUDA graph."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().snn_launch_count()
+        with torch.cuda.graph(g):
+            fn()
+        self._restore(snap)
+        return g, int(_lib.lib().snn_launch_count() - n0)
+
+    def _run_fast_dp(self, f, i):
+        """Data parallel: graph A (everything up to the local gradients) -> eager NCCL all-reduce of the flat bucket
+        -> graph B (adaptive lr, clip + Adam, re-pack).  NCCL itself is not captured."""
+        try:
+            if ("pre", i) not in self._graphs:
+                snap = self._snapshot()
+                self._graphs[("pre", i)], self._graph_launches[("pre", i)] = self._capture(
+                    lambda: self._step_fast(f, i, finish=False), snap)
+            if "post" not in self._graphs:
+                snap = self._snapshot()
+                gsnap = self.optimizer.flat_grads.clone()
+                self._graphs["post"], self._graph_launches["post"] = self._capture(self._post_allreduce, snap)
+                self.optimizer.flat_grads.copy_(gsnap)
+        except Exception as e:  # noqa: BLE001
+            print(f"[PPO] CUDA graph capture failed ({e}); falling back to eager fused steps")
+            self.use_cuda_graph = False
+            return self._step_fast(f, i)
+        self._graphs[("pre", i)].replay()
+        self.dp.allreduce_sum(self.optimizer.flat_grads)
+        self._graphs["post"].replay()
+        self.replayed_kernel_launches += self._graph_launches[("pre", i)] + self._graph_launches["post"]
 
     def _run_fast(self, f, i):
         if not self.use_cuda_graph:
             return self._step_fast(f, i)
         if self.dp is not None:
-            # NCCL inside a captured graph is avoided: eager step (still no host sync)
-            return self._step_fast(f, i)
+            return self._run_fast_dp(f, i)
         g = self._graphs.get(i)
         if g is None:
             # warm-up on a side stream (allocator + lazy init), then capture

@@ -147,3 +147,43 @@ def test_tensor_core_critic_matches_torch_fp32(dims, B):
     for i, l in enumerate(lin):
         assert rel_err(gw[i].cpu(), l.weight.grad.cpu()) < 1e-4, f"dW{i}"
         assert rel_err(gb[i].cpu(), l.bias.grad.cpu()) < 1e-4, f"db{i}"
+
+
+def test_data_parallel_graph_segments_match_single_process():
+    """The data-parallel update (graph A -> NCCL all-reduce -> graph B) with a world of one rank must reproduce the
+    single-process fused update: same kernels, same order, one extra (identity) collective."""
+    import socket
+
+    import torch.distributed as dist
+
+    from fullysnnforleggedrobots_b200 import dist as snn_dist
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+
+    def run(reducer):
+        torch.manual_seed(0)
+        from fullysnnforleggedrobots_b200 import PPO, ActorCriticCassie
+        ac = ActorCriticCassie(pc.obs_dim, pc.obs_dim, pc.act_dim, actor_hidden_dims=list(pc.hidden),
+                               critic_hidden_dims=list(pc.critic_hidden), activation="elu", init_noise_std=1.0)
+        ac.load_state_dict(make_ppo_state_dict(pc))
+        alg = PPO(ac, num_learning_epochs=pc.epochs, num_mini_batches=1, clip_param=0.2, gamma=pc.gamma, lam=pc.lam,
+                  value_loss_coef=1.0, entropy_coef=pc.entropy_coef, learning_rate=pc.lr, max_grad_norm=1.0,
+                  use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cuda", data_parallel=reducer)
+        alg.init_storage(pc.num_envs, pc.num_steps, [pc.obs_dim], [None], [pc.act_dim])
+        fill_storage(alg, pc, g, ro)
+        alg.compute_returns(ro["last_obs"].cuda())
+        out = alg.update()
+        return out, {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}, alg
+
+    (vl0, sl0), sd0, _ = run(None)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        (vl1, sl1), sd1, alg = run(snn_dist.GradientAllReducer())
+        assert alg.use_cuda_graph and ("pre", 0) in alg._graphs and "post" in alg._graphs
+    finally:
+        dist.destroy_process_group()
+    assert abs(vl0 - vl1) <= 1e-5 * abs(vl0) and abs(sl0 - sl1) <= 1e-5 * max(1.0, abs(sl0))
+    for k in sd0:
+        assert rel_err(sd1[k], sd0[k]) < 1e-5, k
