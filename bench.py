@@ -313,6 +313,17 @@ def run_ours(args):
     ms_act = timed(step_act, 2 if args.quick else 50) / (2 if args.quick else 50)
     act_value = world * N / (ms_act * 1e-3)
 
+    # full rollout step PPO.act (actor forward + sample + log-prob + critic), replayed as one CUDA graph
+    def step_ppo_act():
+        with torch.inference_mode():
+            alg.act(obs_dev, obs_dev)
+            alg.transition.clear()
+
+    for _ in range(2 if args.quick else 6):
+        step_ppo_act()
+    ms_pact = timed(step_ppo_act, 2 if args.quick else 50) / (2 if args.quick else 50)
+    pact_value = world * N / (ms_pact * 1e-3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,7 +380,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "extra": {"act_env_steps_per_s": act_value, "act_ms": ms_act, "act_batch": N},
+        "extra": {"act_env_steps_per_s": act_value, "act_ms": ms_act, "act_batch": N,
+                  "ppo_act_env_steps_per_s": pact_value, "ppo_act_ms": ms_pact,
+                  "note": "act_* = PopSpikeActor forward (obs -> mu, std) under inference_mode; ppo_act_* = the whole "
+                          "PPO.act rollout step (sample, log-prob, critic value) as one CUDA-graph replay"},
     }
     if cpu_value is not None:
         line["cpu_baseline"] = {

@@ -65,7 +65,6 @@ class _SpikingActorCritic(nn.Module):
         else:
             self.std = nn.Parameter(std)
         self.distribution = None
-        Normal.set_default_validate_args = False
 
     @staticmethod
     def _warn_unexpected(kwargs):
@@ -93,7 +92,9 @@ class _SpikingActorCritic(nn.Module):
 
     def _set_distribution(self, actor_input):
         mean, std = self.actor(actor_input)
-        self.distribution = Normal(mean, mean * 0. + std)
+        # validate_args=False: the argument check is a host synchronisation (`constraint.check(...).all()`), which the
+        # reference tries to switch off at :378 (`Normal.set_default_validate_args = False` assigns instead of calling)
+        self.distribution = Normal(mean, mean * 0. + std, validate_args=False)
 
     def update_distribution(self, observations):
         self._set_distribution(observations)
@@ -143,7 +144,7 @@ class ActorCriticCassie(_SpikingActorCritic):
 
     def _set_distribution(self, actor_input):
         mean, std = self.actor(actor_input)
-        self.distribution = Normal(mean, std)        # CASSIE :410 — std broadcasts
+        self.distribution = Normal(mean, std, validate_args=False)        # CASSIE :410 — std broadcasts
 
 
 class ActorCriticHumanoid(_SpikingActorCritic):
@@ -164,7 +165,7 @@ class ActorCriticHumanoid(_SpikingActorCritic):
 
     def _set_distribution(self, actor_input):
         mean, std = self.actor(actor_input)
-        self.distribution = Normal(mean, std)        # HUMANOID :430
+        self.distribution = Normal(mean, std, validate_args=False)        # HUMANOID :430
 
 
 class ActorCriticRMA(_SpikingActorCritic):

@@ -66,6 +66,8 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         self.fused = fused
         self.fused_critic = fused_critic
+        self.act_cuda_graph = use_cuda_graph   # rollout step (act) replayed as one CUDA graph
+        self._act_state = None
         self.overlap_critic = True          # critic kernels on a second stream (parallel CUDA-graph branch)
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
@@ -98,13 +100,64 @@ class PPO:
     def train_mode(self):
         self.actor_critic.train()
 
-    def act(self, obs, critic_obs):
+    def _act_body(self, obs, critic_obs, graph_safe=False):
         ac = self.actor_critic
-        self.transition.actions = ac.act(obs).detach()
-        self.transition.values = ac.evaluate(critic_obs).detach()
-        self.transition.actions_log_prob = ac.get_actions_log_prob(self.transition.actions).detach()
-        self.transition.action_mean = ac.action_mean.detach()
-        self.transition.action_sigma = ac.action_std.detach()
+        if graph_safe:
+            # torch.normal(mean_tensor, std_tensor) checks `std >= 0` on the host (a sync): not capturable.
+            # Same distribution from randn_like; the noise stream differs from Normal.sample()'s, parity is defined
+            # on mu / sigma / values / log-probs, not on the random draw.
+            ac.update_distribution(obs)
+            actions = (ac.action_mean + ac.action_std * torch.randn_like(ac.action_mean)).detach()
+        else:
+            actions = ac.act(obs).detach()
+        values = ac.evaluate(critic_obs).detach()
+        logp = ac.get_actions_log_prob(actions).detach()
+        return actions, values, logp, ac.action_mean.detach(), ac.action_std.detach()
+
+    def _act_graphed(self, obs, critic_obs):
+        """Rollout step as ONE CUDA-graph replay (the reference launches ~250 kernels here): inputs are copied into
+        static buffers, the sampled actions / values / log-probs come back as fresh clones."""
+        key = (tuple(obs.shape), tuple(critic_obs.shape), obs.data_ptr() == critic_obs.data_ptr())
+        st = self._act_state
+        if st is None or st["key"] != key:
+            st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0}
+            st["cobs"] = st["obs"] if key[2] else critic_obs.clone()
+            self._act_state = st
+        st["obs"].copy_(obs)
+        if not key[2]:
+            st["cobs"].copy_(critic_obs)
+        st["calls"] += 1
+        if st["graph"] is None:
+            if st["calls"] < 2:                       # first call eager (lazy init, weight packing)
+                return self._act_body(st["obs"], st["cobs"])
+            side = torch.cuda.Stream()                # warm-up on a side stream, as torch.cuda.graph requires
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._act_body(st["obs"], st["cobs"], graph_safe=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["out"] = self._act_body(st["obs"], st["cobs"], graph_safe=True)
+            st["graph"] = g
+        st["graph"].replay()
+        return tuple(t.clone() for t in st["out"])
+
+    def act(self, obs, critic_obs):
+        use_graph = (self.act_cuda_graph and obs.is_cuda and not torch.is_grad_enabled()
+                     and type(self.actor_critic).__name__ != "ActorCriticRMA")
+        if use_graph:
+            try:
+                out = self._act_graphed(obs, critic_obs)
+            except Exception as e:  # noqa: BLE001
+                print(f"[PPO] CUDA graph capture of act() failed ({e}); using the eager path")
+                self.act_cuda_graph = False
+                out = self._act_body(obs, critic_obs)
+        else:
+            out = self._act_body(obs, critic_obs)
+        (self.transition.actions, self.transition.values, self.transition.actions_log_prob,
+         self.transition.action_mean, self.transition.action_sigma) = out
         self.transition.observations = obs
         self.transition.critic_observations = critic_obs
         return self.transition.actions

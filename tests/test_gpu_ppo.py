@@ -187,3 +187,33 @@ def test_data_parallel_graph_segments_match_single_process():
     assert abs(vl0 - vl1) <= 1e-5 * abs(vl0) and abs(sl0 - sl1) <= 1e-5 * max(1.0, abs(sl0))
     for k in sd0:
         assert rel_err(sd1[k], sd0[k]) < 1e-5, k
+
+
+def test_act_cuda_graph_is_consistent_and_sees_updated_weights():
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    obs = ro["obs"][0].cuda()
+    with torch.inference_mode():
+        for k in range(6):                                    # 2 eager warm-ups, capture, replays
+            a = alg.act(obs, obs)
+            assert rel_err(alg.transition.action_mean.cpu(), g["mu"][0]) < 1e-4
+            assert rel_err(alg.transition.values.cpu(), g["values"][0]) < 1e-5
+            lp = ac.get_actions_log_prob(a)                   # distribution state of the eager module is stale: recompute
+            z = (a - alg.transition.action_mean) / alg.transition.action_sigma
+            lp_ref = (-0.5 * z * z - torch.log(alg.transition.action_sigma) - 0.9189385332).sum(-1)
+            assert rel_err(alg.transition.actions_log_prob.cpu(), lp_ref.cpu()) < 1e-4
+            alg.transition.clear()
+        assert alg._act_state["graph"] is not None
+        a1 = alg.act(obs, obs).clone()
+        a2 = alg.act(obs, obs).clone()
+        assert not torch.equal(a1, a2)                        # fresh noise on every replay
+    # parameters change -> the replayed graph must use the new weights
+    fill_storage(alg, pc, g, ro)
+    alg.compute_returns(ro["last_obs"].cuda())
+    alg.update()
+    with torch.inference_mode():
+        alg.act(obs, obs)
+        mu_graph = alg.transition.action_mean.clone()
+        mu_eager = ac.act_inference(obs)
+    assert rel_err(mu_graph.cpu(), mu_eager.cpu()) < 1e-5
+    assert rel_err(mu_graph.cpu(), g["mu"][0]) > 1e-6         # and they did change
