@@ -121,8 +121,8 @@ struct Deferred {
   RowJobs rows{};
   PartJobs parts{};
   int max_n = 0, max_K = 0, max_N = 0;
-  void row(const float* src, int nparts, size_t stride, int n, float* dst) {
-    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride)};
+  void row(const float* src, int nparts, size_t stride, int n, float* dst, int col_step = 1) {
+    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride), col_step};
     if (n > max_n) max_n = n;
   }
   void part(const float* partial, int splits, int n_tiles, int N, int K, float* dW) {
@@ -320,10 +320,12 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     top_scan_kernel<<<Bp / 32, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
-                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top));
+                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
     df.row(dbpart_of(top), Bp / 32, lp.NP, lp.N, g->bias[top]);
+    df.row(small, Bp / 32, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
+    df.row(small + lp.NP, Bp / 32, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
   }
   // ---- walk down the layers
   for (int l = top; l >= 0; --l) {
@@ -384,21 +386,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       }
     }
   }
-  // ---- decoder parameter gradients
-  {
-    const int AP = p.A * p.Pd;
-    if (AP + p.A > 1024) return fail(SNN_EINVAL, "act_dim * de_pop too large for dec_bwd_kernel");
-    const int nblk = (Bi + 63) / 64;
-    const uint32_t* top_bits = reinterpret_cast<const uint32_t*>(at(trace, p.layer[top].tr_bits));
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    dec_bwd_kernel<<<dim3((AP + p.A + 31) / 32, nblk), dim3(32, 8), 0, st>>>(g_mu, mu, d->dec_tanh, top_bits, p.R, Bi, Bp, p.A, p.Pd,
-                                                               p.T, small);
-    }
-    LAUNCH_CHECK("dec_bwd_kernel");
-    df.row(small, nblk, AP + p.A, AP, g->dec_w);
-    df.row(small + AP, nblk, AP + p.A, p.A, g->dec_b);
-  }
-  // ---- encoder parameter gradients (+ d obs)
+  // ---- encoder parameter gradients (+ d obs); the decoder's came out of top_scan_kernel
   {
     const int nblk = (Bi + 63) / 64;
     { ProfScope prof__(CAT_OTHER, 0.0, st);

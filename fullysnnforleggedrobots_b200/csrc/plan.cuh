@@ -135,8 +135,8 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
-  p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (p.A * p.Pd + p.A) * 4 + 1024);
-  p.ws_small_enc = take(static_cast<size_t>(p.Bpad / 64) * 2 * p.K0 * 4 + 1024);
+  p.ws_small = take(static_cast<size_t>(p.Bpad / 32) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
+  p.ws_small_enc = take(static_cast<size_t>(p.Bpad / 64) * 2 * p.K0 * 4 + 1024);                // encoder partials
   p.ws_bwd_bytes = off;
   *out = p;
   return SNN_OK;

@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
                                                       int dec_tanh, const float* __restrict__ dec_w,
                                                       const float* __restrict__ volt, int B, int Bpad, int A, int P,
                                                       int NP, int T, int64_t R, uint8_t* __restrict__ g_img,
-                                                      size_t g_plane, float* __restrict__ db_part) {
+                                                      size_t g_plane, float* __restrict__ db_part,
+                                                      float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
   // block = 8 warps x 32 rows; lane = row, warp w walks the 16-column groups w, w+8, ...  grid = Bpad / 32.
+  // Also produces the decoder gradients: dec_part[blk][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
+  // dec_part[blk][1][n] = sum_b G[b,a(n)] (d bias, read at n = a * P).
   // A warp reads 32 rows x 64 B = one contiguous 2 KiB run of the voltage trace per (t, group).
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + lane;
@@ -246,15 +249,16 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
   const float Tf = static_cast<float>(T);
   for (int g16 = wid; g16 < NP / 16; g16 += 8) {
     const int n0 = g16 * 16;
-    float gup[16];
+    float gup[16], Gc[16], cnt[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int n = n0 + j;
-      gup[j] = 0.f;
+      gup[j] = 0.f; Gc[j] = 0.f; cnt[j] = 0.f;
       if (row_live && n < A * P) {
         const int a = n / P;
         float G = g_mu[static_cast<size_t>(b) * A + a];
         if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
+        Gc[j] = G;
         gup[j] = __fdiv_rn(G * dec_w[n], Tf);
       }
     }
@@ -274,6 +278,8 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
         float v[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cnt[j] += v[j] > 0.5f ? 1.f : 0.f;       // output spike count -> rate
         if (t > 0 && row_live) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep) + j);
@@ -283,47 +289,20 @@ __global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__
     }
     const float tot = warp_col_sums16(dbacc, lane);
     if ((lane & 1) == 0) db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + (lane >> 1)] = tot;
+    float dwd[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dwd[j] = Gc[j] * __fdiv_rn(cnt[j], Tf);
+    const float tw = warp_col_sums16(dwd, lane);
+    const float tb = warp_col_sums16(Gc, lane);
+    if ((lane & 1) == 0) {
+      float* dst = dec_part + (static_cast<size_t>(blockIdx.x) * 2) * NP + n0 + (lane >> 1);
+      dst[0] = tw;
+      dst[NP] = tb;
+    }
   }
 }
 
-// ------------------------------------------------------------------ decoder gradients
-// d w_dec[a,p] = sum_b G[b,a] rate[b, aP+p] ; d bias[a] = sum_b G[b,a].  Block = 128 rows; partials out.
-__global__ void __launch_bounds__(256) dec_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
-                                                     int dec_tanh, const uint32_t* __restrict__ bits, int64_t R, int B,
-                                                     int Bpad, int A, int P, int T,
-                                                     float* __restrict__ part /* [gridDim.y][A*P + A] */) {
-  // block (32 columns, 8 row lanes); grid = (ceil((AP + A)/32), ceil(B/64)); each thread walks 8 rows
-  const int AP = A * P;
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  const bool col_live = i < AP + A;
-  const bool is_w = i < AP;
-  const int a = col_live ? (is_w ? i / P : i - AP) : 0;
-  float acc = 0.f;
-  if (col_live) {
-    for (int j = 0; j < 8; ++j) {
-      const int b = blockIdx.y * 64 + j * 8 + threadIdx.y;
-      if (b >= B) break;
-      float G = g_mu[static_cast<size_t>(b) * A + a];
-      if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
-      if (is_w) {
-        int cnt = 0;
-        for (int t = 0; t < T; ++t)
-          cnt += (bits[static_cast<size_t>(i >> 5) * R + static_cast<size_t>(t) * Bpad + b] >> (i & 31)) & 1u;
-        acc += G * __fdiv_rn(static_cast<float>(cnt), static_cast<float>(T));
-      } else {
-        acc += G;
-      }
-    }
-  }
-  __shared__ float sh[8][33];
-  sh[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && col_live) {
-    float t = 0.f;
-    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
-    part[static_cast<size_t>(blockIdx.y) * (AP + A) + i] = t;
-  }
-}
+// (decoder gradients are produced by top_scan_kernel)
 
 // ------------------------------------------------------------------ encoder gradients
 // From g_a = d loss / d pop_act [Bpad][K0P]:
@@ -403,7 +382,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
 
 // Several independent row reductions / split-K reductions in ONE launch (blockIdx.y resp. .z selects the job):
 // the backward pass defers all of its small reductions to the end instead of launching ten tiny kernels.
-struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; };
+struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; int col_step; };
 struct RowJobs { RowJob j[12]; int count; };
 __global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs jobs) {   // block (32, 32)
   const RowJob jb = jobs.j[blockIdx.y];
@@ -411,7 +390,7 @@ __global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs j
   if (blockIdx.x * 32 >= jb.n) return;
   float acc = 0.f;
   if (i < jb.n)
-    for (int s = threadIdx.y; s < jb.nparts; s += 32) acc += jb.src[static_cast<size_t>(s) * jb.stride + i];
+    for (int s = threadIdx.y; s < jb.nparts; s += 32) acc += jb.src[static_cast<size_t>(s) * jb.stride + static_cast<size_t>(i) * jb.col_step];
   __shared__ float sh[32][33];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
