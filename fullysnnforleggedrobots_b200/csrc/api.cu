@@ -7,6 +7,7 @@
 
 #include "dw_gemm.cuh"
 #include "mlp_kernels.cuh"
+#include "nm_gemm.cuh"
 #include "plan.cuh"
 #include "ppo_kernels.cuh"
 #include "scan_gemm.cuh"
@@ -87,16 +88,14 @@ int device_ready(int* num_sms) {
   }
   if (di.checked < 0) return fail(SNN_EARCH, "device is not compute capability 10.x (sm_100a kernels only, no fallback)");
   if (!di.attrs_set) {
-    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(scan_gemm_smem_bytes<MODE_FWD>(96))));
-    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(scan_gemm_smem_bytes<MODE_DX>(96))));
-    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(scan_gemm_smem_bytes<MODE_DX_ENC>(96))));
+    CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(nm_gemm_smem_bytes<NM_FWD>())));
+    CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(nm_gemm_smem_bytes<NM_DX>())));
+    CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(nm_gemm_smem_bytes<NM_DX_ENC>())));
     CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
-    CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_FWD_TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(scan_gemm_smem_bytes<MODE_FWD_TA>(64))));
     CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
     CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_MLP_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -159,19 +158,28 @@ int plan_for(const SnnDesc* d, int64_t B, int num_sms, SnnPlan* p) {
 inline uint8_t* at(void* base, size_t off) { return static_cast<uint8_t*>(base) + off; }
 inline const uint8_t* at(const void* base, size_t off) { return static_cast<const uint8_t*>(base) + off; }
 
+TileGeom geom_of(const SnnPlan& p) { return TileGeom{p.Bt, p.CT, p.ntile, static_cast<long long>(p.Rt)}; }
+
+void nm_geometry(const SnnPlan& p, int64_t B, NmParams* q) {
+  q->T = p.T; q->Bt = p.Bt; q->TB = p.TB; q->CT = p.CT; q->sets = p.sets; q->ntile = p.ntile;
+  q->B = static_cast<int>(B); q->Rt = p.Rt;
+  q->dbg = debug_mask();
+}
+
 int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
             void* bits_base, void* volt_base /* nullable */, const SnnPlan& p, int num_sms, cudaStream_t st) {
   if (B == 0) return SNN_OK;
+  const TileGeom tg = geom_of(p);
   uint32_t* enc_bits = reinterpret_cast<uint32_t*>(at(bits_base, p.tr_enc_bits));
   {
-    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>(p.Bpad / 128));
+    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>((p.Bcap + 127) / 128));
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     if (p.T == 5)
-      encode_kernel<5><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
-                                            p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+      encode_kernel<5><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), tg, p.O, p.Pe, p.K0, p.T,
+                                            d->enc_eps, enc_bits);
     else
-      encode_kernel<0><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), static_cast<int>(p.Bpad),
-                                            p.O, p.Pe, p.K0, p.T, d->enc_eps, p.R, enc_bits);
+      encode_kernel<0><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), tg, p.O, p.Pe, p.K0, p.T,
+                                            d->enc_eps, enc_bits);
     }
     LAUNCH_CHECK("encode_kernel");
   }
@@ -179,43 +187,37 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const uint32_t* in_bits = enc_bits;
   for (int l = 0; l < p.L; ++l) {
     const LayerPlan& lp = p.layer[l];
-    ScanGemmParams q{};
-    q.a_bits = in_bits;
-    q.b_img = at(packed, lp.w_img);
-    q.b_plane = lp.w_plane;
-    q.b_planes = d->fwd_planes;
-    // T <= 5: spike operand staged in tensor memory (no shared-memory A reads), 64-column chunks
-    // chunk width: balanced split of the layer (e.g. 128 -> 64 + 64, not 96 + 32)
-    const int nch0 = (lp.NP + p.NCmax - 1) / p.NCmax;
-    const int ncb = static_cast<int>(round_up((lp.NP + nch0 - 1) / nch0, 32));
-    // narrow layers (<= 128 neurons): spike operand staged in TENSOR memory (tcgen05.st + TS-mode MMAs, two issuer
-    // warps) measured faster than the shared-memory operand path; wide layers: the opposite (SNN_DBG=32 forces TA)
-    const bool ta = p.T * 64 <= kTaAccCols && (lp.NP <= 128 || (debug_mask() & 32));
-    const int ncf = ta ? 64 : (ncb < p.NCmax ? ncb : p.NCmax);
-    q.KP = lp.KP; q.NPout = lp.NP; q.NCmax = ncf; q.T = p.T;
-    q.B = static_cast<int>(B); q.Bpad = static_cast<int>(p.Bpad); q.R = p.R;
-    q.nchunks = (lp.NP + ncf - 1) / ncf;
-    q.nitems = static_cast<int>(p.Bpad / 128) * q.nchunks;
-    q.dbg = debug_mask();
+    NmParams q{};
+    nm_geometry(p, B, &q);
+    q.KP = lp.KP; q.MP = lp.NP; q.nmt = lp.NP / 128;
+    q.a_img = at(packed, lp.w_img); q.a_plane = lp.w_plane; q.a_planes = d->fwd_planes;
+    q.b_bits = in_bits;
     q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(l) * 148 * 16 : nullptr;
     q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
     q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
-    const int grid = q.nitems < num_sms ? q.nitems : num_sms;
+    const int grid = nm_gemm_grid(q.nmt, p.ntile, num_sms);
     { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-    if (ta)
-      scan_gemm_kernel<MODE_FWD_TA><<<grid, ScanCfg<MODE_FWD_TA>::THREADS, scan_gemm_smem_bytes<MODE_FWD_TA>(64), st>>>(q);
-    else
-      scan_gemm_kernel<MODE_FWD><<<grid, ScanCfg<MODE_FWD>::THREADS, scan_gemm_smem_bytes<MODE_FWD>(ncf), st>>>(q);
+    // explicit 1-CTA cluster: the shared->shared bulk copy of the expanders addresses shared::cluster memory, which is
+    // an illegal instruction in a launch without a cluster dimension
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NmCfg<NM_FWD>::THREADS);
+    cfg.dynamicSmemBytes = nm_gemm_smem_bytes<NM_FWD>(); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, nm_gemm_kernel<NM_FWD>, q);
+    if (le != cudaSuccess) return fail(SNN_ECUDA, "launch nm_gemm_kernel<FWD>: %s", cudaGetErrorString(le));
     }
-    LAUNCH_CHECK("scan_gemm_kernel<FWD>");
+    LAUNCH_CHECK("nm_gemm_kernel<FWD>");
     in_bits = q.out_bits;
   }
   {
     const int n = static_cast<int>(B) * p.A;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, p.R, static_cast<int>(B), static_cast<int>(p.Bpad), p.A, p.Pd,
-                                                   p.T, prm->dec_w, prm->dec_b, d->dec_tanh, mu);
+    decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, tg, static_cast<int>(B), p.A, p.Pd, p.T, prm->dec_w, prm->dec_b,
+                                                   d->dec_tanh, mu);
     }
     LAUNCH_CHECK("decode_kernel");
   }
@@ -304,7 +306,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   if (workspace_bytes < p.ws_bwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
+  const int Bi = static_cast<int>(B);
+  const TileGeom tg = geom_of(p);
   auto dbpart_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_dbpart + static_cast<size_t>(l) * p.ws_dbpart_stride)); };
   auto partial_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_partial + static_cast<size_t>(l) * p.ws_partial_stride)); };
   float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
@@ -313,19 +316,19 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   float* g_a = reinterpret_cast<float*>(at(workspace, p.ws_ga));
   const uint32_t* enc_bits = reinterpret_cast<const uint32_t*>(at(trace, p.tr_enc_bits));
 
-  // ---- output population layer: scan with g_up from the decoder
+  // ---- output population layer: scan with g_up from the decoder (also yields the decoder's gradients)
   const int top = p.L - 1;
   {
     const LayerPlan& lp = p.layer[top];
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<Bp / 32, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
-                                         reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, Bp, p.A, p.Pd, lp.NP,
-                                         p.T, p.R, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
+    top_scan_kernel<<<dim3(p.ntile, lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+                                         reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
+                                         p.T, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
-    df.row(dbpart_of(top), Bp / 32, lp.NP, lp.N, g->bias[top]);
-    df.row(small, Bp / 32, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
-    df.row(small + lp.NP, Bp / 32, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
+    df.row(dbpart_of(top), p.ntile, lp.NP, lp.N, g->bias[top]);
+    df.row(small, p.ntile, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
+    df.row(small + lp.NP, p.ntile, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
   }
   // ---- walk down the layers
   for (int l = top; l >= 0; --l) {
@@ -337,9 +340,9 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       DwGemmParams q{};
       q.g_img = G; q.g_plane = Gplane;
       q.x_bits = l == 0 ? enc_bits : reinterpret_cast<const uint32_t*>(at(trace, p.layer[l - 1].tr_bits));
-      q.NP = lp.NP; q.KP = lp.KP; q.R = p.R;
+      q.NP = lp.NP; q.KP = lp.KP; q.R = p.Rt;
       q.n_tiles = (lp.KP + 255) / 256;
-      q.rblocks = static_cast<int>(p.R / 64);
+      q.rblocks = static_cast<int>(p.Rt / 64);
       const int tiles = (lp.NP / 128) * q.n_tiles;
       int splits = sms / tiles;
       if (splits < 1) splits = 1;
@@ -354,47 +357,44 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
     }
     {   // dX_l + scan of the layer below (or of the encoder)
-      ScanGemmParams q{};
-      q.a_img = G; q.a_plane = Gplane;
-      q.dbg = debug_mask();
+      NmParams q{};
+      nm_geometry(p, B, &q);
+      q.KP = lp.NP; q.MP = lp.KP; q.nmt = lp.KP / 128;
+      q.a_img = at(packed, lp.wt_img); q.a_plane = lp.wt_plane; q.a_planes = 2;
+      q.b_img = G; q.b_plane = Gplane;
       q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(8 + l) * 148 * 16 : nullptr;
-      q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
-      const int ncx = l > 0 ? p.NCdx : p.NCmax;        // hidden layers: double-buffered accumulators, narrower chunks
-      q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = ncx; q.T = p.T;
-      q.B = Bi; q.Bpad = Bp; q.R = p.R;
-      q.nchunks = (lp.KP + ncx - 1) / ncx;
-      q.nitems = (Bp / 128) * q.nchunks;
-      const int grid = q.nitems < sms ? q.nitems : sms;
+      const int grid = nm_gemm_grid(q.nmt, p.ntile, sms);
       if (l > 0) {
         const LayerPlan& lo = p.layer[l - 1];
         q.v_in = reinterpret_cast<const float*>(at(trace, lo.tr_volt));
         q.g_img = at(workspace, p.ws_g[slot ^ 1]);
         q.g_plane = p.ws_g_plane[slot ^ 1];
         q.db_part = dbpart_of(l - 1);
-        q.sets = p.T * ncx <= 256 ? 2 : 1;
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-        scan_gemm_kernel<MODE_DX><<<grid, ScanCfg<MODE_DX>::THREADS, scan_gemm_smem_bytes<MODE_DX>(ncx), st>>>(q);
+        nm_gemm_kernel<NM_DX><<<grid, NmCfg<NM_DX>::THREADS, nm_gemm_smem_bytes<NM_DX>(), st>>>(q);
         }
-        LAUNCH_CHECK("scan_gemm_kernel<DX>");
-        df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
+        LAUNCH_CHECK("nm_gemm_kernel<DX>");
+        df.row(dbpart_of(l - 1), 2 * grid / q.nmt, lo.NP, lo.N, g->bias[l - 1]);
       } else {
         q.g_a = g_a;
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-        scan_gemm_kernel<MODE_DX_ENC><<<grid, ScanCfg<MODE_DX_ENC>::THREADS, scan_gemm_smem_bytes<MODE_DX_ENC>(p.NCmax), st>>>(q);
+        nm_gemm_kernel<NM_DX_ENC><<<grid, NmCfg<NM_DX_ENC>::THREADS, nm_gemm_smem_bytes<NM_DX_ENC>(), st>>>(q);
         }
-        LAUNCH_CHECK("scan_gemm_kernel<DX_ENC>");
+        LAUNCH_CHECK("nm_gemm_kernel<DX_ENC>");
       }
     }
   }
   // ---- encoder parameter gradients (+ d obs); the decoder's came out of top_scan_kernel
   {
-    const int nblk = (Bi + 63) / 64;
+    const int ngroups = (Bi + 15) / 16;
+    const int nblk = ngroups < kEncBwdBlocks ? ngroups : kEncBwdBlocks;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    enc_bwd_kernel<<<dim3((p.K0 + 31) / 32, nblk), dim3(32, 8), 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P, d->enc_eps, small_enc);
+    enc_bwd_kernel<<<dim3(p.K0P / 128, nblk), 128, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P,
+                                                           d->enc_eps, small_enc);
     }
     LAUNCH_CHECK("enc_bwd_kernel");
-    df.row(small_enc, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_mean);
-    df.row(small_enc + p.K0, nblk, 2 * static_cast<size_t>(p.K0), p.K0, g->enc_std);
+    df.row(small_enc, nblk, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
+    df.row(small_enc + p.K0P, nblk, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
     if (g->obs != nullptr) {
       const int n = Bi * p.O;
       { ProfScope prof__(CAT_OTHER, 0.0, st);
@@ -694,15 +694,16 @@ int snn_debug_set_cycle_buffer(void* buf) { g_dbg_out = static_cast<unsigned lon
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out) {
   SnnPlan p;
   if (d == nullptr || out == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return fail(SNN_EINVAL, "bad descriptor");
-  // [0]=L [1]=T [2]=Bpad [3]=R [4]=K0P [5]=enc_bits_off then per layer: NP, KP, bits_off, volt_off
-  const int need = 6 + 4 * p.L;
+  // [0]=L [1]=T [2]=Bt [3]=CT [4]=ntile [5]=Rt [6]=K0P [7]=enc_bits_off then per layer: NP, KP, bits_off, volt_off
+  const int need = 8 + 4 * p.L;
   if (n_out < need) return fail(SNN_EINVAL, "output array too small");
-  out[0] = p.L; out[1] = p.T; out[2] = p.Bpad; out[3] = p.R; out[4] = p.K0P; out[5] = static_cast<int64_t>(p.tr_enc_bits);
+  out[0] = p.L; out[1] = p.T; out[2] = p.Bt; out[3] = p.CT; out[4] = p.ntile; out[5] = p.Rt; out[6] = p.K0P;
+  out[7] = static_cast<int64_t>(p.tr_enc_bits);
   for (int l = 0; l < p.L; ++l) {
-    out[6 + 4 * l] = p.layer[l].NP;
-    out[7 + 4 * l] = p.layer[l].KP;
-    out[8 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_bits);
-    out[9 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_volt);
+    out[8 + 4 * l] = p.layer[l].NP;
+    out[9 + 4 * l] = p.layer[l].KP;
+    out[10 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_bits);
+    out[11 + 4 * l] = static_cast<int64_t>(p.layer[l].tr_volt);
   }
   return need;
 }

@@ -1,0 +1,508 @@
+// nm_gemm.cuh — the actor's "neuron-major" scan-GEMMs (tcgen05 / TMEM / bulk-TMA).
+//
+// One work item = (128 output neurons) x (one batch tile of Bt samples, all T spike steps).  The tensor core
+// computes D[neuron][sample-step] : the 128 neurons are the MMA's M (= the TMEM lanes), the tile's T * Bt
+// sample-steps are its N (= the TMEM columns; 240 for T = 5), so ONE tcgen05.mma per 16 contraction elements and
+// weight plane covers all T timesteps.  tools/mma_rate.cu measures an M = 128 MMA at max(N/2, 57 + N/8) cycles:
+// N = 240 runs at the tensor core's full rate, while "one N <= 96 accumulator per timestep" (the first design of
+// this path) was capped at 70 % (N = 96) / 39 % (N = 48) by the fixed issue cost.
+// After the GEMM the epilogue warps run the sequential-in-time recurrence with thread = neuron, registers = the
+// 16 samples x T steps it is working on:
+//
+//   NM_FWD     A = bf16 hi/mid/lo planes of W (K-major), B = spikes of the layer below: bit-packed in HBM, staged
+//              by bulk copies into a shared-memory ring and expanded there to bf16 0/1 operand tiles.
+//              Epilogue = LIF update (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b);
+//              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of __ballot_sync (lane = neuron); emits the
+//              fp32 voltage trace when training.
+//   NM_DX      A = hi/lo planes of W^T (K-major), B = hi/lo planes of g_c of the layer above (n-major image =
+//              MN-major operand); three products hi*hi + hi*lo + lo*hi.  Epilogue = BPTT recurrence of
+//              SURVEY.md §8a for the layer below (surrogate gradient of PseudoSpikeRect, actor_critic.py:154-167).
+//              Emits g_c planes (n-major image) and the bias gradient (a per-thread sum: no shuffles, no atomics).
+//   NM_DX_ENC  same GEMM into the encoder neurons; epilogue = straight-through encoder recurrence
+//              (actor_critic.py:50-59,116-119): Gamma_t = g_t + 0.001 Gamma_{t+1}; emits g_a = sum_t Gamma_t.
+//
+// Accumulators: TB = T * Bt <= 256 columns -> two sets (set = item parity): the MMA warp fills one while an
+// epilogue group (4 warps = 128 TMEM lanes) drains the other.  TB > 256 (T > 16): one set, the two epilogue
+// groups split its 16-sample groups.
+// A CTA keeps ONE neuron tile (mt = blockIdx.x % nmt) and walks batch tiles, so per-neuron constants (bias) and
+// per-neuron sums (bias gradient) live in registers for the whole kernel.
+//
+// Warp roles: 0 = bulk-copy producer (weights / g_c), 1 = MMA issuer + TMEM owner, 2 = spike-word producer (FWD),
+// 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
+#pragma once
+#include "plan.cuh"
+#include "umma.cuh"
+
+#ifndef SNN_TWAIT
+#define SNN_TWAIT(bar, par, slot)                                   \
+  do {                                                              \
+    const long long t0__ = clock64();                               \
+    mbar_wait(bar, par);                                            \
+    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
+  } while (0)
+#endif
+
+namespace snn {
+
+enum { NM_FWD = 0, NM_DX = 1, NM_DX_ENC = 2 };
+
+struct NmParams {
+  // batch-tile geometry (SnnPlan)
+  int T, Bt, TB, CT, sets, ntile, B;
+  int64_t Rt;
+  int KP;                   // contraction length (padded, % 64 == 0)
+  int MP;                   // output neurons (padded, % 128 == 0) = TMEM lanes over all neuron tiles
+  int nmt;                  // MP / 128; gridDim.x % nmt == 0
+  // A operand: planes of a swz64 image [KP/64][MP rows][128 B]   (FWD: W hi/mid/lo, DX: W^T hi/lo)
+  const uint8_t* a_img;
+  size_t a_plane;
+  int a_planes;             // FWD: 1..3
+  // B operand
+  const uint32_t* b_bits;   // FWD: spike words [KP/32][Rt]
+  const uint8_t* b_img;     // DX: 2 planes of the n-major image [Rt/64][KP/8][8][128 B]
+  size_t b_plane;
+  // FWD epilogue
+  const float* bias;        // [MP]
+  uint32_t* out_bits;       // [MP/32][Rt]
+  float* v_out;             // [Rt/16][MP][16] or null (inference)
+  // DX epilogue
+  const float* v_in;        // [Rt/16][MP][16] voltages of the layer whose gradient is produced
+  uint8_t* g_img;           // 2 planes of the n-major image [Rt/64][MP/8][8][128 B]
+  size_t g_plane;
+  float* db_part;           // [2 * gridDim.x / nmt][MP]
+  // DX_ENC epilogue
+  float* g_a;               // [Bcap/16][MP][16]
+  int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand
+  unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
+};
+
+template <int MODE> struct NmCfg;
+// FWD: 2 weight stages of 3 x 16 KiB planes, 2 spike sub-tiles of <= 256 sample-steps x 128 B (+ one staging buffer
+// of the same size, see the expander role), 4 spike-word stages
+template <> struct NmCfg<NM_FWD> {
+  static constexpr int NW = 2, W_STAGE = 49152, NS = 2, S_STAGE = 32768, NBITS = 4, BITS_STAGE = 2048, THREADS = 512;
+};
+// DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (half a 64-neuron chunk: 2 planes x <= 4 panels x 4 KiB)
+template <> struct NmCfg<NM_DX> {
+  static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 384;
+};
+template <> struct NmCfg<NM_DX_ENC> : NmCfg<NM_DX> {};
+
+template <int MODE>
+__host__ __device__ constexpr size_t nm_gemm_smem_bytes() {
+  return 1024 /*align slack*/ + static_cast<size_t>(NmCfg<MODE>::NW) * NmCfg<MODE>::W_STAGE +
+         static_cast<size_t>(NmCfg<MODE>::NS) * NmCfg<MODE>::S_STAGE +
+         static_cast<size_t>(NmCfg<MODE>::NBITS) * NmCfg<MODE>::BITS_STAGE +
+         (MODE == NM_FWD ? 4096 /*LUT*/ + NmCfg<MODE>::S_STAGE /*staging*/ : 0) + 512;
+}
+
+// CTAs to launch: a multiple of the neuron tiles, at most one per SM, at most one per item
+inline int nm_gemm_grid(int nmt, int ntile, int num_sms) {
+  int per = num_sms / nmt;
+  if (per < 1) per = 1;
+  if (per > ntile) per = ntile;
+  return per * nmt;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const NmParams p) {
+  using C = NmCfg<MODE>;
+  constexpr bool IS_FWD = MODE == NM_FWD;
+  constexpr uint32_t NBM = C::NBITS > 0 ? C::NBITS : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_ring = smem;
+  uint8_t* s_ring = w_ring + C::NW * C::W_STAGE;
+  uint8_t* staging = s_ring + C::NS * C::S_STAGE;                                   // FWD only
+  uint8_t* bits_ring = staging + (IS_FWD ? C::S_STAGE : 0);
+  uint4* lut = reinterpret_cast<uint4*>(bits_ring + C::NBITS * C::BITS_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + (IS_FWD ? 4096 : 0));
+  uint64_t* w_full = bars;                      // [<= 4]
+  uint64_t* w_empty = w_full + 4;               // [<= 4]
+  uint64_t* s_full = w_empty + 4;               // [<= 4]
+  uint64_t* s_empty = s_full + 4;               // [<= 4]
+  uint64_t* acc_full = s_empty + 4;             // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint64_t* bits_full = acc_empty + 2;          // [NBITS]
+  uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bits_empty + C::NBITS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KC = p.KP / 64;
+  const uint32_t nsets = p.sets == 2 ? 2u : 1u;
+  const int nsub = (p.TB + 255) / 256;                 // sample-step sub-tiles of <= 256 columns (2 only when T > 16)
+  const int mt = blockIdx.x % p.nmt;                   // this CTA's neuron tile
+  const int tile0 = blockIdx.x / p.nmt, tstep = gridDim.x / p.nmt;
+  unsigned long long wcyc[3] = {0, 0, 0};
+  const long long t_start = clock64();
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+    for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nsets == 2 ? 128 : 256); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  if (IS_FWD) {
+    // LUT: byte of 8 spike bits -> eight bf16 {0, 1}
+    for (int i = tid; i < 256; i += blockDim.x) {
+      uint4 v;
+      v.x = ((i & 1) ? 0x3F80u : 0u) | ((i & 2) ? 0x3F800000u : 0u);
+      v.y = ((i & 4) ? 0x3F80u : 0u) | ((i & 8) ? 0x3F800000u : 0u);
+      v.z = ((i & 16) ? 0x3F80u : 0u) | ((i & 32) ? 0x3F800000u : 0u);
+      v.w = ((i & 64) ? 0x3F80u : 0u) | ((i & 128) ? 0x3F800000u : 0u);
+      lut[i] = v;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================================================== operand producer (warp-uniform loop, one elected lane issues)
+    uint32_t iw = 0, u = 0;
+    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+      for (int kc = 0; kc < KC; ++kc, ++iw) {
+        const uint32_t ws = iw % C::NW;
+        SNN_TWAIT(&w_empty[ws], ((iw / C::NW) & 1) ^ 1, 0);
+        if (elect_one()) {
+          const int npl = IS_FWD ? p.a_planes : 2;
+          mbar_expect_tx(&w_full[ws], static_cast<uint32_t>(npl * 16384));
+          for (int pl = 0; pl < npl; ++pl)
+            bulk_g2s(w_ring + ws * C::W_STAGE + pl * 16384,
+                     p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.MP + static_cast<size_t>(mt) * 128) * 128, 16384u,
+                     &w_full[ws]);
+        }
+        __syncwarp();
+        if (!IS_FWD) {
+          // g_c units of this 64-neuron chunk: (half chunk) x (sub-tile); panel = 64 sample-steps x 32 neurons = 4 KiB
+          for (int half = 0; half < 2; ++half)
+            for (int sub = 0; sub < nsub; ++sub, ++u) {
+              const uint32_t gs = u % C::NS;
+              SNN_TWAIT(&s_empty[gs], ((u / C::NS) & 1) ^ 1, 1);
+              if (elect_one()) {
+                const int ncols = min(256, p.TB - sub * 256);
+                const int npan = (ncols + 63) >> 6;
+                mbar_expect_tx(&s_full[gs], static_cast<uint32_t>(2 * npan * 4096));
+                const size_t pan0 = static_cast<size_t>(tile) * (p.CT >> 6) + static_cast<size_t>(sub) * 4;
+                for (int pl = 0; pl < 2; ++pl)
+                  for (int pan = 0; pan < npan; ++pan)
+                    bulk_g2s(s_ring + gs * C::S_STAGE + pl * 16384 + pan * 4096,
+                             p.b_img + pl * p.b_plane + ((pan0 + pan) * (p.KP >> 3) + static_cast<size_t>(kc) * 8 + half * 4) * 1024,
+                             4096u, &s_full[gs]);
+              }
+              __syncwarp();
+            }
+        }
+      }
+    }
+  } else if (IS_FWD && warp == 2) {
+    // ===================================================== spike-word producer: per (chunk, sub-tile) two runs of words
+    uint32_t u = 0;
+    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+      for (int kc = 0; kc < KC; ++kc)
+        for (int sub = 0; sub < nsub; ++sub, ++u) {
+          const uint32_t s = u % NBM;
+          SNN_TWAIT(&bits_empty[s], ((u / NBM) & 1) ^ 1, 0);
+          if (elect_one()) {
+            const int ncols = min(256, p.TB - sub * 256);
+            mbar_expect_tx(&bits_full[s], static_cast<uint32_t>(2 * ncols * 4));
+            const size_t c0 = static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256;
+            uint8_t* dst = bits_ring + s * C::BITS_STAGE;
+            bulk_g2s(dst, p.b_bits + static_cast<size_t>(2 * kc) * p.Rt + c0, static_cast<uint32_t>(ncols * 4), &bits_full[s]);
+            bulk_g2s(dst + 1024, p.b_bits + static_cast<size_t>(2 * kc + 1) * p.Rt + c0, static_cast<uint32_t>(ncols * 4),
+                     &bits_full[s]);
+          }
+          __syncwarp();
+        }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
+    uint32_t iw = 0, u = 0, it = 0;
+    const uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t w_ring_lo = smem_desc_lo(smem_u32(w_ring), 16);
+    const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), IS_FWD ? 16 : 4096);   // DX: LBO = 4 KiB between panels
+    for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
+      const uint32_t aset = it % nsets;
+      SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
+      tc_fence_after_sync();
+      for (int kc = 0; kc < KC; ++kc, ++iw) {
+        const uint32_t ws = iw % C::NW;
+        SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
+        const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
+        for (int half = 0; half < (IS_FWD ? 1 : 2); ++half)
+          for (int sub = 0; sub < nsub; ++sub, ++u) {
+            const uint32_t ss = u % C::NS;
+            SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const int ncols = min(256, p.TB - sub * 256);
+              const uint32_t b_lo = s_ring_lo + ss * (C::S_STAGE >> 4);
+              const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
+              if (p.dbg & 1) {
+              } else if (IS_FWD) {
+                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
+                uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16)
+                  for (int pl = 0; pl < p.a_planes; ++pl) {
+                    umma_bf16_lohi(d, a_lo + pl * (16384 >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
+                    acc = 1u;
+                  }
+              } else {
+                // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + hi*lo + lo*hi (lo*lo < 2^-16 relative)
+                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 1);
+                uint32_t acc = (kc > 0 || half > 0) ? 1u : 0u;
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16)
+#pragma unroll
+                  for (int pr = 0; pr < 3; ++pr) {
+                    const uint32_t pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
+                    umma_bf16_lohi(d, a_lo + pa * (16384 >> 4) + (half * 2 + k16) * 2, dhi,
+                                   b_lo + pb * (16384 >> 4) + k16 * (2048 >> 4), dhi, idesc, acc);
+                    acc = 1u;
+                  }
+              }
+              umma_commit(&s_empty[ss]);
+              if (half == (IS_FWD ? 0 : 1) && sub == nsub - 1) {
+                umma_commit(&w_empty[ws]);
+                if (kc == KC - 1) umma_commit(&acc_full[aset]);
+              }
+            }
+            __syncwarp();
+          }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================== epilogue: the time scan, thread = neuron
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int n = mt * 128 + q * 32 + lane;                      // this thread's neuron (row of the layer)
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nbg = p.Bt >> 4;                                    // 16-sample groups per tile
+    const int bg0 = nsets == 2 ? 0 : grp, bgstep = nsets == 2 ? 1 : 2;
+    const float bias = IS_FWD ? p.bias[n] : 0.f;
+    float dbsum = 0.f;
+    uint32_t it = 0;
+    for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
+      const uint32_t aset = it % nsets;
+      if (nsets == 2 && aset != static_cast<uint32_t>(grp)) continue;
+      const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
+      const int b_tile = tile * p.Bt;
+      if (MODE == NM_DX) {
+        // the scan below reads this neuron's voltages (64 B per (t, group)) from the HBM-resident trace: pull them
+        // into L2 while the tensor core is still busy with this item's MMAs
+        for (int bg = bg0; bg < nbg; bg += bgstep)
+          for (int t = 0; t < p.T; ++t)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                p.v_in + (((c_tile + static_cast<size_t>(t * p.Bt + bg * 16)) >> 4) * p.MP + n) * 16));
+      }
+      SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
+      tc_fence_after_sync();
+      const uint32_t t_set = t_lane + aset * 256;
+      for (int bg = (p.dbg & 2) ? nbg : bg0; bg < nbg; bg += bgstep) {
+        const int col0 = bg * 16;
+        // bit j: sample b_tile + col0 + j exists
+        const int nlive = p.B - (b_tile + col0);
+        const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
+        if (IS_FWD) {
+          float cur[16], vol[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
+          uint32_t sprev = 0;
+          uint32_t x[16], xn[16];
+          tmem_ld16(t_set + static_cast<uint32_t>(col0), x);
+          tmem_ld_wait();
+          for (int t = 0; t < p.T; ++t) {
+            if (t + 1 < p.T) tmem_ld16(t_set + static_cast<uint32_t>((t + 1) * p.Bt + col0), xn);
+            uint32_t scur = 0, myword = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float syn = __fadd_rn(__uint_as_float(x[j]), bias);
+              const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
+              const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
+              cur[j] = cj;
+              vol[j] = vj;
+              const bool s = vj > 0.5f;
+              scur |= (s ? 1u : 0u) << j;
+              const uint32_t w = __ballot_sync(0xffffffffu, s);      // the 32 neurons of this warp at sample-step (t, j)
+              if (lane == j) myword = w;
+            }
+            const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
+            if (lane < 16)
+              p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
+            if (p.v_out != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.v_out + ((c >> 4) * p.MP + n) * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
+            }
+            sprev = scur;
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = xn[j];
+          }
+        } else if (MODE == NM_DX) {
+          float gvn[16], gcn[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
+          const size_t vstep = (static_cast<size_t>(p.Bt) >> 4) * p.MP * 16;       // floats between timesteps
+          const float* vbase = p.v_in + (((c_tile + col0) >> 4) * p.MP + n) * 16;
+          float4 vn[4];
+          {
+            const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(p.T - 1) * vstep);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
+          }
+          uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
+          const int sw = n & 7;
+          for (int t = p.T - 1; t >= 0; --t) {
+            uint32_t x[16];
+            tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
+            if (t > 0) {   // prefetch the next (earlier) timestep's voltages
+              const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
+            }
+            tmem_ld_wait();
+            float hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool live = (vmask >> j) & 1u;
+              const float gup = live ? __uint_as_float(x[j]) : 0.f;
+              const float vj = live ? v[j] : 0.f;
+              const float gs = gup - gvn[j] * (0.75f * vj);
+              const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
+              const float keep = vj > 0.5f ? 0.f : 0.75f;
+              const float gv = gs * win + gvn[j] * keep;
+              const float gc = gv + 0.5f * gcn[j];
+              gvn[j] = gv;
+              gcn[j] = gc;
+              dbsum += gc;
+              hi[j] = bf16_round(gc);
+              lo[j] = gc - hi[j];
+            }
+            const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
+            uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7);      // panel stride = MP / 8 * 1024
+            const int p0 = static_cast<int>((c & 63) >> 3);
+            const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+            const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+            const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+            *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) = h0;
+            *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) = h1;
+            *reinterpret_cast<uint4*>(dst + p.g_plane + ((p0 ^ sw) << 4)) = l0;
+            *reinterpret_cast<uint4*>(dst + p.g_plane + (((p0 + 1) ^ sw) << 4)) = l1;
+          }
+        } else {   // NM_DX_ENC
+          float gam[16], ga[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { gam[j] = 0.f; ga[j] = 0.f; }
+          for (int t = p.T - 1; t >= 0; --t) {
+            uint32_t x[16];
+            tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              gam[j] = __uint_as_float(x[j]) + 0.001f * gam[j];
+              ga[j] += gam[j];
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(p.g_a + ((static_cast<size_t>(b_tile + col0) >> 4) * p.MP + n) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(((vmask >> (4 * j)) & 1u) ? ga[4 * j] : 0.f, ((vmask >> (4 * j + 1)) & 1u) ? ga[4 * j + 1] : 0.f,
+                                 ((vmask >> (4 * j + 2)) & 1u) ? ga[4 * j + 2] : 0.f, ((vmask >> (4 * j + 3)) & 1u) ? ga[4 * j + 3] : 0.f);
+        }
+      }
+      if (MODE == NM_DX && (nsets == 2 || grp == 0)) {
+        // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
+        uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
+        for (int cc = p.TB; cc < p.CT; cc += 8) {
+          const size_t c = c_tile + cc;
+          uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7) + (((static_cast<int>(c & 63) >> 3) ^ (n & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + p.g_plane) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[aset]);
+    }
+    if (MODE == NM_DX)
+      p.db_part[(static_cast<size_t>(tile0) * 2 + grp) * p.MP + n] = dbsum;
+  } else if (IS_FWD && warp >= 12) {
+    // ===================================================== spike-bit expanders (smem words -> bf16 B sub-tile)
+    // The four warps expand every sub-tile together (sample-step r = thread, thread + 128; one 128-byte swizzled row
+    // = 64 contraction elements per sample-step) into a STAGING buffer; one thread then moves it into the operand
+    // slot with a shared->shared bulk copy.  Both hops are the canonical cross-proxy patterns: generic stores ->
+    // fence.proxy.async -> bulk-copy read (as for every TMA store), and bulk-copy write -> mbarrier -> tcgen05.mma
+    // read (as for the weights).  Writing the operand slot directly with st.shared was NOT reliable: with the MMA
+    // pipe busy the tensor core now and then read stale 16-byte pieces (run-to-run differences at B = 24576,
+    // rate dependent on the slot's address) although the writers fenced, and although a read-back saw the new data.
+    const int et = tid - 384;
+    uint32_t u = 0;
+    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+      for (int kc = 0; kc < KC; ++kc)
+        for (int sub = 0; sub < nsub; ++sub, ++u) {
+          const int ncols = min(256, p.TB - sub * 256);
+          const uint32_t s = u % NBM;
+          SNN_TWAIT(&bits_full[s], (u / NBM) & 1, 0);
+          const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + s * C::BITS_STAGE);
+          uint32_t w0[2], w1[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = et + 128 * h;
+            w0[h] = r < ncols ? wsrc[r] : 0u;
+            w1[h] = r < ncols ? wsrc[256 + r] : 0u;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bits_empty[s]);
+          // the staging buffer is free once the previous unit's copy has completed (= its s_full phase)
+          if (u > 0) SNN_TWAIT(&s_full[(u - 1) % C::NS], ((u - 1) / C::NS) & 1, 1);
+          if (!(p.dbg & 4)) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = et + 128 * h;
+              if (r < ncols) {
+                const int sw = r & 7;
+                uint8_t* dst = staging + (r >> 3) * 1024 + sw * 128;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                  const uint32_t byte = ((c8 < 4 ? w0[h] : w1[h]) >> ((c8 & 3) * 8)) & 0xFFu;
+                  *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) = lut[byte];
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");       // all four expander warps have written and fenced
+          if (et == 0) {
+            const uint32_t ss = u % C::NS;
+            SNN_TWAIT(&s_empty[ss], ((u / C::NS) & 1) ^ 1, 2);
+            mbar_expect_tx(&s_full[ss], static_cast<uint32_t>(ncols * 128));
+            bulk_s2s(s_ring + ss * C::S_STAGE, staging, static_cast<uint32_t>(ncols * 128), &s_full[ss]);
+          }
+          __syncwarp();
+        }
+    }
+  }
+
+  if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 12)) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 4 ? 2 : 3));
+    unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
+    o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
+    o[3] = static_cast<unsigned long long>(clock64() - t_start);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace snn

@@ -6,8 +6,17 @@
 //       128-byte row XOR-permuted by (row % 8).  A contiguous run of rows of one column chunk is
 //       exactly a 128B-swizzled tcgen05 operand tile, so it is fetched with ONE 1-D bulk copy and
 //       can be consumed K-major (rows = M/N, cols = K) or MN-major (rows = K, cols = M/N).
-//   * spike bits: uint32 words [C/32][R]; word (c32, r) holds columns 32*c32 .. +31 of row r.
-//   * rows of time-stepped tensors: r = t * Bpad + b, Bpad = roundup(B, 128).
+//   * spike bits: uint32 words [C/32][Rt]; word (c32, r) holds neurons 32*c32 .. +31 of sample-step r.
+//   * sample-steps of the actor's time-stepped tensors are "tile-blocked": the batch is cut into tiles of Bt
+//     samples (T * Bt <= 256 when that leaves Bt >= 16, so two accumulator sets fit tensor memory), and
+//       r = tile * CT + t * Bt + (b % Bt),  tile = b / Bt,  CT = roundup(T * Bt, 64),  Rt = ntile * CT.
+//     One tile's T * Bt sample-steps are therefore contiguous: they are the N dimension of ONE tcgen05.mma
+//     (N = 240 for T = 5), which is what lets the scan-GEMMs run at the tensor core's full rate
+//     (tools/mma_rate.cu: an M = 128 MMA costs max(N / 2, 57 + N / 8) cycles).
+//   * "n-major image" of a time-stepped bf16 matrix G[r][n]: [Rt/64][NP/8][8 neurons][128 bytes = 64
+//     sample-steps], 16-byte pieces XOR-permuted by (n % 8) — MN-major B operand of dX, K-major A operand of dW.
+//   * voltages: fp32 [Rt/16][NP][16 sample-steps].
+//   * the dense critic keeps plain rows r = b, Bpad = roundup(B, 128).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -19,6 +28,7 @@ namespace snn {
 constexpr int kTileM = 128;       // batch rows per MMA tile (UMMA_M, cta_group::1)
 constexpr int kChunkK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int kMaxT = 32;
+constexpr int kEncBwdBlocks = 256;   // batch slices of the encoder-gradient kernel (one row of partials each)
 
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -37,8 +47,8 @@ struct LayerPlan {
   size_t wt_img;     // packed: backward operand, 2 planes of swz64 image of W^T [KP rows][NP cols]
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
-  size_t tr_bits;    // trace: output spike words [NP/32][R]
-  size_t tr_volt;    // trace: fp32 voltages [T][NP/16][Bpad][16] (column-group-major)
+  size_t tr_bits;    // trace: output spike words [NP/32][Rt]
+  size_t tr_volt;    // trace: fp32 voltages [Rt/16][NP][16]
 };
 
 struct SnnPlan {
@@ -46,17 +56,20 @@ struct SnnPlan {
   int T;
   int O, A, Pe, Pd;
   int K0, K0P;       // encoder neurons, padded
-  int NCmax;         // accumulator columns per timestep in the scan-GEMMs (T * NCmax <= 512)
-  int NCdx;          // same for the double-buffered backward scan-GEMM (T * NCdx <= 256)
-  int64_t B, Bpad, R;
+  int Bt;            // samples per batch tile
+  int TB;            // T * Bt: live sample-steps (accumulator columns) per tile
+  int CT;            // roundup(TB, 64): sample-steps per tile incl. padding
+  int sets;          // accumulator sets in tensor memory: 2 when TB <= 256
+  int ntile;         // ceil(B / Bt)
+  int64_t B, Bcap, Rt;   // Bcap = ntile * Bt, Rt = ntile * CT
   LayerPlan layer[SNN_MAX_LAYERS];
   size_t packed_bytes;
-  size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][R]
+  size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][Rt]
   size_t trace_bytes;
   // backward workspace
-  size_t ws_g[2];           // two ping-pong G image buffers (2 planes each)
+  size_t ws_g[2];           // two ping-pong G buffers (n-major images, 2 planes each)
   size_t ws_g_plane[2];
-  size_t ws_ga;             // fp32 [Bpad][K0P]  d loss / d pop_act
+  size_t ws_ga;             // fp32 [Bcap/16][K0P][16]  d loss / d pop_act
   size_t ws_partial, ws_partial_stride;   // fp32 split-K partials of dW, one region per layer
   size_t ws_dbpart, ws_dbpart_stride;     // fp32 partial bias grads, one region per layer
   size_t ws_small, ws_small_enc;          // partials of the decoder (ws_small) / encoder (ws_small_enc) gradients
@@ -77,12 +90,17 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.T = d.spike_ts;
   p.O = d.obs_dim; p.A = d.act_dim; p.Pe = d.en_pop; p.Pd = d.de_pop;
   p.K0 = d.obs_dim * d.en_pop;
-  p.K0P = static_cast<int>(round_up(p.K0, 64));
-  p.NCmax = p.T <= 5 ? 96 : (p.T <= 8 ? 64 : (p.T <= 16 ? 32 : 16));
-  p.NCdx = p.T <= 5 ? 48 : (p.T <= 8 ? 32 : 16);      // T > 16: single accumulator set (T * 16 > 256)
+  p.K0P = static_cast<int>(round_up(p.K0, 128));   // the encoder neurons are an M = 128 tile dimension in DX_ENC
+  p.Bt = (256 / p.T) / 16 * 16;
+  if (p.Bt > 128) p.Bt = 128;
+  if (p.Bt < 16) p.Bt = 16;                           // T > 16: one accumulator set of T * 16 <= 512 columns
+  p.TB = p.T * p.Bt;
+  p.CT = static_cast<int>(round_up(p.TB, 64));
+  p.sets = p.TB <= 256 ? 2 : 1;
   p.B = B;
-  p.Bpad = round_up(B > 0 ? B : 1, kTileM);
-  p.R = p.Bpad * p.T;
+  p.ntile = static_cast<int>(((B > 0 ? B : 1) + p.Bt - 1) / p.Bt);
+  p.Bcap = static_cast<int64_t>(p.ntile) * p.Bt;
+  p.Rt = static_cast<int64_t>(p.ntile) * p.CT;
   size_t off = 0;
   auto take = [&off](size_t bytes) { size_t o = off; off += round_up(static_cast<int64_t>(bytes), 1024); return o; };
   int k = p.K0, kp = p.K0P;
@@ -102,21 +120,21 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.packed_bytes = off;
   // trace
   off = 0;
-  p.tr_enc_bits = take(static_cast<size_t>(p.K0P / 32) * p.R * 4);
-  for (int l = 0; l < p.L; ++l) p.layer[l].tr_bits = take(static_cast<size_t>(p.layer[l].NP / 32) * p.R * 4);
+  p.tr_enc_bits = take(static_cast<size_t>(p.K0P / 32) * p.Rt * 4);
+  for (int l = 0; l < p.L; ++l) p.layer[l].tr_bits = take(static_cast<size_t>(p.layer[l].NP / 32) * p.Rt * 4);
   p.ws_fwd_bytes = off;
-  for (int l = 0; l < p.L; ++l) p.layer[l].tr_volt = take(static_cast<size_t>(p.R) * p.layer[l].NP * 4);
+  for (int l = 0; l < p.L; ++l) p.layer[l].tr_volt = take(static_cast<size_t>(p.Rt) * p.layer[l].NP * 4);
   p.trace_bytes = off;
   // backward workspace
   off = 0;
   size_t gmax[2] = {0, 0};
   for (int l = 0; l < p.L; ++l) {
-    const size_t plane = static_cast<size_t>(p.layer[l].NP / 64) * p.R * 128;
+    const size_t plane = static_cast<size_t>(p.layer[l].NP) * p.Rt * 2;
     const int slot = (p.L - 1 - l) & 1;
     if (plane > gmax[slot]) gmax[slot] = plane;
   }
   for (int s = 0; s < 2; ++s) { p.ws_g_plane[s] = gmax[s]; p.ws_g[s] = take(2 * gmax[s]); }
-  p.ws_ga = take(static_cast<size_t>(p.Bpad) * p.K0P * 4);
+  p.ws_ga = take(static_cast<size_t>(p.Bcap) * p.K0P * 4);
   p.dw_max_ctas = num_sms > 0 ? 2 * num_sms : 296;
   size_t part = 0;
   for (int l = 0; l < p.L; ++l) {
@@ -130,13 +148,13 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.ws_partial = take(p.ws_partial_stride * p.L);
   int npmax = p.K0P;
   for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
-  size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;
-  const size_t dbp_top = static_cast<size_t>(p.Bpad / 32) * p.layer[p.L - 1].NP;
+  size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;          // dX kernels: <= one row of partials per CTA
+  const size_t dbp_top = static_cast<size_t>(p.ntile) * p.layer[p.L - 1].NP;   // top scan: one row per batch tile
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
-  p.ws_small = take(static_cast<size_t>(p.Bpad / 32) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
-  p.ws_small_enc = take(static_cast<size_t>(p.Bpad / 64) * 2 * p.K0 * 4 + 1024);                // encoder partials
+  p.ws_small = take(static_cast<size_t>(p.ntile) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
+  p.ws_small_enc = take(static_cast<size_t>(kEncBwdBlocks) * 2 * p.K0P * 4 + 1024);          // encoder partials
   p.ws_bwd_bytes = off;
   *out = p;
   return SNN_OK;

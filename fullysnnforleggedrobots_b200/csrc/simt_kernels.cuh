@@ -101,12 +101,16 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
   return bits;
 }
 
+// batch-tile geometry of the actor's time-stepped tensors (plan.cuh): sample-step (t, b) -> tile * CT + t * Bt + b % Bt
+struct TileGeom { int Bt, CT, ntile; long long Rt; };
+
 // TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T
 template <int TT>
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
-                                                    const float* __restrict__ std, int B, int Bpad, int O, int P,
-                                                    int K0, int T, float eps, int64_t R, uint32_t* __restrict__ bits) {
-  // block (32 neurons, 8 warps) covers 128 rows: each warp walks 16 rows (few, fat blocks: the per-row work is tiny)
+                                                    const float* __restrict__ std, int B, TileGeom tg, int O, int P,
+                                                    int K0, int T, float eps, uint32_t* __restrict__ bits) {
+  // block (32 neurons, 8 warps) covers 128 samples: each warp walks 16 of them (few, fat blocks: the per-sample work is
+  // tiny); lane t of the warp ends up with the spike word of step t and stores it
   const int k = blockIdx.x * 32 + threadIdx.x;
   const bool k_live = k < K0;
   const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
@@ -114,16 +118,15 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ o
   const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
   const float nh_inv_var = -0.5f * __frcp_rn(var);
   const int b0 = blockIdx.y * 128 + threadIdx.y;
-  const float* xp = obs + static_cast<size_t>(b0) * O + o;
-  uint32_t* wp = bits + static_cast<size_t>(blockIdx.x) * R + b0;
+  const int Bcap = tg.ntile * tg.Bt;
   const int nt = TT > 0 ? TT : T;
 #pragma unroll 4
   for (int i = 0; i < 16; ++i) {
     const int b = b0 + i * 8;
-    if (b >= Bpad) break;
+    if (b >= Bcap) break;
     uint32_t sp = 0;
     if ((b < B) && k_live) {
-      const float d = __fsub_rn(xp[static_cast<size_t>(i) * 8 * O], mk);
+      const float d = __fsub_rn(obs[static_cast<size_t>(b) * O + o], mk);
       // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
       // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
       float margin;
@@ -134,17 +137,20 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ o
         sp = regular_spikes<0>(static_cast<float>(exp(static_cast<double>(q))), T, margin);
       }
     }
-    uint32_t* w = wp + i * 8;
+    const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
+    uint32_t mine = 0;
     for (int t = 0; t < nt; ++t) {
       const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
-      if (threadIdx.x == 0) w[static_cast<size_t>(t) * Bpad] = word;
+      if (static_cast<int>(threadIdx.x) == t) mine = word;
     }
+    if (static_cast<int>(threadIdx.x) < nt)
+      bits[static_cast<size_t>(blockIdx.x) * tg.Rt + static_cast<size_t>(tile) * tg.CT + threadIdx.x * tg.Bt + bl] = mine;
   }
 }
 
 // ------------------------------------------------------------------ decoder
 // actor_critic.py:140-150: rate = spike count / T ; mu[b,a] = sum_p w[a,p] rate[b, a P + p] + bias[a] (; tanh)
-__global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict__ bits, int64_t R, int B, int Bpad, int A,
+__global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict__ bits, TileGeom tg, int B, int A,
                                                     int P, int T, const float* __restrict__ dec_w,
                                                     const float* __restrict__ dec_b, int dec_tanh, float* __restrict__ mu) {
   // one thread per (action, sample), samples fastest: the <= 2 spike words an action's population spans are
@@ -153,6 +159,9 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
   if (idx >= B * A) return;
   const int a0 = idx / B, b = idx - a0 * B;
   const float invT = static_cast<float>(T);
+  const long long R = tg.Rt;
+  const int tile = b / tg.Bt;
+  const size_t r0 = static_cast<size_t>(tile) * tg.CT + (b - tile * tg.Bt);     // sample-step (0, b)
   for (int a = a0; a == a0; ++a) {
     const int n0 = a * P;
     const int w0 = n0 >> 5, w1 = (n0 + P - 1) >> 5, sh = n0 & 31;
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
 #pragma unroll
       for (int pp = 0; pp < 16; ++pp) cnt[pp] = 0;
       for (int t = 0; t < T; ++t) {
-        const size_t r = static_cast<size_t>(t) * Bpad + b;
+        const size_t r = r0 + static_cast<size_t>(t) * tg.Bt;
         const uint32_t lo = __ldg(bits + static_cast<size_t>(w0) * R + r);
         const uint32_t hi = w1 != w0 ? __ldg(bits + static_cast<size_t>(w1) * R + r) : 0u;
         const uint32_t x = __funnelshift_r(lo, hi, sh);      // bits n0 .. n0+31 of this sample at step t
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
         const int n = n0 + pp;
         int cnt = 0;
         for (int t = 0; t < T; ++t)
-          cnt += (__ldg(bits + static_cast<size_t>(n >> 5) * R + static_cast<size_t>(t) * Bpad + b) >> (n & 31)) & 1u;
+          cnt += (__ldg(bits + static_cast<size_t>(n >> 5) * R + r0 + static_cast<size_t>(t) * tg.Bt) >> (n & 31)) & 1u;
         acc = __fmaf_rn(dec_w[n], __fdiv_rn(static_cast<float>(cnt), invT), acc);
       }
     }
@@ -188,160 +197,139 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
 
 // ------------------------------------------------------------------ BPTT of the output population layer
 // g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the
-// recurrence of SURVEY.md §8a.  Writes g_c hi/lo planes as swz64 image and per-block bias partials.
-__device__ __forceinline__ float warp_col_sums16(float (&x)[16], int lane) {   // see scan_gemm.cuh
-#pragma unroll
-  for (int h = 16, n = 16; h >= 2; h >>= 1, n >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float send = up ? x[i] : x[i + n / 2];
-      const float keep = up ? x[i + n / 2] : x[i];
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
-}
-
-// one BPTT step of 16 neurons of one row: updates the recurrence state and writes the hi/lo planes of g_c
-__device__ __forceinline__ void top_scan_step(const float (&gup)[16], const float (&v)[16], float (&gvn)[16], float (&gcn)[16],
-                                              float (&dbacc)[16], uint8_t* g_img, size_t g_plane, int64_t R, size_t r, int n0) {
-  float gc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float gs = gup[j] - gvn[j] * (0.75f * v[j]);
-    const float win = fabsf(__fsub_rn(v[j], 0.5f)) < 0.5f ? 1.f : 0.f;
-    const float keep = v[j] > 0.5f ? 0.f : 0.75f;
-    const float gv = gs * win + gvn[j] * keep;
-    gc[j] = gv + 0.5f * gcn[j];
-    gvn[j] = gv; gcn[j] = gc[j];
-    dbacc[j] += gc[j];
-  }
-  float hi[16], lo[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(gc[j]); lo[j] = gc[j] - hi[j]; }
-  const size_t base = static_cast<size_t>(n0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
-  const int p0 = (n0 & 63) >> 3;
-  const int sw = static_cast<int>(r & 7);
-  *reinterpret_cast<uint4*>(g_img + base + ((p0 ^ sw) << 4)) =
-      make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-  *reinterpret_cast<uint4*>(g_img + base + (((p0 + 1) ^ sw) << 4)) =
-      make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-  *reinterpret_cast<uint4*>(g_img + g_plane + base + ((p0 ^ sw) << 4)) =
-      make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-  *reinterpret_cast<uint4*>(g_img + g_plane + base + (((p0 + 1) ^ sw) << 4)) =
-      make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
-}
-
-__global__ void __launch_bounds__(256) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+// recurrence of SURVEY.md §8a.  Same orientation as the dX epilogue (nm_gemm.cuh): thread = neuron, 16 samples x T
+// steps in registers; writes the g_c hi/lo planes (n-major image) and per-tile partials of the bias gradient and of
+// the decoder gradients:  dec_part[tile][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
+// dec_part[tile][1][n] = sum_b G[b,a(n)]  (d bias, read at n = a * P).
+__global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                       int dec_tanh, const float* __restrict__ dec_w,
-                                                      const float* __restrict__ volt, int B, int Bpad, int A, int P,
-                                                      int NP, int T, int64_t R, uint8_t* __restrict__ g_img,
-                                                      size_t g_plane, float* __restrict__ db_part,
-                                                      float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
-  // block = 8 warps x 32 rows; lane = row, warp w walks the 16-column groups w, w+8, ...  grid = Bpad / 32.
-  // Also produces the decoder gradients: dec_part[blk][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
-  // dec_part[blk][1][n] = sum_b G[b,a(n)] (d bias, read at n = a * P).
-  // A warp reads 32 rows x 64 B = one contiguous 2 KiB run of the voltage trace per (t, group).
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b = blockIdx.x * 32 + lane;
-  const bool row_live = b < B;
+                                                      const float* __restrict__ volt, int B, TileGeom tg, int A, int P,
+                                                      int NP, int T, uint8_t* __restrict__ g_img, size_t g_plane,
+                                                      float* __restrict__ db_part /* [ntile][NP] */,
+                                                      float* __restrict__ dec_part /* [ntile][2][NP] */) {
+  // grid (ntile, NP / 128); a warp reads 32 neurons x 64 B = one contiguous 2 KiB run of the voltage trace per (t, group)
+  const int tile = blockIdx.x;
+  const int n = blockIdx.y * 128 + threadIdx.x;
+  const bool n_live = n < A * P;
+  const int a = n_live ? n / P : 0;
+  const float wn = n_live ? dec_w[n] : 0.f;
   const float Tf = static_cast<float>(T);
-  for (int g16 = wid; g16 < NP / 16; g16 += 8) {
-    const int n0 = g16 * 16;
-    float gup[16], Gc[16], cnt[16];
+  const size_t c_tile = static_cast<size_t>(tile) * tg.CT;
+  const int TB = T * tg.Bt;
+  uint8_t* const grow = g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
+  const int sw = n & 7;
+  const size_t vstep = (static_cast<size_t>(tg.Bt) >> 4) * NP * 16;
+  float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
+  for (int bg = 0; bg < (tg.Bt >> 4); ++bg) {
+    const int col0 = bg * 16;
+    const int b0 = tile * tg.Bt + col0;
+    float gup[16], Gc[16], cnt[16], gvn[16], gcn[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int n = n0 + j;
-      gup[j] = 0.f; Gc[j] = 0.f; cnt[j] = 0.f;
-      if (row_live && n < A * P) {
-        const int a = n / P;
-        float G = g_mu[static_cast<size_t>(b) * A + a];
-        if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a]; G = G * (1.f - m * m); }
+      gup[j] = 0.f; Gc[j] = 0.f; cnt[j] = 0.f; gvn[j] = 0.f; gcn[j] = 0.f;
+      if (n_live && b0 + j < B) {
+        float G = g_mu[static_cast<size_t>(b0 + j) * A + a];
+        if (dec_tanh) { const float m = mu[static_cast<size_t>(b0 + j) * A + a]; G = G * (1.f - m * m); }
         Gc[j] = G;
-        gup[j] = __fdiv_rn(G * dec_w[n], Tf);
+        gup[j] = __fdiv_rn(G * wn, Tf);
       }
     }
-    float gvn[16], gcn[16], dbacc[16];
+    const float* vbase = volt + (((c_tile + col0) >> 4) * NP + n) * 16;
+    // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's load in flight
+    float4 vn[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; dbacc[j] = 0.f; }
-    const float* vbase = volt + (static_cast<size_t>(g16) * Bpad + b) * 16;
-    const size_t vstep = static_cast<size_t>(NP >> 4) * Bpad * 16;
-    {
-      // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's load in flight
-      float4 vn[4];
+    for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(T - 1) * vstep) + j);
+    for (int t = T - 1; t >= 0; --t) {
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        vn[j] = row_live ? __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(T - 1) * vstep) + j)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t = T - 1; t >= 0; --t) {
-        float v[16];
+      for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
+      if (t > 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) cnt[j] += v[j] > 0.5f ? 1.f : 0.f;       // output spike count -> rate
-        if (t > 0 && row_live) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep) + j);
-        }
-        top_scan_step(gup, v, gvn, gcn, dbacc, g_img, g_plane, R, static_cast<size_t>(t) * Bpad + b, n0);
+        for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep) + j);
       }
-    }
-    const float tot = warp_col_sums16(dbacc, lane);
-    if ((lane & 1) == 0) db_part[static_cast<size_t>(blockIdx.x) * NP + n0 + (lane >> 1)] = tot;
-    float dwd[16];
+      float hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) dwd[j] = Gc[j] * __fdiv_rn(cnt[j], Tf);
-    const float tw = warp_col_sums16(dwd, lane);
-    const float tb = warp_col_sums16(Gc, lane);
-    if ((lane & 1) == 0) {
-      float* dst = dec_part + (static_cast<size_t>(blockIdx.x) * 2) * NP + n0 + (lane >> 1);
-      dst[0] = tw;
-      dst[NP] = tb;
+      for (int j = 0; j < 16; ++j) {
+        const bool live = b0 + j < B;
+        const float vj = live ? v[j] : 0.f;
+        cnt[j] += vj > 0.5f ? 1.f : 0.f;                       // output spike count -> rate
+        const float gs = gup[j] - gvn[j] * (0.75f * vj);
+        const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
+        const float keep = vj > 0.5f ? 0.f : 0.75f;
+        const float gv = gs * win + gvn[j] * keep;
+        const float gc = gv + 0.5f * gcn[j];
+        gvn[j] = gv; gcn[j] = gc;
+        dbsum += gc;
+        hi[j] = bf16_round(gc);
+        lo[j] = gc - hi[j];
+      }
+      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);
+      uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(NP) << 7);
+      const int p0 = static_cast<int>((c & 63) >> 3);
+      *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+      *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+      *reinterpret_cast<uint4*>(dst + g_plane + ((p0 ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+      *reinterpret_cast<uint4*>(dst + g_plane + (((p0 + 1) ^ sw) << 4)) =
+          make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      dwd += Gc[j] * __fdiv_rn(cnt[j], Tf);
+      dbd += Gc[j];
     }
   }
+  // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
+  for (int cc = TB; cc < tg.CT; cc += 8) {
+    const size_t c = c_tile + cc;
+    uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(NP) << 7) + (((static_cast<int>(c & 63) >> 3) ^ sw) << 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(dst + g_plane) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  db_part[static_cast<size_t>(tile) * NP + n] = dbsum;
+  dec_part[(static_cast<size_t>(tile) * 2) * NP + n] = dwd;
+  dec_part[(static_cast<size_t>(tile) * 2 + 1) * NP + n] = dbd;
 }
 
 // (decoder gradients are produced by top_scan_kernel)
 
 // ------------------------------------------------------------------ encoder gradients
-// From g_a = d loss / d pop_act [Bpad][K0P]:
+// From g_a = d loss / d pop_act, laid out [Bcap/16][K0P][16 samples] by the DX_ENC epilogue:
 //   d mean = sum_b g_a a (x-mean)/var ; d std = sum_b g_a a (x-mean)^2 std / var^2 ; (var = std^2 + eps)
-// Block = 64 rows, threads stride over k; partials [gridDim.x][2][K0].
-__global__ void __launch_bounds__(256) enc_bwd_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
+// thread = encoder neuron; block (128 neurons) x batch slice; partials [gridDim.y][2][K0P].
+__global__ void __launch_bounds__(128) enc_bwd_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                                      const float* __restrict__ std, const float* __restrict__ g_a,
                                                      int B, int O, int P, int K0, int K0P, float eps,
-                                                     float* __restrict__ part /* [gridDim.y][2][K0] */) {
-  // block (32 encoder neurons, 8 row lanes); grid = (ceil(K0/32), ceil(B/64)); each thread walks 8 rows
-  const int k = blockIdx.x * 32 + threadIdx.x;
+                                                     float* __restrict__ part /* [gridDim.y][2][K0P] */) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
   const bool live = k < K0;
   float dm = 0.f, ds = 0.f;
   if (live) {
     const float mk = mean[k], sk = std[k];
     const float inv_var = 1.f / (sk * sk + eps);
     const int o = k / P;
+    const int ngroups = (B + 15) >> 4;
+    for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {
+      const float4* src = reinterpret_cast<const float4*>(g_a + (static_cast<size_t>(g) * K0P + k) * 16);
+      float ga[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = blockIdx.y * 64 + j * 8 + threadIdx.y;
-      if (b < B) {
-        const float x = obs[static_cast<size_t>(b) * O + o];
-        const float d = x - mk;
-        const float a = expf(-0.5f * d * d * inv_var);
-        const float ga = g_a[static_cast<size_t>(b) * K0P + k] * a;
-        dm += ga * d * inv_var;
-        ds += ga * d * d * inv_var * inv_var * sk;
+      for (int j = 0; j < 4; ++j) { const float4 v = __ldg(src + j); ga[4 * j] = v.x; ga[4 * j + 1] = v.y; ga[4 * j + 2] = v.z; ga[4 * j + 3] = v.w; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int b = g * 16 + j;
+        if (b < B) {
+          const float d = obs[static_cast<size_t>(b) * O + o] - mk;
+          const float gaa = ga[j] * expf(-0.5f * d * d * inv_var);
+          dm += gaa * d * inv_var;
+          ds += gaa * d * d * inv_var * inv_var * sk;
+        }
       }
     }
   }
-  __shared__ float sh[2][8][33];
-  sh[0][threadIdx.y][threadIdx.x] = dm;
-  sh[1][threadIdx.y][threadIdx.x] = ds;
-  __syncthreads();
-  if (threadIdx.y < 2 && live) {
-    float t = 0.f;
-    for (int y = 0; y < 8; ++y) t += sh[threadIdx.y][y][threadIdx.x];
-    part[(static_cast<size_t>(blockIdx.y) * 2 + threadIdx.y) * K0 + k] = t;
-  }
+  part[(static_cast<size_t>(blockIdx.y) * 2) * K0P + k] = dm;
+  part[(static_cast<size_t>(blockIdx.y) * 2 + 1) * K0P + k] = ds;
 }
 
 // d obs[b,o] = sum_p g_a a (-(x-mean))/var   (RMA: the actor input is cat(obs, latent) and needs grad)
@@ -358,7 +346,7 @@ __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __re
     const float mk = mean[k], sk = std[k];
     const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
     const float a = pop_activation_fast(x, mk, sk, eps);
-    acc += g_a[static_cast<size_t>(b) * K0P + k] * a * (-(x - mk)) / var;
+    acc += g_a[(static_cast<size_t>(b >> 4) * K0P + k) * 16 + (b & 15)] * a * (-(x - mk)) / var;
   }
   d_obs[idx] = acc;
 }

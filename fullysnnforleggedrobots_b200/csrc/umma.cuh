@@ -68,6 +68,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// 1-D shared -> shared copy by the same engine (destination: this CTA's own shared memory, addressed in the
+// shared::cluster window), completion signalled on an mbarrier.
+__device__ __forceinline__ void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "r"(smem_u32(src_smem)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM
 // One full warp allocates `ncols` (power of two >= 32) columns; base address lands in *dst_smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

@@ -166,25 +166,28 @@ class SnnEngine:
     # ------------------------------------------------------------------ test hooks
     def unpack_trace(self, trace: torch.Tensor, B: int):
         """Decode a training trace into dense tensors (tests / debugging only; not on the product path)."""
-        arr = (C.c_int64 * (6 + 4 * _lib.SNN_MAX_LAYERS))()
+        arr = (C.c_int64 * (8 + 4 * _lib.SNN_MAX_LAYERS))()
         n = _lib.check(_lib.lib().snn_debug_trace_layout(C.byref(self.desc), B, arr, len(arr)), "trace layout")
-        Lc, T, Bpad, R, K0P, enc_off = (int(arr[i]) for i in range(6))
+        Lc, T, Bt, CT, ntile, Rt, K0P, enc_off = (int(arr[i]) for i in range(8))
         raw = trace.cpu()
+        # sample-step (t, b) lives at column tile * CT + t * Bt + b % Bt (csrc/plan.cuh)
+        bb = torch.arange(ntile * Bt)
+        col = ((bb // Bt) * CT + bb % Bt).unsqueeze(0) + (torch.arange(T) * Bt).unsqueeze(1)      # [T, Bcap]
 
         def bits(off, ncols_p, ncols):
-            words = raw[off: off + (ncols_p // 32) * R * 4].view(torch.int32).reshape(ncols_p // 32, R)
+            words = raw[off: off + (ncols_p // 32) * Rt * 4].view(torch.int32).reshape(ncols_p // 32, Rt)
             sh = torch.arange(32, dtype=torch.int32).reshape(1, 32, 1)
-            b = ((words.unsqueeze(1) >> sh) & 1).reshape(ncols_p, T, Bpad)      # [col, t, b]
-            return b.permute(1, 2, 0)[:, :B, :ncols].to(torch.float32).contiguous()
+            b = ((words.unsqueeze(1) >> sh) & 1).reshape(ncols_p, Rt)               # [neuron, sample-step]
+            return b[:, col].permute(1, 2, 0)[:, :B, :ncols].to(torch.float32).contiguous()
 
         res = {"enc_spikes": bits(enc_off, K0P, self.dims[0]), "spikes": [], "volt": []}
         for l in range(Lc):
-            NP, KP, boff, voff = (int(arr[6 + 4 * l + i]) for i in range(4))
+            NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace layout: [t][n / 16][Bpad][16]
-            v = raw[voff: voff + R * NP * 4].view(torch.float32).reshape(T, NP // 16, Bpad, 16)
-            v = v.permute(0, 2, 1, 3).reshape(T, Bpad, NP)
-            res["volt"].append(v[:, :B, :self.dims[l + 1]].contiguous())
+            # voltage trace layout: [Rt / 16][NP][16 sample-steps]
+            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(Rt // 16, NP, 16)
+            v = v.permute(1, 0, 2).reshape(NP, Rt)
+            res["volt"].append(v[:, col].permute(1, 2, 0)[:, :B, :self.dims[l + 1]].contiguous())
         return res
 
 

@@ -1,0 +1,59 @@
+// Does cp.async.bulk shared::cta -> shared::cluster (own CTA) work in a plain (non-cluster) launch?
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "umma.cuh"
+using namespace snn;
+
+__global__ void __launch_bounds__(128, 1) s2s_kernel(uint32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  uint32_t* src = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(smem + 32768);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) { src[i] = i * 2654435761u + blockIdx.x; dst[i] = 0; }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 30720u);
+    bulk_s2s(dst, src, 30720u, &bar);
+  }
+  mbar_wait(&bar, 0);
+  uint32_t bad = 0;
+  for (int i = threadIdx.x; i < 7680; i += blockDim.x) bad += dst[i] != src[i];
+  atomicAdd(out, bad);
+}
+
+int main_cluster();
+int main(int argc, char**) {
+  if (argc > 1) return main_cluster();
+  uint32_t* out;
+  cudaMalloc(&out, 4);
+  cudaMemset(out, 0, 4);
+  cudaFuncSetAttribute(s2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+  s2s_kernel<<<148, 128, 65536 + 1024>>>(out);
+  cudaError_t e = cudaDeviceSynchronize();
+  uint32_t h = 123;
+  cudaMemcpy(&h, out, 4, cudaMemcpyDeviceToHost);
+  std::printf("plain launch: %s, mismatches %u\n", cudaGetErrorString(e), h);
+  return 0;
+}
+
+int main_cluster() {
+  uint32_t* out;
+  cudaMalloc(&out, 4);
+  cudaMemset(out, 0, 4);
+  cudaFuncSetAttribute(s2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 65536 + 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, s2s_kernel, out);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  uint32_t h = 123;
+  cudaMemcpy(&h, out, 4, cudaMemcpyDeviceToHost);
+  std::printf("cluster(1) launch: %s, mismatches %u\n", cudaGetErrorString(e), h);
+  return 0;
+}
