@@ -89,7 +89,7 @@ int device_ready(int* num_sms) {
   if (di.checked < 0) return fail(SNN_EARCH, "device is not compute capability 10.x (sm_100a kernels only, no fallback)");
   if (!di.attrs_set) {
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(nm_gemm_smem_bytes<NM_FWD>())));
+                                  static_cast<int>(kSmemOptIn)));
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(nm_gemm_smem_bytes<NM_DX>())));
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -197,12 +197,14 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = nm_gemm_grid(q.nmt, p.ntile, num_sms);
+    q.s_stage = nm_fwd_s_stage(p.TB);
+    q.nstg = nm_fwd_nstg(q.s_stage);
     { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
     // explicit 1-CTA cluster: the shared->shared bulk copy of the expanders addresses shared::cluster memory, which is
     // an illegal instruction in a launch without a cluster dimension
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NmCfg<NM_FWD>::THREADS);
-    cfg.dynamicSmemBytes = nm_gemm_smem_bytes<NM_FWD>(); cfg.stream = st;
+    cfg.dynamicSmemBytes = nm_fwd_smem_bytes(q.s_stage, q.nstg); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

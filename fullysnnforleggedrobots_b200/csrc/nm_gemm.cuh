@@ -28,7 +28,7 @@
 // per-neuron sums (bias gradient) live in registers for the whole kernel.
 //
 // Warp roles: 0 = bulk-copy producer (weights / g_c), 1 = MMA issuer + TMEM owner, 2 = spike-word producer (FWD),
-// 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
+// 3 = staging -> operand-slot copy issuer (FWD), 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
@@ -72,15 +72,17 @@ struct NmParams {
   float* db_part;           // [2 * gridDim.x / nmt][MP]
   // DX_ENC epilogue
   float* g_a;               // [Bcap/16][MP][16]
+  int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
+  int nstg;                 // FWD: staging buffers (1 or 2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand
   unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
 };
 
 template <int MODE> struct NmCfg;
-// FWD: 2 weight stages of 3 x 16 KiB planes, 2 spike sub-tiles of <= 256 sample-steps x 128 B (+ one staging buffer
-// of the same size, see the expander role), 4 spike-word stages
+// FWD: 2 weight stages of 3 x 16 KiB planes, 2 operand slots + 1-2 staging buffers of one spike sub-tile each
+// (<= 256 sample-steps x 128 B; the size is a launch parameter), 2 spike-word stages
 template <> struct NmCfg<NM_FWD> {
-  static constexpr int NW = 2, W_STAGE = 49152, NS = 2, S_STAGE = 32768, NBITS = 4, BITS_STAGE = 2048, THREADS = 512;
+  static constexpr int NW = 2, W_STAGE = 49152, NS = 2, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
 };
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (half a 64-neuron chunk: 2 planes x <= 4 panels x 4 KiB)
 template <> struct NmCfg<NM_DX> {
@@ -89,12 +91,19 @@ template <> struct NmCfg<NM_DX> {
 template <> struct NmCfg<NM_DX_ENC> : NmCfg<NM_DX> {};
 
 template <int MODE>
-__host__ __device__ constexpr size_t nm_gemm_smem_bytes() {
+__host__ __device__ constexpr size_t nm_gemm_smem_bytes() {      // dX kernels
   return 1024 /*align slack*/ + static_cast<size_t>(NmCfg<MODE>::NW) * NmCfg<MODE>::W_STAGE +
-         static_cast<size_t>(NmCfg<MODE>::NS) * NmCfg<MODE>::S_STAGE +
-         static_cast<size_t>(NmCfg<MODE>::NBITS) * NmCfg<MODE>::BITS_STAGE +
-         (MODE == NM_FWD ? 4096 /*LUT*/ + NmCfg<MODE>::S_STAGE /*staging*/ : 0) + 512;
+         static_cast<size_t>(NmCfg<MODE>::NS) * NmCfg<MODE>::S_STAGE + 512;
 }
+constexpr size_t kSmemOptIn = 232448;    // 227 KiB per CTA
+// forward kernel: spike sub-tile bytes and number of staging buffers for a batch-tile geometry
+inline int nm_fwd_s_stage(int TB) { return ((TB < 256 ? TB : 256) * 128 + 1023) / 1024 * 1024; }
+inline size_t nm_fwd_smem_bytes(int s_stage, int nstg) {
+  return 1024 + static_cast<size_t>(NmCfg<NM_FWD>::NW) * NmCfg<NM_FWD>::W_STAGE +
+         static_cast<size_t>(NmCfg<NM_FWD>::NS + nstg) * s_stage +
+         static_cast<size_t>(NmCfg<NM_FWD>::NBITS) * NmCfg<NM_FWD>::BITS_STAGE + 4096 /*LUT*/ + 512;
+}
+inline int nm_fwd_nstg(int s_stage) { return nm_fwd_smem_bytes(s_stage, 2) <= kSmemOptIn ? 2 : 1; }
 
 // CTAs to launch: a multiple of the neuron tiles, at most one per SM, at most one per item
 inline int nm_gemm_grid(int nmt, int ntile, int num_sms) {
@@ -111,10 +120,11 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   constexpr uint32_t NBM = C::NBITS > 0 ? C::NBITS : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S_STAGE = IS_FWD ? p.s_stage : C::S_STAGE;
   uint8_t* w_ring = smem;
   uint8_t* s_ring = w_ring + C::NW * C::W_STAGE;
-  uint8_t* staging = s_ring + C::NS * C::S_STAGE;                                   // FWD only
-  uint8_t* bits_ring = staging + (IS_FWD ? C::S_STAGE : 0);
+  uint8_t* staging = s_ring + C::NS * S_STAGE;                                      // FWD only: nstg buffers
+  uint8_t* bits_ring = staging + (IS_FWD ? p.nstg * S_STAGE : 0);
   uint4* lut = reinterpret_cast<uint4*>(bits_ring + C::NBITS * C::BITS_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + (IS_FWD ? 4096 : 0));
   uint64_t* w_full = bars;                      // [<= 4]
@@ -125,7 +135,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint64_t* bits_full = acc_empty + 2;          // [NBITS]
   uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bits_empty + C::NBITS);
+  uint64_t* stg_full = bits_empty + C::NBITS;   // [2]  FWD: staging buffer written by the expanders
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(stg_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
@@ -140,6 +151,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) mbar_init(&stg_full[s], 4);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nsets == 2 ? 128 : 256); }
     fence_mbar_init();
   }
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 const size_t pan0 = static_cast<size_t>(tile) * (p.CT >> 6) + static_cast<size_t>(sub) * 4;
                 for (int pl = 0; pl < 2; ++pl)
                   for (int pan = 0; pan < npan; ++pan)
-                    bulk_g2s(s_ring + gs * C::S_STAGE + pl * 16384 + pan * 4096,
+                    bulk_g2s(s_ring + gs * S_STAGE + pl * 16384 + pan * 4096,
                              p.b_img + pl * p.b_plane + ((pan0 + pan) * (p.KP >> 3) + static_cast<size_t>(kc) * 8 + half * 4) * 1024,
                              4096u, &s_full[gs]);
               }
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             tc_fence_after_sync();
             if (elect_one()) {
               const int ncols = min(256, p.TB - sub * 256);
-              const uint32_t b_lo = s_ring_lo + ss * (C::S_STAGE >> 4);
+              const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
               const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
               if (p.dbg & 1) {
               } else if (IS_FWD) {
@@ -302,7 +314,77 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
       const uint32_t t_set = t_lane + aset * 256;
-      for (int bg = (p.dbg & 2) ? nbg : bg0; bg < nbg; bg += bgstep) {
+      if (MODE == NM_DX) {
+        // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the fp32 voltages of a step are 64 B
+        // per thread straight from the HBM/L2-resident trace (~1 us away), so the loads run THREE steps ahead of the
+        // recurrence (two epilogue warps per scheduler cannot hide that latency by themselves)
+        const int nb = (nbg - bg0 + bgstep - 1) / bgstep;
+        const int nsteps = (p.dbg & 2) ? 0 : nb * p.T;
+        uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
+        const int sw = n & 7;
+        float gvn[16], gcn[16];
+        auto loadv = [&](int sidx, float4 (&buf)[4]) {
+          if (sidx < nsteps) {
+            const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
+            const float4* src = reinterpret_cast<const float4*>(
+                p.v_in + (((c_tile + static_cast<size_t>(t * p.Bt + (bg0 + bi * bgstep) * 16)) >> 4) * p.MP + n) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) buf[j] = __ldg(src + j);
+          }
+        };
+        auto step = [&](int sidx, const float4 (&buf)[4]) {
+          const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
+          const int col0 = (bg0 + bi * bgstep) * 16;
+          const int nlive = p.B - (b_tile + col0);
+          const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
+          if (t == p.T - 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
+          }
+          uint32_t x[16];
+          tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
+          const float v[16] = {buf[0].x, buf[0].y, buf[0].z, buf[0].w, buf[1].x, buf[1].y, buf[1].z, buf[1].w,
+                               buf[2].x, buf[2].y, buf[2].z, buf[2].w, buf[3].x, buf[3].y, buf[3].z, buf[3].w};
+          tmem_ld_wait();
+          float hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool live = (vmask >> j) & 1u;
+            const float gup = live ? __uint_as_float(x[j]) : 0.f;
+            const float vj = live ? v[j] : 0.f;
+            const float gs = gup - gvn[j] * (0.75f * vj);
+            const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
+            const float keep = vj > 0.5f ? 0.f : 0.75f;
+            const float gv = gs * win + gvn[j] * keep;
+            const float gc = gv + 0.5f * gcn[j];
+            gvn[j] = gv;
+            gcn[j] = gc;
+            dbsum += gc;
+            hi[j] = bf16_round(gc);
+            lo[j] = gc - hi[j];
+          }
+          const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
+          uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7);      // panel stride = MP / 8 * 1024
+          const int p0 = static_cast<int>((c & 63) >> 3);
+          const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+          const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
+          const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+          const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+          *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) = h0;
+          *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) = h1;
+          *reinterpret_cast<uint4*>(dst + p.g_plane + ((p0 ^ sw) << 4)) = l0;
+          *reinterpret_cast<uint4*>(dst + p.g_plane + (((p0 + 1) ^ sw) << 4)) = l1;
+        };
+        float4 vb0[4], vb1[4], vb2[4];
+        loadv(0, vb0); loadv(1, vb1); loadv(2, vb2);
+        for (int sidx = 0; sidx < nsteps; sidx += 3) {
+          step(sidx, vb0);
+          loadv(sidx + 3, vb0);
+          if (sidx + 1 < nsteps) { step(sidx + 1, vb1); loadv(sidx + 4, vb1); }
+          if (sidx + 2 < nsteps) { step(sidx + 2, vb2); loadv(sidx + 5, vb2); }
+        }
+      }
+      for (int bg = (MODE == NM_DX || (p.dbg & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
         const int col0 = bg * 16;
         // bit j: sample b_tile + col0 + j exists
         const int nlive = p.B - (b_tile + col0);
@@ -344,60 +426,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             for (int j = 0; j < 16; ++j) x[j] = xn[j];
           }
         } else if (MODE == NM_DX) {
-          float gvn[16], gcn[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
-          const size_t vstep = (static_cast<size_t>(p.Bt) >> 4) * p.MP * 16;       // floats between timesteps
-          const float* vbase = p.v_in + (((c_tile + col0) >> 4) * p.MP + n) * 16;
-          float4 vn[4];
-          {
-            const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(p.T - 1) * vstep);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
-          }
-          uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
-          const int sw = n & 7;
-          for (int t = p.T - 1; t >= 0; --t) {
-            uint32_t x[16];
-            tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
-            if (t > 0) {   // prefetch the next (earlier) timestep's voltages
-              const float4* src = reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) vn[j] = __ldg(src + j);
-            }
-            tmem_ld_wait();
-            float hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool live = (vmask >> j) & 1u;
-              const float gup = live ? __uint_as_float(x[j]) : 0.f;
-              const float vj = live ? v[j] : 0.f;
-              const float gs = gup - gvn[j] * (0.75f * vj);
-              const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
-              const float keep = vj > 0.5f ? 0.f : 0.75f;
-              const float gv = gs * win + gvn[j] * keep;
-              const float gc = gv + 0.5f * gcn[j];
-              gvn[j] = gv;
-              gcn[j] = gc;
-              dbsum += gc;
-              hi[j] = bf16_round(gc);
-              lo[j] = gc - hi[j];
-            }
-            const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
-            uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7);      // panel stride = MP / 8 * 1024
-            const int p0 = static_cast<int>((c & 63) >> 3);
-            const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-            const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-            const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-            const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
-            *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) = h0;
-            *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) = h1;
-            *reinterpret_cast<uint4*>(dst + p.g_plane + ((p0 ^ sw) << 4)) = l0;
-            *reinterpret_cast<uint4*>(dst + p.g_plane + (((p0 + 1) ^ sw) << 4)) = l1;
-          }
+          // handled by the software-pipelined loop above
         } else {   // NM_DX_ENC
           float gam[16], ga[16];
 #pragma unroll
@@ -434,16 +463,36 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     }
     if (MODE == NM_DX)
       p.db_part[(static_cast<size_t>(tile0) * 2 + grp) * p.MP + n] = dbsum;
+  } else if (IS_FWD && warp == 3) {
+    // ===================================================== staging -> operand slot (shared->shared bulk copy)
+    uint32_t u = 0;
+    const uint32_t nstg = static_cast<uint32_t>(p.nstg);
+    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+      for (int kc = 0; kc < KC; ++kc)
+        for (int sub = 0; sub < nsub; ++sub, ++u) {
+          const uint32_t ss = u % C::NS, sg = u % nstg;
+          SNN_TWAIT(&stg_full[sg], (u / nstg) & 1, 0);
+          SNN_TWAIT(&s_empty[ss], ((u / C::NS) & 1) ^ 1, 1);
+          if (elect_one()) {
+            const uint32_t bytes = static_cast<uint32_t>(min(256, p.TB - sub * 256) * 128);
+            mbar_expect_tx(&s_full[ss], bytes);
+            bulk_s2s(s_ring + ss * S_STAGE, staging + sg * S_STAGE, bytes, &s_full[ss]);
+          }
+          __syncwarp();
+        }
+    }
   } else if (IS_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 B sub-tile)
     // The four warps expand every sub-tile together (sample-step r = thread, thread + 128; one 128-byte swizzled row
-    // = 64 contraction elements per sample-step) into a STAGING buffer; one thread then moves it into the operand
-    // slot with a shared->shared bulk copy.  Both hops are the canonical cross-proxy patterns: generic stores ->
+    // = 64 contraction elements per sample-step) into a STAGING buffer; warp 3 then moves it into the operand slot
+    // with a shared->shared bulk copy.  Both hops are the canonical cross-proxy patterns: generic stores ->
     // fence.proxy.async -> bulk-copy read (as for every TMA store), and bulk-copy write -> mbarrier -> tcgen05.mma
-    // read (as for the weights).  Writing the operand slot directly with st.shared was NOT reliable: with the MMA
-    // pipe busy the tensor core now and then read stale 16-byte pieces (run-to-run differences at B = 24576,
-    // rate dependent on the slot's address) although the writers fenced, and although a read-back saw the new data.
+    // read (as for the weights).  Writing the operand slot directly with st.shared was NOT reliable for this
+    // K-major B operand: the tensor core now and then read stale 16-byte pieces (run-to-run differences at
+    // B = 24576, at a rate that depended on the slot's shared-memory address) although every writer fenced and a
+    // generic read-back saw the new data; see DESIGN.md.
     const int et = tid - 384;
+    const uint32_t nstg = static_cast<uint32_t>(p.nstg);
     uint32_t u = 0;
     for (int tile = tile0; tile < p.ntile; tile += tstep) {
       for (int kc = 0; kc < KC; ++kc)
@@ -461,15 +510,15 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&bits_empty[s]);
-          // the staging buffer is free once the previous unit's copy has completed (= its s_full phase)
-          if (u > 0) SNN_TWAIT(&s_full[(u - 1) % C::NS], ((u - 1) / C::NS) & 1, 1);
+          // staging buffer u % nstg is free once the copy of unit u - nstg has completed (= that unit's s_full phase)
+          if (u >= nstg) SNN_TWAIT(&s_full[(u - nstg) % C::NS], ((u - nstg) / C::NS) & 1, 1);
           if (!(p.dbg & 4)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int r = et + 128 * h;
               if (r < ncols) {
                 const int sw = r & 7;
-                uint8_t* dst = staging + (r >> 3) * 1024 + sw * 128;
+                uint8_t* dst = staging + (u % nstg) * S_STAGE + (r >> 3) * 1024 + sw * 128;
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
                   const uint32_t byte = ((c8 < 4 ? w0[h] : w1[h]) >> ((c8 & 3) * 8)) & 0xFFu;
@@ -479,14 +528,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             }
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");       // all four expander warps have written and fenced
-          if (et == 0) {
-            const uint32_t ss = u % C::NS;
-            SNN_TWAIT(&s_empty[ss], ((u / C::NS) & 1) ^ 1, 2);
-            mbar_expect_tx(&s_full[ss], static_cast<uint32_t>(ncols * 128));
-            bulk_s2s(s_ring + ss * C::S_STAGE, staging, static_cast<uint32_t>(ncols * 128), &s_full[ss]);
-          }
           __syncwarp();
+          if (lane == 0) mbar_arrive(&stg_full[u % nstg]);
         }
     }
   }

@@ -19,6 +19,28 @@ __global__ void __launch_bounds__(128, 1) s2s_kernel(uint32_t* out) {
     bulk_s2s(dst, src, 30720u, &bar);
   }
   mbar_wait(&bar, 0);
+  // timing: one 30 KiB copy vs the same bytes as 8 / 30 smaller copies issued back to back
+  __shared__ long long cyc[4];
+  if (threadIdx.x == 0) {
+    const int splits[3] = {1, 8, 30};
+    uint32_t ph = 1;
+    for (int v = 0; v < 3; ++v) {
+      const int n = splits[v];
+      const uint32_t each = 30720u / n;
+      long long best = 1 << 30;
+      for (int rep = 0; rep < 5; ++rep, ph ^= 1) {
+        const long long t0 = clock64();
+        mbar_expect_tx(&bar, 30720u);
+        for (int i = 0; i < n; ++i) bulk_s2s(reinterpret_cast<uint8_t*>(dst) + i * each, reinterpret_cast<uint8_t*>(src) + i * each, each, &bar);
+        mbar_wait(&bar, ph);
+        const long long dt = clock64() - t0;
+        best = dt < best ? dt : best;
+      }
+      cyc[v] = best;
+    }
+    if (blockIdx.x == 0) printf("30 KiB shared->shared: 1 copy %lld cyc, 8 copies %lld cyc, 30 copies %lld cyc\n", cyc[0], cyc[1], cyc[2]);
+  }
+  __syncthreads();
   uint32_t bad = 0;
   for (int i = threadIdx.x; i < 7680; i += blockDim.x) bad += dst[i] != src[i];
   atomicAdd(out, bad);
