@@ -2,12 +2,11 @@
 // (the "dW += g_c^T x_t" line of SURVEY.md §8a, i.e. what autograd's mm-backward of nn.Linear does
 // for AMP/.../modules/actor_critic.py:228 summed over the T spike steps).
 //
-// The contraction runs over sample-steps r:
-//   A = g_c hi/lo bf16 planes.  Actor layers: read straight from the n-major image (rows = n = MMA-M, 128 bytes =
-//       64 sample-steps = MMA-K: a K-major operand, ONE 16 KiB bulk copy per plane and 64 sample-steps); dense
-//       critic layers: swz64 image with rows = r (MN-major operand),
+// The contraction runs over batch rows, so both operands are MN-major for the tensor core:
+//   A = g_c hi/lo bf16 planes, read straight from their swz64 images (rows = r = MMA-K,
+//       cols = n = MMA-M) with 1-D bulk copies,
 //   B = input spikes x (exact in bf16), expanded in shared memory from the bit-packed trace
-//       (rows = r = MMA-K, cols = k = MMA-N: MN-major), or hi/lo planes of a dense input.
+//       (rows = r = MMA-K, cols = k = MMA-N).
 // One CTA owns one [128 x <=256] fp32 output tile in TMEM and a contiguous slice of r (split-K over
 // the batch); partial tiles go to a workspace and are summed by reduce_partials_kernel — a fixed
 // order, so gradients are bit-reproducible run to run.
@@ -27,7 +26,7 @@
 namespace snn {
 
 struct DwGemmParams {
-  const uint8_t* g_img;    // 2 planes; sparse: n-major image [R/64][NP/8][8][128 B], dense: swz64 image [NP/64][R rows]
+  const uint8_t* g_img;    // 2 planes, swz64 image [NP/64][R rows]
   size_t g_plane;
   const uint32_t* x_bits;  // [KP/32][R]           (spiking layers: binary input, expanded in shared memory)
   const uint8_t* x_img;    // 2 planes, swz64 image [KP/64][R rows]   (dense layers: real-valued input)
@@ -111,18 +110,11 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
                        p.x_img + pl * p.x_plane + (static_cast<size_t>(kc0 + kcl) * p.R + static_cast<size_t>(rb) * 64) * 128,
                        8192u, &full[s]);
         }
-        if (DENSE) {
-          for (int pl = 0; pl < 2; ++pl)
-            for (int nc = 0; nc < 2; ++nc)
-              bulk_g2s(dst + pl * 16384 + nc * 8192,
-                       p.g_img + pl * p.g_plane + (static_cast<size_t>(mt * 2 + nc) * p.R + static_cast<size_t>(rb) * 64) * 128,
-                       8192u, &full[s]);
-        } else {
-          for (int pl = 0; pl < 2; ++pl)
-            bulk_g2s(dst + pl * 16384,
-                     p.g_img + pl * p.g_plane + (static_cast<size_t>(rb) * (p.NP >> 3) + static_cast<size_t>(mt) * 16) * 1024,
-                     16384u, &full[s]);
-        }
+        for (int pl = 0; pl < 2; ++pl)
+          for (int nc = 0; nc < 2; ++nc)
+            bulk_g2s(dst + pl * 16384 + nc * 8192,
+                     p.g_img + pl * p.g_plane + (static_cast<size_t>(mt * 2 + nc) * p.R + static_cast<size_t>(rb) * 64) * 128,
+                     8192u, &full[s]);
       }
       __syncwarp();
     }
@@ -143,10 +135,9 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform loop, one elected lane issues
-    const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), DENSE ? 1 : 0, 1);
+    const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(nck * 64), 1, 1);
     const uint32_t dhi = smem_desc_hi(1024);
     const uint32_t ring_lo = smem_desc_lo(smem_u32(ring), 8192);
-    const uint32_t ring_lo_k = smem_desc_lo(smem_u32(ring), 16);       // K-major A operand (sparse path)
     uint32_t i = 0;
     for (int rb = rb0; rb < rb1; ++rb, ++i) {
       const uint32_t s = i % kStages;
@@ -167,8 +158,8 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
           } else {
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl)
-              umma_bf16_lohi(tmem_base, ring_lo_k + s * (kStageBytes >> 4) + pl * (16384 >> 4) + k16 * 2, dhi,
-                             b_lo + k16 * (2048 >> 4), dhi, idesc, (i > 0 || k16 > 0 || pl > 0) ? 1u : 0u);
+              umma_bf16_lohi(tmem_base, a_lo + pl * (16384 >> 4) + k16 * (2048 >> 4), dhi, b_lo + k16 * (2048 >> 4), dhi, idesc,
+                             (i > 0 || k16 > 0 || pl > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty[s]);

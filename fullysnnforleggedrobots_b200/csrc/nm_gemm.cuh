@@ -14,10 +14,10 @@
 //              Epilogue = LIF update (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b);
 //              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of __ballot_sync (lane = neuron); emits the
 //              fp32 voltage trace when training.
-//   NM_DX      A = hi/lo planes of W^T (K-major), B = hi/lo planes of g_c of the layer above (n-major image =
-//              MN-major operand); three products hi*hi + hi*lo + lo*hi.  Epilogue = BPTT recurrence of
+//   NM_DX      A = hi/lo planes of W^T (K-major), B = hi/lo planes of g_c of the layer above (swz64 image with rows =
+//              sample-steps: K-major, one bulk copy per plane); three products hi*hi + lo*hi + hi*lo.  Epilogue = BPTT recurrence of
 //              SURVEY.md §8a for the layer below (surrogate gradient of PseudoSpikeRect, actor_critic.py:154-167).
-//              Emits g_c planes (n-major image) and the bias gradient (a per-thread sum: no shuffles, no atomics).
+//              Emits g_c planes (swz64 image) and the bias gradient (a per-thread sum: no shuffles, no atomics).
 //   NM_DX_ENC  same GEMM into the encoder neurons; epilogue = straight-through encoder recurrence
 //              (actor_critic.py:50-59,116-119): Gamma_t = g_t + 0.001 Gamma_{t+1}; emits g_a = sum_t Gamma_t.
 //
@@ -59,15 +59,15 @@ struct NmParams {
   int a_planes;             // FWD: 1..3
   // B operand
   const uint32_t* b_bits;   // FWD: spike words [KP/32][Rt]
-  const uint8_t* b_img;     // DX: 2 planes of the n-major image [Rt/64][KP/8][8][128 B]
+  const uint8_t* b_img;     // DX: 2 planes of the swz64 image [KP/64][Rt rows][128 B] of g_c (rows = sample-steps)
   size_t b_plane;
   // FWD epilogue
   const float* bias;        // [MP]
   uint32_t* out_bits;       // [MP/32][Rt]
-  float* v_out;             // [Rt/16][MP][16] or null (inference)
+  float* v_out;             // [Rt][MP] or null (inference)
   // DX epilogue
-  const float* v_in;        // [Rt/16][MP][16] voltages of the layer whose gradient is produced
-  uint8_t* g_img;           // 2 planes of the n-major image [Rt/64][MP/8][8][128 B]
+  const float* v_in;        // [Rt][MP] voltages of the layer whose gradient is produced
+  uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
   float* db_part;           // [2 * gridDim.x / nmt][MP]
   // DX_ENC epilogue
@@ -84,7 +84,8 @@ template <int MODE> struct NmCfg;
 template <> struct NmCfg<NM_FWD> {
   static constexpr int NW = 2, W_STAGE = 49152, NS = 2, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
 };
-// DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (half a 64-neuron chunk: 2 planes x <= 4 panels x 4 KiB)
+// DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
+// <= 256 sample-steps x 128 B)
 template <> struct NmCfg<NM_DX> {
   static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 384;
 };
@@ -189,21 +190,18 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         }
         __syncwarp();
         if (!IS_FWD) {
-          // g_c units of this 64-neuron chunk: (half chunk) x (sub-tile); panel = 64 sample-steps x 32 neurons = 4 KiB
-          for (int half = 0; half < 2; ++half)
+          // g_c units of this 64-neuron chunk: (plane) x (sub-tile), each one contiguous run of rows of the image
+          for (int pl = 0; pl < 2; ++pl)
             for (int sub = 0; sub < nsub; ++sub, ++u) {
               const uint32_t gs = u % C::NS;
               SNN_TWAIT(&s_empty[gs], ((u / C::NS) & 1) ^ 1, 1);
               if (elect_one()) {
-                const int ncols = min(256, p.TB - sub * 256);
-                const int npan = (ncols + 63) >> 6;
-                mbar_expect_tx(&s_full[gs], static_cast<uint32_t>(2 * npan * 4096));
-                const size_t pan0 = static_cast<size_t>(tile) * (p.CT >> 6) + static_cast<size_t>(sub) * 4;
-                for (int pl = 0; pl < 2; ++pl)
-                  for (int pan = 0; pan < npan; ++pan)
-                    bulk_g2s(s_ring + gs * S_STAGE + pl * 16384 + pan * 4096,
-                             p.b_img + pl * p.b_plane + ((pan0 + pan) * (p.KP >> 3) + static_cast<size_t>(kc) * 8 + half * 4) * 1024,
-                             4096u, &s_full[gs]);
+                const uint32_t bytes = static_cast<uint32_t>(min(256, p.TB - sub * 256) * 128);
+                mbar_expect_tx(&s_full[gs], bytes);
+                bulk_g2s(s_ring + gs * S_STAGE,
+                         p.b_img + pl * p.b_plane +
+                             (static_cast<size_t>(kc) * p.Rt + static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256) * 128,
+                         bytes, &s_full[gs]);
               }
               __syncwarp();
             }
@@ -235,7 +233,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     uint32_t iw = 0, u = 0, it = 0;
     const uint32_t dhi = smem_desc_hi(1024);
     const uint32_t w_ring_lo = smem_desc_lo(smem_u32(w_ring), 16);
-    const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), IS_FWD ? 16 : 4096);   // DX: LBO = 4 KiB between panels
+    const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), 16);
     for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
       const uint32_t aset = it % nsets;
       SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
@@ -244,7 +242,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         const uint32_t ws = iw % C::NW;
         SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
         const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
-        for (int half = 0; half < (IS_FWD ? 1 : 2); ++half)
+        for (int pl = 0; pl < (IS_FWD ? 1 : 2); ++pl)          // DX: g_c plane of the unit
           for (int sub = 0; sub < nsub; ++sub, ++u) {
             const uint32_t ss = u % C::NS;
             SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
@@ -264,21 +262,19 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                     acc = 1u;
                   }
               } else {
-                // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + hi*lo + lo*hi (lo*lo < 2^-16 relative)
-                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 1);
-                uint32_t acc = (kc > 0 || half > 0) ? 1u : 0u;
+                // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + lo*hi on the g_c hi plane, then hi*lo on its lo plane
+                // (lo*lo < 2^-16 relative)
+                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
+                uint32_t acc = (kc > 0 || pl > 0) ? 1u : 0u;
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16)
-#pragma unroll
-                  for (int pr = 0; pr < 3; ++pr) {
-                    const uint32_t pa = pr == 2 ? 1 : 0, pb = pr == 1 ? 1 : 0;
-                    umma_bf16_lohi(d, a_lo + pa * (16384 >> 4) + (half * 2 + k16) * 2, dhi,
-                                   b_lo + pb * (16384 >> 4) + k16 * (2048 >> 4), dhi, idesc, acc);
-                    acc = 1u;
-                  }
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
+                  acc = 1u;
+                  if (pl == 0) umma_bf16_lohi(d, a_lo + (16384 >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, 1u);
+                }
               }
               umma_commit(&s_empty[ss]);
-              if (half == (IS_FWD ? 0 : 1) && sub == nsub - 1) {
+              if (pl == (IS_FWD ? 0 : 1) && sub == nsub - 1) {
                 umma_commit(&w_empty[ws]);
                 if (kc == KC - 1) umma_commit(&acc_full[aset]);
               }
@@ -303,13 +299,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       if (nsets == 2 && aset != static_cast<uint32_t>(grp)) continue;
       const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
       const int b_tile = tile * p.Bt;
-      if (MODE == NM_DX) {
-        // the scan below reads this neuron's voltages (64 B per (t, group)) from the HBM-resident trace: pull them
-        // into L2 while the tensor core is still busy with this item's MMAs
+      if (MODE == NM_DX && lane < 16) {
+        // the scan below reads this warp's voltages (128 B per sample-step) from the HBM-resident trace: pull them
+        // into L2 while the tensor core is still busy with this item's MMAs (lane = sample-step within the group)
         for (int bg = bg0; bg < nbg; bg += bgstep)
           for (int t = 0; t < p.T; ++t)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                p.v_in + (((c_tile + static_cast<size_t>(t * p.Bt + bg * 16)) >> 4) * p.MP + n) * 16));
+                p.v_in + (c_tile + static_cast<size_t>(t * p.Bt + bg * 16 + lane)) * p.MP + (n - lane)));
       }
       SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
@@ -320,19 +316,20 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         // recurrence (two epilogue warps per scheduler cannot hide that latency by themselves)
         const int nb = (nbg - bg0 + bgstep - 1) / bgstep;
         const int nsteps = (p.dbg & 2) ? 0 : nb * p.T;
-        uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
-        const int sw = n & 7;
+        // g_c image [MP/64][Rt rows][128 B]: this thread's neuron is bf16 column n % 64 of chunk n / 64; a warp's 32
+        // neurons are 64 contiguous bytes of a row, so every store below is one coalesced 64-byte request
+        uint8_t* const gcol = p.g_img + static_cast<size_t>(n >> 6) * p.Rt * 128 + (n & 7) * 2;
+        const int cn = (n & 63) >> 3;
         float gvn[16], gcn[16];
-        auto loadv = [&](int sidx, float4 (&buf)[4]) {
+        auto loadv = [&](int sidx, float (&buf)[16]) {
           if (sidx < nsteps) {
             const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
-            const float4* src = reinterpret_cast<const float4*>(
-                p.v_in + (((c_tile + static_cast<size_t>(t * p.Bt + (bg0 + bi * bgstep) * 16)) >> 4) * p.MP + n) * 16);
+            const float* src = p.v_in + (c_tile + static_cast<size_t>(t * p.Bt + (bg0 + bi * bgstep) * 16)) * p.MP + n;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) buf[j] = __ldg(src + j);
+            for (int j = 0; j < 16; ++j) buf[j] = __ldg(src + static_cast<size_t>(j) * p.MP);
           }
         };
-        auto step = [&](int sidx, const float4 (&buf)[4]) {
+        auto step = [&](int sidx, const float (&v)[16]) {
           const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
           const int col0 = (bg0 + bi * bgstep) * 16;
           const int nlive = p.B - (b_tile + col0);
@@ -343,10 +340,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           }
           uint32_t x[16];
           tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
-          const float v[16] = {buf[0].x, buf[0].y, buf[0].z, buf[0].w, buf[1].x, buf[1].y, buf[1].z, buf[1].w,
-                               buf[2].x, buf[2].y, buf[2].z, buf[2].w, buf[3].x, buf[3].y, buf[3].z, buf[3].w};
           tmem_ld_wait();
-          float hi[16], lo[16];
+          const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);          // % 16 == 0
+          uint8_t* const dst = gcol + (c >> 3) * 1024;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const bool live = (vmask >> j) & 1u;
@@ -360,22 +356,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             gvn[j] = gv;
             gcn[j] = gc;
             dbsum += gc;
-            hi[j] = bf16_round(gc);
-            lo[j] = gc - hi[j];
+            const float hi = bf16_round(gc);
+            uint8_t* q = dst + (j >> 3) * 1024 + (j & 7) * 128 + ((cn ^ (j & 7)) << 4);
+            *reinterpret_cast<uint16_t*>(q) = static_cast<uint16_t>(__float_as_uint(hi) >> 16);
+            *reinterpret_cast<uint16_t*>(q + p.g_plane) = static_cast<uint16_t>(__float_as_uint(bf16_round(gc - hi)) >> 16);
           }
-          const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
-          uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7);      // panel stride = MP / 8 * 1024
-          const int p0 = static_cast<int>((c & 63) >> 3);
-          const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-          const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-          const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-          const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
-          *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) = h0;
-          *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) = h1;
-          *reinterpret_cast<uint4*>(dst + p.g_plane + ((p0 ^ sw) << 4)) = l0;
-          *reinterpret_cast<uint4*>(dst + p.g_plane + (((p0 + 1) ^ sw) << 4)) = l1;
         };
-        float4 vb0[4], vb1[4], vb2[4];
+        float vb0[16], vb1[16], vb2[16];
         loadv(0, vb0); loadv(1, vb1); loadv(2, vb2);
         for (int sidx = 0; sidx < nsteps; sidx += 3) {
           step(sidx, vb0);
@@ -416,9 +403,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             if (lane < 16)
               p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
             if (p.v_out != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.v_out + ((c >> 4) * p.MP + n) * 16);
+              float* dst = p.v_out + c * p.MP + n;               // [sample-step][neuron]: a warp stores 128 contiguous bytes
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
+              for (int j = 0; j < 16; ++j) dst[static_cast<size_t>(j) * p.MP] = vol[j];
             }
             sprev = scur;
             tmem_ld_wait();
@@ -450,12 +437,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       }
       if (MODE == NM_DX && (nsets == 2 || grp == 0)) {
         // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
-        uint8_t* const grow = p.g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
-        for (int cc = p.TB; cc < p.CT; cc += 8) {
-          const size_t c = c_tile + cc;
-          uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(p.MP) << 7) + (((static_cast<int>(c & 63) >> 3) ^ (n & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(dst + p.g_plane) = make_uint4(0u, 0u, 0u, 0u);
+        uint8_t* const gcol = p.g_img + static_cast<size_t>(n >> 6) * p.Rt * 128 + (n & 7) * 2;
+        const int cn = (n & 63) >> 3;
+        for (int cc = p.TB; cc < p.CT; ++cc) {
+          const size_t r = c_tile + cc;
+          uint8_t* q = gcol + (r >> 3) * 1024 + (r & 7) * 128 + ((cn ^ static_cast<int>(r & 7)) << 4);
+          *reinterpret_cast<uint16_t*>(q) = 0;
+          *reinterpret_cast<uint16_t*>(q + p.g_plane) = 0;
         }
       }
       tc_fence_before_sync();

@@ -13,9 +13,10 @@
 //     One tile's T * Bt sample-steps are therefore contiguous: they are the N dimension of ONE tcgen05.mma
 //     (N = 240 for T = 5), which is what lets the scan-GEMMs run at the tensor core's full rate
 //     (tools/mma_rate.cu: an M = 128 MMA costs max(N / 2, 57 + N / 8) cycles).
-//   * "n-major image" of a time-stepped bf16 matrix G[r][n]: [Rt/64][NP/8][8 neurons][128 bytes = 64
-//     sample-steps], 16-byte pieces XOR-permuted by (n % 8) — MN-major B operand of dX, K-major A operand of dW.
-//   * voltages: fp32 [Rt/16][NP][16 sample-steps].
+//   * g_c (time-stepped bf16 hi/lo planes): swz64 image with rows = sample-steps r, columns = neurons — the K-major
+//     B operand of dX and the MN-major A operand of dW; the epilogue threads (= neurons) of a warp store 64
+//     contiguous bytes of one row.
+//   * voltages: fp32 [Rt][NP] (a warp = 32 consecutive neurons of one sample-step = 128 contiguous bytes).
 //   * the dense critic keeps plain rows r = b, Bpad = roundup(B, 128).
 #pragma once
 #include <cstddef>
@@ -48,7 +49,7 @@ struct LayerPlan {
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
   size_t tr_bits;    // trace: output spike words [NP/32][Rt]
-  size_t tr_volt;    // trace: fp32 voltages [Rt/16][NP][16]
+  size_t tr_volt;    // trace: fp32 voltages [Rt][NP]
 };
 
 struct SnnPlan {
@@ -67,7 +68,7 @@ struct SnnPlan {
   size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][Rt]
   size_t trace_bytes;
   // backward workspace
-  size_t ws_g[2];           // two ping-pong G buffers (n-major images, 2 planes each)
+  size_t ws_g[2];           // two ping-pong g_c buffers (swz64 images [NP/64][Rt rows], 2 planes each)
   size_t ws_g_plane[2];
   size_t ws_ga;             // fp32 [Bcap/16][K0P][16]  d loss / d pop_act
   size_t ws_partial, ws_partial_stride;   // fp32 split-K partials of dW, one region per layer

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
 // ------------------------------------------------------------------ BPTT of the output population layer
 // g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the
 // recurrence of SURVEY.md §8a.  Same orientation as the dX epilogue (nm_gemm.cuh): thread = neuron, 16 samples x T
-// steps in registers; writes the g_c hi/lo planes (n-major image) and per-tile partials of the bias gradient and of
+// steps in registers; writes the g_c hi/lo planes (swz64 image, rows = sample-steps) and per-tile partials of the bias gradient and of
 // the decoder gradients:  dec_part[tile][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
 // dec_part[tile][1][n] = sum_b G[b,a(n)]  (d bias, read at n = a * P).
 __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
                                                       int NP, int T, uint8_t* __restrict__ g_img, size_t g_plane,
                                                       float* __restrict__ db_part /* [ntile][NP] */,
                                                       float* __restrict__ dec_part /* [ntile][2][NP] */) {
-  // grid (ntile, NP / 128); a warp reads 32 neurons x 64 B = one contiguous 2 KiB run of the voltage trace per (t, group)
+  // grid (ntile, NP / 128); a warp reads / writes 32 consecutive neurons of one sample-step per request
   const int tile = blockIdx.x;
   const int n = blockIdx.y * 128 + threadIdx.x;
   const bool n_live = n < A * P;
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
   const float Tf = static_cast<float>(T);
   const size_t c_tile = static_cast<size_t>(tile) * tg.CT;
   const int TB = T * tg.Bt;
-  uint8_t* const grow = g_img + static_cast<size_t>(n >> 3) * 1024 + (n & 7) * 128;
-  const int sw = n & 7;
-  const size_t vstep = (static_cast<size_t>(tg.Bt) >> 4) * NP * 16;
+  uint8_t* const gcol = g_img + static_cast<size_t>(n >> 6) * tg.Rt * 128 + (n & 7) * 2;     // see nm_gemm.cuh (dX epilogue)
+  const int cn = (n & 63) >> 3;
+  const size_t vstep = static_cast<size_t>(tg.Bt) * NP;                                      // floats between timesteps
   float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
   for (int bg = 0; bg < (tg.Bt >> 4); ++bg) {
     const int col0 = bg * 16;
@@ -234,20 +234,21 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
         gup[j] = __fdiv_rn(G * wn, Tf);
       }
     }
-    const float* vbase = volt + (((c_tile + col0) >> 4) * NP + n) * 16;
-    // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's load in flight
-    float4 vn[4];
+    const float* vbase = volt + (c_tile + col0) * NP + n;
+    // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's loads in flight
+    float vn[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(T - 1) * vstep) + j);
+    for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + static_cast<size_t>(j) * NP);
     for (int t = T - 1; t >= 0; --t) {
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[4 * j] = vn[j].x; v[4 * j + 1] = vn[j].y; v[4 * j + 2] = vn[j].z; v[4 * j + 3] = vn[j].w; }
+      for (int j = 0; j < 16; ++j) v[j] = vn[j];
       if (t > 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) vn[j] = __ldg(reinterpret_cast<const float4*>(vbase + static_cast<size_t>(t - 1) * vstep) + j);
+        for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + static_cast<size_t>(j) * NP);
       }
-      float hi[16], lo[16];
+      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);
+      uint8_t* const dst = gcol + (c >> 3) * 1024;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const bool live = b0 + j < B;
@@ -260,20 +261,11 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
         const float gc = gv + 0.5f * gcn[j];
         gvn[j] = gv; gcn[j] = gc;
         dbsum += gc;
-        hi[j] = bf16_round(gc);
-        lo[j] = gc - hi[j];
+        const float hi = bf16_round(gc);
+        uint8_t* q = dst + (j >> 3) * 1024 + (j & 7) * 128 + ((cn ^ (j & 7)) << 4);
+        *reinterpret_cast<uint16_t*>(q) = static_cast<uint16_t>(__float_as_uint(hi) >> 16);
+        *reinterpret_cast<uint16_t*>(q + g_plane) = static_cast<uint16_t>(__float_as_uint(bf16_round(gc - hi)) >> 16);
       }
-      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);
-      uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(NP) << 7);
-      const int p0 = static_cast<int>((c & 63) >> 3);
-      *reinterpret_cast<uint4*>(dst + ((p0 ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(dst + (((p0 + 1) ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-      *reinterpret_cast<uint4*>(dst + g_plane + ((p0 ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-      *reinterpret_cast<uint4*>(dst + g_plane + (((p0 + 1) ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -282,11 +274,11 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
     }
   }
   // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
-  for (int cc = TB; cc < tg.CT; cc += 8) {
-    const size_t c = c_tile + cc;
-    uint8_t* dst = grow + (c >> 6) * (static_cast<size_t>(NP) << 7) + (((static_cast<int>(c & 63) >> 3) ^ sw) << 4);
-    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(dst + g_plane) = make_uint4(0u, 0u, 0u, 0u);
+  for (int cc = TB; cc < tg.CT; ++cc) {
+    const size_t r = c_tile + cc;
+    uint8_t* q = gcol + (r >> 3) * 1024 + (r & 7) * 128 + ((cn ^ static_cast<int>(r & 7)) << 4);
+    *reinterpret_cast<uint16_t*>(q) = 0;
+    *reinterpret_cast<uint16_t*>(q + g_plane) = 0;
   }
   db_part[static_cast<size_t>(tile) * NP + n] = dbsum;
   dec_part[(static_cast<size_t>(tile) * 2) * NP + n] = dwd;

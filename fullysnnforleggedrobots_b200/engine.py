@@ -184,10 +184,9 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace layout: [Rt / 16][NP][16 sample-steps]
-            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(Rt // 16, NP, 16)
-            v = v.permute(1, 0, 2).reshape(NP, Rt)
-            res["volt"].append(v[:, col].permute(1, 2, 0)[:, :B, :self.dims[l + 1]].contiguous())
+            # voltage trace layout: [Rt sample-steps][NP]
+            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(Rt, NP)
+            res["volt"].append(v[col][:, :B, :self.dims[l + 1]].contiguous())
         return res
 
 

@@ -35,8 +35,9 @@ step()
 torch.cuda.synchronize()
 L.snn_debug_set_cycle_buffer(None)
 d = buf.cpu().view(16, 148, 4, 4).double()
-names = {0: ("producer", ["empty_b", "empty_bits/a", "-"]), 1: ("mma", ["acc_empty", "full_b", "full_a"]),
-         2: ("epilogue", ["acc_full", "-", "-"]), 3: ("expander", ["full_bits", "empty_a", "-"])}
+# wait sites of nm_gemm.cuh (fwd / dx) — the dW kernel reuses the same slots with its own meaning (dw_gemm.cuh)
+names = {0: ("producer", ["w_empty", "g_empty(dx)", "-"]), 1: ("mma", ["acc_empty", "w_full", "s_full"]),
+         2: ("epilogue", ["acc_full", "-", "-"]), 3: ("expander", ["bits_full", "staging_free", "-"])}
 print(f"SNN_DBG={os.environ.get('SNN_DBG', '0')}  (mean over CTAs, kilo-cycles)")
 for slot in range(16):
     x = d[slot]
