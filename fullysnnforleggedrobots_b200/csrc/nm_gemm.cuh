@@ -64,9 +64,9 @@ struct NmParams {
   // FWD epilogue
   const float* bias;        // [MP]
   uint32_t* out_bits;       // [MP/32][Rt]
-  float* v_out;             // [Rt][MP] or null (inference)
+  float* v_out;             // [MP/32][Rt][32] or null (inference)
   // DX epilogue
-  const float* v_in;        // [Rt][MP] voltages of the layer whose gradient is produced
+  const float* v_in;        // [MP/32][Rt][32] voltages of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
   float* db_part;           // [2 * gridDim.x / nmt][MP]
@@ -74,7 +74,8 @@ struct NmParams {
   float* g_a;               // [Bcap/16][MP][16]
   int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
   int nstg;                 // FWD: staging buffers (1 or 2)
-  int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand
+  int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
+                            // 16 = dX: no g_c stores, 32 = dX: no voltage loads
   unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
 };
 
@@ -305,70 +306,85 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         for (int bg = bg0; bg < nbg; bg += bgstep)
           for (int t = 0; t < p.T; ++t)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                p.v_in + (c_tile + static_cast<size_t>(t * p.Bt + bg * 16 + lane)) * p.MP + (n - lane)));
+                p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile + static_cast<size_t>(t * p.Bt + bg * 16 + lane)) * 32));
       }
       SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
       const uint32_t t_set = t_lane + aset * 256;
       if (MODE == NM_DX) {
-        // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the fp32 voltages of a step are 64 B
-        // per thread straight from the HBM/L2-resident trace (~1 us away), so the loads run THREE steps ahead of the
-        // recurrence (two epilogue warps per scheduler cannot hide that latency by themselves)
+        // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the loads of a step's fp32 voltages
+        // (one coalesced 128-byte row per sample-step and warp) run THREE steps ahead of the recurrence.
+        // No validity masks: samples >= B have g_c == 0 in the layer above (the top scan writes zeros there), so
+        // their accumulators are exactly 0, and with the zero initial state every g_c written here is 0 again.
         const int nb = (nbg - bg0 + bgstep - 1) / bgstep;
         const int nsteps = (p.dbg & 2) ? 0 : nb * p.T;
         // g_c image [MP/64][Rt rows][128 B]: this thread's neuron is bf16 column n % 64 of chunk n / 64; a warp's 32
-        // neurons are 64 contiguous bytes of a row, so every store below is one coalesced 64-byte request
-        uint8_t* const gcol = p.g_img + static_cast<size_t>(n >> 6) * p.Rt * 128 + (n & 7) * 2;
-        const int cn = (n & 63) >> 3;
-        float gvn[16], gcn[16];
-        auto loadv = [&](int sidx, float (&buf)[16]) {
-          if (sidx < nsteps) {
-            const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
-            const float* src = p.v_in + (c_tile + static_cast<size_t>(t * p.Bt + (bg0 + bi * bgstep) * 16)) * p.MP + n;
+        // neurons are 64 contiguous bytes of a row, so every store below is one coalesced 64-byte request.
+        // xo[jj]: byte offset of this neuron inside row (8 i + jj) of an 8-row group (128B swizzle: piece ^= row % 8)
+        uint8_t* const gcol = p.g_img + static_cast<size_t>(n >> 6) * p.Rt * 128;
+        uint32_t xo[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) buf[j] = __ldg(src + static_cast<size_t>(j) * p.MP);
+        for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
+        const float* const vcol = p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32 + lane;
+        float gvn[16], gcn[16];
+        // step s <-> (group index bi, timestep t): s = bi * T + (T - 1 - t); tracked incrementally (no divisions)
+        int l_bi = 0, l_t = p.T - 1;          // cursor of the loads
+        int s_bi = 0, s_t = p.T - 1;          // cursor of the recurrence
+        auto loadv = [&](float (&buf)[16]) {
+          if (l_bi < nb && !(p.dbg & 32)) {
+            const float* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 32;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) buf[j] = __ldg(src + j * 32);
           }
+          if (--l_t < 0) { l_t = p.T - 1; ++l_bi; }
         };
-        auto step = [&](int sidx, const float (&v)[16]) {
-          const int bi = sidx / p.T, t = p.T - 1 - (sidx - bi * p.T);
-          const int col0 = (bg0 + bi * bgstep) * 16;
-          const int nlive = p.B - (b_tile + col0);
-          const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
-          if (t == p.T - 1) {
+        auto step = [&](const float (&v)[16]) {
+          const int col0 = (bg0 + s_bi * bgstep) * 16;
+          if (s_t == p.T - 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
           }
           uint32_t x[16];
-          tmem_ld16(t_set + static_cast<uint32_t>(t * p.Bt + col0), x);
+          tmem_ld16(t_set + static_cast<uint32_t>(s_t * p.Bt + col0), x);
           tmem_ld_wait();
-          const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);          // % 16 == 0
+          const size_t c = c_tile + static_cast<size_t>(s_t * p.Bt + col0);          // % 16 == 0
           uint8_t* const dst = gcol + (c >> 3) * 1024;
+          float gc[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const bool live = (vmask >> j) & 1u;
-            const float gup = live ? __uint_as_float(x[j]) : 0.f;
-            const float vj = live ? v[j] : 0.f;
-            const float gs = gup - gvn[j] * (0.75f * vj);
+            const float vj = v[j];
+            const float gs = __uint_as_float(x[j]) - gvn[j] * (0.75f * vj);
             const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
             const float keep = vj > 0.5f ? 0.f : 0.75f;
             const float gv = gs * win + gvn[j] * keep;
-            const float gc = gv + 0.5f * gcn[j];
+            gc[j] = gv + 0.5f * gcn[j];
             gvn[j] = gv;
-            gcn[j] = gc;
-            dbsum += gc;
-            const float hi = bf16_round(gc);
-            uint8_t* q = dst + (j >> 3) * 1024 + (j & 7) * 128 + ((cn ^ (j & 7)) << 4);
-            *reinterpret_cast<uint16_t*>(q) = static_cast<uint16_t>(__float_as_uint(hi) >> 16);
-            *reinterpret_cast<uint16_t*>(q + p.g_plane) = static_cast<uint16_t>(__float_as_uint(bf16_round(gc - hi)) >> 16);
+            gcn[j] = gc[j];
+            dbsum += gc[j];
           }
+          if (!(p.dbg & 16)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              // packed conversions: two sample-steps per cvt; hi = bf16(g_c), lo = bf16(g_c - hi)
+              const uint32_t hp = pack_bf16x2(gc[j], gc[j + 1]);
+              const uint32_t lp = pack_bf16x2(gc[j] - __uint_as_float(hp << 16), gc[j + 1] - __uint_as_float(hp & 0xFFFF0000u));
+              uint8_t* q0 = dst + (j >> 3) * 1024 + xo[j & 7];
+              uint8_t* q1 = dst + (j >> 3) * 1024 + xo[(j + 1) & 7];
+              *reinterpret_cast<uint16_t*>(q0) = static_cast<uint16_t>(hp);
+              *reinterpret_cast<uint16_t*>(q1) = static_cast<uint16_t>(hp >> 16);
+              *reinterpret_cast<uint16_t*>(q0 + p.g_plane) = static_cast<uint16_t>(lp);
+              *reinterpret_cast<uint16_t*>(q1 + p.g_plane) = static_cast<uint16_t>(lp >> 16);
+            }
+          }
+          if (--s_t < 0) { s_t = p.T - 1; ++s_bi; }
         };
-        float vb0[16], vb1[16], vb2[16];
-        loadv(0, vb0); loadv(1, vb1); loadv(2, vb2);
+        float vb0[16] = {}, vb1[16] = {}, vb2[16] = {};
+        loadv(vb0); loadv(vb1); loadv(vb2);
         for (int sidx = 0; sidx < nsteps; sidx += 3) {
-          step(sidx, vb0);
-          loadv(sidx + 3, vb0);
-          if (sidx + 1 < nsteps) { step(sidx + 1, vb1); loadv(sidx + 4, vb1); }
-          if (sidx + 2 < nsteps) { step(sidx + 2, vb2); loadv(sidx + 5, vb2); }
+          step(vb0);
+          loadv(vb0);
+          if (sidx + 1 < nsteps) { step(vb1); loadv(vb1); }
+          if (sidx + 2 < nsteps) { step(vb2); loadv(vb2); }
         }
       }
       for (int bg = (MODE == NM_DX || (p.dbg & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
@@ -403,9 +419,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             if (lane < 16)
               p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
             if (p.v_out != nullptr) {
-              float* dst = p.v_out + c * p.MP + n;               // [sample-step][neuron]: a warp stores 128 contiguous bytes
+              // [neuron / 32][sample-step][32]: this warp's 16 sample-steps are 16 consecutive 128-byte rows
+              float* dst = p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32 + lane;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dst[static_cast<size_t>(j) * p.MP] = vol[j];
+              for (int j = 0; j < 16; ++j) dst[j * 32] = vol[j];
             }
             sprev = scur;
             tmem_ld_wait();

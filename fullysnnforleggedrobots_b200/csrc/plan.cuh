@@ -16,7 +16,8 @@
 //   * g_c (time-stepped bf16 hi/lo planes): swz64 image with rows = sample-steps r, columns = neurons — the K-major
 //     B operand of dX and the MN-major A operand of dW; the epilogue threads (= neurons) of a warp store 64
 //     contiguous bytes of one row.
-//   * voltages: fp32 [Rt][NP] (a warp = 32 consecutive neurons of one sample-step = 128 contiguous bytes).
+//   * voltages: fp32 [NP/32][Rt][32]: a warp (32 consecutive neurons) reads / writes the sample-steps of a
+//     16-sample group as 16 consecutive 128-byte rows.
 //   * the dense critic keeps plain rows r = b, Bpad = roundup(B, 128).
 #pragma once
 #include <cstddef>
@@ -49,7 +50,7 @@ struct LayerPlan {
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
   size_t tr_bits;    // trace: output spike words [NP/32][Rt]
-  size_t tr_volt;    // trace: fp32 voltages [Rt][NP]
+  size_t tr_volt;    // trace: fp32 voltages [NP/32][Rt][32]
 };
 
 struct SnnPlan {

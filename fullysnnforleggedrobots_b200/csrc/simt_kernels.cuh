@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
   const int TB = T * tg.Bt;
   uint8_t* const gcol = g_img + static_cast<size_t>(n >> 6) * tg.Rt * 128 + (n & 7) * 2;     // see nm_gemm.cuh (dX epilogue)
   const int cn = (n & 63) >> 3;
-  const size_t vstep = static_cast<size_t>(tg.Bt) * NP;                                      // floats between timesteps
+  const size_t vstep = static_cast<size_t>(tg.Bt) * 32;                                      // floats between timesteps
   float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
   for (int bg = 0; bg < (tg.Bt >> 4); ++bg) {
     const int col0 = bg * 16;
@@ -234,18 +234,18 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
         gup[j] = __fdiv_rn(G * wn, Tf);
       }
     }
-    const float* vbase = volt + (c_tile + col0) * NP + n;
+    const float* vbase = volt + (static_cast<size_t>(n >> 5) * tg.Rt + c_tile + col0) * 32 + (n & 31);      // [n/32][Rt][32]
     // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's loads in flight
     float vn[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + static_cast<size_t>(j) * NP);
+    for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + j * 32);
     for (int t = T - 1; t >= 0; --t) {
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = vn[j];
       if (t > 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + static_cast<size_t>(j) * NP);
+        for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + j * 32);
       }
       const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);
       uint8_t* const dst = gcol + (c >> 3) * 1024;

@@ -184,8 +184,8 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace layout: [Rt sample-steps][NP]
-            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(Rt, NP)
+            # voltage trace layout: [NP / 32][Rt sample-steps][32]
+            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt, 32).permute(1, 0, 2).reshape(Rt, NP)
             res["volt"].append(v[col][:, :B, :self.dims[l + 1]].contiguous())
         return res
 
