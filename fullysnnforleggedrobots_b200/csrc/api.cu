@@ -323,14 +323,15 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const LayerPlan& lp = p.layer[top];
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<dim3(p.ntile, lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<dim3(p.ntile * (p.Bt / 16), lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
                                          p.T, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
-    df.row(dbpart_of(top), p.ntile, lp.NP, lp.N, g->bias[top]);
-    df.row(small, p.ntile, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
-    df.row(small + lp.NP, p.ntile, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
+    const int nrows = p.ntile * (p.Bt / 16);
+    df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
+    df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
+    df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
   }
   // ---- walk down the layers
   for (int l = top; l >= 0; --l) {
@@ -378,7 +379,12 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         LAUNCH_CHECK("nm_gemm_kernel<DX>");
         df.row(dbpart_of(l - 1), 2 * grid / q.nmt, lo.NP, lo.N, g->bias[l - 1]);
       } else {
-        q.g_a = g_a;
+        q.g_a = g->obs != nullptr ? g_a : nullptr;
+        q.enc_obs = obs; q.enc_mean = prm->enc_mean; q.enc_std = prm->enc_std;
+        q.enc_O = p.O; q.enc_P = p.Pe; q.enc_K0 = p.K0; q.enc_eps = d->enc_eps;
+        q.enc_part = small_enc;
+        df.row(small_enc, 2 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
+        df.row(small_enc + p.K0P, 2 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         nm_gemm_kernel<NM_DX_ENC><<<grid, NmCfg<NM_DX_ENC>::THREADS, nm_gemm_smem_bytes<NM_DX_ENC>(), st>>>(q);
         }
@@ -386,17 +392,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       }
     }
   }
-  // ---- encoder parameter gradients (+ d obs); the decoder's came out of top_scan_kernel
+  // ---- d obs (the encoder parameter gradients came out of the DX_ENC epilogue, the decoder's out of top_scan_kernel)
   {
-    const int ngroups = (Bi + 15) / 16;
-    const int nblk = ngroups < kEncBwdBlocks ? ngroups : kEncBwdBlocks;
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    enc_bwd_kernel<<<dim3(p.K0P / 128, nblk), 128, 0, st>>>(obs, prm->enc_mean, prm->enc_std, g_a, Bi, p.O, p.Pe, p.K0, p.K0P,
-                                                           d->enc_eps, small_enc);
-    }
-    LAUNCH_CHECK("enc_bwd_kernel");
-    df.row(small_enc, nblk, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
-    df.row(small_enc + p.K0P, nblk, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
     if (g->obs != nullptr) {
       const int n = Bi * p.O;
       { ProfScope prof__(CAT_OTHER, 0.0, st);

@@ -70,8 +70,16 @@ struct NmParams {
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
   float* db_part;           // [2 * gridDim.x / nmt][MP]
-  // DX_ENC epilogue
-  float* g_a;               // [Bcap/16][MP][16]
+  // DX_ENC epilogue: g_a = d loss / d pop_act (written only when the caller needs d obs) and, fused, the encoder
+  // parameter gradients (actor_critic.py:105 under autograd):  a = exp(-1/2 d^2 / var), d = obs - mean,
+  //   d mean = sum_b g_a a d / var ;  d std = sum_b g_a a d^2 std / var^2     (per-thread sums, one row per group)
+  float* g_a;               // [Bcap/16][MP][16] or null
+  const float* enc_obs;     // [B][enc_O]
+  const float* enc_mean;    // [enc_K0]
+  const float* enc_std;     // [enc_K0]
+  int enc_O, enc_P, enc_K0;
+  float enc_eps;
+  float* enc_part;          // [2 * gridDim.x / nmt][2][MP]
   int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
   int nstg;                 // FWD: staging buffers (1 or 2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
@@ -294,6 +302,12 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     const int bg0 = nsets == 2 ? 0 : grp, bgstep = nsets == 2 ? 1 : 2;
     const float bias = IS_FWD ? p.bias[n] : 0.f;
     float dbsum = 0.f;
+    // DX_ENC: this thread's encoder neuron
+    const bool enc_live = MODE == NM_DX_ENC && n < p.enc_K0;
+    const float enc_mk = enc_live ? p.enc_mean[n] : 0.f, enc_sk = enc_live ? p.enc_std[n] : 1.f;
+    const float enc_iv = 1.f / (enc_sk * enc_sk + p.enc_eps);
+    const int enc_o = enc_live ? n / p.enc_P : 0;
+    float enc_dm = 0.f, enc_ds = 0.f;
     uint32_t it = 0;
     for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
       const uint32_t aset = it % nsets;
@@ -445,11 +459,29 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
               ga[j] += gam[j];
             }
           }
-          float4* dst = reinterpret_cast<float4*>(p.g_a + ((static_cast<size_t>(b_tile + col0) >> 4) * p.MP + n) * 16);
+          if (p.g_a != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(p.g_a + ((static_cast<size_t>(b_tile + col0) >> 4) * p.MP + n) * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_float4(((vmask >> (4 * j)) & 1u) ? ga[4 * j] : 0.f, ((vmask >> (4 * j + 1)) & 1u) ? ga[4 * j + 1] : 0.f,
-                                 ((vmask >> (4 * j + 2)) & 1u) ? ga[4 * j + 2] : 0.f, ((vmask >> (4 * j + 3)) & 1u) ? ga[4 * j + 3] : 0.f);
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(((vmask >> (4 * j)) & 1u) ? ga[4 * j] : 0.f, ((vmask >> (4 * j + 1)) & 1u) ? ga[4 * j + 1] : 0.f,
+                                   ((vmask >> (4 * j + 2)) & 1u) ? ga[4 * j + 2] : 0.f, ((vmask >> (4 * j + 3)) & 1u) ? ga[4 * j + 3] : 0.f);
+          }
+          if (enc_live) {
+            // all 16 observation loads first (clamped for samples >= B), so their latencies overlap
+            float xv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int b = min(b_tile + col0 + j, p.B - 1);
+              xv[j] = __ldg(p.enc_obs + static_cast<size_t>(b) * p.enc_O + enc_o);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float d = xv[j] - enc_mk;
+              const float gaa = ((vmask >> j) & 1u) ? ga[j] * __expf(-0.5f * d * d * enc_iv) : 0.f;
+              enc_dm += gaa * d * enc_iv;
+              enc_ds += gaa * d * d * enc_iv * enc_iv * enc_sk;
+            }
+          }
         }
       }
       if (MODE == NM_DX && (nsets == 2 || grp == 0)) {
@@ -468,6 +500,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     }
     if (MODE == NM_DX)
       p.db_part[(static_cast<size_t>(tile0) * 2 + grp) * p.MP + n] = dbsum;
+    if (MODE == NM_DX_ENC) {
+      p.enc_part[((static_cast<size_t>(tile0) * 2 + grp) * 2) * p.MP + n] = enc_dm;
+      p.enc_part[((static_cast<size_t>(tile0) * 2 + grp) * 2 + 1) * p.MP + n] = enc_ds;
+    }
   } else if (IS_FWD && warp == 3) {
     // ===================================================== staging -> operand slot (shared->shared bulk copy)
     uint32_t u = 0;

@@ -30,7 +30,6 @@ namespace snn {
 constexpr int kTileM = 128;       // batch rows per MMA tile (UMMA_M, cta_group::1)
 constexpr int kChunkK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int kMaxT = 32;
-constexpr int kEncBwdBlocks = 256;   // batch slices of the encoder-gradient kernel (one row of partials each)
 
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -151,12 +150,12 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   int npmax = p.K0P;
   for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
   size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;          // dX kernels: <= one row of partials per CTA
-  const size_t dbp_top = static_cast<size_t>(p.ntile) * p.layer[p.L - 1].NP;   // top scan: one row per batch tile
+  const size_t dbp_top = static_cast<size_t>(p.ntile) * (p.Bt / 16) * p.layer[p.L - 1].NP;   // top scan: one row per 16-sample group
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
-  p.ws_small = take(static_cast<size_t>(p.ntile) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
-  p.ws_small_enc = take(static_cast<size_t>(kEncBwdBlocks) * 2 * p.K0P * 4 + 1024);          // encoder partials
+  p.ws_small = take(static_cast<size_t>(p.ntile) * (p.Bt / 16) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
+  p.ws_small_enc = take(static_cast<size_t>(p.dw_max_ctas) * 2 * p.K0P * 4 + 1024);          // encoder partials (<= 2 rows per CTA of DX_ENC)
   p.ws_bwd_bytes = off;
   *out = p;
   return SNN_OK;

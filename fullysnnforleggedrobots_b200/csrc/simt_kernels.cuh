@@ -205,10 +205,12 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
                                                       int dec_tanh, const float* __restrict__ dec_w,
                                                       const float* __restrict__ volt, int B, TileGeom tg, int A, int P,
                                                       int NP, int T, uint8_t* __restrict__ g_img, size_t g_plane,
-                                                      float* __restrict__ db_part /* [ntile][NP] */,
-                                                      float* __restrict__ dec_part /* [ntile][2][NP] */) {
-  // grid (ntile, NP / 128); a warp reads / writes 32 consecutive neurons of one sample-step per request
-  const int tile = blockIdx.x;
+                                                      float* __restrict__ db_part /* [gridDim.x][NP] */,
+                                                      float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
+  // grid (ntile * Bt / 16, NP / 128): one block per (tile, 16-sample group); a warp reads / writes 32 consecutive
+  // neurons of one sample-step per request
+  const int nbg = tg.Bt >> 4;
+  const int tile = blockIdx.x / nbg, bg_only = blockIdx.x - tile * nbg;
   const int n = blockIdx.y * 128 + threadIdx.x;
   const bool n_live = n < A * P;
   const int a = n_live ? n / P : 0;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
   const int cn = (n & 63) >> 3;
   const size_t vstep = static_cast<size_t>(tg.Bt) * 32;                                      // floats between timesteps
   float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
-  for (int bg = 0; bg < (tg.Bt >> 4); ++bg) {
+  for (int bg = bg_only; bg == bg_only; ++bg) {
     const int col0 = bg * 16;
     const int b0 = tile * tg.Bt + col0;
     float gup[16], Gc[16], cnt[16], gvn[16], gcn[16];
@@ -274,56 +276,21 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
     }
   }
   // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
-  for (int cc = TB; cc < tg.CT; ++cc) {
+  for (int cc = TB + bg_only; cc < tg.CT; cc += nbg) {
     const size_t r = c_tile + cc;
     uint8_t* q = gcol + (r >> 3) * 1024 + (r & 7) * 128 + ((cn ^ static_cast<int>(r & 7)) << 4);
     *reinterpret_cast<uint16_t*>(q) = 0;
     *reinterpret_cast<uint16_t*>(q + g_plane) = 0;
   }
-  db_part[static_cast<size_t>(tile) * NP + n] = dbsum;
-  dec_part[(static_cast<size_t>(tile) * 2) * NP + n] = dwd;
-  dec_part[(static_cast<size_t>(tile) * 2 + 1) * NP + n] = dbd;
+  db_part[static_cast<size_t>(blockIdx.x) * NP + n] = dbsum;
+  dec_part[(static_cast<size_t>(blockIdx.x) * 2) * NP + n] = dwd;
+  dec_part[(static_cast<size_t>(blockIdx.x) * 2 + 1) * NP + n] = dbd;
 }
 
 // (decoder gradients are produced by top_scan_kernel)
 
-// ------------------------------------------------------------------ encoder gradients
-// From g_a = d loss / d pop_act, laid out [Bcap/16][K0P][16 samples] by the DX_ENC epilogue:
-//   d mean = sum_b g_a a (x-mean)/var ; d std = sum_b g_a a (x-mean)^2 std / var^2 ; (var = std^2 + eps)
-// thread = encoder neuron; block (128 neurons) x batch slice; partials [gridDim.y][2][K0P].
-__global__ void __launch_bounds__(128) enc_bwd_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
-                                                     const float* __restrict__ std, const float* __restrict__ g_a,
-                                                     int B, int O, int P, int K0, int K0P, float eps,
-                                                     float* __restrict__ part /* [gridDim.y][2][K0P] */) {
-  const int k = blockIdx.x * 128 + threadIdx.x;
-  const bool live = k < K0;
-  float dm = 0.f, ds = 0.f;
-  if (live) {
-    const float mk = mean[k], sk = std[k];
-    const float inv_var = 1.f / (sk * sk + eps);
-    const int o = k / P;
-    const int ngroups = (B + 15) >> 4;
-    for (int g = blockIdx.y; g < ngroups; g += gridDim.y) {
-      const float4* src = reinterpret_cast<const float4*>(g_a + (static_cast<size_t>(g) * K0P + k) * 16);
-      float ga[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const float4 v = __ldg(src + j); ga[4 * j] = v.x; ga[4 * j + 1] = v.y; ga[4 * j + 2] = v.z; ga[4 * j + 3] = v.w; }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int b = g * 16 + j;
-        if (b < B) {
-          const float d = obs[static_cast<size_t>(b) * O + o] - mk;
-          const float gaa = ga[j] * expf(-0.5f * d * d * inv_var);
-          dm += gaa * d * inv_var;
-          ds += gaa * d * d * inv_var * inv_var * sk;
-        }
-      }
-    }
-  }
-  part[(static_cast<size_t>(blockIdx.y) * 2) * K0P + k] = dm;
-  part[(static_cast<size_t>(blockIdx.y) * 2 + 1) * K0P + k] = ds;
-}
-
+// ------------------------------------------------------------------ encoder input gradient
+// (the encoder PARAMETER gradients are produced by the DX_ENC epilogue, nm_gemm.cuh)
 // d obs[b,o] = sum_p g_a a (-(x-mean))/var   (RMA: the actor input is cat(obs, latent) and needs grad)
 __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                 const float* __restrict__ std, const float* __restrict__ g_a, int B, int O, int P,
