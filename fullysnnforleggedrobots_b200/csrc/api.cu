@@ -377,14 +377,14 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         nm_gemm_kernel<NM_DX><<<grid, NmCfg<NM_DX>::THREADS, nm_gemm_smem_bytes<NM_DX>(), st>>>(q);
         }
         LAUNCH_CHECK("nm_gemm_kernel<DX>");
-        df.row(dbpart_of(l - 1), 2 * grid / q.nmt, lo.NP, lo.N, g->bias[l - 1]);
+        df.row(dbpart_of(l - 1), 3 * grid / q.nmt, lo.NP, lo.N, g->bias[l - 1]);
       } else {
         q.g_a = g->obs != nullptr ? g_a : nullptr;
         q.enc_obs = obs; q.enc_mean = prm->enc_mean; q.enc_std = prm->enc_std;
         q.enc_O = p.O; q.enc_P = p.Pe; q.enc_K0 = p.K0; q.enc_eps = d->enc_eps;
         q.enc_part = small_enc;
-        df.row(small_enc, 2 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
-        df.row(small_enc + p.K0P, 2 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
+        df.row(small_enc, 3 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
+        df.row(small_enc + p.K0P, 3 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         nm_gemm_kernel<NM_DX_ENC><<<grid, NmCfg<NM_DX_ENC>::THREADS, nm_gemm_smem_bytes<NM_DX_ENC>(), st>>>(q);
         }

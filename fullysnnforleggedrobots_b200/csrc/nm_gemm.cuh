@@ -69,7 +69,7 @@ struct NmParams {
   const float* v_in;        // [MP/32][Rt][32] voltages of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
-  float* db_part;           // [2 * gridDim.x / nmt][MP]
+  float* db_part;           // [3 * gridDim.x / nmt][MP]   (one row per CTA and epilogue group)
   // DX_ENC epilogue: g_a = d loss / d pop_act (written only when the caller needs d obs) and, fused, the encoder
   // parameter gradients (actor_critic.py:105 under autograd):  a = exp(-1/2 d^2 / var), d = obs - mean,
   //   d mean = sum_b g_a a d / var ;  d std = sum_b g_a a d^2 std / var^2     (per-thread sums, one row per group)
@@ -79,7 +79,7 @@ struct NmParams {
   const float* enc_std;     // [enc_K0]
   int enc_O, enc_P, enc_K0;
   float enc_eps;
-  float* enc_part;          // [2 * gridDim.x / nmt][2][MP]
+  float* enc_part;          // [3 * gridDim.x / nmt][2][MP]
   int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
   int nstg;                 // FWD: staging buffers (1 or 2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
@@ -96,7 +96,7 @@ template <> struct NmCfg<NM_FWD> {
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
 // <= 256 sample-steps x 128 B)
 template <> struct NmCfg<NM_DX> {
-  static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 384;
+  static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 512;
 };
 template <> struct NmCfg<NM_DX_ENC> : NmCfg<NM_DX> {};
 
@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
   const uint32_t nsets = p.sets == 2 ? 2u : 1u;
+  // epilogue groups of 4 warps: FWD has two (warps 12-15 expand spikes) and, with two accumulator sets, binds group g
+  // to set g; the dX kernels have three, every group works on every item and the 16-sample groups go round-robin
+  constexpr int NGRP = IS_FWD ? 2 : 3;
+  const bool by_set = IS_FWD && p.sets == 2;
   const int nsub = (p.TB + 255) / 256;                 // sample-step sub-tiles of <= 256 columns (2 only when T > 16)
   const int mt = blockIdx.x % p.nmt;                   // this CTA's neuron tile
   const int tile0 = blockIdx.x / p.nmt, tstep = gridDim.x / p.nmt;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
     for (int s = 0; s < 2; ++s) mbar_init(&stg_full[s], 4);
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], nsets == 2 ? 128 : 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], by_set ? 128 : NGRP * 128); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -292,14 +296,14 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 4 + 4 * NGRP) {
     // ===================================================== epilogue: the time scan, thread = neuron
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int n = mt * 128 + q * 32 + lane;                      // this thread's neuron (row of the layer)
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int nbg = p.Bt >> 4;                                    // 16-sample groups per tile
-    const int bg0 = nsets == 2 ? 0 : grp, bgstep = nsets == 2 ? 1 : 2;
+    const int bg0 = by_set ? 0 : grp, bgstep = by_set ? 1 : NGRP;
     const float bias = IS_FWD ? p.bias[n] : 0.f;
     float dbsum = 0.f;
     // DX_ENC: this thread's encoder neuron
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     uint32_t it = 0;
     for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
       const uint32_t aset = it % nsets;
-      if (nsets == 2 && aset != static_cast<uint32_t>(grp)) continue;
+      if (by_set && aset != static_cast<uint32_t>(grp)) continue;
       const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
       const int b_tile = tile * p.Bt;
       if (MODE == NM_DX && lane < 16) {
@@ -327,10 +331,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       const uint32_t t_set = t_lane + aset * 256;
       if (MODE == NM_DX) {
         // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the loads of a step's fp32 voltages
-        // (one coalesced 128-byte row per sample-step and warp) run THREE steps ahead of the recurrence.
+        // (one coalesced 128-byte row per sample-step and warp) run TWO steps ahead of the recurrence.
         // No validity masks: samples >= B have g_c == 0 in the layer above (the top scan writes zeros there), so
         // their accumulators are exactly 0, and with the zero initial state every g_c written here is 0 again.
-        const int nb = (nbg - bg0 + bgstep - 1) / bgstep;
+        const int nb = bg0 < nbg ? (nbg - bg0 + bgstep - 1) / bgstep : 0;
         const int nsteps = (p.dbg & 2) ? 0 : nb * p.T;
         // g_c image [MP/64][Rt rows][128 B]: this thread's neuron is bf16 column n % 64 of chunk n / 64; a warp's 32
         // neurons are 64 contiguous bytes of a row, so every store below is one coalesced 64-byte request.
@@ -392,13 +396,12 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           }
           if (--s_t < 0) { s_t = p.T - 1; ++s_bi; }
         };
-        float vb0[16] = {}, vb1[16] = {}, vb2[16] = {};
-        loadv(vb0); loadv(vb1); loadv(vb2);
-        for (int sidx = 0; sidx < nsteps; sidx += 3) {
+        float vb0[16] = {}, vb1[16] = {};
+        loadv(vb0); loadv(vb1);
+        for (int sidx = 0; sidx < nsteps; sidx += 2) {
           step(vb0);
           loadv(vb0);
           if (sidx + 1 < nsteps) { step(vb1); loadv(vb1); }
-          if (sidx + 2 < nsteps) { step(vb2); loadv(vb2); }
         }
       }
       for (int bg = (MODE == NM_DX || (p.dbg & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           }
         }
       }
-      if (MODE == NM_DX && (nsets == 2 || grp == 0)) {
+      if (MODE == NM_DX && grp == 0) {
         // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
         uint8_t* const gcol = p.g_img + static_cast<size_t>(n >> 6) * p.Rt * 128 + (n & 7) * 2;
         const int cn = (n & 63) >> 3;
@@ -499,10 +502,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       mbar_arrive(&acc_empty[aset]);
     }
     if (MODE == NM_DX)
-      p.db_part[(static_cast<size_t>(tile0) * 2 + grp) * p.MP + n] = dbsum;
+      p.db_part[(static_cast<size_t>(tile0) * NGRP + grp) * p.MP + n] = dbsum;
     if (MODE == NM_DX_ENC) {
-      p.enc_part[((static_cast<size_t>(tile0) * 2 + grp) * 2) * p.MP + n] = enc_dm;
-      p.enc_part[((static_cast<size_t>(tile0) * 2 + grp) * 2 + 1) * p.MP + n] = enc_ds;
+      p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2) * p.MP + n] = enc_dm;
+      p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2 + 1) * p.MP + n] = enc_ds;
     }
   } else if (IS_FWD && warp == 3) {
     // ===================================================== staging -> operand slot (shared->shared bulk copy)

@@ -136,7 +136,7 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   }
   for (int s = 0; s < 2; ++s) { p.ws_g_plane[s] = gmax[s]; p.ws_g[s] = take(2 * gmax[s]); }
   p.ws_ga = take(static_cast<size_t>(p.Bcap) * p.K0P * 4);
-  p.dw_max_ctas = num_sms > 0 ? 2 * num_sms : 296;
+  p.dw_max_ctas = num_sms > 0 ? 3 * num_sms : 444;      // also bounds the rows of per-CTA partials of the dX kernels (3 per CTA)
   size_t part = 0;
   for (int l = 0; l < p.L; ++l) {
     // worst case: every CTA of the dW launch writes one 128 x 256 fp32 tile
