@@ -172,7 +172,7 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const TileGeom tg = geom_of(p);
   uint32_t* enc_bits = reinterpret_cast<uint32_t*>(at(bits_base, p.tr_enc_bits));
   {
-    dim3 blk(32, 8), grd(p.K0P / 32, static_cast<unsigned>((p.Bcap + 127) / 128));
+    dim3 blk(256), grd(static_cast<unsigned>((p.Bcap + 255) / 256), p.K0P / 32);
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     if (p.T == 5)
       encode_kernel<5><<<grd, blk, 0, st>>>(obs, prm->enc_mean, prm->enc_std, static_cast<int>(B), tg, p.O, p.Pe, p.K0, p.T,
@@ -257,17 +257,19 @@ int snn_pack_weights(const SnnDesc* d, const SnnParams* prm, void* packed, void*
   if ((rc = plan_for(d, 1, sms, &p))) return rc;
   if (prm == nullptr || packed == nullptr) return fail(SNN_EINVAL, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackJobs jobs{};
+  int max_total = 0;
   for (int l = 0; l < p.L; ++l) {
     const LayerPlan& lp = p.layer[l];
     if (prm->weight[l] == nullptr || prm->bias[l] == nullptr) return fail(SNN_EINVAL, "null weight/bias pointer");
-    const int total = lp.NP * lp.KP / 8;
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    pack_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP,
-                                                       at(packed, lp.w_img), lp.w_plane, at(packed, lp.wt_img),
-                                                       lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad)));
-    }
-    LAUNCH_CHECK("pack_w_kernel");
+    jobs.j[l] = PackJob{prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP, at(packed, lp.w_img), lp.w_plane,
+                        at(packed, lp.wt_img), lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad))};
+    if (lp.NP * lp.KP / 8 > max_total) max_total = lp.NP * lp.KP / 8;
   }
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  pack_w_kernel<<<dim3((max_total + 255) / 256, p.L), 256, 0, st>>>(jobs);
+  }
+  LAUNCH_CHECK("pack_w_kernel");
   return SNN_OK;
 }
 
@@ -323,12 +325,12 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const LayerPlan& lp = p.layer[top];
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<dim3(p.ntile * (p.Bt / 16), lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<dim3(p.ntile * (p.Bt / kTopScanSPT), lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
                                          p.T, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
-    const int nrows = p.ntile * (p.Bt / 16);
+    const int nrows = p.ntile * (p.Bt / kTopScanSPT);
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
     df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
     df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
@@ -460,17 +462,19 @@ int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* prm, void* packed, voi
   if (!d || !prm || !packed || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, 1, &p) != SNN_OK)
     return fail(SNN_EINVAL, "bad MLP descriptor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackJobs jobs{};
+  int max_total = 0;
   for (int l = 0; l < p.H; ++l) {
     const MlpLayerPlan& lp = p.layer[l];
     if (!prm->weight[l] || !prm->bias[l]) return fail(SNN_EINVAL, "null weight/bias pointer");
-    const int total = lp.NP * lp.KP / 8;
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    pack_w_kernel<<<(total + 255) / 256, 256, 0, st>>>(prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP,
-                                                       at(packed, lp.w_img), lp.w_plane, at(packed, lp.wt_img),
-                                                       lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad)));
-    }
-    LAUNCH_CHECK("pack_w_kernel(mlp)");
+    jobs.j[l] = PackJob{prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP, at(packed, lp.w_img), lp.w_plane,
+                        at(packed, lp.wt_img), lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad))};
+    if (lp.NP * lp.KP / 8 > max_total) max_total = lp.NP * lp.KP / 8;
   }
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  pack_w_kernel<<<dim3((max_total + 255) / 256, p.H), 256, 0, st>>>(jobs);
+  }
+  LAUNCH_CHECK("pack_w_kernel(mlp)");
   return SNN_OK;
 }
 

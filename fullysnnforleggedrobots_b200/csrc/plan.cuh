@@ -150,11 +150,11 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   int npmax = p.K0P;
   for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
   size_t dbp = static_cast<size_t>(p.dw_max_ctas) * npmax;          // dX kernels: <= one row of partials per CTA
-  const size_t dbp_top = static_cast<size_t>(p.ntile) * (p.Bt / 16) * p.layer[p.L - 1].NP;   // top scan: one row per 16-sample group
+  const size_t dbp_top = static_cast<size_t>(p.ntile) * (p.Bt / 8) * p.layer[p.L - 1].NP;   // top scan: one row per 8-sample group
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
-  p.ws_small = take(static_cast<size_t>(p.ntile) * (p.Bt / 16) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
+  p.ws_small = take(static_cast<size_t>(p.ntile) * (p.Bt / 8) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
   p.ws_small_enc = take(static_cast<size_t>(p.dw_max_ctas) * 2 * p.K0P * 4 + 1024);          // encoder partials (<= 2 rows per CTA of DX_ENC)
   p.ws_bwd_bytes = off;
   *out = p;

@@ -18,9 +18,19 @@ __device__ __forceinline__ void split3(float w, float& h, float& m, float& l) {
   l = bf16_round(r1 - m);
 }
 
-__global__ void pack_w_kernel(const float* __restrict__ W, const float* __restrict__ bias, int N, int K, int NP,
-                              int KP, uint8_t* __restrict__ w_img, size_t w_plane, uint8_t* __restrict__ wt_img,
-                              size_t wt_plane, float* __restrict__ bias_pad) {
+// all layers of a network in ONE launch: blockIdx.y selects the layer
+struct PackJob { const float* W; const float* bias; int N, K, NP, KP; uint8_t* w_img; size_t w_plane; uint8_t* wt_img; size_t wt_plane; float* bias_pad; };
+struct PackJobs { PackJob j[SNN_MAX_LAYERS]; };
+__global__ void pack_w_kernel(const PackJobs jobs) {
+  const PackJob& jb = jobs.j[blockIdx.y];
+  const float* __restrict__ W = jb.W;
+  const float* __restrict__ bias = jb.bias;
+  const int N = jb.N, K = jb.K, NP = jb.NP, KP = jb.KP;
+  uint8_t* __restrict__ w_img = jb.w_img;
+  uint8_t* __restrict__ wt_img = jb.wt_img;
+  const size_t w_plane = jb.w_plane, wt_plane = jb.wt_plane;
+  float* __restrict__ bias_pad = jb.bias_pad;
+  if (static_cast<int>(blockIdx.x * blockDim.x) >= NP * (KP / 8)) return;      // grid.x is sized for the largest layer
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int kp8 = KP / 8;
   if (idx < NP * kp8) {   // forward image: one 16-byte piece = 8 consecutive k of row n
@@ -103,48 +113,62 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
 
 // batch-tile geometry of the actor's time-stepped tensors (plan.cuh): sample-step (t, b) -> tile * CT + t * Bt + b % Bt
 struct TileGeom { int Bt, CT, ntile; long long Rt; };
+constexpr int kTopScanSPT = 8;     // samples per thread of top_scan_kernel (Bt % 16 == 0)
 
-// TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T
+// TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T.
+// Thread = (sample, spike word): it evaluates the word's 32 encoder neurons (independent chains -> ILP, no
+// __ballot), and a warp = 32 consecutive samples stores each timestep's words as one coalesced run.
+// grid (ceil(Bcap / 256), K0P / 32), block 256.
 template <int TT>
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                                     const float* __restrict__ std, int B, TileGeom tg, int O, int P,
                                                     int K0, int T, float eps, uint32_t* __restrict__ bits) {
-  // block (32 neurons, 8 warps) covers 128 samples: each warp walks 16 of them (few, fat blocks: the per-sample work is
-  // tiny); lane t of the warp ends up with the spike word of step t and stores it
-  const int k = blockIdx.x * 32 + threadIdx.x;
-  const bool k_live = k < K0;
-  const int o = static_cast<int>((static_cast<float>(k) + 0.5f) * __frcp_rn(static_cast<float>(P)));   // k / P
-  const float mk = k_live ? mean[k] : 0.f, sk = k_live ? std[k] : 1.f;
-  const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
-  const float nh_inv_var = -0.5f * __frcp_rn(var);
-  const int b0 = blockIdx.y * 128 + threadIdx.y;
-  const int Bcap = tg.ntile * tg.Bt;
-  const int nt = TT > 0 ? TT : T;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int b = b0 + i * 8;
-    if (b >= Bcap) break;
-    uint32_t sp = 0;
-    if ((b < B) && k_live) {
-      const float d = __fsub_rn(obs[static_cast<size_t>(b) * O + o], mk);
+  __shared__ float s_mk[32], s_var[32], s_nh[32];
+  __shared__ int s_o[32];
+  const int kw = blockIdx.y;
+  if (threadIdx.x < 32) {
+    const int k = kw * 32 + threadIdx.x;
+    const bool k_live = k < K0;
+    const float sk = k_live ? std[k] : 1.f;
+    const float var = __fadd_rn(__fmul_rn(sk, sk), eps);
+    s_mk[threadIdx.x] = k_live ? mean[k] : 0.f;
+    s_var[threadIdx.x] = var;
+    s_nh[threadIdx.x] = -0.5f * __frcp_rn(var);
+    s_o[threadIdx.x] = k_live ? k / P : -1;                 // -1: padding neuron, never spikes
+  }
+  __syncthreads();
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= tg.ntile * tg.Bt) return;
+  uint32_t sp[32];
+  const bool b_live = b < B;
+  int o_prev = -2;
+  float x = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int o = s_o[i];
+    sp[i] = 0;
+    if (b_live && o >= 0) {
+      if (o != o_prev) { x = obs[static_cast<size_t>(b) * O + o]; o_prev = o; }
+      const float d = __fsub_rn(x, s_mk[i]);
       // fast path: a within ~1e-6 relative of the reference's exp(((-0.5 d^2) / var)); the spike train can only
       // differ from the exact one if some membrane value comes within ~5e-6 of the threshold
       float margin;
-      sp = regular_spikes<TT>(__expf(d * d * nh_inv_var), T, margin);
+      sp[i] = regular_spikes<TT>(__expf(d * d * s_nh[i]), T, margin);
       if (margin < 4e-5f) {
         // reference arithmetic order (actor_critic.py:105): ((-0.5 * d^2) / std^2), then a correctly rounded exp
-        const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), var);
-        sp = regular_spikes<0>(static_cast<float>(exp(static_cast<double>(q))), T, margin);
+        const float q = __fdiv_rn(__fmul_rn(-0.5f, __fmul_rn(d, d)), s_var[i]);
+        sp[i] = regular_spikes<0>(static_cast<float>(exp(static_cast<double>(q))), T, margin);
       }
     }
-    const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
-    uint32_t mine = 0;
-    for (int t = 0; t < nt; ++t) {
-      const uint32_t word = __ballot_sync(0xffffffffu, (sp >> t) & 1u);
-      if (static_cast<int>(threadIdx.x) == t) mine = word;
-    }
-    if (static_cast<int>(threadIdx.x) < nt)
-      bits[static_cast<size_t>(blockIdx.x) * tg.Rt + static_cast<size_t>(tile) * tg.CT + threadIdx.x * tg.Bt + bl] = mine;
+  }
+  const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
+  uint32_t* dst = bits + static_cast<size_t>(kw) * tg.Rt + static_cast<size_t>(tile) * tg.CT + bl;
+  const int nt = TT > 0 ? TT : T;
+  for (int t = 0; t < nt; ++t) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) word |= ((sp[i] >> t) & 1u) << i;
+    dst[static_cast<size_t>(t) * tg.Bt] = word;
   }
 }
 
@@ -207,9 +231,11 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
                                                       int NP, int T, uint8_t* __restrict__ g_img, size_t g_plane,
                                                       float* __restrict__ db_part /* [gridDim.x][NP] */,
                                                       float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
-  // grid (ntile * Bt / 16, NP / 128): one block per (tile, 16-sample group); a warp reads / writes 32 consecutive
-  // neurons of one sample-step per request
-  const int nbg = tg.Bt >> 4;
+  // grid (ntile * Bt / SPT, NP / 128): one block per (tile, SPT-sample group); a warp reads / writes 32 consecutive
+  // neurons of one sample-step per request.  SPT = 8 keeps the per-thread state small (more resident warps: the
+  // kernel is a chain of dependent loads and recurrences per thread, i.e. latency-bound).
+  constexpr int SPT = kTopScanSPT;
+  const int nbg = tg.Bt / SPT;
   const int tile = blockIdx.x / nbg, bg_only = blockIdx.x - tile * nbg;
   const int n = blockIdx.y * 128 + threadIdx.x;
   const bool n_live = n < A * P;
@@ -222,12 +248,12 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
   const int cn = (n & 63) >> 3;
   const size_t vstep = static_cast<size_t>(tg.Bt) * 32;                                      // floats between timesteps
   float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
-  for (int bg = bg_only; bg == bg_only; ++bg) {
-    const int col0 = bg * 16;
+  {
+    const int col0 = bg_only * SPT;
     const int b0 = tile * tg.Bt + col0;
-    float gup[16], Gc[16], cnt[16], gvn[16], gcn[16];
+    float gup[SPT], Gc[SPT], cnt[SPT], gvn[SPT], gcn[SPT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < SPT; ++j) {
       gup[j] = 0.f; Gc[j] = 0.f; cnt[j] = 0.f; gvn[j] = 0.f; gcn[j] = 0.f;
       if (n_live && b0 + j < B) {
         float G = g_mu[static_cast<size_t>(b0 + j) * A + a];
@@ -238,21 +264,21 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
     }
     const float* vbase = volt + (static_cast<size_t>(n >> 5) * tg.Rt + c_tile + col0) * 32 + (n & 31);      // [n/32][Rt][32]
     // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's loads in flight
-    float vn[16];
+    float vn[SPT];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + j * 32);
+    for (int j = 0; j < SPT; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + j * 32);
     for (int t = T - 1; t >= 0; --t) {
-      float v[16];
+      float v[SPT];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = vn[j];
+      for (int j = 0; j < SPT; ++j) v[j] = vn[j];
       if (t > 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + j * 32);
+        for (int j = 0; j < SPT; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + j * 32);
       }
-      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);
+      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);          // % 8 == 0
       uint8_t* const dst = gcol + (c >> 3) * 1024;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < SPT; ++j) {
         const bool live = b0 + j < B;
         const float vj = live ? v[j] : 0.f;
         cnt[j] += vj > 0.5f ? 1.f : 0.f;                       // output spike count -> rate
@@ -270,7 +296,7 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
       }
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < SPT; ++j) {
       dwd += Gc[j] * __fdiv_rn(cnt[j], Tf);
       dbd += Gc[j];
     }
