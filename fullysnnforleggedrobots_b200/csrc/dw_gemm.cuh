@@ -44,7 +44,7 @@ constexpr int kDwStages = 3;
 constexpr int kDwStageBytes = 65536;   // 32 KiB A (2 planes x 2 n-chunks x 8 KiB) + 32 KiB B (4 k-chunks x 8 KiB)
 constexpr int kDwBitStages = 8;        // ring of spike-word stages: 8 runs of 64 rows x 4 B
 constexpr int kDwBitStageBytes = 2048;
-constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + kDwBitStages * kDwBitStageBytes + 4096 + 512;
+constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + kDwBitStages * kDwBitStageBytes + 512;
 
 // DENSE = false: B operand = spike bits expanded in smem (3 stages of 64 KiB).
 // DENSE = true : B operand = hi/lo planes bulk-copied like A (2 stages of 96 KiB), three products.
@@ -56,8 +56,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint8_t* bits_ring = ring + kStages * kStageBytes;
-  uint4* lut = reinterpret_cast<uint4*>(bits_ring + kDwBitStages * kDwBitStageBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + 4096);
+  uint64_t* full = reinterpret_cast<uint64_t*>(bits_ring + kDwBitStages * kDwBitStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* acc_full = empty + kStages;
   uint64_t* full_bits = acc_full + 1;
@@ -81,14 +80,6 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 256);
-  for (int i = tid; i < 256; i += blockDim.x) {
-    uint4 v;
-    v.x = ((i & 1) ? 0x3F80u : 0u) | ((i & 2) ? 0x3F800000u : 0u);
-    v.y = ((i & 4) ? 0x3F80u : 0u) | ((i & 8) ? 0x3F800000u : 0u);
-    v.z = ((i & 16) ? 0x3F80u : 0u) | ((i & 32) ? 0x3F800000u : 0u);
-    v.w = ((i & 64) ? 0x3F80u : 0u) | ((i & 128) ? 0x3F800000u : 0u);
-    lut[i] = v;
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -200,7 +191,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t byte = ((j < 4 ? w[h][2 * kcl] : w[h][2 * kcl + 1]) >> ((j & 3) * 8)) & 0xFFu;
-              *reinterpret_cast<uint4*>(rbase + kcl * 8192 + ((j ^ sw) << 4)) = lut[byte];
+              *reinterpret_cast<uint4*>(rbase + kcl * 8192 + ((j ^ sw) << 4)) = expand_spike_byte(byte);
             }
           }
         }

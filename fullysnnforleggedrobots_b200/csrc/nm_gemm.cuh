@@ -111,7 +111,7 @@ inline int nm_fwd_s_stage(int TB) { return ((TB < 256 ? TB : 256) * 128 + 1023) 
 inline size_t nm_fwd_smem_bytes(int s_stage, int nstg) {
   return 1024 + static_cast<size_t>(NmCfg<NM_FWD>::NW) * NmCfg<NM_FWD>::W_STAGE +
          static_cast<size_t>(NmCfg<NM_FWD>::NS + nstg) * s_stage +
-         static_cast<size_t>(NmCfg<NM_FWD>::NBITS) * NmCfg<NM_FWD>::BITS_STAGE + 4096 /*LUT*/ + 512;
+         static_cast<size_t>(NmCfg<NM_FWD>::NBITS) * NmCfg<NM_FWD>::BITS_STAGE + 512;
 }
 inline int nm_fwd_nstg(int s_stage) { return nm_fwd_smem_bytes(s_stage, 2) <= kSmemOptIn ? 2 : 1; }
 
@@ -135,8 +135,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint8_t* s_ring = w_ring + C::NW * C::W_STAGE;
   uint8_t* staging = s_ring + C::NS * S_STAGE;                                      // FWD only: nstg buffers
   uint8_t* bits_ring = staging + (IS_FWD ? p.nstg * S_STAGE : 0);
-  uint4* lut = reinterpret_cast<uint4*>(bits_ring + C::NBITS * C::BITS_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(lut) + (IS_FWD ? 4096 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bits_ring + C::NBITS * C::BITS_STAGE);
   uint64_t* w_full = bars;                      // [<= 4]
   uint64_t* w_empty = w_full + 4;               // [<= 4]
   uint64_t* s_full = w_empty + 4;               // [<= 4]
@@ -170,17 +169,6 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
-  if (IS_FWD) {
-    // LUT: byte of 8 spike bits -> eight bf16 {0, 1}
-    for (int i = tid; i < 256; i += blockDim.x) {
-      uint4 v;
-      v.x = ((i & 1) ? 0x3F80u : 0u) | ((i & 2) ? 0x3F800000u : 0u);
-      v.y = ((i & 4) ? 0x3F80u : 0u) | ((i & 8) ? 0x3F800000u : 0u);
-      v.z = ((i & 16) ? 0x3F80u : 0u) | ((i & 32) ? 0x3F800000u : 0u);
-      v.w = ((i & 64) ? 0x3F80u : 0u) | ((i & 128) ? 0x3F800000u : 0u);
-      lut[i] = v;
-    }
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -566,7 +554,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
                   const uint32_t byte = ((c8 < 4 ? w0[h] : w1[h]) >> ((c8 & 3) * 8)) & 0xFFu;
-                  *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) = lut[byte];
+                  *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) = expand_spike_byte(byte);
                 }
               }
             }

@@ -202,6 +202,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// 8 spike bits (bit i = element i) -> eight bf16 {0, 1} (one 16-byte operand piece).  Pure ALU: a shared-memory
+// look-up table costs one bank-conflicted LDS.128 per piece, and the kernels that expand spikes are bound by the
+// shared-memory data pipe (profiles/r1g).  (t & 3) * 0x8001 & 0x10001 moves bit 0 -> bit 0 and bit 1 -> bit 16;
+// * 0x3F80 turns each into bf16 1.0.
+__device__ __forceinline__ uint4 expand_spike_byte(uint32_t b) {
+  uint4 v;
+  v.x = (((b & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+  v.y = ((((b >> 2) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+  v.z = ((((b >> 4) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+  v.w = ((((b >> 6) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
+  return v;
+}
 __device__ __forceinline__ float bf16_round(float x) {   // value of bf16(x) as fp32
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
