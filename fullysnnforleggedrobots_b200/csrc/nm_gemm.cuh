@@ -88,10 +88,11 @@ struct NmParams {
 };
 
 template <int MODE> struct NmCfg;
-// FWD: 2 weight stages of 3 x 16 KiB planes, 2 operand slots + 1-2 staging buffers of one spike sub-tile each
-// (<= 256 sample-steps x 128 B; the size is a launch parameter), 2 spike-word stages
+// FWD: a ring of 6 weight-plane units of 16 KiB (= two 64-wide chunks of hi/mid/lo, released plane by plane so the
+// reloads start early), 2 operand slots + 1-2 staging buffers of one spike sub-tile each (<= 256 sample-steps x
+// 128 B; the size is a launch parameter), 2 spike-word stages
 template <> struct NmCfg<NM_FWD> {
-  static constexpr int NW = 2, W_STAGE = 49152, NS = 2, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
+  static constexpr int NW = 6, W_STAGE = 16384, NS = 2, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
 };
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
 // <= 256 sample-steps x 128 B)
@@ -136,9 +137,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint8_t* staging = s_ring + C::NS * S_STAGE;                                      // FWD only: nstg buffers
   uint8_t* bits_ring = staging + (IS_FWD ? p.nstg * S_STAGE : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bits_ring + C::NBITS * C::BITS_STAGE);
-  uint64_t* w_full = bars;                      // [<= 4]
-  uint64_t* w_empty = w_full + 4;               // [<= 4]
-  uint64_t* s_full = w_empty + 4;               // [<= 4]
+  uint64_t* w_full = bars;                      // [<= 8]
+  uint64_t* w_empty = w_full + 8;               // [<= 8]
+  uint64_t* s_full = w_empty + 8;               // [<= 4]
   uint64_t* s_empty = s_full + 4;               // [<= 4]
   uint64_t* acc_full = s_empty + 4;             // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   const long long t_start = clock64();
 
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
     for (int s = 0; s < 2; ++s) mbar_init(&stg_full[s], 4);
@@ -178,18 +179,33 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     // ===================================================== operand producer (warp-uniform loop, one elected lane issues)
     uint32_t iw = 0, u = 0;
     for (int tile = tile0; tile < p.ntile; tile += tstep) {
-      for (int kc = 0; kc < KC; ++kc, ++iw) {
-        const uint32_t ws = iw % C::NW;
-        SNN_TWAIT(&w_empty[ws], ((iw / C::NW) & 1) ^ 1, 0);
-        if (elect_one()) {
-          const int npl = IS_FWD ? p.a_planes : 2;
-          mbar_expect_tx(&w_full[ws], static_cast<uint32_t>(npl * 16384));
-          for (int pl = 0; pl < npl; ++pl)
-            bulk_g2s(w_ring + ws * C::W_STAGE + pl * 16384,
-                     p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.MP + static_cast<size_t>(mt) * 128) * 128, 16384u,
-                     &w_full[ws]);
+      for (int kc = 0; kc < KC; ++kc) {
+        if (IS_FWD) {
+          // one ring unit per weight plane
+          for (int pl = 0; pl < p.a_planes; ++pl, ++iw) {
+            const uint32_t ws = iw % C::NW;
+            SNN_TWAIT(&w_empty[ws], ((iw / C::NW) & 1) ^ 1, 0);
+            if (elect_one()) {
+              mbar_expect_tx(&w_full[ws], 16384u);
+              bulk_g2s(w_ring + ws * C::W_STAGE,
+                       p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.MP + static_cast<size_t>(mt) * 128) * 128, 16384u,
+                       &w_full[ws]);
+            }
+            __syncwarp();
+          }
+        } else {
+          const uint32_t ws = iw % C::NW;
+          SNN_TWAIT(&w_empty[ws], ((iw / C::NW) & 1) ^ 1, 0);
+          if (elect_one()) {
+            mbar_expect_tx(&w_full[ws], 32768u);
+            for (int pl = 0; pl < 2; ++pl)
+              bulk_g2s(w_ring + ws * C::W_STAGE + pl * 16384,
+                       p.a_img + pl * p.a_plane + (static_cast<size_t>(kc) * p.MP + static_cast<size_t>(mt) * 128) * 128, 16384u,
+                       &w_full[ws]);
+          }
+          __syncwarp();
+          ++iw;
         }
-        __syncwarp();
         if (!IS_FWD) {
           // g_c units of this 64-neuron chunk: (plane) x (sub-tile), each one contiguous run of rows of the image
           for (int pl = 0; pl < 2; ++pl)
@@ -239,49 +255,103 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       const uint32_t aset = it % nsets;
       SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
       tc_fence_after_sync();
-      for (int kc = 0; kc < KC; ++kc, ++iw) {
-        const uint32_t ws = iw % C::NW;
-        SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
-        const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
-        for (int pl = 0; pl < (IS_FWD ? 1 : 2); ++pl)          // DX: g_c plane of the unit
-          for (int sub = 0; sub < nsub; ++sub, ++u) {
+      for (int kc = 0; kc < KC; ++kc) {
+        if (IS_FWD) {
+          const int npl = p.a_planes;
+          if (nsub == 1) {
+            // plane-major: each weight plane unit is released as soon as its four MMAs are issued
             const uint32_t ss = u % C::NS;
             SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
-            tc_fence_after_sync();
-            if (elect_one()) {
-              const int ncols = min(256, p.TB - sub * 256);
-              const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
-              const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
-              if (p.dbg & 1) {
-              } else if (IS_FWD) {
-                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
-                uint32_t acc = kc > 0 ? 1u : 0u;
+            const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
+            const uint32_t d = tmem_base + aset * 256;
+            const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(p.TB), 0, 0);
+            for (int pl = 0; pl < npl; ++pl, ++iw) {
+              const uint32_t ws = iw % C::NW;
+              SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
+                if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16)
-                  for (int pl = 0; pl < p.a_planes; ++pl) {
-                    umma_bf16_lohi(d, a_lo + pl * (16384 >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
-                    acc = 1u;
-                  }
-              } else {
-                // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + lo*hi on the g_c hi plane, then hi*lo on its lo plane
-                // (lo*lo < 2^-16 relative)
-                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
-                uint32_t acc = (kc > 0 || pl > 0) ? 1u : 0u;
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
-                  acc = 1u;
-                  if (pl == 0) umma_bf16_lohi(d, a_lo + (16384 >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, 1u);
+                  for (int k16 = 0; k16 < 4; ++k16)
+                    umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, (kc > 0 || pl > 0 || k16 > 0) ? 1u : 0u);
+                }
+                umma_commit(&w_empty[ws]);
+                if (pl == npl - 1) {
+                  umma_commit(&s_empty[ss]);
+                  if (kc == KC - 1) umma_commit(&acc_full[aset]);
                 }
               }
-              umma_commit(&s_empty[ss]);
-              if (pl == (IS_FWD ? 0 : 1) && sub == nsub - 1) {
-                umma_commit(&w_empty[ws]);
-                if (kc == KC - 1) umma_commit(&acc_full[aset]);
-              }
+              __syncwarp();
             }
-            __syncwarp();
+            ++u;
+          } else {
+            // two sub-tiles share the chunk's weight planes: wait for all of them, release them together
+            const uint32_t iw0 = iw;
+            for (int pl = 0; pl < npl; ++pl) SNN_TWAIT(&w_full[(iw0 + pl) % C::NW], ((iw0 + pl) / C::NW) & 1, 1);
+            for (int sub = 0; sub < nsub; ++sub, ++u) {
+              const uint32_t ss = u % C::NS;
+              SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const int ncols = min(256, p.TB - sub * 256);
+                const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
+                const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
+                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
+                uint32_t acc = kc > 0 ? 1u : 0u;
+                if (!(p.dbg & 1)) {
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16)
+                    for (int pl = 0; pl < npl; ++pl) {
+                      umma_bf16_lohi(d, w_ring_lo + ((iw0 + pl) % C::NW) * (C::W_STAGE >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
+                      acc = 1u;
+                    }
+                }
+                umma_commit(&s_empty[ss]);
+                if (sub == nsub - 1) {
+                  for (int pl = 0; pl < npl; ++pl) umma_commit(&w_empty[(iw0 + pl) % C::NW]);
+                  if (kc == KC - 1) umma_commit(&acc_full[aset]);
+                }
+              }
+              __syncwarp();
+            }
+            iw += npl;
           }
+        } else {
+          const uint32_t ws = iw % C::NW;
+          SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
+          const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
+          for (int pl = 0; pl < 2; ++pl)          // g_c plane of the unit
+            for (int sub = 0; sub < nsub; ++sub, ++u) {
+              const uint32_t ss = u % C::NS;
+              SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const int ncols = min(256, p.TB - sub * 256);
+                const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
+                const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
+                if (!(p.dbg & 1)) {
+                  // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + lo*hi on the g_c hi plane, then hi*lo on its lo plane
+                  // (lo*lo < 2^-16 relative)
+                  const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
+                  uint32_t acc = (kc > 0 || pl > 0) ? 1u : 0u;
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
+                    acc = 1u;
+                    if (pl == 0) umma_bf16_lohi(d, a_lo + (16384 >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, 1u);
+                  }
+                }
+                umma_commit(&s_empty[ss]);
+                if (pl == 1 && sub == nsub - 1) {
+                  umma_commit(&w_empty[ws]);
+                  if (kc == KC - 1) umma_commit(&acc_full[aset]);
+                }
+              }
+              __syncwarp();
+            }
+          ++iw;
+        }
       }
     }
   } else if (warp >= 4 && warp < 4 + 4 * NGRP) {
