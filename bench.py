@@ -330,7 +330,7 @@ def run_ours(args):
         return 0
 
     pk = peaks()
-    cats = ["fwd_scan_gemm", "dx_scan_gemm", "dw_gemm", "other_simt"]
+    cats = ["fwd_nm_gemm", "dx_nm_gemm", "dw_gemm", "other_simt"]
     per_cat = {c: {"ms": pms[i], "launches": int(pln[i]), "algo_tflops": (pfl[i] / (pms[i] * 1e-3) / 1e12) if pms[i] > 0 else 0.0}
                for i, c in enumerate(cats)}
     # dominant kernel = the single (kind, layer) launch site of the actor with the largest total device time
@@ -338,27 +338,30 @@ def run_ours(args):
     dk, dl = max(sites, key=lambda kl: pms32[kl[0] + 4 * kl[1]])
     di = dk + 4 * dl
     dom_name = f"{['fwd', 'dx', 'dw'][dk]}_layer{dl}"
-    dom_kernel = ["scan_gemm_kernel<FWD>", "scan_gemm_kernel<DX>", "dw_gemm_kernel"][dk] + f" (actor layer {dl})"
+    dom_kernel = ["nm_gemm_kernel<FWD>", "nm_gemm_kernel<DX>" if dl > 0 else "nm_gemm_kernel<DX_ENC>", "dw_gemm_kernel"][dk] + f" (actor layer {dl})"
     achieved = pfl32[di] / (pms32[di] * 1e-3) / 1e12
-    traffic, pipe_pct = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1e_traffic.json")
+    traffic, pipe_pct, smem_pct = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "r1j_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tk = json.load(f)["kernels"].get(dom_name)
         if tk:
             traffic, pipe_pct = tk["dram_bytes_per_launch"], tk["tensor_pipe_active_pct"]
+            smem_pct = tk.get("smem_pipe_tensor_pct", 0.0) + tk.get("smem_pipe_lsu_pct", 0.0)
     tc_ms = pms[0] + pms[1] + pms[2]
     tc_fl = pfl[0] + pfl[1] + pfl[2]
     roofline = {
         "bound": "tensor", "kernel": dom_kernel, "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
         "us_per_launch": 1e3 * pms32[di] / pln32[di], "algo_flops_per_launch": pfl32[di] / pln32[di],
-        "ncu_tensor_pipe_active_pct": pipe_pct,
+        "ncu_tensor_pipe_active_pct": pipe_pct, "ncu_smem_data_pipe_pct": smem_pct,
         "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
         "note": "achieved = ALGORITHMIC flops (2*B*K*N*T per layer GEMM, one product per MAC) / CUDA-event kernel time; "
                 "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC, so issued tensor work is 3x 'achieved'; "
                 "kernel times from an eager re-run of the timed steps (the timed region itself replays CUDA graphs); "
-                "traffic / tensor-pipe % from the committed ncu capture profiles/r1e_*",
+                "traffic / tensor-pipe % / shared-memory data-pipe % from the committed ncu capture profiles/r1j_* "
+                "(the tensor-core kernels are bound by the SM's shared-memory data pipe: operand reads of the MMAs plus the "
+                "bulk-copy / expansion writes that feed them, DESIGN.md 4.6)",
         "all_tensor_kernels": {"ms": tc_ms, "algo_tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
                                "share_of_step": tc_ms / ms_total,
                                "eager_profiled_ms_per_step": ms_prof_total / args.steps},
