@@ -631,7 +631,7 @@ int snn_ppo_head(const float* mu, const float* log_std, const float* value, cons
   }
   LAUNCH_CHECK("ppo_head_kernel");
   { ProfScope prof__(CAT_OTHER, 0.0, st);
-  ppo_head_finalize_kernel<<<1, 128, 0, st>>>(q.part, nblk, A, q.B, log_std, ent_coef, 1.0f, g_log_std, stats);
+  ppo_head_finalize_kernel<<<1, 32 * (4 + A) <= 1024 ? 32 * (4 + A) : 1024, 0, st>>>(q.part, nblk, A, q.B, log_std, ent_coef, 1.0f, g_log_std, stats);
   }
   LAUNCH_CHECK("ppo_head_finalize_kernel");
   return SNN_OK;

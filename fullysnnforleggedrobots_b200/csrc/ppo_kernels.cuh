@@ -127,26 +127,35 @@ __global__ void __launch_bounds__(256) ppo_head_kernel(const PpoHeadParams p) {
 // stats: [0] surrogate mean (local), [1] value-loss mean (local), [2] kl mean (local), [3] entropy mean,
 //        [4] accumulated surrogate, [5] accumulated value loss, [6] number of accumulated steps
 // g_log_std[a] = sum_b(...) - ent_coef / world   (entropy bonus: d(-c * mean_b sum_a log sigma_a)/d log_std = -c)
-__global__ void ppo_head_finalize_kernel(const float* __restrict__ part, int nparts, int A, int B,
-                                         const float* __restrict__ log_std, float ent_coef, float inv_world,
-                                         float* __restrict__ g_log_std, float* __restrict__ stats) {
-  const int i = threadIdx.x;
-  if (i < 3) {
+__global__ void __launch_bounds__(1024) ppo_head_finalize_kernel(const float* __restrict__ part, int nparts, int A, int B,
+                                                                 const float* __restrict__ log_std, float ent_coef, float inv_world,
+                                                                 float* __restrict__ g_log_std, float* __restrict__ stats) {
+  // one warp per column of the partials (3 loss sums, entropy, A log-std gradients): lanes stride over the rows,
+  // fixed-order shuffle reduction in double
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x >> 5; i < 4 + A; i += nwarps) {
+    if (i == 3) {
+      if (lane == 0) {
+        float e = 0.f;
+        for (int a = 0; a < A; ++a) e += 0.5f + kHalfLog2Pi + log_std[a];
+        stats[3] = e;
+      }
+      continue;
+    }
     double acc = 0.0;
-    for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * (4 + A) + i];
-    const float mean = static_cast<float>(acc / B);
-    stats[i] = mean;
-    if (i == 0) stats[4] += mean;
-    if (i == 1) stats[5] += mean;
-    if (i == 2) stats[6] += 1.f;
-  } else if (i == 3) {
-    float e = 0.f;
-    for (int a = 0; a < A; ++a) e += 0.5f + kHalfLog2Pi + log_std[a];
-    stats[3] = e;
-  } else if (i >= 4 && i < 4 + A) {
-    double acc = 0.0;
-    for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * (4 + A) + i];
-    g_log_std[i - 4] = static_cast<float>(acc) - ent_coef * inv_world;
+    for (int s = lane; s < nparts; s += 32) acc += part[static_cast<size_t>(s) * (4 + A) + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane != 0) continue;
+    if (i < 3) {
+      const float mean = static_cast<float>(acc / B);
+      stats[i] = mean;
+      if (i == 0) stats[4] += mean;
+      if (i == 1) stats[5] += mean;
+      if (i == 2) stats[6] += 1.f;
+    } else {
+      g_log_std[i - 4] = static_cast<float>(acc) - ent_coef * inv_world;
+    }
   }
 }
 
@@ -185,9 +194,19 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
                                                        float beta1, float beta2, float eps, float weight_decay,
                                                        float max_norm, float grad_scale, float* __restrict__ norm_out) {
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ double s_tot[8];
+  {
+    // every block re-derives the global norm from the per-block partials (parallel, fixed order)
+    double t = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256) t += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int i = 0; i < nparts; ++i) tot += partial[i];
+    for (int i = 0; i < 8; ++i) tot += s_tot[i];
     const float norm = static_cast<float>(sqrt(tot));
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
