@@ -324,13 +324,16 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const int top = p.L - 1;
   {
     const LayerPlan& lp = p.layer[top];
+    const int nbg = p.Bt / kTopScanSPT;
+    int gpb = kTopScanGPB;
+    while (nbg % gpb) --gpb;                       // T = 5: Bt = 48 -> 6 groups per tile, 3 per block
+    const int nrows = p.ntile * nbg / gpb;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<dim3(p.ntile * (p.Bt / kTopScanSPT), lp.NP / 128), 128, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
+    top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
-                                         p.T, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
+                                         p.T, gpb, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
-    const int nrows = p.ntile * (p.Bt / kTopScanSPT);
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
     df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
     df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);

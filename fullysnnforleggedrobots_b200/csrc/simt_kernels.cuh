@@ -114,6 +114,7 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
 // batch-tile geometry of the actor's time-stepped tensors (plan.cuh): sample-step (t, b) -> tile * CT + t * Bt + b % Bt
 struct TileGeom { int Bt, CT, ntile; long long Rt; };
 constexpr int kTopScanSPT = 8;     // samples per thread of top_scan_kernel (Bt % 16 == 0)
+constexpr int kTopScanGPB = 4;     // at most this many sample groups per block (the launch picks a divisor of Bt / SPT)
 
 // TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T.
 // Thread = (sample, spike word): it evaluates the word's 32 encoder neurons (independent chains -> ILP, no
@@ -225,27 +226,34 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
 // steps in registers; writes the g_c hi/lo planes (swz64 image, rows = sample-steps) and per-tile partials of the bias gradient and of
 // the decoder gradients:  dec_part[tile][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
 // dec_part[tile][1][n] = sum_b G[b,a(n)]  (d bias, read at n = a * P).
-__global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+__global__ void __launch_bounds__(128 * kTopScanGPB) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                       int dec_tanh, const float* __restrict__ dec_w,
                                                       const float* __restrict__ volt, int B, TileGeom tg, int A, int P,
-                                                      int NP, int T, uint8_t* __restrict__ g_img, size_t g_plane,
+                                                      int NP, int T, int gpb, uint8_t* __restrict__ g_img, size_t g_plane,
                                                       float* __restrict__ db_part /* [gridDim.x][NP] */,
                                                       float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
-  // grid (ntile * Bt / SPT, NP / 128): one block per (tile, SPT-sample group); a warp reads / writes 32 consecutive
-  // neurons of one sample-step per request.  SPT = 8 keeps the per-thread state small (more resident warps: the
-  // kernel is a chain of dependent loads and recurrences per thread, i.e. latency-bound).
+  // grid (ntile * Bt / (SPT * gpb), NP / 128), block 128 * gpb: thread = (neuron, SPT-sample group), gpb groups per
+  // block (their three per-neuron sums are added in shared memory, fixed order).  A warp reads / writes 32
+  // consecutive neurons of one sample-step per request.  SPT = 8 keeps the per-thread state small (more resident
+  // warps: the kernel is a chain of dependent loads and recurrences per thread, i.e. latency-bound).
   constexpr int SPT = kTopScanSPT;
+  __shared__ float s_red[kTopScanGPB][3][128];
   const int nbg = tg.Bt / SPT;
-  const int tile = blockIdx.x / nbg, bg_only = blockIdx.x - tile * nbg;
-  const int n = blockIdx.y * 128 + threadIdx.x;
+  const int sub = threadIdx.x >> 7, tx = threadIdx.x & 127;
+  const int grp = blockIdx.x * gpb + sub;                    // global sample-group index
+  const int tile = grp / nbg, bg_only = grp - tile * nbg;
+  const int n = blockIdx.y * 128 + tx;
   const bool n_live = n < A * P;
   const int a = n_live ? n / P : 0;
   const float wn = n_live ? dec_w[n] : 0.f;
   const float Tf = static_cast<float>(T);
   const size_t c_tile = static_cast<size_t>(tile) * tg.CT;
   const int TB = T * tg.Bt;
-  uint8_t* const gcol = g_img + static_cast<size_t>(n >> 6) * tg.Rt * 128 + (n & 7) * 2;     // see nm_gemm.cuh (dX epilogue)
-  const int cn = (n & 63) >> 3;
+  // g_c image [NP/64][Rt rows][128 B], see the dX epilogue of nm_gemm.cuh
+  uint8_t* const gcol = g_img + static_cast<size_t>(n >> 6) * tg.Rt * 128;
+  uint32_t xo[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
   const size_t vstep = static_cast<size_t>(tg.Bt) * 32;                                      // floats between timesteps
   float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
   {
@@ -277,6 +285,7 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
       }
       const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);          // % 8 == 0
       uint8_t* const dst = gcol + (c >> 3) * 1024;
+      float gc[SPT];
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
         const bool live = b0 + j < B;
@@ -286,13 +295,20 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
         const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
         const float keep = vj > 0.5f ? 0.f : 0.75f;
         const float gv = gs * win + gvn[j] * keep;
-        const float gc = gv + 0.5f * gcn[j];
-        gvn[j] = gv; gcn[j] = gc;
-        dbsum += gc;
-        const float hi = bf16_round(gc);
-        uint8_t* q = dst + (j >> 3) * 1024 + (j & 7) * 128 + ((cn ^ (j & 7)) << 4);
-        *reinterpret_cast<uint16_t*>(q) = static_cast<uint16_t>(__float_as_uint(hi) >> 16);
-        *reinterpret_cast<uint16_t*>(q + g_plane) = static_cast<uint16_t>(__float_as_uint(bf16_round(gc - hi)) >> 16);
+        gc[j] = gv + 0.5f * gcn[j];
+        gvn[j] = gv; gcn[j] = gc[j];
+        dbsum += gc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < SPT; j += 2) {
+        const uint32_t hp = pack_bf16x2(gc[j], gc[j + 1]);
+        const uint32_t lp = pack_bf16x2(gc[j] - __uint_as_float(hp << 16), gc[j + 1] - __uint_as_float(hp & 0xFFFF0000u));
+        uint8_t* q0 = dst + xo[j];
+        uint8_t* q1 = dst + xo[j + 1];
+        *reinterpret_cast<uint16_t*>(q0) = static_cast<uint16_t>(hp);
+        *reinterpret_cast<uint16_t*>(q1) = static_cast<uint16_t>(hp >> 16);
+        *reinterpret_cast<uint16_t*>(q0 + g_plane) = static_cast<uint16_t>(lp);
+        *reinterpret_cast<uint16_t*>(q1 + g_plane) = static_cast<uint16_t>(lp >> 16);
       }
     }
 #pragma unroll
@@ -304,16 +320,22 @@ __global__ void __launch_bounds__(128) top_scan_kernel(const float* __restrict__
   // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
   for (int cc = TB + bg_only; cc < tg.CT; cc += nbg) {
     const size_t r = c_tile + cc;
-    uint8_t* q = gcol + (r >> 3) * 1024 + (r & 7) * 128 + ((cn ^ static_cast<int>(r & 7)) << 4);
+    uint8_t* q = gcol + (r >> 3) * 1024 + xo[r & 7];
     *reinterpret_cast<uint16_t*>(q) = 0;
     *reinterpret_cast<uint16_t*>(q + g_plane) = 0;
   }
-  db_part[static_cast<size_t>(blockIdx.x) * NP + n] = dbsum;
-  dec_part[(static_cast<size_t>(blockIdx.x) * 2) * NP + n] = dwd;
-  dec_part[(static_cast<size_t>(blockIdx.x) * 2 + 1) * NP + n] = dbd;
+  s_red[sub][0][tx] = dbsum;
+  s_red[sub][1][tx] = dwd;
+  s_red[sub][2][tx] = dbd;
+  __syncthreads();
+  if (sub == 0) {
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    for (int g = 0; g < gpb; ++g) { r0 += s_red[g][0][tx]; r1 += s_red[g][1][tx]; r2 += s_red[g][2][tx]; }
+    db_part[static_cast<size_t>(blockIdx.x) * NP + n] = r0;
+    dec_part[(static_cast<size_t>(blockIdx.x) * 2) * NP + n] = r1;
+    dec_part[(static_cast<size_t>(blockIdx.x) * 2 + 1) * NP + n] = r2;
+  }
 }
-
-// (decoder gradients are produced by top_scan_kernel)
 
 // ------------------------------------------------------------------ encoder input gradient
 // (the encoder PARAMETER gradients are produced by the DX_ENC epilogue, nm_gemm.cuh)
