@@ -108,7 +108,16 @@ int device_ready(int* num_sms) {
   return SNN_OK;
 }
 
+constexpr int kMlpMaxCtasDefault = 0;      // 0 = no cap
 unsigned long long* g_dbg_out = nullptr;   // set by snn_debug_set_cycle_buffer (tools only)
+
+// SMs the dense critic's kernels may occupy.  In the fused PPO step they run on a second stream next to the actor's
+// persistent one-CTA-per-SM kernels: a critic grid as wide as the machine takes whole waves of SMs away from them.
+int mlp_sms(int sms) {
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("SNN_MLP_MAX_CTAS"); cap = e ? atoi(e) : kMlpMaxCtasDefault; }
+  return cap > 0 && cap < sms ? cap : sms;
+}
 
 int debug_mask() {
   static int m = -1;
@@ -515,7 +524,7 @@ int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
     q.dbg = 0;
     q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
     q.g_img = at(trace, lp.tr_h); q.g_plane = lp.tr_h_plane;
-    const int grid = q.nitems < sms ? q.nitems : sms;
+    const int grid = q.nitems < mlp_sms(sms) ? q.nitems : mlp_sms(sms);
     { ProfScope prof__(CAT_FWD + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
     scan_gemm_kernel<MODE_MLP_FWD><<<grid, ScanCfg<MODE_MLP_FWD>::THREADS, scan_gemm_smem_bytes<MODE_MLP_FWD>(128), st>>>(q);
     }
@@ -576,7 +585,7 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       q.n_tiles = (lp.KP + 255) / 256;
       q.rblocks = Bp / 64;
       const int tiles = (lp.NP / 128) * q.n_tiles;
-      int splits = sms / tiles;
+      int splits = mlp_sms(sms) / tiles;
       if (splits < 1) splits = 1;
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
@@ -600,7 +609,7 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
       q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
       q.db_part = dbpart_of(l - 1);
-      const int grid = q.nitems < sms ? q.nitems : sms;
+      const int grid = q.nitems < mlp_sms(sms) ? q.nitems : mlp_sms(sms);
       { ProfScope prof__(CAT_DX + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
       scan_gemm_kernel<MODE_MLP_DX><<<grid, ScanCfg<MODE_MLP_DX>::THREADS, scan_gemm_smem_bytes<MODE_MLP_DX>(128), st>>>(q);
       }

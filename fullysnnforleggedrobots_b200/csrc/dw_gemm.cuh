@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const int rb0 = split * per, rb1 = min(p.rblocks, rb0 + per);
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], DENSE ? 1 : 2); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], DENSE ? 1 : 3); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kDwBitStages; ++s) { mbar_init(&full_bits[s], 1); mbar_init(&empty_bits[s], 2); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -160,39 +160,35 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     }
     if (rb1 <= rb0 && elect_one()) umma_commit(acc_full);
   } else if (warp >= 4) {
-    // spike-bit expanders: warp ew (< kStages) owns ring slot ew, i.e. every kStages-th stage, and expands all of
-    // it (64 rows x nck k-chunks).  One warp per slot keeps each slot's uses in order: a warp can never wait on an
-    // mbarrier phase that is two phases ahead (parity aliasing).  Warps 4-7 run the epilogue afterwards.
-    const int ew = warp - 4;
+    // spike-bit expanders: warps 4 .. 4 + 2 * kStages - 1.  Ring slot ew is owned by the warp PAIR (ew, ew + kStages),
+    // each expanding 32 of the stage's 64 sample-steps (all nck k-chunks).  A fixed owner per slot keeps each slot's
+    // uses in order: a warp can never wait on an mbarrier phase that is two phases ahead (parity aliasing).  The
+    // expansion is the slowest role of this kernel, hence two warps per slot.  Warps 4-7 run the epilogue afterwards.
+    const int ew = (warp - 4) % kStages, hsel = (warp - 4) / kStages;
+    const bool expands = !DENSE && warp < 4 + 2 * kStages;
     const int sw = lane & 7;
     uint32_t i = 0;
-    for (int rb = rb0; rb < (DENSE ? rb0 : rb1); ++rb, ++i) {
+    for (int rb = rb0; rb < (expands ? rb1 : rb0); ++rb, ++i) {
       if (static_cast<int>(i % kStages) != ew) continue;
       const uint32_t sbit = i % kDwBitStages;
       SNN_TWAIT(&full_bits[sbit], (i / kDwBitStages) & 1, 0);
       const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + sbit * kDwBitStageBytes);
-      uint32_t w[2][8];
+      const int row = lane + 32 * hsel;
+      uint32_t w[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) w[h][u] = (u < 2 * nck) ? wsrc[u * 64 + lane + 32 * h] : 0u;
+      for (int u = 0; u < 8; ++u) w[u] = (u < 2 * nck) ? wsrc[u * 64 + row] : 0u;
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bits[sbit]);
       const uint32_t s = i % kStages;
       SNN_TWAIT(&empty[s], ((i / kStages) & 1) ^ 1, 1);
-      uint8_t* bst = ring + s * kStageBytes + 32768;
+      uint8_t* rbase = ring + s * kStageBytes + 32768 + (row >> 3) * 1024 + sw * 128;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = lane + 32 * h;
-        uint8_t* rbase = bst + (row >> 3) * 1024 + sw * 128;
+      for (int kcl = 0; kcl < 4; ++kcl) {
+        if (kcl < nck) {
 #pragma unroll
-        for (int kcl = 0; kcl < 4; ++kcl) {
-          if (kcl < nck) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t byte = ((j < 4 ? w[h][2 * kcl] : w[h][2 * kcl + 1]) >> ((j & 3) * 8)) & 0xFFu;
-              *reinterpret_cast<uint4*>(rbase + kcl * 8192 + ((j ^ sw) << 4)) = expand_spike_byte(byte);
-            }
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t byte = ((j < 4 ? w[2 * kcl] : w[2 * kcl + 1]) >> ((j & 3) * 8)) & 0xFFu;
+            *reinterpret_cast<uint4*>(rbase + kcl * 8192 + ((j ^ sw) << 4)) = expand_spike_byte(byte);
           }
         }
       }
