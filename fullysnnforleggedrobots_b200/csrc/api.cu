@@ -334,8 +334,10 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   {
     const LayerPlan& lp = p.layer[top];
     const int nbg = p.Bt / kTopScanSPT;
-    int gpb = kTopScanGPB;
-    while (nbg % gpb) --gpb;                       // T = 5: Bt = 48 -> 6 groups per tile, 3 per block
+    static int gpb_max = -1;
+    if (gpb_max < 0) { const char* e = getenv("SNN_TOPSCAN_GPB"); gpb_max = e ? atoi(e) : 1; if (gpb_max < 1 || gpb_max > kTopScanGPB) gpb_max = kTopScanGPB; }
+    int gpb = gpb_max;
+    while (nbg % gpb) --gpb;                       // T = 5: Bt = 48 -> 6 groups per tile
     const int nrows = p.ntile * nbg / gpb;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,

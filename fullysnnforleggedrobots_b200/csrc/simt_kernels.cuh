@@ -114,7 +114,8 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
 // batch-tile geometry of the actor's time-stepped tensors (plan.cuh): sample-step (t, b) -> tile * CT + t * Bt + b % Bt
 struct TileGeom { int Bt, CT, ntile; long long Rt; };
 constexpr int kTopScanSPT = 8;     // samples per thread of top_scan_kernel (Bt % 16 == 0)
-constexpr int kTopScanGPB = 4;     // at most this many sample groups per block (the launch picks a divisor of Bt / SPT)
+constexpr int kTopScanGPB = 4;     // at most this many sample groups per block; the launch uses 1 (measured: more
+                                   // groups per block = fewer partial rows to reduce, but fewer resident warps — a wash)
 
 // TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T.
 // Thread = (sample, spike word): it evaluates the word's 32 encoder neurons (independent chains -> ILP, no
@@ -384,8 +385,19 @@ __global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs j
   const int i = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x * 32 >= jb.n) return;
   float acc = 0.f;
-  if (i < jb.n)
-    for (int s = threadIdx.y; s < jb.nparts; s += 32) acc += jb.src[static_cast<size_t>(s) * jb.stride + static_cast<size_t>(i) * jb.col_step];
+  if (i < jb.n) {
+    // eight independent loads in flight per thread (the kernel is pure load latency); fixed summation order
+    const float* src = jb.src + static_cast<size_t>(i) * jb.col_step;
+    int s = threadIdx.y;
+    for (; s + 7 * 32 < jb.nparts; s += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[static_cast<size_t>(s + u * 32) * jb.stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; s < jb.nparts; s += 32) acc += src[static_cast<size_t>(s) * jb.stride];
+  }
   __shared__ float sh[32][33];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
