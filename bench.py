@@ -374,8 +374,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3 planes (fp32-parity), fp32 accumulate", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": W["name"], **{k: v for k, v in W.items() if k != "name"},
+                   "arithmetic": "fp32-parity: weights as three exact bf16 planes (hi+mid+lo == W), spikes exact, fp32 "
+                                 "accumulation on the tensor cores; backward operands as hi/lo bf16 pairs (3 products)",
                    "parallelism": f"dp{world}", "envs_per_gpu": N,
                    "l2": "inputs larger than L2: 54 MB rollout + 0.3 GB traces per minibatch vs 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,

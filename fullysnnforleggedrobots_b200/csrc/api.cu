@@ -94,7 +94,7 @@ int device_ready(int* num_sms) {
                                   static_cast<int>(nm_gemm_smem_bytes<NM_DX>())));
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(nm_gemm_smem_bytes<NM_DX_ENC>())));
-    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(dw_gemm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
     CUDA_TRY(cudaFuncSetAttribute(dw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kDwSmemBytes)));
@@ -342,39 +342,18 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
                                          reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
-                                         p.T, gpb, at(workspace, p.ws_g[0]), p.ws_g_plane[0], dbpart_of(top), small);
+                                         p.T, gpb, at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
     }
     LAUNCH_CHECK("top_scan_kernel");
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
     df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
     df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
   }
-  // ---- walk down the layers
+  // ---- walk down the layers: dX_l + scan of the layer below; the weight gradients follow in one launch
   for (int l = top; l >= 0; --l) {
     const LayerPlan& lp = p.layer[l];
-    const int slot = (p.L - 1 - l) & 1;
-    const uint8_t* G = at(workspace, p.ws_g[slot]);
-    const size_t Gplane = p.ws_g_plane[slot];
-    {   // dW_l
-      DwGemmParams q{};
-      q.g_img = G; q.g_plane = Gplane;
-      q.x_bits = l == 0 ? enc_bits : reinterpret_cast<const uint32_t*>(at(trace, p.layer[l - 1].tr_bits));
-      q.NP = lp.NP; q.KP = lp.KP; q.R = p.Rt;
-      q.n_tiles = (lp.KP + 255) / 256;
-      q.rblocks = static_cast<int>(p.Rt / 64);
-      const int tiles = (lp.NP / 128) * q.n_tiles;
-      int splits = sms / tiles;
-      if (splits < 1) splits = 1;
-      if (splits > q.rblocks) splits = q.rblocks;
-      q.splits = splits;
-      q.partial = partial_of(l);
-      q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(4 + l) * 148 * 16 : nullptr;
-      { ProfScope prof__(CAT_DW + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-      dw_gemm_kernel<false><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
-      }
-      LAUNCH_CHECK("dw_gemm_kernel");
-      df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
-    }
+    const uint8_t* G = at(workspace, p.ws_g[l]);
+    const size_t Gplane = p.ws_g_plane[l];
     {   // dX_l + scan of the layer below (or of the encoder)
       NmParams q{};
       nm_geometry(p, B, &q);
@@ -386,8 +365,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       if (l > 0) {
         const LayerPlan& lo = p.layer[l - 1];
         q.v_in = reinterpret_cast<const float*>(at(trace, lo.tr_volt));
-        q.g_img = at(workspace, p.ws_g[slot ^ 1]);
-        q.g_plane = p.ws_g_plane[slot ^ 1];
+        q.g_img = at(workspace, p.ws_g[l - 1]);
+        q.g_plane = p.ws_g_plane[l - 1];
         q.db_part = dbpart_of(l - 1);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         nm_gemm_kernel<NM_DX><<<grid, NmCfg<NM_DX>::THREADS, nm_gemm_smem_bytes<NM_DX>(), st>>>(q);
@@ -407,6 +386,40 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         LAUNCH_CHECK("nm_gemm_kernel<DX_ENC>");
       }
     }
+  }
+  // ---- dW of all layers: one launch, CTAs split over the layers in proportion to their work
+  {
+    DwJobs jobs{};
+    jobs.count = p.L;
+    double work[SNN_MAX_LAYERS], total = 0.0;
+    for (int l = 0; l < p.L; ++l) { work[l] = static_cast<double>(p.layer[l].NP / 128) * (p.layer[l].KP / 64); total += work[l]; }
+    int cta = 0;
+    double flops = 0.0;
+    for (int l = 0; l < p.L; ++l) {
+      const LayerPlan& lp = p.layer[l];
+      DwGemmParams& q = jobs.j[l];
+      q.g_img = at(workspace, p.ws_g[l]); q.g_plane = p.ws_g_plane[l];
+      q.x_bits = l == 0 ? enc_bits : reinterpret_cast<const uint32_t*>(at(trace, p.layer[l - 1].tr_bits));
+      q.NP = lp.NP; q.KP = lp.KP; q.R = p.Rt;
+      q.n_tiles = (lp.KP + 255) / 256;
+      q.rblocks = static_cast<int>(p.Rt / 64);
+      const int tiles = (lp.NP / 128) * q.n_tiles;
+      int splits = static_cast<int>(sms * (work[l] / total)) / tiles;
+      if (splits < 1) splits = 1;
+      if (splits > q.rblocks) splits = q.rblocks;
+      q.splits = splits;
+      q.partial = partial_of(l);
+      q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(4 + l) * 148 * 16 : nullptr;
+      jobs.first_cta[l] = cta;
+      cta += tiles * splits;
+      flops += 2.0 * B * lp.K * lp.N * p.T;
+      df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
+    }
+    jobs.first_cta[p.L] = cta;
+    { ProfScope prof__(CAT_DW, flops, st);
+    dw_gemm_multi_kernel<<<cta, 384, kDwSmemBytes, st>>>(jobs);
+    }
+    LAUNCH_CHECK("dw_gemm_multi_kernel");
   }
   // ---- d obs (the encoder parameter gradients came out of the DX_ENC epilogue, the decoder's out of top_scan_kernel)
   {

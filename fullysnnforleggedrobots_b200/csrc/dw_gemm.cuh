@@ -49,7 +49,7 @@ constexpr size_t kDwSmemBytes = 1024 + kDwStages * kDwStageBytes + kDwBitStages 
 // DENSE = false: B operand = spike bits expanded in smem (3 stages of 64 KiB).
 // DENSE = true : B operand = hi/lo planes bulk-copied like A (2 stages of 96 KiB), three products.
 template <bool DENSE>
-__global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
+__device__ __forceinline__ void dw_gemm_body(const DwGemmParams& p, const int cta) {
   constexpr int kStages = DENSE ? 2 : 3;
   constexpr int kStageBytes = DENSE ? 98304 : 65536;
   extern __shared__ uint8_t smem_raw[];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
-  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
+  const int tile = cta / p.splits, split = cta - tile * p.splits;
   const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
   const int kc0 = nt * 4;                                   // first 64-wide k chunk of this tile
   const int nck = min(4, p.KP / 64 - kc0);                  // k chunks in this tile
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     if (warp < 8) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      float* out = p.partial + (static_cast<size_t>(blockIdx.x) * 128 + row) * 256;
+      float* out = p.partial + (static_cast<size_t>(cta) * 128 + row) * 256;
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
       const bool any = rb1 > rb0;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
   }
   if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 3);
-    unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
+    unsigned long long* o = p.dbg_out + static_cast<size_t>(cta) * 16 + role * 4;
     o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
     o[3] = static_cast<unsigned long long>(clock64() - t_start);
   }
@@ -228,6 +228,21 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(384, 1) dw_gemm_kernel(const DwGemmParams p) {
+  dw_gemm_body<DENSE>(p, static_cast<int>(blockIdx.x));
+}
+
+// The weight gradients of ALL spiking layers in one launch: CTA c belongs to the job (layer) whose range contains
+// it.  Every dW launch pays ~14 us of fixed cost (pipeline fill, accumulator drain, 128 KiB partial tile store per
+// CTA) that dominates the narrow upper layers; one launch pays it once and balances the layers over the SMs.
+struct DwJobs { DwGemmParams j[SNN_MAX_LAYERS]; int first_cta[SNN_MAX_LAYERS + 1]; int count; };
+__global__ void __launch_bounds__(384, 1) dw_gemm_multi_kernel(const DwJobs jobs) {
+  int l = 0;
+  while (l + 1 < jobs.count && static_cast<int>(blockIdx.x) >= jobs.first_cta[l + 1]) ++l;
+  dw_gemm_body<false>(jobs.j[l], static_cast<int>(blockIdx.x) - jobs.first_cta[l]);
 }
 
 // dW[n][k] = sum_s partial[(tile * splits + s)][n % 128][k % 256]; also reduces the per-CTA bias partials.

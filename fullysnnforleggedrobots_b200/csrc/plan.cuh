@@ -68,8 +68,8 @@ struct SnnPlan {
   size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][Rt]
   size_t trace_bytes;
   // backward workspace
-  size_t ws_g[2];           // two ping-pong g_c buffers (swz64 images [NP/64][Rt rows], 2 planes each)
-  size_t ws_g_plane[2];
+  size_t ws_g[SNN_MAX_LAYERS];        // g_c of every layer (swz64 images [NP/64][Rt rows], 2 planes each): all of them
+  size_t ws_g_plane[SNN_MAX_LAYERS];  // stay alive until the single dW launch at the end of the backward pass
   size_t ws_ga;             // fp32 [Bcap/16][K0P][16]  d loss / d pop_act
   size_t ws_partial, ws_partial_stride;   // fp32 split-K partials of dW, one region per layer
   size_t ws_dbpart, ws_dbpart_stride;     // fp32 partial bias grads, one region per layer
@@ -128,13 +128,10 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.trace_bytes = off;
   // backward workspace
   off = 0;
-  size_t gmax[2] = {0, 0};
   for (int l = 0; l < p.L; ++l) {
-    const size_t plane = static_cast<size_t>(p.layer[l].NP) * p.Rt * 2;
-    const int slot = (p.L - 1 - l) & 1;
-    if (plane > gmax[slot]) gmax[slot] = plane;
+    p.ws_g_plane[l] = static_cast<size_t>(p.layer[l].NP) * p.Rt * 2;
+    p.ws_g[l] = take(2 * p.ws_g_plane[l]);
   }
-  for (int s = 0; s < 2; ++s) { p.ws_g_plane[s] = gmax[s]; p.ws_g[s] = take(2 * gmax[s]); }
   p.ws_ga = take(static_cast<size_t>(p.Bcap) * p.K0P * 4);
   p.dw_max_ctas = num_sms > 0 ? 2 * num_sms : 296;
   const int row_parts = 3 * (num_sms > 0 ? num_sms : 148);      // rows of per-CTA partials of the dX kernels (3 per CTA)
