@@ -20,6 +20,8 @@ the reference's op-by-op structure through torch autograd, still on the same ker
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import torch
@@ -68,7 +70,8 @@ class PPO:
         self.fused_critic = fused_critic
         self.act_cuda_graph = use_cuda_graph   # rollout step (act) replayed as one CUDA graph
         self._act_state = None
-        self.overlap_critic = True          # critic kernels on a second stream (parallel CUDA-graph branch)
+        # critic kernels on a second stream (parallel CUDA-graph branch); SNN_OVERLAP_CRITIC=0 serialises them
+        self.overlap_critic = os.environ.get("SNN_OVERLAP_CRITIC", "1") != "0"
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
