@@ -3,6 +3,7 @@
 Public surface mirrors rsl_rl's for this path only:
     ActorCritic, PopSpikeActor      modules/actor_critic.py of the four reference forks
     PPO, RolloutStorage             algorithms/ppo.py, storage/rollout_storage.py
+    AMPPPO (+ discriminator, replay) algorithms/amp_ppo.py of the AMP fork
 """
 from . import _lib  # noqa: F401
 from .actor import PopSpikeActor  # noqa: F401
@@ -10,7 +11,8 @@ from .actor_critic import (ActorCritic, ActorCriticAMP, ActorCriticCassie, Actor
                            ActorCriticRMA, VARIANTS)
 from .engine import CriticEngine, SnnEngine, gae  # noqa: F401
 from .ppo import PPO, PPORMA  # noqa: F401
+from .amp import AMPPPO, AMPDiscriminator, Normalizer, ReplayBuffer  # noqa: F401
 from .storage import RolloutStorage, RolloutStorageRMA  # noqa: F401
 
 __all__ = ["PopSpikeActor", "SnnEngine", "CriticEngine", "gae", "ActorCritic", "ActorCriticAMP", "ActorCriticCassie",
-           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "RolloutStorage", "RolloutStorageRMA"]
+           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "AMPPPO", "AMPDiscriminator", "ReplayBuffer", "Normalizer", "RolloutStorage", "RolloutStorageRMA"]

@@ -159,3 +159,60 @@ def make_ppo_rollout(pc: PPOCase):
         "noise": torch.randn(S, N, pc.act_dim, generator=g),
         "last_obs": torch.randn(N, pc.obs_dim, generator=g),
     }
+
+
+# --------------------------------------------------------------------------- AMP PPO update case
+AMP_CASE = PPOCase(name="amp_ppo_tiny", variant="amp", seed=22)
+AMP_OBS_DIM = 5
+AMP_DISC_HIDDEN = (32, 16)
+AMP_REWARD_COEF = 2.0
+AMP_MIN_STD = 1.2            # above init_noise_std = 1.0, so the clamp is observable on ActorCritic.std
+AMP_POOL = 64
+
+
+def make_amp_inputs(pc: PPOCase):
+    """Seeded AMP observations of the rollout (state at t, state at t+1), the expert pool and the discriminator."""
+    g = torch.Generator().manual_seed(6000 + pc.seed)
+    S, N, D = pc.num_steps, pc.num_envs, AMP_OBS_DIM
+    out = {
+        "amp_obs": torch.randn(S + 1, N, D, generator=g) * 1.5 + 0.3,
+        "expert_state": torch.randn(AMP_POOL, D, generator=g) * 0.7 - 0.2,
+        "expert_next": torch.randn(AMP_POOL, D, generator=g) * 0.7 - 0.1,
+    }
+    dims = [2 * D] + list(AMP_DISC_HIDDEN)
+    sd = {}
+    for i in range(len(dims) - 1):
+        b = 1.0 / math.sqrt(dims[i])
+        sd[f"trunk.{2 * i}.weight"] = _uniform(g, (dims[i + 1], dims[i]), b)
+        sd[f"trunk.{2 * i}.bias"] = _uniform(g, (dims[i + 1],), b)
+    b = 1.0 / math.sqrt(dims[-1])
+    sd["amp_linear.weight"] = _uniform(g, (1, dims[-1]), b)
+    sd["amp_linear.bias"] = _uniform(g, (1,), b)
+    out["disc_state_dict"] = sd
+    return out
+
+
+class ExpertPool:
+    """Deterministic stand-in for the reference's AMPLoader (needs pybullet_utils + mocap files): same
+    `feed_forward_generator(num_mini_batch, mini_batch_size)` surface, rows picked by a fixed rule."""
+
+    def __init__(self, state, next_state):
+        self.state, self.next_state = state, next_state
+
+    def feed_forward_generator(self, num_mini_batch, mini_batch_size):
+        n = self.state.shape[0]
+        for k in range(num_mini_batch):
+            idx = (torch.arange(mini_batch_size, device=self.state.device) * 5 + 11 * k) % n
+            yield self.state[idx], self.next_state[idx]
+
+
+def deterministic_replay_generator(buf):
+    """Replacement for ReplayBuffer.feed_forward_generator (random in both implementations) with a fixed index rule,
+    installed on the reference's buffer by make_golden_amp.py and on ours by the tests."""
+
+    def gen(num_mini_batch, mini_batch_size):
+        for k in range(num_mini_batch):
+            idx = (torch.arange(mini_batch_size, device=buf.states.device) * 3 + 7 * k) % buf.num_samples
+            yield buf.states[idx], buf.next_states[idx]
+
+    return gen
