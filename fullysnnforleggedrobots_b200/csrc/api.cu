@@ -116,7 +116,7 @@ unsigned long long* g_dbg_out = nullptr;   // set by snn_debug_set_cycle_buffer 
 int mlp_sms(int sms) {
   static int cap = -1;
   if (cap < 0) { const char* e = getenv("SNN_MLP_MAX_CTAS"); cap = e ? atoi(e) : kMlpMaxCtasDefault; }
-  return cap > 0 && cap < sms ? cap : sms;
+  return cap > 0 ? cap : sms;      // cap > SM count: one item per CTA (short CTAs that free their SM early)
 }
 
 int debug_mask() {
@@ -600,7 +600,7 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       q.n_tiles = (lp.KP + 255) / 256;
       q.rblocks = Bp / 64;
       const int tiles = (lp.NP / 128) * q.n_tiles;
-      int splits = mlp_sms(sms) / tiles;
+      int splits = (mlp_sms(sms) < sms ? mlp_sms(sms) : sms) / tiles;
       if (splits < 1) splits = 1;
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;

@@ -83,7 +83,7 @@ struct NmParams {
   int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
   int nstg;                 // FWD: staging buffers (1 or 2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
-                            // 16 = dX: no g_c stores, 32 = dX: no voltage loads
+                            // 16 = dX: no g_c stores, 32 = dX: no voltage loads, 128 = FWD: no voltage stores, 256 = FWD: no spike-word stores
   unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
 };
 
@@ -491,9 +491,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
               if (lane == j) myword = w;
             }
             const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
-            if (lane < 16)
+            if (lane < 16 && !(p.dbg & 256))
               p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
-            if (p.v_out != nullptr) {
+            if (p.v_out != nullptr && !(p.dbg & 128)) {
               // [neuron / 32][sample-step][32]: this warp's 16 sample-steps are 16 consecutive 128-byte rows
               float* dst = p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32 + lane;
 #pragma unroll

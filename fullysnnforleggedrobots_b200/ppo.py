@@ -72,6 +72,10 @@ class PPO:
         self._act_state = None
         # critic kernels on a second stream (parallel CUDA-graph branch); SNN_OVERLAP_CRITIC=0 serialises them
         self.overlap_critic = os.environ.get("SNN_OVERLAP_CRITIC", "1") != "0"
+        # capture the actor chain on a high-priority stream: where both chains have thread blocks pending, the
+        # actor's (the critical path) are placed first (measured: 14.96 -> 14.61 ms per update; SNN_ACTOR_PRIO=0: off)
+        self.actor_high_priority = os.environ.get("SNN_ACTOR_PRIO", "1") != "0"
+        self._hp_stream = None
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -358,10 +362,17 @@ class PPO:
         self._restore(snap)
         g = torch.cuda.CUDAGraph()
         n0 = _lib.lib().snn_launch_count()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, **self._graph_kw()):
             fn()
         self._restore(snap)
         return g, int(_lib.lib().snn_launch_count() - n0)
+
+    def _graph_kw(self):
+        if not self.actor_high_priority:
+            return {}
+        if self._hp_stream is None:
+            self._hp_stream = torch.cuda.Stream(device=self.optimizer.flat_params.device, priority=-1)
+        return {"stream": self._hp_stream}
 
     def _run_fast_dp(self, f, i):
         """Data parallel: graph A (everything up to the local gradients) -> eager NCCL all-reduce of the flat bucket
@@ -404,7 +415,7 @@ class PPO:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.lib().snn_launch_count()
             try:
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, **self._graph_kw()):
                     self._step_fast(f, i)
             except Exception as e:  # noqa: BLE001
                 print(f"[PPO] CUDA graph capture failed ({e}); falling back to eager fused steps")

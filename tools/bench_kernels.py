@@ -13,9 +13,10 @@ from fullysnnforleggedrobots_b200 import PopSpikeActor, _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24576
 dims = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [48, 256, 256, 12]
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+PL = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 reps = 5
 torch.manual_seed(0)
-actor = PopSpikeActor(dims[0], dims[-1], 10, 10, dims[1:-1], (-5, 5), math.sqrt(0.15), spike_ts=T).cuda()
+actor = PopSpikeActor(dims[0], dims[-1], 10, 10, dims[1:-1], (-5, 5), math.sqrt(0.15), spike_ts=T, fwd_planes=PL).cuda()
 obs = torch.randn(B, dims[0], device="cuda")
 G = torch.randn(B, dims[-1], device="cuda")
 L = _lib.lib()
@@ -38,7 +39,7 @@ ms, fl, ln = (C.c_double * 32)(), (C.c_double * 32)(), (C.c_int64 * 32)()
 L.snn_profile_read(ms, fl, ln)
 L.snn_profile_enable(0)
 names = ["fwd", "dx", "dw", "other"]
-print(f"B={B} dims={dims} T={T} SNN_DBG={os.environ.get('SNN_DBG', '0')}")
+print(f"B={B} dims={dims} T={T} fwd_planes={PL} SNN_DBG={os.environ.get('SNN_DBG', '0')}")
 tot = 0.0
 for l in range(8):
     for k in range(4):
