@@ -348,6 +348,16 @@ def run_ours(args):
         if tk:
             traffic, pipe_pct = tk["dram_bytes_per_launch"], tk["tensor_pipe_active_pct"]
             smem_pct = tk.get("smem_pipe_tensor_pct", 0.0) + tk.get("smem_pipe_lsu_pct", 0.0)
+    # secondary bound: HBM.  ncu DRAM bytes per launch (committed capture) over this run's CUDA-event kernel times.
+    hbm_view = {}
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tks = json.load(f)["kernels"]
+        for name, v in per_layer.items():
+            tkk = tks.get(name)
+            if tkk and v["us_per_launch"] > 0:
+                gbs = tkk["dram_bytes_per_launch"] / (v["us_per_launch"] * 1e-6) / 1e9
+                hbm_view[name] = {"dram_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
     tc_ms = pms[0] + pms[1] + pms[2]
     tc_fl = pfl[0] + pfl[1] + pfl[2]
     roofline = {
@@ -365,6 +375,9 @@ def run_ours(args):
         "all_tensor_kernels": {"ms": tc_ms, "algo_tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
                                "share_of_step": tc_ms / ms_total,
                                "eager_profiled_ms_per_step": ms_prof_total / args.steps},
+        "hbm_view": {"peak_gbs": pk["hbm_gbs"], "per_kernel": hbm_view,
+                     "note": "the dX kernels of the hidden layers stream fp32 voltage traces and two bf16 g_c planes and run at "
+                             "~0.7 of the HBM copy peak; the training forward is limited by trace WRITES (DESIGN.md 4.6)"},
         "per_kernel": per_cat,
         "per_layer": per_layer,
         "critic_tensor_kernels": {"ms": sum(cms[:3]), "launches": int(sum(cln[:3])),

@@ -13,6 +13,8 @@ from .engine import CriticEngine, SnnEngine, gae  # noqa: F401
 from .ppo import PPO, PPORMA  # noqa: F401
 from .amp import AMPPPO, AMPDiscriminator, Normalizer, ReplayBuffer  # noqa: F401
 from .storage import RolloutStorage, RolloutStorageRMA  # noqa: F401
+from .export import export_policy, load_checkpoint, load_policy, save_checkpoint  # noqa: F401
 
 __all__ = ["PopSpikeActor", "SnnEngine", "CriticEngine", "gae", "ActorCritic", "ActorCriticAMP", "ActorCriticCassie",
-           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "AMPPPO", "AMPDiscriminator", "ReplayBuffer", "Normalizer", "RolloutStorage", "RolloutStorageRMA"]
+           "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "AMPPPO", "AMPDiscriminator", "ReplayBuffer", "Normalizer", "RolloutStorage", "RolloutStorageRMA",
+           "export_policy", "load_policy", "save_checkpoint", "load_checkpoint"]

@@ -243,6 +243,7 @@ class AMPPPO(PPO):
             f, mb = self.storage.permute_once(self.num_mini_batches)
             if self._fast_state is None or self._fast_state["mb"] != mb:
                 self._fast_setup(mb)
+            self.refresh_packed()
             steps = ((lambda i=i: self._run_fast(f, i)) for _ in range(self.num_learning_epochs)
                      for i in range(self.num_mini_batches))
         else:

@@ -437,6 +437,11 @@ class PPO:
         opt = self.optimizer
         opt.flat_params.copy_(snap[0]); opt.exp_avg.copy_(snap[1]); opt.exp_avg_sq.copy_(snap[2])
         opt.step_dev.copy_(snap[3]); opt.lr_dev.copy_(snap[4]); self._stats.copy_(snap[5])
+        self.refresh_packed()
+
+    def refresh_packed(self):
+        """Re-derive the bf16 operand planes from the fp32 parameters (after anything that changed them behind the
+        fused path's back: a restored snapshot, load_state_dict / load_checkpoint)."""
         actor = self.actor_critic.actor
         layers = actor.snn.linear_layers()
         actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
@@ -454,6 +459,7 @@ class PPO:
             f, mb = self.storage.permute_once(self.num_mini_batches)
             if self._fast_state is None or self._fast_state["mb"] != mb:
                 self._fast_setup(mb)
+            self.refresh_packed()      # the fused steps assume current planes (parameters may have been loaded since)
             for _ in range(self.num_learning_epochs):
                 for i in range(self.num_mini_batches):
                     self._run_fast(f, i)
