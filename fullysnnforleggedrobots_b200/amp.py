@@ -92,18 +92,19 @@ class ReplayBuffer:
         self.num_samples = 0
 
     def insert(self, states, next_states):
+        """Ring write of n rows starting at the cursor: one scatter per field (row i -> (cursor + i) mod size), which
+        is the reference's two-slice wrap-around without the branch.  More rows than the ring holds: the last ones
+        win, as a sequential write would leave them."""
         n = states.shape[0]
-        end = self.step + n
-        if end > self.buffer_size:
-            head = self.buffer_size - self.step
-            self.states[self.step:] = states[:head]
-            self.next_states[self.step:] = next_states[:head]
-            self.states[:end - self.buffer_size] = states[head:]
-            self.next_states[:end - self.buffer_size] = next_states[head:]
-        else:
-            self.states[self.step:end] = states
-            self.next_states[self.step:end] = next_states
-        self.num_samples = min(self.buffer_size, max(end, self.num_samples))
+        if n > self.buffer_size:
+            states, next_states = states[n - self.buffer_size:], next_states[n - self.buffer_size:]
+            self.step = (self.step + n - self.buffer_size) % self.buffer_size
+            self.num_samples = self.buffer_size
+            n = self.buffer_size
+        rows = (torch.arange(n, device=self.states.device) + self.step) % self.buffer_size
+        self.states.index_copy_(0, rows, states.to(self.states.dtype))
+        self.next_states.index_copy_(0, rows, next_states.to(self.states.dtype))
+        self.num_samples = min(self.buffer_size, max(self.step + n, self.num_samples))
         self.step = (self.step + n) % self.buffer_size
 
     def feed_forward_generator(self, num_mini_batch, mini_batch_size):
