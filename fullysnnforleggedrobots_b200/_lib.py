@@ -110,6 +110,8 @@ _SIGS = {
                               C.c_void_p, C.POINTER(SnnMlpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snn_ppo_head": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
                      + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
+    "snn_sample_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 6
                       + [C.c_void_p, C.c_void_p, C.c_void_p]),

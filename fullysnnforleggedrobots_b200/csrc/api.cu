@@ -664,6 +664,20 @@ int snn_ppo_head(const float* mu, const float* log_std, const float* value, cons
   return SNN_OK;
 }
 
+int snn_sample_logprob(const float* mu, const float* log_std, const float* noise, int64_t B, int A, float* actions,
+                       float* logp, float* sigma, void* stream) {
+  if (!mu || !log_std || !noise || !actions || !logp || !sigma) return fail(SNN_EINVAL, "null pointer");
+  if (A < 1 || A > 64 || B < 0) return fail(SNN_EINVAL, "snn_sample_logprob: 1 <= act_dim <= 64");
+  if (B == 0) return SNN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  sample_logprob_kernel<<<static_cast<unsigned>((B + 127) / 128), 128, 0, st>>>(mu, log_std, noise, static_cast<int>(B), A,
+                                                                                actions, logp, sigma);
+  }
+  LAUNCH_CHECK("sample_logprob_kernel");
+  return SNN_OK;
+}
+
 int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, void* stream) {
   if (!kl || !lr) return fail(SNN_EINVAL, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

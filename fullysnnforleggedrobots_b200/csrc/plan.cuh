@@ -95,6 +95,22 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.Bt = (256 / p.T) / 16 * 16;
   if (p.Bt > 128) p.Bt = 128;
   if (p.Bt < 16) p.Bt = 16;                           // T > 16: one accumulator set of T * 16 <= 512 columns
+  if (B > 0 && p.Bt > 16) {
+    // Small batches (rollout: B = num_envs): the widest tile leaves the persistent kernels with a ragged last wave
+    // (4096 envs, T = 5: 86 tiles of 48 over 74 CTAs per neuron tile = 2 waves).  Pick the tile that minimises
+    // waves x (tile + fixed per-item cost) for the first layer; large batches keep the widest tile.  The SM count is
+    // a constant here because buffer-size queries and launches must agree on the geometry.
+    const int nmt0 = static_cast<int>(round_up(d.hidden[0], 128)) / 128;
+    const int ctas = 148 / nmt0 > 0 ? 148 / nmt0 : 1;
+    int best = p.Bt;
+    int64_t best_cost = -1;
+    for (int bt = p.Bt; bt >= 16; bt -= 16) {
+      const int64_t tiles = (B + bt - 1) / bt;
+      const int64_t cost = ((tiles + ctas - 1) / ctas) * (bt + 8);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bt; }
+    }
+    p.Bt = best;
+  }
   p.TB = p.T * p.Bt;
   p.CT = static_cast<int>(round_up(p.TB, 64));
   p.sets = p.TB <= 256 ? 2 : 1;

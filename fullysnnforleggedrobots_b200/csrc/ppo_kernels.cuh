@@ -234,4 +234,36 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
   }
 }
 
+// ------------------------------------------------------------------ rollout step: sample + log-prob in one pass
+// ActorCritic.act / get_actions_log_prob / action_std (actor_critic.py:398-421) on the actor's (mu, log_std):
+//   sigma = exp(log_std) ; action = mu + sigma * noise ; log_prob = sum_a Normal(mu, sigma).log_prob(action)
+// with torch.distributions.Normal's arithmetic order: -((x - mu)^2) / (2 sigma^2) - log(sigma) - log(sqrt(2 pi)).
+// One thread per sample (A <= 64); noise is drawn by the caller (torch's Philox stream, CUDA-graph safe).
+__global__ void __launch_bounds__(128) sample_logprob_kernel(const float* __restrict__ mu, const float* __restrict__ log_std,
+                                                            const float* __restrict__ noise, int B, int A,
+                                                            float* __restrict__ actions, float* __restrict__ logp,
+                                                            float* __restrict__ sigma_out) {
+  __shared__ float s_sig[64], s_two_var[64], s_logsig[64];
+  if (threadIdx.x < A) {
+    const float sg = expf(log_std[threadIdx.x]);
+    s_sig[threadIdx.x] = sg;
+    s_two_var[threadIdx.x] = 2.f * (sg * sg);
+    s_logsig[threadIdx.x] = logf(sg);
+  }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const size_t i = static_cast<size_t>(b) * A + a;
+    const float m = mu[i], sg = s_sig[a];
+    const float x = __fadd_rn(m, __fmul_rn(sg, noise[i]));
+    const float d = __fsub_rn(x, m);
+    lp += __fsub_rn(__fsub_rn(__fdiv_rn(-(d * d), s_two_var[a]), s_logsig[a]), 0.91893853320467267f);
+    actions[i] = x;
+    sigma_out[i] = sg;
+  }
+  logp[b] = lp;
+}
+
 }  // namespace snn

@@ -96,6 +96,17 @@ class SnnEngine:
         with torch.cuda.device(weights[0].device):
             self.packed_weights(weights, biases, ps)
 
+    def ensure_packed(self, enc_mean, enc_std, weights, biases, dec_w, dec_b):
+        """Re-pack only if a weight / bias tensor changed since the last pack (torch version counters).  Callers that
+        replay CUDA graphs over the packed planes run this before the replay: the check is host-side."""
+        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases))
+        if key == self._packed_key and self._packed is not None:
+            return
+        ps = self._params_struct(enc_mean.data, enc_std.data, [w.data for w in weights], [b.data for b in biases],
+                                 dec_w.data, dec_b.data)
+        with torch.cuda.device(weights[0].device):
+            self.packed_weights(weights, biases, ps)
+
     def trace_bytes(self, B: int) -> int:
         return int(_lib.lib().snn_trace_bytes(C.byref(self.desc), B))
 

@@ -37,6 +37,20 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+class _LazyNormal:
+    """What `actor_critic.distribution` holds after a graph-replayed rollout step: Normal(mu, sigma) of that step,
+    built on first use (constructing torch.distributions.Normal costs more host time than the replay itself)."""
+
+    def __init__(self, mu, sigma):
+        self.mean, self.stddev = mu, sigma
+        self._d = None
+
+    def __getattr__(self, name):           # log_prob, entropy, sample, ...
+        if self._d is None:
+            self._d = torch.distributions.Normal(self.mean, self.stddev, validate_args=False)
+        return getattr(self._d, name)
+
+
 class PPO:
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998,
                  lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
@@ -107,28 +121,62 @@ class PPO:
     def train_mode(self):
         self.actor_critic.train()
 
-    def _act_body(self, obs, critic_obs, graph_safe=False):
+    def _act_body(self, obs, critic_obs):
         ac = self.actor_critic
-        if graph_safe:
-            # torch.normal(mean_tensor, std_tensor) checks `std >= 0` on the host (a sync): not capturable.
-            # Same distribution from randn_like; the noise stream differs from Normal.sample()'s, parity is defined
-            # on mu / sigma / values / log-probs, not on the random draw.
-            ac.update_distribution(obs)
-            actions = (ac.action_mean + ac.action_std * torch.randn_like(ac.action_mean)).detach()
-        else:
-            actions = ac.act(obs).detach()
+        actions = ac.act(obs).detach()
         values = ac.evaluate(critic_obs).detach()
         logp = ac.get_actions_log_prob(actions).detach()
         return actions, values, logp, ac.action_mean.detach(), ac.action_std.detach()
 
+    def _act_fused(self, st):
+        """Graph-safe rollout step on static buffers: the critic on a parallel branch (second stream), the actor
+        forward writing mu in place, then ONE kernel for sigma / sampling / log-prob (snn_sample_logprob; the
+        reference's Normal.sample + log_prob + stddev are ~16 elementwise launches).  torch.normal(mean, std) would
+        check `std >= 0` on the host (a sync, not capturable); the noise comes from randn_like instead — same
+        distribution, parity is defined on mu / sigma / values / log-probs, not on the random draw."""
+        ac = self.actor_critic
+        actor = ac.actor
+        dev = st["obs"].device
+        o = st["views"]
+        cur = torch.cuda.current_stream(dev)
+        side = st["side"]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            o["values"].copy_(ac.evaluate(st["cobs"]))
+        layers = actor.snn.linear_layers()
+        # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack only
+        # if a weight changed" check; _act_graphed runs the same check on the host before every replay)
+        actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
+                             [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
+                             train=False, out_mu=o["mu"])
+        noise = torch.randn_like(o["mu"])
+        B, A = o["mu"].shape
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A, _p(o["actions"]),
+                                                     _p(o["logp"]), _p(o["sigma"]), C.c_void_p(cur.cuda_stream)),
+                       "snn_sample_logprob")
+        cur.wait_stream(side)
+
+    @staticmethod
+    def _act_views(packed, B, A):
+        off = [0, B * A, B * A + B, B * A + 2 * B, 2 * B * A + 2 * B]
+        return {"actions": packed[off[0]:off[1]].view(B, A), "values": packed[off[1]:off[2]].view(B, 1),
+                "logp": packed[off[2]:off[3]], "mu": packed[off[3]:off[4]].view(B, A),
+                "sigma": packed[off[4]:off[4] + B * A].view(B, A)}
+
     def _act_graphed(self, obs, critic_obs):
         """Rollout step as ONE CUDA-graph replay (the reference launches ~250 kernels here): inputs are copied into
-        static buffers, the sampled actions / values / log-probs come back as fresh clones."""
+        static buffers; actions / values / log-probs / mu / sigma land in one packed static buffer that is cloned once
+        per call (fresh tensors for the caller, as in the reference)."""
         key = (tuple(obs.shape), tuple(critic_obs.shape), obs.data_ptr() == critic_obs.data_ptr())
         st = self._act_state
         if st is None or st["key"] != key:
-            st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0}
+            B, A = obs.shape[0], self.actor_critic.actor.act_dim
+            st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0,
+                  "packed": torch.empty(3 * B * A + 2 * B, dtype=torch.float32, device=obs.device),
+                  "side": torch.cuda.Stream(device=obs.device)}
             st["cobs"] = st["obs"] if key[2] else critic_obs.clone()
+            st["views"] = self._act_views(st["packed"], B, A)
             self._act_state = st
         st["obs"].copy_(obs)
         if not key[2]:
@@ -141,19 +189,28 @@ class PPO:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._act_body(st["obs"], st["cobs"], graph_safe=True)
+                    self._act_fused(st)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                st["out"] = self._act_body(st["obs"], st["cobs"], graph_safe=True)
+                self._act_fused(st)
             st["graph"] = g
+        actor = self.actor_critic.actor
+        layers = st.get("layers")
+        if layers is None:
+            layers = st["layers"] = actor.snn.linear_layers()
+        actor.engine.ensure_packed(actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
+                                   [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias)
         st["graph"].replay()
-        return tuple(t.clone() for t in st["out"])
+        B, A = st["views"]["mu"].shape
+        v = self._act_views(st["packed"].clone(), B, A)
+        self.actor_critic.distribution = _LazyNormal(v["mu"], v["sigma"])     # reference: act() leaves it set
+        return v["actions"], v["values"], v["logp"], v["mu"], v["sigma"]
 
     def act(self, obs, critic_obs):
         use_graph = (self.act_cuda_graph and obs.is_cuda and not torch.is_grad_enabled()
-                     and type(self.actor_critic).__name__ != "ActorCriticRMA")
+                     and type(self.actor_critic).__name__ != "ActorCriticRMA" and self.actor_critic.actor.act_dim <= 64)
         if use_graph:
             try:
                 out = self._act_graphed(obs, critic_obs)

@@ -148,6 +148,12 @@ int snn_ppo_head(const float* mu, const float* log_std, const float* value, cons
                  float ent_coef, int clipped_value, float* g_mu, float* g_value, float* g_log_std, float* stats,
                  void* scratch, size_t scratch_bytes, void* stream);
 
+/* Rollout step tail (PPO.act, ppo.py:90-102 -> actor_critic.py:398-421): sigma = exp(log_std) broadcast to [B,A],
+ * actions = mu + sigma * noise (noise ~ N(0,1) drawn by the caller), logp[b] = sum_a Normal(mu, sigma).log_prob(action)
+ * in torch.distributions.Normal's arithmetic order.  A <= 64. */
+int snn_sample_logprob(const float* mu, const float* log_std, const float* noise, int64_t B, int A, float* actions,
+                       float* logp, float* sigma, void* stream);
+
 /* Adaptive-KL learning-rate rule (ppo.py:145-148) on a DEVICE learning rate: no host round trip.
  * kl_mean = kl[0] * kl_scale. */
 int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, void* stream);

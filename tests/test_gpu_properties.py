@@ -101,14 +101,15 @@ def test_bptt_is_linear_in_upstream_gradient_and_reproducible():
             assert rel_err(g1[k], g1b[k]) < 1e-5, k
 
 
-def test_full_size_subsample_matches_oracle():
-    """Oracle parity on a 192-row sub-sample of a 24576-row minibatch (forward exact rows; gradients of a loss that
-    only touches those rows)."""
+@pytest.mark.parametrize("B", [24576, 4096, 1000])
+def test_full_size_subsample_matches_oracle(B):
+    """Oracle parity on a 192-row sub-sample of a PPO minibatch (24576: 48-sample tiles) and of rollout-sized batches
+    (4096 / 1000: the plan picks narrower 32- / 16-sample tiles there): forward exact rows; gradients of a loss that
+    only touches those rows."""
     from oracle import snn_oracle as O
-    B = 24576
     actor = make_actor()
     obs = torch.randn(B, 48, device="cuda")
-    idx = torch.arange(5000, 5192, device="cuda")
+    idx = torch.arange(B // 5, B // 5 + 192, device="cuda")
     G = torch.zeros(B, 12, device="cuda")
     G[idx] = torch.randn(192, 12, device="cuda")
     mu, grads = grads_of(actor, obs, G)
