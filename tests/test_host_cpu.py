@@ -34,9 +34,11 @@ def test_size_queries_without_gpu():
     eng = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=5)
     L = _lib.lib()
     assert L.snn_packed_weights_bytes(C.byref(eng.desc)) > 3 * 2 * (512 * 256 + 256 * 256 + 256 * 128)
-    # the batch is cut into tiles of 48 samples for T = 5 (csrc/plan.cuh): 144 = 3 tiles, 145..192 = 4 tiles
-    t1, t2 = L.snn_trace_bytes(C.byref(eng.desc), 144), L.snn_trace_bytes(C.byref(eng.desc), 145)
-    assert 0 < t1 < t2 and t2 == L.snn_trace_bytes(C.byref(eng.desc), 192)
+    # PPO-minibatch-sized batches are cut into tiles of 48 samples for T = 5 (csrc/plan.cuh): 24576 = 512 tiles,
+    # 24577..24624 = 513 tiles; rollout-sized and tiny batches get narrower tiles (16 samples for B <= 16)
+    tb = lambda B: L.snn_trace_bytes(C.byref(eng.desc), B)
+    assert 0 < tb(24576) < tb(24577) and tb(24577) == tb(24624)
+    assert 0 < tb(1) == tb(16) < tb(17)
     assert L.snn_workspace_bytes(C.byref(eng.desc), 4096, 1) > L.snn_workspace_bytes(C.byref(eng.desc), 4096, 0)
     bad = SnnEngine(48, 12, 10, 10, [256, 256], spike_ts=40)                      # unsupported T (> 32)
     assert L.snn_trace_bytes(C.byref(bad.desc), 128) == 0
