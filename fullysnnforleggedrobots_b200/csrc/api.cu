@@ -338,11 +338,25 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     if (gpb_max < 0) { const char* e = getenv("SNN_TOPSCAN_GPB"); gpb_max = e ? atoi(e) : 1; if (gpb_max < 1 || gpb_max > kTopScanGPB) gpb_max = kTopScanGPB; }
     int gpb = gpb_max;
     while (nbg % gpb) --gpb;                       // T = 5: Bt = 48 -> 6 groups per tile
-    const int nrows = p.ntile * nbg / gpb;
+    static int rows_variant = -1;      // SNN_TOPSCAN_ROWS=0: the thread = neuron kernel (A/B runs)
+    if (rows_variant < 0) { const char* e = getenv("SNN_TOPSCAN_ROWS"); rows_variant = e ? atoi(e) : 1; }
+    int nrows = p.ntile * nbg / gpb;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w,
-                                         reinterpret_cast<const float*>(at(trace, lp.tr_volt)), Bi, tg, p.A, p.Pd, lp.NP,
-                                         p.T, gpb, at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+    const float* volt = reinterpret_cast<const float*>(at(trace, lp.tr_volt));
+    if (rows_variant) {
+      nrows = static_cast<int>(p.Bcap / 8);
+      const dim3 grd(nrows, lp.NP / 64);
+      if (p.T == 5)
+        top_scan_rows_kernel<5><<<grd, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+      else
+        top_scan_rows_kernel<0><<<grd, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+    } else {
+      top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A,
+                                           p.Pd, lp.NP, p.T, gpb, at(workspace, p.ws_g[top]), p.ws_g_plane[top],
+                                           dbpart_of(top), small);
+    }
     }
     LAUNCH_CHECK("top_scan_kernel");
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);

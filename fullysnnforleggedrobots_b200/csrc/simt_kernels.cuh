@@ -362,6 +362,105 @@ __global__ void __launch_bounds__(128 * kTopScanGPB) top_scan_kernel(const float
   }
 }
 
+// ------------------------------------------------------------------ BPTT of the output population layer, row-major
+// Same arithmetic per (neuron, sample, t) as top_scan_kernel, other orientation: thread = (PAIR of neurons, one
+// sample), warp = the 64 neurons of one chunk of one sample, block = 8 samples.  Every request is then a full
+// row segment: a warp loads the 64 voltages of a sample-step as two 128-byte lines and stores each g_c plane row as
+// ONE 128-byte line (4-byte bf16x2 stores; thread = neuron needs 2-byte stores that fill only half a line).  The
+// state per thread is two short recurrences (~40 registers -> full occupancy; the kernel is latency-bound).
+// Per-neuron sums: 8 samples are added in shared memory in a fixed order -> one partial row per block, the same
+// [Bcap / 8][..] layout top_scan_kernel writes.   grid (Bcap / 8, NP / 64), block 256.
+template <int TT>
+__global__ void __launch_bounds__(256) top_scan_rows_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+                                                           int dec_tanh, const float* __restrict__ dec_w,
+                                                           const float* __restrict__ volt, int B, TileGeom tg, int A,
+                                                           int P, int NP, int T, uint8_t* __restrict__ g_img,
+                                                           size_t g_plane, float* __restrict__ db_part /* [gridDim.x][NP] */,
+                                                           float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
+  __shared__ float s_red[8][6][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.y;
+  const int n0 = chunk * 64 + 2 * lane;                        // this thread's neurons n0, n0 + 1
+  const int b = blockIdx.x * 8 + w;                            // its sample (< Bcap)
+  const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
+  const int nt = TT > 0 ? TT : T;
+  const float Tf = static_cast<float>(nt);
+  const bool live = b < B;
+  const bool l0 = live && n0 < A * P, l1 = live && n0 + 1 < A * P;
+  const int a0 = l0 ? n0 / P : 0, a1 = l1 ? (n0 + 1) / P : 0;
+  float G0 = 0.f, G1 = 0.f, gup0 = 0.f, gup1 = 0.f;
+  if (l0) {
+    G0 = g_mu[static_cast<size_t>(b) * A + a0];
+    if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a0]; G0 = G0 * (1.f - m * m); }
+    gup0 = __fdiv_rn(G0 * dec_w[n0], Tf);
+  }
+  if (l1) {
+    G1 = g_mu[static_cast<size_t>(b) * A + a1];
+    if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a1]; G1 = G1 * (1.f - m * m); }
+    gup1 = __fdiv_rn(G1 * dec_w[n0 + 1], Tf);
+  }
+  const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
+  const float2* vsrc = reinterpret_cast<const float2*>(volt + (static_cast<size_t>(n0 >> 5) * tg.Rt + r0) * 32 + (n0 & 31));
+  const size_t vstep = static_cast<size_t>(tg.Bt) * 16;        // float2 units between timesteps
+  uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4;
+  const uint32_t piece = static_cast<uint32_t>(lane >> 2);
+  float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, cnt0 = 0.f, cnt1 = 0.f, db0 = 0.f, db1 = 0.f;
+  auto step = [&](int t, float2 v) {
+    const float v0 = live ? v.x : 0.f, v1 = live ? v.y : 0.f;
+    cnt0 += v0 > 0.5f ? 1.f : 0.f;
+    cnt1 += v1 > 0.5f ? 1.f : 0.f;
+    const float gs0 = gup0 - gvn0 * (0.75f * v0), gs1 = gup1 - gvn1 * (0.75f * v1);
+    const float win0 = fabsf(__fsub_rn(v0, 0.5f)) < 0.5f ? 1.f : 0.f, win1 = fabsf(__fsub_rn(v1, 0.5f)) < 0.5f ? 1.f : 0.f;
+    const float gv0 = gs0 * win0 + gvn0 * (v0 > 0.5f ? 0.f : 0.75f), gv1 = gs1 * win1 + gvn1 * (v1 > 0.5f ? 0.f : 0.75f);
+    const float gc0 = gv0 + 0.5f * gcn0, gc1 = gv1 + 0.5f * gcn1;
+    gvn0 = gv0; gvn1 = gv1; gcn0 = gc0; gcn1 = gc1;
+    db0 += gc0; db1 += gc1;
+    const uint32_t hp = pack_bf16x2(gc0, gc1);
+    const uint32_t lp = pack_bf16x2(gc0 - __uint_as_float(hp << 16), gc1 - __uint_as_float(hp & 0xFFFF0000u));
+    const size_t r = r0 + static_cast<size_t>(t) * tg.Bt;
+    uint8_t* q = grow + static_cast<size_t>(t) * tg.Bt * 128 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4);
+    *reinterpret_cast<uint32_t*>(q) = hp;
+    *reinterpret_cast<uint32_t*>(q + g_plane) = lp;
+  };
+  if (TT > 0) {
+    float2 v[TT > 0 ? TT : 1];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) v[t] = __ldg(vsrc + static_cast<size_t>(t) * vstep);      // all loads up front
+#pragma unroll
+    for (int t = TT - 1; t >= 0; --t) step(t, v[t]);
+  } else {
+    float2 vn = __ldg(vsrc + static_cast<size_t>(T - 1) * vstep);
+    for (int t = T - 1; t >= 0; --t) {
+      const float2 v = vn;
+      if (t > 0) vn = __ldg(vsrc + static_cast<size_t>(t - 1) * vstep);
+      step(t, v);
+    }
+  }
+  // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM: the tile's first block clears them
+  if (bl - w == 0) {      // Bt % 8 == 0: the 8 samples of a block lie in one tile; its warps share the rows
+    const int TB = nt * tg.Bt;
+    for (int cc = TB + w; cc < tg.CT; cc += 8) {
+      const size_t r = static_cast<size_t>(tile) * tg.CT + cc;
+      uint8_t* q = g_img + (static_cast<size_t>(chunk) * tg.Rt + r) * 128 + (lane & 3) * 4 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4);
+      *reinterpret_cast<uint32_t*>(q) = 0u;
+      *reinterpret_cast<uint32_t*>(q + g_plane) = 0u;
+    }
+  }
+  s_red[w][0][lane] = db0; s_red[w][1][lane] = db1;
+  s_red[w][2][lane] = G0 * __fdiv_rn(cnt0, Tf); s_red[w][3][lane] = G1 * __fdiv_rn(cnt1, Tf);
+  s_red[w][4][lane] = G0; s_red[w][5][lane] = G1;
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x >> 5;                             // which of the six sums; lane = neuron pair
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc += s_red[g][k][lane];
+    const int n = n0 + (k & 1);
+    if (k < 2) db_part[static_cast<size_t>(blockIdx.x) * NP + n] = acc;
+    else dec_part[(static_cast<size_t>(blockIdx.x) * 2 + (k >= 4 ? 1 : 0)) * NP + n] = acc;
+  }
+}
+
 // ------------------------------------------------------------------ encoder input gradient
 // (the encoder PARAMETER gradients are produced by the DX_ENC epilogue, nm_gemm.cuh)
 // d obs[b,o] = sum_p g_a a (-(x-mean))/var   (RMA: the actor input is cat(obs, latent) and needs grad)
