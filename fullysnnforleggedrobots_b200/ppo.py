@@ -297,8 +297,8 @@ class PPO:
         actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
                             [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
                             actor.decoder.decoder.bias.data)
-        if self._fast_state is not None and self._fast_state.get("critic") is not None:
-            self._fast_state["critic"].repack()
+        # the critic's operand planes are re-derived at the head of the next step's critic branch (second stream):
+        # off the critical path, which continues with the actor's encoder (_step_fast)
 
     def _step_generic(self, batch):
         loss, surrogate_loss, value_loss, kl_mean = self.losses(batch)
@@ -371,8 +371,10 @@ class PPO:
             if side is not None:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
+                    ce.repack()
                     value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
             else:
+                ce.repack()
                 value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
         mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
                                 db.data, train=True, out_mu=st["mu"], out_trace=st["trace"], assume_packed=True)
