@@ -341,7 +341,7 @@ def run_ours(args):
     dom_kernel = ["nm_gemm_kernel<FWD>", "nm_gemm_kernel<DX>" if dl > 0 else "nm_gemm_kernel<DX_ENC>", "dw_gemm_kernel"][dk] + f" (actor layer {dl})"
     achieved = pfl32[di] / (pms32[di] * 1e-3) / 1e12
     traffic, pipe_pct, smem_pct = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r1k_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1m_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tk = json.load(f)["kernels"].get(dom_name)
@@ -369,7 +369,7 @@ def run_ours(args):
         "note": "achieved = ALGORITHMIC flops (2*B*K*N*T per layer GEMM, one product per MAC) / CUDA-event kernel time; "
                 "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC, so issued tensor work is 3x 'achieved'; "
                 "kernel times from an eager re-run of the timed steps (the timed region itself replays CUDA graphs); "
-                "traffic / tensor-pipe % / shared-memory data-pipe % from the committed ncu capture profiles/r1k_* "
+                "traffic / tensor-pipe % / shared-memory data-pipe % from the committed ncu capture profiles/r1m_* "
                 "(the tensor-core kernels are bound by the SM's shared-memory data pipe: operand reads of the MMAs plus the "
                 "bulk-copy / expansion writes that feed them, DESIGN.md 4.6)",
         "all_tensor_kernels": {"ms": tc_ms, "algo_tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
