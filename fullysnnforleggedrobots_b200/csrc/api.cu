@@ -344,13 +344,13 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     const float* volt = reinterpret_cast<const float*>(at(trace, lp.tr_volt));
     if (rows_variant) {
-      nrows = static_cast<int>(p.Bcap / 8);
+      nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
       const dim3 grd(nrows, lp.NP / 64);
       if (p.T == 5)
-        top_scan_rows_kernel<5><<<grd, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+        top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
                                                     at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
       else
-        top_scan_rows_kernel<0><<<grd, 256, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+        top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
                                                     at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
     } else {
       top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A,

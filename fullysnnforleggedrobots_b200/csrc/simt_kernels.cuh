@@ -364,24 +364,26 @@ __global__ void __launch_bounds__(128 * kTopScanGPB) top_scan_kernel(const float
 
 // ------------------------------------------------------------------ BPTT of the output population layer, row-major
 // Same arithmetic per (neuron, sample, t) as top_scan_kernel, other orientation: thread = (PAIR of neurons, one
-// sample), warp = the 64 neurons of one chunk of one sample, block = 8 samples.  Every request is then a full
+// sample), warp = the 64 neurons of one chunk of one sample, block = kTopRowsSPB samples.  Every request is then a full
 // row segment: a warp loads the 64 voltages of a sample-step as two 128-byte lines and stores each g_c plane row as
 // ONE 128-byte line (4-byte bf16x2 stores; thread = neuron needs 2-byte stores that fill only half a line).  The
 // state per thread is two short recurrences (~40 registers -> full occupancy; the kernel is latency-bound).
-// Per-neuron sums: 8 samples are added in shared memory in a fixed order -> one partial row per block, the same
-// [Bcap / 8][..] layout top_scan_kernel writes.   grid (Bcap / 8, NP / 64), block 256.
+// Per-neuron sums: the block's samples are added in shared memory in a fixed order -> one partial row per block
+// ([Bcap / kTopRowsSPB][..], the layout top_scan_kernel writes).   grid (Bcap / kTopRowsSPB, NP / 64), block 32 * kTopRowsSPB.
+constexpr int kTopRowsSPB = 8;       // Bt % 16 == 0: the samples of a block lie in one tile (16: row reduction 12.8 -> 7.1 us but this kernel 36 -> 40 us: a wash)
 template <int TT>
-__global__ void __launch_bounds__(256) top_scan_rows_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
+__global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                            int dec_tanh, const float* __restrict__ dec_w,
                                                            const float* __restrict__ volt, int B, TileGeom tg, int A,
                                                            int P, int NP, int T, uint8_t* __restrict__ g_img,
                                                            size_t g_plane, float* __restrict__ db_part /* [gridDim.x][NP] */,
                                                            float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
-  __shared__ float s_red[8][6][32];
+  constexpr int SPB = kTopRowsSPB;
+  __shared__ float s_red[SPB][6][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const int n0 = chunk * 64 + 2 * lane;                        // this thread's neurons n0, n0 + 1
-  const int b = blockIdx.x * 8 + w;                            // its sample (< Bcap)
+  const int b = blockIdx.x * SPB + w;                          // its sample (< Bcap)
   const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
   const int nt = TT > 0 ? TT : T;
   const float Tf = static_cast<float>(nt);
@@ -437,9 +439,9 @@ __global__ void __launch_bounds__(256) top_scan_rows_kernel(const float* __restr
     }
   }
   // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM: the tile's first block clears them
-  if (bl - w == 0) {      // Bt % 8 == 0: the 8 samples of a block lie in one tile; its warps share the rows
+  if (bl - w == 0) {      // first block of its tile; its warps share the rows
     const int TB = nt * tg.Bt;
-    for (int cc = TB + w; cc < tg.CT; cc += 8) {
+    for (int cc = TB + w; cc < tg.CT; cc += SPB) {
       const size_t r = static_cast<size_t>(tile) * tg.CT + cc;
       uint8_t* q = g_img + (static_cast<size_t>(chunk) * tg.Rt + r) * 128 + (lane & 3) * 4 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4);
       *reinterpret_cast<uint32_t*>(q) = 0u;
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(256) top_scan_rows_kernel(const float* __restr
     const int k = threadIdx.x >> 5;                             // which of the six sums; lane = neuron pair
     float acc = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) acc += s_red[g][k][lane];
+    for (int g = 0; g < SPB; ++g) acc += s_red[g][k][lane];
     const int n = n0 + (k & 1);
     if (k < 2) db_part[static_cast<size_t>(blockIdx.x) * NP + n] = acc;
     else dec_part[(static_cast<size_t>(blockIdx.x) * 2 + (k >= 4 ? 1 : 0)) * NP + n] = acc;
