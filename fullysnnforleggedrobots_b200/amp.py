@@ -165,13 +165,20 @@ class AMPPPO(PPO):
     def __init__(self, actor_critic, discriminator, amp_data, amp_normalizer, num_learning_epochs=1,
                  num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95, value_loss_coef=1.0, entropy_coef=0.0,
                  learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01,
-                 device='cpu', amp_replay_buffer_size=100000, min_std=None, **kwargs):
+                 device='cpu', amp_replay_buffer_size=100000, min_std=None, disc_matmul="tf32", **kwargs):
         super().__init__(actor_critic, num_learning_epochs=num_learning_epochs, num_mini_batches=num_mini_batches,
                          clip_param=clip_param, gamma=gamma, lam=lam, value_loss_coef=value_loss_coef,
                          entropy_coef=entropy_coef, learning_rate=learning_rate, max_grad_norm=max_grad_norm,
                          use_clipped_value_loss=use_clipped_value_loss, schedule=schedule, desired_kl=desired_kl,
                          device=device, **kwargs)
         self.min_std = min_std
+        # Discriminator GEMMs (60 -> 1024 -> 512 -> 1 on 2 x 24576 rows, plus the double backward of the gradient
+        # penalty) are 90 % of an AMP update when cuBLAS runs them as fp32 SIMT sgemm (measured: 205 ms vs 14 ms for the
+        # spiking PPO part).  "tf32" lets cuBLAS use the tensor cores for them — which is what the reference's pinned
+        # torch 1.10 does by default on Ampere and later (allow_tf32 was on until torch 1.12); "fp32" = IEEE sgemm.
+        if disc_matmul not in ("tf32", "fp32"):
+            raise ValueError("disc_matmul must be 'tf32' or 'fp32'")
+        self.disc_matmul = disc_matmul
         self.discriminator = discriminator
         self.discriminator.to(self.device)
         if self.dp is not None:
@@ -205,6 +212,14 @@ class AMPPPO(PPO):
 
     # ------------------------------------------------------------------ discriminator half of a minibatch step
     def _disc_backward(self, sample_amp_policy, sample_amp_expert):
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.disc_matmul == "tf32"
+        try:
+            return self._disc_backward_impl(sample_amp_policy, sample_amp_expert)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _disc_backward_impl(self, sample_amp_policy, sample_amp_expert):
         policy_state, policy_next_state = sample_amp_policy
         expert_state, expert_next_state = sample_amp_expert
         norm = self.amp_normalizer

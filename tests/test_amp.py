@@ -63,10 +63,15 @@ def make_alg(pc, a, **kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fused_graph", "generic"])
+@pytest.mark.parametrize("mode", ["fused_graph", "generic", "fused_graph_tf32"])
 def test_amp_update_matches_reference(mode):
+    """fp32 discriminator GEMMs: the reference fixture's tolerances; tf32 (the default, = the reference's pinned
+    torch 1.10 behaviour on tensor-core GPUs): same checks with the discriminator-side tolerances at TF32 level."""
     pc, g, a, ro = AMP_CASE, load(), make_amp_inputs(AMP_CASE), make_ppo_rollout(AMP_CASE)
-    ac, disc, norm, alg = make_alg(pc, a, fused=mode != "generic", use_cuda_graph=mode == "fused_graph")
+    tf32 = mode.endswith("tf32")
+    ac, disc, norm, alg = make_alg(pc, a, fused=mode != "generic", use_cuda_graph=mode.startswith("fused_graph"),
+                                   disc_matmul="tf32" if tf32 else "fp32")
+    assert alg.disc_matmul == ("tf32" if tf32 else "fp32")
     # rollout through the public act / process_env_step surface (amp_obs rides along), then overwrite the sampled
     # quantities with the reference's (its noise stream cannot be reproduced)
     with torch.inference_mode():
@@ -86,7 +91,8 @@ def test_amp_update_matches_reference(mode):
     ref = g["update_result"]
     assert len(res) == 6
     for i, (x, y) in enumerate(zip(res, ref)):
-        assert abs(x - y) <= 2e-4 * max(1.0, abs(y)), (i, x, y)
+        tol = 5e-3 if (tf32 and i >= 2) else 2e-4           # entries 2.. are discriminator quantities
+        assert abs(x - y) <= tol * max(1.0, abs(y)), (i, x, y)
     assert abs(alg.learning_rate / g["final_lr"] - 1) < 1e-6
     assert torch.equal(ac.std.detach().cpu(), torch.full((pc.act_dim,), AMP_MIN_STD))     # min_std clamp (:251-252)
     sd0 = make_ppo_state_dict(pc)
@@ -101,8 +107,8 @@ def test_amp_update_matches_reference(mode):
     for k, v in disc.state_dict().items():
         d_ref = torch.from_numpy(g["disc_final." + k]) - a["disc_state_dict"][k]
         d = v.cpu() - a["disc_state_dict"][k]
-        frac_bad = ((d - d_ref).abs() > 0.02 * pc.lr).float().mean().item()
-        assert frac_bad < 0.005, (k, frac_bad)
+        frac_bad = ((d - d_ref).abs() > (0.2 if tf32 else 0.02) * pc.lr).float().mean().item()
+        assert frac_bad < (0.02 if tf32 else 0.005), (k, frac_bad)
     assert np.allclose(norm.mean.cpu().numpy(), g["norm_mean"], rtol=1e-5, atol=1e-6)
     assert np.allclose(norm.var.cpu().numpy(), g["norm_var"], rtol=1e-5, atol=1e-6)
     assert abs(norm.count - float(g["norm_count"])) < 1e-9
