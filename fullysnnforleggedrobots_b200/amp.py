@@ -115,20 +115,21 @@ class ReplayBuffer:
 
 class Normalizer:
     """Running mean / variance of the AMP observations (utils.py:79-131), parallel-variance update, kept on the
-    device in float64.  `update` takes a torch tensor (any device) or a numpy array; `count` is a host float
-    (it only depends on batch sizes), so nothing here synchronises."""
+    device in float64 and updated IN PLACE (mean, var and count are device tensors with stable addresses, so the
+    discriminator step that uses them can be replayed as a CUDA graph).  `update` takes a torch tensor (any device)
+    or a numpy array; nothing here synchronises (`float(normalizer.count)` does, when a caller asks)."""
 
     def __init__(self, input_dim, epsilon=1e-4, clip_obs=10.0, device="cpu"):
         self.device = torch.device(device)
         self.mean = torch.zeros(input_dim, dtype=torch.float64, device=self.device)
         self.var = torch.ones(input_dim, dtype=torch.float64, device=self.device)
-        self.count = 1e-4                  # RunningMeanStd's own epsilon (utils.py:80,89)
+        self.count = torch.full((), 1e-4, dtype=torch.float64, device=self.device)   # RunningMeanStd's epsilon (:80,89)
         self.epsilon = epsilon
         self.clip_obs = clip_obs
 
     def to(self, device):
         self.device = torch.device(device)
-        self.mean, self.var = self.mean.to(self.device), self.var.to(self.device)
+        self.mean, self.var, self.count = (t.to(self.device) for t in (self.mean, self.var, self.count))
         return self
 
     @torch.no_grad()
@@ -141,9 +142,9 @@ class Normalizer:
         delta = batch_mean - self.mean
         tot = self.count + batch_count
         m_2 = self.var * self.count + batch_var * batch_count + delta.square() * (self.count * batch_count / tot)
-        self.mean = self.mean + delta * (batch_count / tot)
-        self.var = m_2 / tot
-        self.count = tot
+        self.mean.add_(delta * (batch_count / tot))
+        self.var.copy_(m_2 / tot)
+        self.count.copy_(tot)
 
     def normalize(self, input):
         mean, var = self.mean.cpu().numpy(), self.var.cpu().numpy()
@@ -196,6 +197,10 @@ class AMPPPO(PPO):
              {'params': self.discriminator.amp_linear.parameters(), 'weight_decay': 10e-2, 'name': 'amp_head'}],
             lr=self.optimizer.lr_dev[0], capturable=True, foreach=False)
         self._amp_stats = torch.zeros(4, dtype=torch.float32, device=self.optimizer.flat_params.device)
+        # the discriminator step (normalise, two forwards, gradient penalty, backward, Adam, normaliser update:
+        # ~150 small launches, host-bound when launched eagerly) is replayed as ONE CUDA graph from its third call on
+        self.disc_cuda_graph = self.use_cuda_graph
+        self._disc_state = None
 
     def test_mode(self):
         self.actor_critic.eval()           # the reference calls the non-existent `.test()` here (:111)
@@ -211,11 +216,54 @@ class AMPPPO(PPO):
         self.amp_transition.clear()
 
     # ------------------------------------------------------------------ discriminator half of a minibatch step
-    def _disc_backward(self, sample_amp_policy, sample_amp_expert):
+    def _disc_step_body(self, sample_amp_policy, sample_amp_expert):
+        """Everything of a minibatch step that belongs to the discriminator; runs after the actor-critic's step (the
+        two are independent apart from the learning rate, which that step has just adapted on the device)."""
+        policy_state, expert_state = self._disc_backward_impl(sample_amp_policy, sample_amp_expert)
+        self.disc_optimizer.step()
+        if self.amp_normalizer is not None:
+            self.amp_normalizer.update(policy_state)
+            self.amp_normalizer.update(expert_state)
+
+    def _disc_graphable(self):
+        return (self.disc_cuda_graph and self.dp is None and self._amp_stats.is_cuda
+                and (self.amp_normalizer is None or isinstance(self.amp_normalizer, Normalizer)))
+
+    def _disc_step(self, sample_amp_policy, sample_amp_expert):
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.disc_matmul == "tf32"
         try:
-            return self._disc_backward_impl(sample_amp_policy, sample_amp_expert)
+            if not self._disc_graphable():
+                return self._disc_step_body(sample_amp_policy, sample_amp_expert)
+            tensors = (*sample_amp_policy, *sample_amp_expert)
+            key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+            st = self._disc_state
+            if st is None or st["key"] != key:
+                st = self._disc_state = {"key": key, "calls": 0, "graph": None,
+                                         "inputs": [torch.empty_like(t) for t in tensors]}
+            for dst, src in zip(st["inputs"], tensors):
+                dst.copy_(src)
+            ins = st["inputs"]
+            st["calls"] += 1
+            if st["graph"] is None:
+                if st["calls"] <= 2:      # real steps as warm-up (lazy Adam state, cuBLAS workspaces), on a side stream
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        self._disc_step_body((ins[0], ins[1]), (ins[2], ins[3]))
+                    torch.cuda.current_stream().wait_stream(side)
+                    return
+                try:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):              # capture only records: the step itself runs at replay()
+                        self._disc_step_body((ins[0], ins[1]), (ins[2], ins[3]))
+                    st["graph"] = g
+                except Exception as e:  # noqa: BLE001
+                    print(f"[AMPPPO] CUDA graph capture of the discriminator step failed ({e}); running it eagerly")
+                    self.disc_cuda_graph = False
+                    return self._disc_step_body(sample_amp_policy, sample_amp_expert)
+            st["graph"].replay()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
@@ -266,17 +314,13 @@ class AMPPPO(PPO):
             steps = ((lambda b=b: self._step_generic(b))
                      for b in self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs))
         for ac_step, sample_amp_policy, sample_amp_expert in zip(steps, amp_policy_generator, amp_expert_generator):
-            # discriminator gradients (independent of the actor-critic's)
-            policy_state, expert_state = self._disc_backward(sample_amp_policy, sample_amp_expert)
             # spiking actor-critic: forward, BPTT, adaptive lr -> lr_dev, clip over ITS parameters only (:248), Adam
             ac_step()
-            # the same Adam step for the discriminator's groups, at the learning rate this step just set
-            self.disc_optimizer.step()
+            # discriminator: losses, gradients, the same Adam step for its two groups at the learning rate the
+            # actor-critic step just set, normaliser update
+            self._disc_step(sample_amp_policy, sample_amp_expert)
             if not ac.fixed_std and self.min_std is not None:
-                ac.std.data = ac.std.data.clamp(min=self.min_std)
-            if self.amp_normalizer is not None:
-                self.amp_normalizer.update(policy_state)
-                self.amp_normalizer.update(expert_state)
+                ac.std.data.clamp_(min=self.min_std)
         stats = self._stats.tolist()                       # the host syncs of the update: here ...
         amp = self._amp_stats.tolist()
         self._lr = self.optimizer.sync_lr_from_device()    # ... and here

@@ -112,3 +112,39 @@ def test_amp_update_matches_reference(mode):
     assert np.allclose(norm.mean.cpu().numpy(), g["norm_mean"], rtol=1e-5, atol=1e-6)
     assert np.allclose(norm.var.cpu().numpy(), g["norm_var"], rtol=1e-5, atol=1e-6)
     assert abs(norm.count - float(g["norm_count"])) < 1e-9
+
+
+@pytest.mark.gpu
+def test_amp_discriminator_graph_replay_matches_eager():
+    """The discriminator step is captured into a CUDA graph on its third call.  Three updates (6 steps: 2 eager
+    warm-ups, capture + 4 replays) must leave exactly what the all-eager path leaves."""
+    pc, g, a, ro = AMP_CASE, load(), make_amp_inputs(AMP_CASE), make_ppo_rollout(AMP_CASE)
+
+    def run(disc_graph):
+        ac, disc, norm, alg = make_alg(pc, a)
+        alg.disc_cuda_graph = disc_graph
+        outs = []
+        for _ in range(3):
+            with torch.inference_mode():
+                for s in range(pc.num_steps):
+                    obs = ro["obs"][s].cuda()
+                    alg.act(obs, obs, a["amp_obs"][s].cuda())
+                    alg.process_env_step(ro["rewards"][s].cuda(), ro["dones"][s].cuda(), {}, a["amp_obs"][s + 1].cuda())
+            st = alg.storage
+            for k in ("actions", "values", "actions_log_prob", "mu", "sigma"):
+                getattr(st, k).copy_(torch.from_numpy(g[k]))
+            alg.compute_returns(ro["last_obs"].cuda())
+            alg.amp_storage.feed_forward_generator = deterministic_replay_generator(alg.amp_storage)
+            outs.append(alg.update())
+        graphed = alg._disc_state is not None and alg._disc_state["graph"] is not None
+        return outs, {k: v.detach().cpu().clone() for k, v in disc.state_dict().items()}, norm, graphed
+
+    o_e, sd_e, n_e, g_e = run(False)
+    o_g, sd_g, n_g, g_g = run(True)
+    assert g_g and not g_e
+    for x, y in zip(o_e, o_g):
+        assert np.allclose(x, y, rtol=1e-5, atol=1e-6), (x, y)
+    for k in sd_e:
+        assert rel_err(sd_g[k], sd_e[k]) < 1e-5, k
+    assert np.allclose(n_g.mean.cpu().numpy(), n_e.mean.cpu().numpy(), rtol=1e-9)
+    assert abs(float(n_g.count) - float(n_e.count)) < 1e-9
