@@ -54,7 +54,6 @@ __device__ __forceinline__ float block_sum_256(float x, float* sh) {
 }
 
 __global__ void __launch_bounds__(256) ppo_head_kernel(const PpoHeadParams p) {
-  __shared__ float sh[8];
   __shared__ float s_sigma[kHeadMaxA], s_inv_var[kHeadMaxA], s_log_sigma[kHeadMaxA];
   if (threadIdx.x < p.A) {
     const float ls = p.log_std[threadIdx.x];
@@ -107,20 +106,34 @@ __global__ void __launch_bounds__(256) ppo_head_kernel(const PpoHeadParams p) {
     float* gm = p.g_mu + static_cast<size_t>(b) * p.A;
     for (int a = 0; a < p.A; ++a) gm[a] = g_logp * (act[a] - mu[a]) * s_inv_var[a];
   }
-  float* out = p.part + static_cast<size_t>(blockIdx.x) * (4 + p.A);
-  float t;
-  t = block_sum_256(sur, sh); if (threadIdx.x == 0) out[0] = t;
-  t = block_sum_256(vl, sh);  if (threadIdx.x == 0) out[1] = t;
-  t = block_sum_256(kl, sh);  if (threadIdx.x == 0) out[2] = t;
-  if (threadIdx.x == 0) out[3] = 0.f;
+  // all 3 + A block sums at once: warp shuffles per quantity, one shared-memory exchange, ONE barrier (fifteen
+  // back-to-back two-barrier block reductions were most of this kernel's 11 us); fixed order -> reproducible
+  __shared__ float s_w[8][4 + kHeadMaxA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto warp_sum = [](float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  };
+  {
+    const float a0 = warp_sum(sur), a1 = warp_sum(vl), a2 = warp_sum(kl);
+    if (lane == 0) { s_w[warp][0] = a0; s_w[warp][1] = a1; s_w[warp][2] = a2; s_w[warp][3] = 0.f; }
+  }
   for (int a = 0; a < p.A; ++a) {
     float x = 0.f;
     if (live) {
       const float d = p.actions[static_cast<size_t>(b) * p.A + a] - p.mu[static_cast<size_t>(b) * p.A + a];
       x = g_logp * (d * d * s_inv_var[a] - 1.f);      // d logp / d log_std = (a-mu)^2/sigma^2 - 1
     }
-    t = block_sum_256(x, sh);
-    if (threadIdx.x == 0) out[4 + a] = t;
+    x = warp_sum(x);
+    if (lane == 0) s_w[warp][4 + a] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 + p.A) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_w[w][threadIdx.x];
+    p.part[static_cast<size_t>(blockIdx.x) * (4 + p.A) + threadIdx.x] = t;
   }
 }
 
