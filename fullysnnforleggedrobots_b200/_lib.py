@@ -100,6 +100,8 @@ _SIGS = {
                           C.c_void_p]),
     "snn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                           C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "snn_gather_rows": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "snn_mlp_packed_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc)]),
     "snn_mlp_trace_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc), C.c_int64]),
     "snn_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(SnnMlpDesc), C.c_int64]),

@@ -478,6 +478,25 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values, con
   return SNN_OK;
 }
 
+int snn_gather_rows(int count, const void* const* src, void* const* dst, const int32_t* row_bytes, const int64_t* idx,
+                    int64_t n, void* stream) {
+  if (!src || !dst || !row_bytes || !idx) return fail(SNN_EINVAL, "null pointer");
+  if (count < 1 || count > 12 || n < 0) return fail(SNN_EINVAL, "snn_gather_rows: 1..12 fields");
+  if (n == 0) return SNN_OK;
+  GatherJobs jobs{};
+  jobs.count = count;
+  for (int k = 0; k < count; ++k) {
+    if (!src[k] || !dst[k] || row_bytes[k] <= 0 || row_bytes[k] % 4) return fail(SNN_EINVAL, "snn_gather_rows: rows must be whole 4-byte words");
+    jobs.j[k] = GatherJob{static_cast<const uint32_t*>(src[k]), static_cast<uint32_t*>(dst[k]), row_bytes[k] / 4};
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  gather_rows_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(jobs, reinterpret_cast<const long long*>(idx), n);
+  }
+  LAUNCH_CHECK("gather_rows_kernel");
+  return SNN_OK;
+}
+
 // ------------------------------------------------------------------ dense ELU critic on the tensor cores
 size_t snn_mlp_packed_bytes(const SnnMlpDesc* d) {
   MlpPlan p;

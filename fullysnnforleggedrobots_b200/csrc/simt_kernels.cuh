@@ -463,6 +463,25 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   }
 }
 
+// ------------------------------------------------------------------ minibatch permutation: all fields in one pass
+// RolloutStorage.mini_batch_generator gathers 9 tensors by the same random row indices, 20 times per update
+// (rollout_storage.py:174-182); here every field is gathered ONCE per update, and all of them by this one kernel:
+// warp = one output row, it copies that row of every field (4-byte words; rows are 4..192 bytes).
+struct GatherJob { const uint32_t* src; uint32_t* dst; int words; };
+struct GatherJobs { GatherJob j[12]; int count; };
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherJobs jobs, const long long* __restrict__ idx, long long n) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const long long src_row = idx[row];
+  for (int k = 0; k < jobs.count; ++k) {
+    const GatherJob jb = jobs.j[k];
+    const uint32_t* s = jb.src + src_row * jb.words;
+    uint32_t* d = jb.dst + row * jb.words;
+    for (int c = lane; c < jb.words; c += 32) d[c] = __ldg(s + c);
+  }
+}
+
 // ------------------------------------------------------------------ encoder input gradient
 // (the encoder PARAMETER gradients are produced by the DX_ENC epilogue, nm_gemm.cuh)
 // d obs[b,o] = sum_p g_a a (-(x-mean))/var   (RMA: the actor input is cat(obs, latent) and needs grad)

@@ -10,8 +10,11 @@ identical, the RMA copy adds observation histories), laid out for the B200 updat
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
+from . import _lib
 from . import engine as _engine
 
 
@@ -123,8 +126,21 @@ class RolloutStorage:
             self._perm = {k: torch.empty(n, *v.shape[2:], device=self.device, dtype=v.dtype)
                           for k, v in src.items() if v is not None}
             self._perm_n = n
-        for k, buf in self._perm.items():
-            torch.index_select(src[k].flatten(0, 1), 0, indices, out=buf)
+        if self.observations.is_cuda:
+            # all fields by ONE kernel (snn_gather_rows): the reference's nine `tensor[batch_idx]` gathers x 20
+            keys = list(self._perm.keys())
+            k = len(keys)
+            srcs = (C.c_void_p * k)(*[src[x].data_ptr() for x in keys])
+            dsts = (C.c_void_p * k)(*[self._perm[x].data_ptr() for x in keys])
+            nbytes = (C.c_int32 * k)(*[self._perm[x][0].numel() * self._perm[x].element_size() for x in keys])
+            dev = self.observations.device
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().snn_gather_rows(k, srcs, dsts, nbytes, C.c_void_p(indices.data_ptr()), n,
+                                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                           "snn_gather_rows")
+        else:
+            for k, buf in self._perm.items():
+                torch.index_select(src[k].flatten(0, 1), 0, indices, out=buf)
         out = dict(self._perm)
         if "critic_obs" not in out:
             out["critic_obs"] = out["obs"]

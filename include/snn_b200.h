@@ -108,6 +108,12 @@ int snn_gae(const float* rewards, const uint8_t* dones, const float* values,
             const float* last_values, int64_t S, int64_t N, float gamma, float lam,
             float* returns, float* advantages, int normalize, void* scratch, void* stream);
 
+/* Minibatch permutation (STO:148-184: `tensor[batch_idx]` for 9 tensors, per epoch and minibatch): gathers rows
+ * idx[0..n) of `count` (<= 12) row-major fields in ONE launch: dst[k][i] = src[k][idx[i]], rows of row_bytes[k]
+ * bytes (multiples of 4).  idx is int64 on the device; src/dst/row_bytes are host arrays of device pointers / sizes. */
+int snn_gather_rows(int count, const void* const* src, void* const* dst, const int32_t* row_bytes,
+                    const int64_t* idx, int64_t n, void* stream);
+
 /* ---- dense ELU MLP with one output: the critic (AMP:359-368, evaluate :428-430) -------------------------------
  * Linear -> ELU -> ... -> Linear(., 1).  Hidden layers run on tcgen05 with hi/lo bf16 operand planes (three
  * products, ~2^-16 relative); the 1-wide output layer and its backward are SIMT.  weight[i] / bias[i] for

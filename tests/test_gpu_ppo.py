@@ -217,3 +217,24 @@ def test_act_cuda_graph_is_consistent_and_sees_updated_weights():
         mu_eager = ac.act_inference(obs)
     assert rel_err(mu_graph.cpu(), mu_eager.cpu()) < 1e-5
     assert rel_err(mu_graph.cpu(), g["mu"][0]) > 1e-6         # and they did change
+
+
+def test_permute_once_gathers_every_field_like_index_select():
+    """snn_gather_rows (one launch for all fields) against torch.index_select, odd row widths and a ragged size."""
+    from fullysnnforleggedrobots_b200 import RolloutStorage
+    S, N, O, A = 5, 37, 7, 3
+    st = RolloutStorage(N, S, [O], [11], [A], device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for name in ("observations", "privileged_observations", "actions", "values", "returns", "actions_log_prob",
+                 "advantages", "mu", "sigma"):
+        t = getattr(st, name)
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g))
+    torch.manual_seed(11)
+    f, mb = st.permute_once(4)
+    torch.manual_seed(11)
+    idx = torch.randperm(4 * mb, device="cuda")
+    assert mb == S * N // 4
+    pairs = {"obs": st.observations, "critic_obs": st.privileged_observations, "actions": st.actions, "values": st.values,
+             "returns": st.returns, "logp": st.actions_log_prob, "adv": st.advantages, "mu": st.mu, "sigma": st.sigma}
+    for k, src in pairs.items():
+        assert torch.equal(f[k], src.flatten(0, 1).index_select(0, idx)), k
