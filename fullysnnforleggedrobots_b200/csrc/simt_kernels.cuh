@@ -205,10 +205,14 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
                                                     const float* __restrict__ dec_b, int dec_tanh, float* __restrict__ mu) {
   // one thread per (action, sample), samples fastest: the <= 2 spike words an action's population spans are
   // loaded coalesced across samples
+  // rate = count / T takes T + 1 values: one IEEE division per table entry instead of one per (neuron, sample)
+  // (the kernel is instruction-bound; same quotients, bit for bit)
+  __shared__ float s_rate[kMaxT + 1];
+  if (threadIdx.x <= T) s_rate[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), static_cast<float>(T));
+  __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * A) return;
   const int a0 = idx / B, b = idx - a0 * B;
-  const float invT = static_cast<float>(T);
   const long long R = tg.Rt;
   const int tile = b / tg.Bt;
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + (b - tile * tg.Bt);     // sample-step (0, b)
@@ -230,14 +234,14 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
       }
 #pragma unroll
       for (int pp = 0; pp < 16; ++pp)
-        if (pp < P) acc = __fmaf_rn(dec_w[n0 + pp], __fdiv_rn(static_cast<float>(cnt[pp]), invT), acc);
+        if (pp < P) acc = __fmaf_rn(dec_w[n0 + pp], s_rate[cnt[pp]], acc);
     } else {
       for (int pp = 0; pp < P; ++pp) {
         const int n = n0 + pp;
         int cnt = 0;
         for (int t = 0; t < T; ++t)
           cnt += (__ldg(bits + static_cast<size_t>(n >> 5) * R + r0 + static_cast<size_t>(t) * tg.Bt) >> (n & 31)) & 1u;
-        acc = __fmaf_rn(dec_w[n], __fdiv_rn(static_cast<float>(cnt), invT), acc);
+        acc = __fmaf_rn(dec_w[n], s_rate[cnt], acc);
       }
     }
     acc = __fadd_rn(acc, dec_b[a]);
