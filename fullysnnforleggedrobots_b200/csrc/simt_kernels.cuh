@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
                                                            float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
   constexpr int SPB = kTopRowsSPB;
   __shared__ float s_red[SPB][6][32];
+  __shared__ float s_rate[kMaxT + 1];        // count / T for every possible spike count (the kernel is issue-bound)
+  if (threadIdx.x <= T) s_rate[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), static_cast<float>(T));
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const int n0 = chunk * 64 + 2 * lane;                        // this thread's neurons n0, n0 + 1
@@ -410,11 +412,12 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   const size_t vstep = static_cast<size_t>(tg.Bt) * 16;        // float2 units between timesteps
   uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4;
   const uint32_t piece = static_cast<uint32_t>(lane >> 2);
-  float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, cnt0 = 0.f, cnt1 = 0.f, db0 = 0.f, db1 = 0.f;
+  float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, db0 = 0.f, db1 = 0.f;
+  int cnt0 = 0, cnt1 = 0;
   auto step = [&](int t, float2 v) {
     const float v0 = live ? v.x : 0.f, v1 = live ? v.y : 0.f;
-    cnt0 += v0 > 0.5f ? 1.f : 0.f;
-    cnt1 += v1 > 0.5f ? 1.f : 0.f;
+    cnt0 += v0 > 0.5f ? 1 : 0;
+    cnt1 += v1 > 0.5f ? 1 : 0;
     const float gs0 = gup0 - gvn0 * (0.75f * v0), gs1 = gup1 - gvn1 * (0.75f * v1);
     const float win0 = fabsf(__fsub_rn(v0, 0.5f)) < 0.5f ? 1.f : 0.f, win1 = fabsf(__fsub_rn(v1, 0.5f)) < 0.5f ? 1.f : 0.f;
     const float gv0 = gs0 * win0 + gvn0 * (v0 > 0.5f ? 0.f : 0.75f), gv1 = gs1 * win1 + gvn1 * (v1 > 0.5f ? 0.f : 0.75f);
@@ -453,8 +456,9 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     }
   }
   s_red[w][0][lane] = db0; s_red[w][1][lane] = db1;
-  s_red[w][2][lane] = G0 * __fdiv_rn(cnt0, Tf); s_red[w][3][lane] = G1 * __fdiv_rn(cnt1, Tf);
   s_red[w][4][lane] = G0; s_red[w][5][lane] = G1;
+  __syncthreads();                            // also publishes s_rate
+  s_red[w][2][lane] = G0 * s_rate[cnt0]; s_red[w][3][lane] = G1 * s_rate[cnt1];
   __syncthreads();
   if (threadIdx.x < 192) {
     const int k = threadIdx.x >> 5;                             // which of the six sums; lane = neuron pair
