@@ -410,8 +410,11 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
   const float2* vsrc = reinterpret_cast<const float2*>(volt + (static_cast<size_t>(n0 >> 5) * tg.Rt + r0) * 32 + (n0 & 31));
   const size_t vstep = static_cast<size_t>(tg.Bt) * 16;        // float2 units between timesteps
-  uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4;
   const uint32_t piece = static_cast<uint32_t>(lane >> 2);
+  // Bt % 16 == 0: every timestep's row r0 + t * Bt has the swizzle phase of r0, so the in-row offset is a constant
+  uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4 +
+                        ((piece ^ static_cast<uint32_t>(r0 & 7)) << 4);
+  const size_t gstep = static_cast<size_t>(tg.Bt) * 128;
   float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, db0 = 0.f, db1 = 0.f;
   int cnt0 = 0, cnt1 = 0;
   auto step = [&](int t, float2 v) {
@@ -426,8 +429,7 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     db0 += gc0; db1 += gc1;
     const uint32_t hp = pack_bf16x2(gc0, gc1);
     const uint32_t lp = pack_bf16x2(gc0 - __uint_as_float(hp << 16), gc1 - __uint_as_float(hp & 0xFFFF0000u));
-    const size_t r = r0 + static_cast<size_t>(t) * tg.Bt;
-    uint8_t* q = grow + static_cast<size_t>(t) * tg.Bt * 128 + ((piece ^ static_cast<uint32_t>(r & 7)) << 4);
+    uint8_t* q = grow + static_cast<size_t>(t) * gstep;
     *reinterpret_cast<uint32_t*>(q) = hp;
     *reinterpret_cast<uint32_t*>(q + g_plane) = lp;
   };
