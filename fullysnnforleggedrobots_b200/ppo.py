@@ -46,6 +46,8 @@ class _LazyNormal:
         self._d = None
 
     def __getattr__(self, name):           # log_prob, entropy, sample, ...
+        if name.startswith("__") or name in ("_d", "mean", "stddev"):    # copy / pickle probe a bare instance
+            raise AttributeError(name)
         if self._d is None:
             self._d = torch.distributions.Normal(self.mean, self.stddev, validate_args=False)
         return getattr(self._d, name)
