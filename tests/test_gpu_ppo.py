@@ -238,3 +238,25 @@ def test_permute_once_gathers_every_field_like_index_select():
              "returns": st.returns, "logp": st.actions_log_prob, "adv": st.advantages, "mu": st.mu, "sigma": st.sigma}
     for k, src in pairs.items():
         assert torch.equal(f[k], src.flatten(0, 1).index_select(0, idx)), k
+
+
+@pytest.mark.parametrize("B,A", [(4096, 12), (37, 3), (1, 1), (300, 64)])
+def test_sample_logprob_kernel_matches_torch_normal(B, A):
+    """snn_sample_logprob (the rollout step's sampling / log-prob / sigma tail) against torch.distributions.Normal
+    (actor_critic.py:398-421) fed the same noise."""
+    import ctypes as C
+
+    from fullysnnforleggedrobots_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(B + A)
+    mu = torch.randn(B, A, device="cuda", generator=g) * 2
+    log_std = torch.randn(A, device="cuda", generator=g) * 0.3 - 0.2
+    noise = torch.randn(B, A, device="cuda", generator=g)
+    actions, logp, sigma = torch.empty(B, A, device="cuda"), torch.empty(B, device="cuda"), torch.empty(B, A, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().snn_sample_logprob(p(mu), p(log_std), p(noise), B, A, p(actions), p(logp), p(sigma),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "snn_sample_logprob")
+    std = torch.exp(log_std)
+    dist = torch.distributions.Normal(mu, mu * 0. + std, validate_args=False)
+    assert rel_err(sigma.cpu(), dist.stddev.cpu()) < 1e-6
+    assert rel_err(actions.cpu(), (mu + std * noise).cpu()) < 1e-6
+    assert rel_err(logp.cpu(), dist.log_prob(actions).sum(-1).cpu()) < 1e-5
