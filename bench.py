@@ -103,9 +103,10 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_minibatch_runner(rows: int, seed: int = 0):
+def cpu_minibatch_runner(rows: int, seed: int = 0, device: str = "cpu"):
     """Oracle port of one PPO minibatch step (actor fwd with autograd graph, critic, losses, BPTT, clip, Adam)
-    of the reference on the host cores.  Returns a callable running one step on `rows` samples."""
+    of the reference on the host cores (or, for `--impl port-gpu`, the same torch ops on the CUDA device: the stock
+    PyTorch GPU path of SURVEY 8d).  Returns a callable running one step on `rows` samples."""
     from cases import Case, make_state_dict
     from oracle import ppo_oracle as P
     W = WORKLOAD
@@ -118,6 +119,7 @@ def cpu_minibatch_runner(rows: int, seed: int = 0):
         sd[f"critic.{2 * i}.weight"] = (torch.rand(dims[i + 1], dims[i], generator=g) * 2 - 1) * b
         sd[f"critic.{2 * i}.bias"] = (torch.rand(dims[i + 1], generator=g) * 2 - 1) * b
     sd["std"] = torch.ones(W["act_dim"])
+    sd = {k: v.to(device) for k, v in sd.items()}
     ac = P.OracleActorCritic(sd, spike_ts=W["spike_ts"])
     cfg = P.PPOConfig()
     opt = torch.optim.Adam(ac.parameters(), lr=cfg.learning_rate)
@@ -127,6 +129,7 @@ def cpu_minibatch_runner(rows: int, seed: int = 0):
              torch.randn(rows, 1, generator=g), torch.randn(rows, 1, generator=g),
              -0.5 * A * math.log(2 * math.pi) + torch.randn(rows, 1, generator=g) * 0.1 - 2.0,
              torch.randn(rows, A, generator=g) * 0.3, torch.ones(rows, A))
+    batch = tuple(t.to(device) for t in batch)
     state = {"lr": cfg.learning_rate}
 
     def step():
@@ -162,6 +165,41 @@ def run_reference(args):
         "config": {"workload": WORKLOAD["name"], **{k: v for k, v in WORKLOAD.items() if k != "name"}},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_port_gpu(args):
+    """The oracle port (the reference's torch ops, op for op) on the CUDA device with stock PyTorch kernels: the
+    same-device comparison SURVEY 8d asks for next to the CPU arm.  Full 24 576-row minibatch steps, CUDA events.
+    A baseline leg like `--impl reference`: none of this repo's kernels run here."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise RuntimeError("--impl port-gpu needs a CUDA device")
+    torch.backends.cuda.matmul.allow_tf32 = False       # fp32 like the CPU arm and like our parity mode
+    torch.backends.cudnn.allow_tf32 = False
+    rows = WORKLOAD["num_envs"] * WORKLOAD["steps_per_env"] // WORKLOAD["mini_batches"]
+    step = cpu_minibatch_runner(rows, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    line = {
+        "impl": "port-gpu", "metric": METRIC, "value": rows / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "rows_per_step": rows,
+                   "note": "one PPO minibatch step (actor fwd + BPTT by autograd, critic, losses, clip, Adam) of the "
+                           "oracle port with stock PyTorch CUDA kernels, TF32 off; a step here is ONE minibatch, "
+                           "our arm's step is a whole update of 20"},
     }
     print(json.dumps(line))
     return 0
@@ -419,11 +457,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "port-gpu"])
     ap.add_argument("--quick", action="store_true", help="resident leg only (for ncu runs): no e2e / act / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "port-gpu":
+        return run_port_gpu(args)
     return run_ours(args)
 
 

@@ -112,12 +112,13 @@ def lif_layers(enc_spikes: torch.Tensor, p: ActorParams, tr: Optional[Traces] = 
     """
     T, B = enc_spikes.shape[0], enc_spikes.shape[1]
     L = len(p.weights)
-    c = [torch.zeros(B, w.shape[0]) for w in p.weights]
-    v = [torch.zeros(B, w.shape[0]) for w in p.weights]
-    s = [torch.zeros(B, w.shape[0]) for w in p.weights]
+    dev = enc_spikes.device
+    c = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
+    v = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
+    s = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
     vt = [[] for _ in range(L)]
     st = [[] for _ in range(L)]
-    acc = torch.zeros(B, p.weights[-1].shape[0])
+    acc = torch.zeros(B, p.weights[-1].shape[0], device=dev)
     for t in range(T):
         x = enc_spikes[t]
         for l in range(L):
@@ -263,10 +264,11 @@ def actor_forward_autograd(obs: torch.Tensor, p: ActorParams):
     a = torch.exp(-0.5 * (x - p.enc_mean).pow(2) / var).reshape(B, -1)
     u = torch.zeros_like(a)
     L = len(p.weights)
-    c = [torch.zeros(B, w.shape[0]) for w in p.weights]
-    v = [torch.zeros(B, w.shape[0]) for w in p.weights]
-    s = [torch.zeros(B, w.shape[0]) for w in p.weights]
-    acc = torch.zeros(B, p.weights[-1].shape[0])
+    dev = obs.device
+    c = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
+    v = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
+    s = [torch.zeros(B, w.shape[0], device=dev) for w in p.weights]
+    acc = torch.zeros(B, p.weights[-1].shape[0], device=dev)
     for _ in range(p.spike_ts):
         u = u + a
         es = _EncSpike.apply(u)
