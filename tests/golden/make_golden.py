@@ -167,17 +167,32 @@ def run_ppo_case(pc):
     return out
 
 
-def main():
+def _emit(path, out, check):
+    """Write the fixture, or (--check) compare a fresh run of the reference against the committed file."""
+    if not check:
+        np.savez_compressed(path, **out)
+        return "written"
+    ref = dict(np.load(path))
+    assert set(ref) == set(out), f"{path}: keys differ: {sorted(set(ref) ^ set(out))}"
+    worst = 0.0
+    for k, v in out.items():
+        a, b = np.asarray(v), ref[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, f"{path}:{k}: {a.dtype}{a.shape} vs {b.dtype}{b.shape}"
+        if not np.array_equal(a, b):
+            d = float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
+            worst = max(worst, d / (float(np.max(np.abs(b.astype(np.float64)))) + 1e-30))
+    return "bit-identical" if worst == 0.0 else f"max rel diff {worst:.2e}"
+
+
+def main(check=False):
+    """`--check`: re-run the unmodified reference here and compare with the committed fixtures instead of writing."""
     for c in CASES:
         out = run_actor_case(c)
         path = os.path.join(HERE, f"actor_{c.name}.npz")
-        np.savez_compressed(path, **out)
-        print(f"{c.name:22s} -> {os.path.getsize(path) / 1024:.1f} KiB  mu[0]={out['mu'][0][:3]}")
-    np.savez_compressed(os.path.join(HERE, "gae_cassie.npz"), **run_gae_case())
-    print("gae_cassie done")
-    np.savez_compressed(os.path.join(HERE, f"{PPO_CASE.name}.npz"), **run_ppo_case(PPO_CASE))
-    print("ppo case done")
+        print(f"{c.name:22s} {_emit(path, out, check)}  mu[0]={out['mu'][0][:3]}")
+    print("gae_cassie", _emit(os.path.join(HERE, "gae_cassie.npz"), run_gae_case(), check))
+    print(PPO_CASE.name, _emit(os.path.join(HERE, f"{PPO_CASE.name}.npz"), run_ppo_case(PPO_CASE), check))
 
 
 if __name__ == "__main__":
-    main()
+    main(check="--check" in sys.argv[1:])

@@ -24,7 +24,7 @@ from cases import (AMP_CASE, AMP_MIN_STD, AMP_OBS_DIM, AMP_DISC_HIDDEN, AMP_REWA
 from make_golden import import_ref  # noqa: E402
 
 
-def main():
+def main(check=False):
     pc = AMP_CASE
     import_ref("amp", "modules.actor_critic")
     mods = importlib.import_module("rsl_rl.modules")
@@ -87,9 +87,9 @@ def main():
         out["disc_final." + k] = v.detach().numpy().copy()
     out["norm_mean"], out["norm_var"], out["norm_count"] = norm.mean.copy(), norm.var.copy(), np.float64(norm.count)
     path = os.path.join(HERE, f"{pc.name}.npz")
-    np.savez_compressed(path, **out)
-    print("amp case ->", path, os.path.getsize(path), "bytes; update() =", res, "lr", alg.learning_rate)
+    from make_golden import _emit          # writes, or with --check compares a fresh reference run with the file
+    print("amp case", _emit(path, out, check), "; update() =", res, "lr", alg.learning_rate)
 
 
 if __name__ == "__main__":
-    main()
+    main(check="--check" in sys.argv[1:])
