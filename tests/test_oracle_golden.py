@@ -93,3 +93,20 @@ def test_gae_matches_reference_storage():
     ret, adv = O.gae_returns(rewards, dones, values, last, 0.99, 0.95)
     assert rel_err(ret, g["returns"]) < 1e-6
     assert rel_err(adv, g["advantages"]) < 1e-6
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="the reference tree is not on this box")
+def test_committed_fixtures_are_what_the_reference_produces_here():
+    """Re-run the unmodified reference modules (make_golden.py --check): every committed fixture must come back."""
+    import os
+    import subprocess
+    import sys
+    gold = __import__("helpers").GOLD
+    r = subprocess.run([sys.executable, os.path.join(gold, "make_golden.py"), "--check"], capture_output=True,
+                       text=True, timeout=600, cwd=gold)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == len(CASES) + 2
+    # same torch build as the one that wrote them -> bit-identical; another build may differ in the last ulp
+    assert all(("bit-identical" in l) or ("max rel diff" in l and float(l.split("max rel diff")[1].split()[0]) < 1e-5)
+               for l in lines), r.stdout
