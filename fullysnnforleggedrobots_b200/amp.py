@@ -324,6 +324,7 @@ class AMPPPO(PPO):
         stats = self._stats.tolist()                       # the host syncs of the update: here ...
         amp = self._amp_stats.tolist()
         self._lr = self.optimizer.sync_lr_from_device()    # ... and here
+        self._params_epoch += 1
         self.storage.clear()
         return (stats[5] / num_updates, stats[4] / num_updates, amp[0] / num_updates, amp[1] / num_updates,
                 amp[2] / num_updates, amp[3] / num_updates)

@@ -223,8 +223,8 @@ class CriticEngine:
     """Dense ELU critic (Linear -> ELU -> ... -> Linear(., 1)) on the tensor-core kernels (snn_mlp_*).
 
     `linears` is the list of nn.Linear modules of the reference's `critic` nn.Sequential
-    (AMP/.../modules/actor_critic.py:359-368).  Used by the fused PPO update; `ActorCritic.evaluate` in the
-    rollout keeps the torch path (small batches, no gradient)."""
+    (AMP/.../modules/actor_critic.py:359-368).  Used by the fused PPO update and by the critic branch of the
+    graphed rollout step (PPO._act_fused); a direct `ActorCritic.evaluate` call keeps the torch path."""
 
     def __init__(self, linears):
         if len(linears) < 2 or linears[-1].out_features != 1:

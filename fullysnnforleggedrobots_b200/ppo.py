@@ -86,6 +86,10 @@ class PPO:
         self.fused_critic = fused_critic
         self.act_cuda_graph = use_cuda_graph   # rollout step (act) replayed as one CUDA graph
         self._act_state = None
+        # rollout step: the critic branch on the tensor-core MLP kernels (snn_mlp_fwd) instead of torch / cuBLAS SIMT
+        # sgemm (SNN_ACT_CRITIC=torch: the torch branch)
+        self.act_fused_critic = fused_critic and os.environ.get("SNN_ACT_CRITIC", "tc") != "torch"
+        self._params_epoch = 0                 # bumped by every update(): the act graph's critic planes follow it
         # critic kernels on a second stream (parallel CUDA-graph branch); SNN_OVERLAP_CRITIC=0 serialises them
         self.overlap_critic = os.environ.get("SNN_OVERLAP_CRITIC", "1") != "0"
         # capture the actor chain on a high-priority stream: where both chains have thread blocks pending, the
@@ -144,19 +148,29 @@ class PPO:
         side = st["side"]
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            o["values"].copy_(ac.evaluate(st["cobs"]))
+            if st.get("ce") is not None:
+                st["ce"].forward(st["cobs"], out_value=o["values"].view(-1), out_trace=st["ctrace"])
+            else:
+                o["values"].copy_(ac.evaluate(st["cobs"]))
         layers = actor.snn.linear_layers()
-        # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack only
-        # if a weight changed" check; _act_graphed runs the same check on the host before every replay)
-        actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
-                             [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
-                             train=False, out_mu=o["mu"])
-        noise = torch.randn_like(o["mu"])
-        B, A = o["mu"].shape
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A, _p(o["actions"]),
-                                                     _p(o["logp"]), _p(o["sigma"]), C.c_void_p(cur.cuda_stream)),
-                       "snn_sample_logprob")
+        hp = st.get("hp")                      # actor chain on a high-priority stream (SNN_ACT_PRIO=1), else on `cur`
+        if hp is not None:
+            hp.wait_stream(cur)
+        with torch.cuda.stream(hp if hp is not None else cur):
+            run = torch.cuda.current_stream(dev)
+            # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack
+            # only if a weight changed" check; _act_graphed runs the same check on the host before every replay)
+            actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
+                                 [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
+                                 train=False, out_mu=o["mu"])
+            noise = torch.randn_like(o["mu"])
+            B, A = o["mu"].shape
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A,
+                                                         _p(o["actions"]), _p(o["logp"]), _p(o["sigma"]),
+                                                         C.c_void_p(run.cuda_stream)), "snn_sample_logprob")
+        if hp is not None:
+            cur.wait_stream(hp)
         cur.wait_stream(side)
 
     @staticmethod
@@ -176,14 +190,30 @@ class PPO:
             B, A = obs.shape[0], self.actor_critic.actor.act_dim
             st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0,
                   "packed": torch.empty(3 * B * A + 2 * B, dtype=torch.float32, device=obs.device),
-                  "side": torch.cuda.Stream(device=obs.device)}
+                  "side": torch.cuda.Stream(device=obs.device),
+                  "hp": torch.cuda.Stream(device=obs.device, priority=-1)
+                  if os.environ.get("SNN_ACT_PRIO", "0") == "1" else None}
             st["cobs"] = st["obs"] if key[2] else critic_obs.clone()
             st["views"] = self._act_views(st["packed"], B, A)
+            st["ce"] = None
+            if self.act_fused_critic and isinstance(self.actor_critic.critic, nn.Sequential) \
+                    and st["cobs"].dtype == torch.float32:
+                ce = CriticEngine.from_sequential(self.actor_critic.critic)
+                if ce is not None:
+                    st["ce"], st["ce_ver"] = ce, None
+                    st["ctrace"] = torch.empty(ce.trace_bytes(B), dtype=torch.uint8, device=obs.device)
             self._act_state = st
         st["obs"].copy_(obs)
         if not key[2]:
             st["cobs"].copy_(critic_obs)
         st["calls"] += 1
+        ce = st["ce"]
+        if ce is not None:
+            # operand planes of the critic: re-derived when an update() ran or a parameter was written through torch
+            ver = (self._params_epoch, sum(l.weight._version + l.bias._version for l in ce.linears))
+            if st["ce_ver"] != ver:
+                ce.repack()
+                st["ce_ver"] = ver
         if st["graph"] is None:
             if st["calls"] < 2:                       # first call eager (lazy init, weight packing)
                 return self._act_body(st["obs"], st["cobs"])
@@ -529,6 +559,7 @@ class PPO:
                 self._step_generic(batch)
         stats = self._stats.tolist()                       # the one host sync of the update
         self._lr = self.optimizer.sync_lr_from_device()
+        self._params_epoch += 1
         self.storage.clear()
         return stats[5] / num_updates, stats[4] / num_updates
 
@@ -622,6 +653,7 @@ class PPORMA(PPO):
         num_updates = self.num_learning_epochs * self.num_mini_batches
         stats = self._stats.tolist()
         self._lr = self.optimizer.sync_lr_from_device()
+        self._params_epoch += 1
         self.storage.clear()
         return (stats[5] / num_updates, stats[4] / num_updates,
                 float(adapt_sum) / (num_updates * self.num_adaptation_module_substeps))

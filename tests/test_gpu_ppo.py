@@ -215,8 +215,36 @@ def test_act_cuda_graph_is_consistent_and_sees_updated_weights():
         alg.act(obs, obs)
         mu_graph = alg.transition.action_mean.clone()
         mu_eager = ac.act_inference(obs)
+        v_graph = alg.transition.values.clone()
+        v_eager = ac.evaluate(obs)
     assert rel_err(mu_graph.cpu(), mu_eager.cpu()) < 1e-5
     assert rel_err(mu_graph.cpu(), g["mu"][0]) > 1e-6         # and they did change
+    # the critic branch of the graph (tensor-core MLP kernels, own operand planes) follows update() ...
+    assert alg._act_state["ce"] is not None
+    assert rel_err(v_graph.cpu(), v_eager.cpu()) < 1e-4
+    assert rel_err(v_graph.cpu(), g["values"][0]) > 1e-6
+    # ... and a parameter written through torch (load_state_dict, manual edits)
+    with torch.no_grad():
+        ac.critic[0].bias.add_(0.25)
+    with torch.inference_mode():
+        alg.act(obs, obs)
+        v2 = alg.transition.values.clone()
+        v2_eager = ac.evaluate(obs)
+    assert rel_err(v2.cpu(), v2_eager.cpu()) < 1e-4 and rel_err(v2.cpu(), v_graph.cpu()) > 1e-4
+
+
+def test_act_torch_critic_branch_switch(monkeypatch):
+    """SNN_ACT_CRITIC=torch keeps the rollout's critic on torch (cuBLAS); same values within fp32 noise."""
+    monkeypatch.setenv("SNN_ACT_CRITIC", "torch")
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    obs = ro["obs"][0].cuda()
+    with torch.inference_mode():
+        for k in range(4):
+            alg.act(obs, obs)
+            assert rel_err(alg.transition.values.cpu(), g["values"][0]) < 1e-5
+            alg.transition.clear()
+    assert alg._act_state["graph"] is not None and alg._act_state["ce"] is None
 
 
 def test_permute_once_gathers_every_field_like_index_select():
