@@ -153,24 +153,17 @@ class PPO:
             else:
                 o["values"].copy_(ac.evaluate(st["cobs"]))
         layers = actor.snn.linear_layers()
-        hp = st.get("hp")                      # actor chain on a high-priority stream (SNN_ACT_PRIO=1), else on `cur`
-        if hp is not None:
-            hp.wait_stream(cur)
-        with torch.cuda.stream(hp if hp is not None else cur):
-            run = torch.cuda.current_stream(dev)
-            # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack
-            # only if a weight changed" check; _act_graphed runs the same check on the host before every replay)
-            actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
-                                 [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
-                                 train=False, out_mu=o["mu"])
-            noise = torch.randn_like(o["mu"])
-            B, A = o["mu"].shape
-            with torch.cuda.device(dev):
-                _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A,
-                                                         _p(o["actions"]), _p(o["logp"]), _p(o["sigma"]),
-                                                         C.c_void_p(run.cuda_stream)), "snn_sample_logprob")
-        if hp is not None:
-            cur.wait_stream(hp)
+        # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack only
+        # if a weight changed" check; _act_graphed runs the same check on the host before every replay)
+        actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
+                             [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
+                             train=False, out_mu=o["mu"])
+        noise = torch.randn_like(o["mu"])
+        B, A = o["mu"].shape
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A, _p(o["actions"]),
+                                                     _p(o["logp"]), _p(o["sigma"]), C.c_void_p(cur.cuda_stream)),
+                       "snn_sample_logprob")
         cur.wait_stream(side)
 
     @staticmethod
@@ -190,9 +183,7 @@ class PPO:
             B, A = obs.shape[0], self.actor_critic.actor.act_dim
             st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0,
                   "packed": torch.empty(3 * B * A + 2 * B, dtype=torch.float32, device=obs.device),
-                  "side": torch.cuda.Stream(device=obs.device),
-                  "hp": torch.cuda.Stream(device=obs.device, priority=-1)
-                  if os.environ.get("SNN_ACT_PRIO", "0") == "1" else None}
+                  "side": torch.cuda.Stream(device=obs.device)}
             st["cobs"] = st["obs"] if key[2] else critic_obs.clone()
             st["views"] = self._act_views(st["packed"], B, A)
             st["ce"] = None
