@@ -37,5 +37,17 @@ with torch.inference_mode():
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / REP)
-print(json.dumps({"critic_branch": "tc" if alg._act_state.get("ce") is not None else "torch", "envs": N,
+    # the replayed graph alone (no input copy, no output clone, no host logic of PPO.act)
+    g = alg._act_state["graph"]
+    gbest = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(REP):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gbest = min(gbest, e0.elapsed_time(e1) / REP)
+print(json.dumps({"graph_only_us": gbest * 1e3, "critic_branch": "tc" if alg._act_state.get("ce") is not None else "torch", "envs": N,
                   "ppo_act_us": best * 1e3, "env_steps_per_s": N / (best * 1e-3), "value_rel_err_vs_torch": err}))
