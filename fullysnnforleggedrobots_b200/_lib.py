@@ -14,6 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsnn_b200.so")
+# tools-only build with -DSNN_ABLATE (work-skipping SNN_DBG switches + barrier-wait cycle counters), selected with
+# SNN_LIB=ablate; tests and bench.py check snn_build_flags() == 0, i.e. that they run the release library
+ABLATE_LIB_PATH = os.path.join(LIB_DIR, "libsnn_b200_ablate.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SNN_MAX_LAYERS = 8
@@ -65,12 +68,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -> lib/libsnn_b200.so (sm_100a only; cross-compiles without a GPU)."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, ablate: bool = False) -> str:
+    """nvcc -> lib/libsnn_b200.so (sm_100a only; cross-compiles without a GPU).
+    ablate=True builds lib/libsnn_b200_ablate.so with -DSNN_ABLATE instead (tools only)."""
+    out = ABLATE_LIB_PATH if ablate else LIB_PATH
+    if not force and not ablate and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = ["nvcc", *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "api.cu")]
+    cmd = ["nvcc", *NVCC_FLAGS, "-I", INCLUDE, "-o", out, os.path.join(CSRC, "api.cu")]
+    if ablate:
+        cmd.insert(1, "-DSNN_ABLATE")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -78,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB_PATH
+    return out
 
 
 _lib = None
@@ -87,6 +94,7 @@ _lock = threading.Lock()
 _SIGS = {
     "snn_last_error": (C.c_char_p, []),
     "snn_abi_version": (C.c_int, []),
+    "snn_build_flags": (C.c_int, []),
     "snn_packed_weights_bytes": (C.c_size_t, [C.POINTER(SnnDesc)]),
     "snn_trace_bytes": (C.c_size_t, [C.POINTER(SnnDesc), C.c_int64]),
     "snn_workspace_bytes": (C.c_size_t, [C.POINTER(SnnDesc), C.c_int64, C.c_int]),
@@ -133,11 +141,12 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
+                path = ABLATE_LIB_PATH if os.environ.get("SNN_LIB") == "ablate" else LIB_PATH
+                if not os.path.exists(path):
                     raise RuntimeError(
-                        f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a).  The spiking actor has no CPU or PyTorch fallback.")
-                l = C.CDLL(LIB_PATH)
+                l = C.CDLL(path)
                 for name, (res, args) in _SIGS.items():
                     fn = getattr(l, name)
                     fn.restype = res

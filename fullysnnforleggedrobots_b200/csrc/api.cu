@@ -108,6 +108,17 @@ int device_ready(int* num_sms) {
   return SNN_OK;
 }
 
+// SM count the buffer-size queries plan for: the current device's (so that a query and the launch that follows agree on
+// row_parts / dw_max_ctas on any cc 10.x part), or 148 (B200) when no device is visible (CPU-only build box).
+int plan_sms() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    return sms;
+  cudaGetLastError();
+  return 148;
+}
+
 constexpr int kMlpMaxCtasDefault = 0;      // 0 = no cap
 unsigned long long* g_dbg_out = nullptr;   // set by snn_debug_set_cycle_buffer (tools only)
 
@@ -119,10 +130,16 @@ int mlp_sms(int sms) {
   return cap > 0 ? cap : sms;      // cap > SM count: one item per CTA (short CTAs that free their SM early)
 }
 
+// Work-skipping ablation switches (SNN_DBG) exist only in the -DSNN_ABLATE tools build (a separate library file): the
+// release binary that tests and bench.py load has no such code path.
 int debug_mask() {
+#ifdef SNN_ABLATE
   static int m = -1;
   if (m < 0) { const char* e = getenv("SNN_DBG"); m = e ? atoi(e) : 0; }
   return m;
+#else
+  return 0;
+#endif
 }
 
 struct Deferred {
@@ -241,20 +258,27 @@ extern "C" {
 
 const char* snn_last_error(void) { return g_err; }
 int snn_abi_version(void) { return 1; }
+int snn_build_flags(void) {
+#ifdef SNN_ABLATE
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 size_t snn_packed_weights_bytes(const SnnDesc* d) {
   SnnPlan p;
-  if (d == nullptr || make_plan(*d, 1, 148, &p) != SNN_OK) return 0;
+  if (d == nullptr || make_plan(*d, 1, plan_sms(), &p) != SNN_OK) return 0;
   return p.packed_bytes;
 }
 size_t snn_trace_bytes(const SnnDesc* d, int64_t B) {
   SnnPlan p;
-  if (d == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return 0;
+  if (d == nullptr || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return 0;
   return p.trace_bytes;
 }
 size_t snn_workspace_bytes(const SnnDesc* d, int64_t B, int backward) {
   SnnPlan p;
-  if (d == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return 0;
+  if (d == nullptr || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return 0;
   return backward ? p.ws_bwd_bytes : p.ws_fwd_bytes;
 }
 
@@ -333,32 +357,18 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   const int top = p.L - 1;
   {
     const LayerPlan& lp = p.layer[top];
-    const int nbg = p.Bt / kTopScanSPT;
-    static int gpb_max = -1;
-    if (gpb_max < 0) { const char* e = getenv("SNN_TOPSCAN_GPB"); gpb_max = e ? atoi(e) : 1; if (gpb_max < 1 || gpb_max > kTopScanGPB) gpb_max = kTopScanGPB; }
-    int gpb = gpb_max;
-    while (nbg % gpb) --gpb;                       // T = 5: Bt = 48 -> 6 groups per tile
-    static int rows_variant = -1;      // SNN_TOPSCAN_ROWS=0: the thread = neuron kernel (A/B runs)
-    if (rows_variant < 0) { const char* e = getenv("SNN_TOPSCAN_ROWS"); rows_variant = e ? atoi(e) : 1; }
-    int nrows = p.ntile * nbg / gpb;
+    const int nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     const float* volt = reinterpret_cast<const float*>(at(trace, lp.tr_volt));
-    if (rows_variant) {
-      nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
-      const dim3 grd(nrows, lp.NP / 64);
-      if (p.T == 5)
-        top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
-      else
-        top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
-    } else {
-      top_scan_kernel<<<dim3(nrows, lp.NP / 128), 128 * gpb, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A,
-                                           p.Pd, lp.NP, p.T, gpb, at(workspace, p.ws_g[top]), p.ws_g_plane[top],
-                                           dbpart_of(top), small);
+    const dim3 grd(nrows, lp.NP / 64);
+    if (p.T == 5)
+      top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                  at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+    else
+      top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                  at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
     }
-    }
-    LAUNCH_CHECK("top_scan_kernel");
+    LAUNCH_CHECK("top_scan_rows_kernel");
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
     df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
     df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
@@ -435,7 +445,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     }
     LAUNCH_CHECK("dw_gemm_multi_kernel");
   }
-  // ---- d obs (the encoder parameter gradients came out of the DX_ENC epilogue, the decoder's out of top_scan_kernel)
+  // ---- d obs (the encoder parameter gradients came out of the DX_ENC epilogue, the decoder's out of top_scan_rows_kernel)
   {
     if (g->obs != nullptr) {
       const int n = Bi * p.O;
@@ -771,11 +781,19 @@ int snn_profile_read(double* ms, double* flops, int64_t* launches) {
 
 int64_t snn_launch_count(void) { return g_launch_count; }
 
-int snn_debug_set_cycle_buffer(void* buf) { g_dbg_out = static_cast<unsigned long long*>(buf); return SNN_OK; }
+int snn_debug_set_cycle_buffer(void* buf) {
+#ifdef SNN_ABLATE
+  g_dbg_out = static_cast<unsigned long long*>(buf);
+  return SNN_OK;
+#else
+  (void)buf;
+  return fail(SNN_EINVAL, "cycle counters exist only in the -DSNN_ABLATE tools build");
+#endif
+}
 
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out) {
   SnnPlan p;
-  if (d == nullptr || out == nullptr || make_plan(*d, B, 148, &p) != SNN_OK) return fail(SNN_EINVAL, "bad descriptor");
+  if (d == nullptr || out == nullptr || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return fail(SNN_EINVAL, "bad descriptor");
   // [0]=L [1]=T [2]=Bt [3]=CT [4]=ntile [5]=Rt [6]=K0P [7]=enc_bits_off then per layer: NP, KP, bits_off, volt_off
   const int need = 8 + 4 * p.L;
   if (n_out < need) return fail(SNN_EINVAL, "output array too small");

@@ -8,20 +8,11 @@
 //   B = input spikes x (exact in bf16), expanded in shared memory from the bit-packed trace
 //       (rows = r = MMA-K, cols = k = MMA-N).
 // One CTA owns one [128 x <=256] fp32 output tile in TMEM and a contiguous slice of r (split-K over
-// the batch); partial tiles go to a workspace and are summed by reduce_partials_kernel — a fixed
+// the batch); partial tiles go to a workspace and are summed by multi_reduce_partials_kernel — a fixed
 // order, so gradients are bit-reproducible run to run.
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
-
-#ifndef SNN_TWAIT
-#define SNN_TWAIT(bar, par, slot)                                   \
-  do {                                                              \
-    const long long t0__ = clock64();                               \
-    mbar_wait(bar, par);                                            \
-    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
-  } while (0)
-#endif
 
 namespace snn {
 
@@ -64,8 +55,10 @@ __device__ __forceinline__ void dw_gemm_body(const DwGemmParams& p, const int ct
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(empty_bits + kDwBitStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SNN_ABLATE
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
+#endif
   const int tile = cta / p.splits, split = cta - tile * p.splits;
   const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
   const int kc0 = nt * 4;                                   // first 64-wide k chunk of this tile
@@ -216,12 +209,14 @@ __device__ __forceinline__ void dw_gemm_body(const DwGemmParams& p, const int ct
       }
     }
   }
+#ifdef SNN_ABLATE
   if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 3);
     unsigned long long* o = p.dbg_out + static_cast<size_t>(cta) * 16 + role * 4;
     o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
     o[3] = static_cast<unsigned long long>(clock64() - t_start);
   }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
@@ -243,27 +238,6 @@ __global__ void __launch_bounds__(384, 1) dw_gemm_multi_kernel(const DwJobs jobs
   int l = 0;
   while (l + 1 < jobs.count && static_cast<int>(blockIdx.x) >= jobs.first_cta[l + 1]) ++l;
   dw_gemm_body<false>(jobs.j[l], static_cast<int>(blockIdx.x) - jobs.first_cta[l]);
-}
-
-// dW[n][k] = sum_s partial[(tile * splits + s)][n % 128][k % 256]; also reduces the per-CTA bias partials.
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int n_tiles, int N, int K,
-                                       float* __restrict__ dW) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = blockIdx.y;
-  if (k >= K || n >= N) return;
-  const int tile = (n >> 7) * n_tiles + (k >> 8);
-  const float* src = partial + (static_cast<size_t>(tile) * splits * 128 + (n & 127)) * 256 + (k & 255);
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
-  dW[static_cast<size_t>(n) * K + k] = acc;
-}
-
-__global__ void reduce_db_kernel(const float* __restrict__ part, int nparts, int NP, int N, float* __restrict__ db) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float acc = 0.f;
-  for (int s = 0; s < nparts; ++s) acc += part[static_cast<size_t>(s) * NP + n];
-  db[n] = acc;
 }
 
 }  // namespace snn

@@ -33,15 +33,6 @@
 #include "plan.cuh"
 #include "umma.cuh"
 
-#ifndef SNN_TWAIT
-#define SNN_TWAIT(bar, par, slot)                                   \
-  do {                                                              \
-    const long long t0__ = clock64();                               \
-    mbar_wait(bar, par);                                            \
-    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
-  } while (0)
-#endif
-
 namespace snn {
 
 enum { NM_FWD = 0, NM_DX = 1, NM_DX_ENC = 2 };
@@ -158,8 +149,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   const int nsub = (p.TB + 255) / 256;                 // sample-step sub-tiles of <= 256 columns (2 only when T > 16)
   const int mt = blockIdx.x % p.nmt;                   // this CTA's neuron tile
   const int tile0 = blockIdx.x / p.nmt, tstep = gridDim.x / p.nmt;
+#ifdef SNN_ABLATE
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
+#endif
 
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -271,7 +264,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
               tc_fence_after_sync();
               if (elect_one()) {
                 const uint32_t a_lo = w_ring_lo + ws * (C::W_STAGE >> 4);
-                if (!(p.dbg & 1)) {
+                if (!(SNN_DBG_MASK(p) & 1)) {
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16)
                     umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, (kc > 0 || pl > 0 || k16 > 0) ? 1u : 0u);
@@ -299,7 +292,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
                 const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
                 uint32_t acc = kc > 0 ? 1u : 0u;
-                if (!(p.dbg & 1)) {
+                if (!(SNN_DBG_MASK(p) & 1)) {
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16)
                     for (int pl = 0; pl < npl; ++pl) {
@@ -330,7 +323,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 const int ncols = min(256, p.TB - sub * 256);
                 const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
                 const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
-                if (!(p.dbg & 1)) {
+                if (!(SNN_DBG_MASK(p) & 1)) {
                   // W^T ~ (a_hi + a_lo), g_c ~ (b_hi + b_lo): hi*hi + lo*hi on the g_c hi plane, then hi*lo on its lo plane
                   // (lo*lo < 2^-16 relative)
                   const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
@@ -393,7 +386,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         // No validity masks: samples >= B have g_c == 0 in the layer above (the top scan writes zeros there), so
         // their accumulators are exactly 0, and with the zero initial state every g_c written here is 0 again.
         const int nb = bg0 < nbg ? (nbg - bg0 + bgstep - 1) / bgstep : 0;
-        const int nsteps = (p.dbg & 2) ? 0 : nb * p.T;
+        const int nsteps = (SNN_DBG_MASK(p) & 2) ? 0 : nb * p.T;
         // g_c image [MP/64][Rt rows][128 B]: this thread's neuron is bf16 column n % 64 of chunk n / 64; a warp's 32
         // neurons are 64 contiguous bytes of a row, so every store below is one coalesced 64-byte request.
         // xo[jj]: byte offset of this neuron inside row (8 i + jj) of an 8-row group (128B swizzle: piece ^= row % 8)
@@ -407,7 +400,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         int l_bi = 0, l_t = p.T - 1;          // cursor of the loads
         int s_bi = 0, s_t = p.T - 1;          // cursor of the recurrence
         auto loadv = [&](float (&buf)[16]) {
-          if (l_bi < nb && !(p.dbg & 32)) {
+          if (l_bi < nb && !(SNN_DBG_MASK(p) & 32)) {
             const float* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 32;
 #pragma unroll
             for (int j = 0; j < 16; ++j) buf[j] = __ldg(src + j * 32);
@@ -438,7 +431,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             gcn[j] = gc[j];
             dbsum += gc[j];
           }
-          if (!(p.dbg & 16)) {
+          if (!(SNN_DBG_MASK(p) & 16)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               // packed conversions: two sample-steps per cvt; hi = bf16(g_c), lo = bf16(g_c - hi)
@@ -462,7 +455,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           if (sidx + 1 < nsteps) { step(vb1); loadv(vb1); }
         }
       }
-      for (int bg = (MODE == NM_DX || (p.dbg & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
+      for (int bg = (MODE == NM_DX || (SNN_DBG_MASK(p) & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
         const int col0 = bg * 16;
         // bit j: sample b_tile + col0 + j exists
         const int nlive = p.B - (b_tile + col0);
@@ -491,9 +484,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
               if (lane == j) myword = w;
             }
             const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
-            if (lane < 16 && !(p.dbg & 256))
+            if (lane < 16 && !(SNN_DBG_MASK(p) & 256))
               p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
-            if (p.v_out != nullptr && !(p.dbg & 128)) {
+            if (p.v_out != nullptr && !(SNN_DBG_MASK(p) & 128)) {
               // [neuron / 32][sample-step][32]: this warp's 16 sample-steps are 16 consecutive 128-byte rows
               float* dst = p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32 + lane;
 #pragma unroll
@@ -614,7 +607,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           if (lane == 0) mbar_arrive(&bits_empty[s]);
           // staging buffer u % nstg is free once the copy of unit u - nstg has completed (= that unit's s_full phase)
           if (u >= nstg) SNN_TWAIT(&s_full[(u - nstg) % C::NS], ((u - nstg) / C::NS) & 1, 1);
-          if (!(p.dbg & 4)) {
+          if (!(SNN_DBG_MASK(p) & 4)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int r = et + 128 * h;
@@ -636,12 +629,14 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     }
   }
 
+#ifdef SNN_ABLATE
   if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 12)) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 4 ? 2 : 3));
     unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
     o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
     o[3] = static_cast<unsigned long long>(clock64() - t_start);
   }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {

@@ -110,15 +110,6 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&x)[16], int lan
   return x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);
 }
 
-#ifndef SNN_TWAIT
-#define SNN_TWAIT(bar, par, slot)                                   \
-  do {                                                              \
-    const long long t0__ = clock64();                               \
-    mbar_wait(bar, par);                                            \
-    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
-  } while (0)
-#endif
-
 template <int MODE>
 __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(const ScanGemmParams p) {
   using C = ScanCfg<MODE>;
@@ -140,8 +131,10 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
   const uint32_t nsets = (C::SETS == 2 && p.sets != 1) ? 2u : 1u;
+#ifdef SNN_ABLATE
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
+#endif
 
   if (tid == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
@@ -286,12 +279,14 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
     }
   }
 
+#ifdef SNN_ABLATE
   if (p.dbg_out != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
     unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
     o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
     o[3] = static_cast<unsigned long long>(clock64() - t_start);
   }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (MODE == MODE_MLP_DX) {

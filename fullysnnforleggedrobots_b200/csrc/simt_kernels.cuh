@@ -113,9 +113,6 @@ __device__ __forceinline__ uint32_t regular_spikes(float a, int T, float& margin
 
 // batch-tile geometry of the actor's time-stepped tensors (plan.cuh): sample-step (t, b) -> tile * CT + t * Bt + b % Bt
 struct TileGeom { int Bt, CT, ntile; long long Rt; };
-constexpr int kTopScanSPT = 8;     // samples per thread of top_scan_kernel (Bt % 16 == 0)
-constexpr int kTopScanGPB = 4;     // at most this many sample groups per block; the launch uses 1 (measured: more
-                                   // groups per block = fewer partial rows to reduce, but fewer resident warps — a wash)
 
 // TT = 5: fully unrolled for the reference's spike_ts; TT = 0: generic T.
 // Thread = (sample, spike word): it evaluates the word's 32 encoder neurons (independent chains -> ILP, no
@@ -250,130 +247,16 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------ BPTT of the output population layer
-// g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the
-// recurrence of SURVEY.md §8a.  Same orientation as the dX epilogue (nm_gemm.cuh): thread = neuron, 16 samples x T
-// steps in registers; writes the g_c hi/lo planes (swz64 image, rows = sample-steps) and per-tile partials of the bias gradient and of
-// the decoder gradients:  dec_part[tile][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),
-// dec_part[tile][1][n] = sum_b G[b,a(n)]  (d bias, read at n = a * P).
-__global__ void __launch_bounds__(128 * kTopScanGPB) top_scan_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
-                                                      int dec_tanh, const float* __restrict__ dec_w,
-                                                      const float* __restrict__ volt, int B, TileGeom tg, int A, int P,
-                                                      int NP, int T, int gpb, uint8_t* __restrict__ g_img, size_t g_plane,
-                                                      float* __restrict__ db_part /* [gridDim.x][NP] */,
-                                                      float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
-  // grid (ntile * Bt / (SPT * gpb), NP / 128), block 128 * gpb: thread = (neuron, SPT-sample group), gpb groups per
-  // block (their three per-neuron sums are added in shared memory, fixed order).  A warp reads / writes 32
-  // consecutive neurons of one sample-step per request.  SPT = 8 keeps the per-thread state small (more resident
-  // warps: the kernel is a chain of dependent loads and recurrences per thread, i.e. latency-bound).
-  constexpr int SPT = kTopScanSPT;
-  __shared__ float s_red[kTopScanGPB][3][128];
-  const int nbg = tg.Bt / SPT;
-  const int sub = threadIdx.x >> 7, tx = threadIdx.x & 127;
-  const int grp = blockIdx.x * gpb + sub;                    // global sample-group index
-  const int tile = grp / nbg, bg_only = grp - tile * nbg;
-  const int n = blockIdx.y * 128 + tx;
-  const bool n_live = n < A * P;
-  const int a = n_live ? n / P : 0;
-  const float wn = n_live ? dec_w[n] : 0.f;
-  const float Tf = static_cast<float>(T);
-  const size_t c_tile = static_cast<size_t>(tile) * tg.CT;
-  const int TB = T * tg.Bt;
-  // g_c image [NP/64][Rt rows][128 B], see the dX epilogue of nm_gemm.cuh
-  uint8_t* const gcol = g_img + static_cast<size_t>(n >> 6) * tg.Rt * 128;
-  uint32_t xo[8];
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
-  const size_t vstep = static_cast<size_t>(tg.Bt) * 32;                                      // floats between timesteps
-  float dbsum = 0.f, dwd = 0.f, dbd = 0.f;
-  {
-    const int col0 = bg_only * SPT;
-    const int b0 = tile * tg.Bt + col0;
-    float gup[SPT], Gc[SPT], cnt[SPT], gvn[SPT], gcn[SPT];
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      gup[j] = 0.f; Gc[j] = 0.f; cnt[j] = 0.f; gvn[j] = 0.f; gcn[j] = 0.f;
-      if (n_live && b0 + j < B) {
-        float G = g_mu[static_cast<size_t>(b0 + j) * A + a];
-        if (dec_tanh) { const float m = mu[static_cast<size_t>(b0 + j) * A + a]; G = G * (1.f - m * m); }
-        Gc[j] = G;
-        gup[j] = __fdiv_rn(G * wn, Tf);
-      }
-    }
-    const float* vbase = volt + (static_cast<size_t>(n >> 5) * tg.Rt + c_tile + col0) * 32 + (n & 31);      // [n/32][Rt][32]
-    // the voltage loads do not depend on the recurrence: keep the next (earlier) timestep's loads in flight
-    float vn[SPT];
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(T - 1) * vstep + j * 32);
-    for (int t = T - 1; t >= 0; --t) {
-      float v[SPT];
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) v[j] = vn[j];
-      if (t > 0) {
-#pragma unroll
-        for (int j = 0; j < SPT; ++j) vn[j] = __ldg(vbase + static_cast<size_t>(t - 1) * vstep + j * 32);
-      }
-      const size_t c = c_tile + static_cast<size_t>(t * tg.Bt + col0);          // % 8 == 0
-      uint8_t* const dst = gcol + (c >> 3) * 1024;
-      float gc[SPT];
-#pragma unroll
-      for (int j = 0; j < SPT; ++j) {
-        const bool live = b0 + j < B;
-        const float vj = live ? v[j] : 0.f;
-        cnt[j] += vj > 0.5f ? 1.f : 0.f;                       // output spike count -> rate
-        const float gs = gup[j] - gvn[j] * (0.75f * vj);
-        const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
-        const float keep = vj > 0.5f ? 0.f : 0.75f;
-        const float gv = gs * win + gvn[j] * keep;
-        gc[j] = gv + 0.5f * gcn[j];
-        gvn[j] = gv; gcn[j] = gc[j];
-        dbsum += gc[j];
-      }
-#pragma unroll
-      for (int j = 0; j < SPT; j += 2) {
-        const uint32_t hp = pack_bf16x2(gc[j], gc[j + 1]);
-        const uint32_t lp = pack_bf16x2(gc[j] - __uint_as_float(hp << 16), gc[j + 1] - __uint_as_float(hp & 0xFFFF0000u));
-        uint8_t* q0 = dst + xo[j];
-        uint8_t* q1 = dst + xo[j + 1];
-        *reinterpret_cast<uint16_t*>(q0) = static_cast<uint16_t>(hp);
-        *reinterpret_cast<uint16_t*>(q1) = static_cast<uint16_t>(hp >> 16);
-        *reinterpret_cast<uint16_t*>(q0 + g_plane) = static_cast<uint16_t>(lp);
-        *reinterpret_cast<uint16_t*>(q1 + g_plane) = static_cast<uint16_t>(lp >> 16);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      dwd += Gc[j] * __fdiv_rn(cnt[j], Tf);
-      dbd += Gc[j];
-    }
-  }
-  // the padding sample-steps [TB, CT) of the tile must read as zero in the dW GEMM
-  for (int cc = TB + bg_only; cc < tg.CT; cc += nbg) {
-    const size_t r = c_tile + cc;
-    uint8_t* q = gcol + (r >> 3) * 1024 + xo[r & 7];
-    *reinterpret_cast<uint16_t*>(q) = 0;
-    *reinterpret_cast<uint16_t*>(q + g_plane) = 0;
-  }
-  s_red[sub][0][tx] = dbsum;
-  s_red[sub][1][tx] = dwd;
-  s_red[sub][2][tx] = dbd;
-  __syncthreads();
-  if (sub == 0) {
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-    for (int g = 0; g < gpb; ++g) { r0 += s_red[g][0][tx]; r1 += s_red[g][1][tx]; r2 += s_red[g][2][tx]; }
-    db_part[static_cast<size_t>(blockIdx.x) * NP + n] = r0;
-    dec_part[(static_cast<size_t>(blockIdx.x) * 2) * NP + n] = r1;
-    dec_part[(static_cast<size_t>(blockIdx.x) * 2 + 1) * NP + n] = r2;
-  }
-}
-
-// ------------------------------------------------------------------ BPTT of the output population layer, row-major
-// Same arithmetic per (neuron, sample, t) as top_scan_kernel, other orientation: thread = (PAIR of neurons, one
-// sample), warp = the 64 neurons of one chunk of one sample, block = kTopRowsSPB samples.  Every request is then a full
-// row segment: a warp loads the 64 voltages of a sample-step as two 128-byte lines and stores each g_c plane row as
-// ONE 128-byte line (4-byte bf16x2 stores; thread = neuron needs 2-byte stores that fill only half a line).  The
-// state per thread is two short recurrences (~40 registers -> full occupancy; the kernel is latency-bound).
-// Per-neuron sums: the block's samples are added in shared memory in a fixed order -> one partial row per block
-// ([Bcap / kTopRowsSPB][..], the layout top_scan_kernel writes).   grid (Bcap / kTopRowsSPB, NP / 64), block 32 * kTopRowsSPB.
+// g_up[t] = G[b,a] w_dec[a,p] / T for every t (out_act = sum_t s_t / T feeds the grouped conv), then the recurrence of
+// SURVEY.md 8a.  Orientation: thread = (PAIR of neurons, one sample), warp = the 64 neurons of one chunk of one sample,
+// block = kTopRowsSPB samples (the dX epilogue's thread = neuron orientation is dictated by the TMEM lanes; here
+// nothing dictates it).  Every request is a full row segment: a warp loads the 64 voltages of a sample-step as two
+// 128-byte lines and stores each g_c plane row as ONE 128-byte line (4-byte bf16x2 stores).  The state per thread is
+// two short recurrences (~40 registers -> full occupancy; the kernel is latency-bound).
+// Writes the g_c hi/lo planes (swz64 image, rows = sample-steps) and per-block partials of the bias gradient and of the
+// decoder gradients:  dec_part[blk][0][n] = sum_b G[b,a(n)] rate[b,n]  (d w_dec),  dec_part[blk][1][n] = sum_b G[b,a(n)]
+// (d bias, read at n = a * P); the block's samples are added in shared memory in a fixed order.
+// grid (Bcap / kTopRowsSPB, NP / 64), block 32 * kTopRowsSPB.
 constexpr int kTopRowsSPB = 8;       // Bt % 16 == 0: the samples of a block lie in one tile (16: row reduction 12.8 -> 7.1 us but this kernel 36 -> 40 us: a wash)
 template <int TT>
 __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
@@ -511,23 +394,6 @@ __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __re
     acc += g_a[(static_cast<size_t>(b >> 4) * K0P + k) * 16 + (b & 15)] * a * (-(x - mk)) / var;
   }
   d_obs[idx] = acc;
-}
-
-// out[i] = sum_s part[s * stride + i]; block (32 columns, 8 part lanes), fixed summation order
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, int nparts, size_t stride,
-                                                         int n, float* __restrict__ out) {
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
-  if (i < n)
-    for (int s = threadIdx.y; s < nparts; s += 8) acc += part[static_cast<size_t>(s) * stride + i];
-  __shared__ float sh[8][33];
-  sh[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && i < n) {
-    float t = 0.f;
-    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
-    out[i] = t;
-  }
 }
 
 // Several independent row reductions / split-K reductions in ONE launch (blockIdx.y resp. .z selects the job):

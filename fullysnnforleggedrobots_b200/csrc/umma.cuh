@@ -45,6 +45,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Barrier waits of the pipelined kernels.  Release builds: a plain bounded wait.  -DSNN_ABLATE (tools only, a separate
+// library file): the wait also accumulates its cycles into wcyc[slot] for tools/role_cycles.py.
+#ifdef SNN_ABLATE
+#define SNN_TWAIT(bar, par, slot)                                   \
+  do {                                                              \
+    const long long t0__ = clock64();                               \
+    mbar_wait(bar, par);                                            \
+    wcyc[slot] += static_cast<unsigned long long>(clock64() - t0__); \
+  } while (0)
+#define SNN_DBG_MASK(p) ((p).dbg)
+#else
+#define SNN_TWAIT(bar, par, slot) mbar_wait(bar, par)
+#define SNN_DBG_MASK(p) 0          // the work-skipping ablation switches do not exist in the release binary
+#endif
+
 // ------------------------------------------------------------------ proxies / fences
 // generic-proxy smem writes -> visible to the async proxy (MMA / bulk copy reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -103,17 +118,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors
-// Shared-memory matrix descriptor, 128-byte swizzle, operand tile made of 1024-byte atoms
-// (8 rows x 128 B).  lbo/sbo in bytes.  version = 1 (sm_100), base_offset = 0 (atoms 1 KiB aligned).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;   // descriptor version
-  d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
-  return d;
-}
+// Shared-memory matrix descriptors are built from two 32-bit halves (smem_desc_lo / smem_desc_hi below): 128-byte
+// swizzle, operand tiles made of 1024-byte atoms (8 rows x 128 B), version = 1 (sm_100), base_offset = 0.
 // Instruction descriptor for kind::f16, A = B = bf16, D = fp32.
 // a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
@@ -123,16 +129,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // mbarrier arrives once all tcgen05 ops issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -171,30 +167,6 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-
-// A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements), B from shared memory.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive columns, registers -> tensor memory (thread i writes lane base+i)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -90,7 +90,11 @@ class SnnEngine:
         self._packed_key = None
 
     def repack(self, enc_mean, enc_std, weights, biases, dec_w, dec_b):
-        """Unconditional re-pack (the fused optimizer updates parameters behind torch's version counters)."""
+        """Unconditional re-pack (the fused optimizer updates parameters behind torch's version counters).  Pass the
+        Parameters themselves, not `.data` views: the "changed since the last pack" key is (data_ptr, _version) of what
+        the caller passes, and a `.data` view always reports version 0 — a later ensure_packed() on the Parameters
+        would then re-pack a second time.  A write through `param.data.<op>_()` bumps no counter at all: call
+        PPO.refresh_packed() (or invalidate()) after such a write."""
         self._packed_key = None
         ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
         with torch.cuda.device(weights[0].device):
@@ -110,11 +114,16 @@ class SnnEngine:
     def trace_bytes(self, B: int) -> int:
         return int(_lib.lib().snn_trace_bytes(C.byref(self.desc), B))
 
+    def workspace_bytes(self, B: int, backward: bool) -> int:
+        return int(_lib.lib().snn_workspace_bytes(C.byref(self.desc), B, 1 if backward else 0))
+
     # ------------------------------------------------------------------ calls
     def forward(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, train: bool, out_mu=None,
-                out_trace=None, assume_packed: bool = False):
+                out_trace=None, assume_packed: bool = False, ws=None):
         """Returns (mu, trace or None).  out_mu / out_trace: optional caller-owned (static) output buffers.
-        assume_packed: the caller re-packs explicitly after every optimizer step (fused PPO path)."""
+        assume_packed: the caller re-packs explicitly after every optimizer step (fused PPO path).
+        ws: caller-owned inference workspace (>= workspace_bytes(B, backward=False)); a CUDA graph that captures this
+        call must pass its own, the engine's internal buffer may be re-allocated by a later, larger eager call."""
         _check_f32_cuda(obs, "obs")
         for t, n in ((enc_mean, "encoder.mean"), (enc_std, "encoder.std"), (dec_w, "decoder.weight"),
                      (dec_b, "decoder.bias"), *[(w, "weight") for w in weights], *[(b, "bias") for b in biases]):
@@ -139,14 +148,18 @@ class SnnEngine:
                                            _ptr(trace), nbytes, None, 0, _stream_ptr(dev)), "snn_fwd_train")
                 return mu, trace
             nbytes = L.snn_workspace_bytes(C.byref(self.desc), B, 0)
-            ws = self._buffer("fwd", nbytes, dev)
+            if ws is None:
+                ws = self._buffer("fwd", nbytes, dev)
+            elif ws.numel() < nbytes:
+                raise RuntimeError("inference workspace too small")
             _lib.check(L.snn_fwd_infer(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
                                        _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_fwd_infer")
             return mu, None
 
     def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool,
-                 out=None, assume_packed: bool = False):
-        """out: optional dict of caller-owned gradient tensors (same keys as the returned dict); overwritten."""
+                 out=None, assume_packed: bool = False, ws=None):
+        """out: optional dict of caller-owned gradient tensors (same keys as the returned dict); overwritten.
+        ws: caller-owned backward workspace (>= workspace_bytes(B, backward=True)), see forward()."""
         dev = obs.device
         B = obs.shape[0]
         L = _lib.lib()
@@ -169,35 +182,41 @@ class SnnEngine:
             g.dec_w, g.dec_b = out["dec_w"].data_ptr(), out["dec_b"].data_ptr()
             g.obs = out["obs"].data_ptr() if need_dobs else None
             nbytes = L.snn_workspace_bytes(C.byref(self.desc), B, 1)
-            ws = self._buffer("bwd", nbytes, dev)
+            if ws is None:
+                ws = self._buffer("bwd", nbytes, dev)
+            elif ws.numel() < nbytes:
+                raise RuntimeError("backward workspace too small")
             _lib.check(L.snn_bwd(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu), _ptr(g_mu),
                                  _ptr(trace), C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_bwd")
         return out
 
     # ------------------------------------------------------------------ test hooks
-    def unpack_trace(self, trace: torch.Tensor, B: int):
-        """Decode a training trace into dense tensors (tests / debugging only; not on the product path)."""
+    def unpack_trace(self, trace: torch.Tensor, B: int, rows: Optional[torch.Tensor] = None):
+        """Decode a training trace into dense tensors (tests / debugging only; not on the product path).
+        rows: optional 1-D index tensor — decode only these samples (full-size traces are hundreds of MB)."""
         arr = (C.c_int64 * (8 + 4 * _lib.SNN_MAX_LAYERS))()
         n = _lib.check(_lib.lib().snn_debug_trace_layout(C.byref(self.desc), B, arr, len(arr)), "trace layout")
         Lc, T, Bt, CT, ntile, Rt, K0P, enc_off = (int(arr[i]) for i in range(8))
         raw = trace.cpu()
         # sample-step (t, b) lives at column tile * CT + t * Bt + b % Bt (csrc/plan.cuh)
-        bb = torch.arange(ntile * Bt)
-        col = ((bb // Bt) * CT + bb % Bt).unsqueeze(0) + (torch.arange(T) * Bt).unsqueeze(1)      # [T, Bcap]
+        bb = torch.arange(B) if rows is None else rows.detach().cpu().to(torch.int64)
+        col = ((bb // Bt) * CT + bb % Bt).unsqueeze(0) + (torch.arange(T) * Bt).unsqueeze(1)      # [T, rows]
 
         def bits(off, ncols_p, ncols):
             words = raw[off: off + (ncols_p // 32) * Rt * 4].view(torch.int32).reshape(ncols_p // 32, Rt)
-            sh = torch.arange(32, dtype=torch.int32).reshape(1, 32, 1)
-            b = ((words.unsqueeze(1) >> sh) & 1).reshape(ncols_p, Rt)               # [neuron, sample-step]
-            return b[:, col].permute(1, 2, 0)[:, :B, :ncols].to(torch.float32).contiguous()
+            w = words[:, col]                                                         # [ncols_p / 32, T, rows]
+            sh = torch.arange(32, dtype=torch.int32).reshape(1, 32, 1, 1)
+            b = ((w.unsqueeze(1) >> sh) & 1).reshape(ncols_p, T, -1)                 # [neuron, T, rows]
+            return b.permute(1, 2, 0)[:, :, :ncols].to(torch.float32).contiguous()
 
         res = {"enc_spikes": bits(enc_off, K0P, self.dims[0]), "spikes": [], "volt": []}
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
             # voltage trace layout: [NP / 32][Rt sample-steps][32]
-            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt, 32).permute(1, 0, 2).reshape(Rt, NP)
-            res["volt"].append(v[col][:, :B, :self.dims[l + 1]].contiguous())
+            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt, 32)
+            v = v[:, col]                                                             # [NP / 32, T, rows, 32]
+            res["volt"].append(v.permute(1, 2, 0, 3).reshape(T, -1, NP)[:, :, :self.dims[l + 1]].contiguous())
         return res
 
 
@@ -295,8 +314,12 @@ class CriticEngine:
                                      _ptr(trace), trace.numel(), _stream_ptr(dev)), "snn_mlp_fwd")
         return value, trace
 
-    def backward(self, g_value, trace, B, out=None):
-        """Gradients of sum_b g_value[b] * value[b]; `out` = (list of weight grads, list of bias grads) to overwrite."""
+    def workspace_bytes(self, B):
+        return int(_lib.lib().snn_mlp_workspace_bytes(C.byref(self.desc), B))
+
+    def backward(self, g_value, trace, B, out=None, ws=None):
+        """Gradients of sum_b g_value[b] * value[b]; `out` = (list of weight grads, list of bias grads) to overwrite.
+        ws: caller-owned workspace (a CUDA graph capturing this call passes its own)."""
         dev = g_value.device
         L = _lib.lib()
         if out is None:
@@ -306,10 +329,14 @@ class CriticEngine:
             g.weight[i] = out[0][i].data_ptr()
             g.bias[i] = out[1][i].data_ptr()
         nbytes = L.snn_mlp_workspace_bytes(C.byref(self.desc), B)
-        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if ws is None:
+            if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = self._ws
+        elif ws.numel() < nbytes:
+            raise RuntimeError("critic workspace too small")
         ps = self._params()
         with torch.cuda.device(dev):
             _lib.check(L.snn_mlp_bwd(C.byref(self.desc), C.byref(ps), _ptr(self._packed), B, _ptr(g_value), _ptr(trace),
-                                     C.byref(g), _ptr(self._ws), self._ws.numel(), _stream_ptr(dev)), "snn_mlp_bwd")
+                                     C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_mlp_bwd")
         return out

@@ -5,11 +5,12 @@ act / process_env_step / compute_returns / update keep the reference's semantics
 fused minibatch step with no host round trip (CUDA-graph replayed):
 
     actor forward (sm_100a kernels, traces kept)          snn_fwd_train
-    critic forward                                        dense ELU MLP (torch / cuBLAS; not spiking)
+    critic forward (dense ELU MLP on the tensor cores,    snn_mlp_fwd     (a parallel branch of the CUDA graph;
+    second stream)                                                         torch only if the critic is not Linear/ELU)
     PPO head: log-prob, entropy, KL, surrogate, value     snn_ppo_head    (forward + closed-form gradients)
     loss, and d loss / d (mu, value, log_std)
     actor BPTT backward straight into the flat bucket     snn_bwd
-    critic backward                                       torch autograd on the critic only
+    critic backward                                       snn_mlp_bwd     (second stream)
     [data parallel: ONE all-reduce of the flat bucket, KL statistic riding in its tail]
     adaptive-KL learning rate on the device               snn_lr_adapt
     clip_grad_norm_ + Adam over the flat bucket           snn_clip_adam
@@ -17,6 +18,13 @@ fused minibatch step with no host round trip (CUDA-graph replayed):
 
 The generic path (`fused=False`, or a policy whose actor input needs a gradient such as the RMA latent) keeps
 the reference's op-by-op structure through torch autograd, still on the same kernels.
+
+CUDA graphs: a capture bakes in scalar kernel arguments (clip_param, value_loss_coef, entropy_coef, desired_kl, ...)
+and buffer addresses.  The reference reads those attributes on every step, so `update()` compares a signature of all
+of them (and of the storage's minibatch buffers) with the one the graphs were captured under and re-captures when
+anything changed.  Every graph owns the workspaces its kernels write (never the engines' internal, re-allocatable
+buffers).  A failed capture RAISES: a silent fall-back to eager launches would be a silent 3x slowdown
+(SNN_GRAPH_FALLBACK=1 restores the print-and-continue behaviour for debugging).
 """
 from __future__ import annotations
 
@@ -35,6 +43,16 @@ from .storage import RolloutStorage, RolloutStorageRMA
 
 def _p(t):
     return C.c_void_p(t.data_ptr())
+
+
+def _capture_failed(what, e):
+    """A CUDA-graph capture failed: raise (default) — or, with SNN_GRAPH_FALLBACK=1, report and let the caller go on
+    with eager launches."""
+    if os.environ.get("SNN_GRAPH_FALLBACK", "0") == "1":
+        print(f"[PPO] CUDA graph capture of {what} failed ({e}); SNN_GRAPH_FALLBACK=1: using eager launches")
+        return
+    raise RuntimeError(f"CUDA graph capture of {what} failed: {e}  (set SNN_GRAPH_FALLBACK=1 to continue with eager "
+                       "launches, or use_cuda_graph=False)") from e
 
 
 class _LazyNormal:
@@ -99,6 +117,11 @@ class PPO:
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
+        self._graph_sig = None                 # what the captured graphs baked in (_graph_signature)
+        # data parallel: "single" = the NCCL all-reduce is captured inside the step graph, "segments" = two graph
+        # segments around an eager all-reduce (see _run_fast_dp)
+        self.dp_graph_mode = os.environ.get("SNN_DP_GRAPH", "single")
+        self.dp_graph_note = ""
         self.replayed_kernel_launches = 0      # kernels of this library launched through CUDA-graph replays
         self._fast_state = None
         dev = self.optimizer.flat_params.device
@@ -120,6 +143,7 @@ class PPO:
                                       action_shape, self.device)
         if self.dp is not None:
             self.storage.advantage_stats_allreduce = self.dp.allreduce_sum
+        self._graphs, self._graph_launches, self._graph_sig = {}, {}, None      # graphs read the old storage's buffers
 
     def test_mode(self):
         self.actor_critic.eval()
@@ -157,7 +181,7 @@ class PPO:
         # if a weight changed" check; _act_graphed runs the same check on the host before every replay)
         actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
                              [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
-                             train=False, out_mu=o["mu"])
+                             train=False, out_mu=o["mu"], ws=st["ws_fwd"])
         noise = torch.randn_like(o["mu"])
         B, A = o["mu"].shape
         with torch.cuda.device(dev):
@@ -177,22 +201,30 @@ class PPO:
         """Rollout step as ONE CUDA-graph replay (the reference launches ~250 kernels here): inputs are copied into
         static buffers; actions / values / log-probs / mu / sigma land in one packed static buffer that is cloned once
         per call (fresh tensors for the caller, as in the reference)."""
-        key = (tuple(obs.shape), tuple(critic_obs.shape), obs.data_ptr() == critic_obs.data_ptr())
+        key = (tuple(obs.shape), tuple(critic_obs.shape), obs.data_ptr() == critic_obs.data_ptr(), obs.dtype,
+               critic_obs.dtype)
         st = self._act_state
         if st is None or st["key"] != key:
             B, A = obs.shape[0], self.actor_critic.actor.act_dim
-            st = {"key": key, "obs": obs.clone(), "cobs": None, "graph": None, "calls": 0,
-                  "packed": torch.empty(3 * B * A + 2 * B, dtype=torch.float32, device=obs.device),
-                  "side": torch.cuda.Stream(device=obs.device)}
-            st["cobs"] = st["obs"] if key[2] else critic_obs.clone()
-            st["views"] = self._act_views(st["packed"], B, A)
-            st["ce"] = None
-            if self.act_fused_critic and isinstance(self.actor_critic.critic, nn.Sequential) \
-                    and st["cobs"].dtype == torch.float32:
-                ce = CriticEngine.from_sequential(self.actor_critic.critic)
-                if ce is not None:
-                    st["ce"], st["ce_ver"] = ce, None
-                    st["ctrace"] = torch.empty(ce.trace_bytes(B), dtype=torch.uint8, device=obs.device)
+            dev = obs.device
+            # static buffers are plain (non-inference) contiguous tensors whatever mode / strides the first call came
+            # with: a later call under torch.no_grad() or with a strided view must still be able to copy_ into them
+            with torch.inference_mode(False):
+                st = {"key": key, "graph": None, "calls": 0,
+                      "obs": torch.empty(obs.shape, dtype=obs.dtype, device=dev),
+                      "packed": torch.empty(3 * B * A + 2 * B, dtype=torch.float32, device=dev),
+                      "ws_fwd": torch.empty(max(self.actor_critic.actor.engine.workspace_bytes(B, False), 1024),
+                                            dtype=torch.uint8, device=dev),
+                      "side": torch.cuda.Stream(device=dev)}
+                st["cobs"] = st["obs"] if key[2] else torch.empty(critic_obs.shape, dtype=critic_obs.dtype, device=dev)
+                st["views"] = self._act_views(st["packed"], B, A)
+                st["ce"] = None
+                if self.act_fused_critic and isinstance(self.actor_critic.critic, nn.Sequential) \
+                        and st["cobs"].dtype == torch.float32:
+                    ce = CriticEngine.from_sequential(self.actor_critic.critic)
+                    if ce is not None:
+                        st["ce"], st["ce_ver"] = ce, None
+                        st["ctrace"] = torch.empty(ce.trace_bytes(B), dtype=torch.uint8, device=dev)
             self._act_state = st
         st["obs"].copy_(obs)
         if not key[2]:
@@ -212,12 +244,17 @@ class PPO:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._act_fused(st)
+                    self._act_fused(st)               # kernel / argument errors surface here, un-caught
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._act_fused(st)
+            try:
+                with torch.cuda.graph(g):
+                    self._act_fused(st)
+            except Exception as e:  # noqa: BLE001   (capture-time failure only)
+                _capture_failed("PPO.act", e)
+                self.act_cuda_graph = False
+                return self._act_body(st["obs"], st["cobs"])
             st["graph"] = g
         actor = self.actor_critic.actor
         layers = st.get("layers")
@@ -234,15 +271,7 @@ class PPO:
     def act(self, obs, critic_obs):
         use_graph = (self.act_cuda_graph and obs.is_cuda and not torch.is_grad_enabled()
                      and type(self.actor_critic).__name__ != "ActorCriticRMA" and self.actor_critic.actor.act_dim <= 64)
-        if use_graph:
-            try:
-                out = self._act_graphed(obs, critic_obs)
-            except Exception as e:  # noqa: BLE001
-                print(f"[PPO] CUDA graph capture of act() failed ({e}); using the eager path")
-                self.act_cuda_graph = False
-                out = self._act_body(obs, critic_obs)
-        else:
-            out = self._act_body(obs, critic_obs)
+        out = self._act_graphed(obs, critic_obs) if use_graph else self._act_body(obs, critic_obs)
         (self.transition.actions, self.transition.values, self.transition.actions_log_prob,
          self.transition.action_mean, self.transition.action_sigma) = out
         self.transition.observations = obs
@@ -264,17 +293,15 @@ class PPO:
         self.storage.compute_returns(last_values, self.gamma, self.lam)
 
     # ------------------------------------------------------------------ generic (autograd) minibatch step
-    def losses(self, batch):
-        """Forward of one minibatch through autograd: (loss, surrogate_loss, value_loss, kl_mean or None)."""
-        (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch,
-         old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, hid_states_batch, masks_batch) = batch
+    def _loss_terms(self, actions_batch, target_values_batch, advantages_batch, returns_batch,
+                    old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, value_batch):
+        """The reference's loss block (ppo.py:135-171) on the distribution `actor_critic` currently holds:
+        (loss, surrogate_loss, value_loss, kl_mean or None)."""
         ac = self.actor_critic
-        ac.act(obs_batch, masks=masks_batch, hidden_states=hid_states_batch[0])
         actions_log_prob_batch = ac.get_actions_log_prob(actions_batch)
-        value_batch = ac.evaluate(critic_obs_batch, masks=masks_batch, hidden_states=hid_states_batch[1])
         mu_batch, sigma_batch, entropy_batch = ac.action_mean, ac.action_std, ac.entropy
         kl_mean = None
-        if self.desired_kl is not None and self.schedule == 'adaptive':
+        if self._adaptive():
             with torch.no_grad():
                 kl = torch.sum(torch.log(sigma_batch / old_sigma_batch + 1.e-5)
                                + (torch.square(old_sigma_batch) + torch.square(old_mu_batch - mu_batch))
@@ -296,6 +323,16 @@ class PPO:
         loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_batch.mean()
         return loss, surrogate_loss, value_loss, kl_mean
 
+    def losses(self, batch):
+        """Forward of one minibatch through autograd: (loss, surrogate_loss, value_loss, kl_mean or None)."""
+        (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch,
+         old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, hid_states_batch, masks_batch) = batch
+        ac = self.actor_critic
+        ac.act(obs_batch, masks=masks_batch, hidden_states=hid_states_batch[0])
+        value_batch = ac.evaluate(critic_obs_batch, masks=masks_batch, hidden_states=hid_states_batch[1])
+        return self._loss_terms(actions_batch, target_values_batch, advantages_batch, returns_batch,
+                                old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, value_batch)
+
     def _adaptive(self):
         return self.desired_kl is not None and self.schedule == 'adaptive'
 
@@ -315,13 +352,18 @@ class PPO:
                                                    _p(opt.lr_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                            "snn_lr_adapt")
         opt.step(max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0, grad_scale=1.0 / world)
-        actor = self.actor_critic.actor
-        layers = actor.snn.linear_layers()
-        actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
-                            [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
-                            actor.decoder.decoder.bias.data)
+        self._repack_actor()
         # the critic's operand planes are re-derived at the head of the next step's critic branch (second stream):
         # off the critical path, which continues with the actor's encoder (_step_fast)
+
+    def _repack_actor(self):
+        """bf16 operand planes <- fp32 parameters, unconditionally (the fused optimizer writes parameters behind
+        torch's version counters).  The Parameters themselves are passed, so the engine's "changed since the last pack"
+        key stays the one `ensure_packed` computes before a rollout-graph replay: no second re-pack there."""
+        actor = self.actor_critic.actor
+        layers = actor.snn.linear_layers()
+        actor.engine.repack(actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
+                            [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias)
 
     def _step_generic(self, batch):
         loss, surrogate_loss, value_loss, kl_mean = self.losses(batch)
@@ -340,16 +382,31 @@ class PPO:
         return (self.fused and type(ac).__name__ != "ActorCriticRMA" and not ac.is_recurrent
                 and self.optimizer.flat_params.is_cuda and ac.actor.act_dim <= 64)
 
+    def _graph_signature(self, f, mb):
+        """Everything a captured minibatch-step graph bakes in: the scalar kernel arguments the reference reads from
+        `self` on every step, and the addresses of the minibatch buffers.  `update()` re-captures when it changes (a
+        runner that anneals entropy_coef / clip_param, switches `schedule`, or calls init_storage() again)."""
+        g = self.optimizer.param_groups[0]
+        return (mb, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
+                bool(self.use_clipped_value_loss), self.desired_kl, self.schedule, self.max_grad_norm,
+                tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), self.overlap_critic,
+                1 if self.dp is None else self.dp.world_size,
+                tuple(sorted((k, v.data_ptr()) for k, v in f.items())))
+
     def _fast_setup(self, mb):
         ac = self.actor_critic
         dev = self.optimizer.flat_params.device
         A = ac.actor.act_dim
+        eng = ac.actor.engine
         st = {
             "mb": mb,
             "mu": torch.empty(mb, A, dtype=torch.float32, device=dev),
             "g_mu": torch.empty(mb, A, dtype=torch.float32, device=dev),
             "g_value": torch.empty(mb, dtype=torch.float32, device=dev),
-            "trace": torch.empty(ac.actor.engine.trace_bytes(mb), dtype=torch.uint8, device=dev),
+            "trace": torch.empty(eng.trace_bytes(mb), dtype=torch.uint8, device=dev),
+            # owned by this state (and so by the graphs captured over it), not by the engine: an eager call with a
+            # larger batch re-allocates the engine's internal workspace, which a replayed graph would still write to
+            "ws_bwd": torch.empty(eng.workspace_bytes(mb, True), dtype=torch.uint8, device=dev),
             "scratch": torch.empty(((mb + 255) // 256) * (4 + A) * 4 + 1024, dtype=torch.uint8, device=dev),
         }
         layers = ac.actor.snn.linear_layers()
@@ -368,6 +425,7 @@ class PPO:
                 st["critic"] = ce
                 st["value"] = torch.empty(mb, dtype=torch.float32, device=dev)
                 st["critic_trace"] = torch.empty(ce.trace_bytes(mb), dtype=torch.uint8, device=dev)
+                st["critic_ws"] = torch.empty(ce.workspace_bytes(mb), dtype=torch.uint8, device=dev)
                 st["critic_grads"] = ([l.weight.grad for l in ce.linears], [l.bias.grad for l in ce.linears])
                 st["side_stream"] = torch.cuda.Stream(device=dev) if self.overlap_critic else None
         self._fast_state = st
@@ -408,6 +466,7 @@ class PPO:
             main.wait_stream(side)
         L = _lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        world = 1 if self.dp is None else self.dp.world_size
         with torch.cuda.device(dev):
             _lib.check(L.snn_ppo_head(
                 _p(mu), _p(ac.actor.log_std.data), _p(value.detach()), _p(f["actions"][sl]), _p(f["logp"][sl]),
@@ -420,32 +479,40 @@ class PPO:
         if ce is not None and side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"], ws=st["critic_ws"])
         eng.backward(f["obs"][sl], mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws],
-                     [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"], assume_packed=True)
+                     [b.data for b in bs], dw.data, db.data, need_dobs=False, out=st["grads_out"], assume_packed=True,
+                     ws=st["ws_bwd"])
         if ce is not None:
             if side is not None:
                 main.wait_stream(side)
             else:
-                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"])
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"], ws=st["critic_ws"])
         else:
             value.backward(st["g_value"].view_as(value))
         if finish:
             self._finish_step()
 
-    def _capture(self, fn, snap):
-        """Warm `fn` up on a side stream, restore the training state, capture it into a CUDA graph."""
+    def _capture(self, fn, snap, what):
+        """Warm `fn` up on a side stream, restore the training state, capture it into a CUDA graph.
+        Returns (graph, kernel launches of this library inside it) or None when the capture failed and
+        SNN_GRAPH_FALLBACK=1 allows going on without it."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            fn()
+            fn()                                   # kernel / argument errors surface here, un-caught
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(snap)
         g = torch.cuda.CUDAGraph()
         n0 = _lib.lib().snn_launch_count()
-        with torch.cuda.graph(g, **self._graph_kw()):
-            fn()
+        try:
+            with torch.cuda.graph(g, **self._graph_kw()):
+                fn()
+        except Exception as e:  # noqa: BLE001   (capture-time failure only)
+            self._restore(snap)
+            _capture_failed(what, e)
+            return None
         self._restore(snap)
         return g, int(_lib.lib().snn_launch_count() - n0)
 
@@ -457,22 +524,40 @@ class PPO:
         return {"stream": self._hp_stream}
 
     def _run_fast_dp(self, f, i):
-        """Data parallel: graph A (everything up to the local gradients) -> eager NCCL all-reduce of the flat bucket
-        -> graph B (adaptive lr, clip + Adam, re-pack).  NCCL itself is not captured."""
-        try:
-            if ("pre", i) not in self._graphs:
-                snap = self._snapshot()
-                self._graphs[("pre", i)], self._graph_launches[("pre", i)] = self._capture(
-                    lambda: self._step_fast(f, i, finish=False), snap)
-            if "post" not in self._graphs:
-                snap = self._snapshot()
-                gsnap = self.optimizer.flat_grads.clone()
-                self._graphs["post"], self._graph_launches["post"] = self._capture(self._post_allreduce, snap)
-                self.optimizer.flat_grads.copy_(gsnap)
-        except Exception as e:  # noqa: BLE001
-            print(f"[PPO] CUDA graph capture failed ({e}); falling back to eager fused steps")
-            self.use_cuda_graph = False
-            return self._step_fast(f, i)
+        """Data parallel.  dp_graph_mode "single": the whole step INCLUDING the NCCL all-reduce of the flat bucket is
+        one CUDA graph (NCCL's kernel is captured like any other; no graph boundary, no eager NCCL launch on the
+        critical path).  "segments": graph A (everything up to the local gradients) -> eager NCCL all-reduce ->
+        graph B (adaptive lr, clip + Adam, re-pack) — the round-1 scheme, kept for NCCL builds that cannot be
+        captured (selected with SNN_DP_GRAPH=segments, or automatically when the single-graph capture fails; the
+        mode that ran is reported by bench.py as `dp_graph`)."""
+        if self.dp_graph_mode == "single":
+            if ("full", i) not in self._graphs:
+                try:
+                    cap = self._capture(lambda: self._step_fast(f, i), self._snapshot(), "the data-parallel PPO step")
+                except RuntimeError as e:
+                    cap = None
+                    self.dp_graph_mode, self.dp_graph_note = "segments", f"single-graph capture failed: {e}"
+                if cap is not None:
+                    self._graphs[("full", i)], self._graph_launches[("full", i)] = cap
+            if ("full", i) in self._graphs:
+                self._graphs[("full", i)].replay()
+                self.replayed_kernel_launches += self._graph_launches[("full", i)]
+                return
+            self.dp_graph_mode = "segments"
+        if ("pre", i) not in self._graphs:
+            cap = self._capture(lambda: self._step_fast(f, i, finish=False), self._snapshot(), "the PPO step (pre)")
+            if cap is None:
+                self.use_cuda_graph = False
+                return self._step_fast(f, i)
+            self._graphs[("pre", i)], self._graph_launches[("pre", i)] = cap
+        if "post" not in self._graphs:
+            gsnap = self.optimizer.flat_grads.clone()
+            cap = self._capture(self._post_allreduce, self._snapshot(), "the PPO step (post)")
+            self.optimizer.flat_grads.copy_(gsnap)
+            if cap is None:
+                self.use_cuda_graph = False
+                return self._step_fast(f, i)
+            self._graphs["post"], self._graph_launches["post"] = cap
         self._graphs[("pre", i)].replay()
         self.dp.allreduce_sum(self.optimizer.flat_grads)
         self._graphs["post"].replay()
@@ -483,31 +568,13 @@ class PPO:
             return self._step_fast(f, i)
         if self.dp is not None:
             return self._run_fast_dp(f, i)
-        g = self._graphs.get(i)
-        if g is None:
-            # warm-up on a side stream (allocator + lazy init), then capture
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            snap = self._snapshot()
-            with torch.cuda.stream(s):
-                self._step_fast(f, i)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            self._restore(snap)
-            g = torch.cuda.CUDAGraph()
-            n0 = _lib.lib().snn_launch_count()
-            try:
-                with torch.cuda.graph(g, **self._graph_kw()):
-                    self._step_fast(f, i)
-            except Exception as e:  # noqa: BLE001
-                print(f"[PPO] CUDA graph capture failed ({e}); falling back to eager fused steps")
+        if i not in self._graphs:
+            cap = self._capture(lambda: self._step_fast(f, i), self._snapshot(), "the PPO step")
+            if cap is None:
                 self.use_cuda_graph = False
-                self._restore(snap)
                 return self._step_fast(f, i)
-            self._restore(snap)
-            self._graphs[i] = g
-            self._graph_launches[i] = int(_lib.lib().snn_launch_count() - n0)
-        g.replay()
+            self._graphs[i], self._graph_launches[i] = cap
+        self._graphs[i].replay()
         self.replayed_kernel_launches += self._graph_launches[i]
 
     def _snapshot(self):
@@ -523,12 +590,8 @@ class PPO:
 
     def refresh_packed(self):
         """Re-derive the bf16 operand planes from the fp32 parameters (after anything that changed them behind the
-        fused path's back: a restored snapshot, load_state_dict / load_checkpoint)."""
-        actor = self.actor_critic.actor
-        layers = actor.snn.linear_layers()
-        actor.engine.repack(actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers],
-                            [l.bias.data for l in layers], actor.decoder.decoder.weight.data,
-                            actor.decoder.decoder.bias.data)
+        fused path's back: a restored snapshot, load_state_dict / load_checkpoint, a write through `param.data`)."""
+        self._repack_actor()
         if self._fast_state is not None and self._fast_state.get("critic") is not None:
             self._fast_state["critic"].repack()
 
@@ -541,6 +604,9 @@ class PPO:
             f, mb = self.storage.permute_once(self.num_mini_batches)
             if self._fast_state is None or self._fast_state["mb"] != mb:
                 self._fast_setup(mb)
+            sig = self._graph_signature(f, mb)
+            if sig != self._graph_sig:                 # a hyperparameter or a buffer address changed: re-capture
+                self._graphs, self._graph_launches, self._graph_sig = {}, {}, sig
             self.refresh_packed()      # the fused steps assume current planes (parameters may have been loaded since)
             for _ in range(self.num_learning_epochs):
                 for i in range(self.num_mini_batches):
@@ -599,30 +665,10 @@ class PPORMA(PPO):
          masks_batch) = batch
         ac = self.actor_critic
         ac.act(obs_batch, privileged_obs_batch, masks=masks_batch, hidden_states=hid_states_batch[0])
-        actions_log_prob_batch = ac.get_actions_log_prob(actions_batch)
         value_batch = ac.evaluate(critic_obs_batch, privileged_obs_batch, masks=masks_batch,
                                   hidden_states=hid_states_batch[1])
-        mu_batch, sigma_batch, entropy_batch = ac.action_mean, ac.action_std, ac.entropy
-        kl_mean = None
-        if self.desired_kl is not None and self.schedule == 'adaptive':
-            with torch.no_grad():
-                kl = torch.sum(torch.log(sigma_batch / old_sigma_batch + 1.e-5)
-                               + (torch.square(old_sigma_batch) + torch.square(old_mu_batch - mu_batch))
-                               / (2.0 * torch.square(sigma_batch)) - 0.5, axis=-1)
-                kl_mean = torch.mean(kl)
-        ratio = torch.exp(actions_log_prob_batch - torch.squeeze(old_actions_log_prob_batch))
-        surrogate = -torch.squeeze(advantages_batch) * ratio
-        surrogate_clipped = -torch.squeeze(advantages_batch) * torch.clamp(ratio, 1.0 - self.clip_param,
-                                                                           1.0 + self.clip_param)
-        surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
-        if self.use_clipped_value_loss:
-            value_clipped = target_values_batch + (value_batch - target_values_batch).clamp(-self.clip_param,
-                                                                                            self.clip_param)
-            value_loss = torch.max((value_batch - returns_batch).pow(2), (value_clipped - returns_batch).pow(2)).mean()
-        else:
-            value_loss = (returns_batch - value_batch).pow(2).mean()
-        loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_batch.mean()
-        return loss, surrogate_loss, value_loss, kl_mean
+        return self._loss_terms(actions_batch, target_values_batch, advantages_batch, returns_batch,
+                                old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, value_batch)
 
     def update(self):
         self._stats.zero_()

@@ -73,6 +73,9 @@ typedef struct SnnGrads {
 
 const char* snn_last_error(void);
 int snn_abi_version(void);
+/* bit 0: built with -DSNN_ABLATE (tools build with work-skipping SNN_DBG switches and barrier-wait cycle counters).
+ * The release library returns 0; bench.py and the tests refuse any other value. */
+int snn_build_flags(void);
 
 /* Sizes of the caller-owned buffers, in bytes.  B = batch rows of the call. */
 size_t snn_packed_weights_bytes(const SnnDesc* d);           /* bf16 plane images of all layers */
@@ -182,7 +185,8 @@ int snn_profile_read(double* ms32, double* flops32, int64_t* launches32);
 int64_t snn_launch_count(void);
 
 /* Debug / test hooks: unpack internal buffers into plain tensors (tests only). */
-/* tools only: device buffer of 16 * 148 * 16 uint64 receiving per-role barrier-wait cycle counts (NULL = off) */
+/* -DSNN_ABLATE tools build only (SNN_EINVAL otherwise): device buffer of 16 * 148 * 16 uint64 receiving per-role
+ * barrier-wait cycle counts (NULL = off) */
 int snn_debug_set_cycle_buffer(void* buf);
 int snn_debug_trace_layout(const SnnDesc* d, int64_t B, int64_t* out, int n_out);
 

@@ -161,6 +161,69 @@ def make_ppo_rollout(pc: PPOCase):
     }
 
 
+# --------------------------------------------------------------------------- RMA PPO update case
+@dataclass(frozen=True)
+class RMACase:
+    """RMA fork's PPO.update (RMA-rl/algorithms/ppo.py:134-221): PPO step + adaptation-module regression substeps."""
+    name: str = "rma_ppo_tiny"
+    num_obs: int = 7
+    num_priv: int = 5
+    num_hist: int = 14
+    latent: int = 4
+    hidden: tuple = (32, 24)
+    critic_hidden: tuple = (16, 16)
+    enc_hidden: tuple = (12, 8)
+    adapt_hidden: tuple = (12, 8)
+    act_dim: int = 3
+    num_envs: int = 8
+    num_steps: int = 4
+    epochs: int = 2
+    substeps: int = 2
+    seed: int = 23
+    gamma: float = 0.99
+    lam: float = 0.95
+    lr: float = 1e-3
+    entropy_coef: float = 0.01
+
+
+RMA_CASE = RMACase()
+
+
+def make_rma_state_dict(rc: RMACase) -> Dict[str, torch.Tensor]:
+    c = Case("rma_actor", "rma", rc.num_obs + rc.latent, rc.hidden, rc.act_dim, 1, seed=rc.seed)
+    sd = make_state_dict(c)
+    g = torch.Generator().manual_seed(7000 + rc.seed)
+
+    def mlp(prefix, dims):
+        for i in range(len(dims) - 1):
+            bound = 1.0 / math.sqrt(dims[i])
+            sd[f"{prefix}.{2 * i}.weight"] = _uniform(g, (dims[i + 1], dims[i]), bound)
+            sd[f"{prefix}.{2 * i}.bias"] = _uniform(g, (dims[i + 1],), bound)
+
+    mlp("critic", [rc.num_obs + rc.latent] + list(rc.critic_hidden) + [1])
+    mlp("env_factor_encoder", [rc.num_priv] + list(rc.enc_hidden) + [rc.latent])
+    mlp("adaptation_module", [rc.num_hist] + list(rc.adapt_hidden) + [rc.latent])
+    for k in [k for k in sd if k.startswith("env_factor_encoder.")]:       # the reference registers the module twice
+        sd["encoder." + k[len("env_factor_encoder."):]] = sd[k]
+    sd["std"] = torch.ones(rc.act_dim)
+    return sd
+
+
+def make_rma_rollout(rc: RMACase):
+    g = torch.Generator().manual_seed(8000 + rc.seed)
+    S, N = rc.num_steps, rc.num_envs
+    return {
+        "obs": torch.randn(S, N, rc.num_obs, generator=g),
+        "priv": torch.randn(S, N, rc.num_priv, generator=g),
+        "hist": torch.randn(S, N, rc.num_hist, generator=g),
+        "rewards": torch.randn(S, N, generator=g),
+        "dones": (torch.rand(S, N, generator=g) < 0.15).to(torch.uint8),
+        "noise": torch.randn(S, N, rc.act_dim, generator=g),
+        "last_obs": torch.randn(N, rc.num_obs, generator=g),
+        "last_priv": torch.randn(N, rc.num_priv, generator=g),
+    }
+
+
 # --------------------------------------------------------------------------- AMP PPO update case
 AMP_CASE = PPOCase(name="amp_ppo_tiny", variant="amp", seed=22)
 AMP_OBS_DIM = 5

@@ -22,7 +22,8 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from cases import CASES, PPO_CASE, make_gmu, make_obs, make_ppo_rollout, make_ppo_state_dict, make_state_dict  # noqa: E402
+from cases import (CASES, PPO_CASE, RMA_CASE, make_gmu, make_obs, make_ppo_rollout, make_ppo_state_dict,  # noqa: E402
+                   make_rma_rollout, make_rma_state_dict, make_state_dict)
 
 REF = "/root/reference"
 PKG_ROOT = {
@@ -167,6 +168,61 @@ def run_ppo_case(pc):
     return out
 
 
+def run_rma_ppo_case(rc):
+    """The RMA fork's PPO.update (RMA-rl/algorithms/ppo.py:134-221) on a seeded rollout: 1 minibatch x `epochs` PPO
+    steps, each followed by `substeps` adaptation-module regression steps (second Adam, fixed lr).  Records what the
+    rollout phase produced and every parameter after the update."""
+    import_ref("rma", "modules.actor_critic")
+    mods = importlib.import_module("rsl_rl.modules")
+    algs = importlib.import_module("rsl_rl.algorithms")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ac = mods.ActorCritic(rc.num_obs, rc.num_priv, rc.num_hist, rc.act_dim, actor_hidden_dims=list(rc.hidden),
+                              critic_hidden_dims=list(rc.critic_hidden), encoder_hidden_dims=list(rc.enc_hidden),
+                              adaptation_hidden_dims=list(rc.adapt_hidden), encoder_latent_dims=rc.latent,
+                              activation="elu", init_noise_std=1.0)
+    ac.actor.encoder.device = ac.actor.snn.device = "cpu"
+    ac.load_state_dict(make_rma_state_dict(rc))
+    alg = algs.PPO(ac, num_learning_epochs=rc.epochs, num_mini_batches=1, clip_param=0.2, gamma=rc.gamma, lam=rc.lam,
+                   value_loss_coef=1.0, entropy_coef=rc.entropy_coef, learning_rate=rc.lr, max_grad_norm=1.0,
+                   use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01,
+                   num_adaptation_module_substeps=rc.substeps, device="cpu")
+    alg.init_storage(rc.num_envs, rc.num_steps, [rc.num_obs], [rc.num_priv], [rc.num_hist], [rc.act_dim])
+    ro = make_rma_rollout(rc)
+    st = alg.storage
+    with contextlib.redirect_stdout(io.StringIO()), torch.inference_mode():
+        for s in range(rc.num_steps):
+            obs, priv = ro["obs"][s], ro["priv"][s]
+            ac.update_distribution(obs, priv)
+            mu = ac.action_mean
+            actions = mu + ac.action_std * ro["noise"][s]
+            st.observations[s].copy_(obs)
+            st.privileged_observations[s].copy_(priv)
+            st.observation_histories[s].copy_(ro["hist"][s])
+            st.actions[s].copy_(actions)
+            st.rewards[s].copy_(ro["rewards"][s].view(-1, 1))
+            st.dones[s].copy_(ro["dones"][s].view(-1, 1))
+            st.values[s].copy_(ac.evaluate(obs, priv))
+            st.actions_log_prob[s].copy_(ac.get_actions_log_prob(actions).view(-1, 1))
+            st.mu[s].copy_(mu)
+            st.sigma[s].copy_(ac.action_std)
+            st.step += 1
+        alg.compute_returns(ro["last_obs"], ro["last_priv"])
+    out = {"actions": st.actions.numpy().copy(), "values": st.values.numpy().copy(),
+           "actions_log_prob": st.actions_log_prob.numpy().copy(), "mu": st.mu.numpy().copy(),
+           "sigma": st.sigma.numpy().copy(), "returns": st.returns.numpy().copy(),
+           "advantages": st.advantages.numpy().copy()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        vl, sl, al = alg.update()
+    out["mean_value_loss"] = np.float64(vl)
+    out["mean_surrogate_loss"] = np.float64(sl)
+    out["mean_adaptation_loss"] = np.float64(al)
+    out["final_lr"] = np.float64(alg.learning_rate)
+    for k, v in ac.state_dict().items():
+        out["final." + k] = v.detach().numpy().copy()
+    return out
+
+
 def _emit(path, out, check):
     """Write the fixture, or (--check) compare a fresh run of the reference against the committed file."""
     if not check:
@@ -192,6 +248,7 @@ def main(check=False):
         print(f"{c.name:22s} {_emit(path, out, check)}  mu[0]={out['mu'][0][:3]}")
     print("gae_cassie", _emit(os.path.join(HERE, "gae_cassie.npz"), run_gae_case(), check))
     print(PPO_CASE.name, _emit(os.path.join(HERE, f"{PPO_CASE.name}.npz"), run_ppo_case(PPO_CASE), check))
+    print(RMA_CASE.name, _emit(os.path.join(HERE, f"{RMA_CASE.name}.npz"), run_rma_ppo_case(RMA_CASE), check))
 
 
 if __name__ == "__main__":

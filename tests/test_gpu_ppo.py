@@ -288,3 +288,82 @@ def test_sample_logprob_kernel_matches_torch_normal(B, A):
     assert rel_err(sigma.cpu(), dist.stddev.cpu()) < 1e-6
     assert rel_err(actions.cpu(), (mu + std * noise).cpu()) < 1e-6
     assert rel_err(logp.cpu(), dist.log_prob(actions).sum(-1).cpu()) < 1e-5
+
+
+def _two_updates(pc, g, ro, graph, ent2, intermezzo=False):
+    ac, alg = make_alg(pc, use_cuda_graph=graph)
+    out = []
+    for k in range(2):
+        fill_storage(alg, pc, g, ro)
+        alg.compute_returns(ro["last_obs"].cuda())
+        if k == 1:
+            alg.entropy_coef = ent2                 # a runner annealing the entropy bonus between iterations
+            alg.clip_param = 0.15
+        out.append(alg.update())
+        if intermezzo and k == 0:
+            # eager calls with a LARGER batch between two graph replays: they re-allocate the engines' internal
+            # workspaces, which the captured graphs must not depend on (engine.py:68)
+            big = torch.randn(4096, pc.obs_dim, device="cuda")
+            with torch.inference_mode():
+                ac.act_inference(big)
+            x = big[:1024].clone().requires_grad_(True)
+            m, _ = ac.actor(x)
+            m.sum().backward()
+            for p in ac.parameters():
+                if p.grad is not None:
+                    p.grad.zero_()
+            torch.cuda.synchronize()
+    return out, {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}, alg
+
+
+def test_graphs_follow_hyperparameter_changes_between_updates():
+    """ADVICE r1 (ppo.py:486): the captured minibatch-step graphs bake in clip_param / entropy_coef / ...; the
+    reference reads them every step.  Changing them between two updates must give exactly what eager launches give."""
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    out_e, sd_e, _ = _two_updates(pc, g, ro, graph=False, ent2=0.2)
+    out_g, sd_g, alg = _two_updates(pc, g, ro, graph=True, ent2=0.2)
+    assert alg.use_cuda_graph and len(alg._graphs) == 1
+    _, sd_same, _ = _two_updates(pc, g, ro, graph=True, ent2=pc.entropy_coef)
+    for k in sd_e:
+        assert torch.equal(sd_g[k], sd_e[k]), k                   # same kernels, same order: bit-identical
+    assert any(not torch.equal(sd_g[k], sd_same[k]) for k in sd_e)            # and the change really mattered
+    assert out_g == out_e
+
+
+def test_graphs_survive_larger_eager_calls_and_new_storage():
+    """ADVICE r1 (engine.py:68): graphs own their workspaces; a larger eager call in between must not disturb a replay.
+    Also: init_storage() again (new minibatch buffers) invalidates the graphs instead of replaying over freed memory."""
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    _, sd_ref, _ = _two_updates(pc, g, ro, graph=True, ent2=pc.entropy_coef)
+    _, sd_int, alg = _two_updates(pc, g, ro, graph=True, ent2=pc.entropy_coef, intermezzo=True)
+    for k in sd_ref:
+        assert torch.equal(sd_int[k], sd_ref[k]), k
+    sig0 = alg._graph_sig
+    alg.init_storage(pc.num_envs, pc.num_steps, [pc.obs_dim], [None], [pc.act_dim])
+    assert alg._graphs == {} and alg._graph_sig is None
+    fill_storage(alg, pc, g, ro)
+    alg.compute_returns(ro["last_obs"].cuda())
+    vl, sl = alg.update()
+    assert vl == vl and alg._graph_sig is not None and len(alg._graphs) == 1
+    assert alg._graph_sig[:-1] == sig0[:-1]                 # same hyperparameters, (possibly) other buffer addresses
+
+
+def test_act_graph_static_buffers_accept_other_modes_and_strides():
+    """ADVICE r1 (ppo.py:240): the rollout graph's static buffers must not be inference tensors or inherit strides."""
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    ac, alg = make_alg(pc)
+    obs = ro["obs"][0].cuda()
+    with torch.inference_mode():
+        for _ in range(3):
+            alg.act(obs, obs)
+            alg.transition.clear()
+    assert alg._act_state["graph"] is not None
+    wide = torch.randn(pc.num_envs, 2 * pc.obs_dim, device="cuda")
+    view = wide[:, ::2]                                     # non-contiguous observations, plain no_grad mode
+    assert not view.is_contiguous()
+    with torch.no_grad():
+        alg.act(view, view)
+        mu_graph = alg.transition.action_mean.clone()
+        mu_eager = ac.act_inference(view.contiguous())
+    assert alg._act_state["graph"] is not None and alg.act_cuda_graph
+    assert rel_err(mu_graph.cpu(), mu_eager.cpu()) < 1e-6

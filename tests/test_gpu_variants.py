@@ -92,6 +92,65 @@ def test_rma_ppo_update_runs_and_trains_adaptation_module():
     assert all(torch.isfinite(p).all() for p in ac.parameters())
 
 
+@pytest.mark.parametrize("mode", ["default", "generic"])
+def test_rma_ppo_update_matches_reference_fixture(mode):
+    """The RMA fork's whole PPO.update (RMA-rl/algorithms/ppo.py:134-221: PPO step through the privileged-latent path +
+    adaptation-module regression substeps with a second Adam) against rma_ppo_tiny.npz, written by
+    tests/golden/make_golden.py from the unmodified reference.  mode "default" = whatever PPORMA picks (the fused /
+    graphed path where supported), "generic" = the op-by-op autograd path."""
+    import os
+
+    import numpy as np
+
+    from cases import RMA_CASE as rc, make_rma_rollout, make_rma_state_dict
+    from fullysnnforleggedrobots_b200 import PPORMA, ActorCriticRMA
+    from helpers import GOLD
+    g = dict(np.load(os.path.join(GOLD, f"{rc.name}.npz")))
+    ro = make_rma_rollout(rc)
+    ac = ActorCriticRMA(rc.num_obs, rc.num_priv, rc.num_hist, rc.act_dim, actor_hidden_dims=list(rc.hidden),
+                        critic_hidden_dims=list(rc.critic_hidden), encoder_hidden_dims=list(rc.enc_hidden),
+                        adaptation_hidden_dims=list(rc.adapt_hidden), encoder_latent_dims=rc.latent)
+    sd0 = make_rma_state_dict(rc)
+    ac.load_state_dict(sd0)
+    kw = {} if mode == "default" else {"fused": False}
+    alg = PPORMA(ac, num_learning_epochs=rc.epochs, num_mini_batches=1, clip_param=0.2, gamma=rc.gamma, lam=rc.lam,
+                 value_loss_coef=1.0, entropy_coef=rc.entropy_coef, learning_rate=rc.lr, max_grad_norm=1.0,
+                 use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cuda",
+                 num_adaptation_module_substeps=rc.substeps, **kw)
+    alg.init_storage(rc.num_envs, rc.num_steps, [rc.num_obs], [rc.num_priv], [rc.num_hist], [rc.act_dim])
+    # rollout quantities: act() on the fixture's observations reproduces the reference's mu / values
+    with torch.inference_mode():
+        alg.act(ro["obs"][0].cuda(), ro["priv"][0].cuda(), ro["hist"][0].cuda())
+    assert rel_err(alg.transition.action_mean.cpu(), g["mu"][0]) < 1e-4
+    assert rel_err(alg.transition.values.cpu(), g["values"][0]) < 1e-5
+    alg.transition.clear()
+    st = alg.storage
+    st.observations.copy_(ro["obs"]); st.privileged_observations.copy_(ro["priv"]); st.observation_histories.copy_(ro["hist"])
+    st.actions.copy_(torch.from_numpy(g["actions"])); st.rewards.copy_(ro["rewards"].unsqueeze(-1))
+    st.dones.copy_(ro["dones"].unsqueeze(-1)); st.values.copy_(torch.from_numpy(g["values"]))
+    st.actions_log_prob.copy_(torch.from_numpy(g["actions_log_prob"]))
+    st.mu.copy_(torch.from_numpy(g["mu"])); st.sigma.copy_(torch.from_numpy(g["sigma"]))
+    st.step = rc.num_steps
+    alg.compute_returns(ro["last_obs"].cuda(), ro["last_priv"].cuda())
+    assert rel_err(st.returns.cpu(), g["returns"]) < 1e-5
+    assert rel_err(st.advantages.cpu(), g["advantages"]) < 1e-4
+    vl, sl, al = alg.update()
+    assert abs(vl / g["mean_value_loss"] - 1) < 1e-4
+    assert abs(sl - g["mean_surrogate_loss"]) < 1e-4 * max(1.0, abs(g["mean_surrogate_loss"]))
+    assert abs(al / g["mean_adaptation_loss"] - 1) < 1e-3
+    assert abs(alg.learning_rate / g["final_lr"] - 1) < 1e-6
+    for k, v in ac.state_dict().items():
+        ref = torch.from_numpy(g["final." + k])
+        if k == "std":
+            assert torch.equal(v.cpu(), ref)
+            continue
+        d_ref, d = ref - sd0[k], v.cpu() - sd0[k]
+        frac_bad = ((d - d_ref).abs() > 0.02 * rc.lr).float().mean().item()
+        assert frac_bad < 0.005, (k, frac_bad)
+        if k.startswith(("adaptation_module", "env_factor_encoder")):
+            assert d_ref.abs().max() > 0 and d.abs().max() > 0          # both modules really trained
+
+
 @pytest.mark.parametrize("variant,enc_eps,dec_tanh", [("amp", 0.0, False), ("humanoid", 1e-5, False), ("cassie", 0.0, True)])
 def test_fork_variants_match_cpu_twin(variant, enc_eps, dec_tanh):
     from fullysnnforleggedrobots_b200 import VARIANTS

@@ -106,7 +106,7 @@ def test_committed_fixtures_are_what_the_reference_produces_here():
                        text=True, timeout=600, cwd=gold)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
-    assert len(lines) == len(CASES) + 2
+    assert len(lines) == len(CASES) + 3        # + gae_cassie, ppo_cassie_tiny, rma_ppo_tiny
     # same torch build as the one that wrote them -> bit-identical; another build may differ in the last ulp
     assert all(("bit-identical" in l) or ("max rel diff" in l and float(l.split("max rel diff")[1].split()[0]) < 1e-5)
                for l in lines), r.stdout

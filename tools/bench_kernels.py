@@ -8,6 +8,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 
+# ablation switches / cycle counters live in the -DSNN_ABLATE tools build only (never in the release library)
+if os.environ.get("SNN_DBG", "0") != "0":
+    os.environ["SNN_LIB"] = "ablate"
+    from fullysnnforleggedrobots_b200 import _lib as _l
+    _l.build(ablate=True)
 from fullysnnforleggedrobots_b200 import PopSpikeActor, _lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24576

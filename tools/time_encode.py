@@ -1,6 +1,11 @@
 """GPU-only time of the inference forward (SNN_DBG=64: encoder kernel alone), via CUDA-graph replay."""
 import math, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# ablation switches / cycle counters live in the -DSNN_ABLATE tools build only (never in the release library)
+if os.environ.get("SNN_DBG", "0") != "0":
+    os.environ["SNN_LIB"] = "ablate"
+    from fullysnnforleggedrobots_b200 import _lib as _l
+    _l.build(ablate=True)
 from fullysnnforleggedrobots_b200 import PopSpikeActor
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 24576
 actor = PopSpikeActor(48, 12, 10, 10, [256, 256], (-5, 5), math.sqrt(0.15), spike_ts=5).cuda()
