@@ -123,7 +123,7 @@ _SIGS = {
     "snn_sample_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
-    "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 6
+    "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2 + [C.c_float] * 4
                       + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

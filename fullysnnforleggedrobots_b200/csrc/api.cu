@@ -142,12 +142,27 @@ int debug_mask() {
 #endif
 }
 
+constexpr int kRowSeg = 256;          // rows per segment of the pre-pass (8 loads in flight per thread, one round)
 struct Deferred {
-  RowJobs rows{};
+  RowJobs rows{}, pre{};
   PartJobs parts{};
-  int max_n = 0, max_K = 0, max_N = 0;
+  int max_n = 0, max_K = 0, max_N = 0, pre_max_n = 0, pre_max_seg = 0;
+  float* scratch = nullptr;      // optional: lets jobs with many partial rows go through a segmented pre-pass
+  size_t scratch_floats = 0, scratch_used = 0;
   void row(const float* src, int nparts, size_t stride, int n, float* dst, int col_step = 1) {
-    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride), col_step};
+    const int width = (n - 1) * col_step + 1;
+    const int nseg = (nparts + kRowSeg - 1) / kRowSeg;
+    if (nparts > 2 * kRowSeg && scratch != nullptr && scratch_used + static_cast<size_t>(nseg) * width <= scratch_floats &&
+        pre.count < 12) {
+      float* tmp = scratch + scratch_used;
+      scratch_used += static_cast<size_t>(nseg) * width;
+      pre.j[pre.count++] = RowJob{src, tmp, nparts, width, static_cast<unsigned long long>(stride), 1, kRowSeg,
+                                  static_cast<unsigned long long>(width)};
+      if (width > pre_max_n) pre_max_n = width;
+      if (nseg > pre_max_seg) pre_max_seg = nseg;
+      src = tmp; nparts = nseg; stride = static_cast<size_t>(width);
+    }
+    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride), col_step, 0, 0ull};
     if (n > max_n) max_n = n;
   }
   void part(const float* partial, int splits, int n_tiles, int N, int K, float* dW) {
@@ -164,6 +179,13 @@ int launch_deferred(const Deferred& df, cudaStream_t st) {
     multi_reduce_partials_kernel<<<grd, 128, 0, st>>>(df.parts);
     }
     LAUNCH_CHECK("multi_reduce_partials_kernel");
+  }
+  if (df.pre.count > 0) {
+    dim3 grd((df.pre_max_n + 31) / 32, df.pre.count, df.pre_max_seg);
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    multi_reduce_rows_kernel<<<grd, dim3(32, 32), 0, st>>>(df.pre);
+    }
+    LAUNCH_CHECK("multi_reduce_rows_kernel (segments)");
   }
   if (df.rows.count > 0) {
     dim3 grd((df.max_n + 31) / 32, df.rows.count);
@@ -350,6 +372,8 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
   float* small_enc = reinterpret_cast<float*>(at(workspace, p.ws_small_enc));
   Deferred df;
+  df.scratch = reinterpret_cast<float*>(at(workspace, p.ws_red));
+  df.scratch_floats = p.ws_red_bytes / 4;
   float* g_a = reinterpret_cast<float*>(at(workspace, p.ws_ga));
   const uint32_t* enc_bits = reinterpret_cast<const uint32_t*>(at(trace, p.tr_enc_bits));
 
@@ -737,7 +761,7 @@ int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, v
 }
 
 int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
-                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                  double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream) {
   if (!params || !grads || !m || !v || !lr || !step || !scratch) return fail(SNN_EINVAL, "null pointer");
   if (n <= 0) return fail(SNN_EINVAL, "empty parameter buffer");

@@ -74,6 +74,7 @@ struct SnnPlan {
   size_t ws_partial, ws_partial_stride;   // fp32 split-K partials of dW, one region per layer
   size_t ws_dbpart, ws_dbpart_stride;     // fp32 partial bias grads, one region per layer
   size_t ws_small, ws_small_enc;          // partials of the decoder (ws_small) / encoder (ws_small_enc) gradients
+  size_t ws_red, ws_red_bytes;            // scratch of the segmented row reductions (api.cu: Deferred)
   size_t ws_bwd_bytes;
   size_t ws_fwd_bytes;      // forward-only workspace == a trace without voltages
   int dw_max_ctas;
@@ -170,6 +171,9 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
   p.ws_small = take(static_cast<size_t>(p.ntile) * (p.Bt / 8) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
   p.ws_small_enc = take(static_cast<size_t>(row_parts) * 2 * p.K0P * 4 + 1024);          // encoder partials (3 rows per CTA of DX_ENC)
+  // three jobs (bias, decoder weight, decoder bias) over the top scan's partial rows, 256 rows per segment
+  p.ws_red_bytes = 3 * ((static_cast<size_t>(p.ntile) * (p.Bt / 8) + 255) / 256) * p.layer[p.L - 1].NP * 4 + 4096;
+  p.ws_red = take(p.ws_red_bytes);
   p.ws_bwd_bytes = off;
   *out = p;
   return SNN_OK;

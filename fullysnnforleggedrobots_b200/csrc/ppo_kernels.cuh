@@ -204,8 +204,12 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                        const float* __restrict__ partial, int nparts,
                                                        const float* __restrict__ lr, const int* __restrict__ step,
-                                                       float beta1, float beta2, float eps, float weight_decay,
+                                                       double beta1d, double beta2d, float eps, float weight_decay,
                                                        float max_norm, float grad_scale, float* __restrict__ norm_out) {
+  // torch.optim.Adam: exp_avg.lerp_(g, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2) with the
+  // python-double (1 - beta) rounded to fp32 once
+  const float beta2 = static_cast<float>(beta2d);
+  const float omb1 = static_cast<float>(1.0 - beta1d), omb2 = static_cast<float>(1.0 - beta2d);
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   __shared__ double s_tot[8];
   {
@@ -225,8 +229,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
     s_coef = coef;
     const double t = static_cast<double>(step[0]);
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    const double bc1 = 1.0 - pow(beta1d, t);
+    const double bc2 = 1.0 - pow(beta2d, t);
     s_step_size = static_cast<float>(static_cast<double>(lr[0]) / bc1);
     s_bc2_sqrt = static_cast<float>(sqrt(bc2));
     if (blockIdx.x == 0 && norm_out != nullptr) norm_out[0] = norm;
@@ -238,8 +242,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
     const float pi = prm[i];
     if (weight_decay != 0.f) gi = gi + weight_decay * pi;
     float mi = m[i], vi = v[i];
-    mi = mi + (gi - mi) * (1.f - beta1);
-    vi = vi * beta2 + gi * gi * (1.f - beta2);
+    mi = mi + (gi - mi) * omb1;
+    vi = vi * beta2 + gi * gi * omb2;
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;

@@ -398,12 +398,25 @@ __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __re
 
 // Several independent row reductions / split-K reductions in ONE launch (blockIdx.y resp. .z selects the job):
 // the backward pass defers all of its small reductions to the end instead of launching ten tiny kernels.
-struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; int col_step; };
+// A job with thousands of partial rows (the top-layer scan writes one row per 8 samples: 3072 at B = 24576) is reduced
+// in two launches: blockIdx.z = segment of seg_rows rows -> one row of a scratch matrix, then the scratch rows -> dst
+// (a single block column walking 3072 rows is 12 dependent rounds of load latency: 45 us on the step's critical path).
+struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; int col_step;
+                int seg_rows; unsigned long long seg_dst_stride; };
 struct RowJobs { RowJob j[12]; int count; };
 __global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs jobs) {   // block (32, 32)
-  const RowJob jb = jobs.j[blockIdx.y];
+  RowJob jb = jobs.j[blockIdx.y];
   const int i = blockIdx.x * 32 + threadIdx.x;
   if (blockIdx.x * 32 >= jb.n) return;
+  if (jb.seg_rows > 0) {
+    const int r0 = blockIdx.z * jb.seg_rows;
+    if (r0 >= jb.nparts) return;
+    jb.src += static_cast<size_t>(r0) * jb.stride;
+    jb.dst += static_cast<size_t>(blockIdx.z) * jb.seg_dst_stride;
+    jb.nparts = min(jb.seg_rows, jb.nparts - r0);
+  } else if (blockIdx.z > 0) {
+    return;
+  }
   float acc = 0.f;
   if (i < jb.n) {
     // eight independent loads in flight per thread (the kernel is pure load latency); fixed summation order

@@ -169,9 +169,11 @@ int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, v
 
 /* clip_grad_norm_(max_norm) + Adam.step (ppo.py:176-177) over one flat fp32 buffer of n parameters.
  * grads are first multiplied by grad_scale (1/world after a SUM all-reduce).  lr and step live on the device;
- * step is incremented by this call.  norm_out (nullable) receives the pre-clip gradient norm.  scratch >= 2 KiB. */
+ * step is incremented by this call.  norm_out (nullable) receives the pre-clip gradient norm.  scratch >= 2 KiB.
+ * The betas are doubles: torch.optim.Adam forms (1 - beta) in double before rounding to fp32 (1 - 0.999 in fp32
+ * arithmetic is 1.3e-5 off), and the second-moment buffer must match it. */
 int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
-                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                  double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream);
 
 /* Optional per-launch device timing used by bench.py's roofline: while enabled, every kernel launch is

@@ -149,9 +149,12 @@ def test_tensor_core_critic_matches_torch_fp32(dims, B):
         assert rel_err(gb[i].cpu(), l.bias.grad.cpu()) < 1e-4, f"db{i}"
 
 
-def test_data_parallel_graph_segments_match_single_process():
-    """The data-parallel update (graph A -> NCCL all-reduce -> graph B) with a world of one rank must reproduce the
-    single-process fused update: same kernels, same order, one extra (identity) collective."""
+@pytest.mark.parametrize("dp_mode", ["single", "segments"])
+def test_data_parallel_graph_modes_match_single_process(dp_mode, monkeypatch):
+    """The data-parallel update with a world of one rank must reproduce the single-process fused update: same kernels,
+    same order, one extra (identity) collective.  "single": the NCCL all-reduce captured inside the step graph;
+    "segments": graph A -> eager NCCL all-reduce -> graph B."""
+    monkeypatch.setenv("SNN_DP_GRAPH", dp_mode)
     import socket
 
     import torch.distributed as dist
@@ -181,7 +184,11 @@ def test_data_parallel_graph_segments_match_single_process():
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
     try:
         (vl1, sl1), sd1, alg = run(snn_dist.GradientAllReducer())
-        assert alg.use_cuda_graph and ("pre", 0) in alg._graphs and "post" in alg._graphs
+        assert alg.use_cuda_graph and alg.dp_graph_mode == dp_mode, alg.dp_graph_note
+        if dp_mode == "single":
+            assert ("full", 0) in alg._graphs
+        else:
+            assert ("pre", 0) in alg._graphs and "post" in alg._graphs
     finally:
         dist.destroy_process_group()
     assert abs(vl0 - vl1) <= 1e-5 * abs(vl0) and abs(sl0 - sl1) <= 1e-5 * max(1.0, abs(sl0))
@@ -299,6 +306,7 @@ def _two_updates(pc, g, ro, graph, ent2, intermezzo=False):
         if k == 1:
             alg.entropy_coef = ent2                 # a runner annealing the entropy bonus between iterations
             alg.clip_param = 0.15
+        torch.manual_seed(1000 + k)                 # the update's randperm: same row order in the runs being compared
         out.append(alg.update())
         if intermezzo and k == 0:
             # eager calls with a LARGER batch between two graph replays: they re-allocate the engines' internal
