@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the spiking actor-critic hot path (BASELINE.json configs[1]):
+"""bench.py — headline benchmark of the spiking actor-critic hot path.
 
-    A1 AMP spiking actor-critic PPO update: 4096 envs x 24-step rollout, surrogate-gradient BPTT.
+BASELINE.json's metric has two halves; both are in the one JSON line rank 0 prints:
 
-A "step" is one full PPO `update()` over the rollout (5 epochs x 4 minibatches of 24 576 samples: actor
-forward with traces, critic, PPO losses, BPTT backward, grad-norm clip, Adam; reference
-rsl_rl/algorithms/ppo.py:120-187).  metric = PPO samples/s = envs * steps_per_env * epochs / update time,
-summed over ranks (weak scaling: every rank owns its own 4096 environments, gradients are all-reduced).
+  (ii) PPO samples/s (forward + BPTT)  -> the line's `value` / `e2e` / `roofline` / `cpu_baseline`
+       workload = BASELINE configs[1]: A1 AMP spiking actor-critic PPO update, 4096 envs x 24-step rollout.
+       A "step" is one full PPO `update()` (5 epochs x 4 minibatches of 24 576 samples: actor forward with traces,
+       critic, PPO losses, BPTT backward, grad-norm clip, Adam; reference rsl_rl/algorithms/ppo.py:120-187).
+       N > 1: weak scaling, every rank owns its own 4096 environments, gradients all-reduced (`scaling: "weak"`).
+  (i)  SNN policy env-steps/s (forward) -> the `fwd` block (value, e2e, roofline, cpu_baseline on configs[0]:
+       the A1 spiking actor forward on 4096 observations; reference modules/actor_critic.py:300-320).
+
+plus, at every N, a `strong` block: BASELINE configs[2] (MIT Humanoid, 4096 envs x 24 steps IN TOTAL, sharded
+num_envs / world per GPU as SURVEY 8e partitions it) and `dp_check` (parameter checksums equal across ranks after
+the timed updates).
 
   python bench.py --gpus 1 --steps 3 --warmup 3            # our arm
-  python bench.py --impl reference --steps 3 --warmup 3    # CPU arm (oracle port of the reference path)
-
-Prints ONE JSON line (rank 0).
+  python bench.py --impl reference --steps 3 --warmup 3    # CPU arm: the UNMODIFIED reference PPO.update (staged by
+                                                           # oracle/make_ref.sh) or, if it is not staged, the oracle port
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import math
 import os
@@ -31,10 +38,21 @@ for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golde
 
 import torch  # noqa: E402
 
+# BASELINE.json configs[1] (the headline; also the per-GPU workload of the weak-scaling curve)
 WORKLOAD = {
     "name": "a1_amp_ppo_update_4096x24",
     "num_envs": 4096, "steps_per_env": 24, "obs_dim": 48, "act_dim": 12,
     "actor_hidden": [256, 256], "critic_hidden": [256, 256], "spike_ts": 5,
+    "epochs": 5, "mini_batches": 4,
+}
+# BASELINE.json configs[0]: the forward half of the metric and its CPU-runnable case
+FWD_WORKLOAD = {"name": "a1_rma_actor_fwd_4096", "batch": 4096, "obs_dim": 48, "act_dim": 12, "actor_hidden": [256, 256],
+                "spike_ts": 5, "flops_per_sample": 2 * 5 * (480 * 256 + 256 * 256 + 256 * 120)}
+# BASELINE.json configs[2]: the strong-scaling case, num_envs is the TOTAL over all ranks
+STRONG_WORKLOAD = {
+    "name": "mit_humanoid_ppo_update_4096x24_sharded",
+    "num_envs": 4096, "steps_per_env": 24, "obs_dim": 38, "act_dim": 10,
+    "actor_hidden": [256, 256, 256], "critic_hidden": [256, 256, 256], "spike_ts": 5,
     "epochs": 5, "mini_batches": 4,
 }
 METRIC = "ppo_samples_per_s_fwd_bptt"
@@ -102,14 +120,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_minibatch_runner(rows: int, seed: int = 0, device: str = "cpu"):
-    """Oracle port of one PPO minibatch step (actor fwd with autograd graph, critic, losses, BPTT, clip, Adam)
-    of the reference on the host cores (or, for `--impl port-gpu`, the same torch ops on the CUDA device: the stock
-    PyTorch GPU path of SURVEY 8d).  Returns a callable running one step on `rows` samples."""
+# ---------------------------------------------------------------------------------------------- CPU arms
+def _bench_state_dict(W, seed=0):
+    """Reference default-style init of the C2 actor-critic (same tensors for the reference modules and the port)."""
     from cases import Case, make_state_dict
-    from oracle import ppo_oracle as P
-    W = WORKLOAD
     c = Case("bench", "amp", W["obs_dim"], tuple(W["actor_hidden"]), W["act_dim"], 1, spike_ts=W["spike_ts"], seed=seed)
     sd = make_state_dict(c)
     g = torch.Generator().manual_seed(seed)
@@ -119,6 +133,16 @@ def cpu_minibatch_runner(rows: int, seed: int = 0, device: str = "cpu"):
         sd[f"critic.{2 * i}.weight"] = (torch.rand(dims[i + 1], dims[i], generator=g) * 2 - 1) * b
         sd[f"critic.{2 * i}.bias"] = (torch.rand(dims[i + 1], generator=g) * 2 - 1) * b
     sd["std"] = torch.ones(W["act_dim"])
+    return sd, g
+
+
+def cpu_minibatch_runner(rows: int, seed: int = 0, device: str = "cpu"):
+    """Oracle port of one PPO minibatch step (actor fwd with autograd graph, critic, losses, BPTT, clip, Adam)
+    of the reference on the host cores (or, for `--impl port-gpu`, the same torch ops on the CUDA device: the stock
+    PyTorch GPU path of SURVEY 8d).  Returns a callable running one step on `rows` samples."""
+    from oracle import ppo_oracle as P
+    W = WORKLOAD
+    sd, g = _bench_state_dict(W, seed)
     sd = {k: v.to(device) for k, v in sd.items()}
     ac = P.OracleActorCritic(sd, spike_ts=W["spike_ts"])
     cfg = P.PPOConfig()
@@ -138,34 +162,123 @@ def cpu_minibatch_runner(rows: int, seed: int = 0, device: str = "cpu"):
     return step
 
 
+def reference_minibatch_runner(rows: int, seed: int = 0):
+    """The UNMODIFIED reference on the host cores: AMP fork's ActorCritic + PPO + RolloutStorage (staged under
+    oracle/_ref by oracle/make_ref.sh; AMP-rl/algorithms/ppo.py:120-187), one `PPO.update()` with one epoch and one
+    minibatch of `rows` samples = one minibatch step (incl. the reference's own randperm + nine gathers).
+    Returns None when the reference is not staged."""
+    from oracle import ref_loader as R
+    if not R.available("amp"):
+        return None
+    W = WORKLOAD
+    mods, algs, _ = R.load_all("amp")
+    sd, g = _bench_state_dict(W, seed)
+    with R.quiet():
+        ac = mods.ActorCritic(W["obs_dim"], W["obs_dim"], W["act_dim"], actor_hidden_dims=list(W["actor_hidden"]),
+                              critic_hidden_dims=list(W["critic_hidden"]), activation="elu", init_noise_std=1.0)
+    ac.actor.encoder.device = ac.actor.snn.device = "cpu"        # the ctor hard-codes "cuda" for its zeros (SURVEY 8c)
+    ac.load_state_dict(sd)
+    alg = algs.PPO(ac, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.99, lam=0.95,
+                   value_loss_coef=1.0, entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0,
+                   use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cpu")
+    S = 8
+    N = rows // S
+    A = W["act_dim"]
+    alg.init_storage(N, S, [W["obs_dim"]], [None], [A])
+    st = alg.storage
+    st.observations.copy_(torch.randn(S, N, W["obs_dim"], generator=g))
+    st.actions.copy_(torch.randn(S, N, A, generator=g) * 0.5)
+    st.values.copy_(torch.randn(S, N, 1, generator=g))
+    st.returns.copy_(torch.randn(S, N, 1, generator=g))
+    st.advantages.copy_(torch.randn(S, N, 1, generator=g))
+    st.actions_log_prob.copy_(-0.5 * A * math.log(2 * math.pi) + torch.randn(S, N, 1, generator=g) * 0.1 - 2.0)
+    st.mu.copy_(torch.randn(S, N, A, generator=g) * 0.3)
+    st.sigma.fill_(1.0)
+
+    def step():
+        with R.quiet():                      # the AMP fork's forward prints on every call
+            alg.update()
+
+    return step
+
+
 def time_cpu(rows: int, steps: int, warmup: int):
+    """(samples/s, s/step, kind) of one PPO minibatch step on `rows` rows on all host cores."""
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_minibatch_runner(rows)
+    step = reference_minibatch_runner(rows)
+    kind = "reference"
+    if step is None:
+        step, kind = cpu_minibatch_runner(rows), "port"
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return rows / dt, dt
+    return rows / dt, dt, kind
+
+
+def time_cpu_forward(batch: int, reps: int = 5, warmup: int = 2):
+    """configs[0]: the reference's PopSpikeActor forward (obs -> mu, std) on `batch` observations, host cores, under
+    inference_mode, stdout silenced; best of `reps`.  Falls back to the oracle port when not staged."""
+    from cases import Case, make_state_dict
+    from oracle import ref_loader as R
+    W = FWD_WORKLOAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    c = Case("bench_fwd", "rma", W["obs_dim"], tuple(W["actor_hidden"]), W["act_dim"], 1, spike_ts=W["spike_ts"], seed=0)
+    sd = {k[len("actor."):]: v for k, v in make_state_dict(c).items() if k.startswith("actor.")}
+    obs = torch.randn(batch, W["obs_dim"], generator=torch.Generator().manual_seed(0))
+    if R.available("rma"):
+        mods = R.load("rma", "modules.actor_critic")
+        with R.quiet():
+            actor = mods.PopSpikeActor(W["obs_dim"], W["act_dim"], 10, 10, list(W["actor_hidden"]), (-5, 5),
+                                       math.sqrt(0.15), spike_ts=W["spike_ts"], device="cpu")
+        actor.load_state_dict(sd)
+        kind = "reference"
+
+        def fwd():
+            with R.quiet(), torch.inference_mode():
+                actor(obs)
+    else:
+        from helpers import oracle_params
+        from oracle import snn_oracle as O
+        prm, kind = oracle_params(c), "port"
+
+        def fwd():
+            with torch.inference_mode():
+                O.actor_forward(obs, prm)
+    for _ in range(warmup):
+        fwd()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fwd()
+        best = min(best, time.perf_counter() - t0)
+    return batch / best, best, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, dt = time_cpu(CPU_SAMPLE_ROWS, args.steps, args.warmup)
+    value, dt, kind = time_cpu(CPU_SAMPLE_ROWS, args.steps, args.warmup)
     cores = torch.get_num_threads()
+    what = ("the UNMODIFIED reference (AMP fork ActorCritic + PPO.update + RolloutStorage, staged by oracle/make_ref.sh)"
+            if kind == "reference" else "oracle port of the reference (torch CPU fp32 autograd)")
     sample = (f"one PPO minibatch step (actor fwd+BPTT, critic, losses, clip, Adam) on {CPU_SAMPLE_ROWS} of the "
-              f"24576 minibatch rows per timed step; oracle port of the reference (torch CPU fp32 autograd)")
+              f"24576 minibatch rows per timed step; {what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], **{k: v for k, v in WORKLOAD.items() if k != "name"}},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.quick:
+        fv, fdt, fkind = time_cpu_forward(FWD_WORKLOAD["batch"])
+        line["fwd"] = {"metric": "snn_policy_env_steps_per_s_fwd", "value": fv, "unit": "env-steps/s",
+                       "ms_per_call": fdt * 1e3, "kind": fkind, "cores": cores, "workload": FWD_WORKLOAD["name"]}
     print(json.dumps(line))
     return 0
 
@@ -206,51 +319,38 @@ def run_port_gpu(args):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def latest_traffic():
+    """The newest committed ncu capture summary (profiles/r*_traffic.json): DRAM bytes / tensor-pipe % per kernel, with
+    the commit it was captured at.  ncu numbers cannot be produced inside a bench run (never time under a profiler)."""
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not paths:
+        return None, None
+    with open(paths[-1]) as f:
+        return json.load(f), os.path.relpath(paths[-1], ROOT)
+
+
 def run_ours(args):
+    import ctypes as C
+
     import torch.distributed as dist
 
-    from fullysnnforleggedrobots_b200 import PPO, ActorCritic, _lib
+    from fullysnnforleggedrobots_b200 import PPO, ActorCritic, ActorCriticHumanoid, _lib
     from fullysnnforleggedrobots_b200 import dist as snn_dist
 
-    W = WORKLOAD
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the spiking actor has no CPU fallback")
+    L = _lib.lib()
+    if L.snn_build_flags() != 0 or os.environ.get("SNN_DBG"):
+        raise RuntimeError("bench.py refuses to time a tools build (-DSNN_ABLATE) or a run with SNN_DBG set: "
+                           f"build_flags={L.snn_build_flags()} SNN_DBG={os.environ.get('SNN_DBG')!r}")
+    if os.environ.get("SNN_GRAPH_FALLBACK", "0") == "1":
+        raise RuntimeError("bench.py refuses SNN_GRAPH_FALLBACK=1: a failed CUDA-graph capture must be an error here")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     reducer = snn_dist.init_from_env("nccl") if world > 1 else None
-
-    torch.manual_seed(0)
-    ac = ActorCritic(W["obs_dim"], W["obs_dim"], W["act_dim"], actor_hidden_dims=W["actor_hidden"],
-                     critic_hidden_dims=W["critic_hidden"], activation="elu", init_noise_std=1.0,
-                     spike_ts=W["spike_ts"])
-    alg = PPO(ac, num_learning_epochs=W["epochs"], num_mini_batches=W["mini_batches"], clip_param=0.2, gamma=0.99,
-              lam=0.95, value_loss_coef=1.0, entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0,
-              use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device=dev, data_parallel=reducer)
-    N, S, O, A = W["num_envs"], W["steps_per_env"], W["obs_dim"], W["act_dim"]
-    alg.init_storage(N, S, [O], [None], [A])
-
-    # ---- synthetic rollout (seeded per rank), produced on the host in pinned memory
-    g = torch.Generator().manual_seed(1234 + rank)
-    host = {
-        "obs": torch.randn(S, N, O, generator=g).pin_memory(),
-        "rewards": torch.randn(S, N, generator=g).pin_memory(),
-        "dones": (torch.rand(S, N, generator=g) < 0.02).to(torch.uint8).pin_memory(),
-        "last_obs": torch.randn(N, O, generator=g).pin_memory(),
-    }
-    with torch.inference_mode():
-        for s in range(S):
-            obs = host["obs"][s].to(dev, non_blocking=True)
-            alg.act(obs, obs)
-            alg.process_env_step(host["rewards"][s].to(dev), host["dones"][s].to(dev), {})
-        alg.compute_returns(host["last_obs"].to(dev))
-    st = alg.storage
-    # host copies of what the rollout phase produced (for the end-to-end leg)
-    for name in ("actions", "values", "actions_log_prob", "mu", "sigma"):
-        host[name] = getattr(st, name).detach().cpu().pin_memory()
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -272,13 +372,44 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    def make_job(W, envs_local, cls, seed_off):
+        """ActorCritic + PPO + a filled rollout of `envs_local` environments for workload W (host copies pinned)."""
+        torch.manual_seed(0)
+        ac = cls(W["obs_dim"], W["obs_dim"], W["act_dim"], actor_hidden_dims=W["actor_hidden"],
+                 critic_hidden_dims=W["critic_hidden"], activation="elu", init_noise_std=1.0, spike_ts=W["spike_ts"])
+        alg = PPO(ac, num_learning_epochs=W["epochs"], num_mini_batches=W["mini_batches"], clip_param=0.2, gamma=0.99,
+                  lam=0.95, value_loss_coef=1.0, entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0,
+                  use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device=dev, data_parallel=reducer)
+        N, S, O, A = envs_local, W["steps_per_env"], W["obs_dim"], W["act_dim"]
+        alg.init_storage(N, S, [O], [None], [A])
+        g = torch.Generator().manual_seed(1234 + seed_off + rank)
+        host = {
+            "obs": torch.randn(S, N, O, generator=g).pin_memory(),
+            "rewards": torch.randn(S, N, generator=g).pin_memory(),
+            "dones": (torch.rand(S, N, generator=g) < 0.02).to(torch.uint8).pin_memory(),
+            "last_obs": torch.randn(N, O, generator=g).pin_memory(),
+        }
+        with torch.inference_mode():
+            for s in range(S):
+                obs = host["obs"][s].to(dev, non_blocking=True)
+                alg.act(obs, obs)
+                alg.process_env_step(host["rewards"][s].to(dev), host["dones"][s].to(dev), {})
+            alg.compute_returns(host["last_obs"].to(dev))
+        for name in ("actions", "values", "actions_log_prob", "mu", "sigma"):
+            host[name] = getattr(alg.storage, name).detach().cpu().pin_memory()
+        torch.cuda.synchronize()
+        return ac, alg, host
+
+    W = WORKLOAD
+    N, S, O, A = W["num_envs"], W["steps_per_env"], W["obs_dim"], W["act_dim"]
+    ac, alg, host = make_job(W, N, ActorCritic, 0)
+    st = alg.storage
     samples_per_step = N * S * W["epochs"]          # per rank
 
     # ---- device-resident leg
     def step_resident():
         alg.update()
 
-    L = _lib.lib()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # started before warm-up: nvidia-smi needs ~0.5 s before its first sample
@@ -290,10 +421,25 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * samples_per_step / (ms_per_step * 1e-3)
+    graphs_used = bool(alg.use_cuda_graph and len(alg._graphs) > 0)
+    if not graphs_used:
+        raise RuntimeError("the timed update did not replay CUDA graphs (capture failed or was disabled)")
+
+    # ---- dp_check: after the timed updates every rank must hold bit-identical parameters (the gradients it applied
+    #      came out of one all-reduce; the rollouts differ per rank, so equality is not trivial)
+    flat = alg.optimizer.flat_params
+    chk = torch.stack([flat.double().sum(), flat.view(torch.int32).to(torch.int64).sum().double()])
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        dp_check = {"ranks": world, "params_bit_identical": bool(all(torch.equal(c, allc[0]) for c in allc)),
+                    "param_sum": float(chk[0].item()), "dp_graph": alg.dp_graph_mode, "dp_graph_note": alg.dp_graph_note}
+    else:
+        dp_check = {"ranks": 1, "params_bit_identical": True, "param_sum": float(chk[0].item()), "dp_graph": "n/a",
+                    "dp_graph_note": ""}
 
     # ---- per-kernel device times for the roofline: the SAME steps, launched eagerly (events cannot be read
     #      back from inside a replayed CUDA graph); kernel durations do not depend on how they were launched
-    import ctypes as C
     graph_flag = alg.use_cuda_graph
     alg.use_cuda_graph = False
     step_resident()
@@ -339,17 +485,30 @@ def run_ours(args):
         ms_e2e = timed(step_e2e, args.steps) / args.steps
         e2e_value = world * samples_per_step / (ms_e2e * 1e-3)
 
-    # ---- forward-only metric (rollout `act`): env-steps/s at B = num_envs
-    obs_dev = host["obs"][0].to(dev)
+    # ---- forward half of the metric: the spiking actor's rollout forward at B = 4096 (configs[0] dims == C2's actor)
+    FW = FWD_WORKLOAD
+    Bf = FW["batch"]
+    nrep = 2 if args.quick else 50
+    obs_dev = host["obs"][0][:Bf].to(dev)
+    obs_pin = host["obs"][0][:Bf].contiguous().pin_memory()
+    mu_pin = torch.empty(Bf, A).pin_memory()
 
-    def step_act():
+    def step_act():                                  # obs resident in HBM -> mu, std resident
         with torch.inference_mode():
             ac.act_inference(obs_dev)
 
+    def step_act_e2e():                              # host obs in, host mu out, through the module's public call
+        with torch.inference_mode():
+            mu_pin.copy_(ac.act_inference(obs_pin.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
     for _ in range(2 if args.quick else 10):
         step_act()
-    ms_act = timed(step_act, 2 if args.quick else 50) / (2 if args.quick else 50)
-    act_value = world * N / (ms_act * 1e-3)
+    fl0 = L.snn_launch_count()
+    ms_act = timed(step_act, nrep) / nrep
+    fwd_launches = (L.snn_launch_count() - fl0) // nrep
+    step_act_e2e()
+    ms_act_e2e = timed(step_act_e2e, nrep) / nrep
 
     # full rollout step PPO.act (actor forward + sample + log-prob + critic), replayed as one CUDA graph
     def step_ppo_act():
@@ -359,8 +518,25 @@ def run_ours(args):
 
     for _ in range(2 if args.quick else 6):
         step_ppo_act()
-    ms_pact = timed(step_ppo_act, 2 if args.quick else 50) / (2 if args.quick else 50)
-    pact_value = world * N / (ms_pact * 1e-3)
+    ms_pact = timed(step_ppo_act, nrep) / nrep
+
+    # ---- strong scaling: BASELINE configs[2] / SURVEY C3, 4096 environments IN TOTAL, num_envs / world per rank
+    SW = STRONG_WORKLOAD
+    strong = None
+    if not args.quick:
+        lo, hi = snn_dist.shard_range(SW["num_envs"], rank, world)
+        if (hi - lo) * SW["steps_per_env"] % SW["mini_batches"] != 0 or SW["num_envs"] % world != 0:
+            raise RuntimeError("strong-scaling workload does not shard evenly over this world size")
+        _, salg, _ = make_job(SW, hi - lo, ActorCriticHumanoid, 77)
+        for _ in range(max(args.warmup, 3)):
+            salg.update()
+        ms_s = timed(salg.update, args.steps) / args.steps
+        strong = {"workload": SW["name"], "scaling": "strong", "value": SW["num_envs"] * SW["steps_per_env"] * SW["epochs"] / (ms_s * 1e-3),
+                  "unit": UNIT, "ms_per_step": ms_s, "envs_total": SW["num_envs"], "envs_per_gpu": hi - lo,
+                  "minibatch_rows_per_gpu": (hi - lo) * SW["steps_per_env"] // SW["mini_batches"],
+                  "flops_per_sample_fwd_bptt": 6645760,
+                  "note": "total work fixed: 98304 samples x 5 epochs per update whatever N; per-rank minibatches shrink to "
+                          "24576 / N rows, so every step is 20 x (~37 launch-bound kernels + one gradient all-reduce)"}
 
     if rank != 0:
         if world > 1:
@@ -379,20 +555,16 @@ def run_ours(args):
     dom_kernel = ["nm_gemm_kernel<FWD>", "nm_gemm_kernel<DX>" if dl > 0 else "nm_gemm_kernel<DX_ENC>", "dw_gemm_kernel"][dk] + f" (actor layer {dl})"
     achieved = pfl32[di] / (pms32[di] * 1e-3) / 1e12
     traffic, pipe_pct, smem_pct = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r1m_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tk = json.load(f)["kernels"].get(dom_name)
+    tj, tpath = latest_traffic()
+    hbm_view = {}
+    if tj is not None:
+        tk = tj["kernels"].get(dom_name)
         if tk:
             traffic, pipe_pct = tk["dram_bytes_per_launch"], tk["tensor_pipe_active_pct"]
             smem_pct = tk.get("smem_pipe_tensor_pct", 0.0) + tk.get("smem_pipe_lsu_pct", 0.0)
-    # secondary bound: HBM.  ncu DRAM bytes per launch (committed capture) over this run's CUDA-event kernel times.
-    hbm_view = {}
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tks = json.load(f)["kernels"]
+        # secondary bound: HBM.  ncu DRAM bytes per launch (committed capture) over this run's CUDA-event kernel times.
         for name, v in per_layer.items():
-            tkk = tks.get(name)
+            tkk = tj["kernels"].get(name)
             if tkk and v["us_per_launch"] > 0:
                 gbs = tkk["dram_bytes_per_launch"] / (v["us_per_launch"] * 1e-6) / 1e9
                 hbm_view[name] = {"dram_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
@@ -403,25 +575,39 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic,
         "us_per_launch": 1e3 * pms32[di] / pln32[di], "algo_flops_per_launch": pfl32[di] / pln32[di],
         "ncu_tensor_pipe_active_pct": pipe_pct, "ncu_smem_data_pipe_pct": smem_pct,
+        "ncu_capture": {"file": tpath, "commit": tj.get("commit") if tj else None,
+                        "note": "traffic / tensor-pipe % / shared-memory data-pipe % are read from this committed ncu "
+                                "capture (a profiler never runs inside a bench run); achieved / frac are measured live"},
         "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
         "note": "achieved = ALGORITHMIC flops (2*B*K*N*T per layer GEMM, one product per MAC) / CUDA-event kernel time; "
                 "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC, so issued tensor work is 3x 'achieved'; "
-                "kernel times from an eager re-run of the timed steps (the timed region itself replays CUDA graphs); "
-                "traffic / tensor-pipe % / shared-memory data-pipe % from the committed ncu capture profiles/r1m_* "
-                "(the tensor-core kernels are bound by the SM's shared-memory data pipe: operand reads of the MMAs plus the "
-                "bulk-copy / expansion writes that feed them, DESIGN.md 4.6)",
+                "kernel times from an eager re-run of the timed steps (the timed region itself replays CUDA graphs)",
+        "whole_step": {"algo_tflops": samples_per_step * 5345280 / (ms_per_step * 1e-3) / 1e12,
+                       "frac": samples_per_step * 5345280 / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                       "note": "per GPU: actor fwd+BPTT flops (5 345 280 per sample) over the whole timed update"},
         "all_tensor_kernels": {"ms": tc_ms, "algo_tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
                                "share_of_step": tc_ms / ms_total,
                                "eager_profiled_ms_per_step": ms_prof_total / args.steps},
-        "hbm_view": {"peak_gbs": pk["hbm_gbs"], "per_kernel": hbm_view,
-                     "note": "the dX kernels of the hidden layers stream fp32 voltage traces and two bf16 g_c planes and run at "
-                             "~0.7 of the HBM copy peak; the training forward is limited by trace WRITES (DESIGN.md 4.6)"},
+        "hbm_view": {"peak_gbs": pk["hbm_gbs"], "per_kernel": hbm_view},
         "per_kernel": per_cat,
         "per_layer": per_layer,
         "critic_tensor_kernels": {"ms": sum(cms[:3]), "launches": int(sum(cln[:3])),
                                   "algo_tflops": sum(cfl[:3]) / (sum(cms[:3]) * 1e-3) / 1e12 if sum(cms[:3]) > 0 else 0.0},
     }
-    cpu_value, cpu_dt = time_cpu(CPU_SAMPLE_ROWS, 3, 2) if (world == 1 and not args.quick) else (None, None)
+    fwd_tf = Bf * FW["flops_per_sample"] / (ms_act * 1e-3) / 1e12
+    fwd = {
+        "metric": "snn_policy_env_steps_per_s_fwd", "workload": FW["name"], "unit": "env-steps/s",
+        "value": world * Bf / (ms_act * 1e-3), "ms_per_call": ms_act, "batch_per_gpu": Bf, "gpu_launches_per_call": int(fwd_launches),
+        "e2e": {"value": world * Bf / (ms_act_e2e * 1e-3), "unit": "env-steps/s", "ms_per_call": ms_act_e2e,
+                "h2d_bytes_per_step": Bf * O * 4, "d2h_bytes_per_step": Bf * A * 4},
+        "roofline": {"bound": "tensor", "achieved": fwd_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": fwd_tf / pk["bf16_tflops_sustained"], "traffic": None,
+                     "algo_flops_per_call": Bf * FW["flops_per_sample"],
+                     "note": "per GPU; the whole forward call (all of its launches), 2*T*sum K*N flops per sample; at 4096 "
+                             "environments the call is latency-bound (9 GFLOP = 6.4 us at peak)"},
+        "ppo_act": {"value": world * N / (ms_pact * 1e-3), "ms_per_call": ms_pact,
+                    "note": "the whole PPO.act rollout step (actor forward, sample, log-prob, critic value), one CUDA-graph replay"},
+    }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -430,22 +616,29 @@ def run_ours(args):
                    "arithmetic": "fp32-parity: weights as three exact bf16 planes (hi+mid+lo == W), spikes exact, fp32 "
                                  "accumulation on the tensor cores; backward operands as hi/lo bf16 pairs (3 products)",
                    "parallelism": f"dp{world}", "envs_per_gpu": N,
-                   "l2": "inputs larger than L2: 54 MB rollout + 0.3 GB traces per minibatch vs 126 MB L2"},
+                   "l2": "inputs larger than L2: 54 MB rollout + 0.3 GB traces per minibatch vs 126 MB L2",
+                   "cuda_graphs": graphs_used, "build_flags": int(L.snn_build_flags())},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "extra": {"act_env_steps_per_s": act_value, "act_ms": ms_act, "act_batch": N,
-                  "ppo_act_env_steps_per_s": pact_value, "ppo_act_ms": ms_pact,
-                  "note": "act_* = PopSpikeActor forward (obs -> mu, std) under inference_mode; ppo_act_* = the whole "
-                          "PPO.act rollout step (sample, log-prob, critic value) as one CUDA-graph replay"},
+        "fwd": fwd,
+        "strong": strong,
+        "dp_check": dp_check,
     }
-    if cpu_value is not None:
+    if world == 1 and not args.quick:
+        cpu_value, cpu_dt, kind = time_cpu(CPU_SAMPLE_ROWS, 3, 2)
+        what = ("UNMODIFIED reference PPO.update (AMP fork, staged by oracle/make_ref.sh)" if kind == "reference"
+                else "oracle port (torch CPU fp32 autograd)")
         line["cpu_baseline"] = {
-            "value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one PPO minibatch step on {CPU_SAMPLE_ROWS} of 24576 rows, 2 warm-up + 3 timed, oracle port "
-                      f"(torch CPU fp32 autograd); {cpu_dt:.2f} s/step"}
+            "value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"one PPO minibatch step on {CPU_SAMPLE_ROWS} of 24576 rows, 2 warm-up + 3 timed, {what}; "
+                      f"{cpu_dt:.2f} s/step"}
+        fv, fdt, fkind = time_cpu_forward(Bf)
+        fwd["cpu_baseline"] = {"value": fv, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": fkind,
+                               "sample": f"PopSpikeActor forward on the same {Bf} observations (configs[0]), inference_mode, "
+                                         f"best of 5; {fdt * 1e3:.1f} ms per call"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -458,7 +651,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "port-gpu"])
-    ap.add_argument("--quick", action="store_true", help="resident leg only (for ncu runs): no e2e / act / CPU legs")
+    ap.add_argument("--quick", action="store_true", help="resident leg only (for ncu runs): no e2e / strong / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
