@@ -538,10 +538,20 @@ def run_ours(args):
                   "note": "total work fixed: 98304 samples x 5 epochs per update whatever N; per-rank minibatches shrink to "
                           "24576 / N rows, so every step is 20 x (~37 launch-bound kernels + one gradient all-reduce)"}
 
-    if rank != 0:
+    def leave():
+        """Multi-rank exit.  The step graphs hold captured NCCL kernels; tearing the communicator down under them
+        (destroy_process_group) can block forever (seen at N = 2: the JSON line was out, the processes never left).
+        All ranks meet once more, drain the device and leave without the NCCL teardown."""
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         return 0
+
+    if rank != 0:
+        return leave()
 
     pk = peaks()
     cats = ["fwd_nm_gemm", "dx_nm_gemm", "dw_gemm", "other_simt"]
@@ -640,9 +650,7 @@ def run_ours(args):
                                "sample": f"PopSpikeActor forward on the same {Bf} observations (configs[0]), inference_mode, "
                                          f"best of 5; {fdt * 1e3:.1f} ms per call"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return leave()
 
 
 def main():

@@ -45,7 +45,8 @@ class SnnGrads(C.Structure):
 
 
 class SnnMlpDesc(C.Structure):
-    _fields_ = [("in_dim", C.c_int32), ("num_hidden", C.c_int32), ("hidden", C.c_int32 * SNN_MAX_LAYERS)]
+    _fields_ = [("in_dim", C.c_int32), ("num_hidden", C.c_int32), ("hidden", C.c_int32 * SNN_MAX_LAYERS),
+                ("out_dim", C.c_int32)]
 
 
 class SnnMlpParams(C.Structure):
@@ -118,6 +119,11 @@ _SIGS = {
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snn_mlp_bwd": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_int64, C.c_void_p,
                               C.c_void_p, C.POINTER(SnnMlpGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_mlp_fwd_ex": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_mlp_bwd_ex": (C.c_int, [C.POINTER(SnnMlpDesc), C.POINTER(SnnMlpParams), C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(SnnMlpGrads), C.c_void_p,
+                                 C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snn_ppo_head": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
                      + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "snn_sample_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

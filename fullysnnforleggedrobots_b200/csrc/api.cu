@@ -531,70 +531,41 @@ int snn_gather_rows(int count, const void* const* src, void* const* dst, const i
   return SNN_OK;
 }
 
-// ------------------------------------------------------------------ dense ELU critic on the tensor cores
-size_t snn_mlp_packed_bytes(const SnnMlpDesc* d) {
-  MlpPlan p;
-  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, 1, &p) != SNN_OK) return 0;
-  return p.packed_bytes;
-}
-size_t snn_mlp_trace_bytes(const SnnMlpDesc* d, int64_t B) {
-  MlpPlan p;
-  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return 0;
-  return p.trace_bytes;
-}
-size_t snn_mlp_workspace_bytes(const SnnMlpDesc* d, int64_t B) {
-  MlpPlan p;
-  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return 0;
-  return p.ws_bytes;
-}
-
-int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* prm, void* packed, void* stream) {
-  int sms = 0;
-  int rc = device_ready(&sms);
-  if (rc) return rc;
-  MlpPlan p;
-  if (!d || !prm || !packed || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, 1, &p) != SNN_OK)
-    return fail(SNN_EINVAL, "bad MLP descriptor");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PackJobs jobs{};
-  int max_total = 0;
-  for (int l = 0; l < p.H; ++l) {
-    const MlpLayerPlan& lp = p.layer[l];
-    if (!prm->weight[l] || !prm->bias[l]) return fail(SNN_EINVAL, "null weight/bias pointer");
-    jobs.j[l] = PackJob{prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP, at(packed, lp.w_img), lp.w_plane,
-                        at(packed, lp.wt_img), lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad))};
-    if (lp.NP * lp.KP / 8 > max_total) max_total = lp.NP * lp.KP / 8;
-  }
-  { ProfScope prof__(CAT_OTHER, 0.0, st);
-  pack_w_kernel<<<dim3((max_total + 255) / 256, p.H), 256, 0, st>>>(jobs);
-  }
-  LAUNCH_CHECK("pack_w_kernel(mlp)");
+// ------------------------------------------------------------------ dense ELU MLPs on the tensor cores
+// out_dim == 1: the critic (SIMT value head).  out_dim >= 2: RMA's env_factor_encoder / adaptation_module
+// (RMA-rl/modules/actor_critic.py:394-418): the linear output layer is one more scan-GEMM with a plain fp32 epilogue.
+namespace {
+int mlp_plan_of(const SnnMlpDesc* d, int64_t B, MlpPlan* p) {
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, d->out_dim, B, p) != SNN_OK) return fail(SNN_EINVAL, "bad MLP descriptor");
   return SNN_OK;
 }
+int prof_layer(int l) { return 4 + (l < 3 ? l : 3); }
 
-int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, const float* x, int64_t B,
-                float* value, void* trace, size_t trace_bytes, void* stream) {
+int mlp_forward(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, const float* x, long long xs, int64_t B,
+                float* y, long long ys, void* trace, size_t trace_bytes, void* stream) {
   int sms = 0;
   int rc = device_ready(&sms);
   if (rc) return rc;
   MlpPlan p;
-  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return fail(SNN_EINVAL, "bad MLP descriptor");
-  if (!prm || !packed || !x || !value || !trace) return fail(SNN_EINVAL, "null pointer");
+  if ((rc = mlp_plan_of(d, B, &p))) return rc;
+  if (!prm || !packed || !x || !y || !trace) return fail(SNN_EINVAL, "null pointer");
   if (trace_bytes < p.trace_bytes) return fail(SNN_ENOMEM, "mlp trace too small");
-  if (p.layer[p.H - 1].NP > 256) return fail(SNN_EINVAL, "last hidden layer wider than 256 is not supported by the value head");
+  if (p.out_dim == 1 && p.layer[p.H - 1].NP > 256) return fail(SNN_EINVAL, "last hidden layer wider than 256 is not supported by the value head");
+  if (p.out_dim == 1 && ys != 1) return fail(SNN_EINVAL, "the 1-wide head writes a contiguous [B] vector");
+  if (xs < p.in_dim || ys < p.out_dim) return fail(SNN_EINVAL, "row stride smaller than the row");
   if (B == 0) return SNN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
   {
     const int total = Bp * p.K0P / 8;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    planes_from_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, Bi, Bp, p.in_dim, p.K0P, at(trace, p.tr_x), p.tr_x_plane);
+    planes_from_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(x, xs, nullptr, 0, Bi, Bp, p.in_dim, p.K0P, at(trace, p.tr_x), p.tr_x_plane);
     }
     LAUNCH_CHECK("planes_from_f32_kernel");
   }
   const uint8_t* a_img = at(trace, p.tr_x);
   size_t a_plane = p.tr_x_plane;
-  for (int l = 0; l < p.H; ++l) {
+  for (int l = 0; l < p.LT; ++l) {
     const MlpLayerPlan& lp = p.layer[l];
     ScanGemmParams q{};
     q.a_img = a_img; q.a_plane = a_plane;
@@ -605,46 +576,53 @@ int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
     q.nitems = (Bp / 128) * q.nchunks;
     q.dbg = 0;
     q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
-    q.g_img = at(trace, lp.tr_h); q.g_plane = lp.tr_h_plane;
+    if (l < p.H) {
+      q.g_img = at(trace, lp.tr_h); q.g_plane = lp.tr_h_plane;
+    } else {                      // linear output layer: fp32 rows straight into the caller's buffer
+      q.f32_out = y; q.f32_stride = ys; q.f32_cols = p.out_dim;
+    }
     const int grid = q.nitems < mlp_sms(sms) ? q.nitems : mlp_sms(sms);
-    { ProfScope prof__(CAT_FWD + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+    { ProfScope prof__(CAT_FWD + 4 * prof_layer(l), 2.0 * B * lp.K * lp.N, st);
     scan_gemm_kernel<MODE_MLP_FWD><<<grid, ScanCfg<MODE_MLP_FWD>::THREADS, scan_gemm_smem_bytes<MODE_MLP_FWD>(128), st>>>(q);
     }
     LAUNCH_CHECK("scan_gemm_kernel<MLP_FWD>");
-    a_img = at(trace, lp.tr_h); a_plane = lp.tr_h_plane;
+    if (l < p.H) { a_img = at(trace, lp.tr_h); a_plane = lp.tr_h_plane; }
   }
-  {
+  if (p.out_dim == 1) {
     const MlpLayerPlan& lp = p.layer[p.H - 1];
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    value_head_fwd_kernel<<<(Bi + 7) / 8, 256, 0, st>>>(a_img, a_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], prm->bias[p.H], value);
+    value_head_fwd_kernel<<<(Bi + 7) / 8, 256, 0, st>>>(a_img, a_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], prm->bias[p.H], y);
     }
     LAUNCH_CHECK("value_head_fwd_kernel");
   }
   return SNN_OK;
 }
 
-int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, int64_t B, const float* g_value,
-                const void* trace, const SnnMlpGrads* g, void* workspace, size_t workspace_bytes, void* stream) {
+int mlp_backward(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, int64_t B, const float* g_y, long long gs,
+                 const float* g_y2, long long g2s, const void* trace, const SnnMlpGrads* g, float* d_x, long long dxs,
+                 void* workspace, size_t workspace_bytes, void* stream) {
   int sms = 0;
   int rc = device_ready(&sms);
   if (rc) return rc;
   MlpPlan p;
-  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, B, &p) != SNN_OK) return fail(SNN_EINVAL, "bad MLP descriptor");
-  if (!prm || !packed || !g_value || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if ((rc = mlp_plan_of(d, B, &p))) return rc;
+  if (!prm || !packed || !g_y || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
   if (workspace_bytes < p.ws_bytes) return fail(SNN_ENOMEM, "mlp workspace too small");
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
+  if (p.out_dim == 1 && (gs != 1 || g_y2 != nullptr)) return fail(SNN_EINVAL, "the 1-wide head takes one contiguous [B] gradient");
+  if (gs < p.out_dim || (g_y2 && g2s < p.out_dim) || (d_x && dxs < p.in_dim)) return fail(SNN_EINVAL, "row stride smaller than the row");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
   auto dbpart_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_dbpart + static_cast<size_t>(l) * p.ws_dbpart_stride)); };
   auto partial_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_partial + static_cast<size_t>(l) * p.ws_partial_stride)); };
   float* small = reinterpret_cast<float*>(at(workspace, p.ws_small));
   Deferred df;
-  const int top = p.H - 1;
-  {   // output layer backward + dz of the last hidden layer
+  const int top = p.LT - 1;       // highest layer whose dz lives in operand planes
+  if (p.out_dim == 1) {   // output layer backward + dz of the last hidden layer
     const MlpLayerPlan& lp = p.layer[top];
     const int nblk = Bp / 64;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    value_head_bwd_kernel<<<nblk, 256, 0, st>>>(at(trace, lp.tr_h), lp.tr_h_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], g_value,
+    value_head_bwd_kernel<<<nblk, 256, 0, st>>>(at(trace, lp.tr_h), lp.tr_h_plane, Bp, Bi, lp.N, lp.NP, prm->weight[p.H], g_y,
                                                 at(workspace, p.ws_dz[0]), p.ws_dz_plane[0], small);
     }
     LAUNCH_CHECK("value_head_bwd_kernel");
@@ -652,6 +630,20 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
     df.row(small, nblk, stride, lp.N, g->weight[p.H]);
     df.row(small + lp.NP, nblk, stride, lp.N, g->bias[top]);
     df.row(small + 2 * lp.NP, nblk, stride, 1, g->bias[p.H]);
+  } else {                // dz of the linear output layer = the incoming gradient (sum of up to two sources)
+    const MlpLayerPlan& lp = p.layer[top];
+    const int total = Bp * lp.NP / 8;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    planes_from_f32_kernel<<<(total + 255) / 256, 256, 0, st>>>(g_y, gs, g_y2, g2s, Bi, Bp, p.out_dim, lp.NP,
+                                                                 at(workspace, p.ws_dz[0]), p.ws_dz_plane[0]);
+    }
+    LAUNCH_CHECK("planes_from_f32_kernel(dz)");
+    const int nblk = (Bi + 255) / 256;
+    { ProfScope prof__(CAT_OTHER, 0.0, st);
+    col_sum_kernel<<<nblk, 256, 0, st>>>(g_y, gs, g_y2, g2s, Bi, p.out_dim, small);
+    }
+    LAUNCH_CHECK("col_sum_kernel");
+    df.row(small, nblk, static_cast<size_t>(p.out_dim), p.out_dim, g->bias[top]);
   }
   for (int l = top; l >= 0; --l) {
     const MlpLayerPlan& lp = p.layer[l];
@@ -677,34 +669,103 @@ int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed
       if (splits > q.rblocks) splits = q.rblocks;
       q.splits = splits;
       q.partial = partial_of(l);
-      { ProfScope prof__(CAT_DW + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+      { ProfScope prof__(CAT_DW + 4 * prof_layer(l), 2.0 * B * lp.K * lp.N, st);
       dw_gemm_kernel<true><<<tiles * splits, 384, kDwSmemBytes, st>>>(q);
       }
       LAUNCH_CHECK("dw_gemm_kernel<dense>");
       df.part(partial_of(l), splits, q.n_tiles, lp.N, lp.K, g->weight[l]);
     }
-    if (l > 0) {   // dz_{l-1} = (dz_l . W_l) * ELU'(z_{l-1})
-      const MlpLayerPlan& lo = p.layer[l - 1];
+    if (l > 0 || d_x != nullptr) {   // dz_{l-1} = (dz_l . W_l) * ELU'(z_{l-1});  l == 0: d x = dz_0 . W_0 (no activation below)
       ScanGemmParams q{};
       q.a_img = G; q.a_plane = Gplane;
       q.b_img = at(packed, lp.wt_img); q.b_plane = lp.wt_plane; q.b_planes = 2;
       q.KP = lp.NP; q.NPout = lp.KP; q.NCmax = 128; q.T = 1;
       q.B = Bi; q.Bpad = Bp; q.R = p.Bpad;
-      q.nchunks = lp.KP / 128;
+      q.nchunks = (lp.KP + 127) / 128;
       q.nitems = (Bp / 128) * q.nchunks;
       q.dbg = 0;
-      q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
-      q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
-      q.db_part = dbpart_of(l - 1);
       const int grid = q.nitems < mlp_sms(sms) ? q.nitems : mlp_sms(sms);
-      { ProfScope prof__(CAT_DX + 4 * (4 + l), 2.0 * B * lp.K * lp.N, st);
+      if (l > 0) {
+        const MlpLayerPlan& lo = p.layer[l - 1];
+        q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
+        q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
+        q.db_part = dbpart_of(l - 1);
+        df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
+      } else {
+        q.f32_out = d_x; q.f32_stride = dxs; q.f32_cols = p.in_dim;
+      }
+      { ProfScope prof__(CAT_DX + 4 * prof_layer(l), 2.0 * B * lp.K * lp.N, st);
       scan_gemm_kernel<MODE_MLP_DX><<<grid, ScanCfg<MODE_MLP_DX>::THREADS, scan_gemm_smem_bytes<MODE_MLP_DX>(128), st>>>(q);
       }
       LAUNCH_CHECK("scan_gemm_kernel<MLP_DX>");
-      df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
     }
   }
   return launch_deferred(df, st);
+}
+}  // namespace
+
+size_t snn_mlp_packed_bytes(const SnnMlpDesc* d) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, d->out_dim, 1, &p) != SNN_OK) return 0;
+  return p.packed_bytes;
+}
+size_t snn_mlp_trace_bytes(const SnnMlpDesc* d, int64_t B) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, d->out_dim, B, &p) != SNN_OK) return 0;
+  return p.trace_bytes;
+}
+size_t snn_mlp_workspace_bytes(const SnnMlpDesc* d, int64_t B) {
+  MlpPlan p;
+  if (!d || make_mlp_plan(d->in_dim, d->num_hidden, d->hidden, d->out_dim, B, &p) != SNN_OK) return 0;
+  return p.ws_bytes;
+}
+
+int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* prm, void* packed, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  MlpPlan p;
+  if (!prm || !packed) return fail(SNN_EINVAL, "null pointer");
+  if ((rc = mlp_plan_of(d, 1, &p))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackJobs jobs{};
+  int max_total = 0;
+  for (int l = 0; l < p.LT; ++l) {
+    const MlpLayerPlan& lp = p.layer[l];
+    if (!prm->weight[l] || !prm->bias[l]) return fail(SNN_EINVAL, "null weight/bias pointer");
+    jobs.j[l] = PackJob{prm->weight[l], prm->bias[l], lp.N, lp.K, lp.NP, lp.KP, at(packed, lp.w_img), lp.w_plane,
+                        at(packed, lp.wt_img), lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad))};
+    if (lp.NP * lp.KP / 8 > max_total) max_total = lp.NP * lp.KP / 8;
+  }
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  pack_w_kernel<<<dim3((max_total + 255) / 256, p.LT), 256, 0, st>>>(jobs);
+  }
+  LAUNCH_CHECK("pack_w_kernel(mlp)");
+  return SNN_OK;
+}
+
+int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, const float* x, int64_t B,
+                float* value, void* trace, size_t trace_bytes, void* stream) {
+  if (d && d->out_dim > 1) return fail(SNN_EINVAL, "snn_mlp_fwd is the 1-wide (critic) form: use snn_mlp_fwd_ex");
+  return mlp_forward(d, prm, packed, x, d ? d->in_dim : 0, B, value, 1, trace, trace_bytes, stream);
+}
+
+int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, int64_t B, const float* g_value,
+                const void* trace, const SnnMlpGrads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  if (d && d->out_dim > 1) return fail(SNN_EINVAL, "snn_mlp_bwd is the 1-wide (critic) form: use snn_mlp_bwd_ex");
+  return mlp_backward(d, prm, packed, B, g_value, 1, nullptr, 0, trace, g, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+int snn_mlp_fwd_ex(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, const float* x, int64_t x_stride,
+                   int64_t B, float* y, int64_t y_stride, void* trace, size_t trace_bytes, void* stream) {
+  return mlp_forward(d, prm, packed, x, x_stride, B, y, y_stride, trace, trace_bytes, stream);
+}
+
+int snn_mlp_bwd_ex(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packed, int64_t B, const float* g_y,
+                   int64_t g_stride, const float* g_y2, int64_t g2_stride, const void* trace, const SnnMlpGrads* g,
+                   float* d_x, int64_t dx_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  return mlp_backward(d, prm, packed, B, g_y, g_stride, g_y2, g2_stride, trace, g, d_x, dx_stride, workspace,
+                      workspace_bytes, stream);
 }
 
 int snn_ppo_head(const float* mu, const float* log_std, const float* value, const float* actions,

@@ -7,9 +7,10 @@
 
 namespace snn {
 
-// x [B][K] fp32 -> hi/lo bf16 planes as swz64 image [KP/64][Bpad rows]; padding rows / columns are zero
-__global__ void planes_from_f32_kernel(const float* __restrict__ x, int B, int Bpad, int K, int KP,
-                                       uint8_t* __restrict__ img, size_t plane) {
+// x [B][K] fp32 (row stride xs floats; optional second addend x2: the sum of two gradient sources) -> hi/lo bf16 planes
+// as swz64 image [KP/64][Bpad rows]; padding rows / columns are zero
+__global__ void planes_from_f32_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ x2, long long x2s,
+                                       int B, int Bpad, int K, int KP, uint8_t* __restrict__ img, size_t plane) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int kp8 = KP / 8;
   if (idx >= Bpad * kp8) return;
@@ -18,7 +19,8 @@ __global__ void planes_from_f32_kernel(const float* __restrict__ x, int B, int B
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    const float v = (r < B && c < K) ? x[static_cast<size_t>(r) * K + c] : 0.f;
+    float v = (r < B && c < K) ? x[static_cast<size_t>(r) * xs + c] : 0.f;
+    if (x2 != nullptr && r < B && c < K) v += x2[static_cast<size_t>(r) * x2s + c];
     h[j] = bf16_round(v);
     l[j] = v - h[j];
   }
@@ -27,6 +29,30 @@ __global__ void planes_from_f32_kernel(const float* __restrict__ x, int B, int B
       make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
   *reinterpret_cast<uint4*>(img + plane + off) =
       make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+}
+
+// part[blk][c] = sum over the block's 256 rows of (x + x2)[r, c]   (bias gradient of a linear output layer), c < K <= 128
+__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ x2,
+                                                     long long x2s, int B, int K, float* __restrict__ part) {
+  __shared__ float sh[8][128];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  for (int c = cl; c < K; c += 32) {
+    float acc = 0.f;
+    for (int i = rl; i < 256; i += 8) {
+      const int r = blockIdx.x * 256 + i;
+      if (r < B) {
+        acc += x[static_cast<size_t>(r) * xs + c];
+        if (x2 != nullptr) acc += x2[static_cast<size_t>(r) * x2s + c];
+      }
+    }
+    sh[rl][c] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += 256) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][c];
+    part[static_cast<size_t>(blockIdx.x) * K + c] = t;
+  }
 }
 
 __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float (&x)[8]) {

@@ -55,9 +55,9 @@ struct NmParams {
   // FWD epilogue
   const float* bias;        // [MP]
   uint32_t* out_bits;       // [MP/32][Rt]
-  float* v_out;             // [MP/32][Rt][32] or null (inference)
+  float* v_out;             // [MP/32][Rt/4][32 neurons][4 sample-steps] or null (inference)
   // DX epilogue
-  const float* v_in;        // [MP/32][Rt][32] voltages of the layer whose gradient is produced
+  const float* v_in;        // [MP/32][Rt/4][32][4] voltages of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
   float* db_part;           // [3 * gridDim.x / nmt][MP]   (one row per CTA and epilogue group)
@@ -394,16 +394,19 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         uint32_t xo[8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
-        const float* const vcol = p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32 + lane;
+        const float4* const vcol = reinterpret_cast<const float4*>(p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32) + lane;
         float gvn[16], gcn[16];
         // step s <-> (group index bi, timestep t): s = bi * T + (T - 1 - t); tracked incrementally (no divisions)
         int l_bi = 0, l_t = p.T - 1;          // cursor of the loads
         int s_bi = 0, s_t = p.T - 1;          // cursor of the recurrence
         auto loadv = [&](float (&buf)[16]) {
           if (l_bi < nb && !(SNN_DBG_MASK(p) & 32)) {
-            const float* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 32;
+            const float4* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 8;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) buf[j] = __ldg(src + j * 32);
+            for (int j = 0; j < 4; ++j) {
+              const float4 q4 = __ldg(src + j * 32);
+              buf[4 * j] = q4.x; buf[4 * j + 1] = q4.y; buf[4 * j + 2] = q4.z; buf[4 * j + 3] = q4.w;
+            }
           }
           if (--l_t < 0) { l_t = p.T - 1; ++l_bi; }
         };
@@ -464,13 +467,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           float cur[16], vol[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
-          uint32_t sprev = 0;
+          uint32_t sprev = 0, spend = 0;
           uint32_t x[16], xn[16];
           tmem_ld16(t_set + static_cast<uint32_t>(col0), x);
           tmem_ld_wait();
           for (int t = 0; t < p.T; ++t) {
             if (t + 1 < p.T) tmem_ld16(t_set + static_cast<uint32_t>((t + 1) * p.Bt + col0), xn);
-            uint32_t scur = 0, myword = 0;
+            uint32_t scur = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float syn = __fadd_rn(__uint_as_float(x[j]), bias);
@@ -478,19 +481,28 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
               const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
               cur[j] = cj;
               vol[j] = vj;
-              const bool s = vj > 0.5f;
-              scur |= (s ? 1u : 0u) << j;
-              const uint32_t w = __ballot_sync(0xffffffffu, s);      // the 32 neurons of this warp at sample-step (t, j)
-              if (lane == j) myword = w;
+              scur |= (vj > 0.5f ? 1u : 0u) << j;
             }
             const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
-            if (lane < 16 && !(SNN_DBG_MASK(p) & 256))
-              p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c + lane] = ((vmask >> lane) & 1u) ? myword : 0u;
+            // spike words (bit = neuron of this warp, one word per sample-step): the thread holds a 16-bit mask over its
+            // samples, the words are the transpose.  Two timesteps share one 32 x 32 warp transpose: lane L ends up with
+            // the word of sample L % 16 at step t - 1 (L < 16) or t (L >= 16) — 5 shuffles instead of 32 ballots.
+            if ((t & 1) == 0 && t + 1 < p.T) {
+              spend = scur;
+            } else {
+              const bool pair = (t & 1) != 0;
+              const uint32_t wd = warp_transpose32(pair ? (spend | (scur << 16)) : scur, lane);
+              const int tt = pair ? t - 1 + (lane >> 4) : t;
+              if ((pair || lane < 16) && !(SNN_DBG_MASK(p) & 256))
+                p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c_tile + static_cast<size_t>(tt * p.Bt + col0 + (lane & 15))] =
+                    ((vmask >> (lane & 15)) & 1u) ? wd : 0u;
+            }
             if (p.v_out != nullptr && !(SNN_DBG_MASK(p) & 128)) {
-              // [neuron / 32][sample-step][32]: this warp's 16 sample-steps are 16 consecutive 128-byte rows
-              float* dst = p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32 + lane;
+              // [neuron / 32][sample-step / 4][32 neurons][4 sample-steps]: the thread's 16 sample-steps are four 16-byte
+              // pieces, the warp's 16 x 32 values one contiguous 2 KiB block (4 STG.128 instead of 16 STG.32)
+              float4* dst = reinterpret_cast<float4*>(p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32) + lane;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dst[j * 32] = vol[j];
+              for (int j = 0; j < 4; ++j) dst[j * 32] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
             }
             sprev = scur;
             tmem_ld_wait();

@@ -16,8 +16,8 @@
 //   * g_c (time-stepped bf16 hi/lo planes): swz64 image with rows = sample-steps r, columns = neurons — the K-major
 //     B operand of dX and the MN-major A operand of dW; the epilogue threads (= neurons) of a warp store 64
 //     contiguous bytes of one row.
-//   * voltages: fp32 [NP/32][Rt][32]: a warp (32 consecutive neurons) reads / writes the sample-steps of a
-//     16-sample group as 16 consecutive 128-byte rows.
+//   * voltages: fp32 [NP/32][Rt/4][32 neurons][4 sample-steps]: an epilogue thread (= neuron) reads / writes the 16
+//     sample-steps of a group as four 16-byte pieces, its warp (32 consecutive neurons) one contiguous 2 KiB block.
 //   * the dense critic keeps plain rows r = b, Bpad = roundup(B, 128).
 #pragma once
 #include <cstddef>
@@ -49,7 +49,7 @@ struct LayerPlan {
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
   size_t tr_bits;    // trace: output spike words [NP/32][Rt]
-  size_t tr_volt;    // trace: fp32 voltages [NP/32][Rt][32]
+  size_t tr_volt;    // trace: fp32 voltages [NP/32][Rt/4][32][4]
 };
 
 struct SnnPlan {
@@ -179,7 +179,9 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   return SNN_OK;
 }
 
-// ------------------------------------------------------------------ dense ELU MLP with one output (the critic)
+// ------------------------------------------------------------------ dense ELU MLP: the critic (one output, SIMT value
+// head) and the RMA fork's env_factor_encoder / adaptation_module (out_dim outputs: the linear output layer runs on the
+// tensor cores like a hidden layer, as plan entry layer[H])
 struct MlpLayerPlan {
   int K, N, KP, NP;
   size_t w_img, w_plane;     // 3 planes (hi, mid, lo) of W [NP rows][KP cols]; the MLP kernels use hi + mid
@@ -190,10 +192,12 @@ struct MlpLayerPlan {
 };
 
 struct MlpPlan {
-  int H;                     // hidden (ELU) layers; the output layer [1 x hidden[H-1]] is handled by SIMT kernels
+  int H;                     // hidden (ELU) layers; out_dim == 1: the output layer [1 x hidden[H-1]] is handled by SIMT kernels
+  int out_dim;               // >= 2: layer[H] is the linear output layer [out_dim x hidden[H-1]]
+  int LT;                    // layers on the tensor cores: H (+ 1 when out_dim >= 2)
   int in_dim, K0P;
   int64_t B, Bpad;
-  MlpLayerPlan layer[SNN_MAX_LAYERS];
+  MlpLayerPlan layer[SNN_MAX_LAYERS + 1];
   size_t packed_bytes;
   size_t tr_x, tr_x_plane;   // trace: 2 planes of the input [K0P/64][Bpad rows]
   size_t trace_bytes;
@@ -202,10 +206,14 @@ struct MlpPlan {
   size_t ws_bytes;
 };
 
-inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int64_t B, MlpPlan* out) {
+inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int out_dim, int64_t B, MlpPlan* out) {
   MlpPlan p{};
   if (in_dim <= 0 || num_hidden < 1 || num_hidden > SNN_MAX_LAYERS || B < 0) return SNN_EINVAL;
+  if (out_dim <= 0) out_dim = 1;
+  if (out_dim > 128) return SNN_EINVAL;
   p.H = num_hidden;
+  p.out_dim = out_dim;
+  p.LT = num_hidden + (out_dim >= 2 ? 1 : 0);
   p.in_dim = in_dim;
   p.K0P = static_cast<int>(round_up(in_dim, 64));
   p.B = B;
@@ -213,10 +221,11 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int6
   size_t off = 0;
   auto take = [&off](size_t bytes) { size_t o = off; off += round_up(static_cast<int64_t>(bytes), 1024); return o; };
   int k = in_dim, kp = p.K0P;
-  for (int l = 0; l < p.H; ++l) {
+  for (int l = 0; l < p.LT; ++l) {
     MlpLayerPlan& lp = p.layer[l];
-    if (hidden[l] <= 0 || hidden[l] > 2048) return SNN_EINVAL;
-    lp.K = k; lp.KP = kp; lp.N = hidden[l]; lp.NP = static_cast<int>(round_up(hidden[l], 128));
+    const int n = l < p.H ? hidden[l] : out_dim;
+    if (n <= 0 || n > 2048) return SNN_EINVAL;
+    lp.K = k; lp.KP = kp; lp.N = n; lp.NP = static_cast<int>(round_up(n, 128));
     lp.w_plane = static_cast<size_t>(lp.KP / 64) * lp.NP * 128;
     lp.wt_plane = static_cast<size_t>(lp.NP / 64) * lp.KP * 128;
     lp.w_img = take(3 * lp.w_plane);
@@ -231,10 +240,10 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int6
   p.tr_x = take(2 * p.tr_x_plane);
   size_t dzmax = 0;
   int npmax = p.K0P;
-  for (int l = 0; l < p.H; ++l) {
+  for (int l = 0; l < p.LT; ++l) {
     MlpLayerPlan& lp = p.layer[l];
     lp.tr_h_plane = static_cast<size_t>(lp.NP / 64) * p.Bpad * 128;
-    lp.tr_h = take(2 * lp.tr_h_plane);
+    if (l < p.H) lp.tr_h = take(2 * lp.tr_h_plane);       // the linear output is not an operand of anything: not kept
     if (lp.tr_h_plane > dzmax) dzmax = lp.tr_h_plane;
     if (lp.NP > npmax) npmax = lp.NP;
   }
@@ -242,15 +251,15 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int6
   off = 0;
   for (int s = 0; s < 2; ++s) { p.ws_dz_plane[s] = dzmax; p.ws_dz[s] = take(2 * dzmax); }
   size_t part = 0;
-  for (int l = 0; l < p.H; ++l) {
+  for (int l = 0; l < p.LT; ++l) {
     const size_t tiles = static_cast<size_t>(p.layer[l].NP / 128) * ((p.layer[l].KP + 255) / 256);
     const size_t ctas = tiles > 296 ? tiles : 296;
     if (ctas * 128 * 256 * 4 > part) part = ctas * 128 * 256 * 4;
   }
   p.ws_partial_stride = static_cast<size_t>(round_up(static_cast<int64_t>(part), 1024));
-  p.ws_partial = take(p.ws_partial_stride * p.H);
+  p.ws_partial = take(p.ws_partial_stride * p.LT);
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(296) * npmax * 4, 1024));
-  p.ws_dbpart = take(p.ws_dbpart_stride * p.H);
+  p.ws_dbpart = take(p.ws_dbpart_stride * p.LT);
   p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (2 * npmax + 8) * 4 + 1024);
   p.ws_bytes = off;
   *out = p;

@@ -45,6 +45,12 @@ struct ScanGemmParams {
   // MLP_FWD: writes ELU(acc + bias) as hi/lo planes into g_img.  MLP_DX: reads the layer's ELU output planes
   const uint8_t* h_img;     // 2 planes of swz64 image [NPout/64][R rows]
   size_t h_plane;
+  // Linear ends of a general MLP (RMA env_factor_encoder / adaptation_module; the critic's input gradient): when f32_out
+  // is set the epilogue writes plain fp32 rows instead of operand planes and applies no activation —
+  //   MLP_FWD: y[b, col] = acc + bias (the linear output layer);  MLP_DX: d_x[b, col] = acc (gradient into the input).
+  float* f32_out;           // [B rows][f32_stride floats], columns < f32_cols are written
+  long long f32_stride;
+  int f32_cols;
 };
 
 template <int MODE> struct ScanCfg;
@@ -252,6 +258,15 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           tmem_ld16(t_col, x);
           tmem_ld_wait();
           float h[16];
+          if (p.f32_out != nullptr) {
+            if (valid) {
+              float* dst = p.f32_out + static_cast<size_t>(b) * p.f32_stride;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.f32_cols) dst[col0 + j] = __uint_as_float(x[j]) + s_col[col0 + j];
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float z = __uint_as_float(x[j]) + s_col[col0 + j];
@@ -259,6 +274,18 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           }
           store_planes16(p.g_img, p.g_plane, p.R, static_cast<size_t>(b), col0, h);
         } else {
+          if (p.f32_out != nullptr) {
+            uint32_t x[16];
+            tmem_ld16(t_col, x);
+            tmem_ld_wait();
+            if (valid) {
+              float* dst = p.f32_out + static_cast<size_t>(b) * p.f32_stride;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.f32_cols) dst[col0 + j] = __uint_as_float(x[j]);
+            }
+            continue;
+          }
           // dz = (dz_above . W) * ELU'(z), ELU'(z) = 1 for z > 0 else exp(z) = h + 1
           uint32_t x[16];
           tmem_ld16(t_col, x);
@@ -289,7 +316,7 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 #endif
   tc_fence_before_sync();
   __syncthreads();
-  if (MODE == MODE_MLP_DX) {
+  if (MODE == MODE_MLP_DX && p.db_part != nullptr) {
     for (int i = tid; i < p.NPout; i += blockDim.x) p.db_part[static_cast<size_t>(blockIdx.x) * p.NPout + i] = s_col[i];
   }
   if (warp == 1) {

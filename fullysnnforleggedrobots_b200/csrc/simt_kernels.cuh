@@ -291,8 +291,9 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     gup1 = __fdiv_rn(G1 * dec_w[n0 + 1], Tf);
   }
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
-  const float2* vsrc = reinterpret_cast<const float2*>(volt + (static_cast<size_t>(n0 >> 5) * tg.Rt + r0) * 32 + (n0 & 31));
-  const size_t vstep = static_cast<size_t>(tg.Bt) * 16;        // float2 units between timesteps
+  // voltage trace [NP/32][Rt/4][32 neurons][4 sample-steps]; Bt % 16 == 0, so every timestep's row has r0's phase r0 % 4
+  const float* vsrc = volt + ((static_cast<size_t>(n0 >> 5) * tg.Rt + (r0 & ~static_cast<size_t>(3))) * 32) + (n0 & 31) * 4 + (r0 & 3);
+  const size_t vstep = static_cast<size_t>(tg.Bt) * 32;        // floats between timesteps
   const uint32_t piece = static_cast<uint32_t>(lane >> 2);
   // Bt % 16 == 0: every timestep's row r0 + t * Bt has the swizzle phase of r0, so the in-row offset is a constant
   uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4 +
@@ -319,14 +320,15 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   if (TT > 0) {
     float2 v[TT > 0 ? TT : 1];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) v[t] = __ldg(vsrc + static_cast<size_t>(t) * vstep);      // all loads up front
+    for (int t = 0; t < TT; ++t)                                                           // all loads up front
+      v[t] = make_float2(__ldg(vsrc + static_cast<size_t>(t) * vstep), __ldg(vsrc + static_cast<size_t>(t) * vstep + 4));
 #pragma unroll
     for (int t = TT - 1; t >= 0; --t) step(t, v[t]);
   } else {
-    float2 vn = __ldg(vsrc + static_cast<size_t>(T - 1) * vstep);
+    float2 vn = make_float2(__ldg(vsrc + static_cast<size_t>(T - 1) * vstep), __ldg(vsrc + static_cast<size_t>(T - 1) * vstep + 4));
     for (int t = T - 1; t >= 0; --t) {
       const float2 v = vn;
-      if (t > 0) vn = __ldg(vsrc + static_cast<size_t>(t - 1) * vstep);
+      if (t > 0) vn = make_float2(__ldg(vsrc + static_cast<size_t>(t - 1) * vstep), __ldg(vsrc + static_cast<size_t>(t - 1) * vstep + 4));
       step(t, v);
     }
   }

@@ -186,6 +186,17 @@ __device__ __forceinline__ uint4 expand_spike_byte(uint32_t b) {
   v.w = ((((b >> 6) & 3u) * 0x8001u) & 0x10001u) * 0x3F80u;
   return v;
 }
+// 32 x 32 bit-matrix transpose across a warp: lane i passes row i (bit b = element (i, b)); lane b receives column b
+// (bit i = element (i, b)).  Five block-swap stages (shuffle + two masked merges) instead of 32 ballots.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y & ~m) >> s)) : ((x & m) | ((y & m) << s));
+  }
+  return x;
+}
 __device__ __forceinline__ float bf16_round(float x) {   // value of bf16(x) as fp32
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));

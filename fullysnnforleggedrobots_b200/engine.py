@@ -213,9 +213,9 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace layout: [NP / 32][Rt sample-steps][32]
-            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt, 32)
-            v = v[:, col]                                                             # [NP / 32, T, rows, 32]
+            # voltage trace layout: [NP / 32][Rt / 4][32 neurons][4 sample-steps]
+            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt // 4, 32, 4)
+            v = v.permute(0, 1, 3, 2).reshape(NP // 32, Rt, 32)[:, col]               # [NP / 32, T, rows, 32]
             res["volt"].append(v.permute(1, 2, 0, 3).reshape(T, -1, NP)[:, :, :self.dims[l + 1]].contiguous())
         return res
 

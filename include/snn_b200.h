@@ -125,6 +125,8 @@ typedef struct SnnMlpDesc {
   int32_t in_dim;
   int32_t num_hidden;
   int32_t hidden[SNN_MAX_LAYERS];
+  int32_t out_dim;                    /* 0 or 1: the critic (1-wide SIMT head); 2..128: linear output layer [out_dim, N] on
+                                         the tensor cores (RMA env_factor_encoder / adaptation_module) */
 } SnnMlpDesc;
 typedef struct SnnMlpParams {
   const float* weight[SNN_MAX_LAYERS + 1];
@@ -144,6 +146,18 @@ int snn_mlp_fwd(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, 
 /* gradients of sum_b g_value[b] * value[b] w.r.t. every weight / bias (overwritten) */
 int snn_mlp_bwd(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, int64_t B, const float* g_value,
                 const void* trace, const SnnMlpGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+/* General form (RMA fork, RMA/.../rsl_rl/modules/actor_critic.py:394-418, 549-553, 633-634: the actor and the critic
+ * read cat(obs, latent), latent = env_factor_encoder(privileged_obs), so both need a gradient into their input and
+ * the encoder receives the SUM of the two):
+ *   fwd_ex:  y [B, out_dim] (row stride y_stride floats: lands inside a wider cat buffer) = mlp(x [B, in_dim], row
+ *            stride x_stride);
+ *   bwd_ex:  gradients of sum_b <g_y[b] + g_y2[b], y[b]> (g_y2 nullable; strided rows) w.r.t. every weight / bias, and,
+ *            when d_x is not null, w.r.t. the input rows (d_x [B, in_dim], row stride dx_stride, overwritten). */
+int snn_mlp_fwd_ex(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, const float* x, int64_t x_stride,
+                   int64_t B, float* y, int64_t y_stride, void* trace, size_t trace_bytes, void* stream);
+int snn_mlp_bwd_ex(const SnnMlpDesc* d, const SnnMlpParams* p, const void* packed, int64_t B, const float* g_y,
+                   int64_t g_stride, const float* g_y2, int64_t g2_stride, const void* trace, const SnnMlpGrads* g,
+                   float* d_x, int64_t dx_stride, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Fused PPO head (AMP/.../algorithms/ppo.py:132-171 with modules/actor_critic.py:398-421): Normal log-prob,
  * entropy, KL to the rollout policy, clipped surrogate and clipped value loss, forward AND closed-form
