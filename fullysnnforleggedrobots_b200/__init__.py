@@ -9,12 +9,12 @@ from . import _lib  # noqa: F401
 from .actor import PopSpikeActor  # noqa: F401
 from .actor_critic import (ActorCritic, ActorCriticAMP, ActorCriticCassie, ActorCriticHumanoid,  # noqa: F401
                            ActorCriticRMA, VARIANTS)
-from .engine import CriticEngine, SnnEngine, gae  # noqa: F401
+from .engine import CriticEngine, MlpEngine, SnnEngine, gae  # noqa: F401
 from .ppo import PPO, PPORMA  # noqa: F401
 from .amp import AMPPPO, AMPDiscriminator, Normalizer, ReplayBuffer  # noqa: F401
 from .storage import RolloutStorage, RolloutStorageRMA  # noqa: F401
 from .export import export_policy, load_checkpoint, load_policy, save_checkpoint  # noqa: F401
 
-__all__ = ["PopSpikeActor", "SnnEngine", "CriticEngine", "gae", "ActorCritic", "ActorCriticAMP", "ActorCriticCassie",
+__all__ = ["PopSpikeActor", "SnnEngine", "CriticEngine", "MlpEngine", "gae", "ActorCritic", "ActorCriticAMP", "ActorCriticCassie",
            "ActorCriticHumanoid", "ActorCriticRMA", "VARIANTS", "PPO", "PPORMA", "AMPPPO", "AMPDiscriminator", "ReplayBuffer", "Normalizer", "RolloutStorage", "RolloutStorageRMA",
            "export_policy", "load_policy", "save_checkpoint", "load_checkpoint"]

@@ -131,6 +131,7 @@ _SIGS = {
     "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2 + [C.c_float] * 4
                       + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snn_mse_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "snn_launch_count": (C.c_int64, []),

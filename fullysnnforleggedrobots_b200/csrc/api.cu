@@ -611,6 +611,7 @@ int mlp_backward(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packe
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
   if (p.out_dim == 1 && (gs != 1 || g_y2 != nullptr)) return fail(SNN_EINVAL, "the 1-wide head takes one contiguous [B] gradient");
   if (gs < p.out_dim || (g_y2 && g2s < p.out_dim) || (d_x && dxs < p.in_dim)) return fail(SNN_EINVAL, "row stride smaller than the row");
+  if (d_x && p.K0P > kScanMaxNP) return fail(SNN_EINVAL, "gradient into the input is limited to 2048 input features");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B), Bp = static_cast<int>(p.Bpad);
   auto dbpart_of = [&](int l) { return reinterpret_cast<float*>(at(workspace, p.ws_dbpart + static_cast<size_t>(l) * p.ws_dbpart_stride)); };
@@ -839,6 +840,25 @@ int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t
                                        max_norm, grad_scale, norm_out);
   }
   LAUNCH_CHECK("clip_adam_kernel");
+  return SNN_OK;
+}
+
+int snn_mse_grad(const float* pred, const float* target, int64_t n, float* g, float* loss_accum, void* scratch,
+                 void* stream) {
+  if (!pred || !target || !g || !loss_accum || !scratch) return fail(SNN_EINVAL, "null pointer");
+  if (n <= 0) return fail(SNN_EINVAL, "empty tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nb = static_cast<int>((n + 1023) / 1024);
+  if (nb > 256) nb = 256;
+  float* partial = static_cast<float*>(scratch);     // >= 256 floats
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  mse_grad_kernel<<<nb, 256, 0, st>>>(pred, target, n, 2.0f / static_cast<float>(n), g, partial);
+  }
+  LAUNCH_CHECK("mse_grad_kernel");
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  mse_finalize_kernel<<<1, 32, 0, st>>>(partial, nb, 1.0 / static_cast<double>(n), loss_accum);
+  }
+  LAUNCH_CHECK("mse_finalize_kernel");
   return SNN_OK;
 }
 

@@ -233,7 +233,7 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int 
     lp.bias_pad = take(static_cast<size_t>(lp.NP) * 4);
     k = lp.N; kp = lp.NP;
   }
-  if (p.K0P > 2048) return SNN_EINVAL;
+  if (p.K0P > 16384) return SNN_EINVAL;        // contraction length only (RMA's observation history: 40 x 320 inputs)
   p.packed_bytes = off;
   off = 0;
   p.tr_x_plane = static_cast<size_t>(p.K0P / 64) * p.Bpad * 128;

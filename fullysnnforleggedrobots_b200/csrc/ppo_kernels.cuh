@@ -251,6 +251,30 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
   }
 }
 
+// ------------------------------------------------------------------ adaptation-module regression (RMA fork)
+// F.mse_loss(pred, target) and its gradient (RMA/.../rsl_rl/algorithms/ppo.py:200-213): loss = mean over all n = B*D
+// elements of (pred - target)^2; g = 2 (pred - target) / n.  Block partial sums in a fixed order (bit-reproducible).
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                      int64_t n, float scale, float* __restrict__ g,
+                                                      float* __restrict__ partial) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float d = pred[i] - target[i];
+    acc += d * d;
+    g[i] = d * scale;
+  }
+  const float t = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void mse_finalize_kernel(const float* __restrict__ partial, int nparts, double inv_n, float* __restrict__ loss_accum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += partial[i];
+    loss_accum[0] += static_cast<float>(t * inv_n);
+  }
+}
+
 // ------------------------------------------------------------------ rollout step: sample + log-prob in one pass
 // ActorCritic.act / get_actions_log_prob / action_std (actor_critic.py:398-421) on the actor's (mu, log_std):
 //   sigma = exp(log_std) ; action = mu + sigma * noise ; log_prob = sum_a Normal(mu, sigma).log_prob(action)

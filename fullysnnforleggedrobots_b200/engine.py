@@ -238,35 +238,57 @@ def gae(rewards, dones, values, last_values, gamma: float, lam: float, normalize
     return returns, adv
 
 
-class CriticEngine:
-    """Dense ELU critic (Linear -> ELU -> ... -> Linear(., 1)) on the tensor-core kernels (snn_mlp_*).
+def _check_rows_f32_cuda(t: torch.Tensor, name: str):
+    """2-D (or 1-D) float32 CUDA rows whose elements are contiguous within a row; the row stride is free (a column slice of
+    a wider buffer, e.g. the latent part of cat(obs, latent))."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: no CPU fallback")
+    if t.dtype != torch.float32 or t.dim() not in (1, 2) or (t.dim() == 2 and t.shape[1] > 1 and t.stride(1) != 1):
+        raise RuntimeError(f"{name} must be float32 rows with unit element stride")
 
-    `linears` is the list of nn.Linear modules of the reference's `critic` nn.Sequential
-    (AMP/.../modules/actor_critic.py:359-368).  Used by the fused PPO update and by the critic branch of the
-    graphed rollout step (PPO._act_fused); a direct `ActorCritic.evaluate` call keeps the torch path."""
+
+def _row_stride(t: torch.Tensor) -> int:
+    if t.dim() == 1:
+        return 1
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
+class MlpEngine:
+    """Dense ELU MLP (Linear -> ELU -> ... -> Linear(., out_dim)) on the tensor-core kernels (snn_mlp_*).
+
+    out_dim == 1: the reference's critic (AMP/.../modules/actor_critic.py:359-368), 1-wide SIMT head.
+    out_dim >= 2: the RMA fork's env_factor_encoder / adaptation_module (RMA/.../modules/actor_critic.py:394-418):
+    the linear output layer is one more tensor-core GEMM.  Rows may be strided (a column slice of a wider buffer),
+    `backward` can sum two gradient sources and return the gradient into the input rows.
+
+    `linears` is the list of nn.Linear modules of an nn.Sequential of that form."""
 
     def __init__(self, linears):
-        if len(linears) < 2 or linears[-1].out_features != 1:
-            raise ValueError("critic must end in Linear(., 1) and have at least one hidden layer")
+        if len(linears) < 2:
+            raise ValueError("MLP needs at least one hidden layer")
         if len(linears) - 1 > _lib.SNN_MAX_LAYERS:
-            raise ValueError("too many critic layers")
+            raise ValueError("too many MLP layers")
         d = _lib.SnnMlpDesc()
         d.in_dim = linears[0].in_features
         d.num_hidden = len(linears) - 1
         for i, l in enumerate(linears[:-1]):
             d.hidden[i] = l.out_features
-        if linears[-2].out_features > 256:
+        d.out_dim = linears[-1].out_features
+        if d.out_dim == 1 and linears[-2].out_features > 256:
             raise ValueError("last hidden layer wider than 256 is not supported by the value-head kernels")
+        if d.out_dim > 128:
+            raise ValueError("output layers wider than 128 are not supported")
         self.desc = d
+        self.out_dim = int(d.out_dim)
         self.linears = list(linears)
         self._packed = None
         self._ws = None
         if _lib.lib().snn_mlp_packed_bytes(C.byref(d)) == 0:
-            raise ValueError("unsupported critic dimensions")
+            raise ValueError("unsupported MLP dimensions")
 
-    @staticmethod
-    def from_sequential(seq):
-        """Return a CriticEngine if `seq` is Linear/ELU/.../Linear(., 1), else None."""
+    @classmethod
+    def from_sequential(cls, seq):
+        """Return an engine if `seq` is Linear/ELU/.../Linear (and, for CriticEngine, ends in Linear(., 1)), else None."""
         mods = list(seq)
         lin = [m for m in mods if isinstance(m, torch.nn.Linear)]
         act = [m for m in mods if not isinstance(m, torch.nn.Linear)]
@@ -275,7 +297,7 @@ class CriticEngine:
         if not ok:
             return None
         try:
-            return CriticEngine(lin)
+            return cls(lin)
         except ValueError:
             return None
 
@@ -299,7 +321,8 @@ class CriticEngine:
             _lib.check(L.snn_mlp_pack(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _stream_ptr(dev)), "snn_mlp_pack")
 
     def forward(self, x, out_value=None, out_trace=None):
-        _check_f32_cuda(x, "critic_obs")
+        """y = mlp(x).  out_value: [B] (out_dim 1) or a [B, out_dim] view with unit element stride (any row stride)."""
+        _check_rows_f32_cuda(x, "mlp input")
         dev = x.device
         B = x.shape[0]
         L = _lib.lib()
@@ -307,21 +330,30 @@ class CriticEngine:
             self.repack()
         nbytes = L.snn_mlp_trace_bytes(C.byref(self.desc), B)
         trace = out_trace if out_trace is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        value = out_value if out_value is not None else torch.empty(B, dtype=torch.float32, device=dev)
+        if out_value is None:
+            out_value = torch.empty((B,) if self.out_dim == 1 else (B, self.out_dim), dtype=torch.float32, device=dev)
+        _check_rows_f32_cuda(out_value, "mlp output")
         ps = self._params()
         with torch.cuda.device(dev):
-            _lib.check(L.snn_mlp_fwd(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _ptr(x), B, _ptr(value),
-                                     _ptr(trace), trace.numel(), _stream_ptr(dev)), "snn_mlp_fwd")
-        return value, trace
+            _lib.check(L.snn_mlp_fwd_ex(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _ptr(x), _row_stride(x), B,
+                                        _ptr(out_value), _row_stride(out_value), _ptr(trace), trace.numel(),
+                                        _stream_ptr(dev)), "snn_mlp_fwd_ex")
+        return out_value, trace
 
     def workspace_bytes(self, B):
         return int(_lib.lib().snn_mlp_workspace_bytes(C.byref(self.desc), B))
 
-    def backward(self, g_value, trace, B, out=None, ws=None):
-        """Gradients of sum_b g_value[b] * value[b]; `out` = (list of weight grads, list of bias grads) to overwrite.
+    def backward(self, g_value, trace, B, out=None, ws=None, g2=None, d_x=None):
+        """Gradients of sum_b <g_value[b] (+ g2[b]), y[b]>; `out` = (list of weight grads, list of bias grads) to overwrite.
+        d_x: optional [B, in_dim] rows (any row stride) receiving the gradient into the input.
         ws: caller-owned workspace (a CUDA graph capturing this call passes its own)."""
         dev = g_value.device
         L = _lib.lib()
+        _check_rows_f32_cuda(g_value, "mlp output gradient")
+        if g2 is not None:
+            _check_rows_f32_cuda(g2, "mlp output gradient (second source)")
+        if d_x is not None:
+            _check_rows_f32_cuda(d_x, "mlp input gradient")
         if out is None:
             out = ([torch.empty_like(l.weight) for l in self.linears], [torch.empty_like(l.bias) for l in self.linears])
         g = _lib.SnnMlpGrads()
@@ -334,9 +366,21 @@ class CriticEngine:
                 self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             ws = self._ws
         elif ws.numel() < nbytes:
-            raise RuntimeError("critic workspace too small")
+            raise RuntimeError("mlp workspace too small")
         ps = self._params()
         with torch.cuda.device(dev):
-            _lib.check(L.snn_mlp_bwd(C.byref(self.desc), C.byref(ps), _ptr(self._packed), B, _ptr(g_value), _ptr(trace),
-                                     C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_mlp_bwd")
+            _lib.check(L.snn_mlp_bwd_ex(C.byref(self.desc), C.byref(ps), _ptr(self._packed), B, _ptr(g_value),
+                                        _row_stride(g_value), _ptr(g2), 0 if g2 is None else _row_stride(g2), _ptr(trace),
+                                        C.byref(g), _ptr(d_x), 0 if d_x is None else _row_stride(d_x), _ptr(ws), ws.numel(),
+                                        _stream_ptr(dev)), "snn_mlp_bwd_ex")
         return out
+
+
+class CriticEngine(MlpEngine):
+    """The dense critic: an MlpEngine that must end in Linear(., 1).  Used by the fused PPO update and by the critic
+    branch of the graphed rollout step (PPO._act_fused); a direct `ActorCritic.evaluate` call keeps the torch path."""
+
+    def __init__(self, linears):
+        if len(linears) < 2 or linears[-1].out_features != 1:
+            raise ValueError("critic must end in Linear(., 1) and have at least one hidden layer")
+        super().__init__(linears)

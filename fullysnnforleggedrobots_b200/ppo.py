@@ -625,15 +625,182 @@ class PPORMA(PPO):
     """RMA fork's PPO (RMA/quadruped-robot-master/rl-robotics/rsl_rl/rsl_rl/algorithms/ppo.py:41-221): the policy acts
     on (obs, privileged_obs), and every minibatch step is followed by `num_adaptation_module_substeps` regression
     steps of the adaptation module onto the (detached) privileged-encoder latent with a second Adam (:200-213).
-    The actor's input needs a gradient (it contains the latent), so this class uses the autograd path: the spiking
-    actor still runs on the sm_100a kernels, snn_bwd additionally returns d loss / d actor-input."""
+
+    Fused path (default): one CUDA graph per minibatch index holding
+        env_factor_encoder forward (tensor-core MLP kernels, snn_mlp_fwd_ex) straight into the latent columns of the
+        cat(obs, latent) buffer -> spiking actor forward + dense critic forward on it -> snn_ppo_head -> actor BPTT with
+        d loss / d actor-input (snn_bwd) and critic backward with d loss / d critic-input (snn_mlp_bwd_ex) -> encoder
+        backward on the SUM of the two latent gradients -> all-reduce / adaptive lr / clip + Adam -> the adaptation
+        substeps (adaptation_module forward, encoder target forward, snn_mse_grad, backward, second Adam over the
+        adaptation module's slice of the flat parameter buffer through snn_clip_adam).
+    `fused=False` keeps the autograd path (torch MLPs) on the same spiking kernels."""
 
     def __init__(self, actor_critic, num_adaptation_module_substeps=1, **kwargs):
-        kwargs["fused"] = False
         super().__init__(actor_critic, **kwargs)
         self.num_adaptation_module_substeps = num_adaptation_module_substeps
+        self._adaptation_lr = float(kwargs.get("learning_rate", 1e-3))
         self.adaptation_optimizer = torch.optim.Adam(self.actor_critic.adaptation_module.parameters(),
-                                                     lr=kwargs.get("learning_rate", 1e-3))
+                                                     lr=self._adaptation_lr)
+        self._ad = None                         # fused path: Adam state of the adaptation module's flat slice
+        self._rma_fusable = None
+        dev = self.optimizer.flat_params.device
+        self._adapt_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ fused minibatch step (RMA)
+    def _fast_supported(self):
+        ac = self.actor_critic
+        if not (self.fused and self.fused_critic and not ac.is_recurrent and self.optimizer.flat_params.is_cuda
+                and ac.actor.act_dim <= 64):
+            return False
+        if self._rma_fusable is None:
+            from .engine import MlpEngine
+            self._rma_fusable = all(isinstance(m, nn.Sequential) for m in (ac.env_factor_encoder, ac.adaptation_module,
+                                                                           ac.critic)) \
+                and MlpEngine.from_sequential(ac.env_factor_encoder) is not None \
+                and MlpEngine.from_sequential(ac.adaptation_module) is not None \
+                and CriticEngine.from_sequential(ac.critic) is not None
+        return self._rma_fusable
+
+    def _fast_setup(self, mb):
+        from .engine import MlpEngine
+        super()._fast_setup(mb)
+        st, ac, opt = self._fast_state, self.actor_critic, self.optimizer
+        dev = opt.flat_params.device
+        ce = st["critic"]
+        assert ce is not None
+        enc = MlpEngine.from_sequential(ac.env_factor_encoder)
+        ad = MlpEngine.from_sequential(ac.adaptation_module)
+        D, Lz = int(ce.desc.in_dim), enc.out_dim
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        st.update({
+            "O": D - Lz, "Lz": Lz,
+            "x": torch.zeros(mb, D, **f32),                 # cat(obs, latent): the actor's and the critic's input
+            "dx_actor": torch.zeros(mb, D, **f32), "dx_critic": torch.zeros(mb, D, **f32),
+            "enc": enc, "enc_trace": torch.empty(enc.trace_bytes(mb), **u8), "enc_ws": torch.empty(enc.workspace_bytes(mb), **u8),
+            "enc_grads": ([l.weight.grad for l in enc.linears], [l.bias.grad for l in enc.linears]),
+            "ad": ad, "ad_trace": torch.empty(ad.trace_bytes(mb), **u8), "ad_ws": torch.empty(ad.workspace_bytes(mb), **u8),
+            "ad_grads": ([l.weight.grad for l in ad.linears], [l.bias.grad for l in ad.linears]),
+            "ad_pred": torch.empty(mb, Lz, **f32), "ad_tgt": torch.empty(mb, Lz, **f32), "ad_g": torch.empty(mb, Lz, **f32),
+            "ad_scratch": torch.empty(4096, **u8),
+        })
+        st["grads_out"]["obs"] = st["dx_actor"]
+        enc.repack(); ad.repack()
+        if self._ad is None:
+            # the adaptation module's parameters are one contiguous slice of the flat buffer (parameters() walks modules)
+            params = list(ac.adaptation_module.parameters())
+            off = (params[0].data_ptr() - opt.flat_params.data_ptr()) // 4
+            k, cur = 0, params[0].data_ptr()
+            for p in params:
+                if p.data_ptr() != cur:
+                    raise RuntimeError("adaptation_module parameters are not contiguous in the flat parameter buffer")
+                cur += p.numel() * 4
+                k += p.numel()
+            self._ad = {"off": off, "k": k, "m": torch.zeros(k, **f32), "v": torch.zeros(k, **f32),
+                        "step": torch.zeros(1, dtype=torch.int32, device=dev),
+                        "lr": torch.full((1,), self._adaptation_lr, **f32), "scratch": torch.empty(4096, **u8)}
+
+    def _step_fast(self, f, i, finish=True):
+        if not finish:
+            raise RuntimeError("PPORMA: the data-parallel step is captured as one graph (SNN_DP_GRAPH=single)")
+        st = self._fast_state
+        mb = st["mb"]
+        sl = slice(i * mb, (i + 1) * mb)
+        ac, opt = self.actor_critic, self.optimizer
+        dev = opt.flat_params.device
+        em, es, ws, bs, dw, db = st["actor_tensors"]
+        O = st["O"]
+        x, x_lat = st["x"], st["x"][:, O:]
+        enc, ad, ce, eng = st["enc"], st["ad"], st["critic"], ac.actor.engine
+        priv, hist = f["critic_obs"][sl], f["hist"][sl]       # RolloutStorageRMA: privileged obs / observation histories
+        side = st.get("side_stream")
+        main = torch.cuda.current_stream(dev)
+        L = _lib.lib()
+        opt.zero_grad()
+        # latent = env_factor_encoder(privileged_obs), written straight into the latent columns of cat(obs, latent)
+        x[:, :O].copy_(f["obs"][sl])
+        enc.repack()
+        enc.forward(priv, out_value=x_lat, out_trace=st["enc_trace"])
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ce.repack()
+                value, ctrace = ce.forward(x, out_value=st["value"], out_trace=st["critic_trace"])
+        else:
+            ce.repack()
+            value, ctrace = ce.forward(x, out_value=st["value"], out_trace=st["critic_trace"])
+        mu, trace = eng.forward(x, em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data, db.data,
+                                train=True, out_mu=st["mu"], out_trace=st["trace"], assume_packed=True)
+        if side is not None:
+            main.wait_stream(side)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(L.snn_ppo_head(
+                _p(mu), _p(ac.actor.log_std.data), _p(value), _p(f["actions"][sl]), _p(f["logp"][sl]),
+                _p(f["adv"][sl]), _p(f["returns"][sl]), _p(f["values"][sl]), _p(f["mu"][sl]), _p(f["sigma"][sl]),
+                mb, ac.actor.act_dim, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
+                1 if self.use_clipped_value_loss else 0, _p(st["g_mu"]), _p(st["g_value"]), _p(ac.actor.log_std.grad),
+                _p(self._stats), _p(st["scratch"]), st["scratch"].numel(), stream), "snn_ppo_head")
+        opt.flat_grads[opt.n:].copy_(self._stats[2:3])
+        # both consumers of cat(obs, latent) return the gradient into their input
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"], ws=st["critic_ws"], d_x=st["dx_critic"])
+        else:
+            ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"], ws=st["critic_ws"], d_x=st["dx_critic"])
+        eng.backward(x, mu, st["g_mu"], trace, em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
+                     db.data, need_dobs=True, out=st["grads_out"], assume_packed=True, ws=st["ws_bwd"])
+        if side is not None:
+            main.wait_stream(side)
+        # env_factor_encoder backward on d latent = actor part + critic part
+        enc.backward(st["dx_actor"][:, O:], st["enc_trace"], mb, out=st["enc_grads"], ws=st["enc_ws"],
+                     g2=st["dx_critic"][:, O:])
+        self._finish_step()
+        # ---- adaptation-module regression onto the (updated, detached) encoder latent, second Adam (reference :200-213)
+        a = self._ad
+        world = 1 if self.dp is None else self.dp.world_size
+        gsl = opt.flat_grads[a["off"]:a["off"] + a["k"]]
+        for _ in range(self.num_adaptation_module_substeps):
+            ad.repack()
+            enc.repack()
+            ad.forward(hist, out_value=st["ad_pred"], out_trace=st["ad_trace"])
+            enc.forward(priv, out_value=st["ad_tgt"], out_trace=st["enc_trace"])
+            with torch.cuda.device(dev):
+                _lib.check(L.snn_mse_grad(_p(st["ad_pred"]), _p(st["ad_tgt"]), st["ad_pred"].numel(), _p(st["ad_g"]),
+                                          _p(self._adapt_sum), _p(st["ad_scratch"]),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "snn_mse_grad")
+            ad.backward(st["ad_g"], st["ad_trace"], mb, out=st["ad_grads"], ws=st["ad_ws"])
+            if self.dp is not None:
+                self.dp.allreduce_sum(gsl)
+            g = opt.param_groups[0]
+            with torch.cuda.device(dev):
+                _lib.check(L.snn_clip_adam(
+                    _p(opt.flat_params[a["off"]:]), _p(gsl), _p(a["m"]), _p(a["v"]), a["k"], _p(a["lr"]), _p(a["step"]),
+                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), 0.0, 0.0, 1.0 / world, None,
+                    _p(a["scratch"]), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "snn_clip_adam(adaptation)")
+
+    def _graph_signature(self, f, mb):
+        return super()._graph_signature(f, mb) + (int(self.num_adaptation_module_substeps), float(self._adaptation_lr))
+
+    def _snapshot(self):
+        base = super()._snapshot()
+        if self._ad is None:
+            return base
+        a = self._ad
+        return base + (a["m"].clone(), a["v"].clone(), a["step"].clone(), self._adapt_sum.clone())
+
+    def _restore(self, snap):
+        if self._ad is not None and len(snap) > 6:
+            a = self._ad
+            a["m"].copy_(snap[6]); a["v"].copy_(snap[7]); a["step"].copy_(snap[8]); self._adapt_sum.copy_(snap[9])
+        super()._restore(snap[:6])
+
+    def refresh_packed(self):
+        super().refresh_packed()
+        if self._fast_state is not None and self._fast_state.get("enc") is not None:
+            self._fast_state["enc"].repack()
+            self._fast_state["ad"].repack()
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, privileged_obs_shape, obs_history_shape,
                      action_shape):
@@ -671,6 +838,11 @@ class PPORMA(PPO):
                                 old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, value_batch)
 
     def update(self):
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        if self._fast_supported():
+            self._adapt_sum.zero_()
+            vl, sl = super().update()                  # the fused steps above, one CUDA graph per minibatch index
+            return vl, sl, float(self._adapt_sum.item()) / (num_updates * self.num_adaptation_module_substeps)
         self._stats.zero_()
         self.optimizer.set_lr(self._lr)
         ac = self.actor_critic

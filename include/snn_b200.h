@@ -190,6 +190,12 @@ int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t
                   double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream);
 
+/* Adaptation-module regression of the RMA fork (RMA/.../rsl_rl/algorithms/ppo.py:200-213): loss = F.mse_loss(pred,
+ * target) over n = B*D contiguous elements, g = d loss / d pred = 2 (pred - target) / n; loss_accum[0] += loss.
+ * scratch >= 1 KiB. */
+int snn_mse_grad(const float* pred, const float* target, int64_t n, float* g, float* loss_accum, void* scratch,
+                 void* stream);
+
 /* Optional per-launch device timing used by bench.py's roofline: while enabled, every kernel launch is
  * bracketed by CUDA events on its stream.  Slot = kind + 4 * layer, kind: 0 = forward scan-GEMM, 1 = backward
  * dX scan-GEMM, 2 = dW GEMM, 3 = all other (SIMT) kernels (layer 0).  snn_profile_read synchronises on the

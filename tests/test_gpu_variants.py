@@ -135,6 +135,10 @@ def test_rma_ppo_update_matches_reference_fixture(mode):
     assert rel_err(st.returns.cpu(), g["returns"]) < 1e-5
     assert rel_err(st.advantages.cpu(), g["advantages"]) < 1e-4
     vl, sl, al = alg.update()
+    if mode == "default":          # the fused step (MLPs on the tensor-core kernels), replayed as one CUDA graph
+        assert alg._fast_supported() and len(alg._graphs) == 1 and alg._fast_state.get("enc") is not None
+    else:
+        assert not alg._fast_supported() and len(alg._graphs) == 0
     assert abs(vl / g["mean_value_loss"] - 1) < 1e-4
     assert abs(sl - g["mean_surrogate_loss"]) < 1e-4 * max(1.0, abs(g["mean_surrogate_loss"]))
     assert abs(al / g["mean_adaptation_loss"] - 1) < 1e-3
