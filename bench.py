@@ -509,6 +509,25 @@ def run_ours(args):
     fwd_launches = (L.snn_launch_count() - fl0) // nrep
     step_act_e2e()
     ms_act_e2e = timed(step_act_e2e, nrep) / nrep
+    ms_act_eager = ms_act
+    # the same call replayed as a CUDA graph (how a rollout loop runs it: no per-call host work; PPO.act does the same)
+    with torch.inference_mode():
+        gside = torch.cuda.Stream()
+        gside.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(gside):
+            ac.act_inference(obs_dev)
+        torch.cuda.current_stream().wait_stream(gside)
+        torch.cuda.synchronize()
+        fwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fwd_graph):
+            mu_static = ac.act_inference(obs_dev)
+    for _ in range(3):
+        fwd_graph.replay()
+    ms_act_graph = timed(fwd_graph.replay, nrep) / nrep
+    with torch.inference_mode():
+        if not torch.equal(mu_static, ac.act_inference(obs_dev)):
+            raise RuntimeError("graph replay of act_inference differs from the eager call")
+    ms_act = min(ms_act_eager, ms_act_graph)
 
     # full rollout step PPO.act (actor forward + sample + log-prob + critic), replayed as one CUDA graph
     def step_ppo_act():
@@ -608,13 +627,15 @@ def run_ours(args):
     fwd = {
         "metric": "snn_policy_env_steps_per_s_fwd", "workload": FW["name"], "unit": "env-steps/s",
         "value": world * Bf / (ms_act * 1e-3), "ms_per_call": ms_act, "batch_per_gpu": Bf, "gpu_launches_per_call": int(fwd_launches),
+        "ms_per_call_eager": ms_act_eager, "ms_per_call_graph_replay": ms_act_graph,
         "e2e": {"value": world * Bf / (ms_act_e2e * 1e-3), "unit": "env-steps/s", "ms_per_call": ms_act_e2e,
                 "h2d_bytes_per_step": Bf * O * 4, "d2h_bytes_per_step": Bf * A * 4},
         "roofline": {"bound": "tensor", "achieved": fwd_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": fwd_tf / pk["bf16_tflops_sustained"], "traffic": None,
                      "algo_flops_per_call": Bf * FW["flops_per_sample"],
-                     "note": "per GPU; the whole forward call (all of its launches), 2*T*sum K*N flops per sample; at 4096 "
-                             "environments the call is latency-bound (9 GFLOP = 6.4 us at peak)"},
+                     "note": "per GPU; the whole forward call (one launch: snn_fwd_act), 2*T*sum K*N flops per sample; value = the "
+                             "faster of the eager module call and its CUDA-graph replay (both reported); at 4096 environments "
+                             "one CTA per 32-sample tile streams all weight planes from L2 (9 GFLOP = 6.4 us at peak)"},
         "ppo_act": {"value": world * N / (ms_pact * 1e-3), "ms_per_call": ms_pact,
                     "note": "the whole PPO.act rollout step (actor forward, sample, log-prob, critic value), one CUDA-graph replay"},
     }

@@ -102,6 +102,10 @@ _SIGS = {
     "snn_pack_weights": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p]),
     "snn_fwd_infer": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_fwd_act_supported": (C.c_int, [C.POINTER(SnnDesc), C.c_int64]),
+    "snn_fwd_act_preferred": (C.c_int, [C.POINTER(SnnDesc), C.c_int64]),
+    "snn_fwd_act": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_fwd_train": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snn_bwd": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64,

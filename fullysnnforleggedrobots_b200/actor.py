@@ -72,7 +72,9 @@ class _SpikingActorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: SnnEngine, L: int, obs, enc_mean, enc_std, dec_w, dec_b, *wb):
         weights, biases = list(wb[:L]), list(wb[L:])
-        train = any(ctx.needs_input_grad)
+        # needs_input_grad mirrors requires_grad of the inputs whatever the grad mode: under no_grad / inference_mode
+        # (act_inference, the rollout step) no trace is needed and the one-launch inference kernel runs
+        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         obs_c = obs.contiguous()
         mu, trace = engine.forward(obs_c, enc_mean, enc_std, weights, biases, dec_w, dec_b, train=train)
         if train:

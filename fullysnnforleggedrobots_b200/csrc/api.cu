@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 
+#include "act_fused.cuh"
 #include "dw_gemm.cuh"
 #include "mlp_kernels.cuh"
 #include "nm_gemm.cuh"
@@ -90,6 +91,7 @@ int device_ready(int* num_sms) {
   if (!di.attrs_set) {
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kSmemOptIn)));
+    CUDA_TRY(cudaFuncSetAttribute(act_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemOptIn)));
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(nm_gemm_smem_bytes<NM_DX>())));
     CUDA_TRY(cudaFuncSetAttribute(nm_gemm_kernel<NM_DX_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -274,6 +276,49 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   return SNN_OK;
 }
 
+// ---- geometry of the fused rollout kernel (act_fused.cuh): batch-tile width, weight-ring depth, grid.  The kernel keeps
+// nothing in HBM between layers, so its tile width is free of the layered path's plan: it minimises
+// waves x (max(MMA issue time, weight streaming) + epilogue scans) under the shared-memory budget.
+struct ActGeom { int Bt, TB, ntile, nch, xrows, wd, nw, grid; size_t smem; };
+bool act_geometry(const SnnDesc& d, const SnnPlan& p, int64_t B, int sms, ActGeom* g) {
+  if (B <= 0) return false;
+  int nmt_max = 0, xrows = 64;
+  double nmma = 0;
+  for (int l = 0; l < p.L; ++l) {
+    const int nmt = p.layer[l].NP / 128;
+    if (nmt > nmt_max) nmt_max = nmt;
+    if (l > 0 && p.layer[l].KP > xrows) xrows = p.layer[l].KP;
+    nmma += static_cast<double>(nmt) * (p.layer[l].KP / 64) * d.fwd_planes * 4;
+  }
+  if (nmt_max > 4) return false;
+  double best = -1;
+  for (int bt = 16; bt * p.T <= 256; bt += 16) {
+    const int TB = bt * p.T;
+    const int wd = TB <= 128 ? 128 : 256;
+    if (nmt_max * wd > 512) break;
+    const int nch = (TB + 63) / 64;
+    const size_t fixed = act_smem_fixed(nch, xrows, p.layer[p.L - 1].NP, bt, p.A, p.K0P, TB);
+    if (fixed + 3 * kActWStage > kSmemOptIn) break;
+    if (act_enc_stage_bytes(p.K0P, TB, bt, p.O) > act_x_bytes(nch, xrows, p.K0P, TB)) continue;     // encoder staging lives in X
+    int nw = static_cast<int>((kSmemOptIn - fixed) / kActWStage);
+    if (nw > 8) nw = 8;
+    const int64_t tiles = (B + bt - 1) / bt;
+    const double cyc = TB / 2.0 > 57.0 + TB / 8.0 ? TB / 2.0 : 57.0 + TB / 8.0;
+    const double w_rate = nw * 16384.0 / 1500.0 < 80.0 ? nw * 16384.0 / 1500.0 : 80.0;       // bytes per cycle: ring depth / L2 latency
+    const double t_mma = nmma * cyc, t_w = nmma / 4 * 16384.0 / w_rate;
+    double t_epi = 0;
+    for (int l = 0; l < p.L; ++l) t_epi += ((p.layer[l].NP / 128) * (bt / 16) + 1) / 2 * (600.0 * p.T);
+    const double per_tile = (t_mma > t_w ? t_mma : t_w) + t_epi + 3000.0;
+    const double cost = static_cast<double>((tiles + sms - 1) / sms) * per_tile;
+    if (best < 0 || cost < best) {
+      best = cost;
+      g->Bt = bt; g->TB = TB; g->ntile = static_cast<int>(tiles); g->nch = nch; g->xrows = xrows; g->wd = wd; g->nw = nw;
+      g->smem = fixed + static_cast<size_t>(nw) * kActWStage; g->grid = static_cast<int>(tiles < sms ? tiles : sms);
+    }
+  }
+  return best >= 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -321,8 +366,14 @@ int snn_pack_weights(const SnnDesc* d, const SnnParams* prm, void* packed, void*
                         at(packed, lp.wt_img), lp.wt_plane, reinterpret_cast<float*>(at(packed, lp.bias_pad))};
     if (lp.NP * lp.KP / 8 > max_total) max_total = lp.NP * lp.KP / 8;
   }
+  if (prm->enc_mean == nullptr || prm->enc_std == nullptr) return fail(SNN_EINVAL, "null encoder mean/std pointer");
+  jobs.enc_row = p.L;
+  jobs.enc_mean = prm->enc_mean; jobs.enc_std = prm->enc_std;
+  jobs.enc_tab = reinterpret_cast<float4*>(at(packed, p.enc_tab));
+  jobs.K0 = p.K0; jobs.K0P = p.K0P; jobs.P = p.Pe; jobs.eps = d->enc_eps;
+  if (p.K0P > max_total) max_total = p.K0P;
   { ProfScope prof__(CAT_OTHER, 0.0, st);
-  pack_w_kernel<<<dim3((max_total + 255) / 256, p.L), 256, 0, st>>>(jobs);
+  pack_w_kernel<<<dim3((max_total + 255) / 256, p.L + 1), 256, 0, st>>>(jobs);
   }
   LAUNCH_CHECK("pack_w_kernel");
   return SNN_OK;
@@ -338,6 +389,72 @@ int snn_fwd_infer(const SnnDesc* d, const SnnParams* prm, const void* packed, co
   if (!prm || !packed || !obs || !mu || !workspace) return fail(SNN_EINVAL, "null pointer");
   if (workspace_bytes < p.ws_fwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
   return forward(d, prm, packed, obs, B, mu, workspace, nullptr, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+int snn_fwd_act_supported(const SnnDesc* d, int64_t B) {
+  SnnPlan p;
+  ActGeom g;
+  if (d == nullptr || B <= 0 || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return 0;
+  return act_geometry(*d, p, B, plan_sms(), &g) ? 1 : 0;
+}
+
+int snn_fwd_act_preferred(const SnnDesc* d, int64_t B) {
+  // One CTA walks a whole tile through the network without overlapping the MMAs of one layer with the scan of the one
+  // before, so beyond ~two waves of tiles the layered kernels (persistent, double-buffered accumulators) win: measured
+  // at C1 dims 46.8 vs 67.7 us at B = 4096, 86 vs 98 us at 8192, 165 vs 143 us at 16384 (tools/time_fwd.py).
+  SnnPlan p;
+  ActGeom g;
+  const int sms = plan_sms();
+  if (d == nullptr || B <= 0 || make_plan(*d, B, sms, &p) != SNN_OK) return 0;
+  if (!act_geometry(*d, p, B, sms, &g)) return 0;
+  return g.ntile <= 2 * sms ? 1 : 0;
+}
+
+int snn_fwd_act(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
+                const float* noise, const float* log_std, float* actions, float* logp, float* sigma, void* stream) {
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  SnnPlan p;
+  if ((rc = plan_for(d, B, sms, &p))) return rc;
+  if (!prm || !packed || !obs || !mu) return fail(SNN_EINVAL, "null pointer");
+  const bool sample = noise != nullptr;
+  if (sample && (!log_std || !actions || !logp || !sigma)) return fail(SNN_EINVAL, "snn_fwd_act: the sampling tail needs log_std, actions, logp and sigma");
+  if (sample && p.A > 64) return fail(SNN_EINVAL, "snn_fwd_act: sampling tail supports act_dim <= 64");
+  if (B == 0) return SNN_OK;
+  ActGeom g;
+  if (!act_geometry(*d, p, B, sms, &g)) return fail(SNN_EINVAL, "snn_fwd_act: geometry not supported by the fused kernel (spike_ts > 16, a layer wider than 512, or shared memory); use snn_fwd_infer");
+  ActParams q{};
+  q.L = p.L; q.T = p.T; q.Bt = g.Bt; q.TB = g.TB; q.ntile = g.ntile; q.B = static_cast<int>(B);
+  q.a_planes = d->fwd_planes; q.nch = g.nch; q.xrows = g.xrows; q.wd = g.wd; q.nw = g.nw; q.K0P = p.K0P;
+  q.NPlast = p.layer[p.L - 1].NP; q.O = p.O; q.K0 = p.K0; q.Pe = p.Pe;
+  q.pe_magic = p.Pe < 128 ? static_cast<uint32_t>(((1u << 20) + p.Pe - 1) / p.Pe) : 0u;
+  for (int l = 0; l < p.L; ++l) {
+    const LayerPlan& lp = p.layer[l];
+    q.layer[l] = ActLayer{at(packed, lp.w_img), lp.w_plane, reinterpret_cast<const float*>(at(packed, lp.bias_pad)), lp.KP, lp.NP, lp.NP / 128};
+  }
+  q.obs = obs;
+  q.enc_tab = reinterpret_cast<const float4*>(at(packed, p.enc_tab));
+  q.A = p.A; q.P = p.Pd; q.dec_tanh = d->dec_tanh; q.dec_w = prm->dec_w; q.dec_b = prm->dec_b; q.mu = mu;
+  q.noise = noise; q.log_std = log_std; q.actions = actions; q.logp = logp; q.sigma = sigma;
+  q.dbg_out = g_dbg_out; q.dbg = debug_mask();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double flops = 0;
+  for (int l = 0; l < p.L; ++l) flops += 2.0 * B * p.layer[l].K * p.layer[l].N * p.T;
+  { ProfScope prof__(CAT_FWD, flops, st);
+  // explicit 1-CTA cluster: the shared->shared bulk copy addresses shared::cluster memory (see forward())
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.grid); cfg.blockDim = dim3(kActThreads);
+  cfg.dynamicSmemBytes = g.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, act_fused_kernel, q);
+  if (le != cudaSuccess) return fail(SNN_ECUDA, "launch act_fused_kernel: %s", cudaGetErrorString(le));
+  }
+  LAUNCH_CHECK("act_fused_kernel");
+  return SNN_OK;
 }
 
 int snn_fwd_train(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, float* mu,
@@ -730,6 +847,7 @@ int snn_mlp_pack(const SnnMlpDesc* d, const SnnMlpParams* prm, void* packed, voi
   if ((rc = mlp_plan_of(d, 1, &p))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PackJobs jobs{};
+  jobs.enc_row = -1;
   int max_total = 0;
   for (int l = 0; l < p.LT; ++l) {
     const MlpLayerPlan& lp = p.layer[l];

@@ -64,6 +64,7 @@ struct SnnPlan {
   int ntile;         // ceil(B / Bt)
   int64_t B, Bcap, Rt;   // Bcap = ntile * Bt, Rt = ntile * CT
   LayerPlan layer[SNN_MAX_LAYERS];
+  size_t enc_tab;           // packed: per encoder neuron float4 {mean, std^2 + eps, -0.5 / (std^2 + eps), obs index bits}
   size_t packed_bytes;
   size_t tr_enc_bits;       // trace: encoder spike words [K0P/32][Rt]
   size_t trace_bytes;
@@ -135,6 +136,7 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
     k = n; kp = lp.NP;
   }
   if (p.K0P > 8192) return SNN_EINVAL;
+  p.enc_tab = take(static_cast<size_t>(p.K0P) * 16);
   p.packed_bytes = off;
   // trace
   off = 0;

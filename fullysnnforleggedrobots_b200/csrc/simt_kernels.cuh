@@ -20,8 +20,26 @@ __device__ __forceinline__ void split3(float w, float& h, float& m, float& l) {
 
 // all layers of a network in ONE launch: blockIdx.y selects the layer
 struct PackJob { const float* W; const float* bias; int N, K, NP, KP; uint8_t* w_img; size_t w_plane; uint8_t* wt_img; size_t wt_plane; float* bias_pad; };
-struct PackJobs { PackJob j[SNN_MAX_LAYERS]; };
+// enc_row >= 0: blockIdx.y == enc_row builds the encoder table of the fused rollout kernel (act_fused.cuh) instead:
+// per encoder neuron k  {mean, var = std^2 + eps, -0.5 * rcp(var), obs index k / P as int bits (-1: padding neuron)} —
+// the same per-neuron constants encode_kernel derives in shared memory
+struct PackJobs {
+  PackJob j[SNN_MAX_LAYERS + 1];
+  int enc_row;
+  const float* enc_mean; const float* enc_std; float4* enc_tab; int K0, K0P, P; float eps;
+};
 __global__ void pack_w_kernel(const PackJobs jobs) {
+  if (static_cast<int>(blockIdx.y) == jobs.enc_row) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < jobs.K0P) {
+      const bool live = k < jobs.K0;
+      const float sk = live ? jobs.enc_std[k] : 1.f;
+      const float var = __fadd_rn(__fmul_rn(sk, sk), jobs.eps);
+      jobs.enc_tab[k] = make_float4(live ? jobs.enc_mean[k] : 0.f, var, -0.5f * __frcp_rn(var),
+                                    __int_as_float(live ? k / jobs.P : -1));
+    }
+    return;
+  }
   const PackJob& jb = jobs.j[blockIdx.y];
   const float* __restrict__ W = jb.W;
   const float* __restrict__ bias = jb.bias;

@@ -51,6 +51,9 @@ class SnnEngine:
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
         self._ws: Dict[tuple, torch.Tensor] = {}
+        # inference forward: the one-launch fused kernel (snn_fwd_act) whenever it takes the geometry; False keeps the
+        # layered path (encode -> one scan-GEMM per layer -> decode) — same mu bit for bit, used by tests and A/B timing
+        self.fused_infer = True
 
     # ------------------------------------------------------------------ helpers
     def _params_struct(self, enc_mean, enc_std, weights, biases, dec_w, dec_b) -> _lib.SnnParams:
@@ -70,9 +73,10 @@ class SnnEngine:
             self._ws[key] = buf
         return buf
 
-    def packed_weights(self, weights: List[torch.Tensor], biases: List[torch.Tensor], params_struct) -> torch.Tensor:
-        """bf16 plane images; re-packed only when a weight/bias tensor changed (version counter)."""
-        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases))
+    def packed_weights(self, weights: List[torch.Tensor], biases: List[torch.Tensor], params_struct, enc=()) -> torch.Tensor:
+        """bf16 plane images (+ the encoder table of the fused rollout kernel); re-packed only when a weight / bias /
+        encoder tensor changed (version counter)."""
+        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases, *enc))
         dev = weights[0].device
         if self._packed is None or self._packed.device != dev:
             n = _lib.lib().snn_packed_weights_bytes(C.byref(self.desc))
@@ -98,18 +102,18 @@ class SnnEngine:
         self._packed_key = None
         ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
         with torch.cuda.device(weights[0].device):
-            self.packed_weights(weights, biases, ps)
+            self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
 
     def ensure_packed(self, enc_mean, enc_std, weights, biases, dec_w, dec_b):
         """Re-pack only if a weight / bias tensor changed since the last pack (torch version counters).  Callers that
         replay CUDA graphs over the packed planes run this before the replay: the check is host-side."""
-        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases))
+        key = tuple((t.data_ptr(), t._version) for t in (*weights, *biases, enc_mean, enc_std))
         if key == self._packed_key and self._packed is not None:
             return
         ps = self._params_struct(enc_mean.data, enc_std.data, [w.data for w in weights], [b.data for b in biases],
                                  dec_w.data, dec_b.data)
         with torch.cuda.device(weights[0].device):
-            self.packed_weights(weights, biases, ps)
+            self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
 
     def trace_bytes(self, B: int) -> int:
         return int(_lib.lib().snn_trace_bytes(C.byref(self.desc), B))
@@ -135,7 +139,8 @@ class SnnEngine:
         L = _lib.lib()
         with torch.cuda.device(dev):
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
-            packed = self._packed if (assume_packed and self._packed is not None) else self.packed_weights(weights, biases, ps)
+            packed = self._packed if (assume_packed and self._packed is not None) else \
+                self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
             mu = out_mu if out_mu is not None else torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
             if B == 0:
                 return mu, None
@@ -147,6 +152,10 @@ class SnnEngine:
                 _lib.check(L.snn_fwd_train(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
                                            _ptr(trace), nbytes, None, 0, _stream_ptr(dev)), "snn_fwd_train")
                 return mu, trace
+            if self.fused_infer and L.snn_fwd_act_preferred(C.byref(self.desc), B):
+                _lib.check(L.snn_fwd_act(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu), None, None,
+                                         None, None, None, _stream_ptr(dev)), "snn_fwd_act")
+                return mu, None
             nbytes = L.snn_workspace_bytes(C.byref(self.desc), B, 0)
             if ws is None:
                 ws = self._buffer("fwd", nbytes, dev)
@@ -155,6 +164,38 @@ class SnnEngine:
             _lib.check(L.snn_fwd_infer(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu),
                                        _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_fwd_infer")
             return mu, None
+
+    def act_supported(self, B: int) -> bool:
+        """The one-launch kernel takes this geometry at all."""
+        return bool(B > 0 and _lib.lib().snn_fwd_act_supported(C.byref(self.desc), B))
+
+    def act_preferred(self, B: int) -> bool:
+        """... and is the faster path for this batch (rollout-sized: at most two waves of tiles): what forward() uses."""
+        return bool(self.fused_infer and B > 0 and _lib.lib().snn_fwd_act_preferred(C.byref(self.desc), B))
+
+    def act(self, obs, enc_mean, enc_std, weights, biases, dec_w, dec_b, noise, log_std, out_mu, out_actions, out_logp,
+            out_sigma, assume_packed: bool = False):
+        """Rollout step in one launch (snn_fwd_act): mu, actions = mu + exp(log_std) * noise, summed Normal log-prob and
+        sigma, all written into caller-owned buffers.  noise = None: mu only (the other outputs are ignored).  Only when
+        act_supported(B); forward(train=False) picks this kernel by itself for rollout-sized batches."""
+        _check_f32_cuda(obs, "obs")
+        _check_f32_cuda(out_mu, "mu")
+        if noise is not None:
+            for t, n in ((noise, "noise"), (log_std, "log_std"), (out_actions, "actions"), (out_logp, "logp"),
+                         (out_sigma, "sigma")):
+                _check_f32_cuda(t, n)
+        else:
+            log_std = out_actions = out_logp = out_sigma = None
+        dev = obs.device
+        B = obs.shape[0]
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
+            packed = self._packed if (assume_packed and self._packed is not None) else \
+                self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
+            _lib.check(L.snn_fwd_act(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(out_mu), _ptr(noise),
+                                     _ptr(log_std), _ptr(out_actions), _ptr(out_logp), _ptr(out_sigma), _stream_ptr(dev)),
+                       "snn_fwd_act")
 
     def backward(self, obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs: bool,
                  out=None, assume_packed: bool = False, ws=None):
@@ -166,7 +207,8 @@ class SnnEngine:
         g_mu = g_mu.contiguous().float()
         with torch.cuda.device(dev):
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
-            packed = self._packed if (assume_packed and self._packed is not None) else self.packed_weights(weights, biases, ps)
+            packed = self._packed if (assume_packed and self._packed is not None) else \
+                self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
             g = _lib.SnnGrads()
             if out is None:
                 out = {

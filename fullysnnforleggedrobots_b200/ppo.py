@@ -179,15 +179,19 @@ class PPO:
         layers = actor.snn.linear_layers()
         # the parameters themselves (not .data: that hides torch's version counters from the engine's "re-pack only
         # if a weight changed" check; _act_graphed runs the same check on the host before every replay)
-        actor.engine.forward(st["obs"], actor.encoder.mean, actor.encoder.std, [l.weight for l in layers],
-                             [l.bias for l in layers], actor.decoder.decoder.weight, actor.decoder.decoder.bias,
-                             train=False, out_mu=o["mu"], ws=st["ws_fwd"])
-        noise = torch.randn_like(o["mu"])
+        params = (actor.encoder.mean, actor.encoder.std, [l.weight for l in layers], [l.bias for l in layers],
+                  actor.decoder.decoder.weight, actor.decoder.decoder.bias)
         B, A = o["mu"].shape
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A, _p(o["actions"]),
-                                                     _p(o["logp"]), _p(o["sigma"]), C.c_void_p(cur.cuda_stream)),
-                       "snn_sample_logprob")
+        noise = torch.randn_like(o["mu"])
+        if actor.engine.act_preferred(B) and A <= 64:
+            # ONE launch: encoder, LIF layers, decoder, sigma / sampling / log-prob (snn_fwd_act)
+            actor.engine.act(st["obs"], *params, noise, actor.log_std.data, o["mu"], o["actions"], o["logp"], o["sigma"])
+        else:
+            actor.engine.forward(st["obs"], *params, train=False, out_mu=o["mu"], ws=st["ws_fwd"])
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().snn_sample_logprob(_p(o["mu"]), _p(actor.log_std.data), _p(noise), B, A,
+                                                         _p(o["actions"]), _p(o["logp"]), _p(o["sigma"]),
+                                                         C.c_void_p(cur.cuda_stream)), "snn_sample_logprob")
         cur.wait_stream(side)
 
     @staticmethod

@@ -93,6 +93,21 @@ int snn_pack_weights(const SnnDesc* d, const SnnParams* p, void* packed, void* s
 int snn_fwd_infer(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
                   int64_t B, float* mu, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The rollout step's forward as ONE kernel launch (PPO.act, AMP/.../algorithms/ppo.py:90-102 ->
+ * ActorCritic.act, AMP:410-415 -> PopSpikeActor.forward, AMP:300-320): encoder, every LIF layer and the decoder run
+ * inside one CTA per batch tile; spike words live in shared memory and never touch HBM, so there is no workspace.
+ * mu is bit-identical to snn_fwd_infer's.  With noise != NULL (standard-normal draws [B,A] made by the caller) the
+ * kernel also emits what Normal(mu, exp(log_std)).sample() / log_prob().sum(-1) / stddev give the reference
+ * (AMP:398-421): actions = mu + sigma * noise, logp [B], sigma [B,A]  (act_dim <= 64); with noise == NULL the four
+ * pointers after it are ignored.  snn_fwd_act_supported: 1 when the fused kernel takes this geometry (T * 16 <= 256
+ * accumulator columns per neuron tile, layers <= 512 wide, operand buffers within shared memory), else 0 — callers
+ * then use snn_fwd_infer.  snn_fwd_act_preferred: supported AND the batch is at most two waves of tiles (rollout-sized
+ * batches); larger batches are faster on the layered kernels of snn_fwd_infer. */
+int snn_fwd_act_supported(const SnnDesc* d, int64_t B);
+int snn_fwd_act_preferred(const SnnDesc* d, int64_t B);
+int snn_fwd_act(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs, int64_t B, float* mu,
+                const float* noise, const float* log_std, float* actions, float* logp, float* sigma, void* stream);
+
 /* Same forward with the traces BPTT needs (what autograd would save: AMP:154-167, 216-232). */
 int snn_fwd_train(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
                   int64_t B, float* mu, void* trace, size_t trace_bytes,

@@ -13,6 +13,8 @@ struct Args {
   int a_tiles;    // number of distinct A tiles cycled through (1 = same A every MMA)
   int b_tiles;    // number of distinct B tiles
   int iters;
+  int commit_every;   // > 0: tcgen05.commit to a scratch mbarrier after every commit_every groups of 4 MMAs
+  int b_mn;       // 1: B operand MN-major (rows = K, 64-column blocks 8 KiB apart), as act_fused.cuh / dw_gemm.cuh
   long long* out; // [gridDim.x]
 };
 
@@ -20,13 +22,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[8];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5;
   // A tiles: 16 KB each (128 rows x 64 K), B tiles: 32 KB each (256 rows x 64 K)
   uint8_t* sA = smem;
   uint8_t* sB = smem + 4 * 16384;
   for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&bar2[i], 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a) {
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, a.N, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(128, a.N, 0, a.b_mn);
     const uint32_t hi = smem_desc_hi(1024);
     long long t0 = 0, t1 = 0;
     if (elect_one()) {
@@ -44,12 +47,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t alo = smem_desc_lo(smem_u32(sA + at * 16384) + k * 32, 0);
-          const uint32_t blo = smem_desc_lo(smem_u32(sB + bt * 32768) + k * 32, 0);
+          const uint32_t blo = a.b_mn ? smem_desc_lo(smem_u32(sB + bt * 32768) + k * 2048, 8192)
+                                      : smem_desc_lo(smem_u32(sB + bt * 32768) + k * 32, 0);
           umma_bf16_lohi(tmem + acc * a.N, alo, hi, blo, hi, idesc, 1);
           if (++acc == a.nacc) acc = 0;
           if (++at == a.a_tiles) at = 0;
           if (++bt == a.b_tiles) bt = 0;
         }
+        if (a.commit_every > 0 && (it % a.commit_every) == 0) umma_commit(&bar2[it & 7]);
       }
       umma_commit(&bar);
     }
@@ -75,14 +80,16 @@ int main() {
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   const int Ns[] = {16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 240, 256};
   std::printf("# N nacc a_tiles b_tiles cycles_per_mma mac_per_cycle\n");
-  for (int cfg = 0; cfg < 4; ++cfg) {
+  for (int cfg = 0; cfg < 8; ++cfg) {
     for (int N : Ns) {
       Args a{};
       a.N = N;
       a.nacc = (cfg == 0) ? 1 : (512 / N);
       if (a.nacc > 8) a.nacc = 8;
       a.a_tiles = (cfg >= 2) ? 4 : 1;
-      a.b_tiles = (cfg == 3) ? 4 : 1;
+      a.b_tiles = (cfg == 3 || cfg == 5) ? 4 : 1;
+      a.b_mn = (cfg == 4 || cfg == 5) ? 1 : 0;
+      a.commit_every = cfg == 6 ? 1 : (cfg == 7 ? 4 : 0);
       a.iters = 2000;
       a.out = out;
       for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<<<sms, 128, smem>>>(a);
@@ -94,7 +101,7 @@ int main() {
       for (int i = 0; i < sms; ++i) mean += static_cast<double>(h[i]);
       mean /= sms;
       const double per = mean / (a.iters * 4.0);
-      std::printf("%d %d %d %d %.1f %.0f\n", N, a.nacc, a.a_tiles, a.b_tiles, per, 128.0 * N * 16 / per);
+      std::printf("%d %d %d %d%s %.1f %.0f\n", N, a.nacc, a.a_tiles, a.b_tiles, a.b_mn ? " mn" : (a.commit_every ? (a.commit_every == 1 ? " c1" : " c4") : ""), per, 128.0 * N * 16 / per);
     }
   }
   return 0;
