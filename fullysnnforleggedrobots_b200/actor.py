@@ -70,11 +70,12 @@ class _SpikingActorFn(torch.autograd.Function):
     """obs, params -> mu.  forward = snn_fwd_train / snn_fwd_infer, backward = snn_bwd."""
 
     @staticmethod
-    def forward(ctx, engine: SnnEngine, L: int, obs, enc_mean, enc_std, dec_w, dec_b, *wb):
+    def forward(ctx, engine: SnnEngine, L: int, grad_mode: bool, obs, enc_mean, enc_std, dec_w, dec_b, *wb):
         weights, biases = list(wb[:L]), list(wb[L:])
-        # needs_input_grad mirrors requires_grad of the inputs whatever the grad mode: under no_grad / inference_mode
-        # (act_inference, the rollout step) no trace is needed and the one-launch inference kernel runs
-        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        # needs_input_grad mirrors requires_grad of the inputs whatever the caller's grad mode (and grad mode is always
+        # off inside forward): grad_mode is torch.is_grad_enabled() at the call site.  Under no_grad / inference_mode
+        # (act_inference, the rollout step) no trace is needed and the one-launch inference kernel runs.
+        train = grad_mode and any(ctx.needs_input_grad)
         obs_c = obs.contiguous()
         mu, trace = engine.forward(obs_c, enc_mean, enc_std, weights, biases, dec_w, dec_b, train=train)
         if train:
@@ -87,9 +88,9 @@ class _SpikingActorFn(torch.autograd.Function):
         obs, mu, trace, enc_mean, enc_std, dec_w, dec_b, *wb = ctx.saved_tensors
         L = ctx.L
         weights, biases = list(wb[:L]), list(wb[L:])
-        need_dobs = ctx.needs_input_grad[2]
+        need_dobs = ctx.needs_input_grad[3]
         g = ctx.engine.backward(obs, mu, g_mu, trace, enc_mean, enc_std, weights, biases, dec_w, dec_b, need_dobs)
-        return (None, None, g["obs"], g["enc_mean"], g["enc_std"], g["dec_w"], g["dec_b"], *g["weights"], *g["biases"])
+        return (None, None, None, g["obs"], g["enc_mean"], g["enc_std"], g["dec_w"], g["dec_b"], *g["weights"], *g["biases"])
 
 
 class PopSpikeActor(nn.Module):
@@ -128,7 +129,7 @@ class PopSpikeActor(nn.Module):
 
     def mean_only(self, obs: torch.Tensor) -> torch.Tensor:
         layers = self.snn.linear_layers()
-        return _SpikingActorFn.apply(self._engine, len(layers), obs, self.encoder.mean, self.encoder.std,
+        return _SpikingActorFn.apply(self._engine, len(layers), torch.is_grad_enabled(), obs, self.encoder.mean, self.encoder.std,
                                      self.decoder.decoder.weight, self.decoder.decoder.bias,
                                      *[l.weight for l in layers], *[l.bias for l in layers])
 
