@@ -1,7 +1,7 @@
 """Selected metrics of every kernel in an .ncu-rep (ncu --set full) -> markdown table; optionally a JSON with the
 DRAM traffic / tensor-pipe figures bench.py attaches to its roofline object.
 
-usage: python tools/ncu_summary.py REPORT.ncu-rep "title" [--names a,b,c,...] [--json out.json]
+usage: python tools/ncu_summary.py REPORT.ncu-rep "title" [--names a,b,c,...] [--json out.json] [--commit SHA]
   --names: label of each captured launch, in capture order (e.g. fwd_layer0,fwd_layer1,...)"""
 import csv
 import json
@@ -12,6 +12,7 @@ args = sys.argv[1:]
 rep, title = args[0], (args[1] if len(args) > 1 and not args[1].startswith("--") else args[0])
 names = args[args.index("--names") + 1].split(",") if "--names" in args else None
 jpath = args[args.index("--json") + 1] if "--json" in args else None
+commit = args[args.index("--commit") + 1] if "--commit" in args else None      # the code the capture ran
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -66,4 +67,4 @@ for n, r in enumerate(data):
         }
 if jpath:
     with open(jpath, "w") as f:
-        json.dump({"source": f"{rep} (ncu --set full, B=24576, C1 dims, T=5): {title}", "kernels": kern}, f, indent=1)
+        json.dump({"source": f"{rep} (ncu --set full, B=24576, C1 dims, T=5): {title}", "commit": commit, "kernels": kern}, f, indent=1)
