@@ -248,19 +248,8 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = nm_gemm_grid(q.nmt, p.ntile, num_sms);
     q.s_stage = nm_fwd_s_stage(p.TB);
-    q.nstg = nm_fwd_nstg(q.s_stage);
     { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
-    // explicit 1-CTA cluster: the shared->shared bulk copy of the expanders addresses shared::cluster memory, which is
-    // an illegal instruction in a launch without a cluster dimension
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NmCfg<NM_FWD>::THREADS);
-    cfg.dynamicSmemBytes = nm_fwd_smem_bytes(q.s_stage, q.nstg); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, nm_gemm_kernel<NM_FWD>, q);
-    if (le != cudaSuccess) return fail(SNN_ECUDA, "launch nm_gemm_kernel<FWD>: %s", cudaGetErrorString(le));
+    nm_gemm_kernel<NM_FWD><<<grid, NmCfg<NM_FWD>::THREADS, nm_fwd_smem_bytes(q.s_stage), st>>>(q);
     }
     LAUNCH_CHECK("nm_gemm_kernel<FWD>");
     in_bits = q.out_bits;
@@ -442,16 +431,7 @@ int snn_fwd_act(const SnnDesc* d, const SnnParams* prm, const void* packed, cons
   double flops = 0;
   for (int l = 0; l < p.L; ++l) flops += 2.0 * B * p.layer[l].K * p.layer[l].N * p.T;
   { ProfScope prof__(CAT_FWD, flops, st);
-  // explicit 1-CTA cluster: the shared->shared bulk copy addresses shared::cluster memory (see forward())
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(g.grid); cfg.blockDim = dim3(kActThreads);
-  cfg.dynamicSmemBytes = g.smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, act_fused_kernel, q);
-  if (le != cudaSuccess) return fail(SNN_ECUDA, "launch act_fused_kernel: %s", cudaGetErrorString(le));
+  act_fused_kernel<<<g.grid, kActThreads, g.smem, st>>>(q);
   }
   LAUNCH_CHECK("act_fused_kernel");
   return SNN_OK;
@@ -525,6 +505,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       q.KP = lp.NP; q.MP = lp.KP; q.nmt = lp.KP / 128;
       q.a_img = at(packed, lp.wt_img); q.a_plane = lp.wt_plane; q.a_planes = 2;
       q.b_img = G; q.b_plane = Gplane;
+      q.rev = (top - l) & 1;      // top scan: last to first; dX(top): first to last; then alternating
       q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(8 + l) * 148 * 16 : nullptr;
       const int grid = nm_gemm_grid(q.nmt, p.ntile, sms);
       if (l > 0) {

@@ -10,7 +10,9 @@
 // 16 samples x T steps it is working on:
 //
 //   NM_FWD     A = bf16 hi/mid/lo planes of W (K-major), B = spikes of the layer below: bit-packed in HBM, staged
-//              by bulk copies into a shared-memory ring and expanded there to bf16 0/1 operand tiles.
+//              by bulk copies into a shared-memory ring and expanded there to bf16 0/1 operand tiles, MN-major
+//              ([input neuron][sample-step], a warp-wide 32 x 32 bit transpose per block of spike words), written
+//              straight into the operand slot by the expander warps.
 //              Epilogue = LIF update (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b);
 //              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of __ballot_sync (lane = neuron); emits the
 //              fp32 voltage trace when training.
@@ -28,7 +30,7 @@
 // per-neuron sums (bias gradient) live in registers for the whole kernel.
 //
 // Warp roles: 0 = bulk-copy producer (weights / g_c), 1 = MMA issuer + TMEM owner, 2 = spike-word producer (FWD),
-// 3 = staging -> operand-slot copy issuer (FWD), 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
+// 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
@@ -71,19 +73,20 @@ struct NmParams {
   int enc_O, enc_P, enc_K0;
   float enc_eps;
   float* enc_part;          // [3 * gridDim.x / nmt][2][MP]
-  int s_stage;              // FWD: bytes of one spike sub-tile (operand slot / staging buffer), % 1024 == 0
-  int nstg;                 // FWD: staging buffers (1 or 2)
+  int s_stage;              // FWD: bytes of one spike sub-tile (operand slot): 64-column blocks x 8 KiB
+  int rev;                  // walk the batch tiles last to first: consecutive kernels of the backward chain alternate, so
+                            // a kernel starts on the tiles its predecessor wrote last (still in L2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
                             // 16 = dX: no g_c stores, 32 = dX: no voltage loads, 128 = FWD: no voltage stores, 256 = FWD: no spike-word stores
   unsigned long long* dbg_out;   // optional [gridDim.x][16] cycle counters of the barrier waits (tools/role_cycles.py)
 };
 
 template <int MODE> struct NmCfg;
-// FWD: a ring of 6 weight-plane units of 16 KiB (= two 64-wide chunks of hi/mid/lo, released plane by plane so the
-// reloads start early), 2 operand slots + 1-2 staging buffers of one spike sub-tile each (<= 256 sample-steps x
-// 128 B; the size is a launch parameter), 2 spike-word stages
+// FWD: a ring of 7 weight-plane units of 16 KiB (hi/mid/lo of a 64-wide chunk, released plane by plane so the
+// reloads start early), 3 operand slots of one spike sub-tile each (64 input neurons x <= 256 sample-steps, MN-major:
+// [64-column block][64 rows][128 B]; the size is a launch parameter), 2 spike-word stages
 template <> struct NmCfg<NM_FWD> {
-  static constexpr int NW = 6, W_STAGE = 16384, NS = 2, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
+  static constexpr int NW = 7, W_STAGE = 16384, NS = 3, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
 };
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
 // <= 256 sample-steps x 128 B)
@@ -98,14 +101,13 @@ __host__ __device__ constexpr size_t nm_gemm_smem_bytes() {      // dX kernels
          static_cast<size_t>(NmCfg<MODE>::NS) * NmCfg<MODE>::S_STAGE + 512;
 }
 constexpr size_t kSmemOptIn = 232448;    // 227 KiB per CTA
-// forward kernel: spike sub-tile bytes and number of staging buffers for a batch-tile geometry
-inline int nm_fwd_s_stage(int TB) { return ((TB < 256 ? TB : 256) * 128 + 1023) / 1024 * 1024; }
-inline size_t nm_fwd_smem_bytes(int s_stage, int nstg) {
+// forward kernel: bytes of one spike sub-tile (operand slot) for a batch-tile geometry
+inline int nm_fwd_s_stage(int TB) { return ((TB < 256 ? TB : 256) + 63) / 64 * 8192; }
+inline size_t nm_fwd_smem_bytes(int s_stage) {
   return 1024 + static_cast<size_t>(NmCfg<NM_FWD>::NW) * NmCfg<NM_FWD>::W_STAGE +
-         static_cast<size_t>(NmCfg<NM_FWD>::NS + nstg) * s_stage +
+         static_cast<size_t>(NmCfg<NM_FWD>::NS) * s_stage +
          static_cast<size_t>(NmCfg<NM_FWD>::NBITS) * NmCfg<NM_FWD>::BITS_STAGE + 512;
 }
-inline int nm_fwd_nstg(int s_stage) { return nm_fwd_smem_bytes(s_stage, 2) <= kSmemOptIn ? 2 : 1; }
 
 // CTAs to launch: a multiple of the neuron tiles, at most one per SM, at most one per item
 inline int nm_gemm_grid(int nmt, int ntile, int num_sms) {
@@ -125,8 +127,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   const int S_STAGE = IS_FWD ? p.s_stage : C::S_STAGE;
   uint8_t* w_ring = smem;
   uint8_t* s_ring = w_ring + C::NW * C::W_STAGE;
-  uint8_t* staging = s_ring + C::NS * S_STAGE;                                      // FWD only: nstg buffers
-  uint8_t* bits_ring = staging + (IS_FWD ? p.nstg * S_STAGE : 0);
+  uint8_t* bits_ring = s_ring + C::NS * S_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bits_ring + C::NBITS * C::BITS_STAGE);
   uint64_t* w_full = bars;                      // [<= 8]
   uint64_t* w_empty = w_full + 8;               // [<= 8]
@@ -136,8 +137,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint64_t* bits_full = acc_empty + 2;          // [NBITS]
   uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
-  uint64_t* stg_full = bits_empty + C::NBITS;   // [2]  FWD: staging buffer written by the expanders
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(stg_full + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bits_empty + C::NBITS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
@@ -152,13 +152,14 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
 #ifdef SNN_ABLATE
   unsigned long long wcyc[3] = {0, 0, 0};
   const long long t_start = clock64();
+  const unsigned long long g_start = globaltimer_ns();
 #endif
 
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+    // FWD: an operand slot is full once the four expander warps have written it
+    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], IS_FWD ? 4 : 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
-    for (int s = 0; s < 2; ++s) mbar_init(&stg_full[s], 4);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], by_set ? 128 : NGRP * 128); }
     fence_mbar_init();
   }
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   if (warp == 0) {
     // ===================================================== operand producer (warp-uniform loop, one elected lane issues)
     uint32_t iw = 0, u = 0;
-    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+    for (int tl = tile0; tl < p.ntile; tl += tstep) {
+      const int tile = p.rev ? p.ntile - 1 - tl : tl;
       for (int kc = 0; kc < KC; ++kc) {
         if (IS_FWD) {
           // one ring unit per weight plane
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   } else if (IS_FWD && warp == 2) {
     // ===================================================== spike-word producer: per (chunk, sub-tile) two runs of words
     uint32_t u = 0;
-    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+    for (int tl = tile0; tl < p.ntile; tl += tstep) {
+      const int tile = p.rev ? p.ntile - 1 - tl : tl;
       for (int kc = 0; kc < KC; ++kc)
         for (int sub = 0; sub < nsub; ++sub, ++u) {
           const uint32_t s = u % NBM;
@@ -243,7 +246,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     uint32_t iw = 0, u = 0, it = 0;
     const uint32_t dhi = smem_desc_hi(1024);
     const uint32_t w_ring_lo = smem_desc_lo(smem_u32(w_ring), 16);
-    const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), 16);
+    // FWD: MN-major spike tile, leading-dimension byte offset = one 64-column block; dX: K-major g_c tile
+    const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), IS_FWD ? 8192 : 16);
     for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
       const uint32_t aset = it % nsets;
       SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
             SNN_TWAIT(&s_full[ss], (u / C::NS) & 1, 2);
             const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
             const uint32_t d = tmem_base + aset * 256;
-            const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(p.TB), 0, 0);
+            const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(p.TB), 0, 1);
             for (int pl = 0; pl < npl; ++pl, ++iw) {
               const uint32_t ws = iw % C::NW;
               SNN_TWAIT(&w_full[ws], (iw / C::NW) & 1, 1);
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 if (!(SNN_DBG_MASK(p) & 1)) {
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16)
-                    umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, (kc > 0 || pl > 0 || k16 > 0) ? 1u : 0u);
+                    umma_bf16_lohi(d, a_lo + k16 * 2, dhi, b_lo + k16 * (2048 >> 4), dhi, idesc, (kc > 0 || pl > 0 || k16 > 0) ? 1u : 0u);
                 }
                 umma_commit(&w_empty[ws]);
                 if (pl == npl - 1) {
@@ -290,13 +294,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 const int ncols = min(256, p.TB - sub * 256);
                 const uint32_t b_lo = s_ring_lo + ss * (S_STAGE >> 4);
                 const uint32_t d = tmem_base + aset * 256 + static_cast<uint32_t>(sub * 256);
-                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 0);
+                const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(ncols), 0, 1);
                 uint32_t acc = kc > 0 ? 1u : 0u;
                 if (!(SNN_DBG_MASK(p) & 1)) {
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16)
                     for (int pl = 0; pl < npl; ++pl) {
-                      umma_bf16_lohi(d, w_ring_lo + ((iw0 + pl) % C::NW) * (C::W_STAGE >> 4) + k16 * 2, dhi, b_lo + k16 * 2, dhi, idesc, acc);
+                      umma_bf16_lohi(d, w_ring_lo + ((iw0 + pl) % C::NW) * (C::W_STAGE >> 4) + k16 * 2, dhi, b_lo + k16 * (2048 >> 4), dhi, idesc, acc);
                       acc = 1u;
                     }
                 }
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     const int enc_o = enc_live ? n / p.enc_P : 0;
     float enc_dm = 0.f, enc_ds = 0.f;
     uint32_t it = 0;
-    for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
+    for (int tl = tile0; tl < p.ntile; tl += tstep, ++it) {
+      const int tile = p.rev ? p.ntile - 1 - tl : tl;
       const uint32_t aset = it % nsets;
       if (by_set && aset != static_cast<uint32_t>(grp)) continue;
       const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
@@ -570,73 +575,57 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2) * p.MP + n] = enc_dm;
       p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2 + 1) * p.MP + n] = enc_ds;
     }
-  } else if (IS_FWD && warp == 3) {
-    // ===================================================== staging -> operand slot (shared->shared bulk copy)
-    uint32_t u = 0;
-    const uint32_t nstg = static_cast<uint32_t>(p.nstg);
-    for (int tile = tile0; tile < p.ntile; tile += tstep) {
-      for (int kc = 0; kc < KC; ++kc)
-        for (int sub = 0; sub < nsub; ++sub, ++u) {
-          const uint32_t ss = u % C::NS, sg = u % nstg;
-          SNN_TWAIT(&stg_full[sg], (u / nstg) & 1, 0);
-          SNN_TWAIT(&s_empty[ss], ((u / C::NS) & 1) ^ 1, 1);
-          if (elect_one()) {
-            const uint32_t bytes = static_cast<uint32_t>(min(256, p.TB - sub * 256) * 128);
-            mbar_expect_tx(&s_full[ss], bytes);
-            bulk_s2s(s_ring + ss * S_STAGE, staging + sg * S_STAGE, bytes, &s_full[ss]);
-          }
-          __syncwarp();
-        }
-    }
   } else if (IS_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 B sub-tile)
-    // The four warps expand every sub-tile together (sample-step r = thread, thread + 128; one 128-byte swizzled row
-    // = 64 contraction elements per sample-step) into a STAGING buffer; warp 3 then moves it into the operand slot
-    // with a shared->shared bulk copy.  Both hops are the canonical cross-proxy patterns: generic stores ->
-    // fence.proxy.async -> bulk-copy read (as for every TMA store), and bulk-copy write -> mbarrier -> tcgen05.mma
-    // read (as for the weights).  Writing the operand slot directly with st.shared was NOT reliable for this
-    // K-major B operand: the tensor core now and then read stale 16-byte pieces (run-to-run differences at
-    // B = 24576, at a rate that depended on the slot's shared-memory address) although every writer fenced and a
-    // generic read-back saw the new data; see DESIGN.md.
-    const int et = tid - 384;
-    const uint32_t nstg = static_cast<uint32_t>(p.nstg);
+    // The operand slot is MN-major: [64-column block][64 rows = input neurons of the chunk][128 B = 64 sample-steps],
+    // 128-byte swizzle (piece ^= row % 8).  The words arrive as (32 neurons) x (one sample-step); a warp transposes a
+    // 32 x 32 block (lane = sample-step -> lane = neuron, five shuffles), every lane then owns 32 consecutive
+    // sample-steps of one operand row = four 16-byte pieces.  Generic stores -> fence.proxy.async -> mbarrier ->
+    // tcgen05.mma, the pattern dw_gemm.cuh and act_fused.cuh use for their MN-major spike operands.  (The K-major form
+    // of this tile, [sample-step][64 neurons], written the same way was NOT reliable: the tensor core now and then read
+    // stale 16-byte pieces, and until r2 a shared->shared bulk copy from a staging buffer stood in)
+    const int ew = warp - 12;
     uint32_t u = 0;
     for (int tile = tile0; tile < p.ntile; tile += tstep) {
       for (int kc = 0; kc < KC; ++kc)
         for (int sub = 0; sub < nsub; ++sub, ++u) {
           const int ncols = min(256, p.TB - sub * 256);
+          const int nblk = ((ncols + 31) >> 5) * 2;                 // (32-column block, 32-neuron half) pairs
           const uint32_t s = u % NBM;
           SNN_TWAIT(&bits_full[s], (u / NBM) & 1, 0);
           const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(bits_ring + s * C::BITS_STAGE);
-          uint32_t w0[2], w1[2];
+          uint32_t wv[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = et + 128 * h;
-            w0[h] = r < ncols ? wsrc[r] : 0u;
-            w1[h] = r < ncols ? wsrc[256 + r] : 0u;
+          for (int i = 0; i < 4; ++i) {
+            const int blk = ew + 4 * i, r = (blk >> 1) * 32 + lane;
+            wv[i] = (blk < nblk && r < ncols) ? wsrc[(blk & 1) * 256 + r] : 0u;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&bits_empty[s]);
-          // staging buffer u % nstg is free once the copy of unit u - nstg has completed (= that unit's s_full phase)
-          if (u >= nstg) SNN_TWAIT(&s_full[(u - nstg) % C::NS], ((u - nstg) / C::NS) & 1, 1);
+          // the four transposes are independent shuffle chains: no branch between them, so they interleave (a lone warp
+          // per scheduler runs at the latency of its dependent instructions)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wv[i] = warp_transpose32(wv[i], lane);      // bit j: this lane's neuron at sample-step 32 * rb + j
+          const uint32_t ss = u % C::NS;
+          SNN_TWAIT(&s_empty[ss], ((u / C::NS) & 1) ^ 1, 1);
           if (!(SNN_DBG_MASK(p) & 4)) {
+            uint8_t* const slot = s_ring + ss * S_STAGE;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = et + 128 * h;
-              if (r < ncols) {
-                const int sw = r & 7;
-                uint8_t* dst = staging + (u % nstg) * S_STAGE + (r >> 3) * 1024 + sw * 128;
+            for (int i = 0; i < 4; ++i) {
+              const int blk = ew + 4 * i;
+              const int kl = (blk & 1) * 32 + lane, rb = blk >> 1;
+              uint8_t* row = slot + (rb >> 1) * 8192 + (kl >> 3) * 1024 + (kl & 7) * 128;
+              const bool on = blk < nblk;                                            // predicated stores, no branch
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                  const uint32_t byte = ((c8 < 4 ? w0[h] : w1[h]) >> ((c8 & 3) * 8)) & 0xFFu;
-                  *reinterpret_cast<uint4*>(dst + ((c8 ^ sw) << 4)) = expand_spike_byte(byte);
-                }
+              for (int j = 0; j < 4; ++j) {
+                const uint4 v4 = expand_spike_byte((wv[i] >> (8 * j)) & 0xFFu);
+                if (on) *reinterpret_cast<uint4*>(row + (((((rb & 1) << 2) + j) ^ (kl & 7)) << 4)) = v4;
               }
             }
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&stg_full[u % nstg]);
+          if (lane == 0) mbar_arrive(&s_full[ss]);
         }
     }
   }
@@ -647,6 +636,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     unsigned long long* o = p.dbg_out + static_cast<size_t>(blockIdx.x) * 16 + role * 4;
     o[0] = wcyc[0]; o[1] = wcyc[1]; o[2] = wcyc[2];
     o[3] = static_cast<unsigned long long>(clock64() - t_start);
+    if (role == 2) { o[1] = g_start; o[2] = globaltimer_ns(); }      // wall-clock stamps (ns) of this CTA: first / last instruction
   }
 #endif
   tc_fence_before_sync();

@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.y;
   const int n0 = chunk * 64 + 2 * lane;                        // this thread's neurons n0, n0 + 1
-  const int b = blockIdx.x * SPB + w;                          // its sample (< Bcap)
+  // sample blocks are walked last to first: the forward pass wrote this layer's voltages in ascending order, so its
+  // tail is what the L2 still holds (and the dX kernel that follows starts on the g_c rows written last here)
+  const int b = static_cast<int>(gridDim.x - 1 - blockIdx.x) * SPB + w;      // its sample (< Bcap)
   const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
   const int nt = TT > 0 ? TT : T;
   const float Tf = static_cast<float>(nt);

@@ -39,10 +39,11 @@ buf.zero_()
 step()
 torch.cuda.synchronize()
 L.snn_debug_set_cycle_buffer(None)
-d = buf.cpu().view(16, 148, 4, 4).double()
+di = buf.cpu().view(16, 148, 4, 4)      # int64: the %globaltimer stamps need all 64 bits
+d = di.double()
 # wait sites of nm_gemm.cuh (fwd / dx) — the dW kernel reuses the same slots with its own meaning (dw_gemm.cuh)
 names = {0: ("producer", ["w_empty", "g_empty(dx)", "-"]), 1: ("mma", ["acc_empty", "w_full", "s_full"]),
-         2: ("epilogue", ["acc_full", "-", "-"]), 3: ("expander", ["bits_full", "staging_free", "-"])}
+         2: ("epilogue", ["acc_full", "-", "-"]), 3: ("expander", ["bits_full", "slot_free", "-"])}
 print(f"SNN_DBG={os.environ.get('SNN_DBG', '0')}  (mean over CTAs, kilo-cycles)")
 for slot in range(16):
     x = d[slot]
@@ -57,3 +58,34 @@ for slot in range(16):
         nm, ws = names[r]
         parts = ", ".join(f"wait {w} {x[:, r, i].mean().item() / 1e3:7.1f}" for i, w in enumerate(ws) if w != "-")
         print(f"   {nm:9s} total {tot:7.1f} | {parts}")
+    if slot < 4 or slot >= 8:
+        # nm_gemm kernels: %globaltimer stamps of every CTA (epilogue warp 4): first / last instruction
+        st, en = di[slot][:, 2, 1], di[slot][:, 2, 2]
+        live = st > 0
+        if live.any():
+            t0 = st[live].min()
+            st, en = (st[live] - t0).double(), (en[live] - t0).double()
+            t0 = 0.0
+            print(f"   wall clock (us): CTA starts 0.0 .. {(st.max() - t0).item() / 1e3:.1f}, ends {(en.min() - t0).item() / 1e3:.1f} .. "
+                  f"{(en.max() - t0).item() / 1e3:.1f}; mean CTA life {(en - st).mean().item() / 1e3:.1f}; "
+                  f"cycles/ns of the epilogue warp {(x[:, 2, 3][live] / (en - st)).mean().item():.3f}")
+
+# bubbles between dependent kernels: last CTA end of one kernel -> first CTA start of the next (absolute %globaltimer)
+rows = []
+for slot in range(16):
+    if slot >= 4 and slot < 8:
+        continue
+    st, en = di[slot][:, 2, 1], di[slot][:, 2, 2]
+    live = st > 0
+    if live.any():
+        rows.append((int(st[live].min()), int(st[live].max()), int(en[live].min()), int(en[live].max()), slot))
+rows.sort()
+if rows:
+    t0 = rows[0][0]
+    print("kernel chain (us since the first CTA of the first nm_gemm kernel): first start, last start, first end, last end")
+    prev_end = None
+    for a, b, c, e, slot in rows:
+        kind = "fwd" if slot < 4 else "dx"
+        gap = "" if prev_end is None else f"   bubble since the previous kernel's last CTA: {(a - prev_end) / 1e3:.1f} us"
+        print(f"  {kind} layer {slot % 4 if slot < 8 else slot % 8}: {(a - t0) / 1e3:8.1f} {(b - t0) / 1e3:8.1f} {(c - t0) / 1e3:8.1f} {(e - t0) / 1e3:8.1f}{gap}")
+        prev_end = e
