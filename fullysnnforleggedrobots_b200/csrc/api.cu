@@ -72,7 +72,16 @@ struct DeviceInfo {
   int checked = 0;     // 0 = not yet, 1 = ok, -1 = wrong arch
   int num_sms = 0;
   int attrs_set = 0;
+  int* sched = nullptr;      // this device's instance of g_sched_slots
 };
+
+// Tile-scheduler counters of the persistent scan-GEMM kernels (nm_gemm.cuh): zero at module load, and every kernel leaves
+// its slot zeroed again.  Launches rotate through the slots, so kernels that run concurrently on different streams do
+// not share one (a slot index is baked into a captured graph node: graphs that replay concurrently must not be
+// captured 64 launches apart — this library's graphs replay one after the other on one stream).
+constexpr int kSchedSlots = 64;
+__device__ int g_sched_slots[kSchedSlots * kSchedInts];
+unsigned g_sched_next = 0;
 DeviceInfo g_dev[64];
 
 int device_ready(int* num_sms) {
@@ -104,6 +113,9 @@ int device_ready(int* num_sms) {
                                   static_cast<int>(scan_gemm_smem_bytes<MODE_MLP_FWD>(128))));
     CUDA_TRY(cudaFuncSetAttribute(scan_gemm_kernel<MODE_MLP_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(scan_gemm_smem_bytes<MODE_MLP_DX>(128))));
+    void* sp = nullptr;
+    CUDA_TRY(cudaGetSymbolAddress(&sp, g_sched_slots));
+    di.sched = static_cast<int*>(sp);
     di.attrs_set = 1;
   }
   *num_sms = di.num_sms;
@@ -210,9 +222,16 @@ inline const uint8_t* at(const void* base, size_t off) { return static_cast<cons
 
 TileGeom geom_of(const SnnPlan& p) { return TileGeom{p.Bt, p.CT, p.ntile, static_cast<long long>(p.Rt)}; }
 
+int* sched_slot() {      // device_ready() has run on the current device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev[dev].sched + static_cast<size_t>(g_sched_next++ % kSchedSlots) * kSchedInts;
+}
+
 void nm_geometry(const SnnPlan& p, int64_t B, NmParams* q) {
   q->T = p.T; q->Bt = p.Bt; q->TB = p.TB; q->CT = p.CT; q->sets = p.sets; q->ntile = p.ntile;
   q->B = static_cast<int>(B); q->Rt = p.Rt;
+  q->sched = sched_slot();
   q->dbg = debug_mask();
 }
 
@@ -518,14 +537,14 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
         nm_gemm_kernel<NM_DX><<<grid, NmCfg<NM_DX>::THREADS, nm_gemm_smem_bytes<NM_DX>(), st>>>(q);
         }
         LAUNCH_CHECK("nm_gemm_kernel<DX>");
-        df.row(dbpart_of(l - 1), 3 * grid / q.nmt, lo.NP, lo.N, g->bias[l - 1]);
+        df.row(dbpart_of(l - 1), 3 * p.ntile, lo.NP, lo.N, g->bias[l - 1]);
       } else {
         q.g_a = g->obs != nullptr ? g_a : nullptr;
         q.enc_obs = obs; q.enc_mean = prm->enc_mean; q.enc_std = prm->enc_std;
         q.enc_O = p.O; q.enc_P = p.Pe; q.enc_K0 = p.K0; q.enc_eps = d->enc_eps;
         q.enc_part = small_enc;
-        df.row(small_enc, 3 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
-        df.row(small_enc + p.K0P, 3 * grid / q.nmt, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
+        df.row(small_enc, 3 * p.ntile, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_mean);
+        df.row(small_enc + p.K0P, 3 * p.ntile, 2 * static_cast<size_t>(p.K0P), p.K0, g->enc_std);
         { ProfScope prof__(CAT_DX + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
         nm_gemm_kernel<NM_DX_ENC><<<grid, NmCfg<NM_DX_ENC>::THREADS, nm_gemm_smem_bytes<NM_DX_ENC>(), st>>>(q);
         }

@@ -26,11 +26,16 @@
 // Accumulators: TB = T * Bt <= 256 columns -> two sets (set = item parity): the MMA warp fills one while an
 // epilogue group (4 warps = 128 TMEM lanes) drains the other.  TB > 256 (T > 16): one set, the two epilogue
 // groups split its 16-sample groups.
-// A CTA keeps ONE neuron tile (mt = blockIdx.x % nmt) and walks batch tiles, so per-neuron constants (bias) and
-// per-neuron sums (bias gradient) live in registers for the whole kernel.
+// A CTA keeps ONE neuron tile (mt = blockIdx.x % nmt) and takes batch tiles from a scheduler: its first tile is
+// static, every further one comes from a global counter (one atomicAdd per tile by warp 3, handed to the other warps
+// through a four-entry shared-memory ring one tile ahead of the producers).  CTAs that start late — the critic's
+// kernels hold some SMs when an actor kernel launches inside the PPO step — or run on a slower SM simply take fewer
+// tiles.  Per-neuron constants (bias) live in registers for the whole kernel; per-neuron sums (bias / encoder
+// gradients) are written per TILE, so their summation order does not depend on which CTA ran which tile (bitwise
+// run-to-run reproducibility, tests/test_gpu_properties.py).
 //
 // Warp roles: 0 = bulk-copy producer (weights / g_c), 1 = MMA issuer + TMEM owner, 2 = spike-word producer (FWD),
-// 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD).
+// 3 = tile scheduler, 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD) / third epilogue group (dX).
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
@@ -38,6 +43,8 @@
 namespace snn {
 
 enum { NM_FWD = 0, NM_DX = 1, NM_DX_ENC = 2 };
+constexpr int kSchedInts = 128;     // ints per scheduler slot: one ticket counter per neuron tile (K0P <= 8192: 64 tiles), [127] = CTAs done
+constexpr int kNSch = 4;            // entries of the shared-memory tile ring
 
 struct NmParams {
   // batch-tile geometry (SnnPlan)
@@ -62,7 +69,8 @@ struct NmParams {
   const float* v_in;        // [MP/32][Rt/4][32][4] voltages of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
-  float* db_part;           // [3 * gridDim.x / nmt][MP]   (one row per CTA and epilogue group)
+  float* db_part;           // [3 * ntile][MP]   (one row per batch tile and epilogue group: a fixed summation order
+                            // whatever CTA the scheduler hands a tile to)
   // DX_ENC epilogue: g_a = d loss / d pop_act (written only when the caller needs d obs) and, fused, the encoder
   // parameter gradients (actor_critic.py:105 under autograd):  a = exp(-1/2 d^2 / var), d = obs - mean,
   //   d mean = sum_b g_a a d / var ;  d std = sum_b g_a a d^2 std / var^2     (per-thread sums, one row per group)
@@ -72,8 +80,10 @@ struct NmParams {
   const float* enc_std;     // [enc_K0]
   int enc_O, enc_P, enc_K0;
   float enc_eps;
-  float* enc_part;          // [3 * gridDim.x / nmt][2][MP]
+  float* enc_part;          // [3 * ntile][2][MP]
   int s_stage;              // FWD: bytes of one spike sub-tile (operand slot): 64-column blocks x 8 KiB
+  int* sched;               // tile scheduler: [mt] tiles handed out per neuron tile, [kSchedInts - 1] CTAs that ran out of
+                            // work; all zero at launch, re-armed by the last CTA (one slot per launch, api.cu)
   int rev;                  // walk the batch tiles last to first: consecutive kernels of the backward chain alternate, so
                             // a kernel starts on the tiles its predecessor wrote last (still in L2)
   int dbg;                  // SNN_DBG ablation mask (timing experiments only): 1 = no MMA, 2 = no scan, 4 = no expand,
@@ -137,7 +147,11 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint64_t* bits_full = acc_empty + 2;          // [NBITS]
   uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bits_empty + C::NBITS);
+  uint64_t* sch_full = bits_empty + C::NBITS;   // [kNSch]  tile ring entry published by the scheduler warp
+  uint64_t* sch_empty = sch_full + kNSch;       // [kNSch]  ... read by every consumer warp
+  uint64_t* sch_go = sch_empty + kNSch;         // [1]      the leading producer has taken entry k: fetch entry k + 1
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sch_go + 1);
+  volatile int* s_tiles = reinterpret_cast<volatile int*>(s_tmem + 1);      // [kNSch]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = p.KP / 64;
@@ -161,6 +175,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], IS_FWD ? 4 : 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], by_set ? 128 : NGRP * 128); }
+    // consumers of the tile ring: every warp but the scheduler (and, in the dX kernels, the idle warp 2)
+    for (int s = 0; s < kNSch; ++s) { mbar_init(&sch_full[s], 1); mbar_init(&sch_empty[s], IS_FWD ? 15 : 14); }
+    mbar_init(sch_go, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -168,12 +185,59 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  // entry k of the tile ring: this CTA's k-th batch tile, or -1 when the batch is exhausted (every consumer warp calls
+  // this once per entry; `leader` = the producer warp that runs furthest ahead, its arrival lets the scheduler fetch
+  // the next tile)
+  auto next_tile = [&](uint32_t& k, const bool leader) -> int {
+    const uint32_t sl = k % kNSch;
+    mbar_wait(&sch_full[sl], (k / kNSch) & 1);
+    const int t = s_tiles[sl];
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&sch_empty[sl]);
+      if (leader) mbar_arrive(sch_go);
+    }
+    ++k;
+    return t;
+  };
 
-  if (warp == 0) {
+  if (warp == 3) {
+    // ===================================================== tile scheduler
+    uint32_t k = 0;
+    for (;;) {
+      const uint32_t sl = k % kNSch;
+      mbar_wait(&sch_empty[sl], ((k / kNSch) & 1) ^ 1);
+      int t = tile0;
+      if (k > 0) {
+        mbar_wait(sch_go, (k - 1) & 1);
+        if (lane == 0) t = tstep + atomicAdd(p.sched + mt, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+      }
+      if (t >= p.ntile) t = -1;
+      else if (p.rev) t = p.ntile - 1 - t;
+      if (lane == 0) {
+        s_tiles[sl] = t;
+        mbar_arrive(&sch_full[sl]);      // release: the entry is visible to whoever sees the phase complete
+      }
+      __syncwarp();
+      ++k;
+      if (t < 0) break;
+    }
+    // every CTA has drawn its last ticket before it counts itself done: the last one re-arms the slot for the next launch
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(p.sched + kSchedInts - 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        for (int i = 0; i < p.nmt; ++i) p.sched[i] = 0;
+        p.sched[kSchedInts - 1] = 0;
+        __threadfence();
+      }
+    }
+  } else if (warp == 0) {
     // ===================================================== operand producer (warp-uniform loop, one elected lane issues)
-    uint32_t iw = 0, u = 0;
-    for (int tl = tile0; tl < p.ntile; tl += tstep) {
-      const int tile = p.rev ? p.ntile - 1 - tl : tl;
+    uint32_t iw = 0, u = 0, sk = 0;
+    for (;;) {
+      const int tile = next_tile(sk, !IS_FWD);
+      if (tile < 0) break;
       for (int kc = 0; kc < KC; ++kc) {
         if (IS_FWD) {
           // one ring unit per weight plane
@@ -222,9 +286,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     }
   } else if (IS_FWD && warp == 2) {
     // ===================================================== spike-word producer: per (chunk, sub-tile) two runs of words
-    uint32_t u = 0;
-    for (int tl = tile0; tl < p.ntile; tl += tstep) {
-      const int tile = p.rev ? p.ntile - 1 - tl : tl;
+    uint32_t u = 0, sk = 0;
+    for (;;) {
+      const int tile = next_tile(sk, true);
+      if (tile < 0) break;
       for (int kc = 0; kc < KC; ++kc)
         for (int sub = 0; sub < nsub; ++sub, ++u) {
           const uint32_t s = u % NBM;
@@ -243,12 +308,13 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
-    uint32_t iw = 0, u = 0, it = 0;
+    uint32_t iw = 0, u = 0, it = 0, sk = 0;
     const uint32_t dhi = smem_desc_hi(1024);
     const uint32_t w_ring_lo = smem_desc_lo(smem_u32(w_ring), 16);
     // FWD: MN-major spike tile, leading-dimension byte offset = one 64-column block; dX: K-major g_c tile
     const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), IS_FWD ? 8192 : 16);
-    for (int tile = tile0; tile < p.ntile; tile += tstep, ++it) {
+    for (;; ++it) {
+      if (next_tile(sk, false) < 0) break;
       const uint32_t aset = it % nsets;
       SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
       tc_fence_after_sync();
@@ -367,9 +433,11 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     const float enc_iv = 1.f / (enc_sk * enc_sk + p.enc_eps);
     const int enc_o = enc_live ? n / p.enc_P : 0;
     float enc_dm = 0.f, enc_ds = 0.f;
-    uint32_t it = 0;
-    for (int tl = tile0; tl < p.ntile; tl += tstep, ++it) {
-      const int tile = p.rev ? p.ntile - 1 - tl : tl;
+    uint32_t it = 0, sk = 0;
+    for (;; ++it) {
+      const int tile = next_tile(sk, false);
+      if (tile < 0) break;
+      dbsum = 0.f; enc_dm = 0.f; enc_ds = 0.f;      // per-tile partial rows
       const uint32_t aset = it % nsets;
       if (by_set && aset != static_cast<uint32_t>(grp)) continue;
       const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
@@ -566,14 +634,14 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           *reinterpret_cast<uint16_t*>(q + p.g_plane) = 0;
         }
       }
+      if (MODE == NM_DX)
+        p.db_part[(static_cast<size_t>(tile) * NGRP + grp) * p.MP + n] = dbsum;
+      if (MODE == NM_DX_ENC) {
+        p.enc_part[((static_cast<size_t>(tile) * NGRP + grp) * 2) * p.MP + n] = enc_dm;
+        p.enc_part[((static_cast<size_t>(tile) * NGRP + grp) * 2 + 1) * p.MP + n] = enc_ds;
+      }
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[aset]);
-    }
-    if (MODE == NM_DX)
-      p.db_part[(static_cast<size_t>(tile0) * NGRP + grp) * p.MP + n] = dbsum;
-    if (MODE == NM_DX_ENC) {
-      p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2) * p.MP + n] = enc_dm;
-      p.enc_part[((static_cast<size_t>(tile0) * NGRP + grp) * 2 + 1) * p.MP + n] = enc_ds;
     }
   } else if (IS_FWD && warp >= 12) {
     // ===================================================== spike-bit expanders (smem words -> bf16 B sub-tile)
@@ -585,8 +653,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     // of this tile, [sample-step][64 neurons], written the same way was NOT reliable: the tensor core now and then read
     // stale 16-byte pieces, and until r2 a shared->shared bulk copy from a staging buffer stood in)
     const int ew = warp - 12;
-    uint32_t u = 0;
-    for (int tile = tile0; tile < p.ntile; tile += tstep) {
+    uint32_t u = 0, sk = 0;
+    for (;;) {
+      if (next_tile(sk, false) < 0) break;
       for (int kc = 0; kc < KC; ++kc)
         for (int sub = 0; sub < nsub; ++sub, ++u) {
           const int ncols = min(256, p.TB - sub * 256);

@@ -153,7 +153,7 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   }
   p.ws_ga = take(static_cast<size_t>(p.Bcap) * p.K0P * 4);
   p.dw_max_ctas = num_sms > 0 ? 2 * num_sms : 296;
-  const int row_parts = 3 * (num_sms > 0 ? num_sms : 148);      // rows of per-CTA partials of the dX kernels (3 per CTA)
+  const size_t row_parts = 3 * static_cast<size_t>(p.ntile);     // partial rows of the dX kernels: one per batch tile and epilogue group
   size_t part = 0;
   for (int l = 0; l < p.L; ++l) {
     // worst case: every CTA of the dW launch writes one 128 x 256 fp32 tile
@@ -166,15 +166,19 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.ws_partial = take(p.ws_partial_stride * p.L);
   int npmax = p.K0P;
   for (int l = 0; l < p.L; ++l) if (p.layer[l].NP > npmax) npmax = p.layer[l].NP;
-  size_t dbp = static_cast<size_t>(row_parts) * npmax;
+  size_t dbp = row_parts * npmax;
   const size_t dbp_top = static_cast<size_t>(p.ntile) * (p.Bt / 8) * p.layer[p.L - 1].NP;   // top scan: one row per 8-sample group
   if (dbp_top > dbp) dbp = dbp_top;
   p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(dbp * 4), 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.L);
   p.ws_small = take(static_cast<size_t>(p.ntile) * (p.Bt / 8) * 2 * p.layer[p.L - 1].NP * 4 + 1024);      // decoder partials
-  p.ws_small_enc = take(static_cast<size_t>(row_parts) * 2 * p.K0P * 4 + 1024);          // encoder partials (3 rows per CTA of DX_ENC)
-  // three jobs (bias, decoder weight, decoder bias) over the top scan's partial rows, 256 rows per segment
-  p.ws_red_bytes = 3 * ((static_cast<size_t>(p.ntile) * (p.Bt / 8) + 255) / 256) * p.layer[p.L - 1].NP * 4 + 4096;
+  p.ws_small_enc = take(row_parts * 2 * p.K0P * 4 + 1024);          // encoder partials (3 rows per tile of DX_ENC)
+  // scratch of the two-pass row reductions, 256 rows per segment: three jobs (bias, decoder weight, decoder bias) over
+  // the top scan's partial rows, the bias rows of the layers below and the two encoder jobs over the dX kernels' rows
+  size_t red_cols = 2 * static_cast<size_t>(p.K0P);
+  for (int l = 0; l + 1 < p.L; ++l) red_cols += p.layer[l].NP;
+  p.ws_red_bytes = 3 * ((static_cast<size_t>(p.ntile) * (p.Bt / 8) + 255) / 256) * p.layer[p.L - 1].NP * 4 +
+                   ((row_parts + 255) / 256) * red_cols * 4 + 4096;
   p.ws_red = take(p.ws_red_bytes);
   p.ws_bwd_bytes = off;
   *out = p;
