@@ -79,6 +79,8 @@ def build(force: bool = False, verbose: bool = False, ablate: bool = False) -> s
     cmd = ["nvcc", *NVCC_FLAGS, "-I", INCLUDE, "-o", out, os.path.join(CSRC, "api.cu")]
     if ablate:
         cmd.insert(1, "-DSNN_ABLATE")
+        # tools only: extra -D switches for A/B experiments of kernel geometry (e.g. -DSNN_FWD_NW=9 -DSNN_FWD_NS=2)
+        cmd[2:2] = os.environ.get("SNN_EXTRA_NVCC", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

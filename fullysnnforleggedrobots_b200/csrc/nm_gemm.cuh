@@ -95,8 +95,12 @@ template <int MODE> struct NmCfg;
 // FWD: a ring of 7 weight-plane units of 16 KiB (hi/mid/lo of a 64-wide chunk, released plane by plane so the
 // reloads start early), 3 operand slots of one spike sub-tile each (64 input neurons x <= 256 sample-steps, MN-major:
 // [64-column block][64 rows][128 B]; the size is a launch parameter), 2 spike-word stages
+#ifndef SNN_FWD_NW
+#define SNN_FWD_NW 7
+#define SNN_FWD_NS 3
+#endif
 template <> struct NmCfg<NM_FWD> {
-  static constexpr int NW = 7, W_STAGE = 16384, NS = 3, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
+  static constexpr int NW = SNN_FWD_NW, W_STAGE = 16384, NS = SNN_FWD_NS, S_STAGE = 0, NBITS = 2, BITS_STAGE = 2048, THREADS = 512;
 };
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
 // <= 256 sample-steps x 128 B)

@@ -83,10 +83,11 @@ def test_backward_matches_oracle(c):
     (mu * G.cuda()).sum().backward()
     L = len(p.weights)
     layers = actor.snn.linear_layers()
-    # a tie-flipped spike changes the gradient of that sample; tolerate that through a looser bound
-    # only if the forward actually differed.
-    flipped = ((mu.detach().cpu() - mu_ref).abs() > REL_TOL * mu_ref.abs().max()).any().item()
-    tol = 5e-2 if flipped else REL_TOL
+    # the golden cases (B <= 256) have no threshold ties: the forward must agree on every row, and every gradient is held
+    # to the 1e-4 bar unconditionally (tie rows at rollout / minibatch size are handled with an explicit row mask in
+    # test_gpu_backward_full.py and test_gpu_properties.py)
+    assert not ((mu.detach().cpu() - mu_ref).abs() > REL_TOL * mu_ref.abs().max()).any().item()
+    tol = REL_TOL
     for l in range(L):
         assert rel_err(layers[l].weight.grad.cpu(), gr["weights"][l]) < tol, f"dW{l}"
         assert rel_err(layers[l].bias.grad.cpu(), gr["biases"][l]) < tol, f"db{l}"
