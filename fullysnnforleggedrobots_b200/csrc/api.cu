@@ -948,13 +948,13 @@ int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int nb = static_cast<int>((n + 256 * 8 - 1) / (256 * 8));
   if (nb > 296) nb = 296;
-  float* partial = static_cast<float*>(scratch);     // >= 296 floats
+  float* partial = static_cast<float*>(scratch);     // 296 partial sums + Adam's two step coefficients at kAdamCoefs
   { ProfScope prof__(CAT_OTHER, 0.0, st);
-  sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, grad_scale, partial, step);
+  sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, grad_scale, partial, step, lr, beta1, beta2);
   }
   LAUNCH_CHECK("sumsq_kernel");
   { ProfScope prof__(CAT_OTHER, 0.0, st);
-  clip_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, partial, nb, lr, step, beta1, beta2, eps, weight_decay,
+  clip_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, partial, nb, beta1, beta2, eps, weight_decay,
                                        max_norm, grad_scale, norm_out);
   }
   LAUNCH_CHECK("clip_adam_kernel");

@@ -183,27 +183,37 @@ __global__ void lr_adapt_kernel(const float* __restrict__ kl, float kl_scale, fl
   }
 }
 
-// partial[blockIdx.x] = sum of g^2 over this block's grid-stride slice; block 0 also advances the step counter.
+// partial[blockIdx.x] = sum of g^2 over this block's grid-stride slice; block 0 also advances the step counter and
+// derives Adam's bias corrections for the new step ONCE (double-precision pow / sqrt are a few microseconds of latency on
+// this part: done here, next to the other blocks' sums, instead of by thread 0 of every block of clip_adam_kernel):
+// coefs[0] = lr / (1 - beta1^t), coefs[1] = sqrt(1 - beta2^t)
+constexpr int kAdamCoefs = 384;      // offset (floats) of the two coefficients in the scratch buffer; >= the 296 partials
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float grad_scale,
-                                                   float* __restrict__ partial, int* __restrict__ step) {
+                                                   float* __restrict__ partial, int* __restrict__ step,
+                                                   const float* __restrict__ lr, double beta1d, double beta2d) {
   __shared__ float sh[8];
+  if (blockIdx.x == 0 && threadIdx.x == 32) {      // a lane of warp 1: warp 0's lane 0 finishes the block sum below
+    const int s1 = step[0] + 1;
+    const double t = static_cast<double>(s1);
+    const double bc1 = 1.0 - pow(beta1d, t);
+    const double bc2 = 1.0 - pow(beta2d, t);
+    partial[kAdamCoefs] = static_cast<float>(static_cast<double>(lr[0]) / bc1);
+    partial[kAdamCoefs + 1] = static_cast<float>(sqrt(bc2));
+    step[0] = s1;
+  }
   float acc = 0.f;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
     const float x = g[i] * grad_scale;
     acc += x * x;
   }
   const float t = block_sum_256(acc, sh);
-  if (threadIdx.x == 0) {
-    partial[blockIdx.x] = t;
-    if (blockIdx.x == 0) step[0] += 1;
-  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
 // clip_grad_norm_(max_norm) + Adam (torch semantics: lerp first moment, eps outside the bias-corrected sqrt).
 __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm, const float* __restrict__ g,
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                        const float* __restrict__ partial, int nparts,
-                                                       const float* __restrict__ lr, const int* __restrict__ step,
                                                        double beta1d, double beta2d, float eps, float weight_decay,
                                                        float max_norm, float grad_scale, float* __restrict__ norm_out) {
   // torch.optim.Adam: exp_avg.lerp_(g, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2) with the
@@ -228,11 +238,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
     s_coef = coef;
-    const double t = static_cast<double>(step[0]);
-    const double bc1 = 1.0 - pow(beta1d, t);
-    const double bc2 = 1.0 - pow(beta2d, t);
-    s_step_size = static_cast<float>(static_cast<double>(lr[0]) / bc1);
-    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+    s_step_size = partial[kAdamCoefs];          // lr / (1 - beta1^t) and sqrt(1 - beta2^t), from sumsq_kernel
+    s_bc2_sqrt = partial[kAdamCoefs + 1];
     if (blockIdx.x == 0 && norm_out != nullptr) norm_out[0] = norm;
   }
   __syncthreads();
