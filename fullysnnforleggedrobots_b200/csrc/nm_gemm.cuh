@@ -27,15 +27,16 @@
 // epilogue group (4 warps = 128 TMEM lanes) drains the other.  TB > 256 (T > 16): one set, the two epilogue
 // groups split its 16-sample groups.
 // A CTA keeps ONE neuron tile (mt = blockIdx.x % nmt) and takes batch tiles from a scheduler: its first tile is
-// static, every further one comes from a global counter (one atomicAdd per tile by warp 3, handed to the other warps
-// through a four-entry shared-memory ring one tile ahead of the producers).  CTAs that start late — the critic's
+// static, every further one comes from a global counter (one atomicAdd per tile by warp 2, drawn one tile ahead and
+// handed to the other warps through a four-entry shared-memory ring).  CTAs that start late — the critic's
 // kernels hold some SMs when an actor kernel launches inside the PPO step — or run on a slower SM simply take fewer
 // tiles.  Per-neuron constants (bias) live in registers for the whole kernel; per-neuron sums (bias / encoder
 // gradients) are written per TILE, so their summation order does not depend on which CTA ran which tile (bitwise
 // run-to-run reproducibility, tests/test_gpu_properties.py).
 //
-// Warp roles: 0 = bulk-copy producer (weights / g_c), 1 = MMA issuer + TMEM owner, 2 = spike-word producer (FWD),
-// 3 = tile scheduler, 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD) / third epilogue group (dX).
+// Warp roles: 0 (and 3 in FWD) = weight producers, 1 = MMA issuer + TMEM owner, 2 = B-operand producer (FWD: spike
+// words, dX: g_c units) + tile scheduler, 4-7 and 8-11 = epilogue groups, 12-15 = spike-bit expanders (FWD) / third
+// epilogue group (dX).
 #pragma once
 #include "plan.cuh"
 #include "umma.cuh"
@@ -153,8 +154,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
   uint64_t* sch_full = bits_empty + C::NBITS;   // [kNSch]  tile ring entry published by the scheduler warp
   uint64_t* sch_empty = sch_full + kNSch;       // [kNSch]  ... read by every consumer warp
-  uint64_t* sch_go = sch_empty + kNSch;         // [1]      the leading producer has taken entry k: fetch entry k + 1
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sch_go + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sch_empty + kNSch);
   volatile int* s_tiles = reinterpret_cast<volatile int*>(s_tmem + 1);      // [kNSch]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -179,9 +179,8 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], IS_FWD ? 4 : 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], by_set ? 128 : NGRP * 128); }
-    // consumers of the tile ring: every warp but the scheduler (and, in the dX kernels, the idle warp 2)
+    // consumers of the tile ring: every warp but the scheduling warp 2 (and, in the dX kernels, the idle warp 3)
     for (int s = 0; s < kNSch; ++s) { mbar_init(&sch_full[s], 1); mbar_init(&sch_empty[s], IS_FWD ? 15 : 14); }
-    mbar_init(sch_go, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -190,42 +189,75 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
   // entry k of the tile ring: this CTA's k-th batch tile, or -1 when the batch is exhausted (every consumer warp calls
-  // this once per entry; `leader` = the producer warp that runs furthest ahead, its arrival lets the scheduler fetch
-  // the next tile)
-  auto next_tile = [&](uint32_t& k, const bool leader) -> int {
+  // this once per entry)
+  auto next_tile = [&](uint32_t& k) -> int {
     const uint32_t sl = k % kNSch;
     mbar_wait(&sch_full[sl], (k / kNSch) & 1);
     const int t = s_tiles[sl];
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&sch_empty[sl]);
-      if (leader) mbar_arrive(sch_go);
-    }
+    if (lane == 0) mbar_arrive(&sch_empty[sl]);
     ++k;
     return t;
   };
 
-  if (warp == 3) {
-    // ===================================================== tile scheduler
-    uint32_t k = 0;
+  if (warp == 2) {
+    // ===================================================== B-operand producer + tile scheduler
+    // FWD: the spike words of the layer below, per (chunk, sub-tile) two runs of words; dX: the g_c units of the layer
+    // above.  This warp is the first to need a tile's index, so it also hands the tiles out: the first one is static, the
+    // ticket of the next one is drawn (one atomicAdd) BEFORE this tile's copies are issued and published to the other
+    // warps after them, so the round trip to the counter never shows.
+    uint32_t u = 0, k = 0;
+    int tile = p.rev ? p.ntile - 1 - tile0 : tile0;
     for (;;) {
-      const uint32_t sl = k % kNSch;
-      mbar_wait(&sch_empty[sl], ((k / kNSch) & 1) ^ 1);
-      int t = tile0;
-      if (k > 0) {
-        mbar_wait(sch_go, (k - 1) & 1);
-        if (lane == 0) t = tstep + atomicAdd(p.sched + mt, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+      {   // publish entry k
+        const uint32_t sl = k % kNSch;
+        mbar_wait(&sch_empty[sl], ((k / kNSch) & 1) ^ 1);
+        if (lane == 0) {
+          s_tiles[sl] = tile;
+          mbar_arrive(&sch_full[sl]);      // release: the entry is visible to whoever sees the phase complete
+        }
+        __syncwarp();
+        ++k;
       }
-      if (t >= p.ntile) t = -1;
-      else if (p.rev) t = p.ntile - 1 - t;
-      if (lane == 0) {
-        s_tiles[sl] = t;
-        mbar_arrive(&sch_full[sl]);      // release: the entry is visible to whoever sees the phase complete
+      if (tile < 0) break;
+      int ticket = 0;
+      if (lane == 0) ticket = tstep + atomicAdd(p.sched + mt, 1);
+      for (int kc = 0; kc < KC; ++kc) {
+        if (IS_FWD) {
+          for (int sub = 0; sub < nsub; ++sub, ++u) {
+            const uint32_t s = u % NBM;
+            SNN_TWAIT(&bits_empty[s], ((u / NBM) & 1) ^ 1, 0);
+            if (elect_one()) {
+              const int ncols = min(256, p.TB - sub * 256);
+              mbar_expect_tx(&bits_full[s], static_cast<uint32_t>(2 * ncols * 4));
+              const size_t c0 = static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256;
+              uint8_t* dst = bits_ring + s * C::BITS_STAGE;
+              bulk_g2s(dst, p.b_bits + static_cast<size_t>(2 * kc) * p.Rt + c0, static_cast<uint32_t>(ncols * 4), &bits_full[s]);
+              bulk_g2s(dst + 1024, p.b_bits + static_cast<size_t>(2 * kc + 1) * p.Rt + c0, static_cast<uint32_t>(ncols * 4),
+                       &bits_full[s]);
+            }
+            __syncwarp();
+          }
+        } else {
+          // g_c units of this 64-neuron chunk: (plane) x (sub-tile), each one contiguous run of rows of the image
+          for (int pl = 0; pl < 2; ++pl)
+            for (int sub = 0; sub < nsub; ++sub, ++u) {
+              const uint32_t gs = u % C::NS;
+              SNN_TWAIT(&s_empty[gs], ((u / C::NS) & 1) ^ 1, 1);
+              if (elect_one()) {
+                const uint32_t bytes = static_cast<uint32_t>(min(256, p.TB - sub * 256) * 128);
+                mbar_expect_tx(&s_full[gs], bytes);
+                bulk_g2s(s_ring + gs * S_STAGE,
+                         p.b_img + pl * p.b_plane +
+                             (static_cast<size_t>(kc) * p.Rt + static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256) * 128,
+                         bytes, &s_full[gs]);
+              }
+              __syncwarp();
+            }
+        }
       }
-      __syncwarp();
-      ++k;
-      if (t < 0) break;
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      tile = ticket >= p.ntile ? -1 : (p.rev ? p.ntile - 1 - ticket : ticket);
     }
     // every CTA has drawn its last ticket before it counts itself done: the last one re-arms the slot for the next launch
     if (lane == 0) {
@@ -236,16 +268,20 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         __threadfence();
       }
     }
-  } else if (warp == 0) {
-    // ===================================================== operand producer (warp-uniform loop, one elected lane issues)
-    uint32_t iw = 0, u = 0, sk = 0;
+  } else if (warp == 0 || (IS_FWD && warp == 3)) {
+    // ===================================================== weight producer(s) (warp-uniform loop, one elected lane issues)
+    // One thread issues a bulk copy every ~250 cycles at best (tools/l2_bulk_rate.cu: 65 B/cycle/SM with 16 KiB copies
+    // from one warp whatever the ring depth, 77 - 110 from three), which starved the forward kernel's three 16 KiB plane
+    // units per 64-wide chunk: there warps 0 and 3 take alternate units.
+    const uint32_t wsel = warp == 0 ? 0u : 1u;
+    uint32_t iw = 0, sk = 0;
     for (;;) {
-      const int tile = next_tile(sk, !IS_FWD);
-      if (tile < 0) break;
+      if (next_tile(sk) < 0) break;
       for (int kc = 0; kc < KC; ++kc) {
         if (IS_FWD) {
           // one ring unit per weight plane
           for (int pl = 0; pl < p.a_planes; ++pl, ++iw) {
+            if ((iw & 1u) != wsel) continue;
             const uint32_t ws = iw % C::NW;
             SNN_TWAIT(&w_empty[ws], ((iw / C::NW) & 1) ^ 1, 0);
             if (elect_one()) {
@@ -269,46 +305,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           __syncwarp();
           ++iw;
         }
-        if (!IS_FWD) {
-          // g_c units of this 64-neuron chunk: (plane) x (sub-tile), each one contiguous run of rows of the image
-          for (int pl = 0; pl < 2; ++pl)
-            for (int sub = 0; sub < nsub; ++sub, ++u) {
-              const uint32_t gs = u % C::NS;
-              SNN_TWAIT(&s_empty[gs], ((u / C::NS) & 1) ^ 1, 1);
-              if (elect_one()) {
-                const uint32_t bytes = static_cast<uint32_t>(min(256, p.TB - sub * 256) * 128);
-                mbar_expect_tx(&s_full[gs], bytes);
-                bulk_g2s(s_ring + gs * S_STAGE,
-                         p.b_img + pl * p.b_plane +
-                             (static_cast<size_t>(kc) * p.Rt + static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256) * 128,
-                         bytes, &s_full[gs]);
-              }
-              __syncwarp();
-            }
-        }
       }
-    }
-  } else if (IS_FWD && warp == 2) {
-    // ===================================================== spike-word producer: per (chunk, sub-tile) two runs of words
-    uint32_t u = 0, sk = 0;
-    for (;;) {
-      const int tile = next_tile(sk, true);
-      if (tile < 0) break;
-      for (int kc = 0; kc < KC; ++kc)
-        for (int sub = 0; sub < nsub; ++sub, ++u) {
-          const uint32_t s = u % NBM;
-          SNN_TWAIT(&bits_empty[s], ((u / NBM) & 1) ^ 1, 0);
-          if (elect_one()) {
-            const int ncols = min(256, p.TB - sub * 256);
-            mbar_expect_tx(&bits_full[s], static_cast<uint32_t>(2 * ncols * 4));
-            const size_t c0 = static_cast<size_t>(tile) * p.CT + static_cast<size_t>(sub) * 256;
-            uint8_t* dst = bits_ring + s * C::BITS_STAGE;
-            bulk_g2s(dst, p.b_bits + static_cast<size_t>(2 * kc) * p.Rt + c0, static_cast<uint32_t>(ncols * 4), &bits_full[s]);
-            bulk_g2s(dst + 1024, p.b_bits + static_cast<size_t>(2 * kc + 1) * p.Rt + c0, static_cast<uint32_t>(ncols * 4),
-                     &bits_full[s]);
-          }
-          __syncwarp();
-        }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (warp-uniform loop, one elected lane issues)
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     // FWD: MN-major spike tile, leading-dimension byte offset = one 64-column block; dX: K-major g_c tile
     const uint32_t s_ring_lo = smem_desc_lo(smem_u32(s_ring), IS_FWD ? 8192 : 16);
     for (;; ++it) {
-      if (next_tile(sk, false) < 0) break;
+      if (next_tile(sk) < 0) break;
       const uint32_t aset = it % nsets;
       SNN_TWAIT(&acc_empty[aset], ((it / nsets) & 1) ^ 1, 0);
       tc_fence_after_sync();
@@ -439,7 +436,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     float enc_dm = 0.f, enc_ds = 0.f;
     uint32_t it = 0, sk = 0;
     for (;; ++it) {
-      const int tile = next_tile(sk, false);
+      const int tile = next_tile(sk);
       if (tile < 0) break;
       dbsum = 0.f; enc_dm = 0.f; enc_ds = 0.f;      // per-tile partial rows
       const uint32_t aset = it % nsets;
@@ -659,7 +656,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
     const int ew = warp - 12;
     uint32_t u = 0, sk = 0;
     for (;;) {
-      if (next_tile(sk, false) < 0) break;
+      if (next_tile(sk) < 0) break;
       for (int kc = 0; kc < KC; ++kc)
         for (int sub = 0; sub < nsub; ++sub, ++u) {
           const int ncols = min(256, p.TB - sub * 256);

@@ -7,8 +7,12 @@
 #include "umma.cuh"
 using namespace snn;
 
-constexpr int kSlots = 3;      // per issuing warp
-constexpr int kWarps = 4;
+#ifndef KSLOTS
+#define KSLOTS 3
+#define KWARPS 4
+#endif
+constexpr int kSlots = KSLOTS;      // per issuing warp
+constexpr int kWarps = KWARPS;
 
 __global__ void __launch_bounds__(32 * kWarps, 1) l2_rate_kernel(const uint8_t* src, size_t region, int chunk, int iters, int shared_stream,
                                                        long long* out) {
