@@ -264,7 +264,7 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     q.dbg_out = g_dbg_out ? g_dbg_out + static_cast<size_t>(l) * 148 * 16 : nullptr;
     q.bias = reinterpret_cast<const float*>(at(packed, lp.bias_pad));
     q.out_bits = reinterpret_cast<uint32_t*>(at(bits_base, lp.tr_bits));
-    q.v_out = volt_base ? reinterpret_cast<float*>(at(volt_base, lp.tr_volt)) : nullptr;
+    q.v_out = volt_base ? reinterpret_cast<uint16_t*>(at(volt_base, lp.tr_volt)) : nullptr;
     const int grid = nm_gemm_grid(q.nmt, p.ntile, num_sms);
     q.s_stage = nm_fwd_s_stage(p.TB);
     { ProfScope prof__(CAT_FWD + 4 * l, 2.0 * B * lp.K * lp.N * p.T, st);
@@ -480,6 +480,9 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
   if (!prm || !packed || !obs || !mu || !g_mu || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
   if (workspace_bytes < p.ws_bwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
+  // every region of the plan is a multiple of 1 KiB from the base: make the base itself 1 KiB aligned (ws_bwd_bytes
+  // includes the slack), so the g_c planes are too
+  workspace = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~static_cast<uintptr_t>(1023));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Bi = static_cast<int>(B);
   const TileGeom tg = geom_of(p);
@@ -499,7 +502,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     const LayerPlan& lp = p.layer[top];
     const int nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
     { ProfScope prof__(CAT_OTHER, 0.0, st);
-    const float* volt = reinterpret_cast<const float*>(at(trace, lp.tr_volt));
+    const uint16_t* volt = reinterpret_cast<const uint16_t*>(at(trace, lp.tr_volt));
     const dim3 grd(nrows, lp.NP / 64);
     if (p.T == 5)
       top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
@@ -529,7 +532,7 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
       const int grid = nm_gemm_grid(q.nmt, p.ntile, sms);
       if (l > 0) {
         const LayerPlan& lo = p.layer[l - 1];
-        q.v_in = reinterpret_cast<const float*>(at(trace, lo.tr_volt));
+        q.v_in = reinterpret_cast<const uint16_t*>(at(trace, lo.tr_volt));
         q.g_img = at(workspace, p.ws_g[l - 1]);
         q.g_plane = p.ws_g_plane[l - 1];
         q.db_part = dbpart_of(l - 1);

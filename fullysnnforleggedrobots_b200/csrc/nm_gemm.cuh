@@ -14,8 +14,8 @@
 //              ([input neuron][sample-step], a warp-wide 32 x 32 bit transpose per block of spike words), written
 //              straight into the operand slot by the expander warps.
 //              Epilogue = LIF update (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b);
-//              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of __ballot_sync (lane = neuron); emits the
-//              fp32 voltage trace when training.
+//              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of a warp bit transpose (lane = neuron); emits the
+//              16-bit voltage-code trace (umma.cuh: volt_code) when training.
 //   NM_DX      A = hi/lo planes of W^T (K-major), B = hi/lo planes of g_c of the layer above (swz64 image with rows =
 //              sample-steps: K-major, one bulk copy per plane); three products hi*hi + lo*hi + hi*lo.  Epilogue = BPTT recurrence of
 //              SURVEY.md §8a for the layer below (surrogate gradient of PseudoSpikeRect, actor_critic.py:154-167).
@@ -65,9 +65,9 @@ struct NmParams {
   // FWD epilogue
   const float* bias;        // [MP]
   uint32_t* out_bits;       // [MP/32][Rt]
-  float* v_out;             // [MP/32][Rt/4][32 neurons][4 sample-steps] or null (inference)
+  uint16_t* v_out;          // voltage codes [MP/32][Rt/8][32 neurons][8 sample-steps] or null (inference)
   // DX epilogue
-  const float* v_in;        // [MP/32][Rt/4][32][4] voltages of the layer whose gradient is produced
+  const uint16_t* v_in;     // [MP/32][Rt/8][32][8] voltage codes of the layer whose gradient is produced
   uint8_t* g_img;           // 2 planes of the swz64 image [MP/64][Rt rows][128 B]
   size_t g_plane;
   float* db_part;           // [3 * ntile][MP]   (one row per batch tile and epilogue group: a fixed summation order
@@ -109,6 +109,16 @@ template <> struct NmCfg<NM_DX> {
   static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 512;
 };
 template <> struct NmCfg<NM_DX_ENC> : NmCfg<NM_DX> {};
+
+// the two bf16 halves of v to [addr] and [addr + 1024] (the same column of two rows 8 apart in a swz64 image)
+__device__ __forceinline__ void st_global_u16x2_rows(unsigned long long addr, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %1;\n\t"
+      "st.global.u16 [%0], lo;\n\t"
+      "st.global.u16 [%0+1024], hi;\n\t}" ::"l"(addr), "r"(v)
+      : "memory");
+}
 
 template <int MODE>
 __host__ __device__ constexpr size_t nm_gemm_smem_bytes() {      // dX kernels
@@ -443,20 +453,21 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
       if (by_set && aset != static_cast<uint32_t>(grp)) continue;
       const size_t c_tile = static_cast<size_t>(tile) * p.CT;      // first sample-step of the tile
       const int b_tile = tile * p.Bt;
-      if (MODE == NM_DX && lane < 16) {
-        // the scan below reads this warp's voltages (128 B per sample-step) from the HBM-resident trace: pull them
-        // into L2 while the tensor core is still busy with this item's MMAs (lane = sample-step within the group)
+      if (MODE == NM_DX && lane < 8) {
+        // the scan below reads this warp's voltage codes (64 B per sample-step, 1 KiB per 16-sample group and timestep)
+        // from the HBM-resident trace: pull them into L2 while the tensor core is still busy with this item's MMAs
+        // (lane = 128-byte line of the group).  Prefetching one tile further ahead changes nothing (profiles/r2i_dxab.txt).
         for (int bg = bg0; bg < nbg; bg += bgstep)
           for (int t = 0; t < p.T; ++t)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(
-                p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile + static_cast<size_t>(t * p.Bt + bg * 16 + lane)) * 32));
+                p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile + static_cast<size_t>(t * p.Bt + bg * 16 + lane * 2)) * 32));
       }
       SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
       const uint32_t t_set = t_lane + aset * 256;
       if (MODE == NM_DX) {
-        // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the loads of a step's fp32 voltages
-        // (one coalesced 128-byte row per sample-step and warp) run TWO steps ahead of the recurrence.
+        // BPTT scan, software-pipelined over (16-sample group, timestep) steps: the loads of a step's voltage codes
+        // (one contiguous 1 KiB block per 16 sample-steps and warp) run TWO steps ahead of the recurrence.
         // No validity masks: samples >= B have g_c == 0 in the layer above (the top scan writes zeros there), so
         // their accumulators are exactly 0, and with the zero initial state every g_c written here is 0 again.
         const int nb = bg0 < nbg ? (nbg - bg0 + bgstep - 1) / bgstep : 0;
@@ -468,23 +479,23 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         uint32_t xo[8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
-        const float4* const vcol = reinterpret_cast<const float4*>(p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32) + lane;
+        const uint4* const vcol = reinterpret_cast<const uint4*>(p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32) + lane;
         float gvn[16], gcn[16];
         // step s <-> (group index bi, timestep t): s = bi * T + (T - 1 - t); tracked incrementally (no divisions)
         int l_bi = 0, l_t = p.T - 1;          // cursor of the loads
         int s_bi = 0, s_t = p.T - 1;          // cursor of the recurrence
-        auto loadv = [&](float (&buf)[16]) {
+        auto loadv = [&](uint32_t (&buf)[8]) {
           if (l_bi < nb && !(SNN_DBG_MASK(p) & 32)) {
-            const float4* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 8;
+            const uint4* src = vcol + static_cast<size_t>(l_t * p.Bt + (bg0 + l_bi * bgstep) * 16) * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 q4 = __ldg(src + j * 32);
+            for (int j = 0; j < 2; ++j) {
+              const uint4 q4 = __ldg(src + j * 32);
               buf[4 * j] = q4.x; buf[4 * j + 1] = q4.y; buf[4 * j + 2] = q4.z; buf[4 * j + 3] = q4.w;
             }
           }
           if (--l_t < 0) { l_t = p.T - 1; ++l_bi; }
         };
-        auto step = [&](const float (&v)[16]) {
+        auto step = [&](const uint32_t (&v)[8]) {
           const int col0 = (bg0 + s_bi * bgstep) * 16;
           if (s_t == p.T - 1) {
 #pragma unroll
@@ -494,37 +505,40 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           tmem_ld16(t_set + static_cast<uint32_t>(s_t * p.Bt + col0), x);
           tmem_ld_wait();
           const size_t c = c_tile + static_cast<size_t>(s_t * p.Bt + col0);          // % 16 == 0
-          uint8_t* const dst = gcol + (c >> 3) * 1024;
-          float gc[16];
+          // The epilogue is bound by instruction issue (profiles/r2e: the warps are selected / not selected / in fixed-
+          // latency waits 3/4 of the time), so the store path is written for instruction count: rows c .. c + 15 of this
+          // neuron's chunk are two 1 KiB row groups; both plane bases are 1 KiB aligned (api.cu aligns the workspace), so
+          // the in-group offset xo[jj] is OR-ed into the low address word instead of a 64-bit add per store, and elements
+          // jj and jj + 8 (same xo, rows 8 apart) share one address and one bf16x2 conversion per plane.
+          const unsigned long long dst_hi = reinterpret_cast<unsigned long long>(gcol + (c >> 3) * 1024);
+          const unsigned long long dst_lo = dst_hi + p.g_plane;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float vj = v[j];
-            const float gs = __uint_as_float(x[j]) - gvn[j] * (0.75f * vj);
-            const float win = fabsf(__fsub_rn(vj, 0.5f)) < 0.5f ? 1.f : 0.f;
-            const float keep = vj > 0.5f ? 0.f : 0.75f;
-            const float gv = gs * win + gvn[j] * keep;
-            gc[j] = gv + 0.5f * gcn[j];
-            gvn[j] = gv;
-            gcn[j] = gc[j];
-            dbsum += gc[j];
-          }
-          if (!(SNN_DBG_MASK(p) & 16)) {
+          for (int jj = 0; jj < 8; ++jj) {
+            float gc2[2];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              // packed conversions: two sample-steps per cvt; hi = bf16(g_c), lo = bf16(g_c - hi)
-              const uint32_t hp = pack_bf16x2(gc[j], gc[j + 1]);
-              const uint32_t lp = pack_bf16x2(gc[j] - __uint_as_float(hp << 16), gc[j + 1] - __uint_as_float(hp & 0xFFFF0000u));
-              uint8_t* q0 = dst + (j >> 3) * 1024 + xo[j & 7];
-              uint8_t* q1 = dst + (j >> 3) * 1024 + xo[(j + 1) & 7];
-              *reinterpret_cast<uint16_t*>(q0) = static_cast<uint16_t>(hp);
-              *reinterpret_cast<uint16_t*>(q1) = static_cast<uint16_t>(hp >> 16);
-              *reinterpret_cast<uint16_t*>(q0 + p.g_plane) = static_cast<uint16_t>(lp);
-              *reinterpret_cast<uint16_t*>(q1 + p.g_plane) = static_cast<uint16_t>(lp >> 16);
+            for (int h = 0; h < 2; ++h) {
+              const int j = jj + 8 * h;
+              const float t = volt_t(v[j >> 1], j & 1);                            // voltage code (umma.cuh)
+              const float gs = __fmaf_rn(-gvn[j], volt_value75(t), __uint_as_float(x[j]));
+              const float win = volt_window(t) ? 1.f : 0.f;
+              const float keep = volt_spike(t) ? 0.f : 0.75f;
+              const float gv = __fmaf_rn(gvn[j], keep, gs * win);
+              gc2[h] = __fmaf_rn(0.5f, gcn[j], gv);
+              gvn[j] = gv;
+              gcn[j] = gc2[h];
+              dbsum += gc2[h];
+            }
+            if (!(SNN_DBG_MASK(p) & 16)) {
+              // hi = bf16(g_c), lo = bf16(g_c - hi)
+              const uint32_t hp = pack_bf16x2(gc2[0], gc2[1]);
+              const uint32_t lp = pack_bf16x2(gc2[0] - __uint_as_float(hp << 16), gc2[1] - __uint_as_float(hp & 0xFFFF0000u));
+              st_global_u16x2_rows(dst_hi | xo[jj], hp);
+              st_global_u16x2_rows(dst_lo | xo[jj], lp);
             }
           }
           if (--s_t < 0) { s_t = p.T - 1; ++s_bi; }
         };
-        float vb0[16] = {}, vb1[16] = {};
+        uint32_t vb0[8] = {}, vb1[8] = {};
         loadv(vb0); loadv(vb1);
         for (int sidx = 0; sidx < nsteps; sidx += 2) {
           step(vb0);
@@ -538,24 +552,29 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         const int nlive = p.B - (b_tile + col0);
         const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
         if (IS_FWD) {
-          float cur[16], vol[16];
+          // vst = 0.75-decayed part of the next step's voltage: v (1 - s).  The reset is applied when the spike is decided
+          // (one select on the predicate just computed) instead of testing the previous step's spike bit again
+          float cur[16], vst[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
-          uint32_t sprev = 0, spend = 0;
-          uint32_t x[16], xn[16];
-          tmem_ld16(t_set + static_cast<uint32_t>(col0), x);
-          tmem_ld_wait();
-          for (int t = 0; t < p.T; ++t) {
-            if (t + 1 < p.T) tmem_ld16(t_set + static_cast<uint32_t>((t + 1) * p.Bt + col0), xn);
+          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vst[j] = 0.f; }
+          uint32_t spend = 0;
+          // one LIF step on the accumulators of timestep t (16 samples of this neuron); the next step's accumulators are
+          // in flight while it runs (two register sets, ping-pong: no copies)
+          auto lif_step = [&](const uint32_t (&x)[16], int t) {
             uint32_t scur = 0;
+            float vol[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
+              // reference order (actor_critic.py:228-231): c = c * 0.5 + (Wx + b); v = v * 0.75 * (1 - s) + c.  c * 0.5 is
+              // exact, so the fused multiply-add rounds once like the reference's separate add; 0.75 * 0 + c == c exactly
               const float syn = __fadd_rn(__uint_as_float(x[j]), bias);
-              const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
-              const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
+              const float cj = __fmaf_rn(cur[j], 0.5f, syn);
+              const float vj = __fadd_rn(__fmul_rn(vst[j], 0.75f), cj);
+              const bool sp = vj > 0.5f;
               cur[j] = cj;
               vol[j] = vj;
-              scur |= (vj > 0.5f ? 1u : 0u) << j;
+              vst[j] = sp ? 0.f : vj;
+              scur |= (sp ? 1u : 0u) << j;
             }
             const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
             // spike words (bit = neuron of this warp, one word per sample-step): the thread holds a 16-bit mask over its
@@ -572,16 +591,28 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                     ((vmask >> (lane & 15)) & 1u) ? wd : 0u;
             }
             if (p.v_out != nullptr && !(SNN_DBG_MASK(p) & 128)) {
-              // [neuron / 32][sample-step / 4][32 neurons][4 sample-steps]: the thread's 16 sample-steps are four 16-byte
-              // pieces, the warp's 16 x 32 values one contiguous 2 KiB block (4 STG.128 instead of 16 STG.32)
-              float4* dst = reinterpret_cast<float4*>(p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32) + lane;
+              // 16-bit voltage codes (umma.cuh: volt_code), [neuron / 32][sample-step / 8][32 neurons][8 sample-steps]:
+              // the thread's 16 sample-steps are two 16-byte pieces, the warp's 16 x 32 codes one contiguous 1 KiB block
+              uint32_t cw[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j * 32] = make_float4(vol[4 * j], vol[4 * j + 1], vol[4 * j + 2], vol[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) cw[j] = __byte_perm(volt_code(vol[2 * j]), volt_code(vol[2 * j + 1]), 0x5410u);
+              uint4* dst = reinterpret_cast<uint4*>(p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32) + lane;
+              dst[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+              dst[32] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
             }
-            sprev = scur;
+          };
+          uint32_t xa[16], xb[16];
+          tmem_ld16(t_set + static_cast<uint32_t>(col0), xa);
+          tmem_ld_wait();
+          for (int t = 0; t < p.T; t += 2) {
+            if (t + 1 < p.T) tmem_ld16(t_set + static_cast<uint32_t>((t + 1) * p.Bt + col0), xb);
+            lif_step(xa, t);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = xn[j];
+            if (t + 1 < p.T) {
+              if (t + 2 < p.T) tmem_ld16(t_set + static_cast<uint32_t>((t + 2) * p.Bt + col0), xa);
+              lif_step(xb, t + 1);
+              tmem_ld_wait();
+            }
           }
         } else if (MODE == NM_DX) {
           // handled by the software-pipelined loop above

@@ -16,8 +16,10 @@
 //   * g_c (time-stepped bf16 hi/lo planes): swz64 image with rows = sample-steps r, columns = neurons — the K-major
 //     B operand of dX and the MN-major A operand of dW; the epilogue threads (= neurons) of a warp store 64
 //     contiguous bytes of one row.
-//   * voltages: fp32 [NP/32][Rt/4][32 neurons][4 sample-steps]: an epilogue thread (= neuron) reads / writes the 16
-//     sample-steps of a group as four 16-byte pieces, its warp (32 consecutive neurons) one contiguous 2 KiB block.
+//   * voltages: 16-bit codes (umma.cuh: volt_code — spike flag exact, surrogate-window flag exact up to its edge, the
+//     value inside the window to 2^-17) [NP/32][Rt/8][32 neurons][8 sample-steps]: an epilogue thread (= neuron) reads /
+//     writes the 16 sample-steps of a group as two 16-byte pieces, its warp (32 consecutive neurons) one contiguous 1 KiB
+//     block.
 //   * the dense critic keeps plain rows r = b, Bpad = roundup(B, 128).
 #pragma once
 #include <cstddef>
@@ -49,7 +51,7 @@ struct LayerPlan {
   size_t wt_plane;
   size_t bias_pad;   // packed: fp32 bias padded to NP
   size_t tr_bits;    // trace: output spike words [NP/32][Rt]
-  size_t tr_volt;    // trace: fp32 voltages [NP/32][Rt/4][32][4]
+  size_t tr_volt;    // trace: 16-bit voltage codes [NP/32][Rt/8][32][8]
 };
 
 struct SnnPlan {
@@ -143,7 +145,7 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.tr_enc_bits = take(static_cast<size_t>(p.K0P / 32) * p.Rt * 4);
   for (int l = 0; l < p.L; ++l) p.layer[l].tr_bits = take(static_cast<size_t>(p.layer[l].NP / 32) * p.Rt * 4);
   p.ws_fwd_bytes = off;
-  for (int l = 0; l < p.L; ++l) p.layer[l].tr_volt = take(static_cast<size_t>(p.Rt) * p.layer[l].NP * 4);
+  for (int l = 0; l < p.L; ++l) p.layer[l].tr_volt = take(static_cast<size_t>(p.Rt) * p.layer[l].NP * 2);
   p.trace_bytes = off;
   // backward workspace
   off = 0;
@@ -180,7 +182,8 @@ inline int make_plan(const SnnDesc& d, int64_t B, int num_sms, SnnPlan* out) {
   p.ws_red_bytes = 3 * ((static_cast<size_t>(p.ntile) * (p.Bt / 8) + 255) / 256) * p.layer[p.L - 1].NP * 4 +
                    ((row_parts + 255) / 256) * red_cols * 4 + 4096;
   p.ws_red = take(p.ws_red_bytes);
-  p.ws_bwd_bytes = off;
+  p.ws_bwd_bytes = off + 1024;      // slack: snn_bwd aligns the caller's pointer up to 1 KiB (the dX epilogue ORs in-row-group
+                                    // offsets into the g_c plane addresses)
   *out = p;
   return SNN_OK;
 }

@@ -279,7 +279,7 @@ constexpr int kTopRowsSPB = 8;       // Bt % 16 == 0: the samples of a block lie
 template <int TT>
 __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const float* __restrict__ g_mu, const float* __restrict__ mu,
                                                            int dec_tanh, const float* __restrict__ dec_w,
-                                                           const float* __restrict__ volt, int B, TileGeom tg, int A,
+                                                           const uint16_t* __restrict__ volt, int B, TileGeom tg, int A,
                                                            int P, int NP, int T, uint8_t* __restrict__ g_img,
                                                            size_t g_plane, float* __restrict__ db_part /* [gridDim.x][NP] */,
                                                            float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
@@ -311,9 +311,10 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     gup1 = __fdiv_rn(G1 * dec_w[n0 + 1], Tf);
   }
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
-  // voltage trace [NP/32][Rt/4][32 neurons][4 sample-steps]; Bt % 16 == 0, so every timestep's row has r0's phase r0 % 4
-  const float* vsrc = volt + ((static_cast<size_t>(n0 >> 5) * tg.Rt + (r0 & ~static_cast<size_t>(3))) * 32) + (n0 & 31) * 4 + (r0 & 3);
-  const size_t vstep = static_cast<size_t>(tg.Bt) * 32;        // floats between timesteps
+  // voltage codes (umma.cuh: volt_code) [NP/32][Rt/8][32 neurons][8 sample-steps]; Bt % 16 == 0, so every timestep's
+  // row has r0's phase r0 % 8.  The 8 warps of a block are 8 consecutive samples: together they read whole 16-byte pieces.
+  const uint16_t* vsrc = volt + ((static_cast<size_t>(n0 >> 5) * tg.Rt + (r0 & ~static_cast<size_t>(7))) * 32) + (n0 & 31) * 8 + (r0 & 7);
+  const size_t vstep = static_cast<size_t>(tg.Bt) * 32;        // codes between timesteps
   const uint32_t piece = static_cast<uint32_t>(lane >> 2);
   // Bt % 16 == 0: every timestep's row r0 + t * Bt has the swizzle phase of r0, so the in-row offset is a constant
   uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4 +
@@ -321,13 +322,13 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   const size_t gstep = static_cast<size_t>(tg.Bt) * 128;
   float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, db0 = 0.f, db1 = 0.f;
   int cnt0 = 0, cnt1 = 0;
-  auto step = [&](int t, float2 v) {
-    const float v0 = live ? v.x : 0.f, v1 = live ? v.y : 0.f;
-    cnt0 += v0 > 0.5f ? 1 : 0;
-    cnt1 += v1 > 0.5f ? 1 : 0;
-    const float gs0 = gup0 - gvn0 * (0.75f * v0), gs1 = gup1 - gvn1 * (0.75f * v1);
-    const float win0 = fabsf(__fsub_rn(v0, 0.5f)) < 0.5f ? 1.f : 0.f, win1 = fabsf(__fsub_rn(v1, 0.5f)) < 0.5f ? 1.f : 0.f;
-    const float gv0 = gs0 * win0 + gvn0 * (v0 > 0.5f ? 0.f : 0.75f), gv1 = gs1 * win1 + gvn1 * (v1 > 0.5f ? 0.f : 0.75f);
+  auto step = [&](int t, uint2 v) {
+    const float c0 = volt_t(live ? v.x : 0u, 0), c1 = volt_t(live ? v.y : 0u, 0);      // voltage codes (umma.cuh)
+    cnt0 += volt_spike(c0) ? 1 : 0;
+    cnt1 += volt_spike(c1) ? 1 : 0;
+    const float gs0 = gup0 - gvn0 * volt_value75(c0), gs1 = gup1 - gvn1 * volt_value75(c1);
+    const float win0 = volt_window(c0) ? 1.f : 0.f, win1 = volt_window(c1) ? 1.f : 0.f;
+    const float gv0 = gs0 * win0 + gvn0 * (volt_spike(c0) ? 0.f : 0.75f), gv1 = gs1 * win1 + gvn1 * (volt_spike(c1) ? 0.f : 0.75f);
     const float gc0 = gv0 + 0.5f * gcn0, gc1 = gv1 + 0.5f * gcn1;
     gvn0 = gv0; gvn1 = gv1; gcn0 = gc0; gcn1 = gc1;
     db0 += gc0; db1 += gc1;
@@ -338,17 +339,17 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     *reinterpret_cast<uint32_t*>(q + g_plane) = lp;
   };
   if (TT > 0) {
-    float2 v[TT > 0 ? TT : 1];
+    uint2 v[TT > 0 ? TT : 1];
 #pragma unroll
     for (int t = 0; t < TT; ++t)                                                           // all loads up front
-      v[t] = make_float2(__ldg(vsrc + static_cast<size_t>(t) * vstep), __ldg(vsrc + static_cast<size_t>(t) * vstep + 4));
+      v[t] = make_uint2(__ldg(vsrc + static_cast<size_t>(t) * vstep), __ldg(vsrc + static_cast<size_t>(t) * vstep + 8));
 #pragma unroll
     for (int t = TT - 1; t >= 0; --t) step(t, v[t]);
   } else {
-    float2 vn = make_float2(__ldg(vsrc + static_cast<size_t>(T - 1) * vstep), __ldg(vsrc + static_cast<size_t>(T - 1) * vstep + 4));
+    uint2 vn = make_uint2(__ldg(vsrc + static_cast<size_t>(T - 1) * vstep), __ldg(vsrc + static_cast<size_t>(T - 1) * vstep + 8));
     for (int t = T - 1; t >= 0; --t) {
-      const float2 v = vn;
-      if (t > 0) vn = make_float2(__ldg(vsrc + static_cast<size_t>(t - 1) * vstep), __ldg(vsrc + static_cast<size_t>(t - 1) * vstep + 4));
+      const uint2 v = vn;
+      if (t > 0) vn = make_uint2(__ldg(vsrc + static_cast<size_t>(t - 1) * vstep), __ldg(vsrc + static_cast<size_t>(t - 1) * vstep + 8));
       step(t, v);
     }
   }

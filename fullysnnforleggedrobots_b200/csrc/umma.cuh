@@ -202,6 +202,36 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   }
   return x;
 }
+// ------------------------------------------------------------------ 16-bit voltage trace
+// The backward pass uses a membrane voltage v in exactly three ways (actor_critic.py:154-167, 228-231): the spike flag
+// v > 0.5, the surrogate window |v - 0.5| < 0.5, and — only inside that window — the value of v in the reset term.  The
+// trace therefore keeps a 16-bit code per (neuron, sample-step) instead of the fp32 voltage:
+//   k = ceil(65534 v) saturated to [0, 65535]
+//   k == 0          v <= 0: below the window, no spike
+//   k == 65535      v > 1: above the window, spike
+//   1 <= k <= 65534 inside the window; k > 32767 <=> v > 0.5 EXACTLY (0.5 * 65534 is an integer and the rounding of the
+//                   product is monotone); decoded as (k - 0.5) / 65534: |error| <= 2^-17.
+// The spike flag is exact; the window flag is exact except for v == 1.0f and 0 < v < 2^-25 (where fp32 rounds v - 0.5 to
+// -0.5): both sit on the window's edge, where the surrogate is discontinuous anyway.  Half the bytes of an fp32 trace.
+constexpr float kVoltScale = 65534.f;
+constexpr float kVoltInv = 1.f / 65534.f;
+// All on the fp32 pipe: clamp to [0, 65535 / 65534], then 2^23 + ceil(65534 v) by ONE fused multiply-add rounded towards
+// +inf (exact product, no double rounding).  Returns the float whose low 16 bits are the code (the caller packs two of
+// them with one byte permute).  The saturating conversion cvt.rpi.u16.f32 gives the same codes but runs on the
+// quarter-rate conversion pipe: forward layer 1 59.9 vs 57.8 us (profiles/r2k_encab.txt).
+__device__ __forceinline__ uint32_t volt_code(float v) {
+  const float vc = fminf(fmaxf(v, 0.f), 65535.f / 65534.f);
+  return __float_as_uint(__fmaf_ru(vc, kVoltScale, 8388608.f));
+}
+// the code as a float t in [0, 65535]: bytes {k.lo, k.hi, 0x00, 0x4B} are the float 2^23 + k (one byte permute)
+__device__ __forceinline__ float volt_t(uint32_t word, int upper) {
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, upper ? 0x7632u : 0x7610u)) - 8388608.f;
+}
+__device__ __forceinline__ float volt_value(float t) { return __fmaf_rn(t, kVoltInv, -0.5f * kVoltInv); }           // v inside the window
+__device__ __forceinline__ float volt_value75(float t) { return __fmaf_rn(t, 0.75f * kVoltInv, -0.375f * kVoltInv); }  // 0.75 v
+__device__ __forceinline__ bool volt_spike(float t) { return t > 32767.f; }
+__device__ __forceinline__ bool volt_window(float t) { return fabsf(t - 32767.5f) < 32767.f; }      // 1 <= k <= 65534
+
 __device__ __forceinline__ float bf16_round(float x) {   // value of bf16(x) as fp32
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));

@@ -3,7 +3,7 @@
 Buffers (all torch-allocated, caller-owned from the library's point of view):
   packed   bf16 hi/mid/lo plane images of every layer's W and W^T (re-packed when parameters change)
   ws_fwd   bit-packed spike trains of one inference call
-  trace    spike bits + fp32 voltage traces of one training forward (lives until its backward)
+  trace    spike bits + 16-bit voltage-code traces of one training forward (lives until its backward)
   ws_bwd   g_c plane images, split-K partials, small reduction scratch
 """
 from __future__ import annotations
@@ -255,10 +255,16 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace layout: [NP / 32][Rt / 4][32 neurons][4 sample-steps]
-            v = raw[voff: voff + Rt * NP * 4].view(torch.float32).reshape(NP // 32, Rt // 4, 32, 4)
-            v = v.permute(0, 1, 3, 2).reshape(NP // 32, Rt, 32)[:, col]               # [NP / 32, T, rows, 32]
-            res["volt"].append(v.permute(1, 2, 0, 3).reshape(T, -1, NP)[:, :, :self.dims[l + 1]].contiguous())
+            # voltage trace: 16-bit codes [NP / 32][Rt / 8][32 neurons][8 sample-steps] (csrc/umma.cuh: volt_code).
+            # 0 = below the surrogate window (decoded 0.0), 0xFFFF = above it (decoded 1.0), k in 1..65534 = inside,
+            # v = (k - 0.5) / 65534 to 2^-17 — the value the backward kernels use.
+            c = raw[voff: voff + Rt * NP * 2].view(torch.int16).reshape(NP // 32, Rt // 8, 32, 8)
+            c = c.permute(0, 1, 3, 2).reshape(NP // 32, Rt, 32)[:, col]               # [NP / 32, T, rows, 32]
+            c = c.permute(1, 2, 0, 3).reshape(T, -1, NP)[:, :, :self.dims[l + 1]].to(torch.int32) & 0xFFFF
+            v = (c.to(torch.float32) - 0.5) * (1.0 / 65534.0)
+            v = torch.where(c == 0, torch.zeros_like(v), torch.where(c == 0xFFFF, torch.ones_like(v), v))
+            res["volt"].append(v.contiguous())
+            res.setdefault("volt_code", []).append(c.contiguous())
         return res
 
 
