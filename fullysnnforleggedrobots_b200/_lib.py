@@ -44,6 +44,12 @@ class SnnGrads(C.Structure):
                 ("dec_w", C.c_void_p), ("dec_b", C.c_void_p), ("obs", C.c_void_p)]
 
 
+class SnnPpoActorHead(C.Structure):
+    _fields_ = [("log_std", C.c_void_p), ("actions", C.c_void_p), ("old_logp", C.c_void_p), ("adv", C.c_void_p),
+                ("old_mu", C.c_void_p), ("old_sigma", C.c_void_p), ("clip", C.c_float), ("mu_out", C.c_void_p),
+                ("g_mu_out", C.c_void_p), ("part", C.c_void_p), ("part_bytes", C.c_size_t)]
+
+
 class SnnMlpDesc(C.Structure):
     _fields_ = [("in_dim", C.c_int32), ("num_hidden", C.c_int32), ("hidden", C.c_int32 * SNN_MAX_LAYERS),
                 ("out_dim", C.c_int32)]
@@ -113,6 +119,15 @@ _SIGS = {
     "snn_bwd": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64,
                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SnnGrads), C.c_void_p, C.c_size_t,
                           C.c_void_p]),
+    "snn_ppo_head_part_bytes": (C.c_size_t, [C.POINTER(SnnDesc), C.c_int64]),
+    "snn_bwd_ppo_top": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.POINTER(SnnPpoActorHead), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_bwd_rest": (C.c_int, [C.POINTER(SnnDesc), C.POINTER(SnnParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                               C.POINTER(SnnGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_ppo_value_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snn_ppo_finalize": (C.c_int, [C.POINTER(SnnDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float,
                           C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "snn_gather_rows": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
@@ -137,6 +152,8 @@ _SIGS = {
     "snn_lr_adapt": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "snn_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2 + [C.c_float] * 4
                       + [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snn_clip_adam_kl": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2 + [C.c_float] * 4
+                         + [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_mse_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

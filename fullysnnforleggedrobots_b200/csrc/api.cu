@@ -73,6 +73,7 @@ struct DeviceInfo {
   int num_sms = 0;
   int attrs_set = 0;
   int* sched = nullptr;      // this device's instance of g_sched_slots
+  int* count = nullptr;      // ... of g_count_slots
 };
 
 // Tile-scheduler counters of the persistent scan-GEMM kernels (nm_gemm.cuh): zero at module load, and every kernel leaves
@@ -82,6 +83,12 @@ struct DeviceInfo {
 constexpr int kSchedSlots = 64;
 __device__ int g_sched_slots[kSchedSlots * kSchedInts];
 unsigned g_sched_next = 0;
+// A second pool with the same contract (zero at load, left zeroed by every user) for the SIMT kernels that count blocks:
+// the per-job "last block" counters of multi_reduce_kernel and the grid barrier of adam_fused_kernel.  Separate from the
+// scheduler slots so that a reduction of the critic's stream never shares a slot with an actor kernel running next to it.
+constexpr int kCountInts = 16;
+__device__ int g_count_slots[kSchedSlots * kCountInts];
+unsigned g_count_next = 0;
 DeviceInfo g_dev[64];
 
 int device_ready(int* num_sms) {
@@ -116,6 +123,8 @@ int device_ready(int* num_sms) {
     void* sp = nullptr;
     CUDA_TRY(cudaGetSymbolAddress(&sp, g_sched_slots));
     di.sched = static_cast<int*>(sp);
+    CUDA_TRY(cudaGetSymbolAddress(&sp, g_count_slots));
+    di.count = static_cast<int*>(sp);
     di.attrs_set = 1;
   }
   *num_sms = di.num_sms;
@@ -156,58 +165,43 @@ int debug_mask() {
 #endif
 }
 
-constexpr int kRowSeg = 256;          // rows per segment of the pre-pass (8 loads in flight per thread, one round)
+constexpr int kRowSeg = 256;          // rows per segment of the two-level row reductions (8 loads in flight per thread, one round)
+int* count_slot();
 struct Deferred {
-  RowJobs rows{}, pre{};
-  PartJobs parts{};
-  int max_n = 0, max_K = 0, max_N = 0, pre_max_n = 0, pre_max_seg = 0;
-  float* scratch = nullptr;      // optional: lets jobs with many partial rows go through a segmented pre-pass
+  ReduceJobs jobs{};
+  int max_cols = 0, max_z = 1;
+  float* scratch = nullptr;      // optional: lets jobs with many partial rows be reduced in two levels
   size_t scratch_floats = 0, scratch_used = 0;
   void row(const float* src, int nparts, size_t stride, int n, float* dst, int col_step = 1) {
     const int width = (n - 1) * col_step + 1;
     const int nseg = (nparts + kRowSeg - 1) / kRowSeg;
-    if (nparts > 2 * kRowSeg && scratch != nullptr && scratch_used + static_cast<size_t>(nseg) * width <= scratch_floats &&
-        pre.count < 12) {
-      float* tmp = scratch + scratch_used;
+    RowJob jb{src, dst, nullptr, nparts, n, col_step, 1, nparts, width, static_cast<unsigned long long>(stride)};
+    int cols = n;
+    if (nparts > 2 * kRowSeg && scratch != nullptr && scratch_used + static_cast<size_t>(nseg) * width <= scratch_floats) {
+      jb.tmp = scratch + scratch_used;
       scratch_used += static_cast<size_t>(nseg) * width;
-      pre.j[pre.count++] = RowJob{src, tmp, nparts, width, static_cast<unsigned long long>(stride), 1, kRowSeg,
-                                  static_cast<unsigned long long>(width)};
-      if (width > pre_max_n) pre_max_n = width;
-      if (nseg > pre_max_seg) pre_max_seg = nseg;
-      src = tmp; nparts = nseg; stride = static_cast<size_t>(width);
+      jb.nseg = nseg; jb.seg_rows = kRowSeg;
+      cols = width;
+      if (nseg > max_z) max_z = nseg;
     }
-    rows.j[rows.count++] = RowJob{src, dst, nparts, n, static_cast<unsigned long long>(stride), col_step, 0, 0ull};
-    if (n > max_n) max_n = n;
+    jobs.r[jobs.nr++] = jb;
+    if (cols > max_cols) max_cols = cols;
   }
   void part(const float* partial, int splits, int n_tiles, int N, int K, float* dW) {
-    parts.j[parts.count++] = PartJob{partial, dW, splits, n_tiles, N, K};
-    if (K > max_K) max_K = K;
-    if (N > max_N) max_N = N;
+    jobs.p[jobs.np++] = PartJob{partial, dW, splits, n_tiles, N, K};
+    if (K > max_cols) max_cols = K;
+    if ((N + 31) / 32 > max_z) max_z = (N + 31) / 32;
   }
 };
 
-int launch_deferred(const Deferred& df, cudaStream_t st) {
-  if (df.parts.count > 0) {
-    dim3 grd((df.max_K + 127) / 128, df.max_N, df.parts.count);
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    multi_reduce_partials_kernel<<<grd, 128, 0, st>>>(df.parts);
-    }
-    LAUNCH_CHECK("multi_reduce_partials_kernel");
+int launch_deferred(Deferred& df, cudaStream_t st) {
+  if (df.jobs.nr + df.jobs.np == 0) return SNN_OK;
+  df.jobs.counters = count_slot();      // one zero-initialised, self-re-arming counter per row job (<= 12 of kCountInts)
+  dim3 grd((df.max_cols + 31) / 32, df.jobs.nr + df.jobs.np, df.max_z);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  multi_reduce_kernel<<<grd, dim3(32, 32), 0, st>>>(df.jobs);
   }
-  if (df.pre.count > 0) {
-    dim3 grd((df.pre_max_n + 31) / 32, df.pre.count, df.pre_max_seg);
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    multi_reduce_rows_kernel<<<grd, dim3(32, 32), 0, st>>>(df.pre);
-    }
-    LAUNCH_CHECK("multi_reduce_rows_kernel (segments)");
-  }
-  if (df.rows.count > 0) {
-    dim3 grd((df.max_n + 31) / 32, df.rows.count);
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    multi_reduce_rows_kernel<<<grd, dim3(32, 32), 0, st>>>(df.rows);
-    }
-    LAUNCH_CHECK("multi_reduce_rows_kernel");
-  }
+  LAUNCH_CHECK("multi_reduce_kernel");
   return SNN_OK;
 }
 
@@ -226,6 +220,12 @@ int* sched_slot() {      // device_ready() has run on the current device
   int dev = 0;
   cudaGetDevice(&dev);
   return g_dev[dev].sched + static_cast<size_t>(g_sched_next++ % kSchedSlots) * kSchedInts;
+}
+
+int* count_slot() {      // device_ready() has run on the current device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev[dev].count + static_cast<size_t>(g_count_next++ % kSchedSlots) * kCountInts;
 }
 
 void nm_geometry(const SnnPlan& p, int64_t B, NmParams* q) {
@@ -273,7 +273,7 @@ int forward(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     LAUNCH_CHECK("nm_gemm_kernel<FWD>");
     in_bits = q.out_bits;
   }
-  {
+  if (mu != nullptr) {      // training forward of the fused PPO step: the decoder runs inside actor_head_kernel (snn_bwd_ppo_top)
     const int n = static_cast<int>(B) * p.A;
     { ProfScope prof__(CAT_OTHER, 0.0, st);
     decode_kernel<<<(n + 255) / 256, 256, 0, st>>>(in_bits, tg, static_cast<int>(B), p.A, p.Pd, p.T, prm->dec_w, prm->dec_b,
@@ -464,20 +464,28 @@ int snn_fwd_train(const SnnDesc* d, const SnnParams* prm, const void* packed, co
   if (rc) return rc;
   SnnPlan p;
   if ((rc = plan_for(d, B, sms, &p))) return rc;
-  if (!prm || !packed || !obs || !mu || !trace) return fail(SNN_EINVAL, "null pointer");
+  if (!prm || !packed || !obs || !trace) return fail(SNN_EINVAL, "null pointer");      // mu == NULL: no decoder pass
   if (trace_bytes < p.trace_bytes) return fail(SNN_ENOMEM, "trace buffer too small");
   return forward(d, prm, packed, obs, B, mu, trace, trace, p, sms, static_cast<cudaStream_t>(stream));
 }
 
-int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, const float* mu,
-            const float* g_mu, const void* trace, const SnnGrads* g, void* workspace, size_t workspace_bytes,
-            void* stream) {
+}  // extern "C"
+
+namespace {
+// stages: 1 = the output layer's scan (top_scan_rows_kernel on a given g_mu, preceded by actor_head_kernel when `head` carries the
+// PPO actor head's inputs), 2 = everything below it + dW + the deferred reductions.  snn_bwd runs both; the fused PPO step
+// calls them separately so that the caller can fork its finalize off between them.
+int backward_impl(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, const float* mu,
+                  const float* g_mu, const SnnPpoActorHead* head, int stages, const void* trace, const SnnGrads* g,
+                  void* workspace, size_t workspace_bytes, void* stream) {
   int sms = 0;
   int rc = device_ready(&sms);
   if (rc) return rc;
   SnnPlan p;
   if ((rc = plan_for(d, B, sms, &p))) return rc;
-  if (!prm || !packed || !obs || !mu || !g_mu || !trace || !g || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if (!prm || !packed || !obs || !trace || !workspace) return fail(SNN_EINVAL, "null pointer");
+  if ((stages & 2) && !g) return fail(SNN_EINVAL, "null gradient struct");
+  if ((stages & 1) && head == nullptr && (!mu || !g_mu)) return fail(SNN_EINVAL, "null pointer");
   if (workspace_bytes < p.ws_bwd_bytes) return fail(SNN_ENOMEM, "workspace too small");
   if (B == 0) return fail(SNN_EINVAL, "empty batch has no gradient");
   // every region of the plan is a multiple of 1 KiB from the base: make the base itself 1 KiB aligned (ws_bwd_bytes
@@ -498,20 +506,49 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
 
   // ---- output population layer: scan with g_up from the decoder (also yields the decoder's gradients)
   const int top = p.L - 1;
+  if (stages & 1) {
+    const LayerPlan& lp = p.layer[top];
+    const int nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
+    const uint16_t* volt = reinterpret_cast<const uint16_t*>(at(trace, lp.tr_volt));
+    if (head != nullptr) {
+      // decoder + policy terms of the PPO head (actor_head_kernel) write mu and d loss / d mu; the scan follows directly
+      if (p.A > 64) return fail(SNN_EINVAL, "snn_bwd_ppo_top: act_dim <= 64");
+      if (!head->log_std || !head->actions || !head->old_logp || !head->adv || !head->old_mu || !head->old_sigma || !head->part ||
+          !head->mu_out || !head->g_mu_out)
+        return fail(SNN_EINVAL, "snn_bwd_ppo_top: null head pointer");
+      const int hblk = static_cast<int>((B + kHeadSPB - 1) / kHeadSPB);
+      if (head->part_bytes < static_cast<size_t>(hblk) * (4 + p.A) * 4) return fail(SNN_ENOMEM, "snn_bwd_ppo_top: part buffer too small");
+      ActorHeadParams q{};
+      q.bits = reinterpret_cast<const uint32_t*>(at(trace, lp.tr_bits));
+      q.dec_w = prm->dec_w; q.dec_b = prm->dec_b; q.dec_tanh = d->dec_tanh;
+      q.log_std = head->log_std; q.actions = head->actions; q.old_logp = head->old_logp; q.adv = head->adv;
+      q.old_mu = head->old_mu; q.old_sigma = head->old_sigma; q.clip = head->clip; q.inv_count = 1.0f / static_cast<float>(B);
+      q.mu = head->mu_out; q.g_mu = head->g_mu_out; q.part = head->part;
+      q.B = Bi; q.A = p.A; q.P = p.Pd; q.T = p.T; q.tg = tg;
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
+      actor_head_kernel<<<hblk, 256, 0, st>>>(q);
+      }
+      LAUNCH_CHECK("actor_head_kernel");
+      mu = head->mu_out;
+      g_mu = head->g_mu_out;
+    }
+    {
+      { ProfScope prof__(CAT_OTHER, 0.0, st);
+      const dim3 grd(nrows, lp.NP / 64);
+      if (p.T == 5)
+        top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+      else
+        top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+      }
+      LAUNCH_CHECK("top_scan_rows_kernel");
+    }
+  }
+  if (!(stages & 2)) return SNN_OK;
   {
     const LayerPlan& lp = p.layer[top];
     const int nrows = static_cast<int>(p.Bcap / kTopRowsSPB);
-    { ProfScope prof__(CAT_OTHER, 0.0, st);
-    const uint16_t* volt = reinterpret_cast<const uint16_t*>(at(trace, lp.tr_volt));
-    const dim3 grd(nrows, lp.NP / 64);
-    if (p.T == 5)
-      top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                  at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
-    else
-      top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                  at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
-    }
-    LAUNCH_CHECK("top_scan_rows_kernel");
     df.row(dbpart_of(top), nrows, lp.NP, lp.N, g->bias[top]);
     df.row(small, nrows, 2 * static_cast<size_t>(lp.NP), p.A * p.Pd, g->dec_w);
     df.row(small + lp.NP, nrows, 2 * static_cast<size_t>(lp.NP), p.A, g->dec_b, p.Pd);
@@ -601,6 +638,67 @@ int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const fl
     }
   }
   return launch_deferred(df, st);
+}
+}  // namespace
+
+extern "C" {
+
+int snn_bwd(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, const float* mu,
+            const float* g_mu, const void* trace, const SnnGrads* g, void* workspace, size_t workspace_bytes,
+            void* stream) {
+  if (!mu || !g_mu || !g) return fail(SNN_EINVAL, "null pointer");
+  return backward_impl(d, prm, packed, obs, B, mu, g_mu, nullptr, 3, trace, g, workspace, workspace_bytes, stream);
+}
+
+int snn_bwd_ppo_top(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B,
+                    const SnnPpoActorHead* head, const void* trace, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!head) return fail(SNN_EINVAL, "null pointer");
+  return backward_impl(d, prm, packed, obs, B, nullptr, nullptr, head, 1, trace, nullptr, workspace, workspace_bytes, stream);
+}
+
+int snn_bwd_rest(const SnnDesc* d, const SnnParams* prm, const void* packed, const float* obs, int64_t B, const void* trace,
+                 const SnnGrads* g, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g) return fail(SNN_EINVAL, "null pointer");
+  return backward_impl(d, prm, packed, obs, B, nullptr, nullptr, nullptr, 2, trace, g, workspace, workspace_bytes, stream);
+}
+
+int snn_ppo_value_loss(const float* value, const float* returns, const float* target_v, int64_t B, float clip, float value_coef,
+                       int clipped_value, float* g_value, void* part, size_t part_bytes, void* stream) {
+  if (!value || !returns || !target_v || !g_value || !part) return fail(SNN_EINVAL, "null pointer");
+  if (B <= 0) return fail(SNN_EINVAL, "empty batch");
+  const int nblk = static_cast<int>((B + 255) / 256);
+  if (part_bytes < static_cast<size_t>(nblk) * 4) return fail(SNN_ENOMEM, "value-loss part buffer too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  value_loss_kernel<<<nblk, 256, 0, st>>>(value, returns, target_v, static_cast<int>(B), clip, value_coef, clipped_value,
+                                          1.0f / static_cast<float>(B), g_value, static_cast<float*>(part));
+  }
+  LAUNCH_CHECK("value_loss_kernel");
+  return SNN_OK;
+}
+
+size_t snn_ppo_head_part_bytes(const SnnDesc* d, int64_t B) {
+  SnnPlan p;
+  if (d == nullptr || B <= 0 || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return 0;
+  return static_cast<size_t>((B + kHeadSPB - 1) / kHeadSPB) * (4 + p.A) * 4;
+}
+
+int snn_ppo_finalize(const SnnDesc* d, int64_t B, const void* head_part, const void* value_part, const float* log_std,
+                     float ent_coef, float* g_log_std, float* stats, float* kl_out, void* stream) {
+  if (!head_part || !value_part || !log_std || !g_log_std || !stats) return fail(SNN_EINVAL, "null pointer");
+  SnnPlan p;
+  if (d == nullptr || B <= 0 || make_plan(*d, B, plan_sms(), &p) != SNN_OK) return fail(SNN_EINVAL, "bad descriptor / batch");
+  const int A = p.A;
+  if (A > kHeadMaxA) return fail(SNN_EINVAL, "act_dim <= 64");
+  // rows of head_part: one per block of actor_head_kernel (kHeadSPB samples); rows of value_part: one per 256 samples
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  ppo_finalize_kernel<<<1, 1024, 0, st>>>(
+      static_cast<const float*>(head_part), static_cast<int>((B + kHeadSPB - 1) / kHeadSPB), static_cast<const float*>(value_part),
+      static_cast<int>((B + 255) / 256), A, static_cast<int>(B), log_std, ent_coef, 1.0f, g_log_std, stats, kl_out);
+  }
+  LAUNCH_CHECK("ppo_finalize_kernel");
+  return SNN_OK;
 }
 
 int snn_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, int64_t S,
@@ -943,25 +1041,33 @@ int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, v
   return SNN_OK;
 }
 
+int snn_clip_adam_kl(float* params, const float* grads, float* m, float* v, int64_t n, float* lr, int* step,
+                     double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                     const float* kl, float kl_scale, float desired_kl, float* norm_out, void* scratch, void* stream) {
+  if (!params || !grads || !m || !v || !lr || !step || !scratch) return fail(SNN_EINVAL, "null pointer");
+  if (n <= 0) return fail(SNN_EINVAL, "empty parameter buffer");
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // at most one block per SM: every block is resident, which the kernel's grid barrier relies on
+  int nb = static_cast<int>((n + 256 * 8 - 1) / (256 * 8));
+  if (nb > sms) nb = sms;
+  if (nb > kAdamCoefs) nb = kAdamCoefs;
+  float* partial = static_cast<float*>(scratch);     // <= 384 partial sums + Adam's two step coefficients at kAdamCoefs
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  adam_fused_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, partial, step, lr, kl, kl_scale, desired_kl, beta1, beta2,
+                                        eps, weight_decay, max_norm, grad_scale, norm_out, count_slot());
+  }
+  LAUNCH_CHECK("adam_fused_kernel");
+  return SNN_OK;
+}
+
 int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
                   double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream) {
-  if (!params || !grads || !m || !v || !lr || !step || !scratch) return fail(SNN_EINVAL, "null pointer");
-  if (n <= 0) return fail(SNN_EINVAL, "empty parameter buffer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int nb = static_cast<int>((n + 256 * 8 - 1) / (256 * 8));
-  if (nb > 296) nb = 296;
-  float* partial = static_cast<float*>(scratch);     // 296 partial sums + Adam's two step coefficients at kAdamCoefs
-  { ProfScope prof__(CAT_OTHER, 0.0, st);
-  sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, grad_scale, partial, step, lr, beta1, beta2);
-  }
-  LAUNCH_CHECK("sumsq_kernel");
-  { ProfScope prof__(CAT_OTHER, 0.0, st);
-  clip_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, partial, nb, beta1, beta2, eps, weight_decay,
-                                       max_norm, grad_scale, norm_out);
-  }
-  LAUNCH_CHECK("clip_adam_kernel");
-  return SNN_OK;
+  return snn_clip_adam_kl(params, grads, m, v, n, const_cast<float*>(lr), step, beta1, beta2, eps, weight_decay, max_norm,
+                          grad_scale, nullptr, 0.f, 0.f, norm_out, scratch, stream);
 }
 
 int snn_mse_grad(const float* pred, const float* target, int64_t n, float* g, float* loss_accum, void* scratch,

@@ -480,7 +480,10 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) xo[jj] = static_cast<uint32_t>(jj * 128 + ((((n & 63) >> 3) ^ jj) << 4) + (n & 7) * 2);
         const uint4* const vcol = reinterpret_cast<const uint4*>(p.v_in + (static_cast<size_t>(n >> 5) * p.Rt + c_tile) * 32) + lane;
-        float gvn[16], gcn[16];
+        // state of the recurrence as packed pairs of neighbouring sample-steps (2 i, 2 i + 1): FFMA2 / FADD2 / FMUL2
+        f32x2 gvn[8], gcn[8], db2 = 0ull;
+        const f32x2 k_nc75 = f2_splat(-0.75f * kVoltInv), k_o75 = f2_splat(0.375f * kVoltInv), k_half = f2_splat(0.5f),
+                    k_mid = f2_splat(-32767.5f);
         // step s <-> (group index bi, timestep t): s = bi * T + (T - 1 - t); tracked incrementally (no divisions)
         int l_bi = 0, l_t = p.T - 1;          // cursor of the loads
         int s_bi = 0, s_t = p.T - 1;          // cursor of the recurrence
@@ -499,41 +502,50 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           const int col0 = (bg0 + s_bi * bgstep) * 16;
           if (s_t == p.T - 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { gvn[j] = 0.f; gcn[j] = 0.f; }
+            for (int i = 0; i < 8; ++i) { gvn[i] = 0ull; gcn[i] = 0ull; }
           }
           uint32_t x[16];
           tmem_ld16(t_set + static_cast<uint32_t>(s_t * p.Bt + col0), x);
           tmem_ld_wait();
           const size_t c = c_tile + static_cast<size_t>(s_t * p.Bt + col0);          // % 16 == 0
-          // The epilogue is bound by instruction issue (profiles/r2e: the warps are selected / not selected / in fixed-
-          // latency waits 3/4 of the time), so the store path is written for instruction count: rows c .. c + 15 of this
-          // neuron's chunk are two 1 KiB row groups; both plane bases are 1 KiB aligned (api.cu aligns the workspace), so
-          // the in-group offset xo[jj] is OR-ed into the low address word instead of a 64-bit add per store, and elements
-          // jj and jj + 8 (same xo, rows 8 apart) share one address and one bf16x2 conversion per plane.
+          // The epilogue is bound by instruction issue on the fp32 pipe (profiles/r2e: the warps are selected / not
+          // selected / in fixed-latency or math-pipe waits 3/4 of the time), so it is written for instruction count:
+          // packed fp32 pairs for the recurrence; rows c .. c + 15 of this neuron's chunk are two 1 KiB row groups and
+          // both plane bases are 1 KiB aligned (api.cu aligns the workspace), so the in-group offset xo[jj] is OR-ed
+          // into the low address word instead of a 64-bit add per store, and elements jj and jj + 8 (same xo, rows 8
+          // apart) share one address and one bf16x2 conversion per plane.
           const unsigned long long dst_hi = reinterpret_cast<unsigned long long>(gcol + (c >> 3) * 1024);
           const unsigned long long dst_lo = dst_hi + p.g_plane;
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float gc2[2];
+          for (int i = 0; i < 4; ++i) {
+            float gc4[4];       // elements 2 i, 2 i + 1, 2 i + 8, 2 i + 9
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int j = jj + 8 * h;
-              const float t = volt_t(v[j >> 1], j & 1);                            // voltage code (umma.cuh)
-              const float gs = __fmaf_rn(-gvn[j], volt_value75(t), __uint_as_float(x[j]));
-              const float win = volt_window(t) ? 1.f : 0.f;
-              const float keep = volt_spike(t) ? 0.f : 0.75f;
-              const float gv = __fmaf_rn(gvn[j], keep, gs * win);
-              gc2[h] = __fmaf_rn(0.5f, gcn[j], gv);
-              gvn[j] = gv;
-              gcn[j] = gc2[h];
-              dbsum += gc2[h];
+              const int q = i + 4 * h;                                              // pair (2 q, 2 q + 1) = trace word v[q]
+              const f32x2 t2 = volt_t2(v[q]);                                       // voltage codes (umma.cuh)
+              const f32x2 nd2 = f2_fma(t2, k_nc75, k_o75);                          // -0.75 v
+              const f32x2 u2 = f2_add(t2, k_mid);
+              const f32x2 win2 = f2_pack(fabsf(f2_lo(u2)) < 32767.f ? 1.f : 0.f, fabsf(f2_hi(u2)) < 32767.f ? 1.f : 0.f);
+              const f32x2 keep2 = f2_pack(f2_lo(u2) > 0.f ? 0.f : 0.75f, f2_hi(u2) > 0.f ? 0.f : 0.75f);
+              const f32x2 gs2 = f2_fma(gvn[q], nd2, f2_pack(__uint_as_float(x[2 * q]), __uint_as_float(x[2 * q + 1])));
+              const f32x2 gv2 = f2_fma(gvn[q], keep2, f2_mul(gs2, win2));
+              const f32x2 gc2 = f2_fma(k_half, gcn[q], gv2);
+              gvn[q] = gv2;
+              gcn[q] = gc2;
+              db2 = f2_add(db2, gc2);
+              gc4[2 * h] = f2_lo(gc2);
+              gc4[2 * h + 1] = f2_hi(gc2);
             }
             if (!(SNN_DBG_MASK(p) & 16)) {
-              // hi = bf16(g_c), lo = bf16(g_c - hi)
-              const uint32_t hp = pack_bf16x2(gc2[0], gc2[1]);
-              const uint32_t lp = pack_bf16x2(gc2[0] - __uint_as_float(hp << 16), gc2[1] - __uint_as_float(hp & 0xFFFF0000u));
-              st_global_u16x2_rows(dst_hi | xo[jj], hp);
-              st_global_u16x2_rows(dst_lo | xo[jj], lp);
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                // rows jj and jj + 8: hi = bf16(g_c), lo = bf16(g_c - hi)
+                const int jj = 2 * i + e;
+                const uint32_t hp = pack_bf16x2(gc4[e], gc4[2 + e]);
+                const uint32_t lp = pack_bf16x2(gc4[e] - __uint_as_float(hp << 16), gc4[2 + e] - __uint_as_float(hp & 0xFFFF0000u));
+                st_global_u16x2_rows(dst_hi | xo[jj], hp);
+                st_global_u16x2_rows(dst_lo | xo[jj], lp);
+              }
             }
           }
           if (--s_t < 0) { s_t = p.T - 1; ++s_bi; }
@@ -545,6 +557,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
           loadv(vb0);
           if (sidx + 1 < nsteps) { step(vb1); loadv(vb1); }
         }
+        dbsum = f2_lo(db2) + f2_hi(db2);
       }
       for (int bg = (MODE == NM_DX || (SNN_DBG_MASK(p) & 2)) ? nbg : bg0; bg < nbg; bg += bgstep) {
         const int col0 = bg * 16;
@@ -553,28 +566,33 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
         if (IS_FWD) {
           // vst = 0.75-decayed part of the next step's voltage: v (1 - s).  The reset is applied when the spike is decided
-          // (one select on the predicate just computed) instead of testing the previous step's spike bit again
-          float cur[16], vst[16];
+          // (one select on the predicate just computed) instead of testing the previous step's spike bit again.  State
+          // as packed pairs of neighbouring samples (2 i, 2 i + 1): FADD2 / FFMA2 / FMUL2, each lane rounded like the
+          // scalar operation, so spikes and voltages are bit-identical to the scalar recurrence.
+          f32x2 cur[8], vst[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vst[j] = 0.f; }
+          for (int i = 0; i < 8; ++i) { cur[i] = 0ull; vst[i] = 0ull; }
           uint32_t spend = 0;
+          const f32x2 bias2 = f2_splat(bias), k_half = f2_splat(0.5f), k_075 = f2_splat(0.75f);
+          const bool emit_v = p.v_out != nullptr && !(SNN_DBG_MASK(p) & 128);
           // one LIF step on the accumulators of timestep t (16 samples of this neuron); the next step's accumulators are
           // in flight while it runs (two register sets, ping-pong: no copies)
           auto lif_step = [&](const uint32_t (&x)[16], int t) {
             uint32_t scur = 0;
-            float vol[16];
+            uint32_t cw[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int i = 0; i < 8; ++i) {
               // reference order (actor_critic.py:228-231): c = c * 0.5 + (Wx + b); v = v * 0.75 * (1 - s) + c.  c * 0.5 is
               // exact, so the fused multiply-add rounds once like the reference's separate add; 0.75 * 0 + c == c exactly
-              const float syn = __fadd_rn(__uint_as_float(x[j]), bias);
-              const float cj = __fmaf_rn(cur[j], 0.5f, syn);
-              const float vj = __fadd_rn(__fmul_rn(vst[j], 0.75f), cj);
-              const bool sp = vj > 0.5f;
-              cur[j] = cj;
-              vol[j] = vj;
-              vst[j] = sp ? 0.f : vj;
-              scur |= (sp ? 1u : 0u) << j;
+              const f32x2 syn2 = f2_add(f2_pack(__uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1])), bias2);
+              const f32x2 c2 = f2_fma(cur[i], k_half, syn2);
+              const f32x2 v2 = f2_add(f2_mul(vst[i], k_075), c2);
+              const float v0 = f2_lo(v2), v1 = f2_hi(v2);
+              const bool s0 = v0 > 0.5f, s1 = v1 > 0.5f;
+              cur[i] = c2;
+              vst[i] = f2_pack(s0 ? 0.f : v0, s1 ? 0.f : v1);
+              scur |= ((s0 ? 1u : 0u) | (s1 ? 2u : 0u)) << (2 * i);
+              if (emit_v) cw[i] = volt_code2(v0, v1);
             }
             const size_t c = c_tile + static_cast<size_t>(t * p.Bt + col0);
             // spike words (bit = neuron of this warp, one word per sample-step): the thread holds a 16-bit mask over its
@@ -590,12 +608,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                 p.out_bits[static_cast<size_t>(n >> 5) * p.Rt + c_tile + static_cast<size_t>(tt * p.Bt + col0 + (lane & 15))] =
                     ((vmask >> (lane & 15)) & 1u) ? wd : 0u;
             }
-            if (p.v_out != nullptr && !(SNN_DBG_MASK(p) & 128)) {
+            if (emit_v) {
               // 16-bit voltage codes (umma.cuh: volt_code), [neuron / 32][sample-step / 8][32 neurons][8 sample-steps]:
               // the thread's 16 sample-steps are two 16-byte pieces, the warp's 16 x 32 codes one contiguous 1 KiB block
-              uint32_t cw[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) cw[j] = __byte_perm(volt_code(vol[2 * j]), volt_code(vol[2 * j + 1]), 0x5410u);
               uint4* dst = reinterpret_cast<uint4*>(p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32) + lane;
               dst[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
               dst[32] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
@@ -667,7 +682,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
         }
       }
       if (MODE == NM_DX)
-        p.db_part[(static_cast<size_t>(tile) * NGRP + grp) * p.MP + n] = dbsum;
+        p.db_part[(static_cast<size_t>(tile) * NGRP + grp) * p.MP + n] = dbsum;      // set by the scan: sum of its packed pair
       if (MODE == NM_DX_ENC) {
         p.enc_part[((static_cast<size_t>(tile) * NGRP + grp) * 2) * p.MP + n] = enc_dm;
         p.enc_part[((static_cast<size_t>(tile) * NGRP + grp) * 2 + 1) * p.MP + n] = enc_ds;

@@ -8,8 +8,9 @@
 //       and their autograd nodes in the reference.
 //   lr_adapt_kernel
 //       the adaptive-KL learning-rate schedule (ppo.py:139-151) without the host round trip.
-//   sumsq_kernel / clip_adam_kernel
-//       nn.utils.clip_grad_norm_ + torch.optim.Adam.step (ppo.py:176-177) over ONE flat fp32 buffer.
+//   adam_fused_kernel
+//       adaptive lr + nn.utils.clip_grad_norm_ + torch.optim.Adam.step (ppo.py:145-148, 176-177) over ONE flat fp32
+//       buffer in one launch (grid barrier between the norm and the update).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -172,6 +173,97 @@ __global__ void __launch_bounds__(1024) ppo_head_finalize_kernel(const float* __
   }
 }
 
+// ---- the same head split along the two chains of the fused PPO step (r2): the policy terms are computed inside
+// actor_head_kernel (simt_kernels.cuh) on the actor's stream, the value loss here on the critic's stream, and
+// ppo_finalize_kernel joins their partial sums off the actor's critical path.
+// value loss (ppo.py:160-168) and its gradient: g_value[b] = d (value_coef * mean(vl)) / d value[b]; part[blk] = sum of vl
+__global__ void __launch_bounds__(256) value_loss_kernel(const float* __restrict__ value, const float* __restrict__ returns,
+                                                        const float* __restrict__ target_v, int B, float clip, float value_coef,
+                                                        int clipped_value, float inv_count, float* __restrict__ g_value,
+                                                        float* __restrict__ part) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  float vl = 0.f;
+  if (b < B) {
+    const float v = value[b], R = returns[b];
+    const float e1 = v - R;
+    float gv;
+    if (clipped_value) {
+      const float tv = target_v[b];
+      const float dv = v - tv;
+      const float vc = tv + fminf(fmaxf(dv, -clip), clip);
+      const float e2 = vc - R;
+      const float l1 = e1 * e1, l2 = e2 * e2;
+      vl = fmaxf(l1, l2);
+      const float inside = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
+      const float g1 = 2.f * e1, g2 = 2.f * e2 * inside;
+      gv = l1 > l2 ? g1 : (l1 < l2 ? g2 : 0.5f * (g1 + g2));
+    } else {
+      vl = e1 * e1;
+      gv = 2.f * e1;
+    }
+    g_value[b] = gv * value_coef * inv_count;
+  }
+  const float t = block_sum_256(vl, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// head_part [nrows][4 + A] (actor_head_kernel: column 0 surrogate, 2 kl, 4.. log-std gradient sums), value_part [nrows_v]
+// -> stats / g_log_std as ppo_head_finalize_kernel; kl_out (nullable) receives the KL mean as well (the tail of the
+// gradient bucket: it rides in the data-parallel all-reduce and feeds the adaptive learning rate).
+// One block of 1024 threads: thread = rows r, r + 1024, ... of head_part, all columns of a row in registers (the rows are
+// contiguous: coalesced), then a fixed-order block reduction per column in double (thousands of rows: one per 8 samples).
+__global__ void __launch_bounds__(1024) ppo_finalize_kernel(const float* __restrict__ head_part, int nrows,
+                                                            const float* __restrict__ value_part, int nrows_v, int A, int B,
+                                                            const float* __restrict__ log_std, float ent_coef, float inv_world,
+                                                            float* __restrict__ g_log_std, float* __restrict__ stats,
+                                                            float* __restrict__ kl_out) {
+  __shared__ double s_w[32][4 + kHeadMaxA];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = 4 + A;
+  // column i of this thread's rows (column 1 = the value loss comes from value_part)
+  for (int c0 = 0; c0 < nc; c0 += 8) {
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += 1024) {
+      const float* row = head_part + static_cast<size_t>(r) * nc + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < nc) acc[j] += row[j];
+    }
+    if (c0 == 0) {
+      acc[1] = 0.0;
+      for (int r = threadIdx.x; r < nrows_v; r += 1024) acc[1] += value_part[r];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o);
+      if (lane == 0 && c0 + j < nc) s_w[warp][c0 + j] = acc[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    const int i = threadIdx.x;
+    double acc = 0.0;
+    for (int w = 0; w < 32; ++w) acc += s_w[w][i];
+    if (i == 3) {
+      float e = 0.f;
+      for (int a = 0; a < A; ++a) e += 0.5f + kHalfLog2Pi + log_std[a];
+      stats[3] = e;
+    } else if (i < 3) {
+      const float mean = static_cast<float>(acc / B);
+      stats[i] = mean;
+      if (i == 0) stats[4] += mean;
+      if (i == 1) stats[5] += mean;
+      if (i == 2) { stats[6] += 1.f; if (kl_out != nullptr) kl_out[0] = mean; }
+    } else {
+      g_log_std[i - 4] = static_cast<float>(acc) - ent_coef * inv_world;
+    }
+  }
+}
+
 // ppo.py:145-148.  kl_mean = kl[0] * kl_scale (kl_scale = 1/world when kl[0] is a sum of rank means).
 __global__ void lr_adapt_kernel(const float* __restrict__ kl, float kl_scale, float desired_kl, float* __restrict__ lr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -183,52 +275,76 @@ __global__ void lr_adapt_kernel(const float* __restrict__ kl, float kl_scale, fl
   }
 }
 
-// partial[blockIdx.x] = sum of g^2 over this block's grid-stride slice; block 0 also advances the step counter and
-// derives Adam's bias corrections for the new step ONCE (double-precision pow / sqrt are a few microseconds of latency on
-// this part: done here, next to the other blocks' sums, instead of by thread 0 of every block of clip_adam_kernel):
-// coefs[0] = lr / (1 - beta1^t), coefs[1] = sqrt(1 - beta2^t)
-constexpr int kAdamCoefs = 384;      // offset (floats) of the two coefficients in the scratch buffer; >= the 296 partials
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float grad_scale,
-                                                   float* __restrict__ partial, int* __restrict__ step,
-                                                   const float* __restrict__ lr, double beta1d, double beta2d) {
+// adaptive lr (optional) + clip_grad_norm_(max_norm) + Adam (torch semantics: lerp first moment, eps outside the
+// bias-corrected sqrt) in ONE launch — lr_adapt / sumsq / clip_adam were three dependent launches on the critical path of
+// every minibatch step.  The grid is at most one block per SM, so all blocks are resident and a grid-wide barrier
+// (counter + spin) can separate the two phases:
+//   phase A  partial[blockIdx.x] = sum of (g * grad_scale)^2 over the block's slice (fixed order); block 0 also applies the
+//            adaptive-KL schedule (ppo.py:145-148) to the DEVICE learning rate, advances the step counter and derives
+//            Adam's bias corrections once (double-precision pow / sqrt): coefs[0] = lr / (1 - beta1^t), [1] = sqrt(1 - beta2^t)
+//   barrier
+//   phase B  every block re-derives the global norm from the partials (parallel, fixed order) and updates its slice.
+// counters[0] = barrier arrivals, counters[1] = blocks done; the last block zeroes both (re-armed for the next launch).
+constexpr int kAdamCoefs = 384;      // offset (floats) of the two coefficients in the scratch buffer; >= the partials
+__global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ prm, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        float* __restrict__ partial, int* __restrict__ step,
+                                                        float* __restrict__ lr, const float* __restrict__ kl, float kl_scale,
+                                                        float desired_kl, double beta1d, double beta2d, float eps,
+                                                        float weight_decay, float max_norm, float grad_scale,
+                                                        float* __restrict__ norm_out, int* __restrict__ counters) {
   __shared__ float sh[8];
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ double s_tot[8];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;                 // contiguous slice per block
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * per, i1 = i0 + per < n ? i0 + per : n;
   if (blockIdx.x == 0 && threadIdx.x == 32) {      // a lane of warp 1: warp 0's lane 0 finishes the block sum below
+    float l = lr[0];
+    if (kl != nullptr) {
+      const float k = kl[0] * kl_scale;
+      if (k > desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
+      else if (k < desired_kl / 2.0f && k > 0.0f) l = fminf(1e-2f, l * 1.5f);
+      lr[0] = l;
+    }
     const int s1 = step[0] + 1;
     const double t = static_cast<double>(s1);
     const double bc1 = 1.0 - pow(beta1d, t);
     const double bc2 = 1.0 - pow(beta2d, t);
-    partial[kAdamCoefs] = static_cast<float>(static_cast<double>(lr[0]) / bc1);
+    partial[kAdamCoefs] = static_cast<float>(static_cast<double>(l) / bc1);
     partial[kAdamCoefs + 1] = static_cast<float>(sqrt(bc2));
     step[0] = s1;
   }
+  // four independent elements per trip in both phases: the loops are pure load latency (a one-element grid-stride loop
+  // ran eight dependent round trips per thread: 10 us for 1.2 MB)
   float acc = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
-    const float x = g[i] * grad_scale;
-    acc += x * x;
+  for (int64_t b = i0 + threadIdx.x; b < i1; b += 1024) {
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = b + u * 256 < i1 ? g[b + u * 256] * grad_scale : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += x[u] * x[u];
   }
   const float t = block_sum_256(acc, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
-}
-
-// clip_grad_norm_(max_norm) + Adam (torch semantics: lerp first moment, eps outside the bias-corrected sqrt).
-__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm, const float* __restrict__ g,
-                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                       const float* __restrict__ partial, int nparts,
-                                                       double beta1d, double beta2d, float eps, float weight_decay,
-                                                       float max_norm, float grad_scale, float* __restrict__ norm_out) {
+  // ---- grid barrier
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counters, 1);
+    while (atomicAdd(counters, 0) < static_cast<int>(gridDim.x)) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
   // torch.optim.Adam: exp_avg.lerp_(g, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2) with the
   // python-double (1 - beta) rounded to fp32 once
   const float beta2 = static_cast<float>(beta2d);
   const float omb1 = static_cast<float>(1.0 - beta1d), omb2 = static_cast<float>(1.0 - beta2d);
-  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
-  __shared__ double s_tot[8];
   {
-    // every block re-derives the global norm from the per-block partials (parallel, fixed order)
-    double t = 0.0;
-    for (int i = threadIdx.x; i < nparts; i += 256) t += partial[i];
+    double tt = 0.0;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 256) tt += __ldcg(partial + i);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = t;
+    for (int o = 16; o > 0; o >>= 1) tt += __shfl_down_sync(0xffffffffu, tt, o);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = tt;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -238,23 +354,37 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ prm,
     float coef = 1.f;
     if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
     s_coef = coef;
-    s_step_size = partial[kAdamCoefs];          // lr / (1 - beta1^t) and sqrt(1 - beta2^t), from sumsq_kernel
-    s_bc2_sqrt = partial[kAdamCoefs + 1];
+    s_step_size = __ldcg(partial + kAdamCoefs);
+    s_bc2_sqrt = __ldcg(partial + kAdamCoefs + 1);
     if (blockIdx.x == 0 && norm_out != nullptr) norm_out[0] = norm;
   }
   __syncthreads();
   const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
-    float gi = g[i] * grad_scale * coef;
-    const float pi = prm[i];
-    if (weight_decay != 0.f) gi = gi + weight_decay * pi;
-    float mi = m[i], vi = v[i];
-    mi = mi + (gi - mi) * omb1;
-    vi = vi * beta2 + gi * gi * omb2;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    prm[i] = pi - step_size * (mi / denom);
+  for (int64_t b = i0 + threadIdx.x; b < i1; b += 1024) {
+    float gi[4], pi[4], mi[4], vi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = b + u * 256;
+      const bool on = i < i1;
+      gi[u] = on ? g[i] : 0.f; pi[u] = on ? prm[i] : 0.f; mi[u] = on ? m[i] : 0.f; vi[u] = on ? v[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = b + u * 256;
+      if (i >= i1) continue;
+      float gg = gi[u] * grad_scale * coef;
+      if (weight_decay != 0.f) gg = gg + weight_decay * pi[u];
+      const float mm = mi[u] + (gg - mi[u]) * omb1;
+      const float vv = vi[u] * beta2 + gg * gg * omb2;
+      m[i] = mm;
+      v[i] = vv;
+      const float denom = sqrtf(vv) / bc2_sqrt + eps;
+      prm[i] = pi[u] - step_size * (mm / denom);
+    }
+  }
+  if (threadIdx.x == 0 && atomicAdd(counters + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+    counters[0] = 0;
+    counters[1] = 0;
   }
 }
 

@@ -379,6 +379,142 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   }
 }
 
+// ------------------------------------------------------------------ decoder + PPO actor head, one launch
+// PPO.update between the actor's last LIF layer and its backward chain (AMP/.../algorithms/ppo.py:132-171 for the policy
+// terms, modules/actor_critic.py:140-150 for the decoder): until r2 that was decode_kernel -> ppo_head_kernel ->
+// ppo_head_finalize_kernel -> (copy) -> top_scan_rows_kernel, with a join with the critic's stream in the middle, on the
+// critical path of every minibatch step.  Nothing in the actor's chain needs the critic: the surrogate loss, the KL
+// statistic and d loss / d mu depend on (mu, log_std) and the rollout fields only.  This kernel does the decoder and
+// those policy terms; the value loss goes through value_loss_kernel on the critic's stream and ppo_finalize_kernel joins
+// the partial sums on a third branch.  top_scan_rows_kernel follows directly.
+// (A version that also ran the output layer's scan in the same blocks was bit-identical but no faster than the separate
+// kernels: 60 us, bound by the barriers between its phases at 5 blocks per SM; profiles/r2t, r2v.)
+// Block = 32 samples; thread = one (sample, action) item for the decoder's bit counting (dense lanes), one sample for the
+// log-prob / ratio / surrogate.  part[blk][4 + A] = block sums: surrogate, (unused), kl, (unused), g_log_std[a].
+struct ActorHeadParams {
+  const uint32_t* bits;     // output layer's spike words [NP/32][Rt]
+  const float* dec_w; const float* dec_b; int dec_tanh;
+  const float* log_std; const float* actions; const float* old_logp; const float* adv; const float* old_mu; const float* old_sigma;
+  float clip, inv_count;
+  float* mu;                // [B, A] out
+  float* g_mu;              // [B, A] out: d loss / d mu
+  float* part;              // [gridDim.x][4 + A]
+  int B, A, P, T;
+  TileGeom tg;
+};
+constexpr int kHeadSPB = 16;               // samples per block: 16 x 12 actions = 192 items, one pass of the 256 threads
+constexpr int kHeadMaxItems = kHeadSPB * 64;
+__global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadParams p) {
+  constexpr int SPB = kHeadSPB;
+  __shared__ float s_rate[kMaxT + 1];
+  __shared__ float s_sig[64], s_ivar[64], s_lsig[64];
+  __shared__ float s_lp[kHeadMaxItems], s_kl[kHeadMaxItems], s_d[kHeadMaxItems];      // per item: log-prob / kl terms (then the log-std term), action - mu
+  __shared__ float s_glp[SPB], s_sur[SPB], s_klb[SPB];
+  const int A = p.A, P = p.P, nt = p.T;
+  const TileGeom tg = p.tg;
+  const int b0 = blockIdx.x * SPB;
+  const int nitems = SPB * A;
+  if (threadIdx.x <= nt) s_rate[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), static_cast<float>(nt));
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + A) {
+    const int a = threadIdx.x - 64;
+    const float sg = expf(__ldg(p.log_std + a));
+    s_sig[a] = sg;
+    s_ivar[a] = 1.f / (sg * sg);
+    s_lsig[a] = logf(sg);
+  }
+  __syncthreads();
+  // ---- decoder + per-action Normal terms, thread = item (sample-major: the [B, A] fields are read as one contiguous run)
+  for (int item = threadIdx.x; item < nitems; item += 256) {
+    const int sm = item / A, a = item - sm * A;
+    const int b = b0 + sm;
+    float lp = 0.f, kl = 0.f, dd = 0.f;
+    if (b < p.B) {
+      const int tile = b / tg.Bt;
+      const size_t r0 = static_cast<size_t>(tile) * tg.CT + (b - tile * tg.Bt);      // sample-step (0, b); step t is r0 + t * Bt
+      const int n0 = a * P;
+      float acc = 0.f;
+      if (P <= 16) {
+        const int w0 = n0 >> 5, w1 = (n0 + P - 1) >> 5, sh = n0 & 31;
+        int cnt[16];
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) cnt[pp] = 0;
+        for (int t = 0; t < nt; ++t) {
+          const size_t r = r0 + static_cast<size_t>(t) * tg.Bt;
+          const uint32_t lo = __ldg(p.bits + static_cast<size_t>(w0) * tg.Rt + r);
+          const uint32_t hi = w1 != w0 ? __ldg(p.bits + static_cast<size_t>(w1) * tg.Rt + r) : 0u;
+          const uint32_t x = __funnelshift_r(lo, hi, sh);      // bits n0 .. n0+31 of this sample at step t
+#pragma unroll
+          for (int pp = 0; pp < 16; ++pp) cnt[pp] += (x >> pp) & 1u;
+        }
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp)
+          if (pp < P) acc = __fmaf_rn(__ldg(p.dec_w + n0 + pp), s_rate[cnt[pp]], acc);
+      } else {
+        for (int pp = 0; pp < P; ++pp) {
+          const int n = n0 + pp;
+          int cnt = 0;
+          for (int t = 0; t < nt; ++t)
+            cnt += (__ldg(p.bits + static_cast<size_t>(n >> 5) * tg.Rt + r0 + static_cast<size_t>(t) * tg.Bt) >> (n & 31)) & 1u;
+          acc = __fmaf_rn(__ldg(p.dec_w + n), s_rate[cnt], acc);
+        }
+      }
+      acc = __fadd_rn(acc, __ldg(p.dec_b + a));                 // decode_kernel's arithmetic, bit for bit
+      const float m = p.dec_tanh ? tanhf(acc) : acc;
+      const size_t gi = static_cast<size_t>(b) * A + a;
+      p.mu[gi] = m;
+      // Normal(mu, sigma) terms of this action (ppo_head_kernel's formulas)
+      const float sg = s_sig[a], iv = s_ivar[a];
+      const float d = __ldg(p.actions + gi) - m;
+      lp = -(d * d) * 0.5f * iv - s_lsig[a] - 0.91893853320467274178f;
+      const float os = __ldg(p.old_sigma + gi), dm = __ldg(p.old_mu + gi) - m;
+      kl = logf(sg / os + 1.e-5f) + (os * os + dm * dm) * 0.5f * iv - 0.5f;
+      dd = d;
+    }
+    s_lp[item] = lp;
+    s_kl[item] = kl;
+    s_d[item] = dd;
+  }
+  __syncthreads();
+  // ---- per sample: log-prob, ratio, clipped surrogate (ppo.py:153-158), thread = sample
+  if (threadIdx.x < SPB) {
+    const int b = b0 + threadIdx.x;
+    float logp = 0.f, kl = 0.f, sur = 0.f, g_logp = 0.f;
+    if (b < p.B) {
+      for (int a = 0; a < A; ++a) { logp += s_lp[threadIdx.x * A + a]; kl += s_kl[threadIdx.x * A + a]; }
+      const float ad = __ldg(p.adv + b);
+      const float ratio = expf(logp - __ldg(p.old_logp + b));
+      const float s1 = -ad * ratio;
+      const float s2 = -ad * fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
+      sur = fmaxf(s1, s2);
+      g_logp = (s1 >= s2 ? -ad : 0.f) * ratio * p.inv_count;     // d mean(sur) / d logp
+    }
+    s_glp[threadIdx.x] = g_logp; s_sur[threadIdx.x] = sur; s_klb[threadIdx.x] = kl;
+  }
+  __syncthreads();
+  // ---- d loss / d mu and the log-std gradient terms, thread = item
+  for (int item = threadIdx.x; item < nitems; item += 256) {
+    const int sm = item / A, a = item - sm * A;
+    const int b = b0 + sm;
+    float gls = 0.f;
+    if (b < p.B) {
+      const size_t gi = static_cast<size_t>(b) * A + a;
+      const float d = s_d[item], iv = s_ivar[a], g_logp = s_glp[sm];
+      p.g_mu[gi] = g_logp * d * iv;
+      gls = g_logp * (d * d * iv - 1.f);                          // d logp / d log_std = (a-mu)^2/sigma^2 - 1
+    }
+    s_lp[item] = gls;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 + A) {      // block sums in a fixed order
+    const int i = threadIdx.x;
+    float t = 0.f;
+    if (i == 0) { for (int g = 0; g < SPB; ++g) t += s_sur[g]; }
+    else if (i == 2) { for (int g = 0; g < SPB; ++g) t += s_klb[g]; }
+    else if (i >= 4) { for (int g = 0; g < SPB; ++g) t += s_lp[g * A + (i - 4)]; }
+    p.part[static_cast<size_t>(blockIdx.x) * (4 + A) + i] = t;
+  }
+}
+
 // ------------------------------------------------------------------ minibatch permutation: all fields in one pass
 // RolloutStorage.mini_batch_generator gathers 9 tensors by the same random row indices, 20 times per update
 // (rollout_storage.py:174-182); here every field is gathered ONCE per update, and all of them by this one kernel:
@@ -419,63 +555,82 @@ __global__ void enc_dobs_kernel(const float* __restrict__ obs, const float* __re
   d_obs[idx] = acc;
 }
 
-// Several independent row reductions / split-K reductions in ONE launch (blockIdx.y resp. .z selects the job):
-// the backward pass defers all of its small reductions to the end instead of launching ten tiny kernels.
+// ALL deferred reductions of a backward pass in ONE launch (blockIdx.y selects the job): the row reductions of the
+// per-tile / per-block partial rows (bias, encoder and decoder gradients) and the split-K reductions of the dW tiles.
 // A job with thousands of partial rows (the top-layer scan writes one row per 8 samples: 3072 at B = 24576) is reduced
-// in two launches: blockIdx.z = segment of seg_rows rows -> one row of a scratch matrix, then the scratch rows -> dst
-// (a single block column walking 3072 rows is 12 dependent rounds of load latency: 45 us on the step's critical path).
-struct RowJob { const float* src; float* dst; int nparts; int n; unsigned long long stride; int col_step;
-                int seg_rows; unsigned long long seg_dst_stride; };
-struct RowJobs { RowJob j[12]; int count; };
-__global__ void __launch_bounds__(1024) multi_reduce_rows_kernel(const RowJobs jobs) {   // block (32, 32)
-  RowJob jb = jobs.j[blockIdx.y];
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  if (blockIdx.x * 32 >= jb.n) return;
-  if (jb.seg_rows > 0) {
-    const int r0 = blockIdx.z * jb.seg_rows;
-    if (r0 >= jb.nparts) return;
-    jb.src += static_cast<size_t>(r0) * jb.stride;
-    jb.dst += static_cast<size_t>(blockIdx.z) * jb.seg_dst_stride;
-    jb.nparts = min(jb.seg_rows, jb.nparts - r0);
-  } else if (blockIdx.z > 0) {
+// in two levels inside the same launch: blockIdx.z = segment of seg_rows rows -> one row of a scratch matrix; the LAST
+// segment block of the job to finish (a counter per job) sums the scratch rows in a fixed order -> dst.  Until r2 these
+// were three dependent launches (split-K, segments, finals) on the critical path of every minibatch step.
+struct RowJob {
+  const float* src; float* dst; float* tmp;      // tmp: [nseg][width] scratch (nseg > 1)
+  int nparts, n, col_step, nseg, seg_rows, width;
+  unsigned long long stride;
+};
+struct PartJob { const float* partial; float* dW; int splits, n_tiles, N, K; };
+struct ReduceJobs { RowJob r[12]; PartJob p[8]; int nr, np; int* counters; };
+__global__ void __launch_bounds__(1024) multi_reduce_kernel(const ReduceJobs jobs) {   // block (32, 32)
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (static_cast<int>(blockIdx.y) >= jobs.nr) {
+    // split-K partial tiles [tile][split][128][256] -> dW[n][k]: thread = one element, warp = 32 consecutive k
+    const PartJob jb = jobs.p[blockIdx.y - jobs.nr];
+    const int k = blockIdx.x * 32 + threadIdx.x, n = blockIdx.z * 32 + threadIdx.y;
+    if (k >= jb.K || n >= jb.N) return;
+    const int tile = (n >> 7) * jb.n_tiles + (k >> 8);
+    const float* src = jb.partial + (static_cast<size_t>(tile) * jb.splits * 128 + (n & 127)) * 256 + (k & 255);
+    float acc = 0.f;
+    for (int s = 0; s < jb.splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
+    jb.dW[static_cast<size_t>(n) * jb.K + k] = acc;
     return;
   }
+  const RowJob jb = jobs.r[blockIdx.y];
+  const bool two_level = jb.nseg > 1;
+  const int ncols = two_level ? jb.width : jb.n;           // the segment pass keeps every column of the strided window
+  if (static_cast<int>(blockIdx.x) * 32 >= ncols || static_cast<int>(blockIdx.z) >= jb.nseg) return;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = two_level ? blockIdx.z * jb.seg_rows : 0;
+  const int nrows = two_level ? min(jb.seg_rows, jb.nparts - r0) : jb.nparts;
   float acc = 0.f;
-  if (i < jb.n) {
-    // eight independent loads in flight per thread (the kernel is pure load latency); fixed summation order
-    const float* src = jb.src + static_cast<size_t>(i) * jb.col_step;
+  if (i < ncols) {
+    // eight independent loads in flight per thread (the pass is pure load latency); fixed summation order
+    const float* src = jb.src + static_cast<size_t>(r0) * jb.stride + static_cast<size_t>(i) * (two_level ? 1 : jb.col_step);
     int s = threadIdx.y;
-    for (; s + 7 * 32 < jb.nparts; s += 8 * 32) {
+    for (; s + 7 * 32 < nrows; s += 8 * 32) {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = src[static_cast<size_t>(s + u * 32) * jb.stride];
 #pragma unroll
       for (int u = 0; u < 8; ++u) acc += v[u];
     }
-    for (; s < jb.nparts; s += 32) acc += src[static_cast<size_t>(s) * jb.stride];
+    for (; s < nrows; s += 32) acc += src[static_cast<size_t>(s) * jb.stride];
   }
   __shared__ float sh[32][33];
+  __shared__ int s_last;
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && i < jb.n) {
+  if (threadIdx.y == 0 && i < ncols) {
     float t = 0.f;
     for (int y = 0; y < 32; ++y) t += sh[y][threadIdx.x];
-    jb.dst[i] = t;
+    if (two_level) jb.tmp[static_cast<size_t>(blockIdx.z) * jb.width + i] = t;
+    else jb.dst[i] = t;
   }
-}
-
-struct PartJob { const float* partial; float* dW; int splits, n_tiles, N, K; };
-struct PartJobs { PartJob j[8]; int count; };
-__global__ void multi_reduce_partials_kernel(const PartJobs jobs) {
-  const PartJob jb = jobs.j[blockIdx.z];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = blockIdx.y;
-  if (k >= jb.K || n >= jb.N) return;
-  const int tile = (n >> 7) * jb.n_tiles + (k >> 8);
-  const float* src = jb.partial + (static_cast<size_t>(tile) * jb.splits * 128 + (n & 127)) * 256 + (k & 255);
-  float acc = 0.f;
-  for (int s = 0; s < jb.splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
-  jb.dW[static_cast<size_t>(n) * jb.K + k] = acc;
+  if (!two_level) return;
+  // last segment block of this job: the final pass over the nseg scratch rows (fixed order: bitwise reproducible)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int total = ((jb.width + 31) / 32) * jb.nseg;
+    s_last = atomicAdd(jobs.counters + blockIdx.y, 1) == total - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = tid; c < jb.n; c += 1024) {
+    const float* src = jb.tmp + static_cast<size_t>(c) * jb.col_step;
+    float t = 0.f;
+    for (int z = 0; z < jb.nseg; ++z) t += __ldcg(src + static_cast<size_t>(z) * jb.width);
+    jb.dst[c] = t;
+  }
+  if (tid == 0) jobs.counters[blockIdx.y] = 0;      // re-armed for the next launch that draws this counter slot
 }
 
 // ------------------------------------------------------------------ GAE (rollout_storage.py:124-138)

@@ -202,6 +202,41 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
   }
   return x;
 }
+// ------------------------------------------------------------------ packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2)
+// Two independent IEEE fp32 operations per lane and instruction, each rounded exactly like its scalar form (so every
+// result is bit-identical to the scalar code it replaces).  The time scans of the epilogues are bound by the fp32 /
+// integer-multiply pipe (a three-register FFMA issues every second cycle per scheduler): pairing neighbouring
+// sample-steps halves their floating-point instruction count.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ float f2_lo(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float f2_hi(f32x2 v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_fma_ru(f32x2 a, f32x2 b, f32x2 c) {      // both lanes rounded towards +inf
+  f32x2 d;
+  asm("fma.rp.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ------------------------------------------------------------------ 16-bit voltage trace
 // The backward pass uses a membrane voltage v in exactly three ways (actor_critic.py:154-167, 228-231): the spike flag
 // v > 0.5, the surrogate window |v - 0.5| < 0.5, and — only inside that window — the value of v in the reset term.  The
@@ -226,6 +261,17 @@ __device__ __forceinline__ uint32_t volt_code(float v) {
 // the code as a float t in [0, 65535]: bytes {k.lo, k.hi, 0x00, 0x4B} are the float 2^23 + k (one byte permute)
 __device__ __forceinline__ float volt_t(uint32_t word, int upper) {
   return __uint_as_float(__byte_perm(word, 0x4B000000u, upper ? 0x7632u : 0x7610u)) - 8388608.f;
+}
+// both codes of a 32-bit trace word as floats {t(low half), t(high half)}
+__device__ __forceinline__ f32x2 volt_t2(uint32_t word) {
+  return f2_add(f2_pack(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7610u)), __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7632u))),
+                f2_splat(-8388608.f));
+}
+// two voltages -> one trace word (see volt_code)
+__device__ __forceinline__ uint32_t volt_code2(float v0, float v1) {
+  const float hi = 65535.f / 65534.f;
+  const f32x2 k = f2_fma_ru(f2_pack(fminf(fmaxf(v0, 0.f), hi), fminf(fmaxf(v1, 0.f), hi)), f2_splat(kVoltScale), f2_splat(8388608.f));
+  return __byte_perm(static_cast<uint32_t>(k), static_cast<uint32_t>(k >> 32), 0x5410u);
 }
 __device__ __forceinline__ float volt_value(float t) { return __fmaf_rn(t, kVoltInv, -0.5f * kVoltInv); }           // v inside the window
 __device__ __forceinline__ float volt_value75(float t) { return __fmaf_rn(t, 0.75f * kVoltInv, -0.375f * kVoltInv); }  // 0.75 v

@@ -141,7 +141,12 @@ class SnnEngine:
             ps = self._params_struct(enc_mean, enc_std, weights, biases, dec_w, dec_b)
             packed = self._packed if (assume_packed and self._packed is not None) else \
                 self.packed_weights(weights, biases, ps, enc=(enc_mean, enc_std))
-            mu = out_mu if out_mu is not None else torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
+            if out_mu is False:      # training forward of the fused PPO step: the decoder runs in backward_ppo_top
+                if not train:
+                    raise RuntimeError("out_mu=False (no decoder pass) is a training-forward option")
+                mu = None
+            else:
+                mu = out_mu if out_mu is not None else torch.empty(B, self.desc.act_dim, dtype=torch.float32, device=dev)
             if B == 0:
                 return mu, None
             if train:
@@ -230,6 +235,50 @@ class SnnEngine:
                 raise RuntimeError("backward workspace too small")
             _lib.check(L.snn_bwd(C.byref(self.desc), C.byref(ps), _ptr(packed), _ptr(obs), B, _ptr(mu), _ptr(g_mu),
                                  _ptr(trace), C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_bwd")
+        return out
+
+    def _grads_struct(self, out, need_dobs):
+        g = _lib.SnnGrads()
+        g.enc_mean, g.enc_std = out["enc_mean"].data_ptr(), out["enc_std"].data_ptr()
+        for i in range(self.L):
+            g.weight[i] = out["weights"][i].data_ptr()
+            g.bias[i] = out["biases"][i].data_ptr()
+        g.dec_w, g.dec_b = out["dec_w"].data_ptr(), out["dec_b"].data_ptr()
+        g.obs = out["obs"].data_ptr() if need_dobs else None
+        return g
+
+    def ppo_head_part_bytes(self, B: int) -> int:
+        return int(_lib.lib().snn_ppo_head_part_bytes(C.byref(self.desc), B))
+
+    def backward_ppo_top(self, obs, trace, params, log_std, actions, old_logp, adv, old_mu, old_sigma, clip: float, part,
+                         ws, out_mu, out_g_mu):
+        """Stage 1 of the fused PPO backward (snn_bwd_ppo_top): decoder + the policy terms of the PPO head in one kernel
+        (-> out_mu, out_g_mu), then the output layer's BPTT scan.  params = (enc_mean, enc_std, weights, biases, dec_w,
+        dec_b); the planes must be current (the fused step re-packs after every optimizer step).  part: uint8 buffer of
+        ppo_head_part_bytes(B)."""
+        dev = obs.device
+        B = obs.shape[0]
+        for t, n in ((log_std, "log_std"), (actions, "actions"), (old_logp, "old_logp"), (adv, "adv"), (old_mu, "old_mu"),
+                     (old_sigma, "old_sigma")):
+            _check_f32_cuda(t, n)
+        with torch.cuda.device(dev):
+            ps = self._params_struct(*params)
+            h = _lib.SnnPpoActorHead()
+            h.log_std, h.actions, h.old_logp, h.adv = log_std.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv.data_ptr()
+            h.old_mu, h.old_sigma, h.clip = old_mu.data_ptr(), old_sigma.data_ptr(), float(clip)
+            h.mu_out, h.g_mu_out = out_mu.data_ptr(), out_g_mu.data_ptr()
+            h.part, h.part_bytes = part.data_ptr(), part.numel()
+            _lib.check(_lib.lib().snn_bwd_ppo_top(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _ptr(obs), B, C.byref(h),
+                                                  _ptr(trace), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_bwd_ppo_top")
+
+    def backward_rest(self, obs, trace, params, out, ws, need_dobs: bool = False):
+        """Stage 2 (snn_bwd_rest): the dX chain below the output layer, dW, the deferred reductions -> `out`."""
+        dev = obs.device
+        with torch.cuda.device(dev):
+            ps = self._params_struct(*params)
+            g = self._grads_struct(out, need_dobs)
+            _lib.check(_lib.lib().snn_bwd_rest(C.byref(self.desc), C.byref(ps), _ptr(self._packed), _ptr(obs), obs.shape[0],
+                                               _ptr(trace), C.byref(g), _ptr(ws), ws.numel(), _stream_ptr(dev)), "snn_bwd_rest")
         return out
 
     # ------------------------------------------------------------------ test hooks

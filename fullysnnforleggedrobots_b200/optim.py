@@ -84,16 +84,20 @@ class FlatAdam(torch.optim.Optimizer):
         self.set_lr(self.param_groups[0]["lr"])
 
     @torch.no_grad()
-    def step(self, max_grad_norm: float = 0.0, grad_scale: float = 1.0, closure=None):
-        """clip (if max_grad_norm > 0) + Adam on the flat buffers; lr is read from lr_dev on the device."""
+    def step(self, max_grad_norm: float = 0.0, grad_scale: float = 1.0, closure=None, kl=None, kl_scale: float = 1.0,
+             desired_kl: float = 0.0):
+        """clip (if max_grad_norm > 0) + Adam on the flat buffers; lr is read from lr_dev on the device.
+        kl (a 1-element device tensor): the adaptive-KL schedule of PPO (ppo.py:145-148) is applied to lr_dev first,
+        inside the same kernel (kl_mean = kl[0] * kl_scale)."""
         g = self.param_groups[0]
         b1, b2 = g["betas"]
         dev = self.flat_params.device
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().snn_clip_adam(
+            _lib.check(_lib.lib().snn_clip_adam_kl(
                 C.c_void_p(self.flat_params.data_ptr()), C.c_void_p(self.flat_grads.data_ptr()),
                 C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), self.n,
                 C.c_void_p(self.lr_dev.data_ptr()), C.c_void_p(self.step_dev.data_ptr()), float(b1), float(b2),
                 float(g["eps"]), float(g["weight_decay"]), float(max_grad_norm), float(grad_scale),
+                C.c_void_p(kl.data_ptr()) if kl is not None else None, float(kl_scale), float(desired_kl),
                 C.c_void_p(self.norm_dev.data_ptr()), C.c_void_p(self._scratch.data_ptr()),
-                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "snn_clip_adam")
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "snn_clip_adam_kl")

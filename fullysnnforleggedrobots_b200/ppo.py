@@ -110,6 +110,9 @@ class PPO:
         self._params_epoch = 0                 # bumped by every update(): the act graph's critic planes follow it
         # critic kernels on a second stream (parallel CUDA-graph branch); SNN_OVERLAP_CRITIC=0 serialises them
         self.overlap_critic = os.environ.get("SNN_OVERLAP_CRITIC", "1") != "0"
+        # fused step: decoder + policy terms of the PPO head on the actor's chain, value loss on the critic's branch,
+        # finalize on a third one (SNN_SPLIT_HEAD=0: the one-kernel head snn_ppo_head after a join of the two chains)
+        self.split_head = os.environ.get("SNN_SPLIT_HEAD", "1") != "0"
         # capture the actor chain on a high-priority stream: where both chains have thread blocks pending, the
         # actor's (the critical path) are placed first (measured: 14.96 -> 14.61 ms per update; SNN_ACTOR_PRIO=0: off)
         self.actor_high_priority = os.environ.get("SNN_ACTOR_PRIO", "1") != "0"
@@ -350,12 +353,11 @@ class PPO:
         opt = self.optimizer
         world = 1 if self.dp is None else self.dp.world_size
         dev = opt.flat_params.device
-        with torch.cuda.device(dev):
-            if self._adaptive():
-                _lib.check(_lib.lib().snn_lr_adapt(_p(opt.flat_grads[opt.n:]), 1.0 / world, float(self.desired_kl),
-                                                   _p(opt.lr_dev), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                           "snn_lr_adapt")
-        opt.step(max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0, grad_scale=1.0 / world)
+        # adaptive lr (ppo.py:145-148) + clip + Adam: one kernel (the KL statistic sits in the tail of the gradient bucket)
+        adaptive = self._adaptive()
+        opt.step(max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0, grad_scale=1.0 / world,
+                 kl=opt.flat_grads[opt.n:] if adaptive else None, kl_scale=1.0 / world,
+                 desired_kl=float(self.desired_kl) if adaptive else 0.0)
         self._repack_actor()
         # the critic's operand planes are re-derived at the head of the next step's critic branch (second stream):
         # off the critical path, which continues with the actor's encoder (_step_fast)
@@ -393,7 +395,7 @@ class PPO:
         g = self.optimizer.param_groups[0]
         return (mb, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
                 bool(self.use_clipped_value_loss), self.desired_kl, self.schedule, self.max_grad_norm,
-                tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), self.overlap_critic,
+                tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), self.overlap_critic, self.split_head,
                 1 if self.dp is None else self.dp.world_size,
                 tuple(sorted((k, v.data_ptr()) for k, v in f.items())))
 
@@ -421,6 +423,8 @@ class PPO:
             "weights": [l.weight.grad for l in layers], "biases": [l.bias.grad for l in layers],
             "dec_w": ac.actor.decoder.decoder.weight.grad, "dec_b": ac.actor.decoder.decoder.bias.grad, "obs": None,
         }
+        st["head_part"] = torch.empty(max(eng.ppo_head_part_bytes(mb), 1024), dtype=torch.uint8, device=dev)
+        st["value_part"] = torch.empty(((mb + 255) // 256) * 4 + 1024, dtype=torch.uint8, device=dev)
         st["critic"] = None
         if self.fused_critic:
             ce = CriticEngine.from_sequential(ac.critic) if isinstance(ac.critic, nn.Sequential) else None
@@ -432,6 +436,7 @@ class PPO:
                 st["critic_ws"] = torch.empty(ce.workspace_bytes(mb), dtype=torch.uint8, device=dev)
                 st["critic_grads"] = ([l.weight.grad for l in ce.linears], [l.bias.grad for l in ce.linears])
                 st["side_stream"] = torch.cuda.Stream(device=dev) if self.overlap_critic else None
+                st["fin_stream"] = torch.cuda.Stream(device=dev) if self.overlap_critic else None
         self._fast_state = st
         self._graphs = {}
 
@@ -461,16 +466,64 @@ class PPO:
             else:
                 ce.repack()
                 value, ctrace = ce.forward(f["critic_obs"][sl], out_value=st["value"], out_trace=st["critic_trace"])
-        mu, trace = eng.forward(f["obs"][sl], em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data,
-                                db.data, train=True, out_mu=st["mu"], out_trace=st["trace"], assume_packed=True)
+        split = ce is not None and self.split_head
+        params = (em.data, es.data, [w.data for w in ws], [b.data for b in bs], dw.data, db.data)
+        mu, trace = eng.forward(f["obs"][sl], *params, train=True, out_mu=False if split else st["mu"],
+                                out_trace=st["trace"], assume_packed=True)
+        L = _lib.lib()
+        world = 1 if self.dp is None else self.dp.world_size
+        if split:
+            # The policy terms of the PPO head need nothing from the critic: the actor's chain runs decoder + head as one
+            # kernel, then the output layer's scan (snn_bwd_ppo_top) and goes straight on with its dX chain; the value loss
+            # stays on the critic's branch, and the finalize (loss statistics, d log_std, KL into the tail of the gradient
+            # bucket for the all-reduce / adaptive lr) joins the two partial sets on a third branch, off both chains.
+            eng.backward_ppo_top(f["obs"][sl], trace, params, ac.actor.log_std.data, f["actions"][sl], f["logp"][sl],
+                                 f["adv"][sl], f["mu"][sl], f["sigma"][sl], float(self.clip_param), st["head_part"],
+                                 st["ws_bwd"], out_mu=st["mu"], out_g_mu=st["g_mu"])
+            def finalize(stream_):
+                _lib.check(L.snn_ppo_finalize(C.byref(eng.desc), mb, _p(st["head_part"]), _p(st["value_part"]),
+                                              _p(ac.actor.log_std.data), float(self.entropy_coef), _p(ac.actor.log_std.grad),
+                                              _p(self._stats), _p(opt.flat_grads[opt.n:]), C.c_void_p(stream_.cuda_stream)),
+                           "snn_ppo_finalize")
+
+            branch = side if side is not None else main
+            head_done = vl_done = None
+            if side is not None:
+                head_done = torch.cuda.Event()
+                head_done.record(main)
+            with torch.cuda.stream(branch), torch.cuda.device(dev):
+                _lib.check(L.snn_ppo_value_loss(_p(value.detach()), _p(f["returns"][sl]), _p(f["values"][sl]), mb,
+                                                float(self.clip_param), float(self.value_loss_coef),
+                                                1 if self.use_clipped_value_loss else 0, _p(st["g_value"]),
+                                                _p(st["value_part"]), st["value_part"].numel(),
+                                                C.c_void_p(branch.cuda_stream)), "snn_ppo_value_loss")
+                if side is not None:
+                    vl_done = torch.cuda.Event()
+                    vl_done.record(side)
+                else:
+                    finalize(main)
+                ce.backward(st["g_value"], ctrace, mb, out=st["critic_grads"], ws=st["critic_ws"])
+            if side is not None:
+                # third branch: the finalize needs the head's partial sums and the value loss only — neither the actor's
+                # dX chain nor the critic's backward wait for it, and it is done long before the optimizer joins them
+                fin = st["fin_stream"]
+                fin.wait_event(head_done)
+                fin.wait_event(vl_done)
+                with torch.cuda.stream(fin), torch.cuda.device(dev):
+                    finalize(fin)
+            eng.backward_rest(f["obs"][sl], trace, params, st["grads_out"], st["ws_bwd"])
+            if side is not None:
+                main.wait_stream(side)
+                main.wait_stream(fin)
+            if finish:
+                self._finish_step()
+            return
         if ce is None:
             with torch.enable_grad():
                 value = ac.evaluate(f["critic_obs"][sl])
         elif side is not None:
             main.wait_stream(side)
-        L = _lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        world = 1 if self.dp is None else self.dp.world_size
         with torch.cuda.device(dev):
             _lib.check(L.snn_ppo_head(
                 _p(mu), _p(ac.actor.log_std.data), _p(value.detach()), _p(f["actions"][sl]), _p(f["logp"][sl]),

@@ -119,6 +119,41 @@ int snn_bwd(const SnnDesc* d, const SnnParams* p, const void* packed, const floa
             int64_t B, const float* mu, const float* g_mu, const void* trace,
             const SnnGrads* g, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- The fused PPO step's split of snn_bwd (r2).  Between the actor's last LIF layer and its backward chain the
+ * reference runs the decoder, the whole PPO head and their autograd (AMP/.../algorithms/ppo.py:132-171,
+ * modules/actor_critic.py:140-150, 398-421).  Nothing of the POLICY terms needs the critic, so the actor's chain does them
+ * itself, right before the output layer's BPTT scan:
+ *   snn_bwd_ppo_top  decoder (mu from the recorded output spikes; snn_fwd_train may be called with mu == NULL) + Normal
+ *                    log-prob / ratio / clipped surrogate / KL / d loss / d mu per sample in one kernel, then the output
+ *                    layer's scan.  Partial sums go to head->part (snn_ppo_head_part_bytes); mu_out / g_mu_out receive
+ *                    mu and d loss / d mu (the scan reads them).
+ *   snn_bwd_rest     every stage of snn_bwd below the output layer, dW, the deferred reductions.  Same workspace.
+ *   snn_ppo_value_loss  the clipped value loss and g_value on the critic's side (ppo.py:160-168); part >= ceil(B/256)*4 bytes.
+ *   snn_ppo_finalize    joins both partial sets: stats[0..6] and g_log_std as snn_ppo_head; kl_out (nullable) = KL mean.
+ * Loss means are over B samples (the caller's data-parallel scale goes through snn_clip_adam's grad_scale). */
+typedef struct SnnPpoActorHead {
+  const float* log_std;     /* [A] */
+  const float* actions;     /* [B,A] */
+  const float* old_logp;    /* [B] */
+  const float* adv;         /* [B] */
+  const float* old_mu;      /* [B,A] */
+  const float* old_sigma;   /* [B,A] */
+  float clip;
+  float* mu_out;            /* [B,A] */
+  float* g_mu_out;          /* [B,A] */
+  float* part;              /* snn_ppo_head_part_bytes(d, B) bytes */
+  size_t part_bytes;
+} SnnPpoActorHead;
+size_t snn_ppo_head_part_bytes(const SnnDesc* d, int64_t B);
+int snn_bwd_ppo_top(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs, int64_t B,
+                    const SnnPpoActorHead* head, const void* trace, void* workspace, size_t workspace_bytes, void* stream);
+int snn_bwd_rest(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs, int64_t B, const void* trace,
+                 const SnnGrads* g, void* workspace, size_t workspace_bytes, void* stream);
+int snn_ppo_value_loss(const float* value, const float* returns, const float* target_v, int64_t B, float clip, float value_coef,
+                       int clipped_value, float* g_value, void* part, size_t part_bytes, void* stream);
+int snn_ppo_finalize(const SnnDesc* d, int64_t B, const void* head_part, const void* value_part, const float* log_std,
+                     float ent_coef, float* g_log_std, float* stats, float* kl_out, void* stream);
+
 /* RolloutStorage.compute_returns (STO:124-138): reverse GAE scan over S steps and N envs plus
  * the global advantage normalisation.  rewards/values/returns/advantages are [S,N] fp32,
  * dones [S,N] uint8, last_values [N].  scratch: >= 16 KiB. */
@@ -204,6 +239,12 @@ int snn_lr_adapt(const float* kl, float kl_scale, float desired_kl, float* lr, v
 int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
                   double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream);
+/* The same with the adaptive-KL learning-rate rule of snn_lr_adapt applied first, in the same launch (kl nullable:
+ * no schedule).  lr is updated in place.  One kernel: lr rule, gradient norm, grid barrier, clip + Adam
+ * (AMP/.../algorithms/ppo.py:145-148, 176-177). */
+int snn_clip_adam_kl(float* params, const float* grads, float* m, float* v, int64_t n, float* lr, int* step,
+                     double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                     const float* kl, float kl_scale, float desired_kl, float* norm_out, void* scratch, void* stream);
 
 /* Adaptation-module regression of the RMA fork (RMA/.../rsl_rl/algorithms/ppo.py:200-213): loss = F.mse_loss(pred,
  * target) over n = B*D contiguous elements, g = d loss / d pred = 2 (pred - target) / n; loss_accum[0] += loss.

@@ -126,3 +126,90 @@ def test_lr_adapt_all_branches(kl, lr0, expect):
         lr = torch.full((1,), lr0, device="cuda")
         _lib.check(_lib.lib().snn_lr_adapt(_p(k), 1.0 / world, 0.01, _p(lr), _stream()), "snn_lr_adapt")
         assert abs(lr.item() / expect - 1) < 1e-6
+
+
+@pytest.mark.parametrize("B,dims,tanh", [(24576, (48, 256, 256, 12), 0), (2050, (169, 512, 256, 128, 10), 1)])
+def test_split_head_matches_torch_head_and_one_shot_backward(B, dims, tanh):
+    """The fused PPO step's split head (snn_bwd_ppo_top + snn_ppo_value_loss + snn_ppo_finalize + snn_bwd_rest):
+    mu bit-equal to the layered decoder, d loss / d mu / value / log_std and the loss statistics against torch autograd
+    on that mu, and every actor gradient against the one-shot snn_bwd fed with the SAME d loss / d mu."""
+    import math
+    from fullysnnforleggedrobots_b200 import PopSpikeActor, _lib
+    torch.manual_seed(B)
+    O, A = dims[0], dims[-1]
+    actor = PopSpikeActor(O, A, 10, 10, list(dims[1:-1]), (-5, 5), math.sqrt(0.15), spike_ts=5, dec_tanh=bool(tanh)).cuda()
+    eng = actor.engine
+    layers = actor.snn.linear_layers()
+    params = (actor.encoder.mean.data, actor.encoder.std.data, [l.weight.data for l in layers], [l.bias.data for l in layers],
+              actor.decoder.decoder.weight.data, actor.decoder.decoder.bias.data)
+    g = torch.Generator(device="cuda").manual_seed(B + A)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    obs = r(B, O)
+    mu_ref, trace = eng.forward(obs, *params, train=True)
+    _, trace2 = eng.forward(obs, *params, train=True, out_mu=False, assume_packed=True)
+    log_std = r(A) * 0.2 - 0.1
+    old_mu, old_sigma = mu_ref + r(B, A) * 0.1, torch.exp(log_std + 0.05 * r(A)).expand(B, A).contiguous()
+    actions = old_mu + old_sigma * r(B, A)
+    old_logp = torch.distributions.Normal(old_mu, old_sigma).log_prob(actions).sum(-1)
+    adv, returns, value = r(B), r(B), r(B)
+    target_v = value + 0.3 * r(B)
+    clip, vcoef, ecoef = 0.2, 1.0, 0.01
+    L = _lib.lib()
+    part = torch.empty(eng.ppo_head_part_bytes(B), dtype=torch.uint8, device="cuda")
+    vpart = torch.empty(((B + 255) // 256) * 4, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(eng.workspace_bytes(B, True), dtype=torch.uint8, device="cuda")
+    mu, g_mu = torch.empty(B, A, device="cuda"), torch.empty(B, A, device="cuda")
+    g_value, g_log_std, stats, klo = torch.empty(B, device="cuda"), torch.empty(A, device="cuda"), torch.zeros(8, device="cuda"), torch.zeros(1, device="cuda")
+    eng.backward_ppo_top(obs, trace2, params, log_std, actions, old_logp, adv, old_mu, old_sigma, clip, part, ws,
+                         out_mu=mu, out_g_mu=g_mu)
+    _lib.check(L.snn_ppo_value_loss(_p(value), _p(returns), _p(target_v), B, clip, vcoef, 1, _p(g_value), _p(vpart),
+                                    vpart.numel(), _stream()), "snn_ppo_value_loss")
+    _lib.check(L.snn_ppo_finalize(C.byref(eng.desc), B, _p(part), _p(vpart), _p(log_std), ecoef, _p(g_log_std), _p(stats),
+                                  _p(klo), _stream()), "snn_ppo_finalize")
+    out = {"enc_mean": torch.empty_like(params[0]), "enc_std": torch.empty_like(params[1]),
+           "weights": [torch.empty_like(w) for w in params[2]], "biases": [torch.empty_like(b) for b in params[3]],
+           "dec_w": torch.empty_like(params[4]), "dec_b": torch.empty_like(params[5]), "obs": None}
+    eng.backward_rest(obs, trace2, params, out, ws)
+    assert torch.equal(mu, mu_ref)
+    gm, gv, gl, sur, vl, kl, ent = torch_head(mu_ref, log_std, value, actions, old_logp, adv, returns, target_v, old_mu,
+                                              old_sigma, clip, vcoef, ecoef, True)
+    assert rel_err(g_mu.cpu(), gm.cpu()) < 1e-4
+    assert rel_err(g_value.cpu(), gv.cpu()) < 1e-5
+    assert rel_err(g_log_std.cpu(), gl.cpu()) < 1e-4
+    s = stats.cpu()
+    assert abs(s[0].item() - sur) < 1e-5 * max(1.0, abs(sur))
+    assert abs(s[1].item() - vl) < 1e-5 * max(1.0, abs(vl))
+    assert abs(s[2].item() - kl) < 1e-4 * max(1.0, abs(kl)) and abs(klo.item() - s[2].item()) == 0.0
+    assert abs(s[3].item() - ent) < 1e-5 * max(1.0, abs(ent))
+    ref = eng.backward(obs, mu_ref, g_mu, trace, *params, need_dobs=False)
+    for k in ("enc_mean", "enc_std", "dec_w", "dec_b"):
+        assert rel_err(out[k].cpu(), ref[k].cpu()) < 2e-6, k
+    for i in range(len(layers)):
+        assert rel_err(out["weights"][i].cpu(), ref["weights"][i].cpu()) < 2e-6, f"dW{i}"
+        assert rel_err(out["biases"][i].cpu(), ref["biases"][i].cpu()) < 2e-6, f"db{i}"
+
+
+def test_clip_adam_kl_applies_the_schedule_first():
+    """snn_clip_adam_kl == snn_lr_adapt followed by snn_clip_adam (same lr, same parameters, bit for bit)."""
+    from fullysnnforleggedrobots_b200 import _lib
+    L = _lib.lib()
+    n = 303_117
+    g = torch.Generator(device="cuda").manual_seed(5)
+    prm0, grad = torch.randn(n, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g) * 0.01
+    for klv in (0.05, 0.001, 0.01):
+        res = []
+        for fused in (False, True):
+            prm, m, v = prm0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+            lr, step = torch.full((1,), 1e-3, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+            kl, scratch = torch.full((1,), klv, device="cuda"), torch.empty(4096, dtype=torch.uint8, device="cuda")
+            for _ in range(3):
+                if fused:
+                    _lib.check(L.snn_clip_adam_kl(_p(prm), _p(grad), _p(m), _p(v), n, _p(lr), _p(step), 0.9, 0.999, 1e-8, 0.0,
+                                                  1.0, 1.0, _p(kl), 1.0, 0.01, None, _p(scratch), _stream()), "snn_clip_adam_kl")
+                else:
+                    _lib.check(L.snn_lr_adapt(_p(kl), 1.0, 0.01, _p(lr), _stream()), "snn_lr_adapt")
+                    _lib.check(L.snn_clip_adam(_p(prm), _p(grad), _p(m), _p(v), n, _p(lr), _p(step), 0.9, 0.999, 1e-8, 0.0,
+                                               1.0, 1.0, None, _p(scratch), _stream()), "snn_clip_adam")
+            res.append((prm, lr.clone(), step.clone()))
+        assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+        assert torch.equal(res[0][0], res[1][0])
