@@ -308,6 +308,7 @@ class AMPPPO(PPO):
             if self._fast_state is None or self._fast_state["mb"] != mb:
                 self._fast_setup(mb)
             self.refresh_packed()
+            self.optimizer.zero_grad()     # once per update (PPO._step_fast: the fused kernels overwrite their gradients)
             steps = ((lambda i=i: self._run_fast(f, i)) for _ in range(self.num_learning_epochs)
                      for i in range(self.num_mini_batches))
         else:

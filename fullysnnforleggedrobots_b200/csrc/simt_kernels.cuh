@@ -320,18 +320,27 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   uint8_t* const grow = g_img + (static_cast<size_t>(chunk) * tg.Rt + r0) * 128 + (lane & 3) * 4 +
                         ((piece ^ static_cast<uint32_t>(r0 & 7)) << 4);
   const size_t gstep = static_cast<size_t>(tg.Bt) * 128;
-  float gvn0 = 0.f, gvn1 = 0.f, gcn0 = 0.f, gcn1 = 0.f, db0 = 0.f, db1 = 0.f;
+  // the thread's two neurons as one packed fp32 pair (FFMA2 / FADD2 / FMUL2: each lane rounded like the scalar operation)
+  f32x2 gvn = 0ull, gcn = 0ull, db = 0ull;
+  const f32x2 gup = f2_pack(gup0, gup1);
+  const f32x2 k_nc75 = f2_splat(-0.75f * kVoltInv), k_o75 = f2_splat(0.375f * kVoltInv), k_half = f2_splat(0.5f),
+              k_mid = f2_splat(-32767.5f), k_magic = f2_splat(-8388608.f);
   int cnt0 = 0, cnt1 = 0;
   auto step = [&](int t, uint2 v) {
-    const float c0 = volt_t(live ? v.x : 0u, 0), c1 = volt_t(live ? v.y : 0u, 0);      // voltage codes (umma.cuh)
-    cnt0 += volt_spike(c0) ? 1 : 0;
-    cnt1 += volt_spike(c1) ? 1 : 0;
-    const float gs0 = gup0 - gvn0 * volt_value75(c0), gs1 = gup1 - gvn1 * volt_value75(c1);
-    const float win0 = volt_window(c0) ? 1.f : 0.f, win1 = volt_window(c1) ? 1.f : 0.f;
-    const float gv0 = gs0 * win0 + gvn0 * (volt_spike(c0) ? 0.f : 0.75f), gv1 = gs1 * win1 + gvn1 * (volt_spike(c1) ? 0.f : 0.75f);
-    const float gc0 = gv0 + 0.5f * gcn0, gc1 = gv1 + 0.5f * gcn1;
-    gvn0 = gv0; gvn1 = gv1; gcn0 = gc0; gcn1 = gc1;
-    db0 += gc0; db1 += gc1;
+    // voltage codes (umma.cuh) as floats t in [0, 65535]; u = t - 32767.5: spike <=> u > 0, window <=> |u| < 32767
+    const f32x2 t2 = f2_add(f2_pack(__uint_as_float(0x4B000000u | (live ? v.x : 0u)), __uint_as_float(0x4B000000u | (live ? v.y : 0u))), k_magic);
+    const f32x2 u2 = f2_add(t2, k_mid);
+    const bool sp0 = f2_lo(u2) > 0.f, sp1 = f2_hi(u2) > 0.f;
+    cnt0 += sp0 ? 1 : 0;
+    cnt1 += sp1 ? 1 : 0;
+    const f32x2 win2 = f2_pack(fabsf(f2_lo(u2)) < 32767.f ? 1.f : 0.f, fabsf(f2_hi(u2)) < 32767.f ? 1.f : 0.f);
+    const f32x2 keep2 = f2_pack(sp0 ? 0.f : 0.75f, sp1 ? 0.f : 0.75f);
+    const f32x2 gs2 = f2_fma(gvn, f2_fma(t2, k_nc75, k_o75), gup);          // g_up - g_v(t+1) * 0.75 v
+    const f32x2 gv2 = f2_fma(gvn, keep2, f2_mul(gs2, win2));
+    const f32x2 gc2 = f2_fma(k_half, gcn, gv2);
+    gvn = gv2; gcn = gc2;
+    db = f2_add(db, gc2);
+    const float gc0 = f2_lo(gc2), gc1 = f2_hi(gc2);
     const uint32_t hp = pack_bf16x2(gc0, gc1);
     const uint32_t lp = pack_bf16x2(gc0 - __uint_as_float(hp << 16), gc1 - __uint_as_float(hp & 0xFFFF0000u));
     uint8_t* q = grow + static_cast<size_t>(t) * gstep;
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
       *reinterpret_cast<uint32_t*>(q + g_plane) = 0u;
     }
   }
-  s_red[w][0][lane] = db0; s_red[w][1][lane] = db1;
+  s_red[w][0][lane] = f2_lo(db); s_red[w][1][lane] = f2_hi(db);
   s_red[w][4][lane] = G0; s_red[w][5][lane] = G1;
   __syncthreads();                            // also publishes s_rate
   s_red[w][2][lane] = G0 * s_rate[cnt0]; s_red[w][3][lane] = G1 * s_rate[cnt1];

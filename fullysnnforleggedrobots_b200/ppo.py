@@ -113,6 +113,7 @@ class PPO:
         # fused step: decoder + policy terms of the PPO head on the actor's chain, value loss on the critic's branch,
         # finalize on a third one (SNN_SPLIT_HEAD=0: the one-kernel head snn_ppo_head after a join of the two chains)
         self.split_head = os.environ.get("SNN_SPLIT_HEAD", "1") != "0"
+        self.update_graph = os.environ.get("SNN_UPDATE_GRAPH", "1") != "0"      # one graph per update() (0: one per step)
         # capture the actor chain on a high-priority stream: where both chains have thread blocks pending, the
         # actor's (the critical path) are placed first (measured: 14.96 -> 14.61 ms per update; SNN_ACTOR_PRIO=0: off)
         self.actor_high_priority = os.environ.get("SNN_ACTOR_PRIO", "1") != "0"
@@ -396,6 +397,7 @@ class PPO:
         return (mb, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
                 bool(self.use_clipped_value_loss), self.desired_kl, self.schedule, self.max_grad_norm,
                 tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), self.overlap_critic, self.split_head,
+                self.update_graph, self.num_learning_epochs, self.num_mini_batches,
                 1 if self.dp is None else self.dp.world_size,
                 tuple(sorted((k, v.data_ptr()) for k, v in f.items())))
 
@@ -449,9 +451,15 @@ class PPO:
         ac, opt = self.actor_critic, self.optimizer
         dev = opt.flat_params.device
         em, es, ws, bs, dw, db = st["actor_tensors"]
-        opt.zero_grad()
         eng = ac.actor.engine
         ce = st["critic"]
+        # The gradient bucket is cleared per step only on the paths that ACCUMULATE into it (torch autograd for a critic
+        # that is not on the fused kernels).  Every fused kernel overwrites its slice (actor: snn_bwd*, critic: snn_mlp_bwd,
+        # log_std and the KL tail: the PPO head's finalize), and update() clears the bucket once per call for parameters no
+        # kernel writes (the reference's unused `std`).  The per-step fill sat on the critical path between the re-pack
+        # and the next step's encoder.
+        if ce is None:
+            opt.zero_grad()
         side = st.get("side_stream") if ce is not None else None
         main = torch.cuda.current_stream(dev)
         if ce is not None:
@@ -634,6 +642,27 @@ class PPO:
         self._graphs[i].replay()
         self.replayed_kernel_launches += self._graph_launches[i]
 
+    def _run_update_graph(self, f):
+        """Single process: ALL minibatch steps of the update (epochs x minibatches) as ONE CUDA graph — between two
+        per-step graph replays the GPU idles for 5-8 us (the next graph's launch), 19 times per update at C2.  The steps
+        read the permuted fields `f` in place, so the same graph serves every update until the signature changes.
+        Returns False when this mode does not apply (eager mode, data parallel: per-step graphs around the all-reduce)."""
+        if not self.use_cuda_graph or self.dp is not None or not self.update_graph:
+            return False
+        if "update" not in self._graphs:
+            def all_steps():
+                for _ in range(self.num_learning_epochs):
+                    for i in range(self.num_mini_batches):
+                        self._step_fast(f, i)
+            cap = self._capture(all_steps, self._snapshot(), "the PPO update")
+            if cap is None:
+                self.use_cuda_graph = False
+                return False
+            self._graphs["update"], self._graph_launches["update"] = cap
+        self._graphs["update"].replay()
+        self.replayed_kernel_launches += self._graph_launches["update"]
+        return True
+
     def _snapshot(self):
         opt = self.optimizer
         return (opt.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_dev.clone(),
@@ -665,9 +694,11 @@ class PPO:
             if sig != self._graph_sig:                 # a hyperparameter or a buffer address changed: re-capture
                 self._graphs, self._graph_launches, self._graph_sig = {}, {}, sig
             self.refresh_packed()      # the fused steps assume current planes (parameters may have been loaded since)
-            for _ in range(self.num_learning_epochs):
-                for i in range(self.num_mini_batches):
-                    self._run_fast(f, i)
+            self.optimizer.zero_grad()     # once per update: see _step_fast
+            if not self._run_update_graph(f):
+                for _ in range(self.num_learning_epochs):
+                    for i in range(self.num_mini_batches):
+                        self._run_fast(f, i)
         else:
             for batch in self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs):
                 self._step_generic(batch)

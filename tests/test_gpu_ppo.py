@@ -375,3 +375,33 @@ def test_act_graph_static_buffers_accept_other_modes_and_strides():
         mu_eager = ac.act_inference(view.contiguous())
     assert alg._act_state["graph"] is not None and alg.act_cuda_graph
     assert rel_err(mu_graph.cpu(), mu_eager.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_fused_steps_overwrite_every_gradient_they_use(graph):
+    """The fused path clears the gradient bucket once per update(), not per minibatch step: every fused kernel must then
+    OVERWRITE its slice.  Poison the bucket right after that clear (everything but the reference's unused `std`): the
+    update must come out exactly as from a clean bucket."""
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    res = []
+    for poison in (False, True):
+        ac, alg = make_alg(pc, use_cuda_graph=graph)
+        fill_storage(alg, pc, g, ro)
+        alg.compute_returns(ro["last_obs"].cuda())
+        opt = alg.optimizer
+        if poison:
+            clear = opt.zero_grad
+
+            def poisoned(*a, **k):
+                clear(*a, **k)
+                for name, p in ac.named_parameters():
+                    if name != "std":
+                        p.grad.fill_(float("nan"))
+                opt.flat_grads[opt.n:].fill_(float("nan"))
+            opt.zero_grad = poisoned
+        torch.manual_seed(7)
+        res.append((alg.update(), {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}))
+    assert res[0][0] == res[1][0]
+    for k in res[0][1]:
+        assert torch.isfinite(res[1][1][k]).all(), k
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
