@@ -581,7 +581,8 @@ def run_ours(args):
     dk, dl = max(sites, key=lambda kl: pms32[kl[0] + 4 * kl[1]])
     di = dk + 4 * dl
     dom_name = f"{['fwd', 'dx', 'dw'][dk]}_layer{dl}"
-    dom_kernel = ["nm_gemm_kernel<FWD>", "nm_gemm_kernel<DX>" if dl > 0 else "nm_gemm_kernel<DX_ENC>", "dw_gemm_kernel"][dk] + f" (actor layer {dl})"
+    dom_kernel = (["nm_gemm_kernel<FWD>", "nm_gemm_kernel<DX>" if dl > 0 else "nm_gemm_kernel<DX_ENC>"][dk] + f" (actor layer {dl})"
+                  if dk < 2 else "dw_gemm_multi_kernel (weight gradients of all actor layers, one launch)")
     achieved = pfl32[di] / (pms32[di] * 1e-3) / 1e12
     traffic, pipe_pct, smem_pct = None, None, None
     tj, tpath = latest_traffic()
@@ -609,7 +610,8 @@ def run_ours(args):
                                 "capture (a profiler never runs inside a bench run); achieved / frac are measured live"},
         "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
         "note": "achieved = ALGORITHMIC flops (2*B*K*N*T per layer GEMM, one product per MAC) / CUDA-event kernel time; "
-                "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC, so issued tensor work is 3x 'achieved'; "
+                "fp32-parity mode issues 3 bf16-plane MMAs per algorithmic MAC in the forward / dX kernels and 2 in dW (g_c "
+                "hi + lo planes x exact spikes), so issued tensor work is 3x / 2x 'achieved'; "
                 "kernel times from an eager re-run of the timed steps (the timed region itself replays CUDA graphs)",
         "whole_step": {"algo_tflops": samples_per_step * 5345280 / (ms_per_step * 1e-3) / 1e12,
                        "frac": samples_per_step * 5345280 / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
@@ -647,7 +649,7 @@ def run_ours(args):
                    "arithmetic": "fp32-parity: weights as three exact bf16 planes (hi+mid+lo == W), spikes exact, fp32 "
                                  "accumulation on the tensor cores; backward operands as hi/lo bf16 pairs (3 products)",
                    "parallelism": f"dp{world}", "envs_per_gpu": N,
-                   "l2": "inputs larger than L2: 54 MB rollout + 0.3 GB traces per minibatch vs 126 MB L2",
+                   "l2": "inputs larger than L2: 54 MB rollout + 0.17 GB traces + 0.7 GB gradient planes per minibatch vs 126 MB L2",
                    "cuda_graphs": graphs_used, "build_flags": int(L.snn_build_flags())},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 8},

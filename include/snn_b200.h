@@ -79,7 +79,7 @@ int snn_build_flags(void);
 
 /* Sizes of the caller-owned buffers, in bytes.  B = batch rows of the call. */
 size_t snn_packed_weights_bytes(const SnnDesc* d);           /* bf16 plane images of all layers */
-size_t snn_trace_bytes(const SnnDesc* d, int64_t B);         /* spike bits + fp32 voltage traces */
+size_t snn_trace_bytes(const SnnDesc* d, int64_t B);         /* spike bits + 16-bit voltage-code traces */
 size_t snn_workspace_bytes(const SnnDesc* d, int64_t B, int backward);
 
 /* Split every fp32 weight matrix into bf16 hi/mid/lo planes laid out as swizzled tensor-core

@@ -63,7 +63,7 @@ def run(name, O, H, A, T, B_fwd, B_bwd, variant=None, dobs=False):
         del obs
     width = sum(((h + 127) // 128) * 128 for h in list(H) + [A * 10])
     for B in B_bwd:
-        need = B * T * width * (4 + 4 + 4) * 1.1      # voltage trace + two bf16 g_c planes (all layers kept for dW)
+        need = B * T * width * (2 + 4 + 4) * 1.1      # 16-bit voltage codes + two bf16 g_c planes (all layers kept for dW)
         if need > MEM_CAP:
             rows.append((name, T, B, "fwd+BPTT", None, None, f"skipped: ~{need / 1e9:.0f} GB of traces"))
             continue
