@@ -433,7 +433,9 @@ def run_ours(args):
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         dp_check = {"ranks": world, "params_bit_identical": bool(all(torch.equal(c, allc[0]) for c in allc)),
-                    "param_sum": float(chk[0].item()), "dp_graph": alg.dp_graph_mode, "dp_graph_note": alg.dp_graph_note}
+                    "param_sum": float(chk[0].item()), "dp_graph": alg.dp_graph_mode, "dp_graph_note": alg.dp_graph_note,
+                    "dp_collective": "peer-memory sum inside the optimizer kernel (snn_clip_adam_kl_p2p)" if alg.dp_p2p
+                    else "nccl all-reduce (" + getattr(alg.dp, "p2p_note", "") + ")"}
     else:
         dp_check = {"ranks": 1, "params_bit_identical": True, "param_sum": float(chk[0].item()), "dp_graph": "n/a",
                     "dp_graph_note": ""}

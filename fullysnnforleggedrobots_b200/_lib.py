@@ -154,6 +154,14 @@ _SIGS = {
                       + [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_clip_adam_kl": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2 + [C.c_float] * 4
                          + [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snn_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "snn_p2p_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "snn_p2p_close": (C.c_int, [C.c_void_p]),
+    "snn_p2p_free": (C.c_int, [C.c_void_p]),
+    "snn_clip_adam_kl_p2p": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p] + [C.c_double] * 2
+                             + [C.c_float] * 4 + [C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64,
+                                                  C.c_void_p, C.c_void_p]),
     "snn_mse_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snn_profile_enable": (C.c_int, [C.c_int]),
     "snn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -1063,6 +1063,65 @@ int snn_clip_adam_kl(float* params, const float* grads, float* m, float* v, int6
   return SNN_OK;
 }
 
+// ---- peer-memory buffers of the data-parallel optimizer kernel (one process per GPU, same node: CUDA IPC over NVLink)
+int snn_p2p_alloc(size_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(SNN_EINVAL, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  CUDA_TRY(cudaMemset(p, 0, bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return SNN_OK;
+}
+int snn_p2p_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(SNN_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));      // maps the peer's allocation into this device
+  *ptr = p;
+  return SNN_OK;
+}
+int snn_p2p_close(void* ptr) { if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr)); return SNN_OK; }
+int snn_p2p_free(void* ptr) { if (ptr) CUDA_TRY(cudaFree(ptr)); return SNN_OK; }
+
+int snn_clip_adam_kl_p2p(float* params, float* grads, float* m, float* v, int64_t n, int64_t n_reduce, float* lr, int* step,
+                         double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                         int64_t kl_index, float kl_scale, float desired_kl, float* norm_out, void* scratch,
+                         void* const* stage, void* const* flags, int rank, int world, int64_t stage_stride, int* epoch,
+                         void* stream) {
+  if (!params || !grads || !m || !v || !lr || !step || !scratch || !stage || !flags || !epoch) return fail(SNN_EINVAL, "null pointer");
+  if (n <= 0 || n_reduce < n || n_reduce > stage_stride) return fail(SNN_EINVAL, "bad sizes (n <= n_reduce <= stage_stride)");
+  if (world < 2 || world > kP2PMaxWorld || rank < 0 || rank >= world) return fail(SNN_EINVAL, "world size 2..8");
+  if (kl_index >= n_reduce) return fail(SNN_EINVAL, "kl_index outside the reduced range");
+  int sms = 0;
+  int rc = device_ready(&sms);
+  if (rc) return rc;
+  P2PPeers peers{};
+  for (int q = 0; q < world; ++q) {
+    if (!stage[q] || !flags[q]) return fail(SNN_EINVAL, "null peer pointer");
+    peers.stage[q] = static_cast<float*>(stage[q]);
+    peers.flags[q] = static_cast<int*>(flags[q]);
+  }
+  peers.rank = rank; peers.world = world; peers.stage_stride = stage_stride;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // at most one block per SM: every block is resident, which the kernel's grid barriers rely on
+  int nb = static_cast<int>((n_reduce + 256 * 8 - 1) / (256 * 8));
+  if (nb > sms) nb = sms;
+  if (nb > kAdamCoefs) nb = kAdamCoefs;
+  { ProfScope prof__(CAT_OTHER, 0.0, st);
+  p2p_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, n_reduce, static_cast<float*>(scratch), step, lr, kl_index, kl_scale,
+                                      desired_kl, beta1, beta2, eps, weight_decay, max_norm, grad_scale, norm_out, count_slot(),
+                                      epoch, peers);
+  }
+  LAUNCH_CHECK("p2p_adam_kernel");
+  return SNN_OK;
+}
+
 int snn_clip_adam(float* params, const float* grads, float* m, float* v, int64_t n, const float* lr, int* step,
                   double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   float* norm_out, void* scratch, void* stream) {

@@ -388,6 +388,182 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ prm
   }
 }
 
+// ------------------------------------------------------------------ data parallel: gradient all-reduce + optimizer in ONE kernel
+// Data-parallel PPO sums the flat gradient bucket (and the KL statistic in its tail) over the ranks between the backward
+// pass and the optimizer (one NCCL all-reduce per minibatch step until r2: ~30 us of a 600 us step, nothing to
+// overlap it with).  Here the collective is part of the optimizer kernel, over NVLink peer memory:
+//   phase 0  every rank copies its bucket into its own STAGING buffer (peer-mapped, double-buffered by step parity), grid
+//            barrier, then announces the step number in every peer's flag array (st.release.sys) and waits for all peers'
+//            announcements (ld.acquire.sys, bounded at ~30 s: a lost peer traps instead of hanging the GPU)
+//   phase A  every block reads its slice from ALL ranks' staging buffers and sums them in rank order 0..W-1 — the same
+//            order on every rank, so the ranks' parameters stay bit-identical — writes the sum back into the local bucket
+//            (the all-reduce's result) and accumulates the squared norm; block 0 sums the KL tail the same way, applies the
+//            adaptive learning-rate rule and derives Adam's step coefficients
+//   grid barrier, phase B = clip + Adam as in adam_fused_kernel.
+// A rank re-writes a staging buffer two steps later, after the flag exchange of the step in between, which every peer
+// enters only once it has finished reading: no second barrier.  1.2 MB per rank at C1: W x 1.2 MB of NVLink reads per GPU.
+constexpr int kP2PMaxWorld = 8;
+struct P2PPeers {
+  float* stage[kP2PMaxWorld];      // rank q's staging buffer [2][stage_stride] (own entry: local memory)
+  int* flags[kP2PMaxWorld];        // rank q's flag array [kP2PMaxWorld]: slot r = last step announced by rank r
+  int rank, world;
+  long long stage_stride;          // floats per parity half
+};
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(int* counter, int target) {      // thread 0 of every block; all blocks resident
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1);
+    while (atomicAdd(counter, 0) < target) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, float* __restrict__ g, float* __restrict__ m,
+                                                      float* __restrict__ v, int64_t n, int64_t n_reduce,
+                                                      float* __restrict__ partial, int* __restrict__ step, float* __restrict__ lr,
+                                                      int64_t kl_index, float kl_scale, float desired_kl, double beta1d,
+                                                      double beta2d, float eps, float weight_decay, float max_norm,
+                                                      float grad_scale, float* __restrict__ norm_out, int* __restrict__ counters,
+                                                      int* __restrict__ epoch, const P2PPeers peers) {
+  __shared__ float sh[8];
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ double s_tot[8];
+  const int W = peers.world;
+  const int ep = epoch[0] + 1;                                           // this step's number (written back at the end)
+  const long long half = static_cast<long long>(ep & 1) * peers.stage_stride;
+  const int64_t per = (n_reduce + gridDim.x - 1) / gridDim.x;            // contiguous slice per block
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * per, i1 = i0 + per < n_reduce ? i0 + per : n_reduce;
+  // ---- phase 0: publish the local bucket
+  {
+    float* mine = peers.stage[peers.rank] + half;
+    for (int64_t b = i0 + threadIdx.x; b < i1; b += 1024) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = b + u * 256 < i1 ? g[b + u * 256] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (b + u * 256 < i1) mine[b + u * 256] = x[u];
+    }
+    __threadfence_system();
+  }
+  grid_barrier(counters, static_cast<int>(gridDim.x));
+  if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(peers.flags[threadIdx.x] + peers.rank, ep);
+  if (threadIdx.x < W) {
+    const int* f = peers.flags[peers.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) - ep < 0) {
+      if (clock64() - t0 > 60000000000LL) __trap();                     // a peer never arrived (~30 s): fail, do not hang
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  // ---- phase A: sum over the ranks in rank order, squared norm of the scaled sum
+  if (blockIdx.x == 0 && threadIdx.x == 32) {      // a lane of warp 1: warp 0's lane 0 finishes the block sum below
+    float l = lr[0];
+    if (kl_index >= 0) {
+      float ks = 0.f;
+      for (int q = 0; q < W; ++q) ks += ld_relaxed_sys(peers.stage[q] + half + kl_index);
+      const float k = ks * kl_scale;
+      if (k > desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
+      else if (k < desired_kl / 2.0f && k > 0.0f) l = fminf(1e-2f, l * 1.5f);
+      lr[0] = l;
+    }
+    const int s1 = step[0] + 1;
+    const double t = static_cast<double>(s1);
+    const double bc1 = 1.0 - pow(beta1d, t);
+    const double bc2 = 1.0 - pow(beta2d, t);
+    partial[kAdamCoefs] = static_cast<float>(static_cast<double>(l) / bc1);
+    partial[kAdamCoefs + 1] = static_cast<float>(sqrt(bc2));
+    step[0] = s1;
+  }
+  float acc = 0.f;
+  for (int64_t b = i0 + threadIdx.x; b < i1; b += 1024) {
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < W; ++q) {
+      const float* src = peers.stage[q] + half;
+      float y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) y[u] = b + u * 256 < i1 ? ld_relaxed_sys(src + b + u * 256) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] += y[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = b + u * 256;
+      if (i < i1) {
+        g[i] = x[u];
+        if (i < n) { const float z = x[u] * grad_scale; acc += z * z; }
+      }
+    }
+  }
+  const float t = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  grid_barrier(counters + 1, static_cast<int>(gridDim.x));
+  // ---- phase B: clip + Adam (adam_fused_kernel)
+  const float beta2 = static_cast<float>(beta2d);
+  const float omb1 = static_cast<float>(1.0 - beta1d), omb2 = static_cast<float>(1.0 - beta2d);
+  {
+    double tt = 0.0;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 256) tt += __ldcg(partial + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tt += __shfl_down_sync(0xffffffffu, tt, o);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = tt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += s_tot[i];
+    const float norm = static_cast<float>(sqrt(tot));
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    s_coef = coef;
+    s_step_size = __ldcg(partial + kAdamCoefs);
+    s_bc2_sqrt = __ldcg(partial + kAdamCoefs + 1);
+    if (blockIdx.x == 0 && norm_out != nullptr) norm_out[0] = norm;
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const int64_t j1 = i1 < n ? i1 : n;
+  for (int64_t b = i0 + threadIdx.x; b < j1; b += 1024) {
+    float gi[4], pi[4], mi[4], vi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = b + u * 256;
+      const bool on = i < j1;
+      gi[u] = on ? g[i] : 0.f; pi[u] = on ? prm[i] : 0.f; mi[u] = on ? m[i] : 0.f; vi[u] = on ? v[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = b + u * 256;
+      if (i >= j1) continue;
+      float gg = gi[u] * grad_scale * coef;
+      if (weight_decay != 0.f) gg = gg + weight_decay * pi[u];
+      const float mm = mi[u] + (gg - mi[u]) * omb1;
+      const float vv = vi[u] * beta2 + gg * gg * omb2;
+      m[i] = mm;
+      v[i] = vv;
+      const float denom = sqrtf(vv) / bc2_sqrt + eps;
+      prm[i] = pi[u] - step_size * (mm / denom);
+    }
+  }
+  if (threadIdx.x == 0 && atomicAdd(counters + 2, 1) == static_cast<int>(gridDim.x) - 1) {
+    counters[0] = 0; counters[1] = 0; counters[2] = 0;
+    epoch[0] = ep;
+  }
+}
+
 // ------------------------------------------------------------------ adaptation-module regression (RMA fork)
 // F.mse_loss(pred, target) and its gradient (RMA/.../rsl_rl/algorithms/ppo.py:200-213): loss = mean over all n = B*D
 // elements of (pred - target)^2; g = 2 (pred - target) / n.  Block partial sums in a fixed order (bit-reproducible).

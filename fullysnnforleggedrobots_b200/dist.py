@@ -4,6 +4,10 @@ parameters replicated, and ONE all-reduce (sum) of the flattened actor-critic gr
 the update is the single-process algorithm.
 
 NCCL over NVLink on the GPU box; the same code runs under gloo on CPU for the world_size-2 tests.
+
+r2: on CUDA the per-step all-reduce is not an NCCL call any more but part of the optimizer kernel (`P2PGradientSum`,
+snn_clip_adam_kl_p2p: every rank reads all ranks' gradient buckets over NVLink peer memory and sums them in rank order);
+NCCL / gloo keep the rendezvous, the parameter broadcast and the once-per-iteration advantage statistics.
 """
 from __future__ import annotations
 
@@ -49,12 +53,91 @@ def normalize_advantages_global(adv: torch.Tensor, allreduce_sum) -> torch.Tenso
     return (adv - mean.to(adv.dtype)) / (var.clamp_min(0).sqrt().to(adv.dtype) + 1e-8)
 
 
+class P2PGradientSum:
+    """Peer-mapped staging buffers + flag arrays of all ranks for snn_clip_adam_kl_p2p (one node, 2..8 ranks).
+    Every rank cudaMallocs its own buffers inside the library, the CUDA IPC handles travel through
+    `all_gather_object`, every rank opens the others'.  Raises when any rank cannot set it up (the caller falls back to
+    the NCCL all-reduce on every rank alike)."""
+
+    def __init__(self, n_floats: int, group=None):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        self.world_size, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not 2 <= self.world_size <= 8:
+            raise RuntimeError("peer-memory gradient sum: 2..8 ranks")
+        self.stride = (int(n_floats) + 255) // 256 * 256
+        own, handles, err = [], [], None
+        try:
+            for nbytes in (2 * self.stride * 4, 256):
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                _lib.check(L.snn_p2p_alloc(nbytes, C.byref(ptr), h), "snn_p2p_alloc")
+                own.append(ptr.value)
+                handles.append(h.raw)
+        except Exception as e:  # noqa: BLE001   (reported to every rank below)
+            err = str(e)
+        everyone = [None] * self.world_size
+        dist.all_gather_object(everyone, (handles, err), group=group)
+        bad = [e for _, e in everyone if e is not None]
+        self._own, self._opened = own, []
+        if bad:
+            self.close()
+            raise RuntimeError("peer-memory gradient sum unavailable: " + bad[0])
+        stage, flags = (C.c_void_p * self.world_size)(), (C.c_void_p * self.world_size)()
+        ok = True
+        try:
+            for q, (hs, _) in enumerate(everyone):
+                if q == self.rank:
+                    stage[q], flags[q] = own[0], own[1]
+                    continue
+                for k, arr in ((0, stage), (1, flags)):
+                    ptr = C.c_void_p()
+                    _lib.check(L.snn_p2p_open(hs[k], C.byref(ptr)), "snn_p2p_open")
+                    self._opened.append(ptr.value)
+                    arr[q] = ptr.value
+        except Exception as e:  # noqa: BLE001
+            ok, err = False, str(e)
+        flags_ok = [None] * self.world_size
+        dist.all_gather_object(flags_ok, ok, group=group)
+        if not all(flags_ok):
+            self.close()
+            raise RuntimeError("peer-memory gradient sum unavailable: " + (err or "a peer could not map the buffers"))
+        self.stage, self.flags = stage, flags
+        self.epoch = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def close(self):
+        from . import _lib
+        L = _lib.lib()
+        for p in getattr(self, "_opened", []):
+            L.snn_p2p_close(p)
+        for p in getattr(self, "_own", []):
+            L.snn_p2p_free(p)
+        self._opened, self._own = [], []
+
+
 class GradientAllReducer:
     def __init__(self, group=None):
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._flat = None
+        self.p2p = None             # P2PGradientSum once enable_p2p() succeeded
+
+    def enable_p2p(self, n_floats: int) -> bool:
+        """Set the peer-memory gradient sum up for a bucket of n_floats (all ranks call this together).  False (and a
+        note in `p2p_note`) when it is unavailable: not CUDA, more than 8 ranks, SNN_DP_P2P=0, IPC mapping failed."""
+        self.p2p_note = ""
+        if self.p2p is not None and self.p2p.stride >= n_floats:
+            return True
+        if os.environ.get("SNN_DP_P2P", "1") == "0" or not torch.cuda.is_available() or dist.get_backend(self.group) != "nccl":
+            self.p2p_note = "disabled (SNN_DP_P2P=0 or not a CUDA / NCCL job)"
+            return False
+        try:
+            self.p2p = P2PGradientSum(n_floats, self.group)
+            return True
+        except RuntimeError as e:
+            self.p2p, self.p2p_note = None, str(e)
+            return False
 
     def broadcast_parameters(self, module: torch.nn.Module, src: int = 0):
         for t in list(module.parameters()) + list(module.buffers()):

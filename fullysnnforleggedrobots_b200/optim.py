@@ -84,6 +84,26 @@ class FlatAdam(torch.optim.Optimizer):
         self.set_lr(self.param_groups[0]["lr"])
 
     @torch.no_grad()
+    def step_p2p(self, p2p, max_grad_norm: float = 0.0, grad_scale: float = 1.0, adaptive: bool = False,
+                 kl_scale: float = 1.0, desired_kl: float = 0.0):
+        """Data-parallel step: the sum of the whole bucket (gradients + the KL statistic in its tail) over the ranks, the
+        adaptive-KL rule on the summed statistic, clip and Adam in ONE kernel over peer memory (dist.P2PGradientSum)."""
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        dev = self.flat_params.device
+        ntot = self.flat_grads.numel()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().snn_clip_adam_kl_p2p(
+                C.c_void_p(self.flat_params.data_ptr()), C.c_void_p(self.flat_grads.data_ptr()),
+                C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), self.n, ntot,
+                C.c_void_p(self.lr_dev.data_ptr()), C.c_void_p(self.step_dev.data_ptr()), float(b1), float(b2),
+                float(g["eps"]), float(g["weight_decay"]), float(max_grad_norm), float(grad_scale),
+                self.n if adaptive else -1, float(kl_scale), float(desired_kl),
+                C.c_void_p(self.norm_dev.data_ptr()), C.c_void_p(self._scratch.data_ptr()), p2p.stage, p2p.flags,
+                p2p.rank, p2p.world_size, p2p.stride, C.c_void_p(p2p.epoch.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "snn_clip_adam_kl_p2p")
+
+    @torch.no_grad()
     def step(self, max_grad_norm: float = 0.0, grad_scale: float = 1.0, closure=None, kl=None, kl_scale: float = 1.0,
              desired_kl: float = 0.0):
         """clip (if max_grad_norm > 0) + Adam on the flat buffers; lr is read from lr_dev on the device.

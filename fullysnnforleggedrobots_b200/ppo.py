@@ -125,6 +125,11 @@ class PPO:
         # data parallel: "single" = the NCCL all-reduce is captured inside the step graph, "segments" = two graph
         # segments around an eager all-reduce (see _run_fast_dp)
         self.dp_graph_mode = os.environ.get("SNN_DP_GRAPH", "single")
+        # data parallel on CUDA: the sum of the gradient bucket over the ranks inside the optimizer kernel, over NVLink
+        # peer memory (all ranks set it up together; False = NCCL all-reduce between backward and optimizer)
+        self.dp_p2p = bool(self.dp is not None and self.optimizer.flat_params.is_cuda and hasattr(self.dp, "enable_p2p")
+                           and self.dp.enable_p2p(self.optimizer.flat_grads.numel()))
+        self._p2p_obj = self.dp.p2p if self.dp_p2p else None      # this instance's buffers (its graphs bake the pointers in)
         self.dp_graph_note = ""
         self.replayed_kernel_launches = 0      # kernels of this library launched through CUDA-graph replays
         self._fast_state = None
@@ -344,9 +349,15 @@ class PPO:
     def _adaptive(self):
         return self.desired_kl is not None and self.schedule == 'adaptive'
 
+    def _p2p(self):
+        """The peer-memory gradient sum of a data-parallel CUDA job (dist.P2PGradientSum), or None: single process, CPU /
+        gloo, SNN_DP_P2P=0, or the IPC mapping failed (then every rank falls back to the NCCL all-reduce alike)."""
+        return self._p2p_obj if self.dp_p2p else None
+
     def _finish_step(self):
-        """all-reduce (data parallel) -> adaptive lr -> clip + Adam -> re-pack: shared by both paths."""
-        if self.dp is not None:
+        """all-reduce (data parallel) -> adaptive lr -> clip + Adam -> re-pack: shared by both paths.  With peer memory
+        the sum over the ranks is part of the optimizer kernel (snn_clip_adam_kl_p2p): no collective call at all."""
+        if self.dp is not None and self._p2p() is None:
             self.dp.allreduce_sum(self.optimizer.flat_grads)   # ONE collective: gradients + KL statistic in the tail
         self._post_allreduce()
 
@@ -354,6 +365,14 @@ class PPO:
         opt = self.optimizer
         world = 1 if self.dp is None else self.dp.world_size
         dev = opt.flat_params.device
+        p2p = self._p2p()
+        if p2p is not None:
+            adaptive = self._adaptive()
+            opt.step_p2p(p2p, max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0,
+                         grad_scale=1.0 / world, adaptive=adaptive, kl_scale=1.0 / world,
+                         desired_kl=float(self.desired_kl) if adaptive else 0.0)
+            self._repack_actor()
+            return
         # adaptive lr (ppo.py:145-148) + clip + Adam: one kernel (the KL statistic sits in the tail of the gradient bucket)
         adaptive = self._adaptive()
         opt.step(max_grad_norm=self.max_grad_norm if self.max_grad_norm is not None else 0.0, grad_scale=1.0 / world,
@@ -398,7 +417,7 @@ class PPO:
                 bool(self.use_clipped_value_loss), self.desired_kl, self.schedule, self.max_grad_norm,
                 tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]), self.overlap_critic, self.split_head,
                 self.update_graph, self.num_learning_epochs, self.num_mini_batches,
-                1 if self.dp is None else self.dp.world_size,
+                1 if self.dp is None else self.dp.world_size, self.dp_p2p,
                 tuple(sorted((k, v.data_ptr()) for k, v in f.items())))
 
     def _fast_setup(self, mb):
@@ -647,8 +666,8 @@ class PPO:
         per-step graph replays the GPU idles for 5-8 us (the next graph's launch), 19 times per update at C2.  The steps
         read the permuted fields `f` in place, so the same graph serves every update until the signature changes.
         Returns False when this mode does not apply (eager mode, data parallel: per-step graphs around the all-reduce)."""
-        if not self.use_cuda_graph or self.dp is not None or not self.update_graph:
-            return False
+        if not self.use_cuda_graph or (self.dp is not None and self._p2p() is None) or not self.update_graph:
+            return False      # NCCL inside the graph: one graph per step (_run_fast_dp), as validated in r2
         if "update" not in self._graphs:
             def all_steps():
                 for _ in range(self.num_learning_epochs):

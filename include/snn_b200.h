@@ -246,6 +246,24 @@ int snn_clip_adam_kl(float* params, const float* grads, float* m, float* v, int6
                      double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                      const float* kl, float kl_scale, float desired_kl, float* norm_out, void* scratch, void* stream);
 
+/* Data parallel (one process per GPU, one node): the gradient all-reduce INSIDE the optimizer kernel, over NVLink peer
+ * memory instead of an NCCL call between the backward pass and snn_clip_adam.  Every rank owns a staging
+ * buffer of 2 * stage_stride floats and a flag array of 8 ints (snn_p2p_alloc: cudaMalloc + zero + CUDA IPC handle; the
+ * handles are exchanged by the caller, e.g. torch.distributed.all_gather_object, and opened with snn_p2p_open).
+ * snn_clip_adam_kl_p2p: grads[0..n_reduce) <- sum over the ranks (rank order: bit-identical on every rank), then the
+ * adaptive-KL rule on the summed grads[kl_index] (kl_index < 0: none), gradient norm, clip, Adam over params[0..n), all in
+ * one launch.  stage / flags: host arrays of `world` device pointers (entry `rank` = the local buffers); epoch: a device
+ * int, zero at start, owned by the kernel.  Every rank must make the same sequence of calls.  world 2..8. */
+int snn_p2p_alloc(size_t bytes, void** ptr, void* handle64);
+int snn_p2p_open(const void* handle64, void** ptr);
+int snn_p2p_close(void* ptr);
+int snn_p2p_free(void* ptr);
+int snn_clip_adam_kl_p2p(float* params, float* grads, float* m, float* v, int64_t n, int64_t n_reduce, float* lr, int* step,
+                         double beta1, double beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                         int64_t kl_index, float kl_scale, float desired_kl, float* norm_out, void* scratch,
+                         void* const* stage, void* const* flags, int rank, int world, int64_t stage_stride, int* epoch,
+                         void* stream);
+
 /* Adaptation-module regression of the RMA fork (RMA/.../rsl_rl/algorithms/ppo.py:200-213): loss = F.mse_loss(pred,
  * target) over n = B*D contiguous elements, g = d loss / d pred = 2 (pred - target) / n; loss_accum[0] += loss.
  * scratch >= 1 KiB. */

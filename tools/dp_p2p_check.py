@@ -1,0 +1,74 @@
+"""2+ ranks (torchrun): the data-parallel PPO update with the gradient sum inside the optimizer kernel (peer memory,
+snn_clip_adam_kl_p2p) against the NCCL all-reduce path, same seeds.  With two ranks a + b is the same float either way, so
+the parameters must come out BIT-identical; with more ranks NCCL's summation order is its own and the check is a tolerance.
+Prints one line per mode (ms per update, parameter checksum) and the verdict."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+
+from fullysnnforleggedrobots_b200 import PPO, ActorCriticAMP
+from fullysnnforleggedrobots_b200 import dist as snn_dist
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+dev = torch.device("cuda", torch.cuda.current_device())
+dist.init_process_group("nccl")
+N, S, O, A = int(os.environ.get("ENVS", "4096")), 24, 48, 12
+res = {}
+for mode in ("1", "0", "1"):
+    os.environ["SNN_DP_P2P"] = mode
+    torch.manual_seed(0)
+    ac = ActorCriticAMP(O, O, A, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256], activation="elu",
+                        init_noise_std=1.0, spike_ts=5)
+    alg = PPO(ac, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01, device=dev, data_parallel=snn_dist.GradientAllReducer())
+    alg.init_storage(N, S, [O], [None], [A])
+    g = torch.Generator().manual_seed(1234 + rank)
+    obs, rew = torch.randn(S, N, O, generator=g).to(dev), torch.randn(S, N, generator=g).to(dev)
+    done, last = (torch.rand(S, N, generator=g) < 0.02).to(torch.uint8).to(dev), torch.randn(N, O, generator=g).to(dev)
+    torch.manual_seed(4321 + rank)
+    with torch.inference_mode():
+        for s in range(S):
+            alg.act(obs[s], obs[s])
+            alg.process_env_step(rew[s], done[s], {})
+        alg.compute_returns(last)
+    first = None
+    for _ in range(3):
+        torch.manual_seed(99)
+        alg.update()
+        if first is None:
+            first = alg.optimizer.flat_params.clone()      # after ONE update (20 optimizer steps) from identical states
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        torch.manual_seed(99)
+        alg.update()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 5 * 1e3
+    flat = alg.optimizer.flat_params
+    chk = torch.stack([flat.double().sum(), flat.view(torch.int32).to(torch.int64).sum().double()])
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    same = all(torch.equal(c, allc[0]) for c in allc)
+    res.setdefault(mode, []).append((flat.clone(), first.clone(), ms))
+    if rank == 0:
+        print(f"SNN_DP_P2P={mode}: p2p active {alg.dp_p2p} ({getattr(alg.dp, 'p2p_note', '')}), graphs {list(alg._graphs)[:2]}, "
+              f"{ms:.3f} ms per update (wall), ranks bit-identical {same}, param sum {chk[0].item():.9f}", flush=True)
+if rank == 0:
+    # the step is not bit-reproducible run to run (the critic's bias gradient is summed with shared-memory float atomics),
+    # and spike-threshold ties amplify last-bit differences over many optimizer steps: the yardstick for "p2p vs nccl" is
+    # "p2p vs the same p2p run again"
+    for k, what in ((1, "after 1 update"), (0, "after 8 updates")):
+        a, a2, b = res["1"][0][k], res["1"][1][k], res["0"][0][k]
+        print(f"{what}: p2p vs nccl bit-identical {bool(torch.equal(a, b))}, max |diff| {float((a - b).abs().max()):.3e};  "
+              f"p2p vs p2p again bit-identical {bool(torch.equal(a, a2))}, max |diff| {float((a - a2).abs().max()):.3e}", flush=True)
+dist.barrier()
+torch.cuda.synchronize()
+os._exit(0)
