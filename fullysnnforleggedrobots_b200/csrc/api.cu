@@ -1109,6 +1109,7 @@ int snn_clip_adam_kl_p2p(float* params, float* grads, float* m, float* v, int64_
   }
   peers.rank = rank; peers.world = world; peers.stage_stride = stage_stride;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int one_shot = [] { const char* e = getenv("SNN_P2P_ONE_SHOT"); return e && e[0] == '1' ? 1 : 0; }();   // validation switch
   // at most one block per SM: every block is resident, which the kernel's grid barriers rely on
   int nb = static_cast<int>((n_reduce + 256 * 8 - 1) / (256 * 8));
   if (nb > sms) nb = sms;
@@ -1116,7 +1117,7 @@ int snn_clip_adam_kl_p2p(float* params, float* grads, float* m, float* v, int64_
   { ProfScope prof__(CAT_OTHER, 0.0, st);
   p2p_adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, n_reduce, static_cast<float*>(scratch), step, lr, kl_index, kl_scale,
                                       desired_kl, beta1, beta2, eps, weight_decay, max_norm, grad_scale, norm_out, count_slot(),
-                                      epoch, peers);
+                                      epoch, peers, one_shot);
   }
   LAUNCH_CHECK("p2p_adam_kernel");
   return SNN_OK;

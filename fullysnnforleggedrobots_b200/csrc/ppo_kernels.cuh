@@ -395,13 +395,14 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ prm
 //   phase 0  every rank copies its bucket into its own STAGING buffer (peer-mapped, double-buffered by step parity), grid
 //            barrier, then announces the step number in every peer's flag array (st.release.sys) and waits for all peers'
 //            announcements (ld.acquire.sys, bounded at ~30 s: a lost peer traps instead of hanging the GPU)
-//   phase A  every block reads its slice from ALL ranks' staging buffers and sums them in rank order 0..W-1 — the same
-//            order on every rank, so the ranks' parameters stay bit-identical — writes the sum back into the local bucket
-//            (the all-reduce's result) and accumulates the squared norm; block 0 sums the KL tail the same way, applies the
-//            adaptive learning-rate rule and derives Adam's step coefficients
+//   phase A  the sum over the ranks, every element in rank order 0..W-1 and read back identically by every rank, so the
+//            ranks' parameters stay bit-identical: two ranks read both buckets (one shot); more ranks reduce-scatter
+//            (every rank sums its segment in place in its staging buffer), exchange flags once more and all-gather.  The
+//            result goes back into the local bucket (the all-reduce's result) while the squared norm is accumulated;
+//            block 0 applies the adaptive learning-rate rule to the summed KL tail and derives Adam's step coefficients
 //   grid barrier, phase B = clip + Adam as in adam_fused_kernel.
 // A rank re-writes a staging buffer two steps later, after the flag exchange of the step in between, which every peer
-// enters only once it has finished reading: no second barrier.  1.2 MB per rank at C1: W x 1.2 MB of NVLink reads per GPU.
+// enters only once it has finished reading: no barrier at the end.  1.2 MB per rank at C1.
 constexpr int kP2PMaxWorld = 8;
 struct P2PPeers {
   float* stage[kP2PMaxWorld];      // rank q's staging buffer [2][stage_stride] (own entry: local memory)
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, 
                                                       int64_t kl_index, float kl_scale, float desired_kl, double beta1d,
                                                       double beta2d, float eps, float weight_decay, float max_norm,
                                                       float grad_scale, float* __restrict__ norm_out, int* __restrict__ counters,
-                                                      int* __restrict__ epoch, const P2PPeers peers) {
+                                                      int* __restrict__ epoch, const P2PPeers peers, int one_shot) {
   __shared__ float sh[8];
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   __shared__ double s_tot[8];
@@ -445,6 +446,19 @@ __global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, 
   const long long half = static_cast<long long>(ep & 1) * peers.stage_stride;
   const int64_t per = (n_reduce + gridDim.x - 1) / gridDim.x;            // contiguous slice per block
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * per, i1 = i0 + per < n_reduce ? i0 + per : n_reduce;
+  // announce `what` to every peer (block 0) and wait until every peer has announced at least as much (all blocks)
+  auto exchange = [&](int what) {
+    if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(peers.flags[threadIdx.x] + peers.rank, what);
+    if (threadIdx.x < W) {
+      const int* f = peers.flags[peers.rank] + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) - what < 0) {
+        if (clock64() - t0 > 60000000000LL) __trap();                     // a peer never arrived (~30 s): fail, do not hang
+        __nanosleep(32);
+      }
+    }
+    __syncthreads();
+  };
   // ---- phase 0: publish the local bucket
   {
     float* mine = peers.stage[peers.rank] + half;
@@ -459,22 +473,46 @@ __global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, 
     __threadfence_system();
   }
   grid_barrier(counters, static_cast<int>(gridDim.x));
-  if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(peers.flags[threadIdx.x] + peers.rank, ep);
-  if (threadIdx.x < W) {
-    const int* f = peers.flags[peers.rank] + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) - ep < 0) {
-      if (clock64() - t0 > 60000000000LL) __trap();                     // a peer never arrived (~30 s): fail, do not hang
-      __nanosleep(32);
+  exchange(2 * ep);
+  // ---- phase A: sum over the ranks in rank order.  Two ranks: every rank reads both buckets (one shot).  More: every
+  // rank sums ITS segment of the bucket from all ranks, in place in its staging buffer, a second exchange, then every
+  // rank gathers the segments from their owners (reduce-scatter + all-gather: 2 x the bucket over NVLink per GPU instead
+  // of W x).  Either way every element is one sum in rank order, read back identically by every rank.
+  const bool two_shot = W > 2 && !one_shot;      // one_shot: the two-rank scheme at any world size (validation switch)
+  const int64_t seg = (n_reduce + W - 1) / W;
+  if (two_shot) {
+    const int64_t s0 = seg * peers.rank, s1 = s0 + seg < n_reduce ? s0 + seg : n_reduce;
+    const int64_t sper = (seg + gridDim.x - 1) / gridDim.x;
+    const int64_t j0 = s0 + static_cast<int64_t>(blockIdx.x) * sper, j1 = j0 + sper < s1 ? j0 + sper : s1;
+    float* mine = peers.stage[peers.rank] + half;
+    for (int64_t b = j0 + threadIdx.x; b < j1; b += 1024) {
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < W; ++q) {
+        const float* src = peers.stage[q] + half;
+        float y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y[u] = b + u * 256 < j1 ? ld_relaxed_sys(src + b + u * 256) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] += y[u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (b + u * 256 < j1) mine[b + u * 256] = x[u];
     }
+    __threadfence_system();
+    grid_barrier(counters + 3, static_cast<int>(gridDim.x));
+    exchange(2 * ep + 1);
   }
-  __syncthreads();
-  // ---- phase A: sum over the ranks in rank order, squared norm of the scaled sum
   if (blockIdx.x == 0 && threadIdx.x == 32) {      // a lane of warp 1: warp 0's lane 0 finishes the block sum below
     float l = lr[0];
     if (kl_index >= 0) {
       float ks = 0.f;
-      for (int q = 0; q < W; ++q) ks += ld_relaxed_sys(peers.stage[q] + half + kl_index);
+      if (two_shot) {
+        int owner = static_cast<int>(kl_index / seg);
+        ks = ld_relaxed_sys(peers.stage[owner < W ? owner : W - 1] + half + kl_index);
+      } else {
+        for (int q = 0; q < W; ++q) ks += ld_relaxed_sys(peers.stage[q] + half + kl_index);
+      }
       const float k = ks * kl_scale;
       if (k > desired_kl * 2.0f) l = fmaxf(1e-5f, l / 1.5f);
       else if (k < desired_kl / 2.0f && k > 0.0f) l = fminf(1e-2f, l * 1.5f);
@@ -491,13 +529,24 @@ __global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, 
   float acc = 0.f;
   for (int64_t b = i0 + threadIdx.x; b < i1; b += 1024) {
     float x[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < W; ++q) {
-      const float* src = peers.stage[q] + half;
-      float y[4];
+    if (two_shot) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) y[u] = b + u * 256 < i1 ? ld_relaxed_sys(src + b + u * 256) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = b + u * 256;
+        if (i < i1) {
+          const int owner = static_cast<int>(i / seg);
+          x[u] = ld_relaxed_sys(peers.stage[owner] + half + i);
+        }
+      }
+    } else {
+      for (int q = 0; q < W; ++q) {
+        const float* src = peers.stage[q] + half;
+        float y[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] += y[u];
+        for (int u = 0; u < 4; ++u) y[u] = b + u * 256 < i1 ? ld_relaxed_sys(src + b + u * 256) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] += y[u];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -559,7 +608,7 @@ __global__ void __launch_bounds__(256) p2p_adam_kernel(float* __restrict__ prm, 
     }
   }
   if (threadIdx.x == 0 && atomicAdd(counters + 2, 1) == static_cast<int>(gridDim.x) - 1) {
-    counters[0] = 0; counters[1] = 0; counters[2] = 0;
+    counters[0] = 0; counters[1] = 0; counters[2] = 0; counters[3] = 0;
     epoch[0] = ep;
   }
 }

@@ -20,14 +20,18 @@ dev = torch.device("cuda", torch.cuda.current_device())
 dist.init_process_group("nccl")
 N, S, O, A = int(os.environ.get("ENVS", "4096")), 24, 48, 12
 res = {}
-for mode in ("1", "0", "1"):
-    os.environ["SNN_DP_P2P"] = mode
+for mode in os.environ.get("MODES", "1,0,1").split(","):
+    os.environ["SNN_DP_P2P"] = mode[0]
+    os.environ["SNN_UPDATE_GRAPH"] = "0" if mode.endswith("s") else "1"      # "1s" / "0s": one graph per step
+    # (SNN_P2P_ONE_SHOT=1 in the environment: every rank reads all buckets at any world size — validation of the
+    # reduce-scatter + all-gather scheme that runs for more than two ranks)
     torch.manual_seed(0)
     ac = ActorCriticAMP(O, O, A, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256], activation="elu",
                         init_noise_std=1.0, spike_ts=5)
     alg = PPO(ac, num_learning_epochs=5, num_mini_batches=4, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
-              entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
-              desired_kl=0.01, device=dev, data_parallel=snn_dist.GradientAllReducer())
+              entropy_coef=0.01, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True, schedule=os.environ.get("SCHEDULE", "adaptive"),
+              desired_kl=0.01, device=dev, data_parallel=snn_dist.GradientAllReducer(),
+              use_cuda_graph=os.environ.get("GRAPH", "1") != "0")
     alg.init_storage(N, S, [O], [None], [A])
     g = torch.Generator().manual_seed(1234 + rank)
     obs, rew = torch.randn(S, N, O, generator=g).to(dev), torch.randn(S, N, generator=g).to(dev)
@@ -62,13 +66,17 @@ for mode in ("1", "0", "1"):
         print(f"SNN_DP_P2P={mode}: p2p active {alg.dp_p2p} ({getattr(alg.dp, 'p2p_note', '')}), graphs {list(alg._graphs)[:2]}, "
               f"{ms:.3f} ms per update (wall), ranks bit-identical {same}, param sum {chk[0].item():.9f}", flush=True)
 if rank == 0:
-    # the step is not bit-reproducible run to run (the critic's bias gradient is summed with shared-memory float atomics),
-    # and spike-threshold ties amplify last-bit differences over many optimizer steps: the yardstick for "p2p vs nccl" is
-    # "p2p vs the same p2p run again"
+    # The step is not bit-reproducible run to run (the critic's bias gradient is summed with shared-memory float atomics),
+    # spike-threshold ties amplify last-bit differences, and with schedule="adaptive" a KL statistic near one of the
+    # rule's thresholds flips a x1.5 learning-rate decision (two "attractors" 1e-2 apart, reached by EITHER path from run
+    # to run).  The yardstick for "p2p vs nccl" is therefore a repeated run of the same mode; SCHEDULE=fixed removes the
+    # learning-rate bifurcation.
+    runs = [(f"{k}#{i}", r) for k, v in res.items() for i, r in enumerate(v)]
     for k, what in ((1, "after 1 update"), (0, "after 8 updates")):
-        a, a2, b = res["1"][0][k], res["1"][1][k], res["0"][0][k]
-        print(f"{what}: p2p vs nccl bit-identical {bool(torch.equal(a, b))}, max |diff| {float((a - b).abs().max()):.3e};  "
-              f"p2p vs p2p again bit-identical {bool(torch.equal(a, a2))}, max |diff| {float((a - a2).abs().max()):.3e}", flush=True)
+        for i in range(len(runs)):
+            for j in range(i + 1, len(runs)):
+                a, b = runs[i][1][k], runs[j][1][k]
+                print(f"{what}: {runs[i][0]} vs {runs[j][0]}: max |diff| {float((a - b).abs().max()):.3e}", flush=True)
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)
