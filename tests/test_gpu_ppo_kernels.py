@@ -213,3 +213,21 @@ def test_clip_adam_kl_applies_the_schedule_first():
             res.append((prm, lr.clone(), step.clone()))
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
         assert torch.equal(res[0][0], res[1][0])
+
+
+def test_peer_memory_allreduce_adam_matches_nccl_on_all_visible_gpus():
+    """snn_clip_adam_kl_p2p (the gradient all-reduce inside the optimizer kernel, NVLink peer memory) against NCCL
+    all_reduce + snn_clip_adam_kl, one process per visible GPU (tools/dp_p2p_unit.py under torchrun).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    n = min(n, 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                        "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "dp_p2p_unit.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout.splitlines()[-1] and "MISMATCH" not in r.stdout, r.stdout[-2000:]
