@@ -15,7 +15,7 @@
 //              straight into the operand slot by the expander warps.
 //              Epilogue = LIF update (AMP/.../modules/actor_critic.py:216-232): c = .5c + (Wx+b);
 //              v = .75 v (1-s) + c; s = v > .5.  Spike words come out of a warp bit transpose (lane = neuron); emits the
-//              16-bit voltage-code trace (umma.cuh: volt_code) when training.
+//              16-bit voltage-code trace (umma.cuh: volt_code2) when training.
 //   NM_DX      A = hi/lo planes of W^T (K-major), B = hi/lo planes of g_c of the layer above (swz64 image with rows =
 //              sample-steps: K-major, one bulk copy per plane); three products hi*hi + lo*hi + hi*lo.  Epilogue = BPTT recurrence of
 //              SURVEY.md §8a for the layer below (surrogate gradient of PseudoSpikeRect, actor_critic.py:154-167).
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
                     ((vmask >> (lane & 15)) & 1u) ? wd : 0u;
             }
             if (emit_v) {
-              // 16-bit voltage codes (umma.cuh: volt_code), [neuron / 32][sample-step / 8][32 neurons][8 sample-steps]:
+              // 16-bit voltage codes (umma.cuh: volt_code2), [neuron / 32][sample-step / 8][32 neurons][8 sample-steps]:
               // the thread's 16 sample-steps are two 16-byte pieces, the warp's 16 x 32 codes one contiguous 1 KiB block
               uint4* dst = reinterpret_cast<uint4*>(p.v_out + (static_cast<size_t>(n >> 5) * p.Rt + c) * 32) + lane;
               dst[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);

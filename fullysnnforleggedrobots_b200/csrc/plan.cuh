@@ -16,7 +16,7 @@
 //   * g_c (time-stepped bf16 hi/lo planes): swz64 image with rows = sample-steps r, columns = neurons — the K-major
 //     B operand of dX and the MN-major A operand of dW; the epilogue threads (= neurons) of a warp store 64
 //     contiguous bytes of one row.
-//   * voltages: 16-bit codes (umma.cuh: volt_code — spike flag exact, surrogate-window flag exact up to its edge, the
+//   * voltages: 16-bit codes (umma.cuh: volt_code2 — spike flag exact, surrogate-window flag exact up to its edge, the
 //     value inside the window to 2^-17) [NP/32][Rt/8][32 neurons][8 sample-steps]: an epilogue thread (= neuron) reads /
 //     writes the 16 sample-steps of a group as two 16-byte pieces, its warp (32 consecutive neurons) one contiguous 1 KiB
 //     block.

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
     gup1 = __fdiv_rn(G1 * dec_w[n0 + 1], Tf);
   }
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
-  // voltage codes (umma.cuh: volt_code) [NP/32][Rt/8][32 neurons][8 sample-steps]; Bt % 16 == 0, so every timestep's
+  // voltage codes (umma.cuh: volt_code2) [NP/32][Rt/8][32 neurons][8 sample-steps]; Bt % 16 == 0, so every timestep's
   // row has r0's phase r0 % 8.  The 8 warps of a block are 8 consecutive samples: together they read whole 16-byte pieces.
   const uint16_t* vsrc = volt + ((static_cast<size_t>(n0 >> 5) * tg.Rt + (r0 & ~static_cast<size_t>(7))) * 32) + (n0 & 31) * 8 + (r0 & 7);
   const size_t vstep = static_cast<size_t>(tg.Bt) * 32;        // codes between timesteps

@@ -83,16 +83,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
-// 1-D shared -> shared copy by the same engine (destination: this CTA's own shared memory, addressed in the
-// shared::cluster window), completion signalled on an mbarrier.
-__device__ __forceinline__ void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "r"(smem_u32(src_smem)), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
 // ------------------------------------------------------------------ TMEM
 // One full warp allocates `ncols` (power of two >= 32) columns; base address lands in *dst_smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -250,33 +240,22 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
 // -0.5): both sit on the window's edge, where the surrogate is discontinuous anyway.  Half the bytes of an fp32 trace.
 constexpr float kVoltScale = 65534.f;
 constexpr float kVoltInv = 1.f / 65534.f;
-// All on the fp32 pipe: clamp to [0, 65535 / 65534], then 2^23 + ceil(65534 v) by ONE fused multiply-add rounded towards
-// +inf (exact product, no double rounding).  Returns the float whose low 16 bits are the code (the caller packs two of
-// them with one byte permute).  The saturating conversion cvt.rpi.u16.f32 gives the same codes but runs on the
-// quarter-rate conversion pipe: forward layer 1 59.9 vs 57.8 us (profiles/r2k_encab.txt).
-__device__ __forceinline__ uint32_t volt_code(float v) {
-  const float vc = fminf(fmaxf(v, 0.f), 65535.f / 65534.f);
-  return __float_as_uint(__fmaf_ru(vc, kVoltScale, 8388608.f));
-}
-// the code as a float t in [0, 65535]: bytes {k.lo, k.hi, 0x00, 0x4B} are the float 2^23 + k (one byte permute)
-__device__ __forceinline__ float volt_t(uint32_t word, int upper) {
-  return __uint_as_float(__byte_perm(word, 0x4B000000u, upper ? 0x7632u : 0x7610u)) - 8388608.f;
-}
-// both codes of a 32-bit trace word as floats {t(low half), t(high half)}
+// both codes of a 32-bit trace word as floats {t(low half), t(high half)}, t in [0, 65535]: bytes {k.lo, k.hi, 0x00, 0x4B}
+// are the float 2^23 + k (one byte permute each).  With u = t - 32767.5: spike <=> u > 0, window <=> |u| < 32767,
+// 0.75 v = t * (0.75 / 65534) - 0.375 / 65534 inside the window.
 __device__ __forceinline__ f32x2 volt_t2(uint32_t word) {
   return f2_add(f2_pack(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7610u)), __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7632u))),
                 f2_splat(-8388608.f));
 }
-// two voltages -> one trace word (see volt_code)
+// two voltages -> one trace word, all on the fp32 pipe: clamp to [0, 65535 / 65534], then 2^23 + ceil(65534 v) by ONE fused
+// multiply-add rounded towards +inf (exact product, no double rounding), the two low halves merged by a byte permute.
+// (The saturating conversion cvt.rpi.u16.f32 gives the same codes but runs on the quarter-rate conversion pipe: forward
+// layer 1 59.9 vs 57.8 us, profiles/r2k_encab.txt.)
 __device__ __forceinline__ uint32_t volt_code2(float v0, float v1) {
   const float hi = 65535.f / 65534.f;
   const f32x2 k = f2_fma_ru(f2_pack(fminf(fmaxf(v0, 0.f), hi), fminf(fmaxf(v1, 0.f), hi)), f2_splat(kVoltScale), f2_splat(8388608.f));
   return __byte_perm(static_cast<uint32_t>(k), static_cast<uint32_t>(k >> 32), 0x5410u);
 }
-__device__ __forceinline__ float volt_value(float t) { return __fmaf_rn(t, kVoltInv, -0.5f * kVoltInv); }           // v inside the window
-__device__ __forceinline__ float volt_value75(float t) { return __fmaf_rn(t, 0.75f * kVoltInv, -0.375f * kVoltInv); }  // 0.75 v
-__device__ __forceinline__ bool volt_spike(float t) { return t > 32767.f; }
-__device__ __forceinline__ bool volt_window(float t) { return fabsf(t - 32767.5f) < 32767.f; }      // 1 <= k <= 65534
 
 __device__ __forceinline__ float bf16_round(float x) {   // value of bf16(x) as fp32
   uint32_t r;

@@ -304,7 +304,7 @@ class SnnEngine:
         for l in range(Lc):
             NP, KP, boff, voff = (int(arr[8 + 4 * l + i]) for i in range(4))
             res["spikes"].append(bits(boff, NP, self.dims[l + 1]))
-            # voltage trace: 16-bit codes [NP / 32][Rt / 8][32 neurons][8 sample-steps] (csrc/umma.cuh: volt_code).
+            # voltage trace: 16-bit codes [NP / 32][Rt / 8][32 neurons][8 sample-steps] (csrc/umma.cuh: volt_code2).
             # 0 = below the surrogate window (decoded 0.0), 0xFFFF = above it (decoded 1.0), k in 1..65534 = inside,
             # v = (k - 0.5) / 65534 to 2^-17 — the value the backward kernels use.
             c = raw[voff: voff + Rt * NP * 2].view(torch.int16).reshape(NP // 32, Rt // 8, 32, 8)

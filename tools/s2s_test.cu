@@ -5,6 +5,17 @@
 #include "umma.cuh"
 using namespace snn;
 
+// 1-D shared -> shared copy by the bulk-copy engine (destination: this CTA's own shared memory, addressed in the
+// shared::cluster window), completion signalled on an mbarrier.  (Lived in umma.cuh while the forward kernel staged its
+// spike operand through such a copy, r1; nothing in the library uses it since r2.)
+__device__ __forceinline__ void bulk_s2s(void* dst_smem, const void* src_smem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "r"(smem_u32(src_smem)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 __global__ void __launch_bounds__(128, 1) s2s_kernel(uint32_t* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
