@@ -370,27 +370,28 @@ __global__ void __launch_bounds__(kActThreads, 1) act_fused_kernel(const ActPara
           const uint32_t vmask = nlive >= 16 ? 0xFFFFu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u));
           const uint32_t t_acc = t_lane + static_cast<uint32_t>(mt * p.wd + col0);
           uint8_t* const xrow = xbuf + (n >> 3) * 1024 + (n & 7) * 128;
-          float cur[16], vol[16];
+          // LIF state as packed fp32 pairs of neighbouring samples (FADD2 / FFMA2 / FMUL2, each lane rounded like the scalar
+          // operation); vst = v (1 - s): the reset is applied when the spike is decided; c * 0.5 is exact, so the fused
+          // multiply-add rounds once like the reference's separate add — the same code as the training forward
+          // (nm_gemm.cuh), bit-identical spikes
+          f32x2 cur[8], vst[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { cur[j] = 0.f; vol[j] = 0.f; }
-          uint32_t sprev = 0;
+          for (int i = 0; i < 8; ++i) { cur[i] = 0ull; vst[i] = 0ull; }
+          const f32x2 bias2 = f2_splat(bias), k_half = f2_splat(0.5f), k_075 = f2_splat(0.75f);
           uint32_t c4[4] = {0, 0, 0, 0};                                  // spike counts of the 16 samples, one byte each
-          uint32_t x[16], xn[16];
-          tmem_ld16(t_acc, x);
-          tmem_ld_wait();
-          for (int t = 0; t < p.T; ++t) {
-            if (t + 1 < p.T) tmem_ld16(t_acc + static_cast<uint32_t>((t + 1) * p.Bt), xn);
+          auto lif_step = [&](const uint32_t (&x)[16], int t) {
             uint32_t scur = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float syn = __fadd_rn(__uint_as_float(x[j]), bias);
-              const float cj = __fadd_rn(__fmul_rn(cur[j], 0.5f), syn);
-              const float vj = ((sprev >> j) & 1u) ? cj : __fadd_rn(__fmul_rn(vol[j], 0.75f), cj);
-              cur[j] = cj;
-              vol[j] = vj;
-              scur |= (vj > 0.5f ? 1u : 0u) << j;
+            for (int i = 0; i < 8; ++i) {
+              const f32x2 syn2 = f2_add(f2_pack(__uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1])), bias2);
+              const f32x2 c2 = f2_fma(cur[i], k_half, syn2);
+              const f32x2 v2 = f2_add(f2_mul(vst[i], k_075), c2);
+              const float v0 = f2_lo(v2), v1 = f2_hi(v2);
+              const bool s0 = v0 > 0.5f, s1 = v1 > 0.5f;
+              cur[i] = c2;
+              vst[i] = f2_pack(s0 ? 0.f : v0, s1 ? 0.f : v1);
+              scur |= ((s0 ? 1u : 0u) | (s1 ? 2u : 0u)) << (2 * i);
             }
-            sprev = scur;
             const uint32_t sm = scur & vmask;
             if (!last) {
               // this neuron's row of the next layer's operand: 16 sample-steps = two 16-byte pieces
@@ -406,9 +407,20 @@ __global__ void __launch_bounds__(kActThreads, 1) act_fused_kernel(const ActPara
                 c4[w4] += (nib * 0x00204081u) & 0x01010101u;
               }
             }
+          };
+          // the next step's accumulators are in flight while a step runs (two register sets, ping-pong: no copies)
+          uint32_t xa[16], xb[16];
+          tmem_ld16(t_acc, xa);
+          tmem_ld_wait();
+          for (int t = 0; t < p.T; t += 2) {
+            if (t + 1 < p.T) tmem_ld16(t_acc + static_cast<uint32_t>((t + 1) * p.Bt), xb);
+            lif_step(xa, t);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = xn[j];
+            if (t + 1 < p.T) {
+              if (t + 2 < p.T) tmem_ld16(t_acc + static_cast<uint32_t>((t + 2) * p.Bt), xa);
+              lif_step(xb, t + 1);
+              tmem_ld_wait();
+            }
           }
           if (last) *reinterpret_cast<uint4*>(cnt + static_cast<size_t>(n) * p.Bt + col0) = make_uint4(c4[0], c4[1], c4[2], c4[3]);
         }
