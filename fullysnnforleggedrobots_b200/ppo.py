@@ -643,7 +643,8 @@ class PPO:
                 return self._step_fast(f, i)
             self._graphs["post"], self._graph_launches["post"] = cap
         self._graphs[("pre", i)].replay()
-        self.dp.allreduce_sum(self.optimizer.flat_grads)
+        if self._p2p() is None:        # peer-memory sum: part of the optimizer kernel in the "post" graph
+            self.dp.allreduce_sum(self.optimizer.flat_grads)
         self._graphs["post"].replay()
         self.replayed_kernel_launches += self._graph_launches[("pre", i)] + self._graph_launches["post"]
 
