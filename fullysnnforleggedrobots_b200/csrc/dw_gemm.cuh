@@ -8,7 +8,7 @@
 //   B = input spikes x (exact in bf16), expanded in shared memory from the bit-packed trace
 //       (rows = r = MMA-K, cols = k = MMA-N).
 // One CTA owns one [128 x <=256] fp32 output tile in TMEM and a contiguous slice of r (split-K over
-// the batch); partial tiles go to a workspace and are summed by multi_reduce_partials_kernel — a fixed
+// the batch); partial tiles go to a workspace and are summed by multi_reduce_kernel — a fixed
 // order, so gradients are bit-reproducible run to run.
 #pragma once
 #include "plan.cuh"
