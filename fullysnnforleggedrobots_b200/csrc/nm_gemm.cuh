@@ -105,8 +105,11 @@ template <> struct NmCfg<NM_FWD> {
 };
 // DX: 2 weight stages of 2 x 16 KiB planes, 4 g_c units (one plane of one 64-neuron chunk of one sub-tile:
 // <= 256 sample-steps x 128 B)
+#ifndef SNN_DX_NS
+#define SNN_DX_NS 4
+#endif
 template <> struct NmCfg<NM_DX> {
-  static constexpr int NW = 2, W_STAGE = 32768, NS = 4, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 512;
+  static constexpr int NW = 2, W_STAGE = 32768, NS = SNN_DX_NS, S_STAGE = 32768, NBITS = 0, BITS_STAGE = 0, THREADS = 512;
 };
 template <> struct NmCfg<NM_DX_ENC> : NmCfg<NM_DX> {};
 
@@ -156,9 +159,9 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(bits_ring + C::NBITS * C::BITS_STAGE);
   uint64_t* w_full = bars;                      // [<= 8]
   uint64_t* w_empty = w_full + 8;               // [<= 8]
-  uint64_t* s_full = w_empty + 8;               // [<= 4]
-  uint64_t* s_empty = s_full + 4;               // [<= 4]
-  uint64_t* acc_full = s_empty + 4;             // [2]
+  uint64_t* s_full = w_empty + 8;               // [<= 8]
+  uint64_t* s_empty = s_full + 8;               // [<= 8]
+  uint64_t* acc_full = s_empty + 8;             // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint64_t* bits_full = acc_empty + 2;          // [NBITS]
   uint64_t* bits_empty = bits_full + C::NBITS;  // [NBITS]
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(NmCfg<MODE>::THREADS, 1) nm_gemm_kernel(const 
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     // FWD: an operand slot is full once the four expander warps have written it
-    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], IS_FWD ? 4 : 1); mbar_init(&s_empty[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&s_full[s], IS_FWD ? 4 : 1); mbar_init(&s_empty[s], 1); }
     for (int s = 0; s < C::NBITS; ++s) { mbar_init(&bits_full[s], 1); mbar_init(&bits_empty[s], 4); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], by_set ? 128 : NGRP * 128); }
     // consumers of the tile ring: every warp but the scheduling warp 2 (and, in the dX kernels, the idle warp 3)
