@@ -90,6 +90,10 @@ __global__ void __launch_bounds__(256) value_head_fwd_kernel(const uint8_t* __re
 //   part[blk][0..NP)      = sum_b g_v[b] h[b,n]      (d w_out)
 //   part[blk][NP..2NP)    = sum_b dz[b,n]            (d bias of the last hidden layer)
 //   part[blk][2NP]        = sum_b g_v[b]             (d bias_out)
+#ifndef SNN_VH_AHEAD
+#define SNN_VH_AHEAD 4
+#endif
+constexpr int kVhAhead = SNN_VH_AHEAD;      // 1, 2, 4 or 8 (12.28 / - / 12.18 / 12.22 ms per update on one box: profiles/r2zK_vh_ab.txt)
 __global__ void __launch_bounds__(256) value_head_bwd_kernel(const uint8_t* __restrict__ h_img, size_t h_plane, int Bpad,
                                                             int B, int N, int NP, const float* __restrict__ w,
                                                             const float* __restrict__ g_v, uint8_t* __restrict__ dz_img,
@@ -104,20 +108,31 @@ __global__ void __launch_bounds__(256) value_head_bwd_kernel(const uint8_t* __re
     dw[j] = 0.f; dbh[j] = 0.f;
   }
   float dbo = 0.f;
-  for (int i = 0; i < 8; ++i) {
-    const int b = blockIdx.x * 64 + i * 8 + wid;
+  // kVhAhead rows of this warp are requested before the first of them is used (eight dependent round trips otherwise:
+  // the kernel is pure load latency)
+#pragma unroll
+  for (int c = 0; c < 8; c += kVhAhead) {
+  uint4 qh[kVhAhead], ql[kVhAhead];
+  float gq[kVhAhead];
+#pragma unroll
+  for (int i = 0; i < kVhAhead; ++i) {
+    const int b = blockIdx.x * 64 + (c + i) * 8 + wid;
+    const bool on = b < B && col_live;
+    const size_t off = on ? swz64_offset(b, lane * 8, Bpad) : 0;
+    qh[i] = on ? __ldg(reinterpret_cast<const uint4*>(h_img + off)) : make_uint4(0, 0, 0, 0);
+    ql[i] = on ? __ldg(reinterpret_cast<const uint4*>(h_img + h_plane + off)) : make_uint4(0, 0, 0, 0);
+    gq[i] = b < B ? __ldg(g_v + b) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < kVhAhead; ++i) {
+    const int b = blockIdx.x * 64 + (c + i) * 8 + wid;
     if (b >= Bpad) break;
-    const float g = b < B ? g_v[b] : 0.f;
+    const float g = gq[i];
     if (lane == 0) dbo += g;
     if (col_live) {
       const size_t off = swz64_offset(b, lane * 8, Bpad);
       float h[8], dz[8], hi[8], lo[8];
-      if (b < B) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(h_img + off)), __ldg(reinterpret_cast<const uint4*>(h_img + h_plane + off)), h);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = 0.f;
-      }
+      unpack8(qh[i], ql[i], h);      // rows >= B: zeros
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         dz[j] = g * wl[j] * (h[j] > 0.f ? 1.f : h[j] + 1.f);
@@ -131,6 +146,7 @@ __global__ void __launch_bounds__(256) value_head_bwd_kernel(const uint8_t* __re
       *reinterpret_cast<uint4*>(dz_img + dz_plane + off) =
           make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
     }
+  }
   }
   __shared__ float sh[8][2 * 256 + 1];
   if (col_live) {

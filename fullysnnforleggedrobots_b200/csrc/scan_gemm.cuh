@@ -76,17 +76,24 @@ __device__ __forceinline__ void store_planes16(uint8_t* img, size_t plane, int64
   *reinterpret_cast<uint4*>(img + plane + base + ((p0 ^ sw) << 4)) = l0;
   *reinterpret_cast<uint4*>(img + plane + base + (((p0 + 1) ^ sw) << 4)) = l1;
 }
-// inverse: hi + lo of 16 consecutive columns of one row
-__device__ __forceinline__ void load_planes16(const uint8_t* img, size_t plane, int64_t R, size_t r, int col0, float (&x)[16]) {
+// inverse, in two halves so that the loads can be issued well ahead of their use: the four 16-byte pieces (hi, lo) of 16
+// consecutive columns of one row ...
+struct Planes16 { uint4 h0, h1, l0, l1; };
+__device__ __forceinline__ Planes16 load_planes16_raw(const uint8_t* img, size_t plane, int64_t R, size_t r, int col0) {
   const size_t base = static_cast<size_t>(col0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
   const int p0 = (col0 & 63) >> 3;
   const int sw = static_cast<int>(r & 7);
-  const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(img + base + ((p0 ^ sw) << 4)));
-  const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(img + base + (((p0 + 1) ^ sw) << 4)));
-  const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + ((p0 ^ sw) << 4)));
-  const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + (((p0 + 1) ^ sw) << 4)));
-  const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-  const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+  Planes16 q;
+  q.h0 = __ldg(reinterpret_cast<const uint4*>(img + base + ((p0 ^ sw) << 4)));
+  q.h1 = __ldg(reinterpret_cast<const uint4*>(img + base + (((p0 + 1) ^ sw) << 4)));
+  q.l0 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + ((p0 ^ sw) << 4)));
+  q.l1 = __ldg(reinterpret_cast<const uint4*>(img + plane + base + (((p0 + 1) ^ sw) << 4)));
+  return q;
+}
+// ... and hi + lo as fp32
+__device__ __forceinline__ void planes16_to_f32(const Planes16& q, float (&x)[16]) {
+  const uint32_t hw[8] = {q.h0.x, q.h0.y, q.h0.z, q.h0.w, q.h1.x, q.h1.y, q.h1.z, q.h1.w};
+  const uint32_t lw[8] = {q.l0.x, q.l0.y, q.l0.z, q.l0.w, q.l1.x, q.l1.y, q.l1.z, q.l1.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
@@ -246,10 +253,17 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
       const int b = m * 128 + row;
       const bool valid = b < p.B;
       const uint32_t aset = it % nsets;
+      const int ng = ncw / 16;
+      const int g_first = static_cast<int>((half + gctr) & 1u);
+      // MLP_DX: the layer's stored ELU outputs do not depend on the accumulator: the first group's planes are requested
+      // before the wait for the MMAs, every further group's while the group before it is processed (the loads were the
+      // epilogue's largest stall: thread = batch row, every 16-byte piece in a different line)
+      Planes16 hq{};
+      const bool dx_planes = MODE == MODE_MLP_DX && p.f32_out == nullptr;
+      if (dx_planes && g_first < ng) hq = load_planes16_raw(p.h_img, p.h_plane, p.R, static_cast<size_t>(b), n0 + g_first * 16);
       SNN_TWAIT(&acc_full[aset], (it / nsets) & 1, 0);
       tc_fence_after_sync();
-      const int ng = ncw / 16;
-      for (int g = static_cast<int>((half + gctr) & 1u); g < ng; g += 2) {
+      for (int g = g_first; g < ng; g += 2) {
         const int col0 = n0 + g * 16;
         const uint32_t t_col = t_lane + aset * 256 + static_cast<uint32_t>(g * 16);
         if (MODE == MODE_MLP_FWD) {
@@ -267,10 +281,14 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
             }
             continue;
           }
+          // branch-free ELU (the per-element branch around expf compiled to sixteen divergent regions per group):
+          // exp of min(z, 0) is always evaluated, the select keeps z where it is positive — same values as torch's
+          // x > 0 ? x : exp(x) - 1
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float z = __uint_as_float(x[j]) + s_col[col0 + j];
-            h[j] = valid ? (z > 0.f ? z : expf(z) - 1.f) : 0.f;
+            const float e = expf(fminf(z, 0.f)) - 1.f;
+            h[j] = valid ? (z > 0.f ? z : e) : 0.f;
           }
           store_planes16(p.g_img, p.g_plane, p.R, static_cast<size_t>(b), col0, h);
         } else {
@@ -290,7 +308,8 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
           uint32_t x[16];
           tmem_ld16(t_col, x);
           float h[16];
-          load_planes16(p.h_img, p.h_plane, p.R, static_cast<size_t>(b), col0, h);
+          planes16_to_f32(hq, h);
+          if (g + 2 < ng) hq = load_planes16_raw(p.h_img, p.h_plane, p.R, static_cast<size_t>(b), col0 + 32);
           tmem_ld_wait();
           float dz[16];
 #pragma unroll
