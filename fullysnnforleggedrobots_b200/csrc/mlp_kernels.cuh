@@ -131,20 +131,22 @@ __global__ void __launch_bounds__(256) value_head_bwd_kernel(const uint8_t* __re
     if (lane == 0) dbo += g;
     if (col_live) {
       const size_t off = swz64_offset(b, lane * 8, Bpad);
-      float h[8], dz[8], hi[8], lo[8];
+      float h[8], dz[8];
       unpack8(qh[i], ql[i], h);      // rows >= B: zeros
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         dz[j] = g * wl[j] * (h[j] > 0.f ? 1.f : h[j] + 1.f);
         dw[j] += g * h[j];
         dbh[j] += dz[j];
-        hi[j] = bf16_round(dz[j]);
-        lo[j] = dz[j] - hi[j];
       }
-      *reinterpret_cast<uint4*>(dz_img + off) =
-          make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(dz_img + dz_plane + off) =
-          make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {      // hi = bf16(dz) two columns per cvt, lo = bf16(dz - hi)
+        hp[j] = pack_bf16x2(dz[2 * j], dz[2 * j + 1]);
+        lp[j] = pack_bf16x2(dz[2 * j] - __uint_as_float(hp[j] << 16), dz[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
+      }
+      *reinterpret_cast<uint4*>(dz_img + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(dz_img + dz_plane + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
   }
   }

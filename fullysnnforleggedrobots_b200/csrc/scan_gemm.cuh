@@ -61,16 +61,18 @@ constexpr int kScanMaxNP = 2048;   // floats of per-column smem scratch (MLP_FWD
 
 // 16 consecutive columns of one row -> hi/lo bf16 planes of a swz64 image (two 16-byte pieces per plane)
 __device__ __forceinline__ void store_planes16(uint8_t* img, size_t plane, int64_t R, size_t r, int col0, const float (&x)[16]) {
-  float hi[16], lo[16];
+  // packed conversions: hi = bf16(x) for two columns per cvt, lo = bf16(x - hi) (the same values as one cvt per element)
+  uint32_t hp[8], lp[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { hi[j] = bf16_round(x[j]); lo[j] = x[j] - hi[j]; }
+  for (int j = 0; j < 8; ++j) {
+    hp[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+    lp[j] = pack_bf16x2(x[2 * j] - __uint_as_float(hp[j] << 16), x[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
+  }
   const size_t base = static_cast<size_t>(col0 >> 6) * R * 128 + (r >> 3) * 1024 + (r & 7) * 128;
   const int p0 = (col0 & 63) >> 3;
   const int sw = static_cast<int>(r & 7);
-  const uint4 h0 = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-  const uint4 h1 = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]), pack_bf16x2(hi[14], hi[15]));
-  const uint4 l0 = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-  const uint4 l1 = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]), pack_bf16x2(lo[14], lo[15]));
+  const uint4 h0 = make_uint4(hp[0], hp[1], hp[2], hp[3]), h1 = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+  const uint4 l0 = make_uint4(lp[0], lp[1], lp[2], lp[3]), l1 = make_uint4(lp[4], lp[5], lp[6], lp[7]);
   *reinterpret_cast<uint4*>(img + base + ((p0 ^ sw) << 4)) = h0;
   *reinterpret_cast<uint4*>(img + base + (((p0 + 1) ^ sw) << 4)) = h1;
   *reinterpret_cast<uint4*>(img + plane + base + ((p0 ^ sw) << 4)) = l0;
