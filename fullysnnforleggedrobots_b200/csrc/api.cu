@@ -909,7 +909,7 @@ int mlp_backward(const SnnMlpDesc* d, const SnnMlpParams* prm, const void* packe
         q.h_img = at(trace, lo.tr_h); q.h_plane = lo.tr_h_plane;
         q.g_img = at(workspace, p.ws_dz[slot ^ 1]); q.g_plane = p.ws_dz_plane[slot ^ 1];
         q.db_part = dbpart_of(l - 1);
-        df.row(dbpart_of(l - 1), grid, lo.NP, lo.N, g->bias[l - 1]);
+        df.row(dbpart_of(l - 1), static_cast<int>(Bp / 32), lo.NP, lo.N, g->bias[l - 1]);
       } else {
         q.f32_out = d_x; q.f32_stride = dxs; q.f32_cols = p.in_dim;
       }

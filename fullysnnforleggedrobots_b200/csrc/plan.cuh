@@ -267,7 +267,9 @@ inline int make_mlp_plan(int in_dim, int num_hidden, const int32_t* hidden, int 
   }
   p.ws_partial_stride = static_cast<size_t>(round_up(static_cast<int64_t>(part), 1024));
   p.ws_partial = take(p.ws_partial_stride * p.LT);
-  p.ws_dbpart_stride = static_cast<size_t>(round_up(static_cast<int64_t>(296) * npmax * 4, 1024));
+  // bias-gradient partial rows: one per (128-row tile, lane quarter) of the dX epilogue = Bpad / 32
+  const int64_t db_rows = p.Bpad / 32 > 296 ? p.Bpad / 32 : 296;
+  p.ws_dbpart_stride = static_cast<size_t>(round_up(db_rows * npmax * 4, 1024));
   p.ws_dbpart = take(p.ws_dbpart_stride * p.LT);
   p.ws_small = take(static_cast<size_t>(p.Bpad / 64) * (2 * npmax + 8) * 4 + 1024);
   p.ws_bytes = off;

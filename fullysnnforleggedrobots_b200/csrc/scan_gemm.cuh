@@ -41,7 +41,7 @@ struct ScanGemmParams {
   const float* bias;        // MLP_FWD: [NPout]
   uint8_t* g_img;           // output: 2 planes of swz64 image [NPout/64][R rows]
   size_t g_plane;
-  float* db_part;           // MLP_DX: [gridDim.x][NPout]
+  float* db_part;           // MLP_DX: [4 * Bpad / 128][NPout]: one row per (row tile, lane quarter)
   // MLP_FWD: writes ELU(acc + bias) as hi/lo planes into g_img.  MLP_DX: reads the layer's ELU output planes
   const uint8_t* h_img;     // 2 planes of swz64 image [NPout/64][R rows]
   size_t h_plane;
@@ -317,8 +317,11 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 #pragma unroll
           for (int j = 0; j < 16; ++j) dz[j] = valid ? __uint_as_float(x[j]) * (h[j] > 0.f ? 1.f : h[j] + 1.f) : 0.f;
           store_planes16(p.g_img, p.g_plane, p.R, static_cast<size_t>(b), col0, dz);
+          // bias gradient: the column sums of this warp's 32 rows go to their own partial row (row tile, lane quarter) —
+          // every (row, column) of db_part is written exactly once and the deferred row reduction sums them in a fixed
+          // order (r2: shared-memory float atomics before, the one source of run-to-run differences of an update)
           const float tot = warp_transpose_reduce16(dz, lane);
-          if ((lane & 1) == 0) atomicAdd(&s_col[col0 + (lane >> 1)], tot);
+          if ((lane & 1) == 0) p.db_part[(static_cast<size_t>(m) * 4 + q) * p.NPout + col0 + (lane >> 1)] = tot;
         }
       }
       gctr += static_cast<uint32_t>(ncw / 16);
@@ -337,9 +340,6 @@ __global__ void __launch_bounds__(ScanCfg<MODE>::THREADS, 1) scan_gemm_kernel(co
 #endif
   tc_fence_before_sync();
   __syncthreads();
-  if (MODE == MODE_MLP_DX && p.db_part != nullptr) {
-    for (int i = tid; i < p.NPout; i += blockDim.x) p.db_part[static_cast<size_t>(blockIdx.x) * p.NPout + i] = s_col[i];
-  }
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);

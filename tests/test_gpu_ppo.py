@@ -405,3 +405,21 @@ def test_fused_steps_overwrite_every_gradient_they_use(graph):
     for k in res[0][1]:
         assert torch.isfinite(res[1][1][k]).all(), k
         assert torch.equal(res[0][1][k], res[1][1][k]), k
+
+
+def test_update_is_bitwise_reproducible():
+    """Two updates from identical states give bit-identical parameters: every reduction of the fused step has a fixed
+    order (per-tile partial rows + split-K tiles of the actor, per-(row tile, lane quarter) partial rows of the critic's
+    bias gradients — shared-memory float atomics until r2 —, block partials of the PPO head and the gradient norm)."""
+    pc, g, ro = PPO_CASE, load(), make_ppo_rollout(PPO_CASE)
+    res = []
+    for _ in range(2):
+        ac, alg = make_alg(pc)
+        fill_storage(alg, pc, g, ro)
+        alg.compute_returns(ro["last_obs"].cuda())
+        torch.manual_seed(11)
+        out = alg.update()
+        res.append((out, {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}))
+    assert res[0][0] == res[1][0]
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
