@@ -586,8 +586,17 @@ __global__ void __launch_bounds__(1024) multi_reduce_kernel(const ReduceJobs job
     if (k >= jb.K || n >= jb.N) return;
     const int tile = (n >> 7) * jb.n_tiles + (k >> 8);
     const float* src = jb.partial + (static_cast<size_t>(tile) * jb.splits * 128 + (n & 127)) * 256 + (k & 255);
+    // eight independent loads in flight per thread, summed in split order (fixed: bitwise reproducible)
     float acc = 0.f;
-    for (int s = 0; s < jb.splits; ++s) acc += src[static_cast<size_t>(s) * 128 * 256];
+    int sp = 0;
+    for (; sp + 8 <= jb.splits; sp += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[static_cast<size_t>(sp + u) * 128 * 256];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; sp < jb.splits; ++sp) acc += src[static_cast<size_t>(sp) * 128 * 256];
     jb.dW[static_cast<size_t>(n) * jb.K + k] = acc;
     return;
   }
