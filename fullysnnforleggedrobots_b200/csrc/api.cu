@@ -533,14 +533,16 @@ int backward_impl(const SnnDesc* d, const SnnParams* prm, const void* packed, co
       g_mu = head->g_mu_out;
     }
     {
+      // n / P as a multiply-shift: exact while n (P - 1) < 2^20 (n < NP <= 2048)
+      const uint32_t p_magic = static_cast<int64_t>(lp.NP) * (p.Pd - 1) < (1 << 20) ? ((1u << 20) + p.Pd - 1) / p.Pd : 0u;
       { ProfScope prof__(CAT_OTHER, 0.0, st);
       const dim3 grd(nrows, lp.NP / 64);
       if (p.T == 5)
         top_scan_rows_kernel<5><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small, p_magic);
       else
         top_scan_rows_kernel<0><<<grd, 32 * kTopRowsSPB, 0, st>>>(g_mu, mu, d->dec_tanh, prm->dec_w, volt, Bi, tg, p.A, p.Pd, lp.NP, p.T,
-                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small);
+                                                    at(workspace, p.ws_g[top]), p.ws_g_plane[top], dbpart_of(top), small, p_magic);
       }
       LAUNCH_CHECK("top_scan_rows_kernel");
     }

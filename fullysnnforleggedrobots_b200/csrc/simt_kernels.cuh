@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
                                                            const uint16_t* __restrict__ volt, int B, TileGeom tg, int A,
                                                            int P, int NP, int T, uint8_t* __restrict__ g_img,
                                                            size_t g_plane, float* __restrict__ db_part /* [gridDim.x][NP] */,
-                                                           float* __restrict__ dec_part /* [gridDim.x][2][NP] */) {
+                                                           float* __restrict__ dec_part /* [gridDim.x][2][NP] */,
+                                                           uint32_t p_magic /* ceil(2^20 / P), or 0: divide */) {
   constexpr int SPB = kTopRowsSPB;
   __shared__ float s_red[SPB][6][32];
   __shared__ float s_rate[kMaxT + 1];        // count / T for every possible spike count (the kernel is issue-bound)
@@ -295,20 +296,23 @@ __global__ void __launch_bounds__(32 * kTopRowsSPB) top_scan_rows_kernel(const f
   const int b = static_cast<int>(gridDim.x - 1 - blockIdx.x) * SPB + w;      // its sample (< Bcap)
   const int tile = b / tg.Bt, bl = b - tile * tg.Bt;
   const int nt = TT > 0 ? TT : T;
-  const float Tf = static_cast<float>(nt);
+  // the kernel is bound by instruction issue: no IEEE division per neuron (G w / T as a reciprocal product, within 1 ulp)
+  // and n / P by a multiply-shift (exact for n < 2^20 / P: api.cu passes the magic only then)
+  const float inv_T = 1.f / static_cast<float>(nt);
   const bool live = b < B;
   const bool l0 = live && n0 < A * P, l1 = live && n0 + 1 < A * P;
-  const int a0 = l0 ? n0 / P : 0, a1 = l1 ? (n0 + 1) / P : 0;
+  const int a0 = l0 ? (p_magic ? static_cast<int>((static_cast<uint32_t>(n0) * p_magic) >> 20) : n0 / P) : 0;
+  const int a1 = l1 ? (p_magic ? static_cast<int>((static_cast<uint32_t>(n0 + 1) * p_magic) >> 20) : (n0 + 1) / P) : 0;
   float G0 = 0.f, G1 = 0.f, gup0 = 0.f, gup1 = 0.f;
   if (l0) {
     G0 = g_mu[static_cast<size_t>(b) * A + a0];
     if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a0]; G0 = G0 * (1.f - m * m); }
-    gup0 = __fdiv_rn(G0 * dec_w[n0], Tf);
+    gup0 = G0 * dec_w[n0] * inv_T;
   }
   if (l1) {
     G1 = g_mu[static_cast<size_t>(b) * A + a1];
     if (dec_tanh) { const float m = mu[static_cast<size_t>(b) * A + a1]; G1 = G1 * (1.f - m * m); }
-    gup1 = __fdiv_rn(G1 * dec_w[n0 + 1], Tf);
+    gup1 = G1 * dec_w[n0 + 1] * inv_T;
   }
   const size_t r0 = static_cast<size_t>(tile) * tg.CT + bl;    // sample-step (0, b); step t is r0 + t * Bt
   // voltage codes (umma.cuh: volt_code2) [NP/32][Rt/8][32 neurons][8 sample-steps]; Bt % 16 == 0, so every timestep's
