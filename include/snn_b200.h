@@ -108,7 +108,8 @@ int snn_fwd_act_preferred(const SnnDesc* d, int64_t B);
 int snn_fwd_act(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs, int64_t B, float* mu,
                 const float* noise, const float* log_std, float* actions, float* logp, float* sigma, void* stream);
 
-/* Same forward with the traces BPTT needs (what autograd would save: AMP:154-167, 216-232). */
+/* Same forward with the traces BPTT needs (what autograd would save: AMP:154-167, 216-232).  mu may be NULL: the decoder
+ * pass is skipped (the fused PPO step decodes inside snn_bwd_ppo_top). */
 int snn_fwd_train(const SnnDesc* d, const SnnParams* p, const void* packed, const float* obs,
                   int64_t B, float* mu, void* trace, size_t trace_bytes,
                   void* workspace, size_t workspace_bytes, void* stream);

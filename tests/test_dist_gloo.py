@@ -32,8 +32,12 @@ def _worker(rank, world, port, out_dir):
     red.allreduce_gradients(model)
     adv_all = torch.randn(4, 12, generator=g)
     adv = normalize_advantages_global(adv_all[:, lo:hi].contiguous(), red.allreduce_sum)
+    # the peer-memory gradient sum is a CUDA / NCCL feature: on a CPU (gloo) job every rank declines it alike and the
+    # all-reduce stays a torch.distributed call
+    p2p = red.enable_p2p(1000)
     torch.save({"params": [p.detach().clone() for p in model.parameters()],
-                "grads": [p.grad.clone() for p in model.parameters()], "adv": adv, "range": (lo, hi)},
+                "grads": [p.grad.clone() for p in model.parameters()], "adv": adv, "range": (lo, hi),
+                "p2p": (p2p, red.p2p is None, red.p2p_note)},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
@@ -65,6 +69,9 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     got = torch.cat([r[0]["adv"], r[1]["adv"]], dim=1)
     assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
     assert r[0]["range"] == (0, 6) and r[1]["range"] == (6, 12)
+    for i in range(world):
+        ok, none, note = r[i]["p2p"]
+        assert ok is False and none and "disabled" in note
 
 
 def test_shard_range_covers_everything():
