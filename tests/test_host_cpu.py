@@ -88,3 +88,56 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_voltage_code_format_and_trace_decoder_on_the_host():
+    """The 16-bit voltage trace (csrc/umma.cuh: volt_code2) restated in numpy: k = ceil(65534 v) saturated to
+    [0, 65535] — spike flag exact around 0.5, value inside the surrogate window to 2^-17 — and `engine.unpack_trace`
+    decoding a trace buffer laid out by the plan (no GPU: the layout query is host code)."""
+    import ctypes as C
+    import numpy as np
+    from fullysnnforleggedrobots_b200 import _lib
+    from fullysnnforleggedrobots_b200.engine import SnnEngine
+
+    def code(v):                      # exact product in float64 (an fp32 x 17-bit constant fits), rounded up, saturated
+        v = np.asarray(v, dtype=np.float32)
+        hi = np.float32(65535.0 / 65534.0)
+        return np.ceil(np.clip(v, 0.0, hi).astype(np.float64) * 65534.0).astype(np.int64)
+
+    half = np.float32(0.5)
+    near = np.array([np.nextafter(half, np.float32(0)), half, np.nextafter(half, np.float32(1))], dtype=np.float32)
+    assert list(code(near) > 32767) == [False, False, True]                      # spike flag <=> v > 0.5, to the last ulp
+    assert list(code(np.float32([-3.0, 0.0, 1e-30, 1.0, 1.5, 77.0]))) == [0, 0, 1, 65534, 65535, 65535]
+    v = np.random.default_rng(0).uniform(1e-6, 1 - 1e-6, 200000).astype(np.float32)
+    k = code(v)
+    assert k.min() >= 1 and k.max() <= 65534
+    assert np.abs((k - 0.5) / 65534.0 - v.astype(np.float64)).max() <= 2.0 ** -17 + 1e-9
+
+    eng = SnnEngine(3, 2, 4, 4, [128], spike_ts=5)
+    B = 20
+    arr = (C.c_int64 * (8 + 4 * _lib.SNN_MAX_LAYERS))()
+    _lib.check(_lib.lib().snn_debug_trace_layout(C.byref(eng.desc), B, arr, len(arr)), "trace layout")
+    Lc, T, Bt, CT, ntile, Rt = (int(arr[i]) for i in range(6))
+    nbytes = int(_lib.lib().snn_trace_bytes(C.byref(eng.desc), B))
+    raw = torch.zeros(nbytes, dtype=torch.uint8)
+    rng = np.random.default_rng(1)
+    want = []
+    for l in range(Lc):
+        NP, voff = int(arr[8 + 4 * l]), int(arr[11 + 4 * l])
+        volt = rng.uniform(-0.5, 1.5, size=(T, B, NP)).astype(np.float32)
+        codes = np.zeros((NP // 32, Rt // 8, 32, 8), dtype=np.uint16)
+        for t in range(T):
+            for b in range(B):
+                r = (b // Bt) * CT + t * Bt + b % Bt
+                codes[:, r // 8, :, r % 8] = code(volt[t, b]).reshape(NP // 32, 32).astype(np.uint16)
+        raw[voff: voff + Rt * NP * 2] = torch.from_numpy(codes.reshape(-1).view(np.uint8).copy())
+        want.append(volt)
+    tr = eng.unpack_trace(raw, B)
+    for l in range(Lc):
+        n = eng.dims[l + 1]
+        vw = torch.from_numpy(want[l][:, :, :n])
+        win = (vw > 0) & (vw < 1)
+        assert torch.equal(tr["volt_code"][l] > 32767, vw > 0.5)
+        assert (tr["volt"][l][win] - vw[win]).abs().max() <= 2.0 ** -17 + 1e-7
+        assert torch.equal(tr["volt"][l][vw <= 0], torch.zeros_like(vw[vw <= 0]))
+        assert torch.equal(tr["volt"][l][vw > 1], torch.ones_like(vw[vw > 1]))
