@@ -435,6 +435,12 @@ __global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadParams p
     s_ivar[a] = 1.f / (sg * sg);
     s_lsig[a] = logf(sg);
   }
+  // requested now, used after the decoder: the kernel is a chain of dependent round trips (one block = one wave)
+  float adv_b = 0.f, olp_b = 0.f;
+  if (threadIdx.x < SPB && b0 + threadIdx.x < p.B) {
+    adv_b = __ldg(p.adv + b0 + threadIdx.x);
+    olp_b = __ldg(p.old_logp + b0 + threadIdx.x);
+  }
   __syncthreads();
   // ---- decoder + per-action Normal terms, thread = item (sample-major: the [B, A] fields are read as one contiguous run)
   for (int item = threadIdx.x; item < nitems; item += 256) {
@@ -442,6 +448,8 @@ __global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadParams p
     const int b = b0 + sm;
     float lp = 0.f, kl = 0.f, dd = 0.f;
     if (b < p.B) {
+      const size_t gi0 = static_cast<size_t>(b) * A + a;
+      const float act_i = __ldg(p.actions + gi0), osg_i = __ldg(p.old_sigma + gi0), omu_i = __ldg(p.old_mu + gi0);
       const int tile = b / tg.Bt;
       const size_t r0 = static_cast<size_t>(tile) * tg.CT + (b - tile * tg.Bt);      // sample-step (0, b); step t is r0 + t * Bt
       const int n0 = a * P;
@@ -477,9 +485,9 @@ __global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadParams p
       p.mu[gi] = m;
       // Normal(mu, sigma) terms of this action (ppo_head_kernel's formulas)
       const float sg = s_sig[a], iv = s_ivar[a];
-      const float d = __ldg(p.actions + gi) - m;
+      const float d = act_i - m;
       lp = -(d * d) * 0.5f * iv - s_lsig[a] - 0.91893853320467274178f;
-      const float os = __ldg(p.old_sigma + gi), dm = __ldg(p.old_mu + gi) - m;
+      const float os = osg_i, dm = omu_i - m;
       kl = logf(sg / os + 1.e-5f) + (os * os + dm * dm) * 0.5f * iv - 0.5f;
       dd = d;
     }
@@ -494,8 +502,8 @@ __global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadParams p
     float logp = 0.f, kl = 0.f, sur = 0.f, g_logp = 0.f;
     if (b < p.B) {
       for (int a = 0; a < A; ++a) { logp += s_lp[threadIdx.x * A + a]; kl += s_kl[threadIdx.x * A + a]; }
-      const float ad = __ldg(p.adv + b);
-      const float ratio = expf(logp - __ldg(p.old_logp + b));
+      const float ad = adv_b;
+      const float ratio = expf(logp - olp_b);
       const float s1 = -ad * ratio;
       const float s2 = -ad * fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
       sur = fmaxf(s1, s2);
